@@ -1,0 +1,399 @@
+"""CPU oracle for the EncoderMap training hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file restates, op for op and in the reference's own order of operations, the
+algorithms on the hot path of AG-Peter/encodermap in torch-CPU.
+It exists so that the CUDA kernels can be checked; it is never the product:
+
+  * only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+    ``--impl reference`` legs of ``bench.py`` may import it;
+  * nothing under ``encodermap_b200/`` imports it, and the product path fails loudly
+    when the CUDA library is missing.
+
+Parity pin status
+-----------------
+The reference's arithmetic lives in TensorFlow (``tensorflow>=2.15``, un-pinned,
+``setup.py:48`` of the reference), which is not installed in this image, so the reference
+itself cannot be run.  The restatement is pinned two ways (see ``tests/test_oracle_*``):
+
+  1. against every known-answer vector the reference's own tests hold for this path
+     (``tests/test_pairwise_distances.py``, ``tests/test_losses.py``,
+     ``tests/test_dihedral_to_cartesian.py``, ``tests/test_backmapping_em1_em2.py``);
+  2. against golden outputs produced by executing the reference's *own function
+     bodies* (extracted from ``/root/reference`` with ``ast``) on a numpy-backed
+     stand-in for the ``tf`` namespace -- ``tools/gen_golden.py`` -> ``tests/golden/*.npz``.
+
+What neither covers -- TensorFlow's own kernels and its autodiff tie rules -- stays
+**parity unpinned**: every gradient, and the float32 rounding of Eigen's pow/sqrt/GEMM.
+Gradients here come from torch autograd in float64 over the restated forward.
+
+All functions take/return torch tensors; ``dtype`` follows the inputs (the reference
+computes in float32; float64 evaluation of the same algorithm is the parity target for
+the kernels).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+pi = math.pi
+
+
+def _t(x, dtype=None) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x if dtype is None else x.to(dtype)
+    arr = np.asarray(x)
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t if dtype is None else t.to(dtype)
+
+
+# ----------------------------------------------------------------------------------------
+# encodermap/misc/distances.py
+# ----------------------------------------------------------------------------------------
+
+
+def sigmoid(sig: float, a: float, b: float) -> Callable:
+    """Sketch-map sigmoid closure.  Reference: encodermap/misc/distances.py:66-88
+    (TF1 twin encodermap_tf1/misc.py:115-124):  1 - (1 + (2^(a/b) - 1) (r/sig)^a)^(-b/a)."""
+
+    def func(r):
+        return 1 - (1 + (2 ** (a / b) - 1) * (r / sig) ** a) ** (-b / a)
+
+    return func
+
+
+def periodic_distance(a, b, periodicity: float = 2 * pi):
+    """Minimum-image distance.  Reference: encodermap/misc/distances.py:113-141."""
+    a, b = _t(a), _t(b)
+    d = torch.abs(b - a)
+    return torch.minimum(d, periodicity - d)
+
+
+def pairwise_dist_periodic(positions, periodicity: float):
+    """All-pairs periodic distance through the (N,N,D) broadcast tensor.
+    Reference: encodermap/misc/distances.py:144-176 (eps 1e-12 on zero components and on
+    the result)."""
+    positions = _t(positions)
+    assert positions.dim() == 2
+    vecs = periodic_distance(positions[:, None, :], positions[None, :, :], periodicity)
+    mask = (vecs == 0.0).to(torch.float32).to(vecs.dtype)
+    vecs = vecs + mask * 1e-12
+    return torch.sqrt(torch.sum(torch.square(vecs), dim=2)) + 1.0e-12
+
+
+def pairwise_dist(positions, squared: bool = False, flat: bool = False):
+    """Gram-form Euclidean distance matrix.  Reference: encodermap/misc/distances.py:179-255
+    (TF1 twin encodermap_tf1/misc.py:143-188).  Rank-2 input gains a leading batch axis."""
+    positions = _t(positions)
+    if positions.dim() == 2:
+        positions = positions[None]
+    gram = torch.matmul(positions, positions.transpose(1, 2))
+    sq = torch.diagonal(gram, dim1=1, dim2=2)
+    dist = sq[:, None, :] - 2.0 * gram + sq[:, :, None]
+    dist = torch.clamp_min(dist, 0.0)
+    if flat:
+        n = positions.shape[1]
+        keep = np.ones((n, n), dtype=bool)
+        keep[np.tril_indices(n)] = False
+        dist = dist[:, torch.from_numpy(keep)]
+    if not squared:
+        mask = (dist == 0.0).to(dist.dtype)
+        dist = dist + mask * 1e-16
+        dist = torch.sqrt(dist)
+        dist = dist * (1.0 - mask)
+    return dist
+
+
+# ----------------------------------------------------------------------------------------
+# encodermap/loss_functions/loss_functions.py
+# ----------------------------------------------------------------------------------------
+
+DEFAULT_SIG = (4.5, 12, 6, 1, 2, 6)  # encodermap/parameters/parameters.py:620
+
+
+def sigmoid_loss(periodicity: float = 2 * pi, dist_sig_parameters: Sequence[float] = DEFAULT_SIG) -> Callable:
+    """Reference: encodermap/loss_functions/loss_functions.py:301-369 (TF1 twin
+    ``distance_cost`` encodermap_tf1/misc.py:88-112).  Mean over all N^2 ordered pairs."""
+    sig_h = sigmoid(*dist_sig_parameters[:3])
+    sig_l = sigmoid(*dist_sig_parameters[3:])
+
+    def sigmoid_loss_func(y_true, y_pred):
+        r_h, r_l = _t(y_true), _t(y_pred)
+        if periodicity == float("inf"):
+            dist_h = pairwise_dist(r_h)
+        else:
+            dist_h = pairwise_dist_periodic(r_h, periodicity)
+        dist_l = pairwise_dist(r_l)
+        return torch.mean(torch.square(sig_h(dist_h) - sig_l(dist_l)))
+
+    return sigmoid_loss_func
+
+
+def distance_loss_value(y_true, latent, periodicity=2 * pi, dist_sig_parameters=DEFAULT_SIG,
+                        distance_cost_scale: Optional[float] = 500.0):
+    """The arithmetic of ``distance_loss_func`` once the encoder output is known.
+    Reference: encodermap/loss_functions/loss_functions.py:266-296 (tuple inputs are
+    concatenated over their first three members, scale None => 0)."""
+    if isinstance(y_true, (tuple, list)):
+        y_true = torch.cat([_t(y) for y in y_true[:3]], dim=1)
+    if distance_cost_scale is None:
+        return torch.zeros((), dtype=_t(latent).dtype)
+    return sigmoid_loss(periodicity, dist_sig_parameters)(y_true, latent) * distance_cost_scale
+
+
+def cartesian_distance_loss_value(y_true, latent, cartesian_dist_sig_parameters=DEFAULT_SIG,
+                                  cartesian_distance_cost_scale: Optional[float] = 1.0):
+    """Reference: encodermap/loss_functions/loss_functions.py:917-942 (periodicity forced
+    to inf, second sigmoid parameter set)."""
+    if cartesian_distance_cost_scale is None:
+        return torch.zeros((), dtype=_t(latent).dtype)
+    f = sigmoid_loss(float("inf"), cartesian_dist_sig_parameters)
+    return f(y_true, latent) * cartesian_distance_cost_scale
+
+
+# ----------------------------------------------------------------------------------------
+# encodermap/models/layers.py
+# ----------------------------------------------------------------------------------------
+
+
+def periodic_input(x, periodicity: float = 2 * pi):
+    """Reference: encodermap/models/layers.py:204-215 (twin models/models.py:3345-3350)."""
+    x = _t(x)
+    if periodicity != 2 * pi:
+        x = x / periodicity * 2 * pi
+    return torch.cat([torch.sin(x), torch.cos(x)], dim=1)
+
+
+def pairwise_distances_layer(x, start=None, stop=None, step=None):
+    """Reference: encodermap/models/layers.py:1252-1267 (no-sidechain branch)."""
+    x = _t(x)
+    return pairwise_dist(x[:, start:stop:step], flat=True)
+
+
+# ----------------------------------------------------------------------------------------
+# encodermap/encodermap_tf1/backmapping.py and encodermap/misc/backmapping.py
+# ----------------------------------------------------------------------------------------
+
+
+def straight_tetrahedral_chain(n_atoms=None, bond_lengths=None) -> np.ndarray:
+    """Reference: encodermap/encodermap_tf1/backmapping.py:71-94 (float32 output)."""
+    dx = math.cos(70.63 / 180 * pi)
+    dy = math.sin(70.63 / 180 * pi)
+    if n_atoms and not bond_lengths:
+        xyz = np.zeros((n_atoms, 3), dtype=np.float32)
+        idx = np.repeat(np.arange(int(n_atoms / 2) + 1), 2)
+        xyz[:, 0] = idx[1 : n_atoms + 1] + dx * idx[0:n_atoms]
+        xyz[:, 1] = dy * idx[0:n_atoms]
+    elif (bond_lengths and not n_atoms) or n_atoms == len(bond_lengths) + 1:
+        n_bonds = len(bond_lengths)
+        n_atoms = n_atoms or n_bonds + 1
+        dxs = bond_lengths * np.tile([1, dx], int(n_atoms / 2))[:n_bonds]
+        dys = bond_lengths * np.tile([0, dy], int(n_atoms / 2))[:n_bonds]
+        xyz = np.zeros((n_atoms, 3), dtype=np.float32)
+        xyz[1:, 0] = np.cumsum(dxs)
+        xyz[1:, 1] = np.cumsum(dys)
+    else:
+        raise ValueError("input not compatible")
+    return xyz
+
+
+def chain_in_plane(lengths, angles):
+    """Planar zig-zag chain.  Reference: encodermap/encodermap_tf1/backmapping.py:97-119.
+    ``lengths`` is (1, n-1) (broadcast over the batch) or (B, n-1); ``angles`` (B, n-2)."""
+    lengths, angles = _t(lengths), _t(angles)
+    batch = angles.shape[0]
+    prev = torch.zeros(batch, dtype=angles.dtype)
+    xs = [torch.zeros(batch, dtype=angles.dtype)]
+    ys = [torch.zeros(batch, dtype=angles.dtype)]
+    sign = 1
+    i = -1
+    for i in range(angles.shape[1]):
+        xs.append(xs[-1] + lengths[:, i] * torch.cos(prev))
+        ys.append(ys[-1] + lengths[:, i] * torch.sin(prev) * sign)
+        prev = pi - angles[:, i] - prev
+        sign *= -1
+    xs.append(xs[-1] + lengths[:, i + 1] * torch.cos(prev))
+    ys.append(ys[-1] + lengths[:, i + 1] * torch.sin(prev) * sign)
+    xs = torch.stack(xs, dim=1)
+    ys = torch.stack(ys, dim=1)
+    return torch.stack([xs, ys, torch.zeros_like(xs)], dim=2)
+
+
+def rotation_matrix(axis_unit_vec, angle):
+    """Rodrigues matrix, applied to ROW vectors on the right.
+    Reference: encodermap/misc/backmapping.py:1950-1968 (twin encodermap_tf1/misc.py:286-304)."""
+    u, angle = _t(axis_unit_vec), _t(angle)
+    ang = angle[:, None, None]
+    eye = torch.eye(3, dtype=u.dtype)[None]
+    z = torch.zeros(u.shape[0], dtype=u.dtype)
+    cross = torch.stack(
+        [
+            torch.stack([z, -u[:, 2], u[:, 1]], dim=0),
+            torch.stack([u[:, 2], z, -u[:, 0]], dim=0),
+            torch.stack([-u[:, 1], u[:, 0], z], dim=0),
+        ],
+        dim=0,
+    ).permute(2, 0, 1)
+    r = torch.cos(ang) * eye
+    r = r + torch.sin(ang) * cross
+    uu = u[:, :, None]
+    r = r + (1 - torch.cos(ang)) * torch.matmul(uu, uu.transpose(1, 2))
+    return r
+
+
+def dihedral_to_cartesian_one_way(dihedrals, cartesian, n: Optional[int] = None):
+    """One tail of the chain.  Reference: encodermap/misc/backmapping.py:1873-1912 (explicit
+    sqrt-of-sum norm; TF1 twin encodermap_tf1/backmapping.py:198-214 uses tf.norm)."""
+    dihedrals, cartesian = _t(dihedrals), _t(cartesian)
+    if n is None:
+        n = dihedrals.shape[-1]
+    dihedrals = -dihedrals
+    rotated = cartesian[:, 1:]
+    collected = [cartesian[:, :1]]
+    for i in range(n):
+        collected.append(rotated[:, 0:1])
+        axis = rotated[:, 1] - rotated[:, 0]
+        axis = axis / torch.sqrt(torch.sum(torch.square(axis), dim=1))[:, None]
+        offset = rotated[:, 1:2]
+        rotated = offset + torch.matmul(rotated[:, 1:] - offset, rotation_matrix(axis, dihedrals[:, i]))
+    collected.append(rotated)
+    return torch.cat(collected, dim=1)
+
+
+def split_and_reverse_dihedrals(x):
+    """Reference: encodermap/misc/backmapping.py:179-214."""
+    x = _t(x)
+    middle = int(int(x.shape[1]) / 2)
+    if x.shape[1] % 2 == 0:
+        return torch.flip(x[:, :middle], dims=[1]), x[:, middle:]
+    return torch.flip(x[:, : middle + 1], dims=[1]), x[:, middle + 1 :]
+
+
+def split_and_reverse_cartesians(x):
+    """Reference: encodermap/misc/backmapping.py:217-256."""
+    x = _t(x)
+    split = int(int(x.shape[1]) / 2)
+    return torch.flip(x[:, : split + 2], dims=[1]), x[:, split - 1 :]
+
+
+def split_indices_tf1(n_atoms: int):
+    """The TF1 slicing the reference's split test pins the TF2 helpers against.
+    Reference: encodermap/encodermap_tf1/backmapping.py:175-181 and
+    tests/test_backmapping_em1_em2.py:2130-2137.  Returns numpy index arrays
+    (left_atoms, left_dihedrals, right_atoms, right_dihedrals)."""
+    atoms = np.arange(n_atoms)
+    dih = np.arange(n_atoms - 3)
+    split = int(int(n_atoms) / 2)
+    return (atoms[split + 1 :: -1], dih[split - 2 :: -1], atoms[split - 1 :], dih[split - 1 :])
+
+
+def dihedrals_to_cartesian_layers(dihedrals, cartesians, left_iteration_counter: int, right_iteration_counter: int):
+    """Two-sided build.  Reference: encodermap/misc/backmapping.py:259-309."""
+    dihedrals, cartesians = _t(dihedrals), _t(cartesians)
+    if cartesians.dim() == 2:
+        cartesians = cartesians[None].expand(dihedrals.shape[0], -1, -1)
+    c_left, c_right = split_and_reverse_cartesians(cartesians)
+    d_left, d_right = split_and_reverse_dihedrals(dihedrals)
+    new_left = dihedral_to_cartesian_one_way(d_left, c_left, left_iteration_counter)
+    new_right = dihedral_to_cartesian_one_way(d_right, c_right, right_iteration_counter)
+    return torch.cat([torch.flip(new_left, dims=[1]), new_right[:, 3:]], dim=1)
+
+
+def dihedrals_to_cartesian_tf1(dihedrals, cartesian):
+    """TF1 twin with its own slicing.  Reference: encodermap/encodermap_tf1/backmapping.py:164-195."""
+    dihedrals, cartesian = _t(dihedrals), _t(cartesian)
+    if cartesian.dim() == 2:
+        cartesian = cartesian[None].expand(dihedrals.shape[0], -1, -1)
+    n_atoms = cartesian.shape[1]
+    la, ld, ra, rd = split_indices_tf1(n_atoms)
+    c_right = cartesian[:, torch.from_numpy(ra.copy())]
+    d_right = dihedrals[:, torch.from_numpy(rd.copy())]
+    c_left = cartesian[:, torch.from_numpy(la.copy())]
+    d_left = dihedrals[:, torch.from_numpy(ld.copy())]
+    new_right = dihedral_to_cartesian_one_way(d_right, c_right)
+    new_left = dihedral_to_cartesian_one_way(d_left, c_left)
+    return torch.cat([torch.flip(new_left, dims=[1]), new_right[:, 3:]], dim=1)
+
+
+def split_counts(n_atoms: int) -> Tuple[int, int]:
+    """(left_split, right_split) loop counts.  Reference: encodermap/models/models.py:661-671."""
+    return n_atoms // 2 - 1, (n_atoms - 3) // 2
+
+
+def back_map_layer(distances, angles, dihedrals, left_split: Optional[int] = None, right_split: Optional[int] = None):
+    """Reference: encodermap/models/layers.py:957-986: batch-mean bond lengths ->
+    chain_in_plane -> dihedrals + pi -> two-sided build."""
+    distances, angles, dihedrals = _t(distances), _t(angles), _t(dihedrals)
+    n_atoms = distances.shape[1] + 1
+    if left_split is None or right_split is None:
+        left_split, right_split = split_counts(n_atoms)
+    lengths = torch.mean(distances, dim=0)[None]
+    chain = chain_in_plane(lengths, angles)
+    return dihedrals_to_cartesian_layers(dihedrals + pi, chain, left_split, right_split)
+
+
+# ----------------------------------------------------------------------------------------
+# helpers used by the tests and the CPU baseline (not reference functions)
+# ----------------------------------------------------------------------------------------
+
+
+def sigmoid_loss_and_grad(y_true, y_pred, periodicity=2 * pi, sig=DEFAULT_SIG, dtype=torch.float64):
+    """Loss and dL/d(y_pred) by autograd over the restated forward (the reference relies on
+    tf.GradientTape; only the latent side needs a gradient)."""
+    h = _t(y_true).to(dtype)
+    z = _t(y_pred).to(dtype).clone().requires_grad_(True)
+    loss = sigmoid_loss(periodicity, sig)(h, z)
+    (g,) = torch.autograd.grad(loss, z)
+    return loss.detach(), g
+
+
+def sigmoid_loss_tiles(y_true, y_pred, periodicity, sig, tile_begin: int, tile_end: int, tile: int = 128,
+                       dtype=torch.float64):
+    """Partial loss / gradient over a slice of the upper-triangular tile list (row-major over
+    tile rows), normalised by the full N^2 -- the quantity one rank of the sharded evaluation
+    produces.  Sum over a partition of the tile list == full result."""
+    h = _t(y_true).to(dtype)
+    z = _t(y_pred).to(dtype)
+    n = h.shape[0]
+    nt = (n + tile - 1) // tile
+    sig_h, sig_l = sigmoid(*sig[:3]), sigmoid(*sig[3:])
+    loss = torch.zeros((), dtype=dtype)
+    grad = torch.zeros_like(z)
+    t = 0
+    for ti in range(nt):
+        for tj in range(ti, nt):
+            if tile_begin <= t < tile_end:
+                ri = slice(ti * tile, min(n, (ti + 1) * tile))
+                rj = slice(tj * tile, min(n, (tj + 1) * tile))
+                zi = z[ri].clone().requires_grad_(True)
+                zj = z[rj].clone().requires_grad_(True)
+                if periodicity == float("inf"):
+                    dh = torch.sqrt(torch.sum((h[ri][:, None] - h[rj][None]) ** 2, dim=2))
+                else:
+                    dh = torch.sqrt(torch.sum(periodic_distance(h[ri][:, None], h[rj][None], periodicity) ** 2, dim=2))
+                d2 = torch.sum((zi[:, None] - zj[None]) ** 2, dim=2)
+                m = (d2 == 0).to(dtype)
+                dl = torch.sqrt(d2 + m) * (1 - m)
+                w = 1.0 if ti == tj else 2.0
+                part = w * torch.sum((sig_h(dh) - sig_l(dl)) ** 2) / (n * n)
+                gi, gj = torch.autograd.grad(part, (zi, zj))
+                loss = loss + part.detach()
+                grad[ri] += gi
+                grad[rj] += gj
+            t += 1
+    return loss, grad
+
+
+def dihedral_of(p0, p1, p2, p3):
+    """Signed dihedral of four points in the convention of mdtraj's ``compute_dihedrals``
+    (b1.(b2 x b3)|b2| , (b1 x b2).(b2 x b3)) -- the convention the reference's "recomputed
+    dihedrals == requested" check uses (tests/test_losses.py:663-703)."""
+    b1, b2, b3 = p1 - p0, p2 - p1, p3 - p2
+    c1 = torch.cross(b2, b3, dim=-1)
+    c2 = torch.cross(b1, b2, dim=-1)
+    y = torch.sum(b1 * c1, dim=-1) * torch.linalg.norm(b2, dim=-1)
+    x = torch.sum(c1 * c2, dim=-1)
+    return torch.atan2(y, x)

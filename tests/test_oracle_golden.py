@@ -1,0 +1,126 @@
+"""Oracle vs golden vectors produced by running the reference's own function bodies
+(``tools/gen_golden.py``: ast-extracted from /root/reference, executed on a numpy ``tf`` shim).
+CPU only; the fixtures are committed under tests/golden/."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import em_oracle as O
+
+pi = math.pi
+T = lambda a: torch.from_numpy(np.asarray(a))  # noqa: E731
+
+
+def test_sigmoid_golden(golden):
+    g = golden["distances"]
+    r = T(g["sigmoid_r"])
+    for name in ("h_default", "l_default", "cube_h", "nb_h", "nb_l", "odd"):
+        p = g[f"sigmoid_{name}_params"]
+        np.testing.assert_allclose(O.sigmoid(*p)(r).numpy(), g[f"sigmoid_{name}_out"], rtol=1e-13, atol=1e-15)
+
+
+def test_periodic_distance_golden(golden):
+    g = golden["distances"]
+    a, b = g["perdist_a"], g["perdist_b"]
+    assert np.array_equal(O.periodic_distance(a, b, 2 * pi).numpy(), g["perdist_2pi"])
+    assert np.array_equal(O.periodic_distance(a * 50, b * 50, 360.0).numpy(), g["perdist_360"])
+    assert np.array_equal(O.periodic_distance(a, b, float("inf")).numpy(), g["perdist_inf"])
+
+
+def test_pairwise_golden(golden):
+    g = golden["distances"]
+    np.testing.assert_allclose(O.pairwise_dist_periodic(g["pwp_x"], 2 * pi).numpy(), g["pwp_2pi"], rtol=1e-13)
+    np.testing.assert_allclose(O.pairwise_dist_periodic(g["pwp_x"], 1.0).numpy(), g["pwp_1"], rtol=1e-13)
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x2"]).numpy(), g["pw_2d"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x2"], squared=True).numpy(), g["pw_2d_sq"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x2"], flat=True).numpy(), g["pw_2d_flat"], rtol=1e-12)
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x3"]).numpy(), g["pw_3d"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x3"], flat=True).numpy(), g["pw_3d_flat"], rtol=1e-12)
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x3"], flat=True, squared=True).numpy(), g["pw_3d_flat_sq"], rtol=1e-12)
+    # float32 evaluation agrees to float32 resolution
+    np.testing.assert_allclose(O.pairwise_dist(g["pw_x2"].astype(np.float32)).numpy(), g["pw_2d_f32"], rtol=1e-5, atol=1e-5)
+
+
+CASES = ["periodic_256x51", "nonperiodic_256x51", "cube_256x3", "nb_200x8", "periodic_clustered_300x64",
+         "generic_130x20", "latent3_150x10"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sigmoid_loss_golden(golden, name):
+    g = golden["sigmoid_loss"]
+    f = O.sigmoid_loss(float(g[f"{name}_per"]), tuple(g[f"{name}_sig"]))
+    loss = f(g[f"{name}_high"], g[f"{name}_low"]).item()
+    np.testing.assert_allclose(loss, float(g[f"{name}_loss"]), rtol=1e-12)
+    # float32 evaluation of the reference code vs our float32 oracle: same op order, a few ulp apart
+    l32 = f(g[f"{name}_high"].astype(np.float32), g[f"{name}_low"].astype(np.float32)).item()
+    np.testing.assert_allclose(l32, float(g[f"{name}_loss_f32"]), rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tiled_partial_sums_equal_full(golden, name):
+    """The sharded formulation (upper-triangular tiles, weights 1/2, difference-form distances)
+    sums to the reference's all-ordered-pairs mean -- the identity the multi-GPU split relies on."""
+    g = golden["sigmoid_loss"]
+    h, low, per, sig = g[f"{name}_high"], g[f"{name}_low"], float(g[f"{name}_per"]), tuple(g[f"{name}_sig"])
+    n = h.shape[0]
+    nt = (n + 63) // 64
+    total = nt * (nt + 1) // 2
+    cut = total // 3
+    l0, g0 = O.sigmoid_loss_tiles(h, low, per, sig, 0, cut, tile=64)
+    l1, g1 = O.sigmoid_loss_tiles(h, low, per, sig, cut, total, tile=64)
+    full, gfull = O.sigmoid_loss_and_grad(h, low, per, sig)
+    np.testing.assert_allclose((l0 + l1).item(), float(g[f"{name}_loss"]), rtol=1e-9)
+    np.testing.assert_allclose((l0 + l1).item(), full.item(), rtol=1e-9)
+    gn = torch.linalg.norm(gfull).item()
+    assert torch.linalg.norm(g0 + g1 - gfull).item() <= 1e-8 * gn
+
+
+@pytest.mark.parametrize("n", [9, 12, 30, 31, 300])
+def test_backmapping_golden(golden, n):
+    g = golden["backmapping"]
+    k = f"n{n}"
+    dist, ang, dih = T(g[f"{k}_dist"]), T(g[f"{k}_ang"]), T(g[f"{k}_dih"])
+    chain = O.chain_in_plane(dist.mean(0)[None], ang)
+    np.testing.assert_allclose(chain.numpy(), g[f"{k}_chain"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(O.chain_in_plane(dist, ang).numpy(), g[f"{k}_chain_perframe_lengths"], atol=1e-12)
+    left, right = O.split_counts(n)
+    out = O.dihedrals_to_cartesian_layers(dih + pi, chain, left, right)
+    np.testing.assert_allclose(out.numpy(), g[f"{k}_d2c_layers"], atol=1e-11)
+    np.testing.assert_allclose(O.dihedrals_to_cartesian_tf1(dih + pi, chain).numpy(), g[f"{k}_d2c_tf1"], atol=1e-11)
+    np.testing.assert_allclose(O.back_map_layer(dist, ang, dih).numpy(), g[f"{k}_backmaplayer"], atol=1e-11)
+    # TF1 and TF2 slicing agree (the reference's TestCompareSplits)
+    np.testing.assert_allclose(g[f"{k}_d2c_tf1"], g[f"{k}_d2c_layers"], atol=1e-12)
+    # index construction: bit-exact
+    cl, cr = O.split_and_reverse_cartesians(torch.arange(n)[None])
+    dl, dr = O.split_and_reverse_dihedrals(torch.arange(n - 3)[None])
+    assert np.array_equal(cl[0].numpy(), g[f"{k}_split_atoms_left"]) and np.array_equal(cr[0].numpy(), g[f"{k}_split_atoms_right"])
+    assert np.array_equal(dl[0].numpy(), g[f"{k}_split_dih_left"]) and np.array_equal(dr[0].numpy(), g[f"{k}_split_dih_right"])
+
+
+def test_reference_float32_error_band(golden):
+    """Documents SURVEY.md H1: the reference's own float32 evaluation is far from its float64
+    evaluation on long chains (this is why parity is judged against float64)."""
+    g = golden["backmapping"]
+    err = np.abs(g["n300_backmaplayer_f32"].astype(np.float64) - g["n300_backmaplayer"]).max()
+    assert 1e-5 < err < 5e-2
+
+
+def test_helix_and_rotation_golden(golden):
+    g = golden["backmapping"]
+    start = T(O.straight_tetrahedral_chain(33)).double()
+    assert np.array_equal(O.straight_tetrahedral_chain(33), g["tetra_33"])
+    assert np.array_equal(O.straight_tetrahedral_chain(bond_lengths=[1, 2, 3, 1, 2, 3]), g["tetra_7"])
+    dih = T(g["helix_dih"])
+    np.testing.assert_allclose(O.dihedral_to_cartesian_one_way(dih, start[None].expand(2, -1, -1)).numpy(), g["helix_oneway"], atol=1e-12)
+    np.testing.assert_allclose(O.dihedrals_to_cartesian_tf1(dih, start).numpy(), g["helix_twosided"], atol=1e-12)
+    np.testing.assert_allclose(O.rotation_matrix(T(g["rot_axis"]), T(g["rot_angle"])).numpy(), g["rot_out"], atol=1e-15)
+
+
+def test_layers_golden(golden):
+    g = golden["layers"]
+    np.testing.assert_allclose(O.periodic_input(g["pi_x"], 2 * pi).numpy(), g["pi_2pi"], atol=1e-15)
+    np.testing.assert_allclose(O.periodic_input(g["pi_x"] * 50, 360.0).numpy(), g["pi_360"], atol=1e-14)
+    for tag, sl in {"ca": (1, None, 3), "all": (None, None, None), "odd": (2, 25, 4)}.items():
+        np.testing.assert_allclose(O.pairwise_distances_layer(g["pd_xyz"], *sl).numpy(), g[f"pd_{tag}"], rtol=1e-12, atol=1e-14)

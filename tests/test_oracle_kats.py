@@ -1,0 +1,195 @@
+"""Pin the oracle against the known-answer vectors the reference's OWN tests hold for the path.
+
+Each test names the reference test it restates.  CPU only.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+from scipy.spatial.distance import cdist
+
+from oracle import em_oracle as O
+
+pi = math.pi
+DEFAULT_SIG = (4.5, 12, 6, 1, 2, 6)
+
+
+def _np_sigmoid(r, sig, a, b):
+    return 1 - (1 + (2 ** (a / b) - 1) * (r / sig) ** a) ** (-b / a)
+
+
+def _min_image_metric(periodicity):
+    # reference tests/test_pairwise_distances.py:65-75
+    def func(i, j):
+        dx = np.linalg.norm(j - i)
+        if dx > periodicity * 0.5:
+            dx = dx - periodicity
+        if dx <= -periodicity * 0.5:
+            dx = dx + periodicity
+        return np.abs(dx)
+
+    return func
+
+
+def test_periodic_distance_kat():
+    # reference tests/test_pairwise_distances.py:98-108 (exact equality)
+    a = np.array([0.0, 0.0, 0.0])
+    b = np.array([pi / 2, pi, 3 / 2 * pi])
+    d = O.periodic_distance(a, b, 2 * pi).numpy()
+    assert np.array_equal(d, np.array([pi / 2, pi, pi / 2]))
+
+
+def test_periodic_distance_docstring_kat():
+    # reference encodermap/misc/distances.py:131-137
+    d = O.periodic_distance(np.array([[1.5], [1.5]]), np.array([[-3.1], [-3.1]])).numpy()
+    np.testing.assert_allclose(d, [[1.68318531], [1.68318531]], atol=1e-8)
+
+
+def test_pairwise_dist_periodic_kats():
+    # reference tests/test_pairwise_distances.py:140-148
+    pts = np.array([[1 / 8, 1 / 2], [7 / 8, 1 / 2]], dtype=np.float32)
+    np.testing.assert_allclose(O.pairwise_dist_periodic(pts, 1).numpy(), [[0, 1 / 4], [1 / 4, 0]], atol=1e-6)
+    np.testing.assert_allclose(O.pairwise_dist_periodic(pts, float("inf")).numpy(), [[0, 6 / 8], [6 / 8, 0]], atol=1e-6)
+
+
+def test_pairwise_dist_kat_and_flat_order():
+    # reference tests/test_pairwise_distances.py:150-153 and :164-168 (pins pair order)
+    d = O.pairwise_dist(np.array([[1 / 8, 1 / 2], [7 / 8, 1 / 2]], dtype=np.float32)).numpy()
+    np.testing.assert_allclose(d, [[[0, 6 / 8], [6 / 8, 0]]], atol=1e-6)
+    f = O.pairwise_dist(np.array([[0, 0], [1, 0], [0, 1]], dtype=np.float32), flat=True).numpy()
+    np.testing.assert_allclose(f, [[1, 1, 2 ** 0.5]], atol=1e-6)
+
+
+def test_periodic_many_points():
+    # reference tests/test_pairwise_distances.py:110-135
+    metric = _min_image_metric(360.0)
+    pts = np.vstack([20.0, 40.0, 340.0]).astype(np.float32)
+    np.testing.assert_allclose(cdist(pts, pts, metric), O.pairwise_dist_periodic(pts, 360.0).numpy(), atol=1e-5)
+    np.random.seed(1)
+    pts = np.random.random((100, 1)).astype(np.float32) * 360.0
+    np.testing.assert_allclose(cdist(pts, pts, metric), O.pairwise_dist_periodic(pts, 360.0).numpy(), atol=1e-5)
+
+
+def test_periodic_equals_nonperiodic_for_huge_period():
+    # reference tests/test_pairwise_distances.py:155-162
+    rng = np.random.default_rng(0)
+    pts = rng.normal(size=(10, 3)).astype(np.float32)
+    np.testing.assert_allclose(O.pairwise_dist_periodic(pts, 10000).numpy().reshape(-1),
+                               O.pairwise_dist(pts).numpy().reshape(-1), atol=1e-5)
+
+
+def test_sigmoid_of_pairwise_vs_scipy():
+    # reference tests/test_pairwise_distances.py:80-93
+    np.random.seed(1)
+    pts = np.random.random((100, 2)).astype(np.float32) * 360.0
+    ref = cdist(pts, pts, lambda i, j: _np_sigmoid(np.linalg.norm(j - i), *DEFAULT_SIG[:3]))
+    got = O.sigmoid(*DEFAULT_SIG[:3])(O.pairwise_dist(pts)).numpy().squeeze()
+    np.testing.assert_allclose(ref, got, atol=1e-3)
+
+
+def test_sigmoid_scalar_kat():
+    # reference tests/test_pairwise_distances.py:186-193: em1 sigmoid(1.5, 5, 12, 2) == em2 sigmoid(5, 12, 2)(1.5)
+    assert O.sigmoid(5, 12, 2)(1.5) == _np_sigmoid(1.5, 5, 12, 2)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_sigmoid_loss_vs_scipy(periodic):
+    # reference tests/test_losses.py:195-280 (re-seeded; the reference draws unseeded)
+    rng = np.random.default_rng(7)
+    if periodic:
+        highd = (rng.random((256, 51)).astype("float32") * 2 * np.pi) - np.pi
+        per = 2 * np.pi
+
+        def hmetric(i, j):
+            return _np_sigmoid(_min_image_metric(per)(i, j), *DEFAULT_SIG[:3])
+    else:
+        highd = rng.random((256, 51)).astype("float32") * 100
+        per = float("inf")
+
+        def hmetric(i, j):
+            return _np_sigmoid(np.linalg.norm(j - i), *DEFAULT_SIG[:3])
+    lowd = rng.random((256, 2)).astype("float32") * 10
+    cost = O.sigmoid_loss(per, DEFAULT_SIG)(highd, lowd).item()
+    if periodic:
+        # the reference's numpy restatement (tests/test_losses.py:259-271)
+        d = np.abs(highd[None] - highd[:, None])
+        d = np.minimum(d, 2 * np.pi - d)
+        d = d + np.equal(d, 0.0) * 1e-16
+        sig_h = _np_sigmoid(np.linalg.norm(d, axis=2), *DEFAULT_SIG[:3])
+    else:
+        sig_h = cdist(highd, highd, hmetric)
+    sig_l = cdist(lowd, lowd, lambda i, j: _np_sigmoid(np.linalg.norm(j - i), *DEFAULT_SIG[3:]))
+    np.testing.assert_allclose(cost, np.mean(np.square(sig_h - sig_l)), rtol=1e-5)
+
+
+def test_behavioural_zeros():
+    # reference tests/test_losses.py:311-318 (uniform in + uniform latent => 0) and :897-904
+    x = np.ones((32, 7), dtype=np.float32) * 0.3
+    z = np.ones((32, 2), dtype=np.float32) * 1.7
+    assert O.sigmoid_loss(2 * pi, DEFAULT_SIG)(x, z).item() == 0.0
+    y = np.random.default_rng(3).random((20, 6)).astype(np.float32)
+    assert O.cartesian_distance_loss_value(y, y, (1, 1, 1, 1, 1, 1)).item() == 0.0
+    assert O.cartesian_distance_loss_value(np.zeros((20, 6), np.float32), np.zeros((20, 2), np.float32), (1, 1, 1, 1, 1, 1)).item() == 0.0
+
+
+def test_straight_tetrahedral_chain_kat():
+    # reference tests/test_dihedral_to_cartesian.py:186-197
+    want = [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [1.6633345, 1.8867929, 0.0], [4.6633344, 1.8867929, 0.0],
+            [4.995002, 2.8301892, 0.0], [6.995002, 2.8301892, 0.0], [7.990003, 5.6603785, 0.0]]
+    np.testing.assert_allclose(O.straight_tetrahedral_chain(bond_lengths=[1, 2, 3, 1, 2, 3]), want, rtol=1e-6)
+
+
+def test_helix_kat_one_way(golden):
+    # reference tests/test_dihedral_to_cartesian.py:98-153 (33x3 table, atol 1e-4; upstream skips it
+    # because it predates the two-sided split -- it pins the one-way algorithm)
+    g = golden["backmapping"]
+    start = torch.from_numpy(O.straight_tetrahedral_chain(33)).double()[None].expand(2, -1, -1)
+    out = O.dihedral_to_cartesian_one_way(torch.from_numpy(g["helix_dih"]), start).numpy()
+    np.testing.assert_allclose(out[0], g["helix_kat"], atol=1e-4)
+
+
+def test_split_indices_match_tf1_slicing():
+    # reference tests/test_backmapping_em1_em2.py:2115-2156 (exact equality, random chain lengths)
+    rng = np.random.default_rng(11)
+    for n in list(rng.integers(6, 1000, size=10)) + [6, 7, 8, 9, 300, 1500]:
+        n = int(n)
+        atoms = torch.arange(n)[None]
+        dih = torch.arange(n - 3)[None]
+        la, ld, ra, rd = O.split_indices_tf1(n)
+        cl, cr = O.split_and_reverse_cartesians(atoms)
+        dl, dr = O.split_and_reverse_dihedrals(dih)
+        assert np.array_equal(cl[0].numpy(), la) and np.array_equal(cr[0].numpy(), ra)
+        assert np.array_equal(dl[0].numpy(), ld) and np.array_equal(dr[0].numpy(), rd)
+        left, right = O.split_counts(n)
+        assert left == len(ld) and right == len(rd)
+
+
+def test_split_doctest_examples():
+    # reference encodermap/misc/backmapping.py:186-199 (3 residues: 6 dihedrals -> 3 reversed + 3)
+    d = torch.tensor([[3.69533481, 5.64050171, 5.60165278, 5.12605805, 0.22550092, 4.34644107]], dtype=torch.float64)
+    left, right = O.split_and_reverse_dihedrals(d)
+    assert left[0].tolist() == [5.60165278, 5.64050171, 3.69533481]
+    assert right[0].tolist() == [5.12605805, 0.22550092, 4.34644107]
+    c = torch.arange(27.0).reshape(1, 9, 3)
+    cl, cr = O.split_and_reverse_cartesians(c)
+    assert cl.shape == (1, 6, 3) and cr.shape == (1, 6, 3)
+    assert torch.equal(cl[:, 0], cr[:, 2]) and torch.equal(cl[:, 1], cr[:, 1]) and torch.equal(cl[:, 2], cr[:, 0])
+
+
+def test_backmap_realises_internal_coordinates():
+    # the invariant behind reference tests/test_losses.py:663-703: recomputed bond lengths, angles and
+    # dihedrals of the back-mapped chain equal the requested ones
+    rng = np.random.default_rng(5)
+    B, n = 3, 45
+    dist = torch.from_numpy(rng.uniform(0.13, 0.15, size=(B, n - 1)))
+    ang = torch.from_numpy(rng.uniform(1.9, 2.2, size=(B, n - 2)))
+    dih = torch.from_numpy(rng.uniform(-pi, pi, size=(B, n - 3)))
+    xyz = O.back_map_layer(dist, ang, dih)
+    bonds = xyz[:, 1:] - xyz[:, :-1]
+    np.testing.assert_allclose(torch.linalg.norm(bonds, dim=-1).numpy(), dist.mean(0)[None].expand(B, -1).numpy(), atol=1e-12)
+    cosang = -(bonds[:, 1:] * bonds[:, :-1]).sum(-1) / (torch.linalg.norm(bonds[:, 1:], dim=-1) * torch.linalg.norm(bonds[:, :-1], dim=-1))
+    np.testing.assert_allclose(torch.acos(cosang).numpy(), ang.numpy(), atol=1e-10)
+    got = O.dihedral_of(xyz[:, :-3], xyz[:, 1:-2], xyz[:, 2:-1], xyz[:, 3:])
+    diff = (got - dih + pi) % (2 * pi) - pi
+    assert diff.abs().max().item() < 1e-9

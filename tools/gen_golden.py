@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Generate golden vectors by executing the REFERENCE's own function bodies.
+
+TensorFlow is not installed in this image, so ``import encodermap`` fails.  The hot-path
+functions, however, are short pure functions of a dozen ``tf.*`` primitives.  This script
+
+  1. parses the reference source files under ``/root/reference`` with ``ast`` and pulls out
+     the hot-path function definitions by name (nothing is copied into the repo -- the code
+     is compiled and executed in memory, straight from where it lies);
+  2. executes them against ``_TFShim`` -- a numpy-backed stand-in for the handful of ``tf``
+     symbols they touch (float64 or float32);
+  3. writes inputs and outputs to ``tests/golden/*.npz``.
+
+The oracle (``oracle/em_oracle.py``) and the CUDA kernels are then tested against these
+files.  ``/root/reference`` only exists in the build container, so this script runs there
+only; the fixtures it writes are committed.
+
+    python tools/gen_golden.py            # rewrites tests/golden/*.npz
+"""
+
+from __future__ import annotations
+
+import ast
+import math
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REF = Path(os.environ.get("EMK_REFERENCE", "/root/reference"))
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+# ----------------------------------------------------------------------------------------
+# numpy-backed stand-in for the tf namespace used by the hot-path functions
+# ----------------------------------------------------------------------------------------
+
+
+class T(np.ndarray):
+    """ndarray that also answers the few tf.Tensor methods the reference calls."""
+
+    def get_shape(self):
+        return self.shape
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+def _w(x, dtype=None):
+    a = np.asarray(x, dtype=dtype)
+    return a.view(T)
+
+
+class _Debugging:
+    @staticmethod
+    def is_numeric_tensor(x):
+        return isinstance(x, T)
+
+    @staticmethod
+    def assert_all_finite(x, message=""):
+        assert np.all(np.isfinite(np.asarray(x))), message
+        return x
+
+    @staticmethod
+    def assert_rank(x, rank):
+        assert np.ndim(x) == rank
+
+
+class _Linalg:
+    @staticmethod
+    def diag_part(x):
+        return _w(np.diagonal(x, axis1=-2, axis2=-1).copy())
+
+    @staticmethod
+    def cross(a, b):
+        return _w(np.cross(a, b))
+
+
+class _Math:
+    @staticmethod
+    def equal(a, b):
+        return _w(np.equal(a, b))
+
+    @staticmethod
+    def mod(a, b):
+        return _w(np.mod(a, b))
+
+
+class _TFShim:
+    """Only what distances.py / loss_functions.py / backmapping.py / layers.py use on the path."""
+
+    debugging = _Debugging()
+    linalg = _Linalg()
+    math = _Math()
+    float32 = np.float32
+
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+
+    # construction ---------------------------------------------------------------
+    def convert_to_tensor(self, x, dtype=None):
+        if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], (list, tuple)):
+            x = np.array([[np.asarray(e) for e in row] for row in x])
+        a = np.asarray(x)
+        if a.dtype.kind == "f" or a.dtype.kind in "iu":
+            a = a.astype(self.dtype) if a.dtype.kind == "f" else a
+        return _w(a)
+
+    def constant(self, x, dtype=None):
+        return self.convert_to_tensor(x)
+
+    def is_numeric_tensor(self, x):
+        return isinstance(x, T)
+
+    def zeros(self, shape, dtype=None):
+        return _w(np.zeros(tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, int) else (shape,), self.dtype))
+
+    def ones_like(self, x):
+        return _w(np.ones_like(x))
+
+    def eye(self, n):
+        return _w(np.eye(n, dtype=self.dtype))
+
+    def shape(self, x):
+        return np.asarray(np.shape(x))
+
+    # elementwise ----------------------------------------------------------------
+    def abs(self, x):
+        return _w(np.abs(x))
+
+    def minimum(self, a, b):
+        return _w(np.minimum(a, b))
+
+    def maximum(self, a, b):
+        return _w(np.maximum(a, b))
+
+    def square(self, x):
+        return _w(np.square(x))
+
+    def sqrt(self, x):
+        return _w(np.sqrt(x))
+
+    def cos(self, x):
+        return _w(np.cos(x))
+
+    def sin(self, x):
+        return _w(np.sin(x))
+
+    def add(self, a, b):
+        return _w(np.add(a, b))
+
+    def equal(self, a, b):
+        return _w(np.equal(a, b))
+
+    def where(self, c, a, b):
+        return _w(np.where(c, a, b))
+
+    def cast(self, x, dtype):
+        # the reference casts boolean masks to "float32"/np.float32; keep the working dtype so
+        # the float64 evaluation stays float64 (the mask holds 0/1 exactly either way)
+        return _w(np.asarray(x).astype(self.dtype))
+
+    def to_float(self, x):
+        return self.cast(x, None)
+
+    # reductions / shape ops -------------------------------------------------------
+    def reduce_sum(self, x, axis=None):
+        return _w(np.sum(x, axis=axis))
+
+    def reduce_mean(self, x, axis=None):
+        return _w(np.mean(x, axis=axis))
+
+    def norm(self, x, axis=None, keepdims=False):
+        return _w(np.sqrt(np.sum(np.square(x), axis=axis, keepdims=keepdims)))
+
+    def expand_dims(self, x, axis):
+        return _w(np.expand_dims(x, axis))
+
+    def transpose(self, x, perm=None):
+        return _w(np.transpose(x, perm))
+
+    def matmul(self, a, b):
+        return _w(np.matmul(a, b))
+
+    def stack(self, xs, axis=0):
+        return _w(np.stack([np.asarray(x) for x in xs], axis=axis))
+
+    def concat(self, xs, axis):
+        return _w(np.concatenate([np.asarray(x) for x in xs], axis=axis))
+
+    def tile(self, x, multiples):
+        return _w(np.tile(x, [int(m) for m in multiples]))
+
+    def boolean_mask(self, x, mask, axis=0):
+        # tf.boolean_mask(x, mask, axis=1) with a rank-2 mask flattens dims (1,2) row-major
+        assert axis == 1 and np.ndim(mask) == 2
+        return _w(np.asarray(x)[:, np.asarray(mask)])
+
+    def cond(self, pred, true_fn, false_fn, name=None):
+        return true_fn() if bool(np.asarray(pred)) else false_fn()
+
+
+# ----------------------------------------------------------------------------------------
+# pull function definitions out of the reference sources
+# ----------------------------------------------------------------------------------------
+
+
+def _extract(path: Path, names, ns):
+    """Compile the named top-level (or class-level) function definitions of ``path`` into ``ns``."""
+    tree = ast.parse(path.read_text())
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            node.decorator_list = []  # drop @tf.function / @overload
+            node.returns = None
+            for a in node.args.args + node.args.kwonlyargs:
+                a.annotation = None
+            found[node.name] = node
+    missing = set(names) - set(found)
+    assert not missing, f"{path}: {missing} not found"
+    mod = ast.Module(body=[found[n] for n in names], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, str(path), "exec"), ns)
+
+
+def load_reference(dtype):
+    tf = _TFShim(dtype)
+    ns = {"tf": tf, "np": np, "pi": math.pi, "cos": math.cos, "sin": math.sin, "math": math,
+          "overload": lambda f: f, "Union": None, "Number": None, "Callable": None, "Optional": None}
+    _extract(REF / "encodermap/misc/distances.py",
+             ["sigmoid", "periodic_distance_np", "periodic_distance", "pairwise_dist_periodic", "pairwise_dist"], ns)
+    _extract(REF / "encodermap/misc/backmapping.py",
+             ["split_and_reverse_dihedrals", "split_and_reverse_cartesians", "dihedrals_to_cartesian_tf_layers",
+              "dihedral_to_cartesian_tf_one_way_layers", "rotation_matrix"], ns)
+    ns1 = dict(ns)  # TF1 twins live in their own namespace (same names, different bodies)
+    _extract(REF / "encodermap/encodermap_tf1/backmapping.py",
+             ["straight_tetrahedral_chain", "chain_in_plane", "dihedrals_to_cartesian_tf",
+              "dihedral_to_cartesian_tf_one_way"], ns1)
+    _extract(REF / "encodermap/encodermap_tf1/misc.py", ["rotation_matrix", "distance_cost"], ns1)
+    ns1["sigmoid_tf1"] = None
+    # sigmoid_loss: the closure needs a Parameters-like object
+    ns["Parameters"] = lambda: type("P", (), {"periodicity": 2 * math.pi, "dist_sig_parameters": (4.5, 12, 6, 1, 2, 6)})()
+    _extract(REF / "encodermap/loss_functions/loss_functions.py", ["sigmoid_loss"], ns)
+    ns["chain_in_plane"] = ns1["chain_in_plane"]
+    # BackMapLayer.call / PeriodicInput.call / PairwiseDistances.call bodies
+    ns["Concatenate"] = lambda axis, name=None: (lambda xs: tf.concat(xs, axis))
+    tree = ast.parse((REF / "encodermap/models/layers.py").read_text())
+    for cls in [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("BackMapLayer", "PeriodicInput", "PairwiseDistances")]:
+        for fn in cls.body:
+            if isinstance(fn, ast.FunctionDef) and fn.name == "call":
+                fn.name = f"{cls.name}_call"
+                fn.decorator_list = []
+                fn.returns = None
+                for a in fn.args.args:
+                    a.annotation = None
+                mod = ast.Module(body=[fn], type_ignores=[])
+                ast.fix_missing_locations(mod)
+                exec(compile(mod, "layers.py", "exec"), ns)
+    return tf, ns, ns1
+
+
+class _Self:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(20261017)
+    tf64, R, R1 = load_reference(np.float64)
+    tf32, R32, R132 = load_reference(np.float32)
+    sig_default = (4.5, 12, 6, 1, 2, 6)
+
+    # ---- distances ------------------------------------------------------------------------
+    g = {}
+    r = np.abs(rng.normal(size=64)) * 3
+    for name, p in {"h_default": (4.5, 12, 6), "l_default": (1, 2, 6), "cube_h": (0.2, 3, 6), "nb_h": (0.3, 6, 6),
+                    "nb_l": (1, 4, 6), "odd": (1.3, 2.5, 3.7)}.items():
+        g[f"sigmoid_{name}_params"] = np.array(p, dtype=np.float64)
+        g[f"sigmoid_{name}_out"] = np.asarray(R["sigmoid"](*p)(tf64.convert_to_tensor(r)))
+    g["sigmoid_r"] = r
+    a = rng.uniform(-math.pi, math.pi, size=(7, 5))
+    b = rng.uniform(-math.pi, math.pi, size=(7, 5))
+    g["perdist_a"], g["perdist_b"] = a, b
+    g["perdist_2pi"] = np.asarray(R["periodic_distance"](tf64.convert_to_tensor(a), tf64.convert_to_tensor(b), 2 * math.pi))
+    g["perdist_360"] = np.asarray(R["periodic_distance"](tf64.convert_to_tensor(a * 50), tf64.convert_to_tensor(b * 50), 360.0))
+    g["perdist_inf"] = np.asarray(R["periodic_distance"](tf64.convert_to_tensor(a), tf64.convert_to_tensor(b), float("inf")))
+    x = rng.uniform(-math.pi, math.pi, size=(48, 37))
+    g["pwp_x"] = x
+    g["pwp_2pi"] = np.asarray(R["pairwise_dist_periodic"](tf64.convert_to_tensor(x), 2 * math.pi))
+    g["pwp_1"] = np.asarray(R["pairwise_dist_periodic"](tf64.convert_to_tensor(x), 1.0))
+    y = rng.normal(size=(40, 3))
+    g["pw_x2"] = y
+    g["pw_2d"] = np.asarray(R["pairwise_dist"](tf64.convert_to_tensor(y)))
+    g["pw_2d_sq"] = np.asarray(R["pairwise_dist"](tf64.convert_to_tensor(y), squared=True))
+    g["pw_2d_flat"] = np.asarray(R["pairwise_dist"](tf64.convert_to_tensor(y), flat=True))
+    y3 = rng.normal(size=(5, 17, 3))
+    g["pw_x3"] = y3
+    g["pw_3d"] = np.asarray(R["pairwise_dist"](tf64.convert_to_tensor(y3)))
+    g["pw_3d_flat"] = np.asarray(R["pairwise_dist"](tf64.convert_to_tensor(y3), flat=True))
+    g["pw_3d_flat_sq"] = np.asarray(R["pairwise_dist"](tf64.convert_to_tensor(y3), flat=True, squared=True))
+    # float32 run of the same functions (error band of the reference's own precision)
+    g["pw_2d_f32"] = np.asarray(R32["pairwise_dist"](tf32.convert_to_tensor(y.astype(np.float32))))
+    g["pwp_2pi_f32"] = np.asarray(R32["pairwise_dist_periodic"](tf32.convert_to_tensor(x.astype(np.float32)), 2 * math.pi))
+    np.savez_compressed(OUT / "distances.npz", **g)
+
+    # ---- sigmoid loss ------------------------------------------------------------------------
+    g = {}
+    cases = {
+        "periodic_256x51": dict(n=256, d=51, per=2 * math.pi, sig=sig_default, hscale=None, lscale=10.0),
+        "nonperiodic_256x51": dict(n=256, d=51, per=float("inf"), sig=sig_default, hscale=100.0, lscale=10.0),
+        "cube_256x3": dict(n=256, d=3, per=float("inf"), sig=(0.2, 3, 6, 1, 2, 6), hscale=1.0, lscale=1.0),
+        "nb_200x8": dict(n=200, d=8, per=float("inf"), sig=(0.3, 6, 6, 1, 4, 6), hscale=1.0, lscale=1.0),
+        "periodic_clustered_300x64": dict(n=300, d=64, per=2 * math.pi, sig=sig_default, hscale=None, lscale=3.0, clustered=True),
+        "generic_130x20": dict(n=130, d=20, per=3.0, sig=(1.3, 2.5, 3.7, 0.8, 1.7, 2.9), hscale=None, lscale=2.0),
+        "latent3_150x10": dict(n=150, d=10, per=2 * math.pi, sig=sig_default, hscale=None, lscale=2.0, lat=3),
+    }
+    for name, c in cases.items():
+        n, d = c["n"], c["d"]
+        if c.get("clustered"):
+            centres = rng.uniform(-math.pi, math.pi, size=(6, d))
+            h = centres[rng.integers(0, 6, size=n)] + rng.normal(scale=0.05, size=(n, d))
+            h = (h + math.pi) % (2 * math.pi) - math.pi
+        elif c["hscale"] is None:
+            h = rng.uniform(-0.5, 0.5, size=(n, d)) * (c["per"] if np.isfinite(c["per"]) else 1.0)
+        else:
+            h = rng.uniform(size=(n, d)) * c["hscale"]
+        low = rng.uniform(size=(n, c.get("lat", 2))) * c["lscale"]
+        h = h.astype(np.float32).astype(np.float64)  # float32-representable inputs
+        low = low.astype(np.float32).astype(np.float64)
+        f = R["sigmoid_loss"](None, periodicity_overwrite=c["per"], dist_dig_parameters_overwrite=c["sig"])
+        g[f"{name}_high"], g[f"{name}_low"] = h, low
+        g[f"{name}_per"] = np.float64(c["per"])
+        g[f"{name}_sig"] = np.array(c["sig"], dtype=np.float64)
+        g[f"{name}_loss"] = np.float64(f(tf64.convert_to_tensor(h), tf64.convert_to_tensor(low)))
+        # TF1 twin must agree exactly (reference tests/test_losses.py:226,277)
+        R1["pairwise_dist"], R1["pairwise_dist_periodic"] = R["pairwise_dist"], R["pairwise_dist_periodic"]
+        R1["sigmoid"] = lambda r_, s_, a_, b_: R["sigmoid"](s_, a_, b_)(r_)
+        if c["per"] == float("inf"):
+            l1 = R1["distance_cost"](tf64.convert_to_tensor(h), tf64.convert_to_tensor(low), *c["sig"], c["per"])
+            assert float(l1) == float(g[f"{name}_loss"])
+        f32 = R32["sigmoid_loss"](None, periodicity_overwrite=c["per"], dist_dig_parameters_overwrite=c["sig"])
+        g[f"{name}_loss_f32"] = np.float64(f32(tf32.convert_to_tensor(h.astype(np.float32)), tf32.convert_to_tensor(low.astype(np.float32))))
+    np.savez_compressed(OUT / "sigmoid_loss.npz", **g)
+
+    # ---- back-mapping ----------------------------------------------------------------------------
+    g = {}
+    g["tetra_7"] = np.asarray(R1["straight_tetrahedral_chain"](bond_lengths=[1, 2, 3, 1, 2, 3]))
+    g["tetra_33"] = np.asarray(R1["straight_tetrahedral_chain"](33))
+    for n_atoms, batch in ((9, 4), (12, 3), (30, 5), (31, 5), (300, 2)):
+        dist = rng.uniform(0.13, 0.15, size=(batch, n_atoms - 1)).astype(np.float32).astype(np.float64)
+        ang = rng.uniform(1.9, 2.2, size=(batch, n_atoms - 2)).astype(np.float32).astype(np.float64)
+        dih = rng.uniform(-math.pi, math.pi, size=(batch, n_atoms - 3)).astype(np.float32).astype(np.float64)
+        k = f"n{n_atoms}"
+        g[f"{k}_dist"], g[f"{k}_ang"], g[f"{k}_dih"] = dist, ang, dih
+        lengths = np.mean(dist, axis=0)[None]
+        chain = R1["chain_in_plane"](tf64.convert_to_tensor(lengths), tf64.convert_to_tensor(ang))
+        g[f"{k}_chain"] = np.asarray(chain)
+        chain_b = R1["chain_in_plane"](tf64.convert_to_tensor(dist), tf64.convert_to_tensor(ang))
+        g[f"{k}_chain_perframe_lengths"] = np.asarray(chain_b)
+        left, right = n_atoms // 2 - 1, (n_atoms - 3) // 2
+        d_in = tf64.convert_to_tensor(dih + math.pi)
+        out_layers = R["dihedrals_to_cartesian_tf_layers"](d_in, chain, left, right)
+        g[f"{k}_d2c_layers"] = np.asarray(out_layers)
+        out_tf1 = R1["dihedrals_to_cartesian_tf"](d_in, chain)
+        g[f"{k}_d2c_tf1"] = np.asarray(out_tf1)
+        me = _Self(left_split=left, right_split=right)
+        out_layer = R["BackMapLayer_call"](me, (tf64.convert_to_tensor(dist), tf64.convert_to_tensor(ang), tf64.convert_to_tensor(dih)))
+        g[f"{k}_backmaplayer"] = np.asarray(out_layer)
+        # float32 evaluation of the same reference code (its own error band)
+        out32 = R32["BackMapLayer_call"](me, (tf32.convert_to_tensor(dist.astype(np.float32)),
+                                              tf32.convert_to_tensor(ang.astype(np.float32)),
+                                              tf32.convert_to_tensor(dih.astype(np.float32))))
+        g[f"{k}_backmaplayer_f32"] = np.asarray(out32)
+        # split index construction (integer, bit-exact)
+        ia = np.arange(n_atoms)[None]
+        idh = np.arange(n_atoms - 3)[None]
+        cl, cr = R["split_and_reverse_cartesians"](tf64.convert_to_tensor(ia))
+        dl, dr = R["split_and_reverse_dihedrals"](tf64.convert_to_tensor(idh))
+        g[f"{k}_split_atoms_left"], g[f"{k}_split_atoms_right"] = np.asarray(cl)[0].astype(np.int64), np.asarray(cr)[0].astype(np.int64)
+        g[f"{k}_split_dih_left"], g[f"{k}_split_dih_right"] = np.asarray(dl)[0].astype(np.int64), np.asarray(dr)[0].astype(np.int64)
+    # helix KAT of the reference's (skipped) one-way test: tests/test_dihedral_to_cartesian.py:98-153
+    phi = (57.8 / 180) * math.pi + math.pi
+    psi = (47.0 / 180) * math.pi + math.pi
+    dih = np.array([[phi, psi, 0.0] * 10] * 2)
+    start = R1["straight_tetrahedral_chain"](33)
+    g["helix_dih"] = dih
+    g["helix_oneway"] = np.asarray(R1["dihedral_to_cartesian_tf_one_way"](tf64.convert_to_tensor(dih), tf64.convert_to_tensor(np.tile(start[None], (2, 1, 1)))))
+    g["helix_twosided"] = np.asarray(R1["dihedrals_to_cartesian_tf"](tf64.convert_to_tensor(dih), tf64.convert_to_tensor(start)))
+    # the reference's own 33x3 helix known-answer table (float32 literals in its test file)
+    tree = ast.parse((REF / "tests/test_dihedral_to_cartesian.py").read_text())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "test_straight_to_helix_array":
+            for st in node.body:
+                if isinstance(st, ast.Assign) and getattr(st.targets[0], "id", "") == "result":
+                    g["helix_kat"] = np.array(ast.literal_eval(st.value.args[0].left))[0]
+    assert np.abs(g["helix_oneway"][0] - g["helix_kat"]).max() < 1e-4  # reference's own atol
+    # rotation matrix
+    ax = rng.normal(size=(6, 3))
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    angs = rng.uniform(-math.pi, math.pi, size=6)
+    g["rot_axis"], g["rot_angle"] = ax, angs
+    g["rot_out"] = np.asarray(R["rotation_matrix"](tf64.convert_to_tensor(ax), tf64.convert_to_tensor(angs)))
+    assert np.array_equal(g["rot_out"], np.asarray(R1["rotation_matrix"](tf64.convert_to_tensor(ax), tf64.convert_to_tensor(angs))))
+    np.savez_compressed(OUT / "backmapping.npz", **g)
+
+    # ---- layers ----------------------------------------------------------------------------------
+    g = {}
+    xin = rng.uniform(-math.pi, math.pi, size=(6, 9))
+    g["pi_x"] = xin
+    g["pi_2pi"] = np.asarray(R["PeriodicInput_call"](_Self(p=_Self(periodicity=2 * math.pi), print_name="x"), tf64.convert_to_tensor(xin)))
+    g["pi_360"] = np.asarray(R["PeriodicInput_call"](_Self(p=_Self(periodicity=360.0), print_name="x"), tf64.convert_to_tensor(xin * 50)))
+    xyz = rng.normal(size=(4, 30, 3))
+    g["pd_xyz"] = xyz
+    for tag, (a_, b_, c_) in {"ca": (1, None, 3), "all": (None, None, None), "odd": (2, 25, 4)}.items():
+        p = _Self(reconstruct_sidechains=False, cartesian_pwd_start=a_, cartesian_pwd_stop=b_, cartesian_pwd_step=c_)
+        g[f"pd_{tag}"] = np.asarray(R["PairwiseDistances_call"](_Self(p=p), tf64.convert_to_tensor(xyz)))
+    np.savez_compressed(OUT / "layers.npz", **g)
+    for f in sorted(OUT.glob("*.npz")):
+        print(f"{f.name}: {f.stat().st_size} bytes")
+
+
+if __name__ == "__main__":
+    if not REF.exists():
+        sys.exit(f"{REF} not present: golden vectors can only be regenerated in the build container")
+    main()

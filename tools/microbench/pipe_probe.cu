@@ -1,0 +1,212 @@
+// Microbenchmark: FP32 issue/pipe limits of the periodic pair-distance inner loop on sm_100a.
+// Variants of the per-(pair,dim) instruction mix, same 8x8 register blocking and swizzled
+// LDS.128 operand reads the production kernel uses.  Prints achieved (pair,dim)/s and
+// lane-instr/s for each variant at 1 and 2 resident CTAs per SM.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+constexpr int TM = 128, KC = 32;
+
+__device__ __forceinline__ int swz(int row, int k4) { return row * KC + ((k4 ^ (row & 7)) << 2); }
+
+template <int V>
+__device__ __forceinline__ void pairdim(float a, float b, float P, float Ph, float& acc) {
+  if (V == 0) {            // FADD, FADD(-|d|+P), FMNMX, FFMA : reference form
+    float d = a - b; float t = P - fabsf(d); float m = fminf(fabsf(d), t); acc = fmaf(m, m, acc);
+  } else if (V == 2) {     // all-FMA-pipe form: m = P/2 - ||d| - P/2|
+    float d = a - b; float e = fabsf(d) - Ph; float m = Ph - fabsf(e); acc = fmaf(m, m, acc);
+  } else if (V == 3) {     // pure FFMA (peak probe)
+    acc = fmaf(a, b, acc);
+  } else if (V == 4) {     // difference form (non-periodic)
+    float d = a - b; acc = fmaf(d, d, acc);
+  }
+}
+
+template <int V, int MINB>
+__global__ void __launch_bounds__(256, MINB) probe(const float* __restrict__ g, float* out, float P, int iters) {
+  extern __shared__ __align__(1024) float sm[];
+  float* sa = sm; float* sb = sm + TM * KC;
+  for (int i = threadIdx.x; i < 2 * TM * KC; i += blockDim.x) sm[i] = g[i];
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const float Ph = 0.5f * P;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 2
+    for (int k4 = 0; k4 < KC / 4; k4++) {
+      float4 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) av[i] = *reinterpret_cast<const float4*>(&sa[swz(ty + 16 * i, k4)]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float4 bv = *reinterpret_cast<const float4*>(&sb[swz(tx + 16 * j, k4)]);
+        if (V == 1) {      // packed: FADD2 for d, scalar FADD/FMNMX, FFMA2
+          // handled in the packed kernel below
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          pairdim<V>(av[i].x, bv.x, P, Ph, acc[i][j]);
+          pairdim<V>(av[i].y, bv.y, P, Ph, acc[i][j]);
+          pairdim<V>(av[i].z, bv.z, P, Ph, acc[i][j]);
+          pairdim<V>(av[i].w, bv.w, P, Ph, acc[i][j]);
+        }
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += acc[i][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// packed variant: accumulators are float2 over two k lanes (x,y) and (z,w) of the same pair;
+// d via FADD2, fold via scalar FADD+FMNMX, square-accumulate via FFMA2.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) probe_packed(const float* __restrict__ g, float* out, float P, int iters) {
+  extern __shared__ __align__(1024) float sm[];
+  float* sa = sm; float* sb = sm + TM * KC;
+  for (int i = threadIdx.x; i < 2 * TM * KC; i += blockDim.x) sm[i] = g[i];
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float2 acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = make_float2(0.f, 0.f);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 1
+    for (int k4 = 0; k4 < KC / 4; k4++) {
+      float4 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) av[i] = *reinterpret_cast<const float4*>(&sa[swz(ty + 16 * i, k4)]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float4 bv = *reinterpret_cast<const float4*>(&sb[swz(tx + 16 * j, k4)]);
+        float2 nb0 = make_float2(-bv.x, -bv.y), nb1 = make_float2(-bv.z, -bv.w);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float2 d0 = __fadd2_rn(make_float2(av[i].x, av[i].y), nb0);
+          float2 d1 = __fadd2_rn(make_float2(av[i].z, av[i].w), nb1);
+          float2 m0, m1;
+          m0.x = fminf(fabsf(d0.x), P - fabsf(d0.x)); m0.y = fminf(fabsf(d0.y), P - fabsf(d0.y));
+          m1.x = fminf(fabsf(d1.x), P - fabsf(d1.x)); m1.y = fminf(fabsf(d1.y), P - fabsf(d1.y));
+          acc[i][j] = __ffma2_rn(m0, m0, acc[i][j]);
+          acc[i][j] = __ffma2_rn(m1, m1, acc[i][j]);
+        }
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += acc[i][j].x + acc[i][j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// packed 8x4 micro-tile: 128x64 tile per 256-thread CTA, 64 accumulator registers -> 2 CTAs/SM
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) probe_packed84(const float* __restrict__ g, float* out, float P, int iters) {
+  extern __shared__ __align__(1024) float sm[];
+  float* sa = sm; float* sb = sm + TM * KC;
+  for (int i = threadIdx.x; i < 2 * TM * KC; i += blockDim.x) sm[i] = g[i];
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 1
+    for (int k4 = 0; k4 < KC / 4; k4++) {
+      float4 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) av[i] = *reinterpret_cast<const float4*>(&sa[swz(ty + 16 * i, k4)]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float4 bv = *reinterpret_cast<const float4*>(&sb[swz(tx + 16 * j, k4)]);
+        float2 nb0 = make_float2(-bv.x, -bv.y), nb1 = make_float2(-bv.z, -bv.w);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float2 d0 = __fadd2_rn(make_float2(av[i].x, av[i].y), nb0);
+          float2 d1 = __fadd2_rn(make_float2(av[i].z, av[i].w), nb1);
+          float2 m0, m1;
+          m0.x = fminf(fabsf(d0.x), P - fabsf(d0.x)); m0.y = fminf(fabsf(d0.y), P - fabsf(d0.y));
+          m1.x = fminf(fabsf(d1.x), P - fabsf(d1.x)); m1.y = fminf(fabsf(d1.y), P - fabsf(d1.y));
+          acc[i][j] = __ffma2_rn(m0, m0, acc[i][j]);
+          acc[i][j] = __ffma2_rn(m1, m1, acc[i][j]);
+        }
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s += acc[i][j].x + acc[i][j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void clk_probe(long long* out, int iters) {
+  long long c0 = clock64(); unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  float x = threadIdx.x; for (int i = 0; i < iters; i++) x = fmaf(x, 1.0001f, 0.5f);
+  long long c1 = clock64(); unsigned long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+  if (threadIdx.x == 0) { out[0] = c1 - c0; out[1] = (long long)(t1 - t0); out[2] = (long long)x; }
+}
+
+static double g_pairs_scale = 1.0;
+template <typename K>
+void run(const char* name, K kern, int instr_per_pd, int ctas_per_sm, const float* g, float* out) {
+  int dev; CK(cudaGetDevice(&dev)); cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, dev));
+  int smem = 2 * TM * KC * 4;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  // force residency: pad dynamic smem so that exactly ctas_per_sm fit
+  int dyn = ctas_per_sm == 1 ? 110 * 1024 : smem;
+  int grid = pr.multiProcessorCount * ctas_per_sm;
+  int iters = 2000;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  kern<<<grid, 256, dyn>>>(g, out, 6.2831853f, 10); CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++) {
+    CK(cudaEventRecord(e0)); kern<<<grid, 256, dyn>>>(g, out, 6.2831853f, iters); CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+  }
+  double pd = (double)grid * TM * TM * KC * iters * g_pairs_scale;   // (pair,dim) evaluations
+  printf("%-12s ctas/sm=%d  %.3f ms  %.3e pairdim/s  %.3e lane-instr/s (x%d)  per-SM-clk@1.965GHz: %.1f lane-instr/clk\n",
+         name, ctas_per_sm, best, pd / (best * 1e-3), pd * instr_per_pd / (best * 1e-3), instr_per_pd,
+         pd * instr_per_pd / (best * 1e-3) / pr.multiProcessorCount / 1.965e9);
+}
+
+int main() {
+  float *g, *out; CK(cudaMalloc(&g, 2 * TM * KC * 4)); CK(cudaMalloc(&out, 148 * 4 * 256 * 4));
+  std::vector<float> h(2 * TM * KC); for (auto& x : h) x = (rand() / (float)RAND_MAX - 0.5f) * 6.28f;
+  CK(cudaMemcpy(g, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  { long long* c; CK(cudaMalloc(&c, 24)); clk_probe<<<1, 32>>>(c, 20000000); long long h3[3];
+    CK(cudaMemcpy(h3, c, 24, cudaMemcpyDeviceToHost)); printf("SM clock under light load: %.1f MHz\n", h3[0] * 1e3 / (double)h3[1]); }
+  g_pairs_scale = 0.5;
+  run("packed84/r128", probe_packed84<2>, 4, 2, g, out);
+  run("packed84/r128", probe_packed84<2>, 4, 1, g, out);
+  g_pairs_scale = 1.0;
+  run("ref4/r255", probe<0, 1>, 4, 1, g, out);
+  run("ref4/r128", probe<0, 2>, 4, 1, g, out);
+  run("ref4/r128", probe<0, 2>, 4, 2, g, out);
+  run("packed/r255", probe_packed<1>, 4, 1, g, out);
+  run("allfma4/r255", probe<2, 1>, 4, 1, g, out);
+  run("allfma4/r128", probe<2, 2>, 4, 2, g, out);
+  run("ffma1/r255", probe<3, 1>, 1, 1, g, out);
+  run("ffma1/r128", probe<3, 2>, 1, 2, g, out);
+  run("diff2/r255", probe<4, 1>, 2, 1, g, out);
+  run("diff2/r128", probe<4, 2>, 2, 2, g, out);
+  return 0;
+}
