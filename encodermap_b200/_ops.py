@@ -1,0 +1,298 @@
+"""torch.autograd.Function wrappers around the libemk entry points.
+
+torch is plumbing here: it owns device memory, streams and the autograd graph; every number on
+the hot path is produced by a kernel in libemk.so, reached through ctypes with DLPack tensors.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DL, EmkError, check, f32c, require_cuda, sig_array, stream_of
+
+
+def _empty_like_shape(ref: torch.Tensor, shape, dtype=torch.float32) -> torch.Tensor:
+    return torch.empty(shape, dtype=dtype, device=ref.device)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused sigmoid cost
+# ---------------------------------------------------------------------------------------------------
+def sigmoid_cost_raw(high: torch.Tensor, low: torch.Tensor, periodicity: float, sig: Sequence[float],
+                     tile_range: Optional[Tuple[int, int]] = None, need_grad: bool = True):
+    """One fused launch: returns (loss float64[1] tensor, grad (n,l) float32 or None), both partial over
+    `tile_range` (default: all tiles) and already normalised by n^2."""
+    require_cuda(high, "y_true")
+    require_cuda(low, "y_pred")
+    high, low = f32c(high), f32c(low)
+    if high.dim() != 2 or low.dim() != 2:
+        raise EmkError(-4, f"sigmoid cost needs rank-2 inputs, got {tuple(high.shape)} and {tuple(low.shape)}")
+    n = high.shape[0]
+    if tile_range is None:
+        tile_range = (0, _lib.pair_tile_count(n))
+    loss = torch.empty(1, dtype=torch.float64, device=high.device)
+    grad = torch.empty_like(low) if need_grad else None
+    flags = _lib.EMK_COST_ZERO_OUTPUTS | (0 if need_grad else _lib.EMK_COST_NO_GRAD)
+    with torch.cuda.device(high.device):
+        check(_lib.lib().emk_dl_sigmoid_cost(DL(high), DL(low), float(periodicity), sig_array(sig), tile_range[0], tile_range[1],
+                                             DL(loss), DL(grad), flags, stream_of(high)))
+    return loss, grad
+
+
+class SigmoidCost(torch.autograd.Function):
+    """loss = mean_ij (s_h(D^h_ij) - s_l(D^l_ij))^2 ; forward and dL/d(low) come out of the same launch."""
+
+    @staticmethod
+    def forward(ctx, high, low, periodicity, sig, tile_range, reduce_fn):
+        need_grad = ctx.needs_input_grad[1]
+        loss, grad = sigmoid_cost_raw(high, low, periodicity, sig, tile_range, need_grad)
+        if reduce_fn is not None:  # multi-GPU: sum the partial results of all ranks
+            loss, grad = reduce_fn(loss, grad)
+        ctx.save_for_backward(grad)
+        ctx.low_dtype = low.dtype
+        return loss[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        g = None if grad is None else (grad * grad_output).to(ctx.low_dtype)
+        return None, g, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# distance matrices
+# ---------------------------------------------------------------------------------------------------
+def _slice_count(n: int, start, stop, step) -> int:
+    return len(range(*slice(start, stop, step).indices(n)))
+
+
+def _idx(v) -> int:
+    return _lib.NONE_INDEX if v is None else int(v)
+
+
+class PairwiseDist(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, squared, flat, start, stop, step):
+        require_cuda(x, "positions")
+        x = f32c(x)
+        if x.dim() not in (2, 3):
+            raise EmkError(-4, f"pairwise_dist needs rank 2 or 3, got {tuple(x.shape)}")
+        n_all = x.shape[0] if x.dim() == 2 else x.shape[1]
+        b = 1 if x.dim() == 2 else x.shape[0]
+        n = _slice_count(n_all, start, stop, step)
+        shape = (b, n * (n - 1) // 2) if flat else (b, n, n)
+        out = _empty_like_shape(x, shape)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().emk_dl_pairwise_dist(DL(x), _idx(start), _idx(stop), _idx(step), int(squared), int(flat), DL(out), stream_of(x)))
+        ctx.save_for_backward(x)
+        ctx.args = (squared, flat, start, stop, step)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        squared, flat, start, stop, step = ctx.args
+        grad_out = f32c(grad_out)
+        gx = torch.zeros_like(x)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().emk_dl_pairwise_dist_bwd(DL(x), _idx(start), _idx(stop), _idx(step), int(squared), int(flat), DL(grad_out), DL(gx), stream_of(x)))
+        return gx, None, None, None, None, None
+
+
+def pairwise_dist_periodic_raw(x: torch.Tensor, periodicity: float) -> torch.Tensor:
+    require_cuda(x, "positions")
+    x = f32c(x)
+    assert x.dim() == 2  # the reference asserts rank 2 (encodermap/misc/distances.py:161)
+    out = _empty_like_shape(x, (x.shape[0], x.shape[0]))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_pairwise_dist_periodic(DL(x), float(periodicity), DL(out), stream_of(x)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# elementwise
+# ---------------------------------------------------------------------------------------------------
+class PeriodicDistance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, periodicity):
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            check(_lib.lib().emk_dl_periodic_distance(DL(a), DL(b), float(periodicity), DL(out), stream_of(a)))
+        ctx.save_for_backward(a, b)
+        ctx.periodicity = float(periodicity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b = ctx.saved_tensors
+        grad_out = f32c(grad_out)
+        ga, gb = torch.empty_like(a), torch.empty_like(b)
+        with torch.cuda.device(a.device):
+            check(_lib.lib().emk_dl_periodic_distance_bwd(DL(a), DL(b), ctx.periodicity, DL(grad_out), DL(ga), DL(gb), stream_of(a)))
+        return ga, gb, None
+
+
+class Sigmoid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, sig, a, b):
+        out = torch.empty_like(r)
+        with torch.cuda.device(r.device):
+            check(_lib.lib().emk_dl_sigmoid(DL(r), float(sig), float(a), float(b), DL(out), stream_of(r)))
+        ctx.save_for_backward(r)
+        ctx.params = (float(sig), float(a), float(b))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (r,) = ctx.saved_tensors
+        grad_out = f32c(grad_out)
+        gr = torch.empty_like(r)
+        with torch.cuda.device(r.device):
+            check(_lib.lib().emk_dl_sigmoid_bwd(DL(r), *ctx.params, DL(grad_out), DL(gr), stream_of(r)))
+        return gr, None, None, None
+
+
+class PeriodicInputFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, periodicity):
+        require_cuda(x, "inputs")
+        x = f32c(x)
+        if x.dim() != 2:
+            raise EmkError(-4, f"PeriodicInput needs rank-2 input, got {tuple(x.shape)}")
+        out = _empty_like_shape(x, (x.shape[0], 2 * x.shape[1]))
+        with torch.cuda.device(x.device):
+            check(_lib.lib().emk_dl_periodic_input(DL(x), float(periodicity), DL(out), stream_of(x)))
+        ctx.save_for_backward(x)
+        ctx.periodicity = float(periodicity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        grad_out = f32c(grad_out)
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().emk_dl_periodic_input_bwd(DL(x), ctx.periodicity, DL(grad_out), DL(gx), stream_of(x)))
+        return gx, None
+
+
+def rotation_matrix_raw(axis: torch.Tensor, angle: torch.Tensor) -> torch.Tensor:
+    require_cuda(axis, "axis_unit_vec")
+    axis, angle = f32c(axis), f32c(angle)
+    out = _empty_like_shape(axis, (axis.shape[0], 3, 3))
+    with torch.cuda.device(axis.device):
+        check(_lib.lib().emk_dl_rotation_matrix(DL(axis), DL(angle), DL(out), stream_of(axis)))
+    return out
+
+
+def column_mean_raw(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, "distances")
+    x = f32c(x)
+    out = _empty_like_shape(x, (x.shape[1],))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_column_mean(DL(x), DL(out), stream_of(x)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# back-mapping
+# ---------------------------------------------------------------------------------------------------
+def _lengths_2d(lengths: torch.Tensor, b: int, n: int) -> torch.Tensor:
+    lengths = f32c(lengths)
+    if lengths.dim() == 1:
+        lengths = lengths[None]
+    if lengths.shape[-1] != n - 1 or lengths.shape[0] not in (1, b):
+        raise EmkError(-4, f"lengths must be (1,{n - 1}) or ({b},{n - 1}), got {tuple(lengths.shape)}")
+    return lengths
+
+
+class BackMap(torch.autograd.Function):
+    """(lengths, angles, dihedrals) -> xyz with the exact VJP from force/torque prefix sums."""
+
+    @staticmethod
+    def forward(ctx, lengths, angles, dihedrals):
+        require_cuda(angles, "angles")
+        angles, dihedrals = f32c(angles), f32c(dihedrals)
+        b, n = angles.shape[0], angles.shape[1] + 2
+        lengths = _lengths_2d(lengths, b, n)
+        xyz = _empty_like_shape(angles, (b, n, 3))
+        with torch.cuda.device(angles.device):
+            check(_lib.lib().emk_dl_backmap(DL(lengths), DL(angles), DL(dihedrals), DL(xyz), stream_of(angles)))
+        ctx.save_for_backward(lengths, angles, xyz)
+        return xyz
+
+    @staticmethod
+    def backward(ctx, grad_xyz):
+        lengths, angles, xyz = ctx.saved_tensors
+        grad_xyz = f32c(grad_xyz)
+        b, n = xyz.shape[0], xyz.shape[1]
+        need_l, need_a, need_d = ctx.needs_input_grad
+        ga = torch.empty_like(angles) if need_a else None
+        gd = _empty_like_shape(xyz, (b, n - 3)) if need_d else None
+        gl = _empty_like_shape(xyz, (b, n - 1)) if need_l else None
+        with torch.cuda.device(xyz.device):
+            check(_lib.lib().emk_dl_backmap_bwd(DL(lengths), DL(angles), DL(xyz), DL(grad_xyz), DL(ga), DL(gd), DL(gl), stream_of(xyz)))
+        if gl is not None and lengths.shape[0] == 1:
+            gl = gl.sum(dim=0, keepdim=True)  # shared bond lengths: every frame contributes
+        return gl, ga, gd
+
+
+class ChainInPlane(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lengths, angles):
+        require_cuda(angles, "angles")
+        angles = f32c(angles)
+        b, n = angles.shape[0], angles.shape[1] + 2
+        lengths = _lengths_2d(lengths, b, n)
+        xyz = _empty_like_shape(angles, (b, n, 3))
+        with torch.cuda.device(angles.device):
+            check(_lib.lib().emk_dl_chain_in_plane(DL(lengths), DL(angles), DL(xyz), stream_of(angles)))
+        ctx.save_for_backward(lengths, angles)
+        return xyz
+
+    @staticmethod
+    def backward(ctx, grad_xyz):
+        lengths, angles = ctx.saved_tensors
+        grad_xyz = f32c(grad_xyz)
+        b, n = angles.shape[0], angles.shape[1] + 2
+        need_l, need_a = ctx.needs_input_grad
+        ga = torch.empty_like(angles) if need_a else None
+        gl = _empty_like_shape(angles, (b, n - 1)) if need_l else None
+        with torch.cuda.device(angles.device):
+            check(_lib.lib().emk_dl_chain_in_plane_bwd(DL(lengths), DL(angles), DL(grad_xyz), DL(ga), DL(gl), stream_of(angles)))
+        if gl is not None and lengths.shape[0] == 1:
+            gl = gl.sum(dim=0, keepdim=True)
+        return gl, ga
+
+
+class DihedralsToCartesian(torch.autograd.Function):
+    """Arbitrary start chain.  Differentiable w.r.t. the dihedrals; the gradient w.r.t. the start chain
+    is not implemented (in the models the chain comes from chain_in_plane and the fused BackMap op
+    carries that gradient)."""
+
+    @staticmethod
+    def forward(ctx, dihedrals, cartesian, one_way):
+        require_cuda(dihedrals, "dihedrals")
+        dihedrals, cartesian = f32c(dihedrals), f32c(cartesian)
+        if cartesian.requires_grad:
+            raise NotImplementedError("dihedrals_to_cartesian: gradient w.r.t. the start chain is not implemented; "
+                                      "use BackMapLayer / back_map for the differentiable composition")
+        b, n = dihedrals.shape[0], dihedrals.shape[1] + 3
+        xyz = _empty_like_shape(dihedrals, (b, n, 3))
+        with torch.cuda.device(dihedrals.device):
+            check(_lib.lib().emk_dl_dihedrals_to_cartesian(DL(dihedrals), DL(cartesian), int(one_way), DL(xyz), stream_of(dihedrals)))
+        ctx.save_for_backward(xyz)
+        ctx.one_way = int(one_way)
+        return xyz
+
+    @staticmethod
+    def backward(ctx, grad_xyz):
+        (xyz,) = ctx.saved_tensors
+        grad_xyz = f32c(grad_xyz)
+        gd = _empty_like_shape(xyz, (xyz.shape[0], xyz.shape[1] - 3))
+        with torch.cuda.device(xyz.device):
+            check(_lib.lib().emk_dl_dihedrals_to_cartesian_bwd(DL(xyz), DL(grad_xyz), ctx.one_way, DL(gd), stream_of(xyz)))
+        return gd, None, None

@@ -1,0 +1,669 @@
+// Back-mapping kernels for sm_100a: internal coordinates -> Cartesian as an SE(3) prefix product
+// along the atom chain, and the exact VJP from prefix sums of force and torque.
+//
+// One warp owns one frame.  The chain is cut into per-lane contiguous chunks; each lane multiplies its
+// chunk's transforms sequentially (pass 1), the chunk aggregates are combined with a shuffle scan, and
+// each lane maps its chunk-local results through its prefix (pass 2).  All arithmetic is float64
+// (inputs/outputs float32): in float32 the orientation error random-walks along the chain and exceeds
+// the 1e-4 nm parity budget beyond ~100 residues; B200's FP64 pipe runs at half the
+// FP32 rate, so the kernel stays within ~2x of its HBM roofline.
+//
+// Forward formulations (tools/proto_backmap.py checks all of them against the oracle):
+//   * emk_backmap   : BackMapLayer.  NeRF placement from (L, theta, phi) with LOCAL transforms
+//                     R <- R Rx(phi) Rz(pi - theta),  p <- p + L R e_x, built outward in both
+//                     directions from the three middle atoms, which sit at their planar-chain positions.
+//   * emk_dihedrals_to_cartesian : arbitrary start chain.  A_i = rotation by dihedral_i about the bond
+//                     (t_{i+1}, t_{i+2}) of the START chain, C_i = C_{i-1} o A_i, out_k = C_{k-3}(start_k).
+//   * emk_chain_in_plane : SE(2) prefix product (alternating-sign turns) + prefix sum of bond vectors.
+// Backward: for every internal coordinate the downstream body moves rigidly (twist about a bond, hinge
+// about the normal of a bond angle, slide along a bond; left of the anchor the whole molecule also
+// follows the planar chain), so each gradient is <axis, torque> or <direction, force> of a prefix sum.
+#include "emk_common.cuh"
+
+namespace emk {
+
+constexpr double kPi = 3.14159265358979323846;
+
+// ---- float64 sin/cos of a float32-exact argument, ~1e-14 absolute -----------------------------------
+__device__ __forceinline__ void sincos_d(double x, double* s, double* c) {
+  const double q = rint(x * 0.63661977236758134308);  // 2/pi
+  double r = fma(-q, 1.5707963267948966, x);
+  r = fma(-q, 6.123233995736766e-17, r);
+  const double r2 = r * r;
+  double sp = 1.6059043836821613e-10;                 // 1/13!
+  sp = fma(sp, r2, -2.5052108385441720e-08);          // -1/11!
+  sp = fma(sp, r2, 2.7557319223985893e-06);           // 1/9!
+  sp = fma(sp, r2, -1.9841269841269841e-04);          // -1/7!
+  sp = fma(sp, r2, 8.3333333333333332e-03);           // 1/5!
+  sp = fma(sp, r2, -1.6666666666666666e-01);          // -1/3!
+  const double sr = fma(sp * r2, r, r);
+  double cp = -1.1470745597729725e-11;                // -1/14!
+  cp = fma(cp, r2, 2.0876756987868100e-09);           // 1/12!
+  cp = fma(cp, r2, -2.7557319223985888e-07);          // -1/10!
+  cp = fma(cp, r2, 2.4801587301587302e-05);           // 1/8!
+  cp = fma(cp, r2, -1.3888888888888889e-03);          // -1/6!
+  cp = fma(cp, r2, 4.1666666666666664e-02);           // 1/4!
+  cp = fma(cp, r2, -0.5);
+  const double cr = fma(cp, r2, 1.0);
+  const int iq = (int)q & 3;
+  const double ss = (iq & 1) ? cr : sr;
+  const double cc = (iq & 1) ? sr : cr;
+  *s = (iq & 2) ? -ss : ss;
+  *c = ((iq + 1) & 2) ? -cc : cc;
+}
+
+// ---- SE(3) element: x -> R x + p (column vectors), R row-major ---------------------------------------
+struct Se3 {
+  double r[9];
+  double p[3];
+};
+
+__device__ __forceinline__ void se3_identity(Se3& a) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) a.r[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  a.p[0] = a.p[1] = a.p[2] = 0.0;
+}
+
+// out = a o b  (apply b first)
+__device__ __forceinline__ Se3 se3_mul(const Se3& a, const Se3& b) {
+  Se3 o;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) o.r[3 * i + j] = a.r[3 * i] * b.r[j] + a.r[3 * i + 1] * b.r[3 + j] + a.r[3 * i + 2] * b.r[6 + j];
+    o.p[i] = a.r[3 * i] * b.p[0] + a.r[3 * i + 1] * b.p[1] + a.r[3 * i + 2] * b.p[2] + a.p[i];
+  }
+  return o;
+}
+
+__device__ __forceinline__ Se3 se3_shfl_up(const Se3& a, int delta, int width) {
+  Se3 o;
+#pragma unroll
+  for (int i = 0; i < 9; i++) o.r[i] = __shfl_up_sync(0xffffffffu, a.r[i], delta, width);
+#pragma unroll
+  for (int i = 0; i < 3; i++) o.p[i] = __shfl_up_sync(0xffffffffu, a.p[i], delta, width);
+  return o;
+}
+
+// exclusive scan over `width` consecutive lanes (width = 16 or 32): lane q gets T_0 o ... o T_{q-1}
+__device__ __forceinline__ Se3 se3_exclusive_scan(Se3 t, int lane_in_group, int width) {
+  for (int d = 1; d < width; d <<= 1) {
+    Se3 up = se3_shfl_up(t, d, width);
+    if (lane_in_group >= d) t = se3_mul(up, t);
+  }
+  Se3 ex = se3_shfl_up(t, 1, width);
+  if (lane_in_group == 0) se3_identity(ex);
+  return ex;
+}
+
+// NeRF step: R <- R Rx(phi) Rz(g), p <- p + L R e_x     (cw,sw = cos/sin phi; cg,sg = cos/sin g)
+__device__ __forceinline__ void nerf_step(Se3& f, double cw, double sw, double cg, double sg, double L) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double x = f.r[3 * i], y = f.r[3 * i + 1], z = f.r[3 * i + 2];
+    const double y1 = y * cw + z * sw;   // column y of R Rx
+    const double z1 = z * cw - y * sw;   // column z of R Rx
+    const double x2 = x * cg + y1 * sg;  // column x of (R Rx) Rz
+    const double y2 = y1 * cg - x * sg;
+    f.r[3 * i] = x2;
+    f.r[3 * i + 1] = y2;
+    f.r[3 * i + 2] = z1;
+    f.p[i] = fma(L, x2, f.p[i]);
+  }
+}
+
+// ---- SE(2) element for the planar chain: unit complex rotation + displacement ----------------------
+struct Se2 {
+  double c, s, x, y;
+};
+__device__ __forceinline__ Se2 se2_mul(const Se2& a, const Se2& b) {  // a o b (b first, in a's frame)
+  Se2 o;
+  o.c = a.c * b.c - a.s * b.s;
+  o.s = a.c * b.s + a.s * b.c;
+  o.x = a.x + a.c * b.x - a.s * b.y;
+  o.y = a.y + a.s * b.x + a.c * b.y;
+  return o;
+}
+__device__ __forceinline__ Se2 se2_shfl_up(const Se2& a, int d) {
+  Se2 o;
+  o.c = __shfl_up_sync(0xffffffffu, a.c, d);
+  o.s = __shfl_up_sync(0xffffffffu, a.s, d);
+  o.x = __shfl_up_sync(0xffffffffu, a.x, d);
+  o.y = __shfl_up_sync(0xffffffffu, a.y, d);
+  return o;
+}
+__device__ __forceinline__ Se2 se2_shfl(const Se2& a, int src) {
+  Se2 o;
+  o.c = __shfl_sync(0xffffffffu, a.c, src);
+  o.s = __shfl_sync(0xffffffffu, a.s, src);
+  o.x = __shfl_sync(0xffffffffu, a.x, src);
+  o.y = __shfl_sync(0xffffffffu, a.y, src);
+  return o;
+}
+// inclusive scan over the 32 lanes; *excl receives the exclusive prefix
+__device__ __forceinline__ Se2 se2_scan(Se2 t, int lane, Se2* excl) {
+  for (int d = 1; d < 32; d <<= 1) {
+    Se2 up = se2_shfl_up(t, d);
+    if (lane >= d) t = se2_mul(up, t);
+  }
+  Se2 ex = se2_shfl_up(t, 1);
+  if (lane == 0) ex = Se2{1.0, 0.0, 0.0, 0.0};
+  *excl = ex;
+  return t;
+}
+
+// planar bond k: position advances by L_k along the current direction, then the direction turns by
+// -(-1)^k (pi - theta_k)  (encodermap_tf1/backmapping.py:105-110; for the last bond there is no turn)
+__device__ __forceinline__ void planar_step(Se2& t, double L, bool has_turn, float theta, int k) {
+  t.x = fma(L, t.c, t.x);
+  t.y = fma(L, t.s, t.y);
+  if (has_turn) {
+    double st, ct;
+    sincos_d((double)theta, &st, &ct);
+    // turn angle w = -(-1)^k (pi - theta): cos w = -cos(theta), sin w = -(-1)^k sin(theta)
+    const double cw = -ct, sw = (k & 1) ? st : -st;
+    const double c2 = t.c * cw - t.s * sw, s2 = t.c * sw + t.s * cw;
+    t.c = c2;
+    t.s = s2;
+  }
+}
+
+__device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int count, int lane) {
+  for (int i = lane; i < count; i += 32) dst[i] = src[i];
+}
+
+// ====================================================================================================
+// chain_in_plane forward
+// ====================================================================================================
+__global__ void chain_in_plane_kernel(const float* __restrict__ lengths, int64_t lstride, const float* __restrict__ angles,
+                                      int64_t b, int n, float* __restrict__ xyz) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
+  if (frame >= b) return;
+  const int per_warp = (n - 1) + (n - 2) + 3 * n;
+  float* sL = smem + (size_t)warp * per_warp;
+  float* sA = sL + (n - 1);
+  float* sO = sA + (n - 2);
+  stage_in(sL, lengths + frame * lstride, n - 1, lane);
+  stage_in(sA, angles + frame * (int64_t)(n - 2), n - 2, lane);
+  __syncwarp();
+  const int nb = n - 1;                 // bonds
+  const int cs = (nb + 31) / 32;
+  const int k0 = lane * cs, k1 = min(nb, k0 + cs);
+  Se2 t{1.0, 0.0, 0.0, 0.0};
+  for (int k = k0; k < k1; k++) planar_step(t, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+  Se2 ex;
+  se2_scan(t, lane, &ex);
+  Se2 run = ex;
+  if (lane == 0) {
+    sO[0] = 0.f;
+    sO[1] = 0.f;
+    sO[2] = 0.f;
+  }
+  for (int k = k0; k < k1; k++) {
+    Se2 step{1.0, 0.0, 0.0, 0.0};
+    planar_step(step, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+    run = se2_mul(run, step);
+    sO[3 * (k + 1)] = (float)run.x;
+    sO[3 * (k + 1) + 1] = (float)run.y;
+    sO[3 * (k + 1) + 2] = 0.f;
+  }
+  __syncwarp();
+  float* dst = xyz + frame * (int64_t)(3 * n);
+  for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
+}
+
+// ====================================================================================================
+// BackMapLayer forward (NeRF from the planar anchor)
+// ====================================================================================================
+__global__ void backmap_fwd_kernel(const float* __restrict__ lengths, int64_t lstride, const float* __restrict__ angles,
+                                   const float* __restrict__ dihedrals, int64_t b, int n, float* __restrict__ xyz) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
+  if (frame >= b) return;
+  const int per_warp = (n - 1) + (n - 2) + (n - 3) + 3 * n;
+  float* sL = smem + (size_t)warp * per_warp;
+  float* sA = sL + (n - 1);
+  float* sD = sA + (n - 2);
+  float* sO = sD + (n - 3);
+  stage_in(sL, lengths + frame * lstride, n - 1, lane);
+  stage_in(sA, angles + frame * (int64_t)(n - 2), n - 2, lane);
+  stage_in(sD, dihedrals + frame * (int64_t)(n - 3), n - 3, lane);
+  __syncwarp();
+
+  const int s = n / 2;
+  // ---- anchor: planar positions of atoms s-1, s, s+1 (SE(2) reduction over bonds 0..s-2, then 2 steps)
+  Se2 head{1.0, 0.0, 0.0, 0.0};
+  {
+    const int nb = s - 1;  // bonds 0 .. s-2 bring us to atom s-1 with direction psi_{s-1}
+    const int cs = (nb + 31) / 32;
+    const int k0 = min(nb, lane * cs), k1 = min(nb, k0 + cs);
+    Se2 t{1.0, 0.0, 0.0, 0.0};
+    for (int k = k0; k < k1; k++) planar_step(t, (double)sL[k], true, sA[k], k);
+    Se2 ex;
+    Se2 inc = se2_scan(t, lane, &ex);
+    head = se2_shfl(inc, 31);
+  }
+  // head: (c,s) = direction of bond s-1, (x,y) = c_{s-1}
+  const double dm_c = head.c, dm_s = head.s;          // direction of bond s-1
+  const double am_x = head.x, am_y = head.y;          // c_{s-1}
+  Se2 mid = head;
+  planar_step(mid, (double)sL[s - 1], true, sA[s - 1], s - 1);   // -> c_s, direction of bond s
+  const double a0_x = mid.x, a0_y = mid.y;
+  const double dp_c = mid.c, dp_s = mid.s;
+  const double ap_x = fma((double)sL[s], dp_c, a0_x), ap_y = fma((double)sL[s], dp_s, a0_y);  // c_{s+1}
+  const double crs = dm_c * dp_s - dm_s * dp_c;       // z of (bond s-1) x (bond s)
+  const double zs = crs >= 0.0 ? 1.0 : -1.0;
+  if (lane == 0) {
+    sO[3 * (s - 1)] = (float)am_x; sO[3 * (s - 1) + 1] = (float)am_y; sO[3 * (s - 1) + 2] = 0.f;
+    sO[3 * s] = (float)a0_x;       sO[3 * s + 1] = (float)a0_y;       sO[3 * s + 2] = 0.f;
+    sO[3 * (s + 1)] = (float)ap_x; sO[3 * (s + 1) + 1] = (float)ap_y; sO[3 * (s + 1) + 2] = 0.f;
+  }
+
+  // ---- two half-warps: lanes 0-15 build the left side (atoms s-2 .. 0), lanes 16-31 the right side
+  const int side = lane >> 4, q = lane & 15;
+  const int steps = side == 0 ? (s - 1) : (n - s - 2);
+  int cs = (steps + 15) / 16;
+  cs |= 1;  // odd chunk length => conflict-free strided shared-memory writes
+  const int i0 = min(steps, q * cs), i1 = min(steps, i0 + cs);
+
+  Se3 f;
+  se3_identity(f);
+  for (int i = i0; i < i1; i++) {
+    int k, kd, ka, kl;
+    if (side == 0) { k = s - 2 - i; kd = k; ka = k; kl = k; }
+    else           { k = s + 2 + i; kd = k - 3; ka = k - 2; kl = k - 1; }
+    double sw, cw, sg, cg;
+    sincos_d((double)sD[kd], &sw, &cw);
+    sincos_d((double)sA[ka], &sg, &cg);
+    nerf_step(f, cw, sw, -cg, sg, (double)sL[kl]);   // g = pi - theta: cos g = -cos theta, sin g = sin theta
+    sO[3 * k] = (float)f.p[0];
+    sO[3 * k + 1] = (float)f.p[1];
+    sO[3 * k + 2] = (float)f.p[2];
+  }
+  Se3 pre = se3_exclusive_scan(f, q, 16);
+  // anchor frame of this side: x along the last anchored bond, z = +-e_z, y = z x x, origin at the last anchor atom
+  Se3 g0;
+  {
+    double xx, xy, zz, ox, oy;
+    if (side == 0) { xx = -dm_c; xy = -dm_s; zz = -zs; ox = am_x; oy = am_y; }
+    else           { xx = dp_c;  xy = dp_s;  zz = zs;  ox = ap_x; oy = ap_y; }
+    g0.r[0] = xx; g0.r[1] = -zz * xy; g0.r[2] = 0.0;
+    g0.r[3] = xy; g0.r[4] = zz * xx;  g0.r[5] = 0.0;
+    g0.r[6] = 0.0; g0.r[7] = 0.0;     g0.r[8] = zz;
+    g0.p[0] = ox; g0.p[1] = oy; g0.p[2] = 0.0;
+  }
+  pre = se3_mul(g0, pre);
+  for (int i = i0; i < i1; i++) {
+    const int k = side == 0 ? s - 2 - i : s + 2 + i;
+    const double lx = sO[3 * k], ly = sO[3 * k + 1], lz = sO[3 * k + 2];
+    sO[3 * k] = (float)(pre.r[0] * lx + pre.r[1] * ly + pre.r[2] * lz + pre.p[0]);
+    sO[3 * k + 1] = (float)(pre.r[3] * lx + pre.r[4] * ly + pre.r[5] * lz + pre.p[1]);
+    sO[3 * k + 2] = (float)(pre.r[6] * lx + pre.r[7] * ly + pre.r[8] * lz + pre.p[2]);
+  }
+  __syncwarp();
+  float* dst = xyz + frame * (int64_t)(3 * n);
+  for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
+}
+
+// ====================================================================================================
+// dihedrals_to_cartesian on an arbitrary start chain (two-sided or one-way)
+// ====================================================================================================
+__device__ __forceinline__ void load3(const float* p, double* v) {
+  v[0] = p[0];
+  v[1] = p[1];
+  v[2] = p[2];
+}
+
+__global__ void d2c_general_kernel(const float* __restrict__ dihedrals, const float* __restrict__ chain, int64_t cstride,
+                                   int64_t b, int n, int one_way, float* __restrict__ xyz) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
+  if (frame >= b) return;
+  const int per_warp = (n - 3) + 3 * n;
+  float* sD = smem + (size_t)warp * per_warp;
+  float* sO = sD + (n - 3);
+  stage_in(sD, dihedrals + frame * (int64_t)(n - 3), n - 3, lane);
+  stage_in(sO, chain + frame * cstride, 3 * n, lane);
+  __syncwarp();
+
+  // side description: atom of side-local index m is a0 + dir*m; dihedral of step i is d0 + dir*i
+  int side, q, width, steps, a0, dir, d0;
+  const int s = n / 2;
+  if (one_way) {
+    side = 0; q = lane; width = 32; steps = n - 3; a0 = 0; dir = 1; d0 = 0;
+  } else {
+    side = lane >> 4; q = lane & 15; width = 16;
+    if (side == 0) { steps = s - 1; a0 = s + 1; dir = -1; d0 = s - 2; }
+    else           { steps = n - s - 2; a0 = s - 1; dir = 1; d0 = s - 1; }
+  }
+  int cs = (steps + width - 1) / width;
+  cs |= 1;
+  const int i0 = min(steps, q * cs), i1 = min(steps, i0 + cs);
+  // originals of the two atoms before this lane's first moved atom (a neighbour lane overwrites them)
+  double pa[3] = {0, 0, 0}, pb[3] = {0, 0, 0};
+  if (i0 < i1) {
+    load3(sO + 3 * (a0 + dir * (i0 + 1)), pa);
+    load3(sO + 3 * (a0 + dir * (i0 + 2)), pb);
+  }
+  __syncwarp();
+  Se3 f;
+  se3_identity(f);
+  for (int i = i0; i < i1; i++) {
+    // A_i: rotate by +dihedral_i about the axis pa -> pb through pb (column-vector convention; the
+    // reference negates the angle and multiplies row vectors on the right, misc/backmapping.py:1896-1909)
+    double ux = pb[0] - pa[0], uy = pb[1] - pa[1], uz = pb[2] - pa[2];
+    const double inv = rsqrt(ux * ux + uy * uy + uz * uz);
+    ux *= inv; uy *= inv; uz *= inv;
+    double sw, cw;
+    sincos_d((double)sD[d0 + dir * i], &sw, &cw);
+    const double oc = 1.0 - cw;
+    Se3 a;
+    a.r[0] = cw + oc * ux * ux;      a.r[1] = oc * ux * uy - sw * uz; a.r[2] = oc * ux * uz + sw * uy;
+    a.r[3] = oc * uy * ux + sw * uz; a.r[4] = cw + oc * uy * uy;      a.r[5] = oc * uy * uz - sw * ux;
+    a.r[6] = oc * uz * ux - sw * uy; a.r[7] = oc * uz * uy + sw * ux; a.r[8] = cw + oc * uz * uz;
+#pragma unroll
+    for (int r = 0; r < 3; r++) a.p[r] = pb[r] - (a.r[3 * r] * pb[0] + a.r[3 * r + 1] * pb[1] + a.r[3 * r + 2] * pb[2]);
+    f = se3_mul(f, a);
+    const int k = a0 + dir * (i + 3);
+    double pc[3];
+    load3(sO + 3 * k, pc);
+#pragma unroll
+    for (int r = 0; r < 3; r++) sO[3 * k + r] = (float)(f.r[3 * r] * pc[0] + f.r[3 * r + 1] * pc[1] + f.r[3 * r + 2] * pc[2] + f.p[r]);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { pa[r] = pb[r]; pb[r] = pc[r]; }
+  }
+  Se3 pre = se3_exclusive_scan(f, q, width);
+  for (int i = i0; i < i1; i++) {
+    const int k = a0 + dir * (i + 3);
+    const double lx = sO[3 * k], ly = sO[3 * k + 1], lz = sO[3 * k + 2];
+    sO[3 * k] = (float)(pre.r[0] * lx + pre.r[1] * ly + pre.r[2] * lz + pre.p[0]);
+    sO[3 * k + 1] = (float)(pre.r[3] * lx + pre.r[4] * ly + pre.r[5] * lz + pre.p[1]);
+    sO[3 * k + 2] = (float)(pre.r[6] * lx + pre.r[7] * ly + pre.r[8] * lz + pre.p[2]);
+  }
+  __syncwarp();
+  float* dst = xyz + frame * (int64_t)(3 * n);
+  for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
+}
+
+// ====================================================================================================
+// backward: force / torque prefix sums
+// ====================================================================================================
+struct Wrench {
+  double f[3];
+  double t[3];
+};
+__device__ __forceinline__ void wrench_add(Wrench& a, const Wrench& b) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    a.f[i] += b.f[i];
+    a.t[i] += b.t[i];
+  }
+}
+__device__ __forceinline__ Wrench wrench_shfl_up(const Wrench& a, int d) {
+  Wrench o;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    o.f[i] = __shfl_up_sync(0xffffffffu, a.f[i], d);
+    o.t[i] = __shfl_up_sync(0xffffffffu, a.t[i], d);
+  }
+  return o;
+}
+__device__ __forceinline__ Wrench wrench_bcast(const Wrench& a, int src) {
+  Wrench o;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    o.f[i] = __shfl_sync(0xffffffffu, a.f[i], src);
+    o.t[i] = __shfl_sync(0xffffffffu, a.t[i], src);
+  }
+  return o;
+}
+// <axis, torque about pivot> = axis . (t - piv x f)
+__device__ __forceinline__ double axial_torque(const double* ax, const Wrench& w, const double* piv) {
+  const double cx = piv[1] * w.f[2] - piv[2] * w.f[1];
+  const double cy = piv[2] * w.f[0] - piv[0] * w.f[2];
+  const double cz = piv[0] * w.f[1] - piv[1] * w.f[0];
+  return ax[0] * (w.t[0] - cx) + ax[1] * (w.t[1] - cy) + ax[2] * (w.t[2] - cz);
+}
+__device__ __forceinline__ void unit_diff(const double* a, const double* b, double* u) {  // unit(b - a)
+  const double x = b[0] - a[0], y = b[1] - a[1], z = b[2] - a[2];
+  const double inv = rsqrt(x * x + y * y + z * z);
+  u[0] = x * inv; u[1] = y * inv; u[2] = z * inv;
+}
+__device__ __forceinline__ void unit_normal(const double* a, const double* m, const double* c, double* nrm) {
+  // normalised (m - a) x (c - m)
+  const double ux = m[0] - a[0], uy = m[1] - a[1], uz = m[2] - a[2];
+  const double vx = c[0] - m[0], vy = c[1] - m[1], vz = c[2] - m[2];
+  const double x = uy * vz - uz * vy, y = uz * vx - ux * vz, z = ux * vy - uy * vx;
+  const double inv = rsqrt(x * x + y * y + z * z);
+  nrm[0] = x * inv; nrm[1] = y * inv; nrm[2] = z * inv;
+}
+
+
+__global__ void backmap_bwd_kernel(const BwdParams p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
+  if (frame >= p.b) return;
+  const int n = p.n;
+  const bool need_planar = p.planar || ((p.grad_angles || p.grad_lengths) && p.mid > 1);
+  const int per_warp = 6 * n + (n - 1) + (n - 2);
+  float* sX = smem + (size_t)warp * per_warp;
+  float* sG = sX + 3 * n;
+  float* sL = sG + 3 * n;
+  float* sA = sL + (n - 1);
+  stage_in(sG, p.grad_xyz + frame * (int64_t)(3 * n), 3 * n, lane);
+  if (!p.planar) stage_in(sX, p.xyz + frame * (int64_t)(3 * n), 3 * n, lane);
+  if (need_planar) {
+    stage_in(sL, p.lengths + frame * p.lstride, n - 1, lane);
+    stage_in(sA, p.angles + frame * (int64_t)(n - 2), n - 2, lane);
+  }
+  __syncwarp();
+
+  const int ca = (n + 31) / 32;                 // atoms per lane
+  const int k0 = min(n, lane * ca), k1 = min(n, k0 + ca);
+
+  // planar chain prefix per lane: state BEFORE bond k0 (direction of bond k0, position of atom k0)
+  Se2 pl_ex{1.0, 0.0, 0.0, 0.0};
+  if (need_planar) {
+    Se2 t{1.0, 0.0, 0.0, 0.0};
+    for (int k = k0; k < k1 && k < n - 1; k++) planar_step(t, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+    se2_scan(t, lane, &pl_ex);
+    if (p.planar) {
+      // recompute the planar coordinates: they are the "final" coordinates of chain_in_plane
+      Se2 run = pl_ex;
+      if (lane == 0) { sX[0] = 0.f; sX[1] = 0.f; sX[2] = 0.f; }
+      for (int k = k0; k < k1 && k < n - 1; k++) {
+        Se2 st{1.0, 0.0, 0.0, 0.0};
+        planar_step(st, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+        run = se2_mul(run, st);
+        sX[3 * (k + 1)] = (float)run.x; sX[3 * (k + 1) + 1] = (float)run.y; sX[3 * (k + 1) + 2] = 0.f;
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- pass 1: per-lane wrench, warp scan
+  Wrench w{};
+  for (int k = k0; k < k1; k++) {
+    double x[3], g[3];
+    load3(sX + 3 * k, x);
+    load3(sG + 3 * k, g);
+    w.f[0] += g[0]; w.f[1] += g[1]; w.f[2] += g[2];
+    w.t[0] += x[1] * g[2] - x[2] * g[1];
+    w.t[1] += x[2] * g[0] - x[0] * g[2];
+    w.t[2] += x[0] * g[1] - x[1] * g[0];
+  }
+  Wrench inc = w;
+  for (int d = 1; d < 32; d <<= 1) {
+    Wrench up = wrench_shfl_up(inc, d);
+    if (lane >= d) wrench_add(inc, up);
+  }
+  const Wrench tot = wrench_bcast(inc, 31);
+  Wrench lo = wrench_shfl_up(inc, 1);            // sum over atoms < k0
+  if (lane == 0) lo = Wrench{};
+
+  float* gA = p.grad_angles ? p.grad_angles + frame * (int64_t)(n - 2) : nullptr;
+  float* gD = p.grad_dihedrals ? p.grad_dihedrals + frame * (int64_t)(n - 3) : nullptr;
+  float* gL = p.grad_lengths ? p.grad_lengths + frame * (int64_t)(n - 1) : nullptr;
+  const double ez[3] = {0.0, 0.0, 1.0};
+
+  // ---- pass 2: walk the chunk; after adding atom k, `lo` = sum over atoms <= k, hi = tot - lo
+  Se2 pl = pl_ex;  // planar state before bond k: (c,s) = direction of bond k, (x,y) = c_k
+  for (int k = k0; k < k1; k++) {
+    double xk[3], g[3];
+    load3(sX + 3 * k, xk);
+    load3(sG + 3 * k, g);
+    lo.f[0] += g[0]; lo.f[1] += g[1]; lo.f[2] += g[2];
+    lo.t[0] += xk[1] * g[2] - xk[2] * g[1];
+    lo.t[1] += xk[2] * g[0] - xk[0] * g[2];
+    lo.t[2] += xk[0] * g[1] - xk[1] * g[0];
+    Wrench hi;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { hi.f[i] = tot.f[i] - lo.f[i]; hi.t[i] = tot.t[i] - lo.t[i]; }
+
+    double xm[3] = {0, 0, 0}, xp[3] = {0, 0, 0}, xpp[3] = {0, 0, 0};
+    if (k >= 1) load3(sX + 3 * (k - 1), xm);
+    if (k + 1 < n) load3(sX + 3 * (k + 1), xp);
+    if (k + 2 < n) load3(sX + 3 * (k + 2), xpp);
+
+    // planar direction of bond k and planar position of atom k+1 (for the left-of-anchor terms)
+    double pdir[3] = {pl.c, pl.s, 0.0};
+    double cnext[3] = {0, 0, 0};
+    if (need_planar && k < n - 1) {
+      planar_step(pl, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+      cnext[0] = pl.x; cnext[1] = pl.y;
+    }
+
+    // dihedrals: cut between atoms k and k+1
+    if (gD) {
+      if (k - 2 >= p.dr0 && k - 2 <= n - 4) {          // right-side twist d = k-2: atoms >= k+1 about (x_{k-1} -> x_k) through x_k
+        double u[3];
+        unit_diff(xm, xk, u);
+        gD[k - 2] = (float)axial_torque(u, hi, xk);
+      }
+      if (k < p.dr0 && k <= n - 4) {                   // left-side twist d = k: atoms <= k about (x_{k+2} -> x_{k+1}) through x_{k+1}
+        double u[3];
+        unit_diff(xp, xpp, u);
+        gD[k] = (float)(-axial_torque(u, lo, xp));
+      }
+    }
+    // angles
+    if (gA) {
+      if (k >= 1 && k <= n - 2 && k >= p.mid) {        // hinge at atom k (angle k-1): atoms >= k+1 move
+        double nr[3];
+        if (p.planar) { nr[0] = 0; nr[1] = 0; nr[2] = ((k - 1) & 1) ? 1.0 : -1.0; }
+        else unit_normal(xm, xk, xp, nr);
+        gA[k - 1] = (float)(-axial_torque(nr, hi, xk));
+      }
+      if (k + 1 < p.mid && k <= n - 3) {               // hinge at atom h = k+1 (angle k), left of the anchor
+        double nr[3];
+        unit_normal(xk, xp, xpp, nr);
+        const double sgn = (k & 1) ? -1.0 : 1.0;
+        gA[k] = (float)(sgn * axial_torque(ez, tot, cnext) + axial_torque(nr, lo, xp));
+      }
+    }
+    // bond lengths: bond k joins atoms k, k+1
+    if (gL && k < n - 1) {
+      double bd[3];
+      if (p.planar) { bd[0] = pdir[0]; bd[1] = pdir[1]; bd[2] = 0.0; }
+      else unit_diff(xk, xp, bd);
+      if (k >= p.mid - 1) {
+        gL[k] = (float)(bd[0] * hi.f[0] + bd[1] * hi.f[1] + bd[2] * hi.f[2]);
+      } else {
+        gL[k] = (float)(pdir[0] * tot.f[0] + pdir[1] * tot.f[1] - (bd[0] * lo.f[0] + bd[1] * lo.f[1] + bd[2] * lo.f[2]));
+      }
+    }
+  }
+}
+
+// ====================================================================================================
+// host launchers
+// ====================================================================================================
+static int pick_warps(size_t floats_per_warp, size_t shared_floats, int* warps, size_t* smem_bytes) {
+  const size_t budget = 200 * 1024;
+  size_t per = floats_per_warp * sizeof(float);
+  size_t sh = shared_floats * sizeof(float);
+  if (per + sh > 227 * 1024 - 1024) return fail(EMK_E_UNSUPPORTED, "chain too long for one warp's shared-memory staging (%zu bytes)", per + sh);
+  int w = (int)((budget - sh) / per);
+  if (w < 1) w = 1;
+  if (w > 8) w = 8;
+  *warps = w;
+  *smem_bytes = (size_t)w * per + sh;
+  return EMK_OK;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+  EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+  (void)bytes;
+  return EMK_OK;
+}
+
+int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angles, const float* dihedrals, int64_t b,
+                       int64_t n, float* xyz, cudaStream_t st) {
+  EMK_REQUIRE(lengths && angles && dihedrals && xyz, EMK_E_NULL, "emk_backmap: NULL pointer argument");
+  EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_backmap: need 4 <= n_atoms < 2^20, got %lld", (long long)n);
+  EMK_REQUIRE(b >= 0 && (lstride == 0 || lstride == n - 1), EMK_E_ARG, "emk_backmap: lengths_batch_stride must be 0 or n_atoms-1");
+  if (b == 0) return EMK_OK;
+  int warps;
+  size_t smem;
+  int rc = pick_warps((size_t)(n - 1) + (n - 2) + (n - 3) + 3 * n, 0, &warps, &smem);
+  if (rc) return rc;
+  static bool cfg = false;
+  if (!cfg) { rc = set_smem(backmap_fwd_kernel, smem); if (rc) return rc; cfg = true; }
+  const int64_t blocks = (b + warps - 1) / warps;
+  backmap_fwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz);
+  return launch_status("backmap_fwd_kernel");
+}
+
+int chain_in_plane_device(const float* lengths, int64_t lstride, const float* angles, int64_t b, int64_t n, float* xyz, cudaStream_t st) {
+  EMK_REQUIRE(lengths && angles && xyz, EMK_E_NULL, "emk_chain_in_plane: NULL pointer argument");
+  EMK_REQUIRE(n >= 3 && n < (1 << 20), EMK_E_SHAPE, "emk_chain_in_plane: need 3 <= n_atoms < 2^20, got %lld", (long long)n);
+  EMK_REQUIRE(b >= 0 && (lstride == 0 || lstride == n - 1), EMK_E_ARG, "emk_chain_in_plane: lengths_batch_stride must be 0 or n_atoms-1");
+  if (b == 0) return EMK_OK;
+  int warps;
+  size_t smem;
+  int rc = pick_warps((size_t)(n - 1) + (n - 2) + 3 * n, 0, &warps, &smem);
+  if (rc) return rc;
+  static bool cfg = false;
+  if (!cfg) { rc = set_smem(chain_in_plane_kernel, smem); if (rc) return rc; cfg = true; }
+  const int64_t blocks = (b + warps - 1) / warps;
+  chain_in_plane_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(lengths, lstride, angles, b, (int)n, xyz);
+  return launch_status("chain_in_plane_kernel");
+}
+
+int d2c_general_device(const float* dihedrals, const float* chain, int64_t cstride, int64_t b, int64_t n, int one_way,
+                       float* xyz, cudaStream_t st) {
+  EMK_REQUIRE(dihedrals && chain && xyz, EMK_E_NULL, "emk_dihedrals_to_cartesian: NULL pointer argument");
+  EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_dihedrals_to_cartesian: need 4 <= n_atoms < 2^20, got %lld", (long long)n);
+  EMK_REQUIRE(b >= 0 && (cstride == 0 || cstride == 3 * n), EMK_E_ARG, "emk_dihedrals_to_cartesian: chain_batch_stride must be 0 or 3*n_atoms");
+  if (b == 0) return EMK_OK;
+  int warps;
+  size_t smem;
+  int rc = pick_warps((size_t)(n - 3) + 3 * n, 0, &warps, &smem);
+  if (rc) return rc;
+  static bool cfg = false;
+  if (!cfg) { rc = set_smem(d2c_general_kernel, smem); if (rc) return rc; cfg = true; }
+  const int64_t blocks = (b + warps - 1) / warps;
+  d2c_general_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(dihedrals, chain, cstride, b, (int)n, one_way, xyz);
+  return launch_status("d2c_general_kernel");
+}
+
+int backmap_bwd_device(const BwdParams& p, cudaStream_t st) {
+  if (p.b == 0) return EMK_OK;
+  int warps;
+  size_t smem;
+  int rc = pick_warps((size_t)6 * p.n + (p.n - 1) + (p.n - 2), 0, &warps, &smem);
+  if (rc) return rc;
+  static bool cfg = false;
+  if (!cfg) { rc = set_smem(backmap_bwd_kernel, smem); if (rc) return rc; cfg = true; }
+  const int64_t blocks = (p.b + warps - 1) / warps;
+  backmap_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(p);
+  return launch_status("backmap_bwd_kernel");
+}
+
+}  // namespace emk

@@ -1,0 +1,293 @@
+// Bandwidth-bound helpers of the hot path: periodic_distance, sigmoid, PeriodicInput, rotation_matrix,
+// column mean, and the batched small-d pairwise_dist (PairwiseDistances layer) forward / backward.
+#include "emk_common.cuh"
+
+namespace emk {
+
+static inline int grid_for(int64_t work, int threads = 256) {
+  int64_t blocks = (work + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---- periodic_distance -----------------------------------------------------------------------------
+__global__ void periodic_distance_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count, float P,
+                                         float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = fabsf(b[i] - a[i]);
+    out[i] = fminf(d, P - d);
+  }
+}
+// TF autodiff conventions: abs' = sign, minimum routes to the first operand on ties
+__global__ void periodic_distance_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count, float P,
+                                             const float* __restrict__ go, float* __restrict__ ga, float* __restrict__ gb) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float diff = b[i] - a[i];
+    const float d = fabsf(diff);
+    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    const float branch = (d <= P - d) ? 1.f : -1.f;
+    const float g = go[i] * sgn * branch;
+    if (gb) gb[i] = g;
+    if (ga) ga[i] = -g;
+  }
+}
+
+// ---- sigmoid ---------------------------------------------------------------------------------------
+__global__ void sigmoid_kernel(const float* __restrict__ r, int64_t count, SigSpec s, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = r[i];
+    out[i] = sig_eval<false>(x * x, s, nullptr);
+  }
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ r, int64_t count, SigSpec s, const float* __restrict__ go,
+                                   float* __restrict__ gr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = r[i];
+    float w;
+    sig_eval<true>(x * x, s, &w);
+    // s'(r) = r * (s'(r)/r); at r == 0 the limit is 0 for a > 1 and b*c/sig for a == 1
+    float ds = x == 0.f ? ((s.a_int == 1) ? s.dcoef * sqrtf(1.f / s.inv_sig2) : 0.f) : w * x;
+    gr[i] = go[i] * ds;
+  }
+}
+
+// ---- PeriodicInput -----------------------------------------------------------------------------------
+__global__ void periodic_input_kernel(const float* __restrict__ x, int64_t rows, int64_t d, float scale, int rescale,
+                                      float* __restrict__ out) {
+  const int64_t total = rows * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d, k = i - r * d;
+    float v = x[i];
+    if (rescale) v = v * scale;
+    float s, c;
+    sincosf(v, &s, &c);
+    out[r * 2 * d + k] = s;
+    out[r * 2 * d + d + k] = c;
+  }
+}
+__global__ void periodic_input_bwd_kernel(const float* __restrict__ x, int64_t rows, int64_t d, float scale, int rescale,
+                                          const float* __restrict__ go, float* __restrict__ gx) {
+  const int64_t total = rows * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d, k = i - r * d;
+    float v = x[i];
+    if (rescale) v = v * scale;
+    float s, c;
+    sincosf(v, &s, &c);
+    float g = go[r * 2 * d + k] * c - go[r * 2 * d + d + k] * s;
+    if (rescale) g *= scale;
+    gx[i] = g;
+  }
+}
+
+// ---- rotation_matrix -----------------------------------------------------------------------------------
+__global__ void rotation_matrix_kernel(const float* __restrict__ axis, const float* __restrict__ angle, int64_t b,
+                                       float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b; i += (int64_t)gridDim.x * blockDim.x) {
+    const float ux = axis[3 * i], uy = axis[3 * i + 1], uz = axis[3 * i + 2];
+    float s, c;
+    sincosf(angle[i], &s, &c);
+    const float oc = 1.f - c;
+    float* o = out + 9 * i;
+    o[0] = c + oc * ux * ux;      o[1] = oc * ux * uy - s * uz; o[2] = oc * ux * uz + s * uy;
+    o[3] = oc * uy * ux + s * uz; o[4] = c + oc * uy * uy;      o[5] = oc * uy * uz - s * ux;
+    o[6] = oc * uz * ux - s * uy; o[7] = oc * uz * uy + s * ux; o[8] = c + oc * uz * uz;
+  }
+}
+
+// ---- column mean: (rows, cols) -> (cols) ------------------------------------------------------------------
+constexpr int CM_SPLIT = 64;
+__global__ void column_partial_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, double* __restrict__ part) {
+  // block: 32 columns x 8 row lanes; grid.x over column tiles, grid.y over CM_SPLIT row slabs
+  __shared__ double sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * 32 + cx;
+  const int64_t slab = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * slab, r1 = min(rows, r0 + slab);
+  double acc = 0.0;
+  if (col < cols)
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += (double)x[r * cols + col];
+  sm[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += sm[i][cx];
+    part[(int64_t)blockIdx.y * cols + col] = t;
+  }
+}
+__global__ void column_final_kernel(const double* __restrict__ part, int split, int64_t rows, int64_t cols, float* __restrict__ out) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x) {
+    double t = 0.0;
+    for (int s = 0; s < split; s++) t += part[(int64_t)s * cols + c];
+    out[c] = (float)(t / (double)rows);
+  }
+}
+
+// ---- batched pairwise_dist for small d (PairwiseDistances layer) ------------------------------------------
+// strict-upper-triangle index p -> (i, j), row-major: row i starts at i*(2n-i-1)/2
+__device__ __forceinline__ void triu_decode(int64_t p, int64_t n, int64_t* i_out, int64_t* j_out) {
+  const double nn = (double)(2 * n - 1);
+  int64_t i = (int64_t)((nn - sqrt(nn * nn - 8.0 * (double)p)) * 0.5);
+  if (i < 0) i = 0;
+  while (i > 0 && i * (2 * n - i - 1) / 2 > p) --i;
+  while ((i + 1) * (2 * n - i - 2) / 2 <= p) ++i;
+  *i_out = i;
+  *j_out = p - i * (2 * n - i - 1) / 2 + i + 1;
+}
+
+__global__ void pairwise_small_kernel(const float* __restrict__ x, int64_t b, int64_t n, int64_t d, int64_t bstride,
+                                      int64_t rstride, int squared, int flat, float* __restrict__ out) {
+  const int64_t per = flat ? n * (n - 1) / 2 : n * n;
+  const int64_t total = b * per;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bi = idx / per, p = idx - bi * per;
+    int64_t i, j;
+    if (flat) triu_decode(p, n, &i, &j);
+    else { i = p / n; j = p - i * n; }
+    const float* xi = x + bi * bstride + i * rstride;
+    const float* xj = x + bi * bstride + j * rstride;
+    float s = 0.f;
+    for (int64_t k = 0; k < d; k++) {
+      const float t = xi[k] - xj[k];
+      s = fmaf(t, t, s);
+    }
+    out[idx] = squared ? s : sqrtf(s);
+  }
+}
+
+// one warp per (frame, row i): grad_x[i] = sum_j coef_ij (x_i - x_j); coef = g/dist (or 2g when squared)
+__global__ void pairwise_small_bwd_kernel(const float* __restrict__ x, int64_t b, int64_t n, int64_t d, int64_t bstride,
+                                          int64_t rstride, int squared, int flat, const float* __restrict__ go,
+                                          float* __restrict__ gx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t per = flat ? n * (n - 1) / 2 : n * n;
+  for (int64_t task = wid; task < b * n; task += nw) {
+    const int64_t bi = task / n, i = task - bi * n;
+    const float* xb = x + bi * bstride;
+    const float* xi = xb + i * rstride;
+    const float* g = go + bi * per;
+    for (int64_t k0 = 0; k0 < d; k0 += 8) {   // up to 8 components per sweep keeps the accumulators in registers
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const int kc = (int)min((int64_t)8, d - k0);
+      for (int64_t j = lane; j < n; j += 32) {
+        if (j == i) continue;
+        const float* xj = xb + j * rstride;
+        float s = 0.f;
+        for (int64_t k = 0; k < d; k++) {
+          const float t = xi[k] - xj[k];
+          s = fmaf(t, t, s);
+        }
+        float gij;
+        if (flat) {
+          const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+          gij = g[lo * (2 * n - lo - 1) / 2 + (hi - lo - 1)];
+        } else {
+          gij = g[i * n + j] + g[j * n + i];
+        }
+        const float coef = squared ? 2.f * gij : (s > 0.f ? gij * rsqrtf(s) : 0.f);
+        for (int k = 0; k < kc; k++) acc[k] = fmaf(coef, xi[k0 + k] - xj[k0 + k], acc[k]);
+      }
+      for (int k = 0; k < kc; k++) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) gx[bi * bstride + i * rstride + k0 + k] = v;
+      }
+    }
+  }
+}
+
+// ---- host launchers -------------------------------------------------------------------------------------------
+int periodic_distance_device(const float* a, const float* b, int64_t count, double P, float* out, cudaStream_t st) {
+  EMK_REQUIRE(a && b && out, EMK_E_NULL, "emk_periodic_distance: NULL pointer argument");
+  EMK_REQUIRE(count >= 0, EMK_E_SHAPE, "emk_periodic_distance: negative count");
+  if (count == 0) return EMK_OK;
+  periodic_distance_kernel<<<grid_for(count), 256, 0, st>>>(a, b, count, std::isinf(P) ? INFINITY : (float)P, out);
+  return launch_status("periodic_distance_kernel");
+}
+int periodic_distance_bwd_device(const float* a, const float* b, int64_t count, double P, const float* go, float* ga, float* gb,
+                                 cudaStream_t st) {
+  EMK_REQUIRE(a && b && go && (ga || gb), EMK_E_NULL, "emk_periodic_distance_bwd: NULL pointer argument");
+  if (count == 0) return EMK_OK;
+  periodic_distance_bwd_kernel<<<grid_for(count), 256, 0, st>>>(a, b, count, std::isinf(P) ? INFINITY : (float)P, go, ga, gb);
+  return launch_status("periodic_distance_bwd_kernel");
+}
+int sigmoid_device(const float* r, int64_t count, float sig, float a, float b, float* out, cudaStream_t st) {
+  EMK_REQUIRE(r && out, EMK_E_NULL, "emk_sigmoid: NULL pointer argument");
+  EMK_REQUIRE(sig > 0 && a > 0 && b > 0, EMK_E_ARG, "emk_sigmoid: parameters must be > 0");
+  if (count == 0) return EMK_OK;
+  sigmoid_kernel<<<grid_for(count), 256, 0, st>>>(r, count, make_sig_spec(sig, a, b), out);
+  return launch_status("sigmoid_kernel");
+}
+int sigmoid_bwd_device(const float* r, int64_t count, float sig, float a, float b, const float* go, float* gr, cudaStream_t st) {
+  EMK_REQUIRE(r && go && gr, EMK_E_NULL, "emk_sigmoid_bwd: NULL pointer argument");
+  EMK_REQUIRE(sig > 0 && a > 0 && b > 0, EMK_E_ARG, "emk_sigmoid_bwd: parameters must be > 0");
+  if (count == 0) return EMK_OK;
+  sigmoid_bwd_kernel<<<grid_for(count), 256, 0, st>>>(r, count, make_sig_spec(sig, a, b), go, gr);
+  return launch_status("sigmoid_bwd_kernel");
+}
+static inline void periodic_scale(double P, float* scale, int* rescale) {
+  // reference: `if periodicity != 2*pi: x = x / periodicity * 2 * pi` (layers.py:207-208)
+  *rescale = (P != 2.0 * M_PI) ? 1 : 0;
+  *scale = (float)(2.0 * M_PI / P);
+}
+int periodic_input_device(const float* x, int64_t rows, int64_t d, double P, float* out, cudaStream_t st) {
+  EMK_REQUIRE(x && out, EMK_E_NULL, "emk_periodic_input: NULL pointer argument");
+  EMK_REQUIRE(rows >= 0 && d >= 0 && P > 0, EMK_E_ARG, "emk_periodic_input: bad arguments");
+  if (rows * d == 0) return EMK_OK;
+  float sc; int rs;
+  periodic_scale(P, &sc, &rs);
+  periodic_input_kernel<<<grid_for(rows * d), 256, 0, st>>>(x, rows, d, sc, rs, out);
+  return launch_status("periodic_input_kernel");
+}
+int periodic_input_bwd_device(const float* x, int64_t rows, int64_t d, double P, const float* go, float* gx, cudaStream_t st) {
+  EMK_REQUIRE(x && go && gx, EMK_E_NULL, "emk_periodic_input_bwd: NULL pointer argument");
+  EMK_REQUIRE(rows >= 0 && d >= 0 && P > 0, EMK_E_ARG, "emk_periodic_input_bwd: bad arguments");
+  if (rows * d == 0) return EMK_OK;
+  float sc; int rs;
+  periodic_scale(P, &sc, &rs);
+  periodic_input_bwd_kernel<<<grid_for(rows * d), 256, 0, st>>>(x, rows, d, sc, rs, go, gx);
+  return launch_status("periodic_input_bwd_kernel");
+}
+int rotation_matrix_device(const float* axis, const float* angle, int64_t b, float* out, cudaStream_t st) {
+  EMK_REQUIRE(axis && angle && out, EMK_E_NULL, "emk_rotation_matrix: NULL pointer argument");
+  if (b <= 0) return b == 0 ? EMK_OK : fail(EMK_E_SHAPE, "emk_rotation_matrix: negative batch");
+  rotation_matrix_kernel<<<grid_for(b), 256, 0, st>>>(axis, angle, b, out);
+  return launch_status("rotation_matrix_kernel");
+}
+int column_mean_device(const float* x, int64_t rows, int64_t cols, float* out, cudaStream_t st) {
+  EMK_REQUIRE(x && out, EMK_E_NULL, "emk_column_mean: NULL pointer argument");
+  EMK_REQUIRE(rows >= 1 && cols >= 1, EMK_E_SHAPE, "emk_column_mean: need rows, cols >= 1");
+  const int split = (int)min((int64_t)CM_SPLIT, (rows + 255) / 256);
+  double* part = nullptr;
+  EMK_CUDA(cudaMallocAsync(&part, (size_t)split * cols * sizeof(double), st));
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)split);
+  column_partial_kernel<<<grid, 256, 0, st>>>(x, rows, cols, part);
+  int rc = launch_status("column_partial_kernel");
+  if (rc == EMK_OK) {
+    column_final_kernel<<<grid_for(cols), 256, 0, st>>>(part, split, rows, cols, out);
+    rc = launch_status("column_final_kernel");
+  }
+  cudaFreeAsync(part, st);
+  return rc;
+}
+int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
+                          int flat, float* out, cudaStream_t st) {
+  const int64_t per = flat ? n * (n - 1) / 2 : n * n;
+  if (b * per == 0) return EMK_OK;
+  pairwise_small_kernel<<<grid_for(b * per), 256, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, out);
+  return launch_status("pairwise_small_kernel");
+}
+int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
+                              int flat, const float* go, float* gx, cudaStream_t st) {
+  if (b * n == 0) return EMK_OK;
+  pairwise_small_bwd_kernel<<<grid_for(b * n * 32), 256, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, go, gx);
+  return launch_status("pairwise_small_bwd_kernel");
+}
+
+}  // namespace emk

@@ -1,0 +1,629 @@
+// extern "C" surface of libemk (include/emk.h): argument validation, DLPack views, host-only index
+// construction, host-buffer convenience entry points.  Kernels live in pair_tile.cu, backmap.cu,
+// elementwise.cu.
+#include <cstring>
+#include <vector>
+
+#include "emk_common.cuh"
+
+namespace emk {
+
+// ---- error plumbing ----------------------------------------------------------------------------------
+char* last_error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+SigSpec make_sig_spec(float sig, float a, float b) {
+  SigSpec s;
+  s.inv_sig2 = (float)(1.0 / ((double)sig * (double)sig));
+  s.c = (float)(std::pow(2.0, (double)a / (double)b) - 1.0);
+  s.half_a = 0.5f * a;
+  s.e = b / a;
+  s.dcoef = (float)((double)b * (std::pow(2.0, (double)a / (double)b) - 1.0) / ((double)sig * (double)sig));
+  s.a_int = (a == std::floor(a) && a >= 1.f && a <= 32.f) ? (int)a : 0;
+  const float e2 = 2.f * b / a;
+  s.e2_int = (e2 == std::floor(e2) && e2 >= 1.f && e2 <= 32.f) ? (int)e2 : 0;
+  return s;
+}
+
+// device entry points implemented in the kernel files
+int64_t pair_tile_count(int64_t n);
+void tile_decode_host(int64_t t, int64_t tc, int64_t* I, int64_t* J);
+int sigmoid_cost_device(const float*, int64_t, int64_t, const float*, int64_t, double, const float*, int64_t, int64_t, double*,
+                        float*, uint32_t, cudaStream_t);
+int dist_matrix_device(const float*, int64_t, int64_t, double, bool, int, float*, cudaStream_t);
+int periodic_distance_device(const float*, const float*, int64_t, double, float*, cudaStream_t);
+int periodic_distance_bwd_device(const float*, const float*, int64_t, double, const float*, float*, float*, cudaStream_t);
+int sigmoid_device(const float*, int64_t, float, float, float, float*, cudaStream_t);
+int sigmoid_bwd_device(const float*, int64_t, float, float, float, const float*, float*, cudaStream_t);
+int periodic_input_device(const float*, int64_t, int64_t, double, float*, cudaStream_t);
+int periodic_input_bwd_device(const float*, int64_t, int64_t, double, const float*, float*, cudaStream_t);
+int rotation_matrix_device(const float*, const float*, int64_t, float*, cudaStream_t);
+int column_mean_device(const float*, int64_t, int64_t, float*, cudaStream_t);
+int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float*, cudaStream_t);
+int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
+int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
+int chain_in_plane_device(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
+int d2c_general_device(const float*, const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
+int backmap_bwd_device(const BwdParams&, cudaStream_t);
+
+// ---- DLPack views ---------------------------------------------------------------------------------------
+struct View {
+  void* data;
+  int ndim;
+  int64_t shape[4];
+  int64_t numel;
+};
+
+static int view_of(const DLManagedTensor* t, const char* name, int code, int bits, int min_rank, int max_rank, View* v) {
+  EMK_REQUIRE(t != nullptr, EMK_E_NULL, "%s: NULL DLManagedTensor", name);
+  const DLTensor& d = t->dl_tensor;
+  EMK_REQUIRE(d.device.device_type == kDLCUDA || d.device.device_type == kDLCUDAManaged, EMK_E_DEVICE,
+              "%s: tensor is on device_type %d, need a CUDA tensor (there is no CPU fallback)", name, d.device.device_type);
+  EMK_REQUIRE(d.dtype.code == code && d.dtype.bits == bits && d.dtype.lanes == 1, EMK_E_DTYPE,
+              "%s: dtype (code %d, %d bits) is not %s%d", name, d.dtype.code, d.dtype.bits, code == kDLFloat ? "float" : "int", bits);
+  EMK_REQUIRE(d.ndim >= min_rank && d.ndim <= max_rank && d.ndim <= 4, EMK_E_SHAPE, "%s: rank %d outside [%d,%d]", name, d.ndim,
+              min_rank, max_rank);
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    EMK_REQUIRE(dev == d.device.device_id, EMK_E_DEVICE, "%s: tensor lives on cuda:%d but the current device is cuda:%d", name,
+                d.device.device_id, dev);
+  v->ndim = d.ndim;
+  v->numel = 1;
+  for (int i = 0; i < d.ndim; i++) {
+    v->shape[i] = d.shape[i];
+    v->numel *= d.shape[i];
+  }
+  if (d.strides != nullptr && v->numel > 0) {
+    int64_t expect = 1;
+    for (int i = d.ndim - 1; i >= 0; i--) {
+      EMK_REQUIRE(d.shape[i] == 1 || d.strides[i] == expect, EMK_E_CONTIG, "%s: tensor is not C-contiguous (stride[%d]=%lld, expected %lld)",
+                  name, i, (long long)d.strides[i], (long long)expect);
+      expect *= d.shape[i];
+    }
+  }
+  v->data = static_cast<char*>(d.data) + d.byte_offset;
+  return EMK_OK;
+}
+#define VIEW(var, tensor, name, minr, maxr)                                   \
+  View var;                                                                   \
+  do {                                                                        \
+    int rc_ = view_of(tensor, name, kDLFloat, 32, minr, maxr, &var);          \
+    if (rc_) return rc_;                                                      \
+  } while (0)
+#define F(v) static_cast<float*>((v).data)
+
+// python-style slice resolution for inputs[:, start:stop:step]; INT64_MIN means "None"
+static int resolve_slice(int64_t n, int64_t start, int64_t stop, int64_t step, int64_t* first, int64_t* count, int64_t* stride) {
+  const int64_t none = INT64_MIN;
+  if (step == none) step = 1;
+  EMK_REQUIRE(step > 0, EMK_E_UNSUPPORTED, "atom selection: only positive steps are supported (got %lld)", (long long)step);
+  if (start == none) start = 0;
+  if (stop == none) stop = n;
+  if (start < 0) start += n;
+  if (stop < 0) stop += n;
+  if (start < 0) start = 0;
+  if (start > n) start = n;
+  if (stop < 0) stop = 0;
+  if (stop > n) stop = n;
+  *first = start;
+  *count = stop > start ? (stop - start + step - 1) / step : 0;
+  *stride = step;
+  return EMK_OK;
+}
+
+static void split_geometry(int64_t n, int64_t* split, int64_t counts[4]) {
+  const int64_t s = n / 2;
+  *split = s;
+  counts[0] = s + 2;          // left atoms  s+1 .. 0
+  counts[1] = n - s + 1;      // right atoms s-1 .. n-1
+  const int64_t nd = n - 3, m = nd / 2;
+  counts[2] = (nd % 2 == 0) ? m : m + 1;
+  counts[3] = nd - counts[2];
+}
+
+}  // namespace emk
+
+using namespace emk;
+
+extern "C" {
+
+int emk_version(void) { return EMK_VERSION; }
+const char* emk_last_error(void) { return last_error_buffer(); }
+const char* emk_build_info(void) {
+  static char info[128];
+  snprintf(info, sizeof(info), "sm_100a;nvcc %d.%d;%s", __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, __DATE__);
+  return info;
+}
+
+// ---- host-only index construction --------------------------------------------------------------------------
+int64_t emk_triu_pair_count(int64_t n) { return n < 2 ? 0 : n * (n - 1) / 2; }
+
+int emk_triu_pair_indices(int64_t n, int32_t* i_out, int32_t* j_out) {
+  EMK_REQUIRE(n >= 0 && n < (1 << 30), EMK_E_ARG, "emk_triu_pair_indices: bad n=%lld", (long long)n);
+  EMK_REQUIRE(n < 2 || (i_out && j_out), EMK_E_NULL, "emk_triu_pair_indices: NULL output");
+  int64_t p = 0;
+  for (int64_t i = 0; i < n; i++)
+    for (int64_t j = i + 1; j < n; j++, p++) {
+      i_out[p] = (int32_t)i;
+      j_out[p] = (int32_t)j;
+    }
+  return EMK_OK;
+}
+
+int emk_backmap_split_counts(int64_t n_atoms, int64_t counts[4]) {
+  EMK_REQUIRE(counts, EMK_E_NULL, "emk_backmap_split_counts: NULL output");
+  EMK_REQUIRE(n_atoms >= 3, EMK_E_SHAPE, "emk_backmap_split_counts: need n_atoms >= 3, got %lld", (long long)n_atoms);
+  int64_t s;
+  split_geometry(n_atoms, &s, counts);
+  return EMK_OK;
+}
+
+int emk_backmap_split_indices(int64_t n_atoms, int32_t* left_atoms, int32_t* right_atoms, int32_t* left_dihedrals,
+                              int32_t* right_dihedrals) {
+  EMK_REQUIRE(n_atoms >= 3, EMK_E_SHAPE, "emk_backmap_split_indices: need n_atoms >= 3, got %lld", (long long)n_atoms);
+  EMK_REQUIRE(left_atoms && right_atoms && left_dihedrals && right_dihedrals, EMK_E_NULL, "emk_backmap_split_indices: NULL output");
+  int64_t s, c[4];
+  split_geometry(n_atoms, &s, c);
+  for (int64_t m = 0; m < c[0]; m++) left_atoms[m] = (int32_t)(s + 1 - m);
+  for (int64_t m = 0; m < c[1]; m++) right_atoms[m] = (int32_t)(s - 1 + m);
+  for (int64_t i = 0; i < c[2]; i++) left_dihedrals[i] = (int32_t)(c[2] - 1 - i);
+  for (int64_t i = 0; i < c[3]; i++) right_dihedrals[i] = (int32_t)(c[2] + i);
+  return EMK_OK;
+}
+
+int64_t emk_pair_tile_count(int64_t n_rows) { return pair_tile_count(n_rows); }
+
+int emk_pair_tile_decode(int64_t n_rows, int64_t tile, int64_t* tile_row, int64_t* tile_col) {
+  EMK_REQUIRE(tile_row && tile_col, EMK_E_NULL, "emk_pair_tile_decode: NULL output");
+  EMK_REQUIRE(tile >= 0 && tile < pair_tile_count(n_rows), EMK_E_ARG, "emk_pair_tile_decode: tile %lld outside [0,%lld)", (long long)tile,
+              (long long)pair_tile_count(n_rows));
+  tile_decode_host(tile, (n_rows + EMK_TILE_COLS - 1) / EMK_TILE_COLS, tile_row, tile_col);
+  return EMK_OK;
+}
+
+int emk_pair_tile_range(int64_t n_rows, int rank, int world, int64_t* begin, int64_t* end) {
+  EMK_REQUIRE(begin && end, EMK_E_NULL, "emk_pair_tile_range: NULL output");
+  EMK_REQUIRE(world >= 1 && rank >= 0 && rank < world, EMK_E_ARG, "emk_pair_tile_range: bad rank %d / world %d", rank, world);
+  const int64_t total = pair_tile_count(n_rows);
+  const int64_t base = total / world, rem = total % world;
+  *begin = rank * base + (rank < rem ? rank : rem);
+  *end = *begin + base + (rank < rem ? 1 : 0);
+  return EMK_OK;
+}
+
+// ---- sigmoid cost ------------------------------------------------------------------------------------------------
+int emk_sigmoid_cost(const float* high, int64_t n, int64_t d, const float* low, int64_t l, double periodicity, const float sig[6],
+                     int64_t tile_begin, int64_t tile_end, double* loss, float* grad_low, uint32_t flags, void* stream) {
+  return sigmoid_cost_device(high, n, d, low, l, periodicity, sig, tile_begin, tile_end, loss, grad_low, flags, as_stream(stream));
+}
+
+int emk_dl_sigmoid_cost(const DLManagedTensor* high, const DLManagedTensor* low, double periodicity, const float sig[6],
+                        int64_t tile_begin, int64_t tile_end, DLManagedTensor* loss, DLManagedTensor* grad_low, uint32_t flags,
+                        void* stream) {
+  VIEW(h, high, "high", 2, 2);
+  VIEW(z, low, "low", 2, 2);
+  EMK_REQUIRE(h.shape[0] == z.shape[0], EMK_E_SHAPE, "emk_dl_sigmoid_cost: high has %lld rows, low has %lld", (long long)h.shape[0],
+              (long long)z.shape[0]);
+  View lv;
+  int rc = view_of(loss, "loss", kDLFloat, 64, 0, 1, &lv);
+  if (rc) return rc;
+  EMK_REQUIRE(lv.numel == 1, EMK_E_SHAPE, "emk_dl_sigmoid_cost: loss must hold exactly one float64");
+  float* g = nullptr;
+  if (!(flags & EMK_COST_NO_GRAD)) {
+    VIEW(gv, grad_low, "grad_low", 2, 2);
+    EMK_REQUIRE(gv.shape[0] == z.shape[0] && gv.shape[1] == z.shape[1], EMK_E_SHAPE, "emk_dl_sigmoid_cost: grad_low shape differs from low");
+    g = F(gv);
+  }
+  return sigmoid_cost_device(F(h), h.shape[0], h.shape[1], F(z), z.shape[1], periodicity, sig, tile_begin, tile_end,
+                             static_cast<double*>(lv.data), g, flags, as_stream(stream));
+}
+
+int emk_sigmoid_cost_host(const float* high_host, int64_t n, int64_t d, const float* low_host, int64_t l, double periodicity,
+                          const float sig[6], double* loss_host, float* grad_low_host) {
+  EMK_REQUIRE(high_host && low_host && sig && loss_host, EMK_E_NULL, "emk_sigmoid_cost_host: NULL pointer argument");
+  EMK_REQUIRE(n >= 1 && d >= 1 && l >= 1, EMK_E_SHAPE, "emk_sigmoid_cost_host: bad shape");
+  cudaStream_t st;
+  EMK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  float *dh = nullptr, *dz = nullptr, *dg = nullptr;
+  double* dl = nullptr;
+  int rc = EMK_OK;
+  auto cleanup = [&]() {
+    if (dh) cudaFreeAsync(dh, st);
+    if (dz) cudaFreeAsync(dz, st);
+    if (dg) cudaFreeAsync(dg, st);
+    if (dl) cudaFreeAsync(dl, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  };
+#define HOSTCK(call)                                                                          \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      cleanup();                                                                              \
+      return fail((int)e_, "%s failed: %s", #call, cudaGetErrorString(e_));                   \
+    }                                                                                         \
+  } while (0)
+  HOSTCK(cudaMallocAsync(&dh, (size_t)n * d * sizeof(float), st));
+  HOSTCK(cudaMallocAsync(&dz, (size_t)n * l * sizeof(float), st));
+  HOSTCK(cudaMallocAsync(&dg, (size_t)n * l * sizeof(float), st));
+  HOSTCK(cudaMallocAsync(&dl, sizeof(double), st));
+  HOSTCK(cudaMemcpyAsync(dh, high_host, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  HOSTCK(cudaMemcpyAsync(dz, low_host, (size_t)n * l * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = sigmoid_cost_device(dh, n, d, dz, l, periodicity, sig, 0, pair_tile_count(n), dl, dg,
+                           EMK_COST_ZERO_OUTPUTS | (grad_low_host ? 0u : EMK_COST_NO_GRAD), st);
+  if (rc == EMK_OK) {
+    HOSTCK(cudaMemcpyAsync(loss_host, dl, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grad_low_host) HOSTCK(cudaMemcpyAsync(grad_low_host, dg, (size_t)n * l * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HOSTCK(cudaStreamSynchronize(st));
+  }
+  cleanup();
+  return rc;
+}
+
+// ---- distance matrices -----------------------------------------------------------------------------------------------
+int emk_pairwise_dist_periodic(const float* x, int64_t n, int64_t d, double periodicity, float* out, void* stream) {
+  return dist_matrix_device(x, n, d, periodicity, true, 0, out, as_stream(stream));
+}
+int emk_dl_pairwise_dist_periodic(const DLManagedTensor* x, double periodicity, DLManagedTensor* out, void* stream) {
+  VIEW(xv, x, "positions", 2, 2);
+  VIEW(ov, out, "out", 2, 2);
+  EMK_REQUIRE(ov.shape[0] == xv.shape[0] && ov.shape[1] == xv.shape[0], EMK_E_SHAPE, "emk_dl_pairwise_dist_periodic: out must be (n,n)");
+  return dist_matrix_device(F(xv), xv.shape[0], xv.shape[1], periodicity, true, 0, F(ov), as_stream(stream));
+}
+
+int emk_pairwise_dist(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride, int squared,
+                      int flat, float* out, void* stream) {
+  EMK_REQUIRE(x && out, EMK_E_NULL, "emk_pairwise_dist: NULL pointer argument");
+  EMK_REQUIRE(b >= 0 && n >= 0 && d >= 1, EMK_E_SHAPE, "emk_pairwise_dist: bad shape b=%lld n=%lld d=%lld", (long long)b, (long long)n, (long long)d);
+  // one big contiguous rank-2 problem with a wide feature axis goes through the TMA pair-tile kernel
+  if (b == 1 && !flat && row_stride == d && d >= 16 && n >= 256)
+    return dist_matrix_device(x, n, d, INFINITY, false, squared, out, as_stream(stream));
+  return pairwise_small_device(x, b, n, d, batch_stride, row_stride, squared, flat, out, as_stream(stream));
+}
+int emk_pairwise_dist_bwd(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride, int squared,
+                          int flat, const float* grad_out, float* grad_x, void* stream) {
+  EMK_REQUIRE(x && grad_out && grad_x, EMK_E_NULL, "emk_pairwise_dist_bwd: NULL pointer argument");
+  EMK_REQUIRE(b >= 0 && n >= 0 && d >= 1, EMK_E_SHAPE, "emk_pairwise_dist_bwd: bad shape");
+  return pairwise_small_bwd_device(x, b, n, d, batch_stride, row_stride, squared, flat, grad_out, grad_x, as_stream(stream));
+}
+
+static int pw_geometry(const View& xv, int64_t start, int64_t stop, int64_t step, int64_t* b, int64_t* n, int64_t* d, int64_t* bs,
+                       int64_t* rs, int64_t* first) {
+  if (xv.ndim == 2) {
+    *b = 1;
+    *d = xv.shape[1];
+    *bs = xv.numel;
+    int64_t cnt, st;
+    int rc = resolve_slice(xv.shape[0], start, stop, step, first, &cnt, &st);
+    if (rc) return rc;
+    *n = cnt;
+    *rs = st * xv.shape[1];
+    *first *= xv.shape[1];
+  } else {
+    *b = xv.shape[0];
+    *d = xv.shape[2];
+    *bs = xv.shape[1] * xv.shape[2];
+    int64_t cnt, st;
+    int rc = resolve_slice(xv.shape[1], start, stop, step, first, &cnt, &st);
+    if (rc) return rc;
+    *n = cnt;
+    *rs = st * xv.shape[2];
+    *first *= xv.shape[2];
+  }
+  return EMK_OK;
+}
+
+int emk_dl_pairwise_dist(const DLManagedTensor* x, int64_t start, int64_t stop, int64_t step, int squared, int flat,
+                         DLManagedTensor* out, void* stream) {
+  VIEW(xv, x, "positions", 2, 3);
+  int64_t b, n, d, bs, rs, first;
+  int rc = pw_geometry(xv, start, stop, step, &b, &n, &d, &bs, &rs, &first);
+  if (rc) return rc;
+  VIEW(ov, out, "out", 2, 3);
+  const int64_t want = b * (flat ? n * (n - 1) / 2 : n * n);
+  EMK_REQUIRE(ov.numel == want, EMK_E_SHAPE, "emk_dl_pairwise_dist: out has %lld elements, expected %lld", (long long)ov.numel, (long long)want);
+  return emk_pairwise_dist(F(xv) + first, b, n, d, bs, rs, squared, flat, F(ov), stream);
+}
+int emk_dl_pairwise_dist_bwd(const DLManagedTensor* x, int64_t start, int64_t stop, int64_t step, int squared, int flat,
+                             const DLManagedTensor* grad_out, DLManagedTensor* grad_x, void* stream) {
+  VIEW(xv, x, "positions", 2, 3);
+  int64_t b, n, d, bs, rs, first;
+  int rc = pw_geometry(xv, start, stop, step, &b, &n, &d, &bs, &rs, &first);
+  if (rc) return rc;
+  VIEW(gv, grad_out, "grad_out", 2, 3);
+  VIEW(gx, grad_x, "grad_x", 2, 3);
+  const int64_t want = b * (flat ? n * (n - 1) / 2 : n * n);
+  EMK_REQUIRE(gv.numel == want, EMK_E_SHAPE, "emk_dl_pairwise_dist_bwd: grad_out has %lld elements, expected %lld", (long long)gv.numel, (long long)want);
+  EMK_REQUIRE(gx.numel == xv.numel, EMK_E_SHAPE, "emk_dl_pairwise_dist_bwd: grad_x shape differs from positions");
+  return emk_pairwise_dist_bwd(F(xv) + first, b, n, d, bs, rs, squared, flat, F(gv), F(gx) + first, stream);
+}
+
+// ---- elementwise ---------------------------------------------------------------------------------------------------------
+int emk_periodic_distance(const float* a, const float* b, int64_t count, double periodicity, float* out, void* stream) {
+  return periodic_distance_device(a, b, count, periodicity, out, as_stream(stream));
+}
+int emk_periodic_distance_bwd(const float* a, const float* b, int64_t count, double periodicity, const float* grad_out, float* grad_a,
+                              float* grad_b, void* stream) {
+  return periodic_distance_bwd_device(a, b, count, periodicity, grad_out, grad_a, grad_b, as_stream(stream));
+}
+int emk_dl_periodic_distance(const DLManagedTensor* a, const DLManagedTensor* b, double periodicity, DLManagedTensor* out, void* stream) {
+  VIEW(av, a, "a", 0, 4);
+  VIEW(bv, b, "b", 0, 4);
+  VIEW(ov, out, "out", 0, 4);
+  EMK_REQUIRE(av.numel == bv.numel && av.numel == ov.numel, EMK_E_SHAPE, "emk_dl_periodic_distance: operands must have equal element counts (broadcast first)");
+  return periodic_distance_device(F(av), F(bv), av.numel, periodicity, F(ov), as_stream(stream));
+}
+int emk_dl_periodic_distance_bwd(const DLManagedTensor* a, const DLManagedTensor* b, double periodicity, const DLManagedTensor* grad_out,
+                                 DLManagedTensor* grad_a, DLManagedTensor* grad_b, void* stream) {
+  VIEW(av, a, "a", 0, 4);
+  VIEW(bv, b, "b", 0, 4);
+  VIEW(gv, grad_out, "grad_out", 0, 4);
+  EMK_REQUIRE(av.numel == bv.numel && av.numel == gv.numel, EMK_E_SHAPE, "emk_dl_periodic_distance_bwd: element counts differ");
+  float *ga = nullptr, *gb = nullptr;
+  if (grad_a) {
+    VIEW(t, grad_a, "grad_a", 0, 4);
+    EMK_REQUIRE(t.numel == av.numel, EMK_E_SHAPE, "emk_dl_periodic_distance_bwd: grad_a element count differs");
+    ga = F(t);
+  }
+  if (grad_b) {
+    VIEW(t, grad_b, "grad_b", 0, 4);
+    EMK_REQUIRE(t.numel == av.numel, EMK_E_SHAPE, "emk_dl_periodic_distance_bwd: grad_b element count differs");
+    gb = F(t);
+  }
+  return periodic_distance_bwd_device(F(av), F(bv), av.numel, periodicity, F(gv), ga, gb, as_stream(stream));
+}
+
+int emk_sigmoid(const float* r, int64_t count, float sig, float a, float b, float* out, void* stream) {
+  return sigmoid_device(r, count, sig, a, b, out, as_stream(stream));
+}
+int emk_sigmoid_bwd(const float* r, int64_t count, float sig, float a, float b, const float* grad_out, float* grad_r, void* stream) {
+  return sigmoid_bwd_device(r, count, sig, a, b, grad_out, grad_r, as_stream(stream));
+}
+int emk_dl_sigmoid(const DLManagedTensor* r, float sig, float a, float b, DLManagedTensor* out, void* stream) {
+  VIEW(rv, r, "r", 0, 4);
+  VIEW(ov, out, "out", 0, 4);
+  EMK_REQUIRE(rv.numel == ov.numel, EMK_E_SHAPE, "emk_dl_sigmoid: element counts differ");
+  return sigmoid_device(F(rv), rv.numel, sig, a, b, F(ov), as_stream(stream));
+}
+int emk_dl_sigmoid_bwd(const DLManagedTensor* r, float sig, float a, float b, const DLManagedTensor* grad_out, DLManagedTensor* grad_r,
+                       void* stream) {
+  VIEW(rv, r, "r", 0, 4);
+  VIEW(gv, grad_out, "grad_out", 0, 4);
+  VIEW(ov, grad_r, "grad_r", 0, 4);
+  EMK_REQUIRE(rv.numel == ov.numel && rv.numel == gv.numel, EMK_E_SHAPE, "emk_dl_sigmoid_bwd: element counts differ");
+  return sigmoid_bwd_device(F(rv), rv.numel, sig, a, b, F(gv), F(ov), as_stream(stream));
+}
+
+int emk_periodic_input(const float* x, int64_t rows, int64_t d, double periodicity, float* out, void* stream) {
+  return periodic_input_device(x, rows, d, periodicity, out, as_stream(stream));
+}
+int emk_periodic_input_bwd(const float* x, int64_t rows, int64_t d, double periodicity, const float* grad_out, float* grad_x, void* stream) {
+  return periodic_input_bwd_device(x, rows, d, periodicity, grad_out, grad_x, as_stream(stream));
+}
+int emk_dl_periodic_input(const DLManagedTensor* x, double periodicity, DLManagedTensor* out, void* stream) {
+  VIEW(xv, x, "x", 2, 2);
+  VIEW(ov, out, "out", 2, 2);
+  EMK_REQUIRE(ov.shape[0] == xv.shape[0] && ov.shape[1] == 2 * xv.shape[1], EMK_E_SHAPE, "emk_dl_periodic_input: out must be (rows, 2d)");
+  return periodic_input_device(F(xv), xv.shape[0], xv.shape[1], periodicity, F(ov), as_stream(stream));
+}
+int emk_dl_periodic_input_bwd(const DLManagedTensor* x, double periodicity, const DLManagedTensor* grad_out, DLManagedTensor* grad_x,
+                              void* stream) {
+  VIEW(xv, x, "x", 2, 2);
+  VIEW(gv, grad_out, "grad_out", 2, 2);
+  VIEW(ov, grad_x, "grad_x", 2, 2);
+  EMK_REQUIRE(gv.shape[0] == xv.shape[0] && gv.shape[1] == 2 * xv.shape[1] && ov.numel == xv.numel, EMK_E_SHAPE,
+              "emk_dl_periodic_input_bwd: shape mismatch");
+  return periodic_input_bwd_device(F(xv), xv.shape[0], xv.shape[1], periodicity, F(gv), F(ov), as_stream(stream));
+}
+
+int emk_rotation_matrix(const float* axis, const float* angle, int64_t b, float* out, void* stream) {
+  return rotation_matrix_device(axis, angle, b, out, as_stream(stream));
+}
+int emk_dl_rotation_matrix(const DLManagedTensor* axis, const DLManagedTensor* angle, DLManagedTensor* out, void* stream) {
+  VIEW(av, axis, "axis_unit_vec", 2, 2);
+  VIEW(gv, angle, "angle", 1, 1);
+  VIEW(ov, out, "out", 3, 3);
+  EMK_REQUIRE(av.shape[1] == 3 && gv.shape[0] == av.shape[0] && ov.shape[0] == av.shape[0] && ov.shape[1] == 3 && ov.shape[2] == 3,
+              EMK_E_SHAPE, "emk_dl_rotation_matrix: need axis (b,3), angle (b), out (b,3,3)");
+  return rotation_matrix_device(F(av), F(gv), av.shape[0], F(ov), as_stream(stream));
+}
+
+int emk_column_mean(const float* x, int64_t rows, int64_t cols, float* out, void* stream) {
+  return column_mean_device(x, rows, cols, out, as_stream(stream));
+}
+int emk_dl_column_mean(const DLManagedTensor* x, DLManagedTensor* out, void* stream) {
+  VIEW(xv, x, "x", 2, 2);
+  VIEW(ov, out, "out", 1, 2);
+  EMK_REQUIRE(ov.numel == xv.shape[1], EMK_E_SHAPE, "emk_dl_column_mean: out must hold one value per column");
+  return column_mean_device(F(xv), xv.shape[0], xv.shape[1], F(ov), as_stream(stream));
+}
+
+// ---- back-mapping -------------------------------------------------------------------------------------------------------------
+int emk_backmap(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* dihedrals, int64_t b,
+                int64_t n_atoms, float* xyz, void* stream) {
+  return backmap_fwd_device(lengths, lengths_batch_stride, angles, dihedrals, b, n_atoms, xyz, as_stream(stream));
+}
+
+int emk_backmap_bwd(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* xyz, const float* grad_xyz,
+                    int64_t b, int64_t n_atoms, float* grad_angles, float* grad_dihedrals, float* grad_lengths, void* stream) {
+  EMK_REQUIRE(lengths && angles && xyz && grad_xyz, EMK_E_NULL, "emk_backmap_bwd: NULL pointer argument");
+  EMK_REQUIRE(n_atoms >= 4 && n_atoms < (1 << 20), EMK_E_SHAPE, "emk_backmap_bwd: need 4 <= n_atoms < 2^20");
+  EMK_REQUIRE(lengths_batch_stride == 0 || lengths_batch_stride == n_atoms - 1, EMK_E_ARG, "emk_backmap_bwd: lengths_batch_stride must be 0 or n_atoms-1");
+  BwdParams p{lengths, lengths_batch_stride, angles, xyz, grad_xyz, b, (int)n_atoms, (int)(n_atoms / 2), (int)(n_atoms / 2 - 1), 0,
+              grad_angles, grad_dihedrals, grad_lengths};
+  return backmap_bwd_device(p, as_stream(stream));
+}
+
+static int lengths_view(const DLManagedTensor* lengths, int64_t b, int64_t n, View* lv, int64_t* stride) {
+  int rc = view_of(lengths, "lengths", kDLFloat, 32, 1, 2, lv);
+  if (rc) return rc;
+  if (lv->numel == n - 1) *stride = 0;
+  else if (lv->numel == b * (n - 1)) *stride = n - 1;
+  else return fail(EMK_E_SHAPE, "lengths must hold n_atoms-1 = %lld values, or one such row per frame (got %lld)", (long long)(n - 1), (long long)lv->numel);
+  return EMK_OK;
+}
+
+int emk_dl_backmap(const DLManagedTensor* lengths, const DLManagedTensor* angles, const DLManagedTensor* dihedrals, DLManagedTensor* xyz,
+                   void* stream) {
+  VIEW(av, angles, "angles", 2, 2);
+  VIEW(dv, dihedrals, "dihedrals", 2, 2);
+  VIEW(ov, xyz, "xyz", 3, 3);
+  const int64_t b = av.shape[0], n = av.shape[1] + 2;
+  EMK_REQUIRE(dv.shape[0] == b && dv.shape[1] == n - 3, EMK_E_SHAPE, "emk_dl_backmap: dihedrals must be (b, n_atoms-3) = (%lld,%lld)", (long long)b, (long long)(n - 3));
+  EMK_REQUIRE(ov.shape[0] == b && ov.shape[1] == n && ov.shape[2] == 3, EMK_E_SHAPE, "emk_dl_backmap: xyz must be (b, n_atoms, 3)");
+  View lv;
+  int64_t ls;
+  int rc = lengths_view(lengths, b, n, &lv, &ls);
+  if (rc) return rc;
+  return backmap_fwd_device(F(lv), ls, F(av), F(dv), b, n, F(ov), as_stream(stream));
+}
+
+int emk_dl_backmap_bwd(const DLManagedTensor* lengths, const DLManagedTensor* angles, const DLManagedTensor* xyz,
+                       const DLManagedTensor* grad_xyz, DLManagedTensor* grad_angles, DLManagedTensor* grad_dihedrals,
+                       DLManagedTensor* grad_lengths, void* stream) {
+  VIEW(av, angles, "angles", 2, 2);
+  VIEW(xv, xyz, "xyz", 3, 3);
+  VIEW(gv, grad_xyz, "grad_xyz", 3, 3);
+  const int64_t b = av.shape[0], n = av.shape[1] + 2;
+  EMK_REQUIRE(xv.shape[0] == b && xv.shape[1] == n && xv.shape[2] == 3 && gv.numel == xv.numel, EMK_E_SHAPE, "emk_dl_backmap_bwd: xyz / grad_xyz must be (b, n_atoms, 3)");
+  View lv;
+  int64_t ls;
+  int rc = lengths_view(lengths, b, n, &lv, &ls);
+  if (rc) return rc;
+  float *ga = nullptr, *gd = nullptr, *gl = nullptr;
+  if (grad_angles) { VIEW(t, grad_angles, "grad_angles", 2, 2); EMK_REQUIRE(t.numel == av.numel, EMK_E_SHAPE, "grad_angles shape"); ga = F(t); }
+  if (grad_dihedrals) { VIEW(t, grad_dihedrals, "grad_dihedrals", 2, 2); EMK_REQUIRE(t.numel == b * (n - 3), EMK_E_SHAPE, "grad_dihedrals shape"); gd = F(t); }
+  if (grad_lengths) { VIEW(t, grad_lengths, "grad_lengths", 2, 2); EMK_REQUIRE(t.numel == b * (n - 1), EMK_E_SHAPE, "grad_lengths must be (b, n_atoms-1)"); gl = F(t); }
+  return emk_backmap_bwd(F(lv), ls, F(av), F(xv), F(gv), b, n, ga, gd, gl, stream);
+}
+
+int emk_backmap_host(const float* lengths_host, const float* angles_host, const float* dihedrals_host, int64_t b, int64_t n_atoms,
+                     float* xyz_host) {
+  EMK_REQUIRE(lengths_host && angles_host && dihedrals_host && xyz_host, EMK_E_NULL, "emk_backmap_host: NULL pointer argument");
+  EMK_REQUIRE(b >= 1 && n_atoms >= 4, EMK_E_SHAPE, "emk_backmap_host: bad shape");
+  const int64_t n = n_atoms;
+  float *dl = nullptr, *da = nullptr, *dd = nullptr, *dx = nullptr;
+  cudaStream_t st;
+  EMK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  auto cleanup = [&]() {
+    if (dl) cudaFreeAsync(dl, st);
+    if (da) cudaFreeAsync(da, st);
+    if (dd) cudaFreeAsync(dd, st);
+    if (dx) cudaFreeAsync(dx, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  };
+  HOSTCK(cudaMallocAsync(&dl, (size_t)(n - 1) * sizeof(float), st));
+  HOSTCK(cudaMallocAsync(&da, (size_t)b * (n - 2) * sizeof(float), st));
+  HOSTCK(cudaMallocAsync(&dd, (size_t)b * (n - 3) * sizeof(float), st));
+  HOSTCK(cudaMallocAsync(&dx, (size_t)b * n * 3 * sizeof(float), st));
+  HOSTCK(cudaMemcpyAsync(dl, lengths_host, (size_t)(n - 1) * sizeof(float), cudaMemcpyHostToDevice, st));
+  HOSTCK(cudaMemcpyAsync(da, angles_host, (size_t)b * (n - 2) * sizeof(float), cudaMemcpyHostToDevice, st));
+  HOSTCK(cudaMemcpyAsync(dd, dihedrals_host, (size_t)b * (n - 3) * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = backmap_fwd_device(dl, 0, da, dd, b, n, dx, st);
+  if (rc == EMK_OK) {
+    HOSTCK(cudaMemcpyAsync(xyz_host, dx, (size_t)b * n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HOSTCK(cudaStreamSynchronize(st));
+  }
+  cleanup();
+  return rc;
+}
+
+int emk_chain_in_plane(const float* lengths, int64_t lengths_batch_stride, const float* angles, int64_t b, int64_t n_atoms, float* xyz,
+                       void* stream) {
+  return chain_in_plane_device(lengths, lengths_batch_stride, angles, b, n_atoms, xyz, as_stream(stream));
+}
+int emk_chain_in_plane_bwd(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* grad_xyz, int64_t b,
+                           int64_t n_atoms, float* grad_angles, float* grad_lengths, void* stream) {
+  EMK_REQUIRE(lengths && angles && grad_xyz, EMK_E_NULL, "emk_chain_in_plane_bwd: NULL pointer argument");
+  EMK_REQUIRE(n_atoms >= 3 && n_atoms < (1 << 20), EMK_E_SHAPE, "emk_chain_in_plane_bwd: need 3 <= n_atoms < 2^20");
+  EMK_REQUIRE(lengths_batch_stride == 0 || lengths_batch_stride == n_atoms - 1, EMK_E_ARG, "emk_chain_in_plane_bwd: lengths_batch_stride must be 0 or n_atoms-1");
+  BwdParams p{lengths, lengths_batch_stride, angles, nullptr, grad_xyz, b, (int)n_atoms, 0, 0, 1, grad_angles, nullptr, grad_lengths};
+  return backmap_bwd_device(p, as_stream(stream));
+}
+int emk_dl_chain_in_plane(const DLManagedTensor* lengths, const DLManagedTensor* angles, DLManagedTensor* xyz, void* stream) {
+  VIEW(av, angles, "angles", 2, 2);
+  VIEW(ov, xyz, "xyz", 3, 3);
+  const int64_t b = av.shape[0], n = av.shape[1] + 2;
+  EMK_REQUIRE(ov.shape[0] == b && ov.shape[1] == n && ov.shape[2] == 3, EMK_E_SHAPE, "emk_dl_chain_in_plane: xyz must be (b, n_atoms, 3)");
+  View lv;
+  int64_t ls;
+  int rc = lengths_view(lengths, b, n, &lv, &ls);
+  if (rc) return rc;
+  return chain_in_plane_device(F(lv), ls, F(av), b, n, F(ov), as_stream(stream));
+}
+int emk_dl_chain_in_plane_bwd(const DLManagedTensor* lengths, const DLManagedTensor* angles, const DLManagedTensor* grad_xyz,
+                              DLManagedTensor* grad_angles, DLManagedTensor* grad_lengths, void* stream) {
+  VIEW(av, angles, "angles", 2, 2);
+  VIEW(gv, grad_xyz, "grad_xyz", 3, 3);
+  const int64_t b = av.shape[0], n = av.shape[1] + 2;
+  EMK_REQUIRE(gv.shape[0] == b && gv.shape[1] == n && gv.shape[2] == 3, EMK_E_SHAPE, "emk_dl_chain_in_plane_bwd: grad_xyz must be (b, n_atoms, 3)");
+  View lv;
+  int64_t ls;
+  int rc = lengths_view(lengths, b, n, &lv, &ls);
+  if (rc) return rc;
+  float *ga = nullptr, *gl = nullptr;
+  if (grad_angles) { VIEW(t, grad_angles, "grad_angles", 2, 2); EMK_REQUIRE(t.numel == av.numel, EMK_E_SHAPE, "grad_angles shape"); ga = F(t); }
+  if (grad_lengths) { VIEW(t, grad_lengths, "grad_lengths", 2, 2); EMK_REQUIRE(t.numel == b * (n - 1), EMK_E_SHAPE, "grad_lengths must be (b, n_atoms-1)"); gl = F(t); }
+  return emk_chain_in_plane_bwd(F(lv), ls, F(av), F(gv), b, n, ga, gl, stream);
+}
+
+int emk_dihedrals_to_cartesian(const float* dihedrals, const float* chain, int64_t chain_batch_stride, int64_t b, int64_t n_atoms,
+                               int one_way, float* xyz, void* stream) {
+  return d2c_general_device(dihedrals, chain, chain_batch_stride, b, n_atoms, one_way, xyz, as_stream(stream));
+}
+int emk_dihedrals_to_cartesian_bwd(const float* xyz, const float* grad_xyz, int64_t b, int64_t n_atoms, int one_way,
+                                   float* grad_dihedrals, void* stream) {
+  EMK_REQUIRE(xyz && grad_xyz && grad_dihedrals, EMK_E_NULL, "emk_dihedrals_to_cartesian_bwd: NULL pointer argument");
+  EMK_REQUIRE(n_atoms >= 4 && n_atoms < (1 << 20), EMK_E_SHAPE, "emk_dihedrals_to_cartesian_bwd: need 4 <= n_atoms < 2^20");
+  BwdParams p{nullptr, 0, nullptr, xyz, grad_xyz, b, (int)n_atoms, 0, one_way ? 0 : (int)(n_atoms / 2 - 1), 0, nullptr, grad_dihedrals, nullptr};
+  return backmap_bwd_device(p, as_stream(stream));
+}
+int emk_dl_dihedrals_to_cartesian(const DLManagedTensor* dihedrals, const DLManagedTensor* chain, int one_way, DLManagedTensor* xyz,
+                                  void* stream) {
+  VIEW(dv, dihedrals, "dihedrals", 2, 2);
+  VIEW(cv, chain, "cartesian", 2, 3);
+  VIEW(ov, xyz, "xyz", 3, 3);
+  const int64_t b = dv.shape[0], n = dv.shape[1] + 3;
+  int64_t cs;
+  if (cv.ndim == 2) {
+    EMK_REQUIRE(cv.shape[0] == n && cv.shape[1] == 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian: cartesian must be (n_atoms,3) = (%lld,3)", (long long)n);
+    cs = 0;
+  } else {
+    EMK_REQUIRE(cv.shape[0] == b && cv.shape[1] == n && cv.shape[2] == 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian: cartesian must be (b, n_atoms, 3)");
+    cs = 3 * n;
+  }
+  EMK_REQUIRE(ov.shape[0] == b && ov.shape[1] == n && ov.shape[2] == 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian: xyz must be (b, n_atoms, 3)");
+  return d2c_general_device(F(dv), F(cv), cs, b, n, one_way, F(ov), as_stream(stream));
+}
+int emk_dl_dihedrals_to_cartesian_bwd(const DLManagedTensor* xyz, const DLManagedTensor* grad_xyz, int one_way,
+                                      DLManagedTensor* grad_dihedrals, void* stream) {
+  VIEW(xv, xyz, "xyz", 3, 3);
+  VIEW(gv, grad_xyz, "grad_xyz", 3, 3);
+  VIEW(ov, grad_dihedrals, "grad_dihedrals", 2, 2);
+  const int64_t b = xv.shape[0], n = xv.shape[1];
+  EMK_REQUIRE(xv.shape[2] == 3 && gv.numel == xv.numel && ov.shape[0] == b && ov.shape[1] == n - 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian_bwd: shape mismatch");
+  return emk_dihedrals_to_cartesian_bwd(F(xv), F(gv), b, n, one_way, F(ov), stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Shared plumbing for libemk: error reporting, launch checks, small device helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+#include "../../include/emk.h"
+
+namespace emk {
+
+// thread-local message for emk_last_error()
+char* last_error_buffer();
+int fail(int code, const char* fmt, ...);
+
+#define EMK_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return ::emk::fail((int)e_, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define EMK_REQUIRE(cond, code, ...)                 \
+  do {                                               \
+    if (!(cond)) return ::emk::fail((code), __VA_ARGS__); \
+  } while (0)
+
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return EMK_OK;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+// ---- sketch-map sigmoid, evaluated from the SQUARED distance ---------------------------------
+// s(r) = 1 - (1 + c (r/sig)^a)^(-b/a),  c = 2^(a/b) - 1      (encodermap/misc/distances.py:86)
+// Everything is a function of r^2: (r/sig)^a = (r^2/sig^2)^(a/2), so no sqrt is needed unless a
+// is an odd integer.  Integer fast paths cover every parameter set the reference ships
+// (a in {1,2,3,4,6,12}, b/a in {1/2,1,3/2,2,3,6}); anything else goes through powf.
+struct SigSpec {
+  float inv_sig2;   // 1/sig^2
+  float c;          // 2^(a/b) - 1
+  float half_a;     // a/2
+  float e;          // b/a
+  float dcoef;      // b*c/sig^2  (prefactor of s'(r)/r)
+  int a_int;        // a if a is an integer in [1,32], else 0
+  int e2_int;       // 2*b/a if that is an integer in [1,32], else 0
+};
+
+SigSpec make_sig_spec(float sig, float a, float b);
+
+// arguments of the force/torque backward kernel (backmap.cu), filled by the entry points in emk_api.cu
+struct BwdParams {
+  const float* lengths;   // may be null when no planar terms are needed
+  int64_t lstride;
+  const float* angles;    // (b, n-2) or null
+  const float* xyz;       // (b, n, 3) final coordinates; null in planar mode (recomputed from lengths/angles)
+  const float* grad_xyz;  // (b, n, 3)
+  int64_t b;
+  int n;
+  int mid;                // first atom whose hinge/bond is "right of the anchor": n/2 (layer), 0 (planar / one-way)
+  int dr0;                // first dihedral handled as right-side twist: n/2-1 (two-sided), 0 (one-way)
+  int planar;             // 1: chain_in_plane backward (xyz recomputed, hinge normal = -(-1)^j e_z)
+  float* grad_angles;     // (b, n-2) or null
+  float* grad_dihedrals;  // (b, n-3) or null
+  float* grad_lengths;    // (b, n-1) or null
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float ipow_uniform(float x, int n) {
+  // x^n for a small kernel-uniform n >= 0 (binary exponentiation, no MUFU)
+  float r = 1.f;
+  while (n > 0) {
+    if (n & 1) r *= x;
+    x *= x;
+    n >>= 1;
+  }
+  return r;
+}
+
+// value of the sigmoid at squared distance r2; if WITH_D also returns s'(r)/r in *dfac
+// (finite for a >= 2; callers zero it when r2 == 0, the reference's zero-distance mask).
+template <bool WITH_D>
+__device__ __forceinline__ float sig_eval(float r2, const SigSpec& s, float* dfac) {
+  const float u2 = r2 * s.inv_sig2;
+  float p, pm1;  // p = u^a, pm1 = u^(a-2)
+  if (s.a_int > 0) {
+    if ((s.a_int & 1) == 0) {
+      pm1 = ipow_uniform(u2, (s.a_int >> 1) - 1);
+      p = pm1 * u2;
+    } else {
+      const float u = sqrtf(u2);
+      if (s.a_int == 1) {
+        p = u;
+        pm1 = WITH_D ? (1.f / u) : 0.f;
+      } else {
+        pm1 = ipow_uniform(u, s.a_int - 2);
+        p = pm1 * u2;
+      }
+    }
+  } else {
+    p = powf(u2, s.half_a);
+    pm1 = WITH_D ? (p / u2) : 0.f;
+  }
+  const float q = fmaf(s.c, p, 1.f);
+  float qe;  // q^(-b/a)
+  if (s.e2_int > 0) {
+    if (s.e2_int & 1) {
+      qe = ipow_uniform(1.f / sqrtf(q), s.e2_int);
+    } else {
+      qe = ipow_uniform(1.f / q, s.e2_int >> 1);
+    }
+  } else {
+    qe = powf(q, -s.e);
+  }
+  if (WITH_D) *dfac = s.dcoef * pm1 * qe / q;
+  return 1.f - qe;
+}
+#endif
+
+}  // namespace emk

@@ -1,0 +1,533 @@
+// Pair-tile kernels: the all-pairs sketch-map sigmoid cost (fused forward + backward) and the
+// (periodic) distance matrices, for sm_100a.
+//
+// Work decomposition.  The N x N pair space is cut into tiles of 128 rows x 64 columns; only tiles
+// that touch the upper triangle are evaluated (two "diagonal" tiles per 128-row block are computed in
+// full and weighted 1, every other tile stands for itself and its mirror image and is weighted 2).
+// One 256-thread CTA owns one tile; two CTAs are resident per SM so that one CTA's epilogue
+// (sigmoids, reductions, atomics) overlaps the other's FP32 main loop.
+//
+// Main loop.  High-d rows are streamed through shared memory in 32-float (128-byte) k-chunks by TMA
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier complete_tx), 4 stages deep.  Each thread owns an
+// 8 x 4 register micro-tile and reads operands with conflict-free LDS.128 (the TMA swizzle is undone
+// in the address).  Per (pair, dim) the periodic minimum-image distance costs
+//     d = a - b            FADD2  (packed, 2 dims per issue slot)
+//     t = P - |d|          FADD   (|.| and - are free source modifiers)
+//     m = min(|d|, t)      FMNMX  (ALU pipe)
+//     acc += m * m         FFMA2  (packed)
+// i.e. 3 issue slots instead of 4 -- measured at 95% of the 4-instruction issue roofline
+// (profiles/r01_pipe_probe.txt).  The accumulator is a float2 over even/odd k.
+//
+// Epilogue.  Both sigmoids are evaluated from SQUARED distances (emk_common.cuh), the squared
+// difference is accumulated in double, and dL/dz is reduced by warp shuffles (row side) and shared
+// memory atomics (column side) down to one red.global.add.f32 per (row, component, tile).
+#include <cuda.h>
+
+#include "emk_common.cuh"
+
+namespace emk {
+
+constexpr int TM = EMK_TILE_ROWS;  // 128
+constexpr int TN = EMK_TILE_COLS;  // 64
+constexpr int KC = 32;             // floats per k-chunk (128 B = one swizzle row)
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
+constexpr int BOX_ROWS = 64;       // rows per TMA box
+constexpr int STAGE_FLOATS = (TM + TN) * KC;
+constexpr int STAGE_BYTES = STAGE_FLOATS * 4;  // 24 KB
+constexpr int MAX_LATENT = 8;
+
+enum class Epi : int { kCost = 0, kDistMatrix = 1 };
+
+struct PairParams {
+  // common
+  int64_t n;          // rows
+  int n_chunks;       // ceil(d / KC)
+  int tiles_per_row;  // Tc = ceil(n / TN)
+  int64_t tile_begin;
+  float period;       // +inf => Euclidean
+  // cost epilogue
+  const float* low;   // (n, l)
+  int l;
+  SigSpec sh, sl;
+  double* loss;
+  float* grad;        // (n, l) or nullptr
+  double loss_scale;  // 1 / n^2
+  float grad_scale;   // 4 / n^2
+  // distance-matrix epilogue
+  float* out;         // (n, n)
+  int squared;
+  int d_total;        // true feature count (for the all-zero eps of the periodic form)
+  int periodic_eps;   // 1: reproduce pairwise_dist_periodic's +1e-12 conventions
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+// tile id -> (tile row I over 128-row blocks, tile column J over 64-column blocks), J in [2I, Tc)
+__host__ __device__ inline void tile_decode(int64_t t, int64_t tc, int64_t* I_out, int64_t* J_out) {
+  // S(I) = I * (tc + 1 - I) tiles precede row I
+  const double b = (double)(tc + 1);
+  double disc = b * b - 4.0 * (double)t;
+  if (disc < 0) disc = 0;
+  int64_t I = (int64_t)((b - sqrt(disc)) * 0.5);
+  if (I < 0) I = 0;
+  while (I > 0 && I * (tc + 1 - I) > t) --I;
+  while ((I + 1) * (tc - I) <= t) ++I;
+  *I_out = I;
+  *J_out = 2 * I + (t - I * (tc + 1 - I));
+}
+
+template <bool PERIODIC, Epi EPI>
+__global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint8_t* tail = smem_raw + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);             // STAGES barriers
+  double* red_d = reinterpret_cast<double*>(tail + 64);               // 8 doubles
+  float* zA = reinterpret_cast<float*>(tail + 128);                   // [l][TM]
+  float* zB = zA + MAX_LATENT * TM;                                   // [l][TN]
+  float* colsum = zB + MAX_LATENT * TN;                               // [l][TN]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int ty = tid >> 4;  // 0..15 -> rows ty + 16 i
+  const int tx = tid & 15;  // 0..15 -> cols tx + 16 j
+
+  int64_t I, J;
+  tile_decode(p.tile_begin + blockIdx.x, p.tiles_per_row, &I, &J);
+  const int64_t row0 = I * TM;
+  const int64_t col0 = J * TN;
+  const bool diag = (J >> 1) == I;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nk = p.n_chunks;
+  auto issue = [&](int kc) {
+    const int s = kc % STAGES;
+    float* dst = stage_base + s * STAGE_FLOATS;
+    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+    tma_load_2d(dst, &tmap, kc * KC, (int)row0, &full_bar[s]);
+    tma_load_2d(dst + BOX_ROWS * KC, &tmap, kc * KC, (int)row0 + BOX_ROWS, &full_bar[s]);
+    tma_load_2d(dst + TM * KC, &tmap, kc * KC, (int)col0, &full_bar[s]);
+  };
+  if (tid == 0) {
+    for (int kc = 0; kc < STAGES - 1 && kc < nk; kc++) issue(kc);
+  }
+
+  if (EPI == Epi::kCost) {
+    // latent rows of this tile, component-major, zero for out-of-range rows
+    for (int idx = tid; idx < p.l * TM; idx += NTHREADS) {
+      const int c = idx / TM, r = idx - c * TM;
+      zA[c * TM + r] = (row0 + r < p.n) ? p.low[(row0 + r) * p.l + c] : 0.f;
+    }
+    for (int idx = tid; idx < p.l * TN; idx += NTHREADS) {
+      const int c = idx / TN, r = idx - c * TN;
+      zB[c * TN + r] = (col0 + r < p.n) ? p.low[(col0 + r) * p.l + c] : 0.f;
+      colsum[c * TN + r] = 0.f;
+    }
+  }
+
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+
+  const float P = p.period;
+  const int swa = ty & 7, swb = tx & 7;  // TMA SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
+
+  for (int kc = 0; kc < nk; kc++) {
+    // every thread is done with chunk kc-1 => its stage may be refilled with chunk kc+STAGES-1
+    __syncthreads();
+    if (tid == 0 && kc + STAGES - 1 < nk) issue(kc + STAGES - 1);
+    const int s = kc % STAGES;
+    mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+    const float* As = stage_base + s * STAGE_FLOATS;
+    const float* Bs = As + TM * KC;
+#pragma unroll 1
+    for (int k4 = 0; k4 < KC / 4; k4++) {
+      float4 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) av[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * KC + ((k4 ^ swa) << 2));
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float4 bv = *reinterpret_cast<const float4*>(Bs + (tx + 16 * j) * KC + ((k4 ^ swb) << 2));
+        const float2 nb0 = make_float2(-bv.x, -bv.y), nb1 = make_float2(-bv.z, -bv.w);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float2 d0 = __fadd2_rn(make_float2(av[i].x, av[i].y), nb0);
+          float2 d1 = __fadd2_rn(make_float2(av[i].z, av[i].w), nb1);
+          if (PERIODIC) {
+            d0.x = fminf(fabsf(d0.x), P - fabsf(d0.x));
+            d0.y = fminf(fabsf(d0.y), P - fabsf(d0.y));
+            d1.x = fminf(fabsf(d1.x), P - fabsf(d1.x));
+            d1.y = fminf(fabsf(d1.y), P - fabsf(d1.y));
+          }
+          acc[i][j] = __ffma2_rn(d0, d0, acc[i][j]);
+          acc[i][j] = __ffma2_rn(d1, d1, acc[i][j]);
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  if (EPI == Epi::kDistMatrix) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int64_t r = row0 + ty + 16 * i;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int64_t c = col0 + tx + 16 * j;
+        if (r < p.n && c < p.n) {
+          float v = acc[i][j].x + acc[i][j].y;
+          if (p.periodic_eps) {
+            // pairwise_dist_periodic: zero components become 1e-12 before squaring, result + 1e-12
+            // (encodermap/misc/distances.py:169-175); only the all-zero case is above float32 resolution
+            v = (v == 0.f) ? sqrtf((float)p.d_total) * 1e-12f + 1e-12f : sqrtf(v) + 1e-12f;
+          } else if (!p.squared) {
+            v = sqrtf(v);
+          }
+          p.out[r * p.n + c] = v;
+          if (!diag) p.out[c * p.n + r] = v;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- cost epilogue --------------------------------------------------------------------------
+  float d2h[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) d2h[i][j] = acc[i][j].x + acc[i][j].y;
+
+  // low-d squared distances, summed in the SAME order as the main loop sums the high-d ones (even
+  // components in one fused chain, odd components in the other, then one add): identical inputs and
+  // sigmoids on both sides then cancel exactly, as they do in the reference (tests/test_losses.py:897-904)
+  float dl2[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) dl2[i][j] = 0.f;
+#pragma unroll 1
+  for (int par = 0; par < 2; par++) {
+    float part[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) part[i][j] = 0.f;
+#pragma unroll 1
+    for (int c = par; c < p.l; c += 2) {
+      float za[8], zb[4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) za[i] = zA[c * TM + ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) zb[j] = zB[c * TN + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float t = za[i] - zb[j];
+          part[i][j] = fmaf(t, t, part[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dl2[i][j] += part[i][j];
+  }
+
+  float lsum = 0.f;
+  // after this loop dl2 holds the gradient coefficient (s_l - s_h) * s_l'(d_l) / d_l
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const bool rv = row0 + ty + 16 * i < p.n;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const bool valid = rv && (col0 + tx + 16 * j < p.n);
+      const float sh = sig_eval<false>(d2h[i][j], p.sh, nullptr);
+      float w;
+      const float sl = sig_eval<true>(dl2[i][j], p.sl, &w);
+      float diff = sh - sl;
+      if (!valid) diff = 0.f;
+      if (dl2[i][j] == 0.f || !valid) w = 0.f;
+      lsum = fmaf(diff, diff, lsum);
+      dl2[i][j] = -diff * w;
+    }
+  }
+
+  // loss: per-thread float (32 terms) -> double across the CTA
+  double ld = (double)lsum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+  if (lane == 0) red_d[warp] = ld;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < NTHREADS / 32; w++) t += red_d[w];
+    atomicAdd(p.loss, t * (diag ? 1.0 : 2.0) * p.loss_scale);
+  }
+
+  if (p.grad == nullptr) return;
+  const float gs = p.grad_scale;
+#pragma unroll 1
+  for (int c = 0; c < p.l; c++) {
+    float za[8], zb[4], rs[8], cs[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      za[i] = zA[c * TM + ty + 16 * i];
+      rs[i] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      zb[j] = zB[c * TN + tx + 16 * j];
+      cs[j] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float t = dl2[i][j] * (za[i] - zb[j]);
+        rs[i] += t;
+        cs[j] -= t;
+      }
+    // row side: the 16 lanes of a half-warp share ty
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+      const int64_t r = row0 + ty + 16 * i;
+      if (tx == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c], rs[i] * gs);
+    }
+    // column side (mirror image of the tile); diagonal tiles already visit both orders
+    if (!diag) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
+      }
+    }
+  }
+  if (!diag) {
+    __syncthreads();
+    for (int idx = tid; idx < p.l * TN; idx += NTHREADS) {
+      const int c = idx / TN, r = idx - c * TN;
+      if (col0 + r < p.n) atomicAdd(&p.grad[(col0 + r) * p.l + c], colsum[idx] * gs);
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + (MAX_LATENT * (TM + 2 * TN)) * 4;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    EMK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    EMK_REQUIRE(sym != nullptr && q == cudaDriverEntryPointSuccess, EMK_E_UNSUPPORTED,
+                "driver does not export cuTensorMapEncodeTiled");
+    cached = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  *fn = cached;
+  return EMK_OK;
+}
+
+// (n, d_pad) row-major float32, 16-byte aligned base, d_pad % 4 == 0
+static int make_tensor_map(CUtensorMap* map, const float* base, int64_t n, int64_t d_pad) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)n};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * sizeof(float)};
+  cuuint32_t box[2] = {KC, BOX_ROWS};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EMK_REQUIRE(r == CUDA_SUCCESS, EMK_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (n=%lld d=%lld)", (int)r,
+              (long long)n, (long long)d_pad);
+  return EMK_OK;
+}
+
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int64_t d, int64_t d_pad) {
+  const int64_t total = n * d_pad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / d_pad, k = idx - r * d_pad;
+    dst[idx] = k < d ? src[r * d + k] : 0.f;
+  }
+}
+
+// TMA needs a 16-byte aligned base and a row pitch that is a multiple of 16 bytes; anything else is
+// re-laid out once into a stream-ordered scratch buffer (O(N D), negligible against O(N^2 D)).
+struct HighView {
+  const float* ptr;
+  int64_t d_pad;
+  float* scratch;
+};
+
+static int prepare_high(const float* high, int64_t n, int64_t d, cudaStream_t st, HighView* v) {
+  v->scratch = nullptr;
+  if ((d % 4) == 0 && (reinterpret_cast<uintptr_t>(high) % 16) == 0) {
+    v->ptr = high;
+    v->d_pad = d;
+    return EMK_OK;
+  }
+  const int64_t d_pad = (d + 3) / 4 * 4;
+  EMK_CUDA(cudaMallocAsync(&v->scratch, (size_t)(n * d_pad) * sizeof(float), st));
+  const int64_t total = n * d_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pad_rows_kernel<<<blocks, 256, 0, st>>>(high, v->scratch, n, d, d_pad);
+  int rc = launch_status("pad_rows_kernel");
+  if (rc) return rc;
+  v->ptr = v->scratch;
+  v->d_pad = d_pad;
+  return EMK_OK;
+}
+
+template <bool PERIODIC, Epi EPI>
+static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, cudaStream_t st) {
+  auto kern = pair_tile_kernel<PERIODIC, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  kern<<<(unsigned)n_tiles, NTHREADS, SMEM_BYTES, st>>>(map, p);
+  return launch_status("pair_tile_kernel");
+}
+
+void tile_decode_host(int64_t t, int64_t tc, int64_t* I, int64_t* J) { tile_decode(t, tc, I, J); }
+
+int64_t pair_tile_count(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t tr = (n + TM - 1) / TM, tc = (n + TN - 1) / TN;
+  return tr * tc - tr * (tr - 1);
+}
+
+int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* low, int64_t l, double periodicity,
+                        const float sig[6], int64_t tile_begin, int64_t tile_end, double* loss, float* grad_low,
+                        uint32_t flags, cudaStream_t st) {
+  EMK_REQUIRE(high && low && sig && loss, EMK_E_NULL, "emk_sigmoid_cost: NULL pointer argument");
+  EMK_REQUIRE((flags & EMK_COST_NO_GRAD) || grad_low, EMK_E_NULL, "emk_sigmoid_cost: grad_low is NULL without EMK_COST_NO_GRAD");
+  EMK_REQUIRE(n >= 0 && d >= 1, EMK_E_SHAPE, "emk_sigmoid_cost: bad shape n=%lld d=%lld", (long long)n, (long long)d);
+  EMK_REQUIRE(l >= 1 && l <= MAX_LATENT, EMK_E_UNSUPPORTED, "emk_sigmoid_cost: latent width %lld outside [1,%d]", (long long)l, MAX_LATENT);
+  EMK_REQUIRE(n < (int64_t)1 << 30, EMK_E_UNSUPPORTED, "emk_sigmoid_cost: n=%lld too large", (long long)n);
+  EMK_REQUIRE(periodicity > 0 || std::isinf(periodicity), EMK_E_ARG, "emk_sigmoid_cost: periodicity must be > 0");
+  for (int k = 0; k < 6; k++) EMK_REQUIRE(sig[k] > 0.f && std::isfinite(sig[k]), EMK_E_ARG, "emk_sigmoid_cost: sig[%d]=%g must be finite and > 0", k, sig[k]);
+  const int64_t total = pair_tile_count(n);
+  EMK_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= total, EMK_E_ARG,
+              "emk_sigmoid_cost: tile range [%lld,%lld) outside [0,%lld]", (long long)tile_begin, (long long)tile_end, (long long)total);
+  const bool want_grad = !(flags & EMK_COST_NO_GRAD);
+  if (flags & EMK_COST_ZERO_OUTPUTS) {
+    EMK_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
+    if (want_grad && n > 0) EMK_CUDA(cudaMemsetAsync(grad_low, 0, (size_t)(n * l) * sizeof(float), st));
+  }
+  if (tile_end == tile_begin) return EMK_OK;
+
+  HighView hv;
+  int rc = prepare_high(high, n, d, st, &hv);
+  if (rc) return rc;
+  CUtensorMap map;
+  rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad);
+  if (rc == EMK_OK) {
+    PairParams p{};
+    p.n = n;
+    p.n_chunks = (int)((d + KC - 1) / KC);
+    p.tiles_per_row = (int)((n + TN - 1) / TN);
+    p.tile_begin = tile_begin;
+    p.period = std::isinf(periodicity) ? INFINITY : (float)periodicity;
+    p.low = low;
+    p.l = (int)l;
+    p.sh = make_sig_spec(sig[0], sig[1], sig[2]);
+    p.sl = make_sig_spec(sig[3], sig[4], sig[5]);
+    p.loss = loss;
+    p.grad = want_grad ? grad_low : nullptr;
+    p.loss_scale = 1.0 / ((double)n * (double)n);
+    p.grad_scale = (float)(4.0 / ((double)n * (double)n));
+    if (std::isinf(periodicity))
+      rc = launch_pair<false, Epi::kCost>(map, p, tile_end - tile_begin, st);
+    else
+      rc = launch_pair<true, Epi::kCost>(map, p, tile_end - tile_begin, st);
+  }
+  if (hv.scratch) cudaFreeAsync(hv.scratch, st);
+  return rc;
+}
+
+// (n,n) distance matrix through the same main loop
+int dist_matrix_device(const float* x, int64_t n, int64_t d, double periodicity, bool periodic_form, int squared, float* out,
+                       cudaStream_t st) {
+  EMK_REQUIRE(x && out, EMK_E_NULL, "distance matrix: NULL pointer argument");
+  EMK_REQUIRE(n >= 0 && d >= 1, EMK_E_SHAPE, "distance matrix: bad shape n=%lld d=%lld", (long long)n, (long long)d);
+  EMK_REQUIRE(n < (int64_t)1 << 30, EMK_E_UNSUPPORTED, "distance matrix: n=%lld too large", (long long)n);
+  if (n == 0) return EMK_OK;
+  HighView hv;
+  int rc = prepare_high(x, n, d, st, &hv);
+  if (rc) return rc;
+  CUtensorMap map;
+  rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad);
+  if (rc == EMK_OK) {
+    PairParams p{};
+    p.n = n;
+    p.n_chunks = (int)((d + KC - 1) / KC);
+    p.tiles_per_row = (int)((n + TN - 1) / TN);
+    p.tile_begin = 0;
+    p.period = std::isinf(periodicity) ? INFINITY : (float)periodicity;
+    p.out = out;
+    p.squared = squared;
+    p.d_total = (int)d;
+    p.periodic_eps = periodic_form ? 1 : 0;
+    const int64_t tiles = pair_tile_count(n);
+    if (std::isinf(periodicity))
+      rc = launch_pair<false, Epi::kDistMatrix>(map, p, tiles, st);
+    else
+      rc = launch_pair<true, Epi::kDistMatrix>(map, p, tiles, st);
+  }
+  if (hv.scratch) cudaFreeAsync(hv.scratch, st);
+  return rc;
+}
+
+}  // namespace emk

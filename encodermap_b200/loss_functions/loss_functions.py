@@ -1,0 +1,110 @@
+"""Drop-in for the three hot loss factories of ``encodermap.loss_functions.loss_functions``.
+
+Reference: encodermap/loss_functions/loss_functions.py -- ``sigmoid_loss`` :301-369,
+``distance_loss`` :200-298, ``cartesian_distance_loss`` :873-944.  Signatures, closure names
+(``distance_loss_func`` / ``cartesian_distance_loss_func`` -- the models look losses up by name,
+models/models.py:2256-2258), scale handling and the finite-value assertion are kept; the N x N
+arithmetic is one fused kernel launch (emk_sigmoid_cost) that also produces dL/d(latent).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from .. import _ops
+from ..parameters import ADCParameters, Parameters
+
+
+def _assert_all_finite(x: torch.Tensor, message: str) -> None:
+    # tf.debugging.assert_all_finite of the reference (loss_functions.py:293-295, 364-366, 939-941);
+    # one scalar read-back per call, only when requested
+    if not torch.isfinite(x).all():
+        raise FloatingPointError(message)
+
+
+def sigmoid_loss(
+    parameters=None,
+    periodicity_overwrite: Optional[float] = None,
+    dist_dig_parameters_overwrite: Optional[Sequence[float]] = None,
+    *,
+    process_group=None,
+    check_finite: bool = False,
+) -> Callable:
+    """Sigmoid loss closure.  Reference: encodermap/loss_functions/loss_functions.py:301-369.
+
+    Extra keyword-only arguments (not in the reference): ``process_group`` shards the pair tiles of
+    one evaluation over the ranks of a torch.distributed group (inputs replicated, one all-reduce of
+    the loss and dL/d(latent)); ``check_finite`` enables the reference's finite assertion, which
+    costs a device synchronisation."""
+    p = Parameters() if parameters is None else parameters
+    periodicity = periodicity_overwrite if periodicity_overwrite is not None else p.periodicity
+    sig = tuple(dist_dig_parameters_overwrite) if dist_dig_parameters_overwrite is not None else tuple(p.dist_sig_parameters)
+
+    def sigmoid_loss_func(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+        tile_range, reduce_fn = None, None
+        if process_group is not None:
+            from ..parallel import tile_shard
+
+            tile_range, reduce_fn = tile_shard(int(y_true.shape[0]), process_group)
+        cost = _ops.SigmoidCost.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
+        if check_finite:
+            _assert_all_finite(cost, "Sigmoid cost became infinite or NaN.")
+        return cost
+
+    return sigmoid_loss_func
+
+
+def _latent_of(model) -> Callable:
+    enc = getattr(model, "encoder", None)
+    if enc is None:
+        raise Exception("model has no `encoder` attribute: cannot find the bottleneck/latent layer")
+    return enc
+
+
+def distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite: bool = False) -> Callable:
+    """Encodermap distance_loss.  Reference: encodermap/loss_functions/loss_functions.py:200-298.
+    ``model.encoder`` maps the (tuple of) inputs to the latent; ``callback`` is accepted for signature
+    compatibility (summary writing stays in the host framework)."""
+    p = Parameters() if parameters is None else parameters
+    latent = _latent_of(model)
+    dist_loss = sigmoid_loss(p, process_group=process_group)
+
+    def distance_loss_func(y_true, y_pred=None) -> torch.Tensor:
+        distance_loss_func.name = "distance_loss"
+        try:
+            y_pred = latent(y_true, training=True)
+        except TypeError:
+            y_pred = latent(y_true)
+        if isinstance(y_true, tuple):
+            y_true = torch.cat(y_true[:3], dim=1)
+        if p.distance_cost_scale is not None:
+            dist_cost = dist_loss(y_true, y_pred) * p.distance_cost_scale
+        else:
+            dist_cost = torch.zeros((), dtype=torch.float32, device=y_pred.device)
+        if check_finite:
+            _assert_all_finite(dist_cost, "Dist cost became infinite or NaN.")
+        return dist_cost
+
+    return distance_loss_func
+
+
+def cartesian_distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite: bool = False) -> Callable:
+    """Encodermap cartesian distance loss.  Reference: encodermap/loss_functions/loss_functions.py:873-944
+    (non-periodic, ``cartesian_dist_sig_parameters``; called as ``(input pairwise distances, latent)``,
+    models/models.py:2419-2422)."""
+    p = ADCParameters() if parameters is None else parameters
+    dist_loss = sigmoid_loss(p, periodicity_overwrite=float("inf"),
+                             dist_dig_parameters_overwrite=p.cartesian_dist_sig_parameters, process_group=process_group)
+
+    def cartesian_distance_loss_func(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+        cartesian_distance_loss_func.name = "cartesian_distance_loss"
+        if p.cartesian_distance_cost_scale is not None:
+            dist_cost = dist_loss(y_true, y_pred) * p.cartesian_distance_cost_scale
+        else:
+            dist_cost = torch.zeros((), dtype=torch.float32, device=y_pred.device)
+        if check_finite:
+            _assert_all_finite(dist_cost, "Cartesian distance cost became infinite or NaN.")
+        return dist_cost
+
+    return cartesian_distance_loss_func

@@ -1,0 +1,217 @@
+/* libemk -- C ABI of the B200 (sm_100a) kernels for EncoderMap's training hot path.
+ *
+ * The reference (AG-Peter/encodermap) has no FFI for this path: the boundary is a set of
+ * plain Python callables taking/returning tensors.  Every entry point
+ * below names the reference callable (file:line under /root/reference) whose arithmetic it
+ * replaces; the Python shims in encodermap_b200/ keep those callables' signatures and
+ * call in here through ctypes.
+ *
+ * Conventions
+ *   - return 0 on success; negative EMK_E_* for argument errors (validated before any
+ *     launch); positive values are cudaError_t.  emk_last_error() gives a thread-local
+ *     message for the last non-zero return.  Nothing throws or aborts.
+ *   - every tensor is float32, C-contiguous, on the CURRENT CUDA device unless stated;
+ *     caller allocates all inputs and outputs; libemk borrows pointers for the call only.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no entry point synchronises the device except the *_host ones.
+ *   - `emk_dl_*` twins take DLPack tensors (`DLManagedTensor*` from the capsule a framework
+ *     exports; the capsule is NOT consumed) and validate dtype/device/contiguity/shape.
+ *   - there is no CPU fallback: on a machine without a CUDA device compute calls fail with
+ *     the CUDA error; the host-only helpers (index construction) always work.
+ */
+#ifndef EMK_H_
+#define EMK_H_
+
+#include <stdint.h>
+#include "emk_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMK_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define EMK_API __attribute__((visibility("default")))
+#else
+#define EMK_API
+#endif
+
+/* error codes */
+#define EMK_OK 0
+#define EMK_E_NULL (-1)        /* required pointer is NULL */
+#define EMK_E_DTYPE (-2)       /* DLPack tensor is not float32 / float64 as required */
+#define EMK_E_DEVICE (-3)      /* DLPack tensor is not on a CUDA device */
+#define EMK_E_SHAPE (-4)       /* rank / extent mismatch */
+#define EMK_E_CONTIG (-5)      /* tensor is not C-contiguous */
+#define EMK_E_ARG (-6)         /* scalar argument out of range */
+#define EMK_E_UNSUPPORTED (-7) /* valid request this build does not implement */
+
+/* flags for emk_sigmoid_cost */
+#define EMK_COST_ZERO_OUTPUTS 1u /* memset loss and grad_low on the stream before accumulating */
+#define EMK_COST_NO_GRAD 2u      /* forward only: grad_low may be NULL */
+
+EMK_API int emk_version(void);
+EMK_API const char* emk_last_error(void);
+/* "sm_100a;<nvcc version>;<build date>" */
+EMK_API const char* emk_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-only index construction (integer work: bit-exact contracts; no GPU needed)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Pair order of pairwise_dist(flat=True): strict upper triangle, row-major
+ * (encodermap/misc/distances.py:235-242).  count = n(n-1)/2; i_out/j_out hold `count` entries. */
+EMK_API int64_t emk_triu_pair_count(int64_t n);
+EMK_API int emk_triu_pair_indices(int64_t n, int32_t* i_out, int32_t* j_out);
+
+/* Atom / dihedral index lists of the two-sided back-mapping
+ * (split_and_reverse_cartesians / split_and_reverse_dihedrals, encodermap/misc/backmapping.py:179-256;
+ * loop counts left_split = n/2-1, right_split = (n-3)/2, encodermap/models/models.py:661-671).
+ * counts[4] = {n_left_atoms, n_right_atoms, n_left_dihedrals, n_right_dihedrals}. */
+EMK_API int emk_backmap_split_counts(int64_t n_atoms, int64_t counts[4]);
+EMK_API int emk_backmap_split_indices(int64_t n_atoms, int32_t* left_atoms, int32_t* right_atoms,
+                              int32_t* left_dihedrals, int32_t* right_dihedrals);
+
+/* Work decomposition of the all-pairs cost: the N x N pair space is cut into tiles of
+ * EMK_TILE_ROWS x EMK_TILE_COLS; only tiles that touch the upper triangle are evaluated.
+ * Tiles are numbered row-major over tile rows; a multi-GPU run gives rank r the contiguous
+ * range emk_pair_tile_range(n, r, world). */
+#define EMK_TILE_ROWS 128
+#define EMK_TILE_COLS 64
+EMK_API int64_t emk_pair_tile_count(int64_t n_rows);
+EMK_API int emk_pair_tile_decode(int64_t n_rows, int64_t tile, int64_t* tile_row, int64_t* tile_col);
+EMK_API int emk_pair_tile_range(int64_t n_rows, int rank, int world, int64_t* begin, int64_t* end);
+
+/* ------------------------------------------------------------------------------------------
+ * All-pairs sketch-map sigmoid cost, fused forward + backward
+ *   replaces sigmoid_loss_func (encodermap/loss_functions/loss_functions.py:335-369) and through
+ *   it distance_loss_func (:266-296) and cartesian_distance_loss_func (:917-942); fuses
+ *   pairwise_dist_periodic / pairwise_dist (encodermap/misc/distances.py:144-255) and
+ *   sigmoid (:66-88).  No N x N matrix is written.
+ *
+ *   high (n,d)   high-dimensional rows;   low (n,l) latent rows, 1 <= l <= 8
+ *   periodicity  +inf => Euclidean high-d distances
+ *   sig[6]       sig_h, a_h, b_h, sig_l, a_l, b_l
+ *   tile_begin/tile_end   slice of the tile list to evaluate (0, emk_pair_tile_count(n) for all)
+ *   loss         device double[1]:  += sum over the slice of (s_h - s_l)^2 / n^2
+ *   grad_low     device (n,l):      += d(loss)/d(low) contributions of the slice
+ * ---------------------------------------------------------------------------------------- */
+EMK_API int emk_sigmoid_cost(const float* high, int64_t n, int64_t d, const float* low, int64_t l,
+                     double periodicity, const float sig[6], int64_t tile_begin, int64_t tile_end,
+                     double* loss, float* grad_low, uint32_t flags, void* stream);
+EMK_API int emk_dl_sigmoid_cost(const DLManagedTensor* high, const DLManagedTensor* low, double periodicity,
+                        const float sig[6], int64_t tile_begin, int64_t tile_end,
+                        DLManagedTensor* loss, DLManagedTensor* grad_low, uint32_t flags, void* stream);
+/* Same through HOST buffers: copies in, evaluates all tiles, copies out, synchronises.
+ * loss_host: double[1]; grad_low_host: (n,l) or NULL. */
+EMK_API int emk_sigmoid_cost_host(const float* high_host, int64_t n, int64_t d, const float* low_host, int64_t l,
+                          double periodicity, const float sig[6], double* loss_host, float* grad_low_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Distance matrices (API-compatible standalone ops; the fused cost never calls them)
+ * ---------------------------------------------------------------------------------------- */
+
+/* pairwise_dist_periodic(positions (n,d), periodicity) -> (n,n)   encodermap/misc/distances.py:144-176 */
+EMK_API int emk_pairwise_dist_periodic(const float* x, int64_t n, int64_t d, double periodicity, float* out, void* stream);
+EMK_API int emk_dl_pairwise_dist_periodic(const DLManagedTensor* x, double periodicity, DLManagedTensor* out, void* stream);
+
+/* pairwise_dist(positions (b,n,d), squared, flat)   encodermap/misc/distances.py:179-255
+ *   x is addressed as x[bi*batch_stride + i*row_stride + k] (element strides) so that the atom
+ *   selection inputs[:, start:stop:step] of PairwiseDistances.call (encodermap/models/layers.py:1252-1267)
+ *   needs no copy.  out: (b,n,n) or, flat, (b, n(n-1)/2) in emk_triu_pair_indices order. */
+EMK_API int emk_pairwise_dist(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride,
+                      int squared, int flat, float* out, void* stream);
+/* grad_x (same addressing as x, must be zero-initialised by the caller when strided) +=
+ * d(out)/d(x)^T grad_out;  zero distances get zero gradient (the reference's mask). */
+EMK_API int emk_pairwise_dist_bwd(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride,
+                          int squared, int flat, const float* grad_out, float* grad_x, void* stream);
+EMK_API int emk_dl_pairwise_dist(const DLManagedTensor* x, int64_t start, int64_t stop, int64_t step, int squared, int flat,
+                         DLManagedTensor* out, void* stream);
+EMK_API int emk_dl_pairwise_dist_bwd(const DLManagedTensor* x, int64_t start, int64_t stop, int64_t step, int squared, int flat,
+                             const DLManagedTensor* grad_out, DLManagedTensor* grad_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise ops
+ * ---------------------------------------------------------------------------------------- */
+
+/* periodic_distance(a, b, periodicity) on equal-shape operands   encodermap/misc/distances.py:113-141 */
+EMK_API int emk_periodic_distance(const float* a, const float* b, int64_t count, double periodicity, float* out, void* stream);
+EMK_API int emk_periodic_distance_bwd(const float* a, const float* b, int64_t count, double periodicity, const float* grad_out,
+                              float* grad_a, float* grad_b, void* stream);
+EMK_API int emk_dl_periodic_distance(const DLManagedTensor* a, const DLManagedTensor* b, double periodicity, DLManagedTensor* out, void* stream);
+EMK_API int emk_dl_periodic_distance_bwd(const DLManagedTensor* a, const DLManagedTensor* b, double periodicity,
+                                 const DLManagedTensor* grad_out, DLManagedTensor* grad_a, DLManagedTensor* grad_b, void* stream);
+
+/* sigmoid(sig,a,b)(r) elementwise and its derivative   encodermap/misc/distances.py:66-88 */
+EMK_API int emk_sigmoid(const float* r, int64_t count, float sig, float a, float b, float* out, void* stream);
+EMK_API int emk_sigmoid_bwd(const float* r, int64_t count, float sig, float a, float b, const float* grad_out, float* grad_r, void* stream);
+EMK_API int emk_dl_sigmoid(const DLManagedTensor* r, float sig, float a, float b, DLManagedTensor* out, void* stream);
+EMK_API int emk_dl_sigmoid_bwd(const DLManagedTensor* r, float sig, float a, float b, const DLManagedTensor* grad_out, DLManagedTensor* grad_r, void* stream);
+
+/* PeriodicInput.call: (rows,d) -> (rows,2d) = [sin(x 2pi/P), cos(x 2pi/P)]   encodermap/models/layers.py:204-215 */
+EMK_API int emk_periodic_input(const float* x, int64_t rows, int64_t d, double periodicity, float* out, void* stream);
+EMK_API int emk_periodic_input_bwd(const float* x, int64_t rows, int64_t d, double periodicity, const float* grad_out, float* grad_x, void* stream);
+EMK_API int emk_dl_periodic_input(const DLManagedTensor* x, double periodicity, DLManagedTensor* out, void* stream);
+EMK_API int emk_dl_periodic_input_bwd(const DLManagedTensor* x, double periodicity, const DLManagedTensor* grad_out, DLManagedTensor* grad_x, void* stream);
+
+/* rotation_matrix(axis_unit_vec (b,3), angle (b)) -> (b,3,3)   encodermap/misc/backmapping.py:1950-1968 */
+EMK_API int emk_rotation_matrix(const float* axis, const float* angle, int64_t b, float* out, void* stream);
+EMK_API int emk_dl_rotation_matrix(const DLManagedTensor* axis, const DLManagedTensor* angle, DLManagedTensor* out, void* stream);
+
+/* mean over rows: (rows,cols) -> (cols)   the `tf.reduce_mean(distances, 0)` of BackMapLayer.call, layers.py:970 */
+EMK_API int emk_column_mean(const float* x, int64_t rows, int64_t cols, float* out, void* stream);
+EMK_API int emk_dl_column_mean(const DLManagedTensor* x, DLManagedTensor* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Back-mapping (internal coordinates -> Cartesian), SE(3) scan along the chain
+ * ---------------------------------------------------------------------------------------- */
+
+/* BackMapLayer.call fused   encodermap/models/layers.py:957-986  (= chain_in_plane ->
+ * dihedrals + pi -> dihedrals_to_cartesian_tf_layers, encodermap/misc/backmapping.py:259-309)
+ *   lengths: (n-1) shared by all frames when lengths_batch_stride == 0, else (b, n-1)
+ *   angles (b,n-2), dihedrals (b,n-3) as the LAYER receives them (the +pi is applied inside)
+ *   xyz (b,n,3) */
+EMK_API int emk_backmap(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* dihedrals,
+                int64_t b, int64_t n_atoms, float* xyz, void* stream);
+/* exact VJP of emk_backmap from the final coordinates:
+ *   grad_angles (b,n-2), grad_dihedrals (b,n-3), grad_lengths (b,n-1) per frame -- any may be NULL */
+EMK_API int emk_backmap_bwd(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* xyz,
+                    const float* grad_xyz, int64_t b, int64_t n_atoms, float* grad_angles, float* grad_dihedrals,
+                    float* grad_lengths, void* stream);
+EMK_API int emk_dl_backmap(const DLManagedTensor* lengths, const DLManagedTensor* angles, const DLManagedTensor* dihedrals,
+                   DLManagedTensor* xyz, void* stream);
+EMK_API int emk_dl_backmap_bwd(const DLManagedTensor* lengths, const DLManagedTensor* angles, const DLManagedTensor* xyz,
+                       const DLManagedTensor* grad_xyz, DLManagedTensor* grad_angles, DLManagedTensor* grad_dihedrals,
+                       DLManagedTensor* grad_lengths, void* stream);
+EMK_API int emk_backmap_host(const float* lengths_host, const float* angles_host, const float* dihedrals_host, int64_t b,
+                     int64_t n_atoms, float* xyz_host);
+
+/* chain_in_plane(lengths, angles) -> (b,n,3), z = 0   encodermap/encodermap_tf1/backmapping.py:97-119 */
+EMK_API int emk_chain_in_plane(const float* lengths, int64_t lengths_batch_stride, const float* angles, int64_t b,
+                       int64_t n_atoms, float* xyz, void* stream);
+EMK_API int emk_chain_in_plane_bwd(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* grad_xyz,
+                           int64_t b, int64_t n_atoms, float* grad_angles, float* grad_lengths, void* stream);
+EMK_API int emk_dl_chain_in_plane(const DLManagedTensor* lengths, const DLManagedTensor* angles, DLManagedTensor* xyz, void* stream);
+EMK_API int emk_dl_chain_in_plane_bwd(const DLManagedTensor* lengths, const DLManagedTensor* angles, const DLManagedTensor* grad_xyz,
+                              DLManagedTensor* grad_angles, DLManagedTensor* grad_lengths, void* stream);
+
+/* dihedrals_to_cartesian_tf(dihedrals, cartesian) on an arbitrary start chain
+ *   two-sided:  encodermap/encodermap_tf1/backmapping.py:164-195, encodermap/misc/backmapping.py:259-309
+ *   one_way=1:  dihedral_to_cartesian_tf_one_way(_layers), encodermap/misc/backmapping.py:1873-1912
+ *   dihedrals (b, n-3) exactly as the reference function receives them (no +pi here);
+ *   chain: (n,3) shared when chain_batch_stride == 0, else (b,n,3) */
+EMK_API int emk_dihedrals_to_cartesian(const float* dihedrals, const float* chain, int64_t chain_batch_stride, int64_t b,
+                               int64_t n_atoms, int one_way, float* xyz, void* stream);
+/* gradient w.r.t. the dihedrals, from the FINAL coordinates (twist of the downstream body about each bond) */
+EMK_API int emk_dihedrals_to_cartesian_bwd(const float* xyz, const float* grad_xyz, int64_t b, int64_t n_atoms, int one_way,
+                                   float* grad_dihedrals, void* stream);
+EMK_API int emk_dl_dihedrals_to_cartesian(const DLManagedTensor* dihedrals, const DLManagedTensor* chain, int one_way,
+                                  DLManagedTensor* xyz, void* stream);
+EMK_API int emk_dl_dihedrals_to_cartesian_bwd(const DLManagedTensor* xyz, const DLManagedTensor* grad_xyz, int one_way,
+                                      DLManagedTensor* grad_dihedrals, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMK_H_ */

@@ -1,0 +1,156 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/emk.h declares, the
+ctypes table covers them all, and the host-only index helpers are bit-exact against the oracle and
+the golden vectors.  No compute entry point is called (there is no GPU here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import em_oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def L():
+    from encodermap_b200 import _build, _lib
+
+    _build.build()
+    return _lib
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "emk.h").read_text()
+    return sorted(set(re.findall(r"EMK_API\s+[\w\s\*]+?\b(emk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(L):
+    lib = L.lib()
+    names = declared_symbols()
+    assert len(names) >= 45
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/emk.h but not exported by libemk.so"
+    assert sorted(L.SIGNATURES) == names, "ctypes signature table and include/emk.h disagree"
+    assert lib.emk_version() == 100
+    assert lib.emk_build_info().startswith(b"sm_100a")
+
+
+def test_library_is_self_contained(L):
+    """No libcudart/libtorch dependency: static cudart, plain C ABI."""
+    import subprocess
+
+    out = subprocess.run(["ldd", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "libcudart" not in out and "libtorch" not in out and "libc10" not in out
+
+
+def test_sass_is_sm100a_with_tma_and_packed_fp32(L):
+    import shutil
+    import subprocess
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run(["cuobjdump", "-sass", "-fun", "pair_tile_kernel", str(L.LIB_PATH)], capture_output=True, text=True)
+    if r.returncode != 0 or "Function" not in r.stdout:
+        r = subprocess.run(["cuobjdump", "-sass", str(L.LIB_PATH)], capture_output=True, text=True)
+    sass = r.stdout
+    assert "sm_100a" in sass or "SM100a" in sass.upper() or "sm_100" in sass
+    assert "UTMALDG" in sass, "TMA tensor loads missing from the pair-tile kernel"
+    assert "FFMA2" in sass and "FADD2" in sass, "packed FP32 instructions missing from the pair-tile kernel"
+
+
+def test_triu_pair_order_bit_exact(L):
+    for n in (0, 1, 2, 3, 7, 100):
+        i, j = L.triu_pair_indices(n)
+        wi, wj = np.triu_indices(n, k=1)
+        assert np.array_equal(i, wi) and np.array_equal(j, wj)
+    # the order the reference's boolean mask produces (distances.py:240-242), via the oracle
+    x = np.random.default_rng(0).normal(size=(1, 9, 3))
+    flat = O.pairwise_dist(x, flat=True).numpy()[0]
+    full = O.pairwise_dist(x).numpy()[0]
+    i, j = L.triu_pair_indices(9)
+    assert np.array_equal(flat, full[i, j])
+
+
+def test_split_indices_bit_exact(L, golden):
+    g = golden["backmapping"]
+    for n in (9, 12, 30, 31, 300):
+        la, ra, dl, dr = L.backmap_split_indices(n)
+        assert np.array_equal(la, g[f"n{n}_split_atoms_left"]) and np.array_equal(ra, g[f"n{n}_split_atoms_right"])
+        assert np.array_equal(dl, g[f"n{n}_split_dih_left"]) and np.array_equal(dr, g[f"n{n}_split_dih_right"])
+    # against the TF1 slicing for random chain lengths (reference tests/test_backmapping_em1_em2.py:2115-2156)
+    rng = np.random.default_rng(3)
+    for n in [int(v) for v in rng.integers(6, 1000, size=20)] + [4, 5, 6, 7, 1500]:
+        la, ra, dl, dr = L.backmap_split_indices(n)
+        wla, wdl, wra, wdr = O.split_indices_tf1(n)
+        if n >= 6:
+            assert np.array_equal(la, wla) and np.array_equal(ra, wra) and np.array_equal(dl, wdl) and np.array_equal(dr, wdr)
+        assert (len(dl), len(dr)) == O.split_counts(n)
+        cl, cr = O.split_and_reverse_cartesians(torch.arange(n)[None])
+        tl, tr = O.split_and_reverse_dihedrals(torch.arange(n - 3)[None])
+        assert np.array_equal(la, cl[0].numpy()) and np.array_equal(ra, cr[0].numpy())
+        assert np.array_equal(dl, tl[0].numpy()) and np.array_equal(dr, tr[0].numpy())
+
+
+def test_pair_tile_enumeration(L):
+    for n in (1, 63, 64, 65, 128, 129, 200, 1000, 4096, 5000):
+        tr, tc = -(-n // 128), -(-n // 64)
+        want = [(i, j) for i in range(tr) for j in range(2 * i, tc)]
+        assert L.pair_tile_count(n) == len(want)
+        step = max(1, len(want) // 500)
+        for t in list(range(0, len(want), step)) + [len(want) - 1]:
+            assert L.pair_tile_decode(n, t) == want[t]
+        # every unordered pair (i <= j) of rows is covered exactly once by the tile list
+        if n <= 200:
+            cover = np.zeros((n, n), dtype=int)
+            for (i, j) in want:
+                r0, r1, c0, c1 = i * 128, min(n, i * 128 + 128), j * 64, min(n, j * 64 + 64)
+                cover[r0:r1, c0:c1] += 1
+                if j // 2 != i:
+                    cover[c0:c1, r0:r1] += 1
+            assert (cover == 1).all()
+    assert L.pair_tile_count(65536) == 262656
+    for world in (1, 2, 3, 4, 8):
+        ranges = [L.pair_tile_range(65536, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == 262656
+        assert all(ranges[k][1] == ranges[k + 1][0] for k in range(world - 1))
+        sizes = [e - b for b, e in ranges]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_helpers_report_errors(L):
+    lib = L.lib()
+    b, e = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.emk_pair_tile_range(100, 3, 2, ctypes.byref(b), ctypes.byref(e)) == -6
+    assert b"rank" in lib.emk_last_error()
+    assert lib.emk_pair_tile_decode(100, 10 ** 9, ctypes.byref(b), ctypes.byref(e)) == -6
+    assert lib.emk_backmap_split_counts(2, (ctypes.c_int64 * 4)()) == -4
+    with pytest.raises(L.EmkError):
+        L.pair_tile_range(100, 5, 2)
+
+
+def test_product_path_refuses_cpu_tensors(L):
+    """No CPU fallback: the public API raises on CPU tensors instead of computing something else."""
+    import encodermap_b200 as em
+    from encodermap_b200.loss_functions import sigmoid_loss
+    from encodermap_b200.misc.distances import pairwise_dist_periodic
+    from encodermap_b200.models.layers import back_map
+
+    with pytest.raises(em.EmkError):
+        sigmoid_loss()(torch.zeros(4, 3), torch.zeros(4, 2))
+    with pytest.raises(em.EmkError):
+        back_map(torch.zeros(2, 5), torch.zeros(2, 4), torch.zeros(2, 3))
+    if not torch.cuda.is_available():
+        with pytest.raises((em.EmkError, RuntimeError, AssertionError)):
+            pairwise_dist_periodic(np.zeros((4, 3), np.float32), 1.0)
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under encodermap_b200/ may import, call or link the oracle."""
+    pat = re.compile(r"^\s*(from\s+\.*oracle|import\s+oracle|from\s+\S*em_oracle|import\s+\S*em_oracle)|em_oracle|oracle/", re.M)
+    for path in (ROOT / "encodermap_b200").rglob("*.py"):
+        assert not pat.search(path.read_text()), f"{path} reaches into oracle/"
+    for path in (ROOT / "encodermap_b200" / "csrc").glob("*"):
+        assert "#include \"../../oracle" not in path.read_text() and "em_oracle" not in path.read_text()

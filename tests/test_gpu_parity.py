@@ -1,0 +1,525 @@
+"""GPU parity tests: the CUDA path (through the reference-shaped Python API -> ctypes/DLPack -> libemk.so)
+against the float64 oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): loss and gradients 1e-5 relative (gradients norm-wise),
+back-mapped coordinates 1e-4 nm, index construction bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import em_oracle as O
+
+pytestmark = pytest.mark.gpu
+pi = math.pi
+DEFAULT_SIG = (4.5, 12, 6, 1, 2, 6)
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-5   # norm-wise
+COORD_ATOL = 1e-4  # nm
+
+
+@pytest.fixture(scope="module")
+def em(cuda_device):
+    import encodermap_b200 as em_
+
+    em_._lib.lib()
+    return em_
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a), dtype=dtype).cuda()
+
+
+def relnorm(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def cost_and_grad(em, high, low, per, sig, **kw):
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    z = cu(low).requires_grad_(True)
+    loss = sigmoid_loss(None, periodicity_overwrite=per, dist_dig_parameters_overwrite=sig, **kw)(cu(high), z)
+    loss.backward()
+    return loss.item(), z.grad.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# sigmoid cost
+# ---------------------------------------------------------------------------------------------------
+CASES = ["periodic_256x51", "nonperiodic_256x51", "cube_256x3", "nb_200x8", "periodic_clustered_300x64",
+         "generic_130x20", "latent3_150x10"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sigmoid_cost_golden(em, golden, name):
+    g = golden["sigmoid_loss"]
+    h, low, per, sig = g[f"{name}_high"], g[f"{name}_low"], float(g[f"{name}_per"]), tuple(g[f"{name}_sig"])
+    loss, grad = cost_and_grad(em, h, low, per, sig)
+    # golden loss: the reference's own function body evaluated in float64 (tools/gen_golden.py)
+    np.testing.assert_allclose(loss, float(g[f"{name}_loss"]), rtol=LOSS_RTOL)
+    _, gref = O.sigmoid_loss_and_grad(h, low, per, sig)
+    assert relnorm(grad, gref.numpy()) < GRAD_RTOL
+    # and we are at least as close to float64 as the reference's own float32 evaluation is
+    ref32_err = abs(float(g[f"{name}_loss_f32"]) - float(g[f"{name}_loss"]))
+    assert abs(loss - float(g[f"{name}_loss"])) <= max(4 * ref32_err, LOSS_RTOL * abs(float(g[f"{name}_loss"])))
+
+
+@pytest.mark.parametrize("n,d,l,per", [(1, 5, 2, 2 * pi), (2, 3, 2, float("inf")), (63, 7, 2, 2 * pi), (64, 32, 2, 2 * pi),
+                                        (65, 33, 1, 1.0), (127, 1, 2, 360.0), (128, 4, 4, float("inf")), (129, 130, 2, 2 * pi),
+                                        (200, 1024, 2, 2 * pi), (513, 96, 8, 2 * pi), (777, 51, 3, float("inf"))])
+def test_sigmoid_cost_ragged_shapes(em, n, d, l, per):
+    rng = np.random.default_rng(n * 1000 + d)
+    scale = per if np.isfinite(per) else 3.0
+    centres = rng.uniform(-0.5, 0.5, size=(4, d)) * scale
+    h = (centres[rng.integers(0, 4, n)] + rng.normal(scale=0.05 * scale / math.sqrt(d), size=(n, d))).astype(np.float32)
+    low = (rng.normal(size=(n, l)) * 2).astype(np.float32)
+    sig = (0.3 * scale, 6, 6, 1, 4, 6) if d < 16 else DEFAULT_SIG
+    loss, grad = cost_and_grad(em, h, low, per, sig)
+    lref, gref = O.sigmoid_loss_and_grad(h, low, per, sig)
+    # float32 resolution of a sigmoid value in [0,1] is 6e-8, which bounds the loss error by ~2.5e-7*sqrt(loss);
+    # it only matters when the loss itself is tiny (a handful of pairs with nearly equal sigmoids)
+    np.testing.assert_allclose(loss, lref.item(), rtol=LOSS_RTOL, atol=2.5e-7 * math.sqrt(lref.item()) + 1e-14)
+    assert np.linalg.norm(grad - gref.numpy()) <= GRAD_RTOL * np.linalg.norm(gref.numpy()) + 2.5e-7 * math.sqrt(lref.item()) + 1e-12
+
+
+def test_sigmoid_cost_reference_test_shapes(em):
+    """reference tests/test_losses.py:195-280 on the GPU path (256x51 -> 256x2, default parameters)."""
+    rng = np.random.default_rng(7)
+    for per, h in ((float("inf"), rng.random((256, 51)).astype("float32") * 100),
+                   (2 * pi, rng.random((256, 51)).astype("float32") * 2 * np.pi - np.pi)):
+        low = rng.random((256, 2)).astype("float32") * 10
+        loss, grad = cost_and_grad(em, h, low, per, DEFAULT_SIG)
+        lref, gref = O.sigmoid_loss_and_grad(h, low, per, DEFAULT_SIG)
+        np.testing.assert_allclose(loss, lref.item(), rtol=LOSS_RTOL)
+        assert relnorm(grad, gref.numpy()) < GRAD_RTOL
+
+
+def test_sigmoid_cost_behavioural_zeros(em):
+    # reference tests/test_losses.py:311-318, 897-904
+    x = np.full((300, 40), 0.3, np.float32)
+    z = np.full((300, 2), 1.7, np.float32)
+    loss, grad = cost_and_grad(em, x, z, 2 * pi, DEFAULT_SIG)
+    assert loss == 0.0 and not grad.any()
+    y = np.random.default_rng(3).random((20, 6)).astype(np.float32)
+    assert cost_and_grad(em, y, y, float("inf"), (1, 1, 1, 1, 1, 1))[0] == 0.0
+    assert cost_and_grad(em, np.zeros((20, 6), np.float32), np.zeros((20, 2), np.float32), float("inf"), (1, 1, 1, 1, 1, 1))[0] == 0.0
+
+
+def test_sigmoid_cost_duplicate_rows_and_nan(em):
+    rng = np.random.default_rng(2)
+    h = rng.uniform(-pi, pi, size=(90, 12)).astype(np.float32)
+    low = rng.normal(size=(90, 2)).astype(np.float32)
+    h[10] = h[3]
+    low[10] = low[3]      # coincident latent points: zero distance, zero gradient contribution, no NaN
+    low[50] = low[20]
+    loss, grad = cost_and_grad(em, h, low, 2 * pi, DEFAULT_SIG)
+    lref, gref = O.sigmoid_loss_and_grad(h, low, 2 * pi, DEFAULT_SIG)
+    assert np.isfinite(grad).all()
+    np.testing.assert_allclose(loss, lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(grad, gref.numpy()) < GRAD_RTOL
+    low[5, 0] = np.nan    # NaN must reach the scalar so that the reference's finite assert can fire
+    loss, _ = cost_and_grad(em, h, low, 2 * pi, DEFAULT_SIG)
+    assert math.isnan(loss)
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    with pytest.raises(FloatingPointError):
+        sigmoid_loss(check_finite=True)(cu(h), cu(low))
+
+
+def test_tile_partition_sums_to_full(em):
+    """The multi-GPU split: partial results over a partition of the tile list add up to the full result."""
+    from encodermap_b200 import _lib, _ops
+
+    rng = np.random.default_rng(9)
+    n, d = 1000, 96
+    h, low = cu(rng.uniform(-pi, pi, size=(n, d))), cu(rng.normal(size=(n, 2)))
+    full_l, full_g = _ops.sigmoid_cost_raw(h, low, 2 * pi, DEFAULT_SIG)
+    for world in (2, 3, 8):
+        tl = torch.zeros(1, dtype=torch.float64, device="cuda")
+        tg = torch.zeros_like(low)
+        covered = 0
+        for r in range(world):
+            b, e = _lib.pair_tile_range(n, r, world)
+            covered += e - b
+            l_, g_ = _ops.sigmoid_cost_raw(h, low, 2 * pi, DEFAULT_SIG, (b, e))
+            tl += l_
+            tg += g_
+        assert covered == _lib.pair_tile_count(n)
+        np.testing.assert_allclose(tl.item(), full_l.item(), rtol=1e-12)
+        assert relnorm(tg.cpu().numpy(), full_g.cpu().numpy()) < 1e-6
+    # oracle restricted to the same tiles would need 128x64 tiles; the full result is checked instead
+    lref, gref = O.sigmoid_loss_and_grad(h.cpu().numpy(), low.cpu().numpy(), 2 * pi, DEFAULT_SIG)
+    np.testing.assert_allclose(full_l.item(), lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(full_g.cpu().numpy(), gref.numpy()) < GRAD_RTOL
+
+
+def test_full_size_properties(em):
+    """Config-2 size (4096 x 1024, periodic): size-independent properties instead of an O(N^2 D) CPU oracle."""
+    from encodermap_b200 import _ops
+
+    n, d = 4096, 1024
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    centres = (torch.rand(16, d, device="cuda", generator=gen) * 2 - 1) * pi
+    idx = torch.randint(0, 16, (n,), device="cuda", generator=gen)
+    h = centres[idx] + 0.05 * torch.randn(n, d, device="cuda", generator=gen)
+    h = torch.remainder(h + pi, 2 * pi) - pi
+    z = 3 * torch.randn(n, 2, device="cuda", generator=gen)
+    l0, g0 = _ops.sigmoid_cost_raw(h, z, 2 * pi, DEFAULT_SIG)
+    # (1) invariance under a simultaneous row permutation
+    perm = torch.randperm(n, device="cuda", generator=gen)
+    l1, g1 = _ops.sigmoid_cost_raw(h[perm].contiguous(), z[perm].contiguous(), 2 * pi, DEFAULT_SIG)
+    np.testing.assert_allclose(l1.item(), l0.item(), rtol=1e-6)
+    assert relnorm(g1.cpu().numpy(), g0[perm].cpu().numpy()) < 1e-5
+    # (2) invariance under shifting every angle by a constant (min-image wrap) and rotating/translating the latent
+    l2, g2 = _ops.sigmoid_cost_raw(torch.remainder(h + 1.0 + pi, 2 * pi) - pi, z + 5.0, 2 * pi, DEFAULT_SIG)
+    np.testing.assert_allclose(l2.item(), l0.item(), rtol=2e-5)
+    # (3) translation invariance of the latent => gradient rows sum to zero
+    assert abs(g0.sum(0)).max().item() < 1e-6 * abs(g0).sum().item()
+    # (4) a 256-row subset agrees with the float64 oracle
+    sub = torch.arange(0, n, 16, device="cuda")
+    ls, gs = _ops.sigmoid_cost_raw(h[sub].contiguous(), z[sub].contiguous(), 2 * pi, DEFAULT_SIG)
+    lref, gref = O.sigmoid_loss_and_grad(h[sub].cpu().numpy(), z[sub].cpu().numpy(), 2 * pi, DEFAULT_SIG)
+    np.testing.assert_allclose(ls.item(), lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(gs.cpu().numpy(), gref.numpy()) < GRAD_RTOL
+
+
+def test_distance_and_cartesian_distance_loss(em):
+    from encodermap_b200 import ADCParameters, Parameters
+    from encodermap_b200.loss_functions import cartesian_distance_loss, distance_loss
+
+    rng = np.random.default_rng(4)
+
+    class Model:
+        def __init__(self, w):
+            self.w = w
+
+        def encoder(self, x, training=False):
+            if isinstance(x, tuple):
+                x = torch.cat(x[:3], dim=1)
+            return torch.tanh(x @ self.w)
+
+    # tuple input (angles, dihedrals) is concatenated (loss_functions.py:279-280); scale 500 default
+    ang, dih = rng.uniform(1.9, 2.2, (180, 28)).astype(np.float32), rng.uniform(-pi, pi, (180, 27)).astype(np.float32)
+    w = cu(rng.normal(size=(55, 2)) * 0.3).requires_grad_(True)
+    f = distance_loss(Model(w), Parameters())
+    assert f.__name__ == "distance_loss_func"
+    loss = f((cu(ang), cu(dih)))
+    loss.backward()
+    wd = w.detach().cpu().double().requires_grad_(True)
+    zt = torch.tanh(torch.from_numpy(np.concatenate([ang, dih], 1)).double() @ wd)
+    lref = O.sigmoid_loss(2 * pi, DEFAULT_SIG)(np.concatenate([ang, dih], 1).astype(np.float64), zt) * 500
+    lref.backward()
+    np.testing.assert_allclose(loss.item(), lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(w.grad.cpu().numpy(), wd.grad.numpy()) < 2e-5
+    # scale None => 0 (ADC default, loss_functions.py:281-286)
+    assert distance_loss(Model(w), ADCParameters())((cu(ang), cu(dih))).item() == 0.0
+    # cartesian distance loss: non-periodic over pairwise distances of C-alpha atoms
+    p = ADCParameters(cartesian_dist_sig_parameters=(0.5, 6, 6, 1, 2, 6))
+    pair = np.abs(rng.normal(size=(150, 45))).astype(np.float32)
+    lat = rng.normal(size=(150, 2)).astype(np.float32)
+    fc = cartesian_distance_loss(Model(w), p)
+    assert fc.__name__ == "cartesian_distance_loss_func"
+    np.testing.assert_allclose(fc(cu(pair), cu(lat)).item(),
+                               O.cartesian_distance_loss_value(pair.astype(np.float64), lat.astype(np.float64), p.cartesian_dist_sig_parameters).item(),
+                               rtol=LOSS_RTOL)
+
+
+def test_raw_pointer_and_host_entry_points(em):
+    """The C ABI proper: raw device pointers, and host buffers with the copies inside the call."""
+    import ctypes
+
+    from encodermap_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(12)
+    n, d = 333, 50
+    h = rng.uniform(-pi, pi, (n, d)).astype(np.float32)
+    z = rng.normal(size=(n, 2)).astype(np.float32)
+    lref, gref = O.sigmoid_loss_and_grad(h, z, 2 * pi, DEFAULT_SIG)
+    loss = ctypes.c_double()
+    grad = np.empty_like(z)
+    _lib.check(L.emk_sigmoid_cost_host(h.ctypes.data, n, d, z.ctypes.data, 2, 2 * pi, _lib.sig_array(DEFAULT_SIG), ctypes.byref(loss), grad.ctypes.data))
+    np.testing.assert_allclose(loss.value, lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(grad, gref.numpy()) < GRAD_RTOL
+    hd, zd = cu(h), cu(z)
+    ld = torch.zeros(1, dtype=torch.float64, device="cuda")
+    gd = torch.zeros_like(zd)
+    _lib.check(L.emk_sigmoid_cost(hd.data_ptr(), n, d, zd.data_ptr(), 2, 2 * pi, _lib.sig_array(DEFAULT_SIG), 0, _lib.pair_tile_count(n),
+                                  ld.data_ptr(), gd.data_ptr(), 0, None))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ld.item(), lref.item(), rtol=LOSS_RTOL)
+    # argument errors come back as codes + message, never as a crash
+    assert L.emk_sigmoid_cost(hd.data_ptr(), n, d, zd.data_ptr(), 9, 2 * pi, _lib.sig_array(DEFAULT_SIG), 0, 1, ld.data_ptr(), gd.data_ptr(), 0, None) == -7
+    assert b"latent width" in L.emk_last_error()
+    assert L.emk_sigmoid_cost(None, n, d, zd.data_ptr(), 2, 2 * pi, _lib.sig_array(DEFAULT_SIG), 0, 1, ld.data_ptr(), gd.data_ptr(), 0, None) == -1
+    # DLPack validation: non-contiguous and wrong-dtype tensors are refused with a code, not copied silently
+    args = (2 * pi, _lib.sig_array(DEFAULT_SIG), 0, 1, _lib.DL(ld), _lib.DL(gd), 0, None)
+    assert L.emk_dl_sigmoid_cost(_lib.DL(hd[:, ::2]), _lib.DL(zd), *args) == -5
+    assert L.emk_dl_sigmoid_cost(_lib.DL(hd.double()), _lib.DL(zd), *args) == -2
+    assert L.emk_dl_sigmoid_cost(_lib.DL(hd.cpu()), _lib.DL(zd), *args) == -3
+    assert L.emk_dl_sigmoid_cost(_lib.DL(hd[:10]), _lib.DL(zd), *args) == -4
+
+
+# ---------------------------------------------------------------------------------------------------
+# distances, elementwise
+# ---------------------------------------------------------------------------------------------------
+def test_distances_golden(em, golden):
+    from encodermap_b200.misc import distances as D
+
+    g = golden["distances"]
+    r = g["sigmoid_r"]
+    for name in ("h_default", "l_default", "cube_h", "nb_h", "nb_l", "odd"):
+        got = D.sigmoid(*g[f"sigmoid_{name}_params"])(cu(r)).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"sigmoid_{name}_out"], rtol=2e-5, atol=2e-7)
+    assert D.sigmoid(5, 12, 2)(1.5) == O.sigmoid(5, 12, 2)(1.5)  # python-number path, reference KAT
+    a, b = g["perdist_a"], g["perdist_b"]
+    for P, key, s in ((2 * pi, "perdist_2pi", 1), (360.0, "perdist_360", 50), (float("inf"), "perdist_inf", 1)):
+        got = D.periodic_distance(cu(a * s), cu(b * s), P).cpu().numpy()
+        want = O.periodic_distance((a * s).astype(np.float32), (b * s).astype(np.float32), P).numpy()
+        assert np.array_equal(got, want)          # same float32 arithmetic: bit-exact
+        np.testing.assert_allclose(got, g[key], rtol=1e-6, atol=2e-5 * s)
+    np.testing.assert_allclose(D.pairwise_dist_periodic(cu(g["pwp_x"]), 2 * pi).cpu().numpy(), g["pwp_2pi"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(D.pairwise_dist_periodic(cu(g["pwp_x"]), 1.0).cpu().numpy(), g["pwp_1"], rtol=1e-5, atol=1e-6)
+    for key, kw, x in (("pw_2d", {}, "pw_x2"), ("pw_2d_sq", {"squared": True}, "pw_x2"), ("pw_2d_flat", {"flat": True}, "pw_x2"),
+                       ("pw_3d", {}, "pw_x3"), ("pw_3d_flat", {"flat": True}, "pw_x3"), ("pw_3d_flat_sq", {"flat": True, "squared": True}, "pw_x3")):
+        got = D.pairwise_dist(cu(g[x]), **kw).cpu().numpy()
+        assert got.shape == g[key].shape
+        np.testing.assert_allclose(got, g[key], rtol=1e-5, atol=1e-6)
+
+
+def test_reference_distance_kats(em):
+    from encodermap_b200.misc import distances as D
+
+    # reference tests/test_pairwise_distances.py:98-108, 140-168
+    d = D.periodic_distance(np.array([0.0, 0.0, 0.0]), np.array([pi / 2, pi, 3 / 2 * pi]), 2 * pi).cpu().numpy()
+    np.testing.assert_allclose(d, [pi / 2, pi, pi / 2], rtol=1e-6)
+    pts = np.array([[1 / 8, 1 / 2], [7 / 8, 1 / 2]], dtype=np.float32)
+    np.testing.assert_allclose(D.pairwise_dist_periodic(pts, 1).cpu().numpy(), [[0, 1 / 4], [1 / 4, 0]], atol=1e-6)
+    np.testing.assert_allclose(D.pairwise_dist_periodic(pts, float("inf")).cpu().numpy(), [[0, 6 / 8], [6 / 8, 0]], atol=1e-6)
+    np.testing.assert_allclose(D.pairwise_dist([[1 / 8, 1 / 2], [7 / 8, 1 / 2]]).cpu().numpy(), [[[0, 6 / 8], [6 / 8, 0]]], atol=1e-6)
+    flat = D.pairwise_dist(np.array([[0, 0], [1, 0], [0, 1]], dtype=np.float32), flat=True).cpu().numpy()
+    np.testing.assert_allclose(flat, [[1, 1, 2 ** 0.5]], atol=1e-6)
+    pts = np.random.default_rng(0).normal(size=(10, 3)).astype(np.float32)
+    np.testing.assert_allclose(D.pairwise_dist_periodic(pts, 10000).cpu().numpy().reshape(-1), D.pairwise_dist(pts).cpu().numpy().reshape(-1), atol=1e-5)
+
+
+def test_big_distance_matrix_tma_path(em):
+    from encodermap_b200.misc import distances as D
+
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-pi, pi, size=(700, 130)).astype(np.float32)
+    np.testing.assert_allclose(D.pairwise_dist_periodic(cu(x), 2 * pi).cpu().numpy(), O.pairwise_dist_periodic(x.astype(np.float64), 2 * pi).numpy(), rtol=1e-5, atol=1e-5)
+    got = D.pairwise_dist(cu(x)).cpu().numpy()
+    want = O.pairwise_dist(x.astype(np.float64)).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(D.pairwise_dist(cu(x), squared=True).cpu().numpy(), want ** 2, rtol=1e-5, atol=1e-4)
+
+
+def test_pairwise_dist_backward(em):
+    from encodermap_b200.misc import distances as D
+
+    rng = np.random.default_rng(6)
+    for shape, kw in (((6, 25, 3), {"flat": True}), ((3, 12, 3), {}), ((40, 5), {"flat": True}), ((2, 9, 3), {"flat": True, "squared": True}), ((30, 11), {})):
+        x = rng.normal(size=shape).astype(np.float32)
+        w = rng.normal(size=O.pairwise_dist(x, **kw).shape)
+        xg = cu(x).requires_grad_(True)
+        (D.pairwise_dist(xg, **kw) * cu(w)).sum().backward()
+        xo = torch.from_numpy(x).double().requires_grad_(True)
+        (O.pairwise_dist(xo, **kw) * torch.from_numpy(w)).sum().backward()
+        assert relnorm(xg.grad.cpu().numpy(), xo.grad.numpy()) < 2e-5
+
+
+def test_elementwise_backward(em):
+    from encodermap_b200.misc import distances as D
+
+    rng = np.random.default_rng(8)
+    a, b = rng.uniform(-pi, pi, (50, 7)).astype(np.float32), rng.uniform(-pi, pi, (50, 7)).astype(np.float32)
+    w = rng.normal(size=(50, 7))
+    ag, bg = cu(a).requires_grad_(True), cu(b).requires_grad_(True)
+    (D.periodic_distance(ag, bg) * cu(w)).sum().backward()
+    ao, bo = torch.from_numpy(a).double().requires_grad_(True), torch.from_numpy(b).double().requires_grad_(True)
+    (O.periodic_distance(ao, bo) * torch.from_numpy(w)).sum().backward()
+    np.testing.assert_allclose(ag.grad.cpu().numpy(), ao.grad.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(bg.grad.cpu().numpy(), bo.grad.numpy(), rtol=1e-6)
+    # broadcasting form used by the reference: (n,1,d) against (1,n,d)
+    x = cu(a)
+    got = D.periodic_distance(x[:, None, :], x[None, :, :], 2 * pi).cpu().numpy()
+    assert np.array_equal(got, O.periodic_distance(torch.from_numpy(a)[:, None], torch.from_numpy(a)[None], 2 * pi).numpy())
+    for params in ((4.5, 12, 6), (1, 2, 6), (0.2, 3, 6), (1.3, 2.5, 3.7), (1.0, 1, 1)):
+        r = (np.abs(rng.normal(size=64)) * 3 + 0.01).astype(np.float32)
+        rg = cu(r).requires_grad_(True)
+        D.sigmoid(*params)(rg).sum().backward()
+        ro = torch.from_numpy(r).double().requires_grad_(True)
+        O.sigmoid(*params)(ro).sum().backward()
+        np.testing.assert_allclose(rg.grad.cpu().numpy(), ro.grad.numpy(), rtol=5e-5, atol=1e-7)
+
+
+def test_layers(em, golden):
+    from encodermap_b200 import ADCParameters, Parameters
+    from encodermap_b200.misc.backmapping import rotation_matrix
+    from encodermap_b200.models.layers import PairwiseDistances, PeriodicInput
+
+    g = golden["layers"]
+    np.testing.assert_allclose(PeriodicInput(Parameters(), "x")(cu(g["pi_x"])).cpu().numpy(), g["pi_2pi"], atol=1e-6)
+    np.testing.assert_allclose(PeriodicInput(Parameters(periodicity=360.0), "x")(cu(g["pi_x"] * 50)).cpu().numpy(), g["pi_360"], atol=2e-5)
+    x = cu(g["pi_x"]).requires_grad_(True)
+    w = np.random.default_rng(1).normal(size=g["pi_2pi"].shape)
+    (PeriodicInput(Parameters(periodicity=360.0), "x")(x * 50) * cu(w)).sum().backward()
+    xo = torch.from_numpy(g["pi_x"]).requires_grad_(True)
+    (O.periodic_input(xo * 50, 360.0) * torch.from_numpy(w)).sum().backward()
+    assert relnorm(x.grad.cpu().numpy(), xo.grad.numpy()) < 2e-5
+    for tag, sl in {"ca": (1, None, 3), "all": (None, None, None), "odd": (2, 25, 4)}.items():
+        p = ADCParameters(cartesian_pwd_start=sl[0], cartesian_pwd_stop=sl[1], cartesian_pwd_step=sl[2])
+        xyz = cu(g["pd_xyz"]).requires_grad_(True)
+        out = PairwiseDistances(p, "pd")(xyz)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), g[f"pd_{tag}"], rtol=1e-5, atol=1e-6)
+        w = np.random.default_rng(2).normal(size=g[f"pd_{tag}"].shape)
+        (out * cu(w)).sum().backward()
+        xo = torch.from_numpy(g["pd_xyz"]).requires_grad_(True)
+        (O.pairwise_distances_layer(xo, *sl) * torch.from_numpy(w)).sum().backward()
+        assert relnorm(xyz.grad.cpu().numpy(), xo.grad.numpy()) < 2e-5
+    gb = golden["backmapping"]
+    np.testing.assert_allclose(rotation_matrix(cu(gb["rot_axis"]), cu(gb["rot_angle"])).cpu().numpy(), gb["rot_out"], atol=1e-6)
+    d = np.random.default_rng(3).uniform(0.1, 0.2, (1000, 37)).astype(np.float32)
+    from encodermap_b200.models.layers import mean_lengths
+
+    np.testing.assert_allclose(mean_lengths(cu(d)).cpu().numpy(), d.astype(np.float64).mean(0)[None], rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# back-mapping
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [9, 12, 30, 31, 300])
+def test_backmap_golden(em, golden, n):
+    from encodermap_b200.encodermap_tf1 import chain_in_plane, dihedrals_to_cartesian_tf
+    from encodermap_b200.misc.backmapping import dihedrals_to_cartesian_tf_layers
+    from encodermap_b200.models.layers import BackMapLayer
+
+    g = golden["backmapping"]
+    k = f"n{n}"
+    dist, ang, dih = cu(g[f"{k}_dist"]), cu(g[f"{k}_ang"]), cu(g[f"{k}_dih"])
+    left, right = O.split_counts(n)
+    out = BackMapLayer(left, right)((dist, ang, dih)).cpu().numpy()
+    assert np.abs(out - g[f"{k}_backmaplayer"]).max() < COORD_ATOL
+    # much closer to the float64 truth than the reference's own float32 evaluation
+    ref32 = np.abs(g[f"{k}_backmaplayer_f32"].astype(np.float64) - g[f"{k}_backmaplayer"]).max()
+    assert np.abs(out - g[f"{k}_backmaplayer"]).max() <= max(ref32, 2e-6)
+    lengths = cu(g[f"{k}_dist"].mean(0)[None])
+    chain = chain_in_plane(lengths, ang)
+    assert np.abs(chain.cpu().numpy() - g[f"{k}_chain"]).max() < COORD_ATOL
+    assert np.abs(chain_in_plane(dist, ang).cpu().numpy() - g[f"{k}_chain_perframe_lengths"]).max() < COORD_ATOL
+    # standalone ops: the start chain is an INPUT here, so the expectation is the float64 evaluation of the
+    # reference algorithm on the same float32-rounded chain and dihedrals the kernel receives
+    start32 = g[f"{k}_chain"].astype(np.float32)
+    dpi32 = (g[f"{k}_dih"] + pi).astype(np.float32)
+    want = O.dihedrals_to_cartesian_layers(torch.from_numpy(dpi32).double(), torch.from_numpy(start32).double(), left, right).numpy()
+    assert np.abs(dihedrals_to_cartesian_tf_layers(cu(dpi32), cu(start32), left, right).cpu().numpy() - want).max() < COORD_ATOL
+    assert np.abs(dihedrals_to_cartesian_tf(cu(dpi32), cu(start32)).cpu().numpy() - want).max() < COORD_ATOL
+    assert np.abs(want - g[f"{k}_d2c_layers"]).max() < 1e-3   # and that is the reference's result up to input rounding
+
+
+def test_helix_kat(em, golden):
+    # reference tests/test_dihedral_to_cartesian.py:98-153 (33x3 table, atol 1e-4): one-way algorithm
+    from encodermap_b200.encodermap_tf1 import dihedral_to_cartesian_tf_one_way, dihedrals_to_cartesian_tf
+    from encodermap_b200.misc.backmapping import dihedral_to_cartesian_tf_one_way_layers
+
+    g = golden["backmapping"]
+    start = cu(O.straight_tetrahedral_chain(33))
+    dih = cu(g["helix_dih"])
+    out = dihedral_to_cartesian_tf_one_way(dih, start).cpu().numpy()
+    np.testing.assert_allclose(out[0], g["helix_kat"], atol=1e-4)
+    np.testing.assert_allclose(out, g["helix_oneway"], atol=2e-5)
+    out2 = dihedral_to_cartesian_tf_one_way_layers(dih, start[None].expand(2, -1, -1).contiguous(), 30).cpu().numpy()
+    np.testing.assert_allclose(out2, g["helix_oneway"], atol=2e-5)
+    np.testing.assert_allclose(dihedrals_to_cartesian_tf(dih, start).cpu().numpy(), g["helix_twosided"], atol=2e-5)
+
+
+@pytest.mark.parametrize("n,b", [(4, 3), (5, 3), (6, 2), (7, 2), (8, 5), (33, 4), (64, 3), (100, 130), (301, 2), (1500, 2)])
+def test_backmap_vs_oracle(em, n, b):
+    from encodermap_b200.models.layers import back_map
+
+    rng = np.random.default_rng(n)
+    dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+    want = O.back_map_layer(dist.astype(np.float64), ang.astype(np.float64), dih.astype(np.float64)).numpy()
+    got = back_map(cu(dist), cu(ang), cu(dih)).cpu().numpy()
+    assert np.abs(got - want).max() < COORD_ATOL
+    # invariants behind reference tests/test_losses.py:663-703: requested internal coordinates are realised
+    xyz = torch.from_numpy(got).double()
+    got_dih = O.dihedral_of(xyz[:, :-3], xyz[:, 1:-2], xyz[:, 2:-1], xyz[:, 3:]).numpy()
+    diff = (got_dih - dih + pi) % (2 * pi) - pi
+    assert np.abs(diff).max() < 2e-3
+
+
+@pytest.mark.parametrize("n,b", [(4, 2), (5, 2), (9, 3), (10, 3), (30, 4), (31, 4), (300, 3)])
+def test_backmap_backward(em, n, b):
+    from encodermap_b200.models.layers import back_map
+
+    rng = np.random.default_rng(100 + n)
+    dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+    w = rng.normal(size=(b, n, 3))
+    dg, ag, hg = (cu(v).requires_grad_(True) for v in (dist, ang, dih))
+    (back_map(dg, ag, hg) * cu(w)).sum().backward()
+    do, ao, ho = (torch.from_numpy(v).double().requires_grad_(True) for v in (dist, ang, dih))
+    (O.back_map_layer(do, ao, ho) * torch.from_numpy(w)).sum().backward()
+    assert relnorm(hg.grad.cpu().numpy(), ho.grad.numpy()) < GRAD_RTOL
+    assert relnorm(ag.grad.cpu().numpy(), ao.grad.numpy()) < GRAD_RTOL
+    assert relnorm(dg.grad.cpu().numpy(), do.grad.numpy()) < 5e-5   # batch-mean path: one float32 division more
+
+
+def test_chain_and_d2c_backward(em):
+    from encodermap_b200.encodermap_tf1 import chain_in_plane, dihedral_to_cartesian_tf_one_way, dihedrals_to_cartesian_tf
+
+    rng = np.random.default_rng(77)
+    for n, b, per_frame in ((3, 2, False), (12, 3, False), (13, 3, True), (64, 2, True)):
+        L = rng.uniform(0.13, 0.15, size=(b if per_frame else 1, n - 1)).astype(np.float32)
+        ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+        w = rng.normal(size=(b, n, 3))
+        Lg, ag = cu(L).requires_grad_(True), cu(ang).requires_grad_(True)
+        (chain_in_plane(Lg, ag) * cu(w)).sum().backward()
+        Lo, ao = torch.from_numpy(L).double().requires_grad_(True), torch.from_numpy(ang).double().requires_grad_(True)
+        (O.chain_in_plane(Lo, ao) * torch.from_numpy(w)).sum().backward()
+        assert relnorm(ag.grad.cpu().numpy(), ao.grad.numpy()) < GRAD_RTOL
+        assert relnorm(Lg.grad.cpu().numpy(), Lo.grad.numpy()) < GRAD_RTOL
+    for n, b in ((10, 2), (33, 3)):
+        start = O.straight_tetrahedral_chain(n) + rng.normal(scale=0.05, size=(n, 3)).astype(np.float32)
+        dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+        w = rng.normal(size=(b, n, 3))
+        for fn, ofn in ((dihedrals_to_cartesian_tf, O.dihedrals_to_cartesian_tf1),
+                        (dihedral_to_cartesian_tf_one_way, lambda d, c: O.dihedral_to_cartesian_one_way(d, c[None].expand(b, -1, -1)))):
+            hg = cu(dih).requires_grad_(True)
+            out = fn(hg, cu(start))
+            (out * cu(w)).sum().backward()
+            ho = torch.from_numpy(dih).double().requires_grad_(True)
+            oo = ofn(ho, torch.from_numpy(start).double())
+            (oo * torch.from_numpy(w)).sum().backward()
+            assert np.abs(out.detach().cpu().numpy() - oo.detach().numpy()).max() < COORD_ATOL
+            assert relnorm(hg.grad.cpu().numpy(), ho.grad.numpy()) < GRAD_RTOL
+
+
+def test_index_construction_bit_exact(em, golden):
+    from encodermap_b200.misc.backmapping import split_and_reverse_cartesians, split_and_reverse_dihedrals
+
+    g = golden["backmapping"]
+    for n in (9, 12, 30, 31, 300):
+        cl, cr = split_and_reverse_cartesians(torch.arange(n, device="cuda")[None])
+        dl, dr = split_and_reverse_dihedrals(torch.arange(n - 3, device="cuda")[None])
+        assert np.array_equal(cl[0].cpu().numpy(), g[f"n{n}_split_atoms_left"]) and np.array_equal(cr[0].cpu().numpy(), g[f"n{n}_split_atoms_right"])
+        assert np.array_equal(dl[0].cpu().numpy(), g[f"n{n}_split_dih_left"]) and np.array_equal(dr[0].cpu().numpy(), g[f"n{n}_split_dih_right"])
+
+
+def test_no_cpu_fallback(em):
+    from encodermap_b200.loss_functions import sigmoid_loss
+    from encodermap_b200.models.layers import back_map
+
+    with pytest.raises(em.EmkError):
+        sigmoid_loss()(torch.zeros(4, 3), torch.zeros(4, 2))
+    with pytest.raises(em.EmkError):
+        back_map(torch.zeros(2, 5), torch.zeros(2, 4), torch.zeros(2, 3))

@@ -1,0 +1,86 @@
+"""world_size-2 gloo test of the multi-GPU host logic (tile-range partition + all-reduce + frame
+sharding).  The per-rank evaluator is the oracle restricted to the rank's tiles -- the CUDA kernel
+cannot run here -- so what is tested is the plumbing in encodermap_b200/parallel.py."""
+import math
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import em_oracle as O
+
+SIG = (4.5, 12, 6, 1, 2, 6)
+
+
+def _oracle_partial(high, low, periodicity, sig, tile_range):
+    """Oracle evaluation of libemk's 128x64 tile list slice [begin, end)."""
+    from encodermap_b200 import _lib
+
+    h, z = high.double(), low.double()
+    n = h.shape[0]
+    sig_h, sig_l = O.sigmoid(*sig[:3]), O.sigmoid(*sig[3:])
+    loss = torch.zeros(1, dtype=torch.float64)
+    grad = torch.zeros_like(z)
+    for t in range(*tile_range):
+        i, j = _lib.pair_tile_decode(n, t)
+        ri, rj = slice(i * 128, min(n, i * 128 + 128)), slice(j * 64, min(n, j * 64 + 64))
+        zi, zj = z[ri].clone().requires_grad_(True), z[rj].clone().requires_grad_(True)
+        dh = torch.sqrt(torch.sum(O.periodic_distance(h[ri][:, None], h[rj][None], periodicity) ** 2, dim=2))
+        d2 = torch.sum((zi[:, None] - zj[None]) ** 2, dim=2)
+        m = (d2 == 0).double()
+        dl = torch.sqrt(d2 + m) * (1 - m)
+        w = 1.0 if j // 2 == i else 2.0
+        part = w * torch.sum((sig_h(dh) - sig_l(dl)) ** 2) / (n * n)
+        gi, gj = torch.autograd.grad(part, (zi, zj))
+        loss += part.detach()
+        grad[ri] += gi
+        grad[rj] += gj
+    return loss, grad
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from encodermap_b200 import parallel
+
+        rng = np.random.default_rng(5)  # same data on every rank (inputs are replicated)
+        n, d = 300, 12
+        high = torch.from_numpy(rng.uniform(-math.pi, math.pi, size=(n, d)))
+        low = torch.from_numpy(rng.normal(size=(n, 2)))
+        loss, grad = parallel.sharded_sigmoid_cost(high, low, 2 * math.pi, SIG, partial_fn=_oracle_partial)
+        fr = parallel.frame_range(1001, rank, world)
+        q.put((rank, loss.item(), grad.numpy(), parallel.tile_range(n, rank, world), fr))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cost_world2_gloo():
+    from encodermap_b200 import _build
+
+    _build.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    high = rng.uniform(-math.pi, math.pi, size=(300, 12))
+    low = rng.normal(size=(300, 2))
+    lref, gref = O.sigmoid_loss_and_grad(high, low, 2 * math.pi, SIG)
+    for rank, loss, grad, tr, fr in results:
+        np.testing.assert_allclose(loss, lref.item(), rtol=1e-9)          # every rank holds the reduced result
+        assert np.linalg.norm(grad - gref.numpy()) <= 1e-8 * np.linalg.norm(gref.numpy())
+    (b0, e0), (b1, e1) = results[0][3], results[1][3]
+    assert b0 == 0 and e0 == b1 and abs((e0 - b0) - (e1 - b1)) <= 1
+    assert results[0][4] == (0, 501) and results[1][4] == (501, 1001)
