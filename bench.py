@@ -255,10 +255,10 @@ def run_ours(args):
     e2e_value = pairs / (e2e_ms * 1e-3)
 
     extra = {}
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         extra.update(secondary_metrics(dev, peaks))
     barrier()
-    if world > 1:
+    if world > 1 and not args.no_extra:
         # frame-sharded back-mapping (configs[4]): no communication, every rank does its slice of 1M frames
         fps = backmap_frames_per_s(dev, BACKMAP_FRAMES // world)
         t = torch.tensor([fps[1]], dtype=torch.float64, device=dev)
@@ -387,6 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary metrics (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
