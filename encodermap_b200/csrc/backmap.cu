@@ -18,6 +18,8 @@
 // Backward: for every internal coordinate the downstream body moves rigidly (twist about a bond, hinge
 // about the normal of a bond angle, slide along a bond; left of the anchor the whole molecule also
 // follows the planar chain), so each gradient is <axis, torque> or <direction, force> of a prefix sum.
+#include <algorithm>
+
 #include "emk_common.cuh"
 
 namespace emk {
@@ -132,6 +134,14 @@ __device__ __forceinline__ Se2 se2_shfl_up(const Se2& a, int d) {
   o.y = __shfl_up_sync(0xffffffffu, a.y, d);
   return o;
 }
+__device__ __forceinline__ Se2 se2_shfl_down(const Se2& a, int d) {
+  Se2 o;
+  o.c = __shfl_down_sync(0xffffffffu, a.c, d);
+  o.s = __shfl_down_sync(0xffffffffu, a.s, d);
+  o.x = __shfl_down_sync(0xffffffffu, a.x, d);
+  o.y = __shfl_down_sync(0xffffffffu, a.y, d);
+  return o;
+}
 __device__ __forceinline__ Se2 se2_shfl(const Se2& a, int src) {
   Se2 o;
   o.c = __shfl_sync(0xffffffffu, a.c, src);
@@ -166,6 +176,39 @@ __device__ __forceinline__ void planar_step(Se2& t, double L, bool has_turn, flo
     t.c = c2;
     t.s = s2;
   }
+}
+
+// ---- asynchronous, vectorised staging of one contiguous row into shared memory -------------------------
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// `region` is 16-byte aligned with 4 floats of slack.  The copy starts at the 16-byte boundary at or below
+// `src` (those <= 3 leading floats belong to the previous row of the same tensor), so that the body moves
+// 16 bytes per request with every request in flight at once; returns the address of element 0.
+__device__ __forceinline__ float* stage_row_async(float* region, const float* __restrict__ src, int len, int t, int nthreads) {
+  const int sh = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
+  const float* asrc = src - sh;
+  const int total = sh + len;
+  const int nvec = total >> 2;
+  for (int v = t; v < nvec; v += nthreads) cp_async16(region + 4 * v, asrc + 4 * v);
+  for (int e = (nvec << 2) + t; e < total; e += nthreads) cp_async4(region + e, asrc + e);
+  return region + sh;
+}
+// coalesced copy of `len` floats from shared to global; sm and dst are congruent modulo 16 bytes
+__device__ __forceinline__ void store_row(float* __restrict__ dst, const float* sm, int len, int t, int nthreads) {
+  const int head = min(len, (int)(((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2));
+  for (int e = t; e < head; e += nthreads) dst[e] = sm[e];
+  const int nvec = (len - head) >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(sm + head);
+  float4* d4 = reinterpret_cast<float4*>(dst + head);
+  for (int v = t; v < nvec; v += nthreads) d4[v] = s4[v];
+  for (int e = head + (nvec << 2) + t; e < len; e += nthreads) dst[e] = sm[e];
 }
 
 __device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int count, int lane) {
@@ -215,97 +258,195 @@ __global__ void chain_in_plane_kernel(const float* __restrict__ lengths, int64_t
 }
 
 // ====================================================================================================
-// BackMapLayer forward (NeRF from the planar anchor)
+// BackMapLayer forward (NeRF from the planar anchor).
+//   * 64 threads per frame: one warp builds the left half outward from the middle, one the right half;
+//     two frames per 128-thread CTA.  Inputs and outputs are staged through shared memory so that every
+//     global access is coalesced.
+//   * pass 1: each lane multiplies the local transforms of its contiguous chunk in float64 and leaves
+//     chunk-local positions (float32, |x| < 4 nm) in the output buffer; the left warp builds the planar
+//     SE(2) product of the same bonds on the side, re-using the sin/cos of the bond angles.
+//   * warp scan of the chunk aggregates (5 shuffle steps), anchor frame from the planar product.
+//   * pass 2: out = prefix(local) -- rotation in float32 (local coordinates are small), translation as a
+//     float32 hi/lo pair, so this pass needs no FP64 and no conversions.
+//   * sin/cos: float32 Cody-Waite reduction to |r| <= pi/1024, float32 2-term corrections, float64 table +
+//     4 DFMA: 2.3e-10 absolute error (tools/gen_golden.py-independent check in tests), 4 FP64 ops instead of 30.
 // ====================================================================================================
-__global__ void backmap_fwd_kernel(const float* __restrict__ lengths, int64_t lstride, const float* __restrict__ angles,
-                                   const float* __restrict__ dihedrals, int64_t b, int n, float* __restrict__ xyz) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
-  if (frame >= b) return;
-  const int per_warp = (n - 1) + (n - 2) + (n - 3) + 3 * n;
-  float* sL = smem + (size_t)warp * per_warp;
-  float* sA = sL + (n - 1);
-  float* sD = sA + (n - 2);
-  float* sO = sD + (n - 3);
-  stage_in(sL, lengths + frame * lstride, n - 1, lane);
-  stage_in(sA, angles + frame * (int64_t)(n - 2), n - 2, lane);
-  stage_in(sD, dihedrals + frame * (int64_t)(n - 3), n - 3, lane);
-  __syncwarp();
+constexpr int SC_TABLE = 1024;               // table step 2 pi / 1024
+__global__ void sincos_table_kernel(double2* tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < SC_TABLE) {
+    double s, c;
+    sincospi(2.0 * (double)i / (double)SC_TABLE, &s, &c);
+    tab[i] = make_double2(s, c);
+  }
+}
+
+__device__ __forceinline__ void sincos_tab(float x, const double2* __restrict__ tab, double* s, double* c) {
+  if (fabsf(x) < 48.f) {
+    // k = rint(x * 1024 / 2pi) by the magic-number trick; the low mantissa bits of (x*A + M) are k mod 2^22
+    const float km = fmaf(x, 162.9746551513672f, 12582912.f);
+    const float kf = km - 12582912.f;
+    // 2pi/1024 = C1 + C2 + C3 with 11-bit C1, C2: the first two reductions are exact in float32
+    float r = fmaf(-kf, 0.006134033203125f, x);
+    r = fmaf(-kf, 1.889653503894806e-06f, r);
+    r = fmaf(-kf, 2.949136768126692e-10f, r);
+    const float r2 = r * r;
+    const float sr = fmaf(r * r2, -0.16666667f, r);                  // sin r
+    const float cm = r2 * fmaf(r2, 0.041666668f, -0.5f);             // cos r - 1
+    const double2 t = __ldg(tab + (__float_as_int(km) & (SC_TABLE - 1)));
+    *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
+    *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
+  } else {
+    sincos_d((double)x, s, c);
+  }
+}
+
+constexpr int FWD_THREADS = 128;
+
+__global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const float* __restrict__ lengths, int64_t lstride,
+                                                                      const float* __restrict__ angles,
+                                                                      const float* __restrict__ dihedrals, int64_t b, int n,
+                                                                      float* __restrict__ xyz, const double2* __restrict__ tab) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double anchor[FWD_THREADS / 64][2][12];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid >> 6, t = tid & 63, side = (tid >> 5) & 1;
+  const int64_t frame = (int64_t)blockIdx.x * (FWD_THREADS / 64) + g;
+  const bool active = frame < b;
+  // per-frame shared-memory regions (each 16-byte aligned, 4 floats of slack): lengths, angles, dihedrals, xyz
+  const int out_floats = 3 * n;
+  const int rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3, rD = (n - 3 + 7) & ~3, rO = (out_floats + 7) & ~3;
+  float* base = smem + (size_t)g * (rL + rA + rD + rO);
+  float *sL = base, *sA = base + rL, *sD = base + rL + rA, *sO = base + rL + rA + rD;
+  float* dst = xyz + (active ? frame : 0) * (int64_t)out_floats;
+  sO += (int)((reinterpret_cast<uintptr_t>(dst) & 15) >> 2);   // congruent with the global row modulo 16 bytes
+
+  if (active) {
+    sL = stage_row_async(sL, lengths + frame * lstride, n - 1, t, 64);
+    sA = stage_row_async(sA, angles + frame * (int64_t)(n - 2), n - 2, t, 64);
+    sD = stage_row_async(sD, dihedrals + frame * (int64_t)(n - 3), n - 3, t, 64);
+  }
+  cp_async_wait_all();
+  __syncthreads();
 
   const int s = n / 2;
-  // ---- anchor: planar positions of atoms s-1, s, s+1 (SE(2) reduction over bonds 0..s-2, then 2 steps)
-  Se2 head{1.0, 0.0, 0.0, 0.0};
-  {
-    const int nb = s - 1;  // bonds 0 .. s-2 bring us to atom s-1 with direction psi_{s-1}
-    const int cs = (nb + 31) / 32;
-    const int k0 = min(nb, lane * cs), k1 = min(nb, k0 + cs);
-    Se2 t{1.0, 0.0, 0.0, 0.0};
-    for (int k = k0; k < k1; k++) planar_step(t, (double)sL[k], true, sA[k], k);
-    Se2 ex;
-    Se2 inc = se2_scan(t, lane, &ex);
-    head = se2_shfl(inc, 31);
-  }
-  // head: (c,s) = direction of bond s-1, (x,y) = c_{s-1}
-  const double dm_c = head.c, dm_s = head.s;          // direction of bond s-1
-  const double am_x = head.x, am_y = head.y;          // c_{s-1}
-  Se2 mid = head;
-  planar_step(mid, (double)sL[s - 1], true, sA[s - 1], s - 1);   // -> c_s, direction of bond s
-  const double a0_x = mid.x, a0_y = mid.y;
-  const double dp_c = mid.c, dp_s = mid.s;
-  const double ap_x = fma((double)sL[s], dp_c, a0_x), ap_y = fma((double)sL[s], dp_s, a0_y);  // c_{s+1}
-  const double crs = dm_c * dp_s - dm_s * dp_c;       // z of (bond s-1) x (bond s)
-  const double zs = crs >= 0.0 ? 1.0 : -1.0;
-  if (lane == 0) {
-    sO[3 * (s - 1)] = (float)am_x; sO[3 * (s - 1) + 1] = (float)am_y; sO[3 * (s - 1) + 2] = 0.f;
-    sO[3 * s] = (float)a0_x;       sO[3 * s + 1] = (float)a0_y;       sO[3 * s + 2] = 0.f;
-    sO[3 * (s + 1)] = (float)ap_x; sO[3 * (s + 1) + 1] = (float)ap_y; sO[3 * (s + 1) + 2] = 0.f;
-  }
-
-  // ---- two half-warps: lanes 0-15 build the left side (atoms s-2 .. 0), lanes 16-31 the right side
-  const int side = lane >> 4, q = lane & 15;
   const int steps = side == 0 ? (s - 1) : (n - s - 2);
-  int cs = (steps + 15) / 16;
-  cs |= 1;  // odd chunk length => conflict-free strided shared-memory writes
-  const int i0 = min(steps, q * cs), i1 = min(steps, i0 + cs);
+  const int ch = ((max(s - 1, n - s - 2) + 31) / 32) | 1;   // odd chunk length: conflict-free strided smem access
+  const int i0 = lane * ch;
 
+  // ---- pass 1 (branch-free body: out-of-range steps load zeros and store nothing, so the unrolled
+  //      iterations can be software-pipelined: the sin/cos of step c+1 overlap the matrix chain of step c)
   Se3 f;
   se3_identity(f);
-  for (int i = i0; i < i1; i++) {
-    int k, kd, ka, kl;
-    if (side == 0) { k = s - 2 - i; kd = k; ka = k; kl = k; }
-    else           { k = s + 2 + i; kd = k - 3; ka = k - 2; kl = k - 1; }
-    double sw, cw, sg, cg;
-    sincos_d((double)sD[kd], &sw, &cw);
-    sincos_d((double)sA[ka], &sg, &cg);
-    nerf_step(f, cw, sw, -cg, sg, (double)sL[kl]);   // g = pi - theta: cos g = -cos theta, sin g = sin theta
-    sO[3 * k] = (float)f.p[0];
-    sO[3 * k + 1] = (float)f.p[1];
-    sO[3 * k + 2] = (float)f.p[2];
-  }
-  Se3 pre = se3_exclusive_scan(f, q, 16);
-  // anchor frame of this side: x along the last anchored bond, z = +-e_z, y = z x x, origin at the last anchor atom
-  Se3 g0;
+  Se2 pl{1.0, 0.0, 0.0, 0.0};   // planar product of this lane's bonds (left warp only), ascending bond order
+  const int nvalid = active ? max(0, min(ch, steps - i0)) : 0;
+  const int dk = side == 0 ? -1 : 1;
+  const int kfirst = side == 0 ? s - 2 - i0 : s + 2 + i0;
   {
-    double xx, xy, zz, ox, oy;
-    if (side == 0) { xx = -dm_c; xy = -dm_s; zz = -zs; ox = am_x; oy = am_y; }
-    else           { xx = dp_c;  xy = dp_s;  zz = zs;  ox = ap_x; oy = ap_y; }
-    g0.r[0] = xx; g0.r[1] = -zz * xy; g0.r[2] = 0.0;
-    g0.r[3] = xy; g0.r[4] = zz * xx;  g0.r[5] = 0.0;
-    g0.r[6] = 0.0; g0.r[7] = 0.0;     g0.r[8] = zz;
-    g0.p[0] = ox; g0.p[1] = oy; g0.p[2] = 0.0;
+    const float* pD = sD + (side == 0 ? kfirst : kfirst - 3);
+    const float* pA = sA + (side == 0 ? kfirst : kfirst - 2);
+    const float* pL = sL + (side == 0 ? kfirst : kfirst - 1);
+    float* pO = sO + 3 * kfirst;
+    int kpar = kfirst;
+#pragma unroll 5
+    for (int c = 0; c < ch; c++) {
+      const bool ok = c < nvalid;
+      const float fd = ok ? *pD : 0.f, fa = ok ? *pA : 0.f, fl = ok ? *pL : 0.f;
+      double sw, cw, sg, cg;
+      sincos_tab(fd, tab, &sw, &cw);
+      sincos_tab(fa, tab, &sg, &cg);
+      const double L = (double)fl;
+      nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
+      if (ok) {
+        pO[0] = (float)f.p[0];
+        pO[1] = (float)f.p[1];
+        pO[2] = (float)f.p[2];
+      }
+      if (side == 0) {
+        // planar bond k: advance L along the current direction, then turn by -(-1)^k (pi - theta_k);
+        // this lane walks k downwards, so the step is prepended: pl <- step_k o pl
+        const double tc = ok ? -cg : 1.0, ts = ok ? ((kpar & 1) ? sg : -sg) : 0.0;
+        const double nc = tc * pl.c - ts * pl.s, ns = tc * pl.s + ts * pl.c;
+        const double nx = L + tc * pl.x - ts * pl.y, ny = ts * pl.x + tc * pl.y;
+        pl.c = nc; pl.s = ns; pl.x = nx; pl.y = ny;
+      }
+      pD += dk; pA += dk; pL += dk; pO += 3 * dk; kpar += dk;
+    }
   }
-  pre = se3_mul(g0, pre);
-  for (int i = i0; i < i1; i++) {
-    const int k = side == 0 ? s - 2 - i : s + 2 + i;
-    const double lx = sO[3 * k], ly = sO[3 * k + 1], lz = sO[3 * k + 2];
-    sO[3 * k] = (float)(pre.r[0] * lx + pre.r[1] * ly + pre.r[2] * lz + pre.p[0]);
-    sO[3 * k + 1] = (float)(pre.r[3] * lx + pre.r[4] * ly + pre.r[5] * lz + pre.p[1]);
-    sO[3 * k + 2] = (float)(pre.r[6] * lx + pre.r[7] * ly + pre.r[8] * lz + pre.p[2]);
+
+  // ---- scan of the chunk aggregates inside the warp ---------------------------------------------------
+  Se3 inc = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Se3 up = se3_shfl_up(inc, d, 32);
+    if (lane >= d) inc = se3_mul(up, inc);
   }
-  __syncwarp();
-  float* dst = xyz + frame * (int64_t)(3 * n);
-  for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
+  Se3 ex = se3_shfl_up(inc, 1, 32);
+  if (lane == 0) se3_identity(ex);
+
+  // ---- anchor: the left warp reduces the planar product (higher lanes hold lower bonds => go on the left)
+  if (side == 0) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Se2 o = se2_shfl_down(pl, d);
+      if (lane + d < 32) pl = se2_mul(o, pl);
+    }
+    if (lane == 0 && active) {
+      // pl: direction of bond s-1 and position of atom s-1 in the plane
+      const double dm_c = pl.c, dm_s = pl.s, am_x = pl.x, am_y = pl.y;
+      Se2 mid = pl;
+      planar_step(mid, (double)sL[s - 1], true, sA[s - 1], s - 1);
+      const double a0_x = mid.x, a0_y = mid.y, dp_c = mid.c, dp_s = mid.s;
+      const double ap_x = fma((double)sL[s], dp_c, a0_x), ap_y = fma((double)sL[s], dp_s, a0_y);
+      const double zs = (dm_c * dp_s - dm_s * dp_c) >= 0.0 ? 1.0 : -1.0;
+      sO[3 * (s - 1)] = (float)am_x; sO[3 * (s - 1) + 1] = (float)am_y; sO[3 * (s - 1) + 2] = 0.f;
+      sO[3 * s] = (float)a0_x;       sO[3 * s + 1] = (float)a0_y;       sO[3 * s + 2] = 0.f;
+      sO[3 * (s + 1)] = (float)ap_x; sO[3 * (s + 1) + 1] = (float)ap_y; sO[3 * (s + 1) + 2] = 0.f;
+      // anchor frames: x along the last anchored bond, z = +-e_z, y = z x x, origin at the last anchor atom
+#pragma unroll
+      for (int sd = 0; sd < 2; sd++) {
+        const double xx = sd == 0 ? -dm_c : dp_c, xy = sd == 0 ? -dm_s : dp_s, zz = sd == 0 ? -zs : zs;
+        double* a = anchor[g][sd];
+        a[0] = xx; a[1] = -zz * xy; a[2] = 0.0;
+        a[3] = xy; a[4] = zz * xx;  a[5] = 0.0;
+        a[6] = 0.0; a[7] = 0.0;     a[8] = zz;
+        a[9] = sd == 0 ? am_x : ap_x; a[10] = sd == 0 ? am_y : ap_y; a[11] = 0.0;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: out = (anchor o prefix)(local), float32 -------------------------------------------------
+  if (active) {
+    Se3 carry;
+#pragma unroll
+    for (int i = 0; i < 9; i++) carry.r[i] = anchor[g][side][i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) carry.p[i] = anchor[g][side][9 + i];
+    const Se3 pre = se3_mul(carry, ex);
+    float rf[9], ph[3], plo[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) rf[i] = (float)pre.r[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      ph[i] = (float)pre.p[i];
+      plo[i] = (float)(pre.p[i] - (double)ph[i]);
+    }
+    float* pO = sO + 3 * kfirst;
+#pragma unroll 5
+    for (int c = 0; c < ch; c++) {
+      if (c < nvalid) {
+        const float lx = pO[0], ly = pO[1], lz = pO[2];
+        pO[0] = ph[0] + (fmaf(rf[0], lx, fmaf(rf[1], ly, rf[2] * lz)) + plo[0]);
+        pO[1] = ph[1] + (fmaf(rf[3], lx, fmaf(rf[4], ly, rf[5] * lz)) + plo[1]);
+        pO[2] = ph[2] + (fmaf(rf[6], lx, fmaf(rf[7], ly, rf[8] * lz)) + plo[2]);
+      }
+      pO += 3 * dk;
+    }
+  }
+  __syncthreads();
+  if (active) store_row(dst, sO, out_floats, t, 64);
 }
 
 // ====================================================================================================
@@ -603,21 +744,45 @@ static int set_smem(K kern, size_t bytes) {
   return EMK_OK;
 }
 
+static int get_sincos_table(const double2** out) {
+  static double2* tables[64] = {nullptr};
+  int dev = 0;
+  EMK_CUDA(cudaGetDevice(&dev));
+  EMK_REQUIRE(dev >= 0 && dev < 64, EMK_E_UNSUPPORTED, "device ordinal %d out of range", dev);
+  if (!tables[dev]) {
+    double2* t = nullptr;
+    EMK_CUDA(cudaMalloc(&t, SC_TABLE * sizeof(double2)));
+    sincos_table_kernel<<<SC_TABLE / 256, 256>>>(t);
+    int rc = launch_status("sincos_table_kernel");
+    if (rc) return rc;
+    EMK_CUDA(cudaDeviceSynchronize());
+    tables[dev] = t;
+  }
+  *out = tables[dev];
+  return EMK_OK;
+}
+
 int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angles, const float* dihedrals, int64_t b,
                        int64_t n, float* xyz, cudaStream_t st) {
   EMK_REQUIRE(lengths && angles && dihedrals && xyz, EMK_E_NULL, "emk_backmap: NULL pointer argument");
   EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_backmap: need 4 <= n_atoms < 2^20, got %lld", (long long)n);
   EMK_REQUIRE(b >= 0 && (lstride == 0 || lstride == n - 1), EMK_E_ARG, "emk_backmap: lengths_batch_stride must be 0 or n_atoms-1");
   if (b == 0) return EMK_OK;
-  int warps;
-  size_t smem;
-  int rc = pick_warps((size_t)(n - 1) + (n - 2) + (n - 3) + 3 * n, 0, &warps, &smem);
+  const double2* tab;
+  int rc = get_sincos_table(&tab);
   if (rc) return rc;
+  constexpr int FPC = FWD_THREADS / 64;
+  const size_t per_frame = (((size_t)n - 1 + 7) & ~(size_t)3) + (((size_t)n - 2 + 7) & ~(size_t)3) + (((size_t)n - 3 + 7) & ~(size_t)3) + ((3 * (size_t)n + 7) & ~(size_t)3);
+  const size_t smem = (size_t)FPC * per_frame * sizeof(float);
+  EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "emk_backmap: chain of %lld atoms needs %zu bytes of staging shared memory", (long long)n, smem);
   static bool cfg = false;
-  if (!cfg) { rc = set_smem(backmap_fwd_kernel, smem); if (rc) return rc; cfg = true; }
-  const int64_t blocks = (b + warps - 1) / warps;
-  backmap_fwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz);
-  return launch_status("backmap_fwd_kernel");
+  if (!cfg) {
+    EMK_CUDA(cudaFuncSetAttribute(backmap_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  const int64_t blocks = (b + FPC - 1) / FPC;
+  backmap_fwd3_kernel<<<(unsigned)blocks, FWD_THREADS, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz, tab);
+  return launch_status("backmap_fwd3_kernel");
 }
 
 int chain_in_plane_device(const float* lengths, int64_t lstride, const float* angles, int64_t b, int64_t n, float* xyz, cudaStream_t st) {

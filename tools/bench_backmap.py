@@ -1,0 +1,50 @@
+"""Quick timing of the back-mapping kernels (fwd, fwd+bwd) at config-3 and config-5 shapes."""
+import math
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from encodermap_b200 import _ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+HBM = 6464.3
+
+
+def run(n, b, reps=5):
+    g = torch.Generator(device=dev).manual_seed(1)
+    lengths = (0.13 + 0.02 * torch.rand(1, n - 1, device=dev, generator=g)).contiguous()
+    ang = (1.9 + 0.3 * torch.rand(b, n - 2, device=dev, generator=g)).requires_grad_(True)
+    dih = ((torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).requires_grad_(True)
+    w = torch.randn(b, n, 3, device=dev, generator=g)
+    with torch.no_grad():
+        for _ in range(2):
+            _ops.BackMap.apply(lengths, ang, dih)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            _ops.BackMap.apply(lengths, ang, dih)
+        e1.record()
+        torch.cuda.synchronize()
+    fwd = e0.elapsed_time(e1) / reps
+    xyz = _ops.BackMap.apply(lengths, ang, dih)
+    xyz.backward(w)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ang.grad = dih.grad = None
+        xyz = _ops.BackMap.apply(lengths, ang, dih)
+        xyz.backward(w)
+    e1.record()
+    torch.cuda.synchronize()
+    both = e0.elapsed_time(e1) / reps
+    bf = 4 * ((n - 2) + (n - 3)) + 12 * n
+    bb = bf + 12 * n * 2 + 4 * (n - 2) * 2 + 4 * (n - 3)
+    print(f"n={n} b={b}: fwd {fwd:.3f} ms {b / fwd / 1e3:.2f} Mframes/s {b * bf / fwd / 1e6 / HBM:.3f} of HBM | "
+          f"fwd+bwd {both:.3f} ms {b / both / 1e3:.2f} Mframes/s {b * bb / both / 1e6 / HBM:.3f} of HBM (bwd alone {both - fwd:.3f} ms)")
+
+
+for n, b in ((300, 1024), (300, 65536), (1500, 65536), (999, 32768), (3000, 8192)):
+    run(n, b)
