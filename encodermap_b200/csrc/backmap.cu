@@ -281,23 +281,29 @@ __global__ void sincos_table_kernel(double2* tab) {
   }
 }
 
+// valid for |x| < 48 (larger arguments are wrapped once while staging, see wrap_large_angles)
 __device__ __forceinline__ void sincos_tab(float x, const double2* __restrict__ tab, double* s, double* c) {
-  if (fabsf(x) < 48.f) {
-    // k = rint(x * 1024 / 2pi) by the magic-number trick; the low mantissa bits of (x*A + M) are k mod 2^22
-    const float km = fmaf(x, 162.9746551513672f, 12582912.f);
-    const float kf = km - 12582912.f;
-    // 2pi/1024 = C1 + C2 + C3 with 11-bit C1, C2: the first two reductions are exact in float32
-    float r = fmaf(-kf, 0.006134033203125f, x);
-    r = fmaf(-kf, 1.889653503894806e-06f, r);
-    r = fmaf(-kf, 2.949136768126692e-10f, r);
-    const float r2 = r * r;
-    const float sr = fmaf(r * r2, -0.16666667f, r);                  // sin r
-    const float cm = r2 * fmaf(r2, 0.041666668f, -0.5f);             // cos r - 1
-    const double2 t = __ldg(tab + (__float_as_int(km) & (SC_TABLE - 1)));
-    *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
-    *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
-  } else {
-    sincos_d((double)x, s, c);
+  // k = rint(x * 1024 / 2pi) by the magic-number trick; the low mantissa bits of (x*A + M) are k mod 2^22
+  const float km = fmaf(x, 162.9746551513672f, 12582912.f);
+  const float kf = km - 12582912.f;
+  // 2pi/1024 = C1 + C2 + C3 with 11-bit C1, C2: the first two reductions are exact in float32
+  float r = fmaf(-kf, 0.006134033203125f, x);
+  r = fmaf(-kf, 1.889653503894806e-06f, r);
+  r = fmaf(-kf, 2.949136768126692e-10f, r);
+  const float r2 = r * r;
+  const float sr = fmaf(r * r2, -0.16666667f, r);                  // sin r
+  const float cm = r2 * fmaf(r2, 0.041666668f, -0.5f);             // cos r - 1
+  const double2 t = __ldg(tab + (__float_as_int(km) & (SC_TABLE - 1)));
+  *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
+  *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
+}
+// angles beyond +-48 rad (never produced by the models; allowed by the reference) are wrapped by a multiple of
+// 2 pi in float64 once, in shared memory, so that the hot loops stay branch-free; the float32 rounding of the
+// wrapped value (<= 1.2e-7 rad) is far below the ulp of the original argument
+__device__ __forceinline__ void wrap_large_angles(float* a, int len, int t, int nthreads) {
+  for (int i = t; i < len; i += nthreads) {
+    const float v = a[i];
+    if (fabsf(v) >= 48.f) a[i] = (float)remainder((double)v, 6.283185307179586476925);
   }
 }
 
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const floa
                                                                       float* __restrict__ xyz, const double2* __restrict__ tab) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double anchor[FWD_THREADS / 64][2][12];
+  __shared__ float dump_s[FWD_THREADS][3];   // sink for the stores of out-of-range steps
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid >> 6, t = tid & 63, side = (tid >> 5) & 1;
@@ -329,6 +336,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const floa
   }
   cp_async_wait_all();
   __syncthreads();
+  if (active) {
+    wrap_large_angles(sA, n - 2, t, 64);
+    wrap_large_angles(sD, n - 3, t, 64);
+  }
+  __syncthreads();
 
   const int s = n / 2;
   const int steps = side == 0 ? (s - 1) : (n - s - 2);
@@ -341,6 +353,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const floa
   se3_identity(f);
   Se2 pl{1.0, 0.0, 0.0, 0.0};   // planar product of this lane's bonds (left warp only), ascending bond order
   const int nvalid = active ? max(0, min(ch, steps - i0)) : 0;
+  float* dump = dump_s[tid];
   const int dk = side == 0 ? -1 : 1;
   const int kfirst = side == 0 ? s - 2 - i0 : s + 2 + i0;
   {
@@ -358,11 +371,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const floa
       sincos_tab(fa, tab, &sg, &cg);
       const double L = (double)fl;
       nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
-      if (ok) {
-        pO[0] = (float)f.p[0];
-        pO[1] = (float)f.p[1];
-        pO[2] = (float)f.p[2];
-      }
+      float* po = ok ? pO : dump;
+      po[0] = (float)f.p[0];
+      po[1] = (float)f.p[1];
+      po[2] = (float)f.p[2];
       if (side == 0) {
         // planar bond k: advance L along the current direction, then turn by -(-1)^k (pi - theta_k);
         // this lane walks k downwards, so the step is prepended: pl <- step_k o pl
@@ -532,191 +544,260 @@ __global__ void d2c_general_kernel(const float* __restrict__ dihedrals, const fl
 
 // ====================================================================================================
 // backward: force / torque prefix sums
+//   T threads per frame (64 ... 1024, 12 atoms per thread), inputs staged with cp.async, outputs staged
+//   through shared memory.  Sums of (g, x cross g) and the reduced torque about the pivot are float64; the
+//   geometry (bond directions, bond-angle normals) and the final dot products are float32 -- they only
+//   scale a correctly reduced torque, so their 1e-7 relative error is the error of the result.
 // ====================================================================================================
 struct Wrench {
   double f[3];
   double t[3];
 };
-__device__ __forceinline__ void wrench_add(Wrench& a, const Wrench& b) {
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    a.f[i] += b.f[i];
-    a.t[i] += b.t[i];
-  }
-}
-__device__ __forceinline__ Wrench wrench_shfl_up(const Wrench& a, int d) {
-  Wrench o;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    o.f[i] = __shfl_up_sync(0xffffffffu, a.f[i], d);
-    o.t[i] = __shfl_up_sync(0xffffffffu, a.t[i], d);
-  }
-  return o;
-}
-__device__ __forceinline__ Wrench wrench_bcast(const Wrench& a, int src) {
-  Wrench o;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    o.f[i] = __shfl_sync(0xffffffffu, a.f[i], src);
-    o.t[i] = __shfl_sync(0xffffffffu, a.t[i], src);
-  }
-  return o;
-}
-// <axis, torque about pivot> = axis . (t - piv x f)
-__device__ __forceinline__ double axial_torque(const double* ax, const Wrench& w, const double* piv) {
-  const double cx = piv[1] * w.f[2] - piv[2] * w.f[1];
-  const double cy = piv[2] * w.f[0] - piv[0] * w.f[2];
-  const double cz = piv[0] * w.f[1] - piv[1] * w.f[0];
-  return ax[0] * (w.t[0] - cx) + ax[1] * (w.t[1] - cy) + ax[2] * (w.t[2] - cz);
-}
-__device__ __forceinline__ void unit_diff(const double* a, const double* b, double* u) {  // unit(b - a)
-  const double x = b[0] - a[0], y = b[1] - a[1], z = b[2] - a[2];
-  const double inv = rsqrt(x * x + y * y + z * z);
+constexpr int BWD_CA = 13;   // atoms per thread; odd => the strided shared-memory walks are conflict-free
+
+__device__ __forceinline__ void unit3(float x, float y, float z, float* u) {
+  const float inv = rsqrtf(fmaf(x, x, fmaf(y, y, z * z)));
   u[0] = x * inv; u[1] = y * inv; u[2] = z * inv;
 }
-__device__ __forceinline__ void unit_normal(const double* a, const double* m, const double* c, double* nrm) {
-  // normalised (m - a) x (c - m)
-  const double ux = m[0] - a[0], uy = m[1] - a[1], uz = m[2] - a[2];
-  const double vx = c[0] - m[0], vy = c[1] - m[1], vz = c[2] - m[2];
-  const double x = uy * vz - uz * vy, y = uz * vx - ux * vz, z = ux * vy - uy * vx;
-  const double inv = rsqrt(x * x + y * y + z * z);
-  nrm[0] = x * inv; nrm[1] = y * inv; nrm[2] = z * inv;
-}
 
+template <int T>
+__global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd2_kernel(const BwdParams p, const double2* __restrict__ tab) {
+  constexpr int CTA = T < 128 ? 128 : T;
+  constexpr int FPC = CTA / T;
+  constexpr int WPF = T / 32;
+  static_assert(T >= 32 && T % 32 == 0, "whole warps per frame");
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double wsum[FPC][WPF][6];
+  __shared__ double psum[FPC][WPF][4];
 
-__global__ void backmap_bwd_kernel(const BwdParams p) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
-  if (frame >= p.b) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid / T, t = tid % T, wf = t >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * FPC + g;
+  const bool active = frame < p.b;
+  const int64_t fr = active ? frame : 0;
   const int n = p.n;
   const bool need_planar = p.planar || ((p.grad_angles || p.grad_lengths) && p.mid > 1);
-  const int per_warp = 6 * n + (n - 1) + (n - 2);
-  float* sX = smem + (size_t)warp * per_warp;
-  float* sG = sX + 3 * n;
-  float* sL = sG + 3 * n;
-  float* sA = sL + (n - 1);
-  stage_in(sG, p.grad_xyz + frame * (int64_t)(3 * n), 3 * n, lane);
-  if (!p.planar) stage_in(sX, p.xyz + frame * (int64_t)(3 * n), 3 * n, lane);
-  if (need_planar) {
-    stage_in(sL, p.lengths + frame * p.lstride, n - 1, lane);
-    stage_in(sA, p.angles + frame * (int64_t)(n - 2), n - 2, lane);
+
+  const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3;
+  float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0));
+  float* sX = base;
+  float* sG = base + rX;
+  float* sL = sG + rG;
+  float* sA = sL + rL;
+  if (active) {
+    sG = stage_row_async(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
+    if (!p.planar) sX = stage_row_async(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
+    if (need_planar) {
+      sL = stage_row_async(sL, p.lengths + fr * p.lstride, n - 1, t, T);
+      sA = stage_row_async(sA, p.angles + fr * (int64_t)(n - 2), n - 2, t, T);
+    }
   }
-  __syncwarp();
+  cp_async_wait_all();
+  __syncthreads();
 
-  const int ca = (n + 31) / 32;                 // atoms per lane
-  const int k0 = min(n, lane * ca), k1 = min(n, k0 + ca);
+  const int k0 = min(n, t * BWD_CA), k1 = min(n, k0 + BWD_CA);
 
-  // planar chain prefix per lane: state BEFORE bond k0 (direction of bond k0, position of atom k0)
+  // ---- planar chain: state before bond k0 (direction of bond k0, position of atom k0) -----------------------
   Se2 pl_ex{1.0, 0.0, 0.0, 0.0};
   if (need_planar) {
-    Se2 t{1.0, 0.0, 0.0, 0.0};
-    for (int k = k0; k < k1 && k < n - 1; k++) planar_step(t, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
-    se2_scan(t, lane, &pl_ex);
-    if (p.planar) {
-      // recompute the planar coordinates: they are the "final" coordinates of chain_in_plane
-      Se2 run = pl_ex;
-      if (lane == 0) { sX[0] = 0.f; sX[1] = 0.f; sX[2] = 0.f; }
+    Se2 part{1.0, 0.0, 0.0, 0.0};
+    if (active)
       for (int k = k0; k < k1 && k < n - 1; k++) {
-        Se2 st{1.0, 0.0, 0.0, 0.0};
-        planar_step(st, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
-        run = se2_mul(run, st);
-        sX[3 * (k + 1)] = (float)run.x; sX[3 * (k + 1) + 1] = (float)run.y; sX[3 * (k + 1) + 2] = 0.f;
+        part.x = fma((double)sL[k], part.c, part.x);
+        part.y = fma((double)sL[k], part.s, part.y);
+        if (k < n - 2) {
+          float a = sA[k];
+          if (fabsf(a) >= 48.f) {   // wrap exotic arguments once; this thread is the only reader of sA[k]
+            a = (float)remainder((double)a, 6.283185307179586476925);
+            sA[k] = a;
+          }
+          double st, ct;
+          sincos_tab(a, tab, &st, &ct);
+          const double cw = -ct, sw = (k & 1) ? st : -st;
+          const double c2 = part.c * cw - part.s * sw, s2 = part.c * sw + part.s * cw;
+          part.c = c2; part.s = s2;
+        }
       }
-      __syncwarp();
-    }
-  }
-
-  // ---- pass 1: per-lane wrench, warp scan
-  Wrench w{};
-  for (int k = k0; k < k1; k++) {
-    double x[3], g[3];
-    load3(sX + 3 * k, x);
-    load3(sG + 3 * k, g);
-    w.f[0] += g[0]; w.f[1] += g[1]; w.f[2] += g[2];
-    w.t[0] += x[1] * g[2] - x[2] * g[1];
-    w.t[1] += x[2] * g[0] - x[0] * g[2];
-    w.t[2] += x[0] * g[1] - x[1] * g[0];
-  }
-  Wrench inc = w;
-  for (int d = 1; d < 32; d <<= 1) {
-    Wrench up = wrench_shfl_up(inc, d);
-    if (lane >= d) wrench_add(inc, up);
-  }
-  const Wrench tot = wrench_bcast(inc, 31);
-  Wrench lo = wrench_shfl_up(inc, 1);            // sum over atoms < k0
-  if (lane == 0) lo = Wrench{};
-
-  float* gA = p.grad_angles ? p.grad_angles + frame * (int64_t)(n - 2) : nullptr;
-  float* gD = p.grad_dihedrals ? p.grad_dihedrals + frame * (int64_t)(n - 3) : nullptr;
-  float* gL = p.grad_lengths ? p.grad_lengths + frame * (int64_t)(n - 1) : nullptr;
-  const double ez[3] = {0.0, 0.0, 1.0};
-
-  // ---- pass 2: walk the chunk; after adding atom k, `lo` = sum over atoms <= k, hi = tot - lo
-  Se2 pl = pl_ex;  // planar state before bond k: (c,s) = direction of bond k, (x,y) = c_k
-  for (int k = k0; k < k1; k++) {
-    double xk[3], g[3];
-    load3(sX + 3 * k, xk);
-    load3(sG + 3 * k, g);
-    lo.f[0] += g[0]; lo.f[1] += g[1]; lo.f[2] += g[2];
-    lo.t[0] += xk[1] * g[2] - xk[2] * g[1];
-    lo.t[1] += xk[2] * g[0] - xk[0] * g[2];
-    lo.t[2] += xk[0] * g[1] - xk[1] * g[0];
-    Wrench hi;
+    Se2 inc = part;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { hi.f[i] = tot.f[i] - lo.f[i]; hi.t[i] = tot.t[i] - lo.t[i]; }
-
-    double xm[3] = {0, 0, 0}, xp[3] = {0, 0, 0}, xpp[3] = {0, 0, 0};
-    if (k >= 1) load3(sX + 3 * (k - 1), xm);
-    if (k + 1 < n) load3(sX + 3 * (k + 1), xp);
-    if (k + 2 < n) load3(sX + 3 * (k + 2), xpp);
-
-    // planar direction of bond k and planar position of atom k+1 (for the left-of-anchor terms)
-    double pdir[3] = {pl.c, pl.s, 0.0};
-    double cnext[3] = {0, 0, 0};
-    if (need_planar && k < n - 1) {
-      planar_step(pl, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
-      cnext[0] = pl.x; cnext[1] = pl.y;
+    for (int d = 1; d < 32; d <<= 1) {
+      Se2 up = se2_shfl_up(inc, d);
+      if (lane >= d) inc = se2_mul(up, inc);
     }
+    Se2 ex = se2_shfl_up(inc, 1);
+    if (lane == 0) ex = Se2{1.0, 0.0, 0.0, 0.0};
+    if (lane == 31) {
+      psum[g][wf][0] = inc.c; psum[g][wf][1] = inc.s; psum[g][wf][2] = inc.x; psum[g][wf][3] = inc.y;
+    }
+    __syncthreads();
+    Se2 prev{1.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < wf; w++) prev = se2_mul(prev, Se2{psum[g][w][0], psum[g][w][1], psum[g][w][2], psum[g][w][3]});
+    pl_ex = se2_mul(prev, ex);
+    if (p.planar) {
+      // chain_in_plane backward: the planar coordinates are the "final" coordinates
+      Se2 run = pl_ex;
+      if (active) {
+        if (t == 0) { sX[0] = 0.f; sX[1] = 0.f; sX[2] = 0.f; }
+        for (int k = k0; k < k1 && k < n - 1; k++) {
+          run.x = fma((double)sL[k], run.c, run.x);
+          run.y = fma((double)sL[k], run.s, run.y);
+          if (k < n - 2) {
+            double st, ct;
+            sincos_tab(sA[k], tab, &st, &ct);
+            const double cw = -ct, sw = (k & 1) ? st : -st;
+            const double c2 = run.c * cw - run.s * sw, s2 = run.c * sw + run.s * cw;
+            run.c = c2; run.s = s2;
+          }
+          sX[3 * (k + 1)] = (float)run.x; sX[3 * (k + 1) + 1] = (float)run.y; sX[3 * (k + 1) + 2] = 0.f;
+        }
+      }
+      __syncthreads();
+    }
+  }
 
-    // dihedrals: cut between atoms k and k+1
-    if (gD) {
-      if (k - 2 >= p.dr0 && k - 2 <= n - 4) {          // right-side twist d = k-2: atoms >= k+1 about (x_{k-1} -> x_k) through x_k
-        double u[3];
-        unit_diff(xm, xk, u);
-        gD[k - 2] = (float)axial_torque(u, hi, xk);
-      }
-      if (k < p.dr0 && k <= n - 4) {                   // left-side twist d = k: atoms <= k about (x_{k+2} -> x_{k+1}) through x_{k+1}
-        double u[3];
-        unit_diff(xp, xpp, u);
-        gD[k] = (float)(-axial_torque(u, lo, xp));
-      }
+  // ---- pass 1: wrench of this thread's atoms, block-wide prefix ------------------------------------------------
+  Wrench w{};
+  if (active)
+    for (int k = k0; k < k1; k++) {
+      const double x0 = sX[3 * k], x1 = sX[3 * k + 1], x2 = sX[3 * k + 2];
+      const double g0 = sG[3 * k], g1 = sG[3 * k + 1], g2 = sG[3 * k + 2];
+      w.f[0] += g0; w.f[1] += g1; w.f[2] += g2;
+      w.t[0] += x1 * g2 - x2 * g1;
+      w.t[1] += x2 * g0 - x0 * g2;
+      w.t[2] += x0 * g1 - x1 * g0;
     }
-    // angles
-    if (gA) {
-      if (k >= 1 && k <= n - 2 && k >= p.mid) {        // hinge at atom k (angle k-1): atoms >= k+1 move
-        double nr[3];
-        if (p.planar) { nr[0] = 0; nr[1] = 0; nr[2] = ((k - 1) & 1) ? 1.0 : -1.0; }
-        else unit_normal(xm, xk, xp, nr);
-        gA[k - 1] = (float)(-axial_torque(nr, hi, xk));
-      }
-      if (k + 1 < p.mid && k <= n - 3) {               // hinge at atom h = k+1 (angle k), left of the anchor
-        double nr[3];
-        unit_normal(xk, xp, xpp, nr);
-        const double sgn = (k & 1) ? -1.0 : 1.0;
-        gA[k] = (float)(sgn * axial_torque(ez, tot, cnext) + axial_torque(nr, lo, xp));
-      }
+  Wrench inc = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double uf = __shfl_up_sync(0xffffffffu, inc.f[i], d), ut = __shfl_up_sync(0xffffffffu, inc.t[i], d);
+      if (lane >= d) { inc.f[i] += uf; inc.t[i] += ut; }
     }
-    // bond lengths: bond k joins atoms k, k+1
-    if (gL && k < n - 1) {
-      double bd[3];
-      if (p.planar) { bd[0] = pdir[0]; bd[1] = pdir[1]; bd[2] = 0.0; }
-      else unit_diff(xk, xp, bd);
-      if (k >= p.mid - 1) {
-        gL[k] = (float)(bd[0] * hi.f[0] + bd[1] * hi.f[1] + bd[2] * hi.f[2]);
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { wsum[g][wf][i] = inc.f[i]; wsum[g][wf][3 + i] = inc.t[i]; }
+  }
+  Wrench lo;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    lo.f[i] = __shfl_up_sync(0xffffffffu, inc.f[i], 1);
+    lo.t[i] = __shfl_up_sync(0xffffffffu, inc.t[i], 1);
+    if (lane == 0) { lo.f[i] = 0.0; lo.t[i] = 0.0; }
+  }
+  __syncthreads();
+  Wrench tot{};
+#pragma unroll
+  for (int wq = 0; wq < WPF; wq++) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double a = wsum[g][wq][i], b2 = wsum[g][wq][3 + i];
+      tot.f[i] += a; tot.t[i] += b2;
+      if (wq < wf) { lo.f[i] += a; lo.t[i] += b2; }
+    }
+  }
+
+  // ---- pass 2: walk the chunk with a sliding window of positions; results overwrite g_k in place ---------------
+  //      (sG[3k] <- dihedral term, sG[3k+1] <- angle term, sG[3k+2] <- bond term of the cut after atom k)
+  const bool wantD = p.grad_dihedrals != nullptr, wantA = p.grad_angles != nullptr, wantL = p.grad_lengths != nullptr;
+  if (active && k0 < k1) {
+    Se2 pl = pl_ex;
+    auto ld = [&](int k, float* v) {
+      const int kk = min(max(k, 0), n - 1);
+      v[0] = sX[3 * kk]; v[1] = sX[3 * kk + 1]; v[2] = sX[3 * kk + 2];
+    };
+    float xm[3], xk[3], xp[3], xq[3];
+    ld(k0 - 1, xm); ld(k0, xk); ld(k0 + 1, xp);
+    double xkd[3] = {xk[0], xk[1], xk[2]}, xpd[3] = {xp[0], xp[1], xp[2]};
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) {
+      ld(k + 2, xq);
+      const double xqd[3] = {xq[0], xq[1], xq[2]};
+      {
+        const double g0 = sG[3 * k], g1 = sG[3 * k + 1], g2 = sG[3 * k + 2];
+        lo.f[0] += g0; lo.f[1] += g1; lo.f[2] += g2;
+        lo.t[0] += xkd[1] * g2 - xkd[2] * g1;
+        lo.t[1] += xkd[2] * g0 - xkd[0] * g2;
+        lo.t[2] += xkd[0] * g1 - xkd[1] * g0;
+      }
+      const bool left = k < p.dr0;
+      // wrench of the moving body and its pivot: atoms <= k about x_{k+1} (left of the anchor), atoms > k about x_k
+      double wf0, wf1, wf2, wt0, wt1, wt2, pv0, pv1, pv2;
+      if (left) {
+        wf0 = lo.f[0]; wf1 = lo.f[1]; wf2 = lo.f[2]; wt0 = lo.t[0]; wt1 = lo.t[1]; wt2 = lo.t[2];
+        pv0 = xpd[0]; pv1 = xpd[1]; pv2 = xpd[2];
       } else {
-        gL[k] = (float)(pdir[0] * tot.f[0] + pdir[1] * tot.f[1] - (bd[0] * lo.f[0] + bd[1] * lo.f[1] + bd[2] * lo.f[2]));
+        wf0 = tot.f[0] - lo.f[0]; wf1 = tot.f[1] - lo.f[1]; wf2 = tot.f[2] - lo.f[2];
+        wt0 = tot.t[0] - lo.t[0]; wt1 = tot.t[1] - lo.t[1]; wt2 = tot.t[2] - lo.t[2];
+        pv0 = xkd[0]; pv1 = xkd[1]; pv2 = xkd[2];
       }
+      const float tq0 = (float)(wt0 - (pv1 * wf2 - pv2 * wf1));
+      const float tq1 = (float)(wt1 - (pv2 * wf0 - pv0 * wf2));
+      const float tq2 = (float)(wt2 - (pv0 * wf1 - pv1 * wf0));
+      const float b00 = xk[0] - xm[0], b01 = xk[1] - xm[1], b02 = xk[2] - xm[2];   // bond k-1
+      const float b10 = xp[0] - xk[0], b11 = xp[1] - xk[1], b12 = xp[2] - xk[2];   // bond k
+      const float b20 = xq[0] - xp[0], b21 = xq[1] - xp[1], b22 = xq[2] - xp[2];   // bond k+1
+      // planar direction of bond k and planar position of atom k+1
+      const double pdir0 = pl.c, pdir1 = pl.s;
+      double cn0 = 0.0, cn1 = 0.0;
+      if (need_planar && k < n - 1) {
+        pl.x = fma((double)sL[k], pl.c, pl.x);
+        pl.y = fma((double)sL[k], pl.s, pl.y);
+        if (k < n - 2) {
+          double st, ct;
+          sincos_tab(sA[k], tab, &st, &ct);
+          const double cw = -ct, sw = (k & 1) ? st : -st;
+          const double c2 = pl.c * cw - pl.s * sw, s2 = pl.c * sw + pl.s * cw;
+          pl.c = c2; pl.s = s2;
+        }
+        cn0 = pl.x; cn1 = pl.y;
+      }
+      float rD = 0.f, rA = 0.f, rL = 0.f;
+      if (wantD) {
+        float u[3];
+        if (left) unit3(b20, b21, b22, u); else unit3(b00, b01, b02, u);
+        const float v = u[0] * tq0 + u[1] * tq1 + u[2] * tq2;
+        rD = left ? -v : v;
+      }
+      if (wantA) {
+        float nr[3];
+        if (p.planar) { nr[0] = 0.f; nr[1] = 0.f; nr[2] = ((k - 1) & 1) ? 1.f : -1.f; }
+        else if (left) unit3(b11 * b22 - b12 * b21, b12 * b20 - b10 * b22, b10 * b21 - b11 * b20, nr);
+        else unit3(b01 * b12 - b02 * b11, b02 * b10 - b00 * b12, b00 * b11 - b01 * b10, nr);
+        const float v = nr[0] * tq0 + nr[1] * tq1 + nr[2] * tq2;
+        rA = left ? (float)(((k & 1) ? -1.0 : 1.0) * (tot.t[2] - (cn0 * tot.f[1] - cn1 * tot.f[0]))) + v : -v;
+      }
+      if (wantL) {
+        float bd[3];
+        if (p.planar) { bd[0] = (float)pdir0; bd[1] = (float)pdir1; bd[2] = 0.f; }
+        else unit3(b10, b11, b12, bd);
+        const float v = bd[0] * (float)wf0 + bd[1] * (float)wf1 + bd[2] * (float)wf2;
+        rL = left ? (float)(pdir0 * tot.f[0] + pdir1 * tot.f[1]) - v : v;
+      }
+      sG[3 * k] = rD; sG[3 * k + 1] = rA; sG[3 * k + 2] = rL;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xm[i] = xk[i]; xk[i] = xp[i]; xp[i] = xq[i];
+        xkd[i] = xpd[i]; xpd[i] = xqd[i];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- gather the per-cut results into the three output rows (coalesced global stores) -----------------------------
+  if (active) {
+    if (wantD) {
+      float* gD = p.grad_dihedrals + fr * (int64_t)(n - 3);
+      for (int d = t; d < n - 3; d += T) gD[d] = sG[3 * (d < p.dr0 ? d : d + 2)];      // left: cut d, right: cut d+2
+    }
+    if (wantA) {
+      float* gA = p.grad_angles + fr * (int64_t)(n - 2);
+      for (int j = t; j < n - 2; j += T) gA[j] = sG[3 * (j + 1 < p.mid ? j : j + 1) + 1];  // left: cut j, right: cut j+1
+    }
+    if (wantL) {
+      float* gL = p.grad_lengths + fr * (int64_t)(n - 1);
+      for (int k = t; k < n - 1; k += T) gL[k] = sG[3 * k + 2];
     }
   }
 }
@@ -818,17 +899,41 @@ int d2c_general_device(const float* dihedrals, const float* chain, int64_t cstri
   return launch_status("d2c_general_kernel");
 }
 
+template <int T>
+static int launch_bwd2(const BwdParams& p, const double2* tab, bool need_planar, cudaStream_t st) {
+  constexpr int CTA = T < 128 ? 128 : T;
+  constexpr int FPC = CTA / T;
+  const size_t n = (size_t)p.n;
+  const size_t per_frame = ((3 * n + 27) & ~(size_t)3) + ((3 * n + 7) & ~(size_t)3) +
+                           (need_planar ? ((n - 1 + 7) & ~(size_t)3) + ((n - 2 + 7) & ~(size_t)3) : 0);
+  const size_t smem = FPC * per_frame * sizeof(float);
+  EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "back-mapping backward: chain of %d atoms needs %zu bytes of staging shared memory", p.n, smem);
+  auto kern = backmap_bwd2_kernel<T>;
+  static bool cfg = false;
+  if (!cfg) {
+    EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  const int64_t blocks = (p.b + FPC - 1) / FPC;
+  kern<<<(unsigned)blocks, CTA, smem, st>>>(p, tab);
+  return launch_status("backmap_bwd2_kernel");
+}
+
 int backmap_bwd_device(const BwdParams& p, cudaStream_t st) {
   if (p.b == 0) return EMK_OK;
-  int warps;
-  size_t smem;
-  int rc = pick_warps((size_t)6 * p.n + (p.n - 1) + (p.n - 2), 0, &warps, &smem);
+  EMK_REQUIRE(p.mid == 0 || p.mid - 1 == p.dr0, EMK_E_ARG, "back-mapping backward: inconsistent split (mid=%d, dr0=%d)", p.mid, p.dr0);
+  const double2* tab;
+  int rc = get_sincos_table(&tab);
   if (rc) return rc;
-  static bool cfg = false;
-  if (!cfg) { rc = set_smem(backmap_bwd_kernel, smem); if (rc) return rc; cfg = true; }
-  const int64_t blocks = (p.b + warps - 1) / warps;
-  backmap_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(p);
-  return launch_status("backmap_bwd_kernel");
+  const bool need_planar = p.planar || ((p.grad_angles || p.grad_lengths) && p.mid > 1);
+  const int n = p.n;
+  if (n <= 32 * BWD_CA) return launch_bwd2<32>(p, tab, need_planar, st);
+  if (n <= 64 * BWD_CA) return launch_bwd2<64>(p, tab, need_planar, st);
+  if (n <= 128 * BWD_CA) return launch_bwd2<128>(p, tab, need_planar, st);
+  if (n <= 256 * BWD_CA) return launch_bwd2<256>(p, tab, need_planar, st);
+  if (n <= 512 * BWD_CA) return launch_bwd2<512>(p, tab, need_planar, st);
+  EMK_REQUIRE(n <= 1024 * BWD_CA, EMK_E_UNSUPPORTED, "back-mapping backward: chains above %d atoms are not supported", 1024 * BWD_CA);
+  return launch_bwd2<1024>(p, tab, need_planar, st);
 }
 
 }  // namespace emk

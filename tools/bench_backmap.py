@@ -29,17 +29,22 @@ def run(n, b, reps=5):
         e1.record()
         torch.cuda.synchronize()
     fwd = e0.elapsed_time(e1) / reps
-    xyz = _ops.BackMap.apply(lengths, ang, dih)
-    xyz.backward(w)
+    # backward kernel alone, preallocated outputs, straight through the C ABI
+    from encodermap_b200 import _lib
+    with torch.no_grad():
+        xyz = _ops.BackMap.apply(lengths, ang, dih)
+    ga, gd = torch.empty_like(ang), torch.empty_like(dih)
+    args = [_lib.DL(v) for v in (lengths, ang.detach(), xyz, w, ga, gd)]
+    def bwd():
+        _lib.check(_lib.lib().emk_dl_backmap_bwd(args[0], args[1], args[2], args[3], args[4], args[5], None, _lib.stream_of(xyz)))
+    bwd(); bwd()
     torch.cuda.synchronize()
     e0.record()
     for _ in range(reps):
-        ang.grad = dih.grad = None
-        xyz = _ops.BackMap.apply(lengths, ang, dih)
-        xyz.backward(w)
+        bwd()
     e1.record()
     torch.cuda.synchronize()
-    both = e0.elapsed_time(e1) / reps
+    both = fwd + e0.elapsed_time(e1) / reps
     bf = 4 * ((n - 2) + (n - 3)) + 12 * n
     bb = bf + 12 * n * 2 + 4 * (n - 2) * 2 + 4 * (n - 3)
     print(f"n={n} b={b}: fwd {fwd:.3f} ms {b / fwd / 1e3:.2f} Mframes/s {b * bf / fwd / 1e6 / HBM:.3f} of HBM | "
