@@ -350,8 +350,9 @@ def secondary_metrics(dev, peaks):
     ang = (1.9 + 0.3 * torch.rand(chunk, n - 2, device=dev, generator=g)).requires_grad_(True)
     dih = ((torch.rand(chunk, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).requires_grad_(True)
     w = torch.randn(chunk, n, 3, device=dev, generator=g)
-    for it in range(3):
-        if it == 1:
+    n_warm, n_timed = 3, 5
+    for it in range(n_warm + n_timed):
+        if it == n_warm:
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -360,7 +361,7 @@ def secondary_metrics(dev, peaks):
         ang.grad = dih.grad = None
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 2
+    ms = e0.elapsed_time(e1) / n_timed
     out["backmap_fwd_bwd"] = {"frames_per_s": chunk / (ms * 1e-3), "frames": chunk, "ms": ms,
                               "bytes_per_frame": bytes_per_frame + 41960}
     # configs[1]: per-batch cost, 4096 x 1024

@@ -47,7 +47,7 @@ SigSpec make_sig_spec(float sig, float a, float b) {
 
 // device entry points implemented in the kernel files
 int64_t pair_tile_count(int64_t n);
-void tile_decode_host(int64_t t, int64_t tc, int64_t* I, int64_t* J);
+void tile_decode_host(int64_t t, int64_t n_rows, int64_t* I, int64_t* J);
 int sigmoid_cost_device(const float*, int64_t, int64_t, const float*, int64_t, double, const float*, int64_t, int64_t, double*,
                         float*, uint32_t, cudaStream_t);
 int dist_matrix_device(const float*, int64_t, int64_t, double, bool, int, float*, cudaStream_t);
@@ -197,7 +197,7 @@ int emk_pair_tile_decode(int64_t n_rows, int64_t tile, int64_t* tile_row, int64_
   EMK_REQUIRE(tile_row && tile_col, EMK_E_NULL, "emk_pair_tile_decode: NULL output");
   EMK_REQUIRE(tile >= 0 && tile < pair_tile_count(n_rows), EMK_E_ARG, "emk_pair_tile_decode: tile %lld outside [0,%lld)", (long long)tile,
               (long long)pair_tile_count(n_rows));
-  tile_decode_host(tile, (n_rows + EMK_TILE_COLS - 1) / EMK_TILE_COLS, tile_row, tile_col);
+  tile_decode_host(tile, n_rows, tile_row, tile_col);
   return EMK_OK;
 }
 

@@ -44,6 +44,7 @@ struct PairParams {
   int64_t n;          // rows
   int n_chunks;       // ceil(d / KC)
   int tiles_per_row;  // Tc = ceil(n / TN)
+  int tile_rows;      // Tr = ceil(n / TM)
   int64_t tile_begin;
   float period;       // +inf => Euclidean
   // cost epilogue
@@ -91,18 +92,42 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-// tile id -> (tile row I over 128-row blocks, tile column J over 64-column blocks), J in [2I, Tc)
-__host__ __device__ inline void tile_decode(int64_t t, int64_t tc, int64_t* I_out, int64_t* J_out) {
-  // S(I) = I * (tc + 1 - I) tiles precede row I
-  const double b = (double)(tc + 1);
-  double disc = b * b - 4.0 * (double)t;
+// tile id -> (tile row I over 128-row blocks, tile column J over 64-column blocks), J in [2I, Tc).
+// Tiles are numbered band by band: a band is BAND consecutive tile rows (1024 rows of `high`, 4 MB at
+// D = 1024); inside a band the order is column-major, so CTAs that run together share one column block and
+// the band's row blocks stay in L2 -- every column block is fetched from HBM once per band instead of
+// once per tile row.
+constexpr int BAND = 8;
+__host__ __device__ inline int64_t band_prefix(int64_t gb, int64_t tc) {   // tiles before full band gb
+  return BAND * gb * (tc - BAND + 1) - (int64_t)BAND * BAND * gb * (gb - 1);
+}
+__host__ __device__ inline void tile_decode(int64_t t, int64_t tc, int64_t tr, int64_t* I_out, int64_t* J_out) {
+  // band index from the quadratic prefix, then fix up
+  const double a = (double)BAND * BAND, bq = (double)BAND * (tc - BAND + 1) + a;
+  double disc = bq * bq - 4.0 * a * (double)t;
   if (disc < 0) disc = 0;
-  int64_t I = (int64_t)((b - sqrt(disc)) * 0.5);
-  if (I < 0) I = 0;
-  while (I > 0 && I * (tc + 1 - I) > t) --I;
-  while ((I + 1) * (tc - I) <= t) ++I;
-  *I_out = I;
-  *J_out = 2 * I + (t - I * (tc + 1 - I));
+  int64_t gb = (int64_t)((bq - sqrt(disc)) / (2.0 * a));
+  const int64_t nb = (tr + BAND - 1) / BAND;
+  if (gb < 0) gb = 0;
+  if (gb > nb - 1) gb = nb - 1;
+  while (gb > 0 && band_prefix(gb, tc) > t) --gb;
+  while (gb + 1 < nb && band_prefix(gb + 1, tc) <= t) ++gb;
+  const int64_t I0 = gb * BAND;
+  const int64_t R = (tr - I0) < BAND ? (tr - I0) : BAND;
+  int64_t u = t - band_prefix(gb, tc);
+  if (u < R * (R - 1)) {
+    // ragged head of the band: column pair p holds p+1 valid rows per column
+    int64_t pq = (int64_t)((sqrt(4.0 * (double)u + 1.0) - 1.0) * 0.5);
+    while (pq > 0 && pq * (pq + 1) > u) --pq;
+    while ((pq + 1) * (pq + 2) <= u) ++pq;
+    const int64_t rem = u - pq * (pq + 1);
+    *J_out = 2 * I0 + 2 * pq + (rem >= pq + 1 ? 1 : 0);
+    *I_out = I0 + rem % (pq + 1);
+  } else {
+    u -= R * (R - 1);
+    *J_out = 2 * (I0 + R - 1) + u / R;
+    *I_out = I0 + u % R;
+  }
 }
 
 template <bool PERIODIC, Epi EPI>
@@ -123,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
   const int tx = tid & 15;  // 0..15 -> cols tx + 16 j
 
   int64_t I, J;
-  tile_decode(p.tile_begin + blockIdx.x, p.tiles_per_row, &I, &J);
+  tile_decode(p.tile_begin + blockIdx.x, p.tiles_per_row, p.tile_rows, &I, &J);
   const int64_t row0 = I * TM;
   const int64_t col0 = J * TN;
   const bool diag = (J >> 1) == I;
@@ -440,7 +465,9 @@ static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_ti
   return launch_status("pair_tile_kernel");
 }
 
-void tile_decode_host(int64_t t, int64_t tc, int64_t* I, int64_t* J) { tile_decode(t, tc, I, J); }
+void tile_decode_host(int64_t t, int64_t n_rows, int64_t* I, int64_t* J) {
+  tile_decode(t, (n_rows + TN - 1) / TN, (n_rows + TM - 1) / TM, I, J);
+}
 
 int64_t pair_tile_count(int64_t n) {
   if (n <= 0) return 0;
@@ -478,6 +505,7 @@ int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* lo
     p.n = n;
     p.n_chunks = (int)((d + KC - 1) / KC);
     p.tiles_per_row = (int)((n + TN - 1) / TN);
+    p.tile_rows = (int)((n + TM - 1) / TM);
     p.tile_begin = tile_begin;
     p.period = std::isinf(periodicity) ? INFINITY : (float)periodicity;
     p.low = low;
@@ -514,6 +542,7 @@ int dist_matrix_device(const float* x, int64_t n, int64_t d, double periodicity,
     p.n = n;
     p.n_chunks = (int)((d + KC - 1) / KC);
     p.tiles_per_row = (int)((n + TN - 1) / TN);
+    p.tile_rows = (int)((n + TM - 1) / TM);
     p.tile_begin = 0;
     p.period = std::isinf(periodicity) ? INFINITY : (float)periodicity;
     p.out = out;

@@ -75,8 +75,9 @@ EMK_API int emk_backmap_split_indices(int64_t n_atoms, int32_t* left_atoms, int3
 
 /* Work decomposition of the all-pairs cost: the N x N pair space is cut into tiles of
  * EMK_TILE_ROWS x EMK_TILE_COLS; only tiles that touch the upper triangle are evaluated.
- * Tiles are numbered row-major over tile rows; a multi-GPU run gives rank r the contiguous
- * range emk_pair_tile_range(n, r, world). */
+ * Tiles are numbered band by band (8 tile rows per band, column-major inside a band, so that
+ * concurrently running tiles share their column block in L2); a multi-GPU run gives rank r the
+ * contiguous range emk_pair_tile_range(n, r, world). */
 #define EMK_TILE_ROWS 128
 #define EMK_TILE_COLS 64
 EMK_API int64_t emk_pair_tile_count(int64_t n_rows);

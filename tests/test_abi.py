@@ -95,13 +95,18 @@ def test_split_indices_bit_exact(L, golden):
 
 
 def test_pair_tile_enumeration(L):
-    for n in (1, 63, 64, 65, 128, 129, 200, 1000, 4096, 5000):
+    for n in (1, 63, 64, 65, 128, 129, 200, 1000, 1100, 4096, 5000, 9000):
         tr, tc = -(-n // 128), -(-n // 64)
-        want = [(i, j) for i in range(tr) for j in range(2 * i, tc)]
+        want = {(i, j) for i in range(tr) for j in range(2 * i, tc)}
         assert L.pair_tile_count(n) == len(want)
-        step = max(1, len(want) // 500)
-        for t in list(range(0, len(want), step)) + [len(want) - 1]:
-            assert L.pair_tile_decode(n, t) == want[t]
+        got = [L.pair_tile_decode(n, t) for t in range(len(want))]
+        assert len(set(got)) == len(got) and set(got) == want      # a bijection onto the upper-triangular tiles
+        # band-major order: 8 tile rows per band, column-major inside a band
+        bands = [i // 8 for i, _ in got]
+        assert bands == sorted(bands)
+        for (i0, j0), (i1, j1) in zip(got, got[1:]):
+            if i0 // 8 == i1 // 8:
+                assert (j1, i1) > (j0, i0)
         # every unordered pair (i <= j) of rows is covered exactly once by the tile list
         if n <= 200:
             cover = np.zeros((n, n), dtype=int)
@@ -112,6 +117,8 @@ def test_pair_tile_enumeration(L):
                     cover[c0:c1, r0:r1] += 1
             assert (cover == 1).all()
     assert L.pair_tile_count(65536) == 262656
+    seen = {L.pair_tile_decode(65536, t) for t in range(0, 262656, 97)} | {L.pair_tile_decode(65536, 262655)}
+    assert all(0 <= i < 512 and 2 * i <= j < 1024 for i, j in seen) and len(seen) == len(range(0, 262656, 97)) + 1
     for world in (1, 2, 3, 4, 8):
         ranges = [L.pair_tile_range(65536, r, world) for r in range(world)]
         assert ranges[0][0] == 0 and ranges[-1][1] == 262656

@@ -53,3 +53,23 @@ def run(n, b, reps=5):
 
 for n, b in ((300, 1024), (300, 65536), (1500, 65536), (999, 32768), (3000, 8192)):
     run(n, b)
+
+
+def autograd_path(n=1500, b=32768, reps=4):
+    import time
+    g = torch.Generator(device=dev).manual_seed(1)
+    lengths = (0.13 + 0.02 * torch.rand(1, n - 1, device=dev, generator=g)).contiguous()
+    ang = (1.9 + 0.3 * torch.rand(b, n - 2, device=dev, generator=g)).requires_grad_(True)
+    dih = ((torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).requires_grad_(True)
+    w = torch.randn(b, n, 3, device=dev, generator=g)
+    for it in range(reps):
+        ang.grad = dih.grad = None
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        xyz = _ops.BackMap.apply(lengths, ang, dih)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        xyz.backward(w)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        print(f"autograd n={n} b={b}: fwd {1e3 * (t1 - t0):.3f} ms  bwd {1e3 * (t2 - t1):.3f} ms")
+
+
+autograd_path()
