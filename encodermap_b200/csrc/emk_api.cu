@@ -39,9 +39,9 @@ SigSpec make_sig_spec(float sig, float a, float b) {
   s.half_a = 0.5f * a;
   s.e = b / a;
   s.dcoef = (float)((double)b * (std::pow(2.0, (double)a / (double)b) - 1.0) / ((double)sig * (double)sig));
-  s.a_int = (a == std::floor(a) && a >= 1.f && a <= 32.f) ? (int)a : 0;
+  s.a_int = (a == std::floor(a) && a >= 1.f && a <= 17.f) ? (int)a : 0;
   const float e2 = 2.f * b / a;
-  s.e2_int = (e2 == std::floor(e2) && e2 >= 1.f && e2 <= 32.f) ? (int)e2 : 0;
+  s.e2_int = (e2 == std::floor(e2) && e2 >= 1.f && e2 <= 15.f) ? (int)e2 : 0;
   return s;
 }
 

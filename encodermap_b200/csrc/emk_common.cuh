@@ -47,8 +47,8 @@ struct SigSpec {
   float half_a;     // a/2
   float e;          // b/a
   float dcoef;      // b*c/sig^2  (prefactor of s'(r)/r)
-  int a_int;        // a if a is an integer in [1,32], else 0
-  int e2_int;       // 2*b/a if that is an integer in [1,32], else 0
+  int a_int;        // a if a is an integer in [1,17], else 0 (0 => generic powf path)
+  int e2_int;       // 2*b/a if that is an integer in [1,15], else 0
 };
 
 SigSpec make_sig_spec(float sig, float a, float b);
@@ -71,16 +71,20 @@ struct BwdParams {
 };
 
 #ifdef __CUDACC__
+// x^n for a kernel-uniform n in [0,15]: branch-free binary exponentiation (3 squarings, no MUFU).  Kept tiny on
+// purpose: the pair-tile epilogue instantiates it 128 times and must stay inside the instruction cache.
 __device__ __forceinline__ float ipow_uniform(float x, int n) {
-  // x^n for a small kernel-uniform n >= 0 (binary exponentiation, no MUFU)
-  float r = 1.f;
-  while (n > 0) {
-    if (n & 1) r *= x;
-    x *= x;
-    n >>= 1;
-  }
+  float r = (n & 1) ? x : 1.f;
+  x *= x;
+  r = (n & 2) ? r * x : r;
+  x *= x;
+  r = (n & 4) ? r * x : r;
+  x *= x;
+  r = (n & 8) ? r * x : r;
   return r;
 }
+// generic exponents go through one shared out-of-line powf (never taken by the shipped parameter sets)
+static __device__ __noinline__ float pow_generic(float x, float y) { return powf(x, y); }
 
 // value of the sigmoid at squared distance r2; if WITH_D also returns s'(r)/r in *dfac
 // (finite for a >= 2; callers zero it when r2 == 0, the reference's zero-distance mask).
@@ -103,19 +107,16 @@ __device__ __forceinline__ float sig_eval(float r2, const SigSpec& s, float* dfa
       }
     }
   } else {
-    p = powf(u2, s.half_a);
+    p = pow_generic(u2, s.half_a);
     pm1 = WITH_D ? (p / u2) : 0.f;
   }
   const float q = fmaf(s.c, p, 1.f);
   float qe;  // q^(-b/a)
   if (s.e2_int > 0) {
-    if (s.e2_int & 1) {
-      qe = ipow_uniform(1.f / sqrtf(q), s.e2_int);
-    } else {
-      qe = ipow_uniform(1.f / q, s.e2_int >> 1);
-    }
+    const float t = (s.e2_int & 1) ? 1.f / sqrtf(q) : 1.f / q;
+    qe = ipow_uniform(t, (s.e2_int & 1) ? s.e2_int : (s.e2_int >> 1));
   } else {
-    qe = powf(q, -s.e);
+    qe = pow_generic(q, -s.e);
   }
   if (WITH_D) *dfac = s.dcoef * pm1 * qe / q;
   return 1.f - qe;

@@ -158,6 +158,47 @@ __global__ void __launch_bounds__(256, MINB) probe_packed84(const float* __restr
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed 8x4 micro-tile with a 2-k loop body (LDS.64): half the code size of the LDS.128 body (fits L0 I-cache)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) probe_packed84_k2(const float* __restrict__ g, float* out, float P, int iters) {
+  extern __shared__ __align__(1024) float sm[];
+  float* sa = sm; float* sb = sm + TM * KC;
+  for (int i = threadIdx.x; i < 2 * TM * KC; i += blockDim.x) sm[i] = g[i];
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 1
+    for (int k2 = 0; k2 < KC / 2; k2++) {
+      float2 av[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) av[i] = *reinterpret_cast<const float2*>(&sa[swz(ty + 16 * i, k2 >> 1) + 2 * (k2 & 1)]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float2 bv = *reinterpret_cast<const float2*>(&sb[swz(tx + 16 * j, k2 >> 1) + 2 * (k2 & 1)]);
+        float2 nb0 = make_float2(-bv.x, -bv.y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float2 d0 = __fadd2_rn(av[i], nb0);
+          float2 m0;
+          m0.x = fminf(fabsf(d0.x), P - fabsf(d0.x)); m0.y = fminf(fabsf(d0.y), P - fabsf(d0.y));
+          acc[i][j] = __ffma2_rn(m0, m0, acc[i][j]);
+        }
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s += acc[i][j].x + acc[i][j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void clk_probe(long long* out, int iters) {
   long long c0 = clock64(); unsigned long long t0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   float x = threadIdx.x; for (int i = 0; i < iters; i++) x = fmaf(x, 1.0001f, 0.5f);
@@ -197,6 +238,8 @@ int main() {
   g_pairs_scale = 0.5;
   run("packed84/r128", probe_packed84<2>, 4, 2, g, out);
   run("packed84/r128", probe_packed84<2>, 4, 1, g, out);
+  run("p84_k2/r128", probe_packed84_k2<2>, 4, 2, g, out);
+  run("p84_k2/r128", probe_packed84_k2<2>, 4, 1, g, out);
   g_pairs_scale = 1.0;
   run("ref4/r255", probe<0, 1>, 4, 1, g, out);
   run("ref4/r128", probe<0, 2>, 4, 1, g, out);
