@@ -376,6 +376,15 @@ def secondary_metrics(dev, peaks):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     p2 = 4096 * 4097 / 2
+    # third metric: train steps/s, the callers of the hot path driven by tools/train_harness.py (torch adapter;
+    # fit()/summary/callback overhead of the reference excluded); eager and whole-step CUDA-graph replay
+    try:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import train_harness
+
+        out["train_steps"] = train_harness.run_all(dev, steps=20)
+    except Exception as e:  # noqa: BLE001 - a secondary metric must not take the headline down
+        out["train_steps"] = {"error": repr(e)}
     out["cfg2_batch_cost"] = {"pairs_per_s": p2 / (ms * 1e-3), "ms": ms, "n_rows": 4096, "n_dims": 1024,
                               "frac_fp32_issue": p2 * (4 * 1024 + 60) / (ms * 1e-3) / (148 * 128 * peaks["sm_max_mhz"] * 1e6)}
     return out

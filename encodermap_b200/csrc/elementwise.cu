@@ -1,5 +1,7 @@
 // Bandwidth-bound helpers of the hot path: periodic_distance, sigmoid, PeriodicInput, rotation_matrix,
 // column mean, and the batched small-d pairwise_dist (PairwiseDistances layer) forward / backward.
+#include <algorithm>
+
 #include "emk_common.cuh"
 
 namespace emk {
@@ -127,8 +129,20 @@ __global__ void column_final_kernel(const double* __restrict__ part, int split, 
 }
 
 // ---- batched pairwise_dist for small d (PairwiseDistances layer) ------------------------------------------
-// strict-upper-triangle index p -> (i, j), row-major: row i starts at i*(2n-i-1)/2
+// strict-upper-triangle index p -> (i, j), row-major: row i starts at i*(2n-i-1)/2.  32-bit arithmetic with a
+// float estimate + fix-up (exact for n < 4096); the 64-bit / double form covers larger n.
 __device__ __forceinline__ void triu_decode(int64_t p, int64_t n, int64_t* i_out, int64_t* j_out) {
+  if (n < 4096) {
+    const int pi = (int)p, ni = (int)n;
+    const float nn = (float)(2 * ni - 1);
+    int i = (int)((nn - sqrtf(fmaf(nn, nn, -8.f * (float)pi))) * 0.5f);
+    i = max(0, min(i, ni - 2));
+    while (i > 0 && i * (2 * ni - i - 1) / 2 > pi) --i;
+    while ((i + 1) * (2 * ni - i - 2) / 2 <= pi) ++i;
+    *i_out = i;
+    *j_out = pi - i * (2 * ni - i - 1) / 2 + i + 1;
+    return;
+  }
   const double nn = (double)(2 * n - 1);
   int64_t i = (int64_t)((nn - sqrt(nn * nn - 8.0 * (double)p)) * 0.5);
   if (i < 0) i = 0;
@@ -138,65 +152,77 @@ __device__ __forceinline__ void triu_decode(int64_t p, int64_t n, int64_t* i_out
   *j_out = p - i * (2 * n - i - 1) / 2 + i + 1;
 }
 
+// grid: (ceil(per / 256), b): one frame per blockIdx.y, coalesced output writes, inputs from L1
 __global__ void pairwise_small_kernel(const float* __restrict__ x, int64_t b, int64_t n, int64_t d, int64_t bstride,
                                       int64_t rstride, int squared, int flat, float* __restrict__ out) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
-  const int64_t total = b * per;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t bi = idx / per, p = idx - bi * per;
-    int64_t i, j;
-    if (flat) triu_decode(p, n, &i, &j);
-    else { i = p / n; j = p - i * n; }
-    const float* xi = x + bi * bstride + i * rstride;
-    const float* xj = x + bi * bstride + j * rstride;
-    float s = 0.f;
-    for (int64_t k = 0; k < d; k++) {
-      const float t = xi[k] - xj[k];
-      s = fmaf(t, t, s);
+  for (int64_t bi = blockIdx.y; bi < b; bi += gridDim.y) {
+    const float* xb = x + bi * bstride;
+    float* ob = out + bi * per;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < per; p += (int64_t)gridDim.x * blockDim.x) {
+      int64_t i, j;
+      if (flat) triu_decode(p, n, &i, &j);
+      else { i = p / n; j = p - i * n; }
+      const float* xi = xb + i * rstride;
+      const float* xj = xb + j * rstride;
+      float s = 0.f;
+      for (int64_t k = 0; k < d; k++) {
+        const float t = xi[k] - xj[k];
+        s = fmaf(t, t, s);
+      }
+      ob[p] = squared ? s : sqrtf(s);
     }
-    out[idx] = squared ? s : sqrtf(s);
   }
 }
 
-// one warp per (frame, row i): grad_x[i] = sum_j coef_ij (x_i - x_j); coef = g/dist (or 2g when squared)
+// one thread per (frame, atom i): grad_x[i] = sum_j coef_ij (x_i - x_j); coef = g/dist (or 2g when squared).
+// Threads of a warp own consecutive atoms of one frame: x_j is a broadcast read, g[pair(j,i)] for j < i is
+// contiguous across the warp; the running flat offsets avoid any per-pair index arithmetic.
 __global__ void pairwise_small_bwd_kernel(const float* __restrict__ x, int64_t b, int64_t n, int64_t d, int64_t bstride,
                                           int64_t rstride, int squared, int flat, const float* __restrict__ go,
                                           float* __restrict__ gx) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
-  for (int64_t task = wid; task < b * n; task += nw) {
-    const int64_t bi = task / n, i = task - bi * n;
+  for (int64_t bi = blockIdx.y; bi < b; bi += gridDim.y) {
     const float* xb = x + bi * bstride;
-    const float* xi = xb + i * rstride;
     const float* g = go + bi * per;
-    for (int64_t k0 = 0; k0 < d; k0 += 8) {   // up to 8 components per sweep keeps the accumulators in registers
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const int kc = (int)min((int64_t)8, d - k0);
-      for (int64_t j = lane; j < n; j += 32) {
-        if (j == i) continue;
-        const float* xj = xb + j * rstride;
-        float s = 0.f;
-        for (int64_t k = 0; k < d; k++) {
-          const float t = xi[k] - xj[k];
-          s = fmaf(t, t, s);
-        }
-        float gij;
-        if (flat) {
-          const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
-          gij = g[lo * (2 * n - lo - 1) / 2 + (hi - lo - 1)];
-        } else {
-          gij = g[i * n + j] + g[j * n + i];
-        }
-        const float coef = squared ? 2.f * gij : (s > 0.f ? gij * rsqrtf(s) : 0.f);
-        for (int k = 0; k < kc; k++) acc[k] = fmaf(coef, xi[k0 + k] - xj[k0 + k], acc[k]);
-      }
-      for (int k = 0; k < kc; k++) {
-        float v = acc[k];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float* xi = xb + i * rstride;
+      for (int64_t k0 = 0; k0 < d; k0 += 8) {   // up to 8 components per sweep keeps the accumulators in registers
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float xik[8];
+        const int kc = (int)min((int64_t)8, d - k0);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) gx[bi * bstride + i * rstride + k0 + k] = v;
+        for (int k = 0; k < 8; k++) xik[k] = k < kc ? xi[k0 + k] : 0.f;
+        // flat: pair (j,i) with j < i sits at j*(2n-j-1)/2 + (i-j-1): starts at i-1 and advances by n-j-2 per j
+        int64_t off_lo = i - 1;
+        const int64_t off_hi = i * (2 * n - i - 1) / 2 - i - 1;   // + j for j > i
+        for (int64_t j = 0; j < n; j++) {
+          float gij;
+          if (flat) {
+            if (j < i) { gij = g[off_lo]; off_lo += n - j - 2; }
+            else if (j > i) gij = g[off_hi + j];
+            else continue;
+          } else {
+            if (j == i) continue;
+            gij = g[i * n + j] + g[j * n + i];
+          }
+          const float* xj = xb + j * rstride;
+          float s = 0.f;
+          if (d <= 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              if (k < kc) { const float t = xik[k] - xj[k]; s = fmaf(t, t, s); }
+          } else {
+            for (int64_t k = 0; k < d; k++) { const float t = xi[k] - xj[k]; s = fmaf(t, t, s); }
+          }
+          const float coef = squared ? 2.f * gij : (s > 0.f ? gij * rsqrtf(s) : 0.f);
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (k < kc) acc[k] = fmaf(coef, xik[k] - xj[k0 + k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < kc) gx[bi * bstride + i * rstride + k0 + k] = acc[k];
       }
     }
   }
@@ -280,13 +306,17 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
                           int flat, float* out, cudaStream_t st) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
   if (b * per == 0) return EMK_OK;
-  pairwise_small_kernel<<<grid_for(b * per), 256, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, out);
+  const int64_t bx = std::min<int64_t>((per + 255) / 256, 1024);
+  dim3 grid((unsigned)bx, (unsigned)std::min<int64_t>(b, 65535));
+  pairwise_small_kernel<<<grid, 256, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, out);
   return launch_status("pairwise_small_kernel");
 }
 int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
                               int flat, const float* go, float* gx, cudaStream_t st) {
   if (b * n == 0) return EMK_OK;
-  pairwise_small_bwd_kernel<<<grid_for(b * n * 32), 256, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, go, gx);
+  const int threads = n >= 128 ? 128 : (int)((n + 31) / 32 * 32);
+  dim3 grid((unsigned)((n + threads - 1) / threads), (unsigned)std::min<int64_t>(b, 65535));
+  pairwise_small_bwd_kernel<<<grid, threads, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, go, gx);
   return launch_status("pairwise_small_bwd_kernel");
 }
 

@@ -1,0 +1,206 @@
+"""Measurement harness for the third metric (train steps/s): the CALLERS of the hot path, restated in
+torch so that a step can be driven end to end without TensorFlow.  Not product code -- the dense
+autoencoder stays in the host framework (cuBLAS through torch.nn.Linear); every hot op comes from
+libemk through ``encodermap_b200``.
+
+* ``EncoderMapStep``  -- what ``SequentialModel.train_step`` does (reference encodermap/models/models.py:3367-3401):
+  encoder (sin/cos for periodic input) -> latent -> decoder (atan2) ; losses auto (mean |periodic distance|) +
+  L2 regularisation + center + 500 x distance_loss (second encoder pass, loss_functions.py:277) ; Adam(1e-3, clipvalue=1).
+* ``ADCStep``         -- what ``ADCFunctionalModel.train_step`` does (:2260-2521) with use_backbone_angles=True:
+  PeriodicInput on angles+dihedrals -> encoder -> latent -> decoder -> angles / dihedrals ; BackMapLayer ->
+  PairwiseDistances(C-alpha) ; losses dihedral + angle + cartesian (mean |pair distance difference|) +
+  cartesian_distance_loss + center + regularisation.
+"""
+from __future__ import annotations
+
+import math
+import sys
+from pathlib import Path
+
+import torch
+from torch import nn
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from encodermap_b200 import ADCParameters, Parameters  # noqa: E402
+from encodermap_b200.loss_functions import cartesian_distance_loss, distance_loss  # noqa: E402
+from encodermap_b200.misc.distances import periodic_distance  # noqa: E402
+from encodermap_b200.models.layers import BackMapLayer, PairwiseDistances, PeriodicInput  # noqa: E402
+
+
+def mlp(sizes, final_activation=False):
+    layers = []
+    for i, (a, b) in enumerate(zip(sizes[:-1], sizes[1:])):
+        layers.append(nn.Linear(a, b))
+        if i < len(sizes) - 2 or final_activation:
+            layers.append(nn.Tanh())
+    return nn.Sequential(*layers)
+
+
+class EncoderMapStep(nn.Module):
+    def __init__(self, input_dim: int, p: Parameters):
+        super().__init__()
+        self.p = p
+        self.periodic = p.periodicity < float("inf")
+        d_in = input_dim * (2 if self.periodic else 1)
+        self.periodic_input = PeriodicInput(p, "input")
+        self.encoder_model = mlp([d_in, *p.n_neurons])
+        self.decoder_model = mlp([p.n_neurons[-1], *p.n_neurons[-2::-1], d_in])
+        self.dist_loss = distance_loss(self, p)
+
+    def encoder(self, x, training=False):
+        if self.periodic:
+            x = self.periodic_input(x)
+        return self.encoder_model(x)
+
+    def decoder(self, z):
+        y = self.decoder_model(z)
+        if self.periodic:
+            s, c = torch.chunk(y, 2, dim=1)
+            y = torch.atan2(s, c)
+            if self.p.periodicity != 2 * math.pi:
+                y = y / (2 * math.pi) * self.p.periodicity
+        return y
+
+    def loss(self, x):
+        z = self.encoder(x)
+        y = self.decoder(z)
+        if self.periodic:
+            auto = periodic_distance(x, y, self.p.periodicity).mean()
+        else:
+            auto = (x - y).abs().mean()
+        reg = sum((m.weight ** 2).sum() for m in self.modules() if isinstance(m, nn.Linear)) * self.p.l2_reg_constant
+        center = (z ** 2).mean() * self.p.center_cost_scale
+        return self.p.auto_cost_scale * auto + reg + center + self.dist_loss(x)
+
+
+class ADCStep(nn.Module):
+    def __init__(self, n_atoms: int, p: ADCParameters):
+        super().__init__()
+        self.p = p
+        self.n = n_atoms
+        d_in = 2 * ((n_atoms - 2) + (n_atoms - 3))
+        self.pi_angles = PeriodicInput(p, "angles")
+        self.pi_dihedrals = PeriodicInput(p, "dihedrals")
+        self.encoder_model = mlp([d_in, *p.n_neurons])
+        self.decoder_model = mlp([p.n_neurons[-1], *p.n_neurons[-2::-1], d_in])
+        self.backmap = BackMapLayer(n_atoms // 2 - 1, (n_atoms - 3) // 2)
+        self.pairwise = PairwiseDistances(p, "pairwise")
+        self.cart_dist_loss = cartesian_distance_loss(self, p)
+
+    def encoder(self, inputs, training=False):
+        angles, dihedrals = inputs[:2]
+        return self.encoder_model(torch.cat([self.pi_angles(angles), self.pi_dihedrals(dihedrals)], dim=1))
+
+    def loss(self, angles, dihedrals, cartesians, distances):
+        z = self.encoder((angles, dihedrals))
+        y = self.decoder_model(z)
+        na, nd = self.n - 2, self.n - 3
+        sa, sd, ca, cd = torch.split(y, [na, nd, na, nd], dim=1)
+        out_angles, out_dihedrals = torch.atan2(sa, ca), torch.atan2(sd, cd)
+        back = self.backmap((distances, out_angles, out_dihedrals))
+        inp_pair = self.pairwise(cartesians)
+        out_pair = self.pairwise(back)
+        dihedral_loss = periodic_distance(dihedrals, out_dihedrals, self.p.periodicity).mean()
+        angle_loss = periodic_distance(angles, out_angles, self.p.periodicity).mean()
+        cartesian_loss = (inp_pair - out_pair).abs().mean()
+        reg = sum((m.weight ** 2).sum() for m in self.modules() if isinstance(m, nn.Linear)) * self.p.l2_reg_constant
+        center = (z ** 2).mean() * self.p.center_cost_scale
+        return dihedral_loss + angle_loss + cartesian_loss + self.cart_dist_loss(inp_pair, z) + center + reg
+
+
+def time_steps(model, batch_fn, steps=20, warmup=5, graph=False):
+    """steps/s of a full training step.  graph=True captures the whole step (forward, backward, clip, Adam) in one
+    CUDA graph with static input buffers and replays it: the step is launch-bound otherwise."""
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        loss = model.loss(*batch)
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(model.parameters(), 1.0)
+        opt.step()
+        return loss.detach()
+
+    if not graph:
+        losses = []
+        for it in range(warmup + steps):
+            if it == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            losses.append(step(batch_fn(it)))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return 1e3 / ms, ms, float(losses[warmup]), float(losses[-1])
+
+    static = [b.clone() for b in batch_fn(0)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for it in range(3):
+            step(static)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    opt.zero_grad(set_to_none=True)
+    with torch.cuda.graph(g):
+        static_loss = step(static)
+    first = last = None
+    for it in range(warmup + steps):
+        if it == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        for dst, src in zip(static, batch_fn(it)):
+            dst.copy_(src)
+        g.replay()
+        if it == warmup:
+            first = static_loss.clone()
+    e1.record()
+    torch.cuda.synchronize()
+    last = static_loss.clone()
+    ms = e0.elapsed_time(e1) / steps
+    return 1e3 / ms, ms, float(first), float(last)
+
+
+def run_all(dev, steps=20):
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(7)
+    n_data = 16384
+    centres = (torch.rand(16, 1024, device=dev, generator=g) * 2 - 1) * math.pi
+    data = centres[torch.randint(0, 16, (n_data,), device=dev, generator=g)] + 0.3 * torch.randn(n_data, 1024, device=dev, generator=g)
+    data = torch.remainder(data + math.pi, 2 * math.pi) - math.pi
+    pts = torch.rand(6000, 3, device=dev, generator=g)
+    n, b = 300, 1024
+    dist = 0.13 + 0.02 * torch.rand(b, n - 1, device=dev, generator=g)
+    ang = 1.9 + 0.3 * torch.rand(b, n - 2, device=dev, generator=g)
+    dih = (torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi
+    with torch.no_grad():
+        cart = BackMapLayer(n // 2 - 1, (n - 3) // 2)((dist, ang, dih))
+    cases = {
+        # configs[1]: periodic 1024-dim angular features, batch 4096
+        "train_cfg1_encodermap_periodic_1024d_batch4096":
+            (lambda: EncoderMapStep(1024, Parameters()), lambda it: (data[(it * 4096) % n_data:(it * 4096) % n_data + 4096],)),
+        # configs[0] shape: 3-d points -> 2-d latent, batch 256, non-periodic, cube sigmoid parameters
+        "train_cfg0_cube_batch256":
+            (lambda: EncoderMapStep(3, Parameters(periodicity=float("inf"), dist_sig_parameters=(0.2, 3, 6, 1, 2, 6))),
+             lambda it: (pts[(it * 256) % 5632:(it * 256) % 5632 + 256],)),
+        # configs[2]: ADC, 100-residue chain, batch 1024
+        "train_cfg2_adc_100res_batch1024":
+            (lambda: ADCStep(n, ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True)),
+             lambda it: (ang, dih, cart, dist)),
+    }
+    for name, (make, batch_fn) in cases.items():
+        res = {}
+        for mode in ("eager", "cuda_graph"):
+            torch.manual_seed(0)
+            m = make().to(dev)
+            sps, ms, l0, l1 = time_steps(m, batch_fn, steps, graph=(mode == "cuda_graph"))
+            res[mode] = {"steps_per_s": sps, "ms_per_step": ms, "loss_first": l0, "loss_last": l1}
+        out[name] = res
+    return out
+
+
+if __name__ == "__main__":
+    import json
+
+    print(json.dumps(run_all(torch.device("cuda:0")), indent=1))
