@@ -281,8 +281,11 @@ __global__ void sincos_table_kernel(double2* tab) {
   }
 }
 
-// valid for |x| < 48 (larger arguments are wrapped once while staging, see wrap_large_angles)
 __device__ __forceinline__ void sincos_tab(float x, const double2* __restrict__ tab, double* s, double* c) {
+  if (fabsf(x) >= 48.f) {   // never produced by the models, allowed by the reference: full float64 reduction
+    sincos_d((double)x, s, c);
+    return;
+  }
   // k = rint(x * 1024 / 2pi) by the magic-number trick; the low mantissa bits of (x*A + M) are k mod 2^22
   const float km = fmaf(x, 162.9746551513672f, 12582912.f);
   const float kf = km - 12582912.f;
@@ -296,15 +299,6 @@ __device__ __forceinline__ void sincos_tab(float x, const double2* __restrict__ 
   const double2 t = __ldg(tab + (__float_as_int(km) & (SC_TABLE - 1)));
   *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
   *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
-}
-// angles beyond +-48 rad (never produced by the models; allowed by the reference) are wrapped by a multiple of
-// 2 pi in float64 once, in shared memory, so that the hot loops stay branch-free; the float32 rounding of the
-// wrapped value (<= 1.2e-7 rad) is far below the ulp of the original argument
-__device__ __forceinline__ void wrap_large_angles(float* a, int len, int t, int nthreads) {
-  for (int i = t; i < len; i += nthreads) {
-    const float v = a[i];
-    if (fabsf(v) >= 48.f) a[i] = (float)remainder((double)v, 6.283185307179586476925);
-  }
 }
 
 constexpr int FWD_THREADS = 128;
@@ -335,11 +329,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const floa
     sD = stage_row_async(sD, dihedrals + frame * (int64_t)(n - 3), n - 3, t, 64);
   }
   cp_async_wait_all();
-  __syncthreads();
-  if (active) {
-    wrap_large_angles(sA, n - 2, t, 64);
-    wrap_large_angles(sD, n - 3, t, 64);
-  }
   __syncthreads();
 
   const int s = n / 2;
@@ -606,13 +595,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd2_kernel(const
         part.x = fma((double)sL[k], part.c, part.x);
         part.y = fma((double)sL[k], part.s, part.y);
         if (k < n - 2) {
-          float a = sA[k];
-          if (fabsf(a) >= 48.f) {   // wrap exotic arguments once; this thread is the only reader of sA[k]
-            a = (float)remainder((double)a, 6.283185307179586476925);
-            sA[k] = a;
-          }
           double st, ct;
-          sincos_tab(a, tab, &st, &ct);
+          sincos_tab(sA[k], tab, &st, &ct);
           const double cw = -ct, sw = (k & 1) ? st : -st;
           const double c2 = part.c * cw - part.s * sw, s2 = part.c * sw + part.s * cw;
           part.c = c2; part.s = s2;

@@ -456,6 +456,27 @@ def test_backmap_vs_oracle(em, n, b):
     assert np.abs(diff).max() < 2e-3
 
 
+def test_backmap_unwrapped_angles(em):
+    """Angles far outside (-pi, pi] (the reference accepts any float): forward and backward still match float64."""
+    from encodermap_b200.models.layers import back_map
+
+    rng = np.random.default_rng(42)
+    n, b = 120, 6
+    dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
+    ang = (rng.uniform(1.9, 2.2, size=(b, n - 2)) + 2 * pi * rng.integers(-15, 16, size=(b, n - 2))).astype(np.float32)
+    dih = (rng.uniform(-pi, pi, size=(b, n - 3)) + 2 * pi * rng.integers(-40, 41, size=(b, n - 3))).astype(np.float32)
+    w = rng.normal(size=(b, n, 3))
+    ag, hg = cu(ang).requires_grad_(True), cu(dih).requires_grad_(True)
+    out = back_map(cu(dist), ag, hg)
+    (out * cu(w)).sum().backward()
+    ao, ho = torch.from_numpy(ang).double().requires_grad_(True), torch.from_numpy(dih).double().requires_grad_(True)
+    ref = O.back_map_layer(torch.from_numpy(dist).double(), ao, ho)
+    (ref * torch.from_numpy(w)).sum().backward()
+    assert np.abs(out.detach().cpu().numpy() - ref.detach().numpy()).max() < COORD_ATOL
+    assert relnorm(hg.grad.cpu().numpy(), ho.grad.numpy()) < GRAD_RTOL
+    assert relnorm(ag.grad.cpu().numpy(), ao.grad.numpy()) < GRAD_RTOL
+
+
 @pytest.mark.parametrize("n,b", [(4, 2), (5, 2), (9, 3), (10, 3), (30, 4), (31, 4), (300, 3)])
 def test_backmap_backward(em, n, b):
     from encodermap_b200.models.layers import back_map

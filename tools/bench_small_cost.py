@@ -1,0 +1,33 @@
+"""Per-batch sigmoid cost at training-step sizes (python tools/bench_small_cost.py); EMK_CLUSTER=1 disables the K-split."""
+import math
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from encodermap_b200 import _ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+SIG = (4.5, 12, 6, 1, 2, 6)
+for n, d, per in ((256, 3, float("inf")), (256, 1024, 2 * math.pi), (512, 1024, 2 * math.pi), (1024, 1024, 2 * math.pi),
+                  (1024, 4950, float("inf")), (2048, 1024, 2 * math.pi), (4096, 1024, 2 * math.pi), (8192, 1024, 2 * math.pi)):
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = (torch.rand(n, d, device=dev, generator=g) * 2 - 1) * math.pi
+    z = torch.randn(n, 2, device=dev, generator=g)
+    for _ in range(3):
+        _ops.sigmoid_cost_raw(x, z, per, SIG)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        _ops.sigmoid_cost_raw(x, z, per, SIG)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pairs = n * (n + 1) / 2
+    instr = pairs * ((4 if per < 1e30 else 2) * d + 60)
+    print(f"EMK_CLUSTER={os.environ.get('EMK_CLUSTER', 'auto'):>4} n={n:5d} d={d:5d} {'periodic' if per < 1e30 else 'euclid  '}: {ms * 1e3:8.1f} us  "
+          f"{pairs / ms / 1e6:8.2f} Gpairs/s  {instr / (ms * 1e-3) / (148 * 128 * 1.965e9):.3f} of FP32 issue roofline")
