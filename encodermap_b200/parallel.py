@@ -57,3 +57,47 @@ def sharded_sigmoid_cost(high: torch.Tensor, low: torch.Tensor, periodicity: flo
     else:
         loss, grad = partial_fn(high, low, periodicity, sig, tr)
     return allreduce_cost(loss, grad, group)
+
+
+class _DataParallelCost(torch.autograd.Function):
+    """Per-batch cost inside data-parallel training: every rank owns n/G rows of the
+    batch.  One exchange each way: all-gather the high-d rows and the latent, evaluate this rank's slice of the
+    pair tiles of the FULL batch, sum loss and dL/dz over ranks, keep the gradient rows this rank owns."""
+
+    @staticmethod
+    def forward(ctx, high_local, low_local, periodicity, sig, group, partial_fn):
+        from . import _ops
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        rows = high_local.shape[0]
+        high = torch.empty((rows * world, high_local.shape[1]), dtype=high_local.dtype, device=high_local.device)
+        low = torch.empty((rows * world, low_local.shape[1]), dtype=low_local.dtype, device=low_local.device)
+        dist.all_gather_into_tensor(high, high_local.contiguous(), group=group)
+        dist.all_gather_into_tensor(low, low_local.detach().contiguous(), group=group)
+        tr = tile_range(rows * world, rank, world)
+        if partial_fn is None:
+            loss, grad = _ops.sigmoid_cost_raw(high, low, periodicity, sig, tr, True)
+        else:
+            loss, grad = partial_fn(high, low, periodicity, sig, tr)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        mine = torch.empty_like(low_local)
+        try:
+            dist.reduce_scatter_tensor(mine, grad.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        except (RuntimeError, NotImplementedError):  # gloo has no reduce-scatter: all-reduce and slice
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+            mine = grad[rank * rows:(rank + 1) * rows].clone()
+        ctx.save_for_backward(mine)
+        return loss[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (mine,) = ctx.saved_tensors
+        return None, mine * grad_output, None, None, None, None
+
+
+def data_parallel_sigmoid_cost(high_local: torch.Tensor, low_local: torch.Tensor, periodicity: float, sig, group=None,
+                               partial_fn: Optional[Callable] = None) -> torch.Tensor:
+    """Sigmoid cost of the GLOBAL batch (all ranks' rows, equal counts per rank), differentiable w.r.t. this rank's
+    latent rows.  The value is the same on every rank; averaging of the dense-layer gradients is the host
+    framework's usual data-parallel all-reduce."""
+    return _DataParallelCost.apply(high_local, low_local, periodicity, tuple(sig), group, partial_fn)

@@ -19,6 +19,13 @@ def _oracle_partial(high, low, periodicity, sig, tile_range):
     """Oracle evaluation of libemk's 128x64 tile list slice [begin, end)."""
     from encodermap_b200 import _lib
 
+    with torch.enable_grad():   # also called from inside an autograd.Function.forward, where grad mode is off
+        return _oracle_partial_impl(high, low, periodicity, sig, tile_range)
+
+
+def _oracle_partial_impl(high, low, periodicity, sig, tile_range):
+    from encodermap_b200 import _lib
+
     h, z = high.double(), low.double()
     n = h.shape[0]
     sig_h, sig_l = O.sigmoid(*sig[:3]), O.sigmoid(*sig[3:])
@@ -53,7 +60,12 @@ def _worker(rank, world, port, q):
         low = torch.from_numpy(rng.normal(size=(n, 2)))
         loss, grad = parallel.sharded_sigmoid_cost(high, low, 2 * math.pi, SIG, partial_fn=_oracle_partial)
         fr = parallel.frame_range(1001, rank, world)
-        q.put((rank, loss.item(), grad.numpy(), parallel.tile_range(n, rank, world), fr))
+        # data-parallel form: every rank owns half of the rows
+        rows = n // world
+        zl = low[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+        dp = parallel.data_parallel_sigmoid_cost(high[rank * rows:(rank + 1) * rows], zl, 2 * math.pi, SIG, partial_fn=_oracle_partial)
+        dp.backward()
+        q.put((rank, loss.item(), grad.numpy(), parallel.tile_range(n, rank, world), fr, dp.item(), zl.grad.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -78,9 +90,12 @@ def test_sharded_cost_world2_gloo():
     high = rng.uniform(-math.pi, math.pi, size=(300, 12))
     low = rng.normal(size=(300, 2))
     lref, gref = O.sigmoid_loss_and_grad(high, low, 2 * math.pi, SIG)
-    for rank, loss, grad, tr, fr in results:
+    for rank, loss, grad, tr, fr, dp_loss, dp_grad in results:
         np.testing.assert_allclose(loss, lref.item(), rtol=1e-9)          # every rank holds the reduced result
         assert np.linalg.norm(grad - gref.numpy()) <= 1e-8 * np.linalg.norm(gref.numpy())
+        np.testing.assert_allclose(dp_loss, lref.item(), rtol=1e-6)       # float32 scalar out of the autograd op
+        mine = gref.numpy()[rank * 150:(rank + 1) * 150]
+        assert np.linalg.norm(dp_grad - mine) <= 1e-6 * np.linalg.norm(mine)
     (b0, e0), (b1, e1) = results[0][3], results[1][3]
     assert b0 == 0 and e0 == b1 and abs((e0 - b0) - (e1 - b1)) <= 1
     assert results[0][4] == (0, 501) and results[1][4] == (501, 1001)
