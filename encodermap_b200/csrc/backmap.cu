@@ -19,6 +19,7 @@
 // about the normal of a bond angle, slide along a bond; left of the anchor the whole molecule also
 // follows the planar chain), so each gradient is <axis, torque> or <direction, force> of a prefix sum.
 #include <algorithm>
+#include <mutex>
 
 #include "emk_common.cuh"
 
@@ -810,10 +811,12 @@ static int set_smem(K kern, size_t bytes) {
 }
 
 static int get_sincos_table(const double2** out) {
-  static double2* tables[64] = {nullptr};
+  static double2* tables[kMaxDevices] = {nullptr};
+  static std::mutex mu;
   int dev = 0;
   EMK_CUDA(cudaGetDevice(&dev));
-  EMK_REQUIRE(dev >= 0 && dev < 64, EMK_E_UNSUPPORTED, "device ordinal %d out of range", dev);
+  EMK_REQUIRE(dev >= 0 && dev < kMaxDevices, EMK_E_UNSUPPORTED, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
   if (!tables[dev]) {
     double2* t = nullptr;
     EMK_CUDA(cudaMalloc(&t, SC_TABLE * sizeof(double2)));
@@ -840,11 +843,8 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
   const size_t per_frame = (((size_t)n - 1 + 7) & ~(size_t)3) + (((size_t)n - 2 + 7) & ~(size_t)3) + (((size_t)n - 3 + 7) & ~(size_t)3) + ((3 * (size_t)n + 7) & ~(size_t)3);
   const size_t smem = (size_t)FPC * per_frame * sizeof(float);
   EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "emk_backmap: chain of %lld atoms needs %zu bytes of staging shared memory", (long long)n, smem);
-  static bool cfg = false;
-  if (!cfg) {
-    EMK_CUDA(cudaFuncSetAttribute(backmap_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
-  }
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(backmap_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t blocks = (b + FPC - 1) / FPC;
   backmap_fwd3_kernel<<<(unsigned)blocks, FWD_THREADS, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz, tab);
   return launch_status("backmap_fwd3_kernel");
@@ -859,8 +859,8 @@ int chain_in_plane_device(const float* lengths, int64_t lstride, const float* an
   size_t smem;
   int rc = pick_warps((size_t)(n - 1) + (n - 2) + 3 * n, 0, &warps, &smem);
   if (rc) return rc;
-  static bool cfg = false;
-  if (!cfg) { rc = set_smem(chain_in_plane_kernel, smem); if (rc) return rc; cfg = true; }
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) { rc = set_smem(chain_in_plane_kernel, smem); if (rc) return rc; }
   const int64_t blocks = (b + warps - 1) / warps;
   chain_in_plane_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(lengths, lstride, angles, b, (int)n, xyz);
   return launch_status("chain_in_plane_kernel");
@@ -876,8 +876,8 @@ int d2c_general_device(const float* dihedrals, const float* chain, int64_t cstri
   size_t smem;
   int rc = pick_warps((size_t)(n - 3) + 3 * n, 0, &warps, &smem);
   if (rc) return rc;
-  static bool cfg = false;
-  if (!cfg) { rc = set_smem(d2c_general_kernel, smem); if (rc) return rc; cfg = true; }
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) { rc = set_smem(d2c_general_kernel, smem); if (rc) return rc; }
   const int64_t blocks = (b + warps - 1) / warps;
   d2c_general_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(dihedrals, chain, cstride, b, (int)n, one_way, xyz);
   return launch_status("d2c_general_kernel");
@@ -893,11 +893,8 @@ static int launch_bwd2(const BwdParams& p, const double2* tab, bool need_planar,
   const size_t smem = FPC * per_frame * sizeof(float);
   EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "back-mapping backward: chain of %d atoms needs %zu bytes of staging shared memory", p.n, smem);
   auto kern = backmap_bwd2_kernel<T>;
-  static bool cfg = false;
-  if (!cfg) {
-    EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
-  }
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t blocks = (p.b + FPC - 1) / FPC;
   kern<<<(unsigned)blocks, CTA, smem, st>>>(p, tab);
   return launch_status("backmap_bwd2_kernel");

@@ -2,6 +2,7 @@
 // construction, host-buffer convenience entry points.  Kernels live in pair_tile.cu, backmap.cu,
 // elementwise.cu.
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "emk_common.cuh"
@@ -21,15 +22,20 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return 148;
-  }
-  return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    return n;
+  return 148;
+}
+
+bool first_use_on_device(bool* flags) {
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  std::lock_guard<std::mutex> lock(mu);
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
 }
 
 SigSpec make_sig_spec(float sig, float a, float b) {

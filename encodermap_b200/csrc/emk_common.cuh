@@ -36,6 +36,11 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 int sm_count();
 
+// one-time per-device kernel configuration (cudaFuncSetAttribute is per device): returns true exactly once
+// per (call site, device); call sites pass their own static flag array
+constexpr int kMaxDevices = 64;
+bool first_use_on_device(bool* flags);
+
 // ---- sketch-map sigmoid, evaluated from the SQUARED distance ---------------------------------
 // s(r) = 1 - (1 + c (r/sig)^a)^(-b/a),  c = 2^(a/b) - 1      (encodermap/misc/distances.py:86)
 // Everything is a function of r^2: (r/sig)^a = (r^2/sig^2)^(a/2), so no sqrt is needed unless a

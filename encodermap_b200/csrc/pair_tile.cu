@@ -503,11 +503,10 @@ static int pick_cluster(int64_t n_tiles, int n_chunks) {
 template <bool PERIODIC, Epi EPI>
 static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, cudaStream_t st) {
   auto kern = pair_tile_kernel<PERIODIC, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (first_use_on_device(configured)) {
     EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured = true;
   }
   const int cluster = pick_cluster(n_tiles, p.n_chunks);
   cudaLaunchConfig_t cfg{};

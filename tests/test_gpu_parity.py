@@ -544,3 +544,70 @@ def test_no_cpu_fallback(em):
         sigmoid_loss()(torch.zeros(4, 3), torch.zeros(4, 2))
     with pytest.raises(em.EmkError):
         back_map(torch.zeros(2, 5), torch.zeros(2, 4), torch.zeros(2, 3))
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties (a CPU oracle of these sizes is impossible:
+# the reference needs 17.6 TB for config 3 and O(n^2) per frame for config 4)
+# ---------------------------------------------------------------------------------------------------
+def test_config3_full_size_properties(em):
+    """65 536 x 1 024 periodic full-set cost: the 8-way tile split sums to the full result, the gradient is
+    translation invariant, a sampled row block agrees with the float64 oracle."""
+    from encodermap_b200 import _lib, _ops
+
+    n, d = 65536, 1024
+    gen = torch.Generator(device="cuda").manual_seed(4321)
+    centres = (torch.rand(16, d, device="cuda", generator=gen) * 2 - 1) * pi
+    h = centres[torch.randint(0, 16, (n,), device="cuda", generator=gen)] + 0.05 * torch.randn(n, d, device="cuda", generator=gen)
+    h = (torch.remainder(h + pi, 2 * pi) - pi).contiguous()
+    z = (3 * torch.randn(n, 2, device="cuda", generator=gen)).contiguous()
+    full_l, full_g = _ops.sigmoid_cost_raw(h, z, 2 * pi, DEFAULT_SIG)
+    tl = torch.zeros(1, dtype=torch.float64, device="cuda")
+    tg = torch.zeros_like(z)
+    for r in range(8):
+        l_, g_ = _ops.sigmoid_cost_raw(h, z, 2 * pi, DEFAULT_SIG, _lib.pair_tile_range(n, r, 8))
+        tl += l_
+        tg += g_
+    np.testing.assert_allclose(tl.item(), full_l.item(), rtol=1e-11)
+    assert relnorm(tg.cpu().numpy(), full_g.cpu().numpy()) < 1e-5
+    assert 0.0 < full_l.item() < 1.0 and torch.isfinite(full_g).all()
+    assert abs(full_g.double().sum(0)).max().item() < 1e-5 * abs(full_g.double()).sum().item()
+    # exactness on a sample: rows 0, 256, 512, ... form a 256-row problem the oracle can do
+    sub = torch.arange(0, n, 256, device="cuda")
+    ls, gs = _ops.sigmoid_cost_raw(h[sub].contiguous(), z[sub].contiguous(), 2 * pi, DEFAULT_SIG)
+    lref, gref = O.sigmoid_loss_and_grad(h[sub].cpu().numpy(), z[sub].cpu().numpy(), 2 * pi, DEFAULT_SIG)
+    np.testing.assert_allclose(ls.item(), lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(gs.cpu().numpy(), gref.numpy()) < GRAD_RTOL
+
+
+def test_config4_full_size_invariants(em):
+    """One 65 536-frame chunk of the 500-residue back-mapping: the output realises the requested bond lengths,
+    angles and dihedrals (the invariant behind reference tests/test_losses.py:663-703); a few frames agree with
+    the float64 oracle."""
+    from encodermap_b200.models.layers import back_map, mean_lengths
+
+    n, b = 1500, 65536
+    gen = torch.Generator(device="cuda").manual_seed(555)
+    dist = 0.13 + 0.02 * torch.rand(b, n - 1, device="cuda", generator=gen)
+    ang = 1.9 + 0.3 * torch.rand(b, n - 2, device="cuda", generator=gen)
+    dih = (torch.rand(b, n - 3, device="cuda", generator=gen) * 2 - 1) * pi
+    xyz = back_map(dist, ang, dih)
+    assert torch.isfinite(xyz).all()
+    lengths = mean_lengths(dist)[0].double()
+    for lo in range(0, b, 8192):   # float64 invariants in slabs to bound memory
+        x = xyz[lo:lo + 8192].double()
+        bonds = x[:, 1:] - x[:, :-1]
+        bl = torch.linalg.norm(bonds, dim=-1)
+        assert (bl - lengths).abs().max().item() < 2e-5
+        cosang = -(bonds[:, 1:] * bonds[:, :-1]).sum(-1) / (bl[:, 1:] * bl[:, :-1])
+        assert (torch.acos(cosang.clamp(-1, 1)) - ang[lo:lo + 8192].double()).abs().max().item() < 2e-4
+        got = O.dihedral_of(x[:, :-3], x[:, 1:-2], x[:, 2:-1], x[:, 3:])
+        diff = torch.remainder(got - dih[lo:lo + 8192].double() + pi, 2 * pi) - pi
+        assert diff.abs().max().item() < 5e-4
+    pick = [0, 1, 40000, b - 1]
+    want = O.back_map_layer(dist.cpu().double(), ang[pick].cpu().double(), dih[pick].cpu().double())
+    # the layer's bond lengths are the mean over the WHOLE batch: feed the oracle the same means
+    want = O.dihedrals_to_cartesian_layers(dih[pick].cpu().double() + pi,
+                                           O.chain_in_plane(dist.cpu().double().mean(0)[None], ang[pick].cpu().double()),
+                                           *O.split_counts(n))
+    assert (xyz[pick].cpu().double() - want).abs().max().item() < COORD_ATOL
