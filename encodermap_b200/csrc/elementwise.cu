@@ -153,6 +153,7 @@ __device__ __forceinline__ void triu_decode(int64_t p, int64_t n, int64_t* i_out
 }
 
 // grid: (ceil(per / 256), b): one frame per blockIdx.y, coalesced output writes, inputs from L1
+// (general fallback: non-flat output, wide d, very long chains)
 __global__ void pairwise_small_kernel(const float* __restrict__ x, int64_t b, int64_t n, int64_t d, int64_t bstride,
                                       int64_t rstride, int squared, int flat, float* __restrict__ out) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
@@ -171,6 +172,101 @@ __global__ void pairwise_small_kernel(const float* __restrict__ x, int64_t b, in
         s = fmaf(t, t, s);
       }
       ob[p] = squared ? s : sqrtf(s);
+    }
+  }
+}
+
+// PairwiseDistances layer, forward: flat upper triangle of 3-d points.  One CTA per frame: the selected atoms are
+// staged in shared memory (SoA), each warp walks whole rows of the triangle, lanes over j, so that the output
+// writes are contiguous runs and no per-element index decode is needed.
+constexpr int PW_THREADS = 128;
+__global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                    int64_t rstride, int squared, float* __restrict__ out) {
+  extern __shared__ float sx[];   // [3][n]
+  const int64_t per = (int64_t)n * (n - 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
+    const float* xb = x + bi * bstride;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 3 * n; idx += PW_THREADS) {
+      const int a = idx / 3, c = idx - 3 * a;
+      sx[c * n + a] = xb[a * rstride + c];
+    }
+    __syncthreads();
+    float* ob = out + bi * per;
+    // rows are dealt to the warps in (i, n-2-i) pairs so that every warp gets the same number of elements
+    for (int r = warp; r < (n - 1 + 1) / 2; r += PW_THREADS / 32) {
+      for (int half = 0; half < 2; half++) {
+        const int i = half == 0 ? r : n - 2 - r;
+        if (half == 1 && i == r) break;
+        const float xi = sx[i], yi = sx[n + i], zi = sx[2 * n + i];
+        float* orow = ob + (int64_t)i * (2 * n - i - 1) / 2 - i - 1;   // + j
+        // two columns per lane and iteration; sqrt as s2 * rsqrt(s2) (MUFU + FMUL, 2 ulp) with the zero guarded
+        int j = i + 1 + lane;
+        for (; j + 32 < n; j += 64) {
+          const float dx0 = xi - sx[j], dy0 = yi - sx[n + j], dz0 = zi - sx[2 * n + j];
+          const float dx1 = xi - sx[j + 32], dy1 = yi - sx[n + j + 32], dz1 = zi - sx[2 * n + j + 32];
+          const float a0 = fmaf(dx0, dx0, fmaf(dy0, dy0, dz0 * dz0));
+          const float a1 = fmaf(dx1, dx1, fmaf(dy1, dy1, dz1 * dz1));
+          orow[j] = squared ? a0 : (a0 > 0.f ? a0 * rsqrtf(a0) : 0.f);
+          orow[j + 32] = squared ? a1 : (a1 > 0.f ? a1 * rsqrtf(a1) : 0.f);
+        }
+        if (j < n) {
+          const float dx = xi - sx[j], dy = yi - sx[n + j], dz = zi - sx[2 * n + j];
+          const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+          orow[j] = squared ? s2 : (s2 > 0.f ? s2 * rsqrtf(s2) : 0.f);
+        }
+      }
+    }
+  }
+}
+
+// PairwiseDistances layer, backward: one CTA per frame, one thread per atom i looping over j; positions (and the
+// upstream gradient when it fits) are staged in shared memory, so the inner loop is ~20 instructions with no
+// global traffic.  grad_x[i] = sum_j coef_ij (x_i - x_j), coef = g/dist (2g when squared), 0 at zero distance.
+template <bool G_IN_SMEM>
+__global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                        int64_t rstride, int squared, const float* __restrict__ go,
+                                                                        float* __restrict__ gx) {
+  extern __shared__ float sm[];   // [3][n] positions, then (optionally) the frame's upstream gradient
+  float* sx = sm;
+  float* sg = sm + ((3 * n + 3) & ~3);
+  const int64_t per = (int64_t)n * (n - 1) / 2;
+  for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
+    const float* xb = x + bi * bstride;
+    const float* g = go + bi * per;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 3 * n; idx += PW_THREADS) {
+      const int a = idx / 3, c = idx - 3 * a;
+      sx[c * n + a] = xb[a * rstride + c];
+    }
+    if (G_IN_SMEM)
+      for (int64_t idx = threadIdx.x; idx < per; idx += PW_THREADS) sg[idx] = g[idx];
+    __syncthreads();
+    const float* gg = G_IN_SMEM ? sg : g;
+    for (int i = threadIdx.x; i < n; i += PW_THREADS) {
+      const float xi = sx[i], yi = sx[n + i], zi = sx[2 * n + i];
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      // pair (j,i), j < i, sits at j(2n-j-1)/2 + (i-j-1): starts at i-1 and advances by n-j-2 per j
+      int off = i - 1;
+      for (int j = 0; j < i; j++) {
+        const float dx = xi - sx[j], dy = yi - sx[n + j], dz = zi - sx[2 * n + j];
+        const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float gij = gg[off];
+        off += n - j - 2;
+        const float coef = squared ? 2.f * gij : (s2 > 0.f ? gij * rsqrtf(s2) : 0.f);
+        ax = fmaf(coef, dx, ax); ay = fmaf(coef, dy, ay); az = fmaf(coef, dz, az);
+      }
+      const float* grow = gg + (int64_t)i * (2 * n - i - 1) / 2 - i - 1;   // + j for j > i
+      for (int j = i + 1; j < n; j++) {
+        const float dx = xi - sx[j], dy = yi - sx[n + j], dz = zi - sx[2 * n + j];
+        const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float gij = grow[j];
+        const float coef = squared ? 2.f * gij : (s2 > 0.f ? gij * rsqrtf(s2) : 0.f);
+        ax = fmaf(coef, dx, ax); ay = fmaf(coef, dy, ay); az = fmaf(coef, dz, az);
+      }
+      float* o = gx + bi * bstride + (int64_t)i * rstride;
+      o[0] = ax; o[1] = ay; o[2] = az;
     }
   }
 }
@@ -306,6 +402,12 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
                           int flat, float* out, cudaStream_t st) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
   if (b * per == 0) return EMK_OK;
+  if (flat && d == 3 && n >= 2 && n <= 8192) {
+    const size_t smem = 3 * (size_t)n * sizeof(float);
+    const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);
+    pairwise_flat3_kernel<<<grid, PW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, out);
+    return launch_status("pairwise_flat3_kernel");
+  }
   const int64_t bx = std::min<int64_t>((per + 255) / 256, 1024);
   dim3 grid((unsigned)bx, (unsigned)std::min<int64_t>(b, 65535));
   pairwise_small_kernel<<<grid, 256, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, out);
@@ -314,6 +416,23 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
 int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
                               int flat, const float* go, float* gx, cudaStream_t st) {
   if (b * n == 0) return EMK_OK;
+  if (flat && d == 3 && n >= 2 && n <= 8192) {
+    const size_t sx = ((3 * (size_t)n + 3) & ~(size_t)3) * sizeof(float);
+    const size_t sg = (size_t)n * (n - 1) / 2 * sizeof(float);
+    const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);
+    if (sx + sg <= 96 * 1024) {
+      static bool cfg[kMaxDevices] = {false};
+      if (first_use_on_device(cfg))
+        EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      pairwise_flat3_bwd_kernel<true><<<grid, PW_THREADS, sx + sg, st>>>(x, b, (int)n, bstride, rstride, squared, go, gx);
+    } else {
+      static bool cfg[kMaxDevices] = {false};
+      if (first_use_on_device(cfg))
+        EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      pairwise_flat3_bwd_kernel<false><<<grid, PW_THREADS, sx, st>>>(x, b, (int)n, bstride, rstride, squared, go, gx);
+    }
+    return launch_status("pairwise_flat3_bwd_kernel");
+  }
   const int threads = n >= 128 ? 128 : (int)((n + 31) / 32 * 32);
   dim3 grid((unsigned)((n + threads - 1) / threads), (unsigned)std::min<int64_t>(b, 65535));
   pairwise_small_bwd_kernel<<<grid, threads, 0, st>>>(x, b, n, d, bstride, rstride, squared, flat, go, gx);
