@@ -88,6 +88,20 @@ __device__ __forceinline__ Se3 se3_shfl_up(const Se3& a, int delta, int width) {
   return o;
 }
 
+// same, but only rows 0 and 1 of the rotation travel: row 2 = row 0 x row 1 (9 FP64 operations instead of
+// 6 32-bit shuffles -- shuffles share the L1 data pipe with shared memory, which bounds the forward kernel)
+__device__ __forceinline__ Se3 se3_shfl_up_rot(const Se3& a, int delta) {
+  Se3 o;
+#pragma unroll
+  for (int i = 0; i < 6; i++) o.r[i] = __shfl_up_sync(0xffffffffu, a.r[i], delta);
+#pragma unroll
+  for (int i = 0; i < 3; i++) o.p[i] = __shfl_up_sync(0xffffffffu, a.p[i], delta);
+  o.r[6] = o.r[1] * o.r[5] - o.r[2] * o.r[4];
+  o.r[7] = o.r[2] * o.r[3] - o.r[0] * o.r[5];
+  o.r[8] = o.r[0] * o.r[4] - o.r[1] * o.r[3];
+  return o;
+}
+
 // exclusive scan over `width` consecutive lanes (width = 16 or 32): lane q gets T_0 o ... o T_{q-1}
 __device__ __forceinline__ Se3 se3_exclusive_scan(Se3 t, int lane_in_group, int width) {
   for (int d = 1; d < width; d <<= 1) {
@@ -452,6 +466,258 @@ __global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const floa
 }
 
 // ====================================================================================================
+// BackMapLayer forward, version 5: same mathematics as version 3, half the shared memory, ~2/3 of the
+// instructions per NeRF step and a shared-memory sin/cos table, so that 24 instead of 12 warps are resident
+// per SM (the kernel is bound by dependent FP64 latencies and by L1 data-pipe wavefronts, not by a math pipe).
+//   * persistent CTAs of 6 independent 64-thread groups (one warp per side of the chain); a group loops over
+//     frames and synchronises with its own named barrier, so a slow frame never holds up its neighbours.
+//   * ONE shared-memory region of 3n floats per group.  The inputs of atom k -- (dihedral, angle, length) of the
+//     step that places it -- are staged INTERLEAVED at T[3k .. 3k+2] (4-byte cp.async, stride-3 scatter, bank
+//     conflict free), pass 1 overwrites each triple with the chunk-local position of the atom it placed, pass 2
+//     transforms it in place, and the region leaves as one contiguous, vectorised row store.
+//     slot of dihedral j: j (left of the anchor, j < s-1) or j+3;  angle j: j (j < s) or j+2;  length j: j
+//     (j < s+1) or j+1 -- the middle angle theta_{s-1} and the two middle bond lengths land in the slots of
+//     the three anchor atoms, which the anchor lane reads before it writes their planar positions.
+//   * sin/cos: 256-entry float64 table in shared memory (v3 read a 1024-entry table through L1, which the
+//     shared-memory carve-out had shrunk to ~30 KB: 51 % hit rate, 30 sectors per warp-wide lookup).
+//   * per-lane trip counts (no dummy steps, no selects); arguments beyond the table path's range only raise a
+//     flag, and a flagged warp re-stages its side and repeats pass 1 with the float64 polynomial sin/cos
+//     (never taken by model outputs).
+// ====================================================================================================
+constexpr int FWD5_GROUPS = 6;
+constexpr int FWD5_THREADS = 64 * FWD5_GROUPS;
+constexpr int SC_SMALL = 256;                 // shared-memory table: step 2 pi / 256
+constexpr float SC_FAST_LIMIT = 48.f;
+
+__device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); }
+
+// table path without the range check (|x| < SC_FAST_LIMIT is the caller's business); tabS in shared memory
+__device__ __forceinline__ void sincos_tab256(float x, const double2* tabS, double* s, double* c) {
+  const float km = fmaf(x, 40.74366543152521f, 12582912.f);   // 256 / 2pi; low mantissa bits = rint(x * 256 / 2pi)
+  const float kf = km - 12582912.f;
+  // 2pi/256 = C1 + C2 + C3 with 8- and 11-bit C1, C2: the first two reductions are exact in float32
+  float r = fmaf(-kf, 0.0245361328125f, x);
+  r = fmaf(-kf, 7.558614015579224e-06f, r);
+  r = fmaf(-kf, 1.1796547072506768e-09f, r);
+  const float r2 = r * r;
+  const float sr = fmaf(r * r2, -0.16666667f, r);                  // sin r      (|r| <= pi/256: r^5/120 < 3e-12)
+  const float cm = r2 * fmaf(r2, 0.041666668f, -0.5f);             // cos r - 1
+  const double2 t = tabS[__float_as_int(km) & (SC_SMALL - 1)];
+  *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
+  *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
+}
+
+template <bool LEFT, bool SLOW>
+__device__ __forceinline__ void fwd5_step(float* pT, int& kpar, const double2* tabS, Se3& f, Se2& pl, float& amax) {
+  const float fd = pT[0], fa = pT[1], fl = pT[2];
+  double sw, cw, sg, cg;
+  if (SLOW) {
+    sincos_d((double)fd, &sw, &cw);
+    sincos_d((double)fa, &sg, &cg);
+  } else {
+    amax = fmaxf(amax, fmaxf(fabsf(fd), fabsf(fa)));
+    sincos_tab256(fd, tabS, &sw, &cw);
+    sincos_tab256(fa, tabS, &sg, &cg);
+  }
+  const double L = (double)fl;
+  nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
+  pT[0] = (float)f.p[0];
+  pT[1] = (float)f.p[1];
+  pT[2] = (float)f.p[2];
+  if (LEFT) {
+    // planar bond k: advance L along the current direction, then turn by -(-1)^k (pi - theta_k); this lane walks
+    // k downwards, so the step is prepended: pl <- step_k o pl
+    const double tc = -cg, ts = (kpar & 1) ? sg : -sg;
+    const double nc = tc * pl.c - ts * pl.s, ns = tc * pl.s + ts * pl.c;
+    const double nx = L + tc * pl.x - ts * pl.y, ny = ts * pl.x + tc * pl.y;
+    pl.c = nc; pl.s = ns; pl.x = nx; pl.y = ny;
+    kpar--;
+  }
+}
+
+// pass 1 of one lane: `nvalid` steps walking the interleaved region from pT (LEFT: downwards).  Returns false if
+// an argument was outside the table path's range (NaN compares false and propagates through the table path).
+template <bool LEFT, bool SLOW>
+__device__ __forceinline__ bool fwd5_pass1(float* pT, int nvalid, int kpar, const double2* tabS, Se3& f, Se2& pl) {
+  constexpr int dk = LEFT ? -3 : 3;
+  float amax = 0.f;
+  int c = 0;
+#pragma unroll 1
+  for (; c + 1 < nvalid; c += 2) {
+    fwd5_step<LEFT, SLOW>(pT, kpar, tabS, f, pl, amax);
+    fwd5_step<LEFT, SLOW>(pT + dk, kpar, tabS, f, pl, amax);
+    pT += 2 * dk;
+  }
+  if (c < nvalid) fwd5_step<LEFT, SLOW>(pT, kpar, tabS, f, pl, amax);
+  return amax < SC_FAST_LIMIT;
+}
+
+// interleaving stage of row elements [j0, j1) of `src` into T[3 (j + shift) + COMP] by the 64 threads of a group:
+// thread t copies j = j0 + t + 64 i.  Uniform trip count, 4 predicated copies with immediate offsets per iteration
+// (about 3 instructions per element; the plain strided loop needed 7).
+__device__ __forceinline__ void cp_async4_s(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int COMP>
+__device__ __forceinline__ void stage_interleaved(uint32_t sT, const float* __restrict__ src, int j0, int j1, int shift, int t) {
+  uint32_t d = sT + 4u * (uint32_t)(3 * (j0 + t + shift) + COMP);
+  const float* s = src + j0 + t;
+  int left = j1 - j0 - t;                  // copy i of this thread is in range iff 64 i < left
+  const int iters = (j1 - j0 + 63) >> 6;   // uniform over the group
+  int i = 0;
+#pragma unroll 1
+  for (; i + 4 <= iters; i += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (64 * u < left) cp_async4_s(d + 768u * u, s + 64 * u);
+    d += 4 * 768;
+    s += 256;
+    left -= 256;
+  }
+#pragma unroll
+  for (int u = 0; u < 3; u++)
+    if (i + u < iters && 64 * u < left) cp_async4_s(d + 768u * u, s + 64 * u);
+}
+
+__global__ void __launch_bounds__(FWD5_THREADS, 2) backmap_fwd5_kernel(const float* __restrict__ lengths, int64_t lstride,
+                                                                       const float* __restrict__ angles,
+                                                                       const float* __restrict__ dihedrals, int64_t b, int n,
+                                                                       float* __restrict__ xyz, const double2* __restrict__ tab) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double anchor[FWD5_GROUPS][2][12];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid >> 6, t = tid & 63, side = (tid >> 5) & 1;
+  double2* tabS = reinterpret_cast<double2*>(smem);
+  for (int i = tid; i < SC_SMALL; i += FWD5_THREADS) tabS[i] = __ldg(tab + i * (SC_TABLE / SC_SMALL));
+  __syncthreads();
+
+  const int out_floats = 3 * n;
+  const int rO = (out_floats + 7) & ~3;
+  float* region = smem + SC_SMALL * 4 + (size_t)g * rO;
+  const int s = n / 2;
+  const int steps = side == 0 ? (s - 1) : (n - s - 2);
+  const int ch = ((max(s - 1, n - s - 2) + 31) / 32) | 1;   // odd chunk length: conflict-free strided smem access
+  const int i0 = lane * ch;
+  const int nvalid = max(0, min(ch, steps - i0));
+  const int kfirst = side == 0 ? s - 2 - i0 : s + 2 + i0;
+
+  for (int64_t frame = (int64_t)blockIdx.x * FWD5_GROUPS + g; frame < b; frame += (int64_t)gridDim.x * FWD5_GROUPS) {
+    float* dst = xyz + frame * (int64_t)out_floats;
+    // congruent with the global row modulo 16 bytes, so that the final copy is float4 on both sides
+    float* T = region + (int)((reinterpret_cast<uintptr_t>(dst) & 15) >> 2);
+    const float* rowD = dihedrals + frame * (int64_t)(n - 3);
+    const float* rowA = angles + frame * (int64_t)(n - 2);
+    const float* rowL = lengths + frame * lstride;
+    const uint32_t sT = (uint32_t)__cvta_generic_to_shared(T);
+    stage_interleaved<0>(sT, rowD, 0, s - 1, 0, t);
+    stage_interleaved<0>(sT, rowD, s - 1, n - 3, 3, t);
+    stage_interleaved<1>(sT, rowA, 0, s, 0, t);
+    stage_interleaved<1>(sT, rowA, s, n - 2, 2, t);
+    stage_interleaved<2>(sT, rowL, 0, s + 1, 0, t);
+    stage_interleaved<2>(sT, rowL, s + 1, n - 1, 1, t);
+    cp_async_wait_all();
+    group_barrier(g);
+
+    float* pT = T + 3 * kfirst;
+    Se3 f;
+    se3_identity(f);
+    Se2 pl{1.0, 0.0, 0.0, 0.0};
+    bool fast_ok;
+    if (side == 0) fast_ok = fwd5_pass1<true, false>(pT, nvalid, kfirst, tabS, f, pl);
+    else fast_ok = fwd5_pass1<false, false>(pT, nvalid, kfirst, tabS, f, pl);
+    if (!__all_sync(0xffffffffu, fast_ok)) {
+      // out-of-range argument somewhere on this side: restore the side's inputs and repeat with float64 sin/cos
+      if (side == 0) {
+        for (int j = lane; j < s - 1; j += 32) { T[3 * j] = rowD[j]; T[3 * j + 1] = rowA[j]; T[3 * j + 2] = rowL[j]; }
+      } else {
+        for (int k = s + 2 + lane; k < n; k += 32) { T[3 * k] = rowD[k - 3]; T[3 * k + 1] = rowA[k - 2]; T[3 * k + 2] = rowL[k - 1]; }
+      }
+      __syncwarp();
+      se3_identity(f);
+      pl = Se2{1.0, 0.0, 0.0, 0.0};
+      if (side == 0) fwd5_pass1<true, true>(pT, nvalid, kfirst, tabS, f, pl);
+      else fwd5_pass1<false, true>(pT, nvalid, kfirst, tabS, f, pl);
+    }
+
+    // ---- scan of the chunk aggregates inside the warp ---------------------------------------------------
+    Se3 inc = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Se3 up = se3_shfl_up_rot(inc, d);
+      if (lane >= d) inc = se3_mul(up, inc);
+    }
+    Se3 ex = se3_shfl_up_rot(inc, 1);
+    if (lane == 0) se3_identity(ex);
+
+    // ---- anchor: the left warp reduces the planar product (higher lanes hold lower bonds => go on the left)
+    if (side == 0) {
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        Se2 o = se2_shfl_down(pl, d);
+        if (lane + d < 32) pl = se2_mul(o, pl);
+      }
+      if (lane == 0) {
+        // pl: direction of bond s-1 and position of atom s-1 in the plane
+        const double dm_c = pl.c, dm_s = pl.s, am_x = pl.x, am_y = pl.y;
+        const float th_mid = T[3 * (s - 1) + 1], l_m = T[3 * (s - 1) + 2], l_p = T[3 * s + 2];
+        Se2 mid = pl;
+        planar_step(mid, (double)l_m, true, th_mid, s - 1);
+        const double a0_x = mid.x, a0_y = mid.y, dp_c = mid.c, dp_s = mid.s;
+        const double ap_x = fma((double)l_p, dp_c, a0_x), ap_y = fma((double)l_p, dp_s, a0_y);
+        const double zs = (dm_c * dp_s - dm_s * dp_c) >= 0.0 ? 1.0 : -1.0;
+        T[3 * (s - 1)] = (float)am_x; T[3 * (s - 1) + 1] = (float)am_y; T[3 * (s - 1) + 2] = 0.f;
+        T[3 * s] = (float)a0_x;       T[3 * s + 1] = (float)a0_y;       T[3 * s + 2] = 0.f;
+        T[3 * (s + 1)] = (float)ap_x; T[3 * (s + 1) + 1] = (float)ap_y; T[3 * (s + 1) + 2] = 0.f;
+        // anchor frames: x along the last anchored bond, z = +-e_z, y = z x x, origin at the last anchor atom
+#pragma unroll
+        for (int sd = 0; sd < 2; sd++) {
+          const double xx = sd == 0 ? -dm_c : dp_c, xy = sd == 0 ? -dm_s : dp_s, zz = sd == 0 ? -zs : zs;
+          double* a = anchor[g][sd];
+          a[0] = xx; a[1] = -zz * xy; a[2] = 0.0;
+          a[3] = xy; a[4] = zz * xx;  a[5] = 0.0;
+          a[6] = 0.0; a[7] = 0.0;     a[8] = zz;
+          a[9] = sd == 0 ? am_x : ap_x; a[10] = sd == 0 ? am_y : ap_y; a[11] = 0.0;
+        }
+      }
+    }
+    group_barrier(g);
+
+    // ---- pass 2: out = (anchor o prefix)(local), float32 rotation (chunk-local coordinates are < 4 nm), translation
+    //      as a float32 hi/lo pair so that the only full-magnitude rounding is the one of the float32 output
+    if (nvalid > 0) {
+      Se3 carry;
+#pragma unroll
+      for (int i = 0; i < 9; i++) carry.r[i] = anchor[g][side][i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) carry.p[i] = anchor[g][side][9 + i];
+      const Se3 pre = se3_mul(carry, ex);
+      float rf[9], ph[3], plo[3];
+#pragma unroll
+      for (int i = 0; i < 9; i++) rf[i] = (float)pre.r[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        ph[i] = (float)pre.p[i];
+        plo[i] = (float)(pre.p[i] - (double)ph[i]);
+      }
+      float* pO = pT;
+      const int dk = side == 0 ? -3 : 3;
+#pragma unroll 4
+      for (int c = 0; c < nvalid; c++) {
+        const float lx = pO[0], ly = pO[1], lz = pO[2];
+        pO[0] = ph[0] + fmaf(rf[0], lx, fmaf(rf[1], ly, fmaf(rf[2], lz, plo[0])));
+        pO[1] = ph[1] + fmaf(rf[3], lx, fmaf(rf[4], ly, fmaf(rf[5], lz, plo[1])));
+        pO[2] = ph[2] + fmaf(rf[6], lx, fmaf(rf[7], ly, fmaf(rf[8], lz, plo[2])));
+        pO += dk;
+      }
+    }
+    group_barrier(g);
+    store_row(dst, T, out_floats, t, 64);
+    group_barrier(g);   // the next frame's staging overwrites T
+  }
+}
+
+// ====================================================================================================
 // dihedrals_to_cartesian on an arbitrary start chain (two-sided or one-way)
 // ====================================================================================================
 __device__ __forceinline__ void load3(const float* p, double* v) {
@@ -788,6 +1054,310 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd2_kernel(const
 }
 
 // ====================================================================================================
+// backward, version 3: float32 wrench recurrences about a MOVING pivot.
+//
+// Every internal coordinate moves one end of the chain rigidly (the end that does not hold the anchor), so its
+// gradient is <axis, torque about the pivot> or <direction, force> of the wrench of that end.  Version 2 summed
+// (g, x cross g) about the ORIGIN in float64 and subtracted pivot cross force afterwards (a cancellation of two
+// ~80 nm lever arms that float32 cannot carry).  Here both ends are walked from the chain end towards the anchor
+// and the torque is kept about the atom the walk has reached:
+//     S_i = S_{i-1} + g(a_i),      M_i = M_{i-1} - (x(a_{i+1}) - x(a_i)) x S_i        (M_i is about x(a_{i+1}))
+// with a_i = i on the left of the anchor and a_i = n-1-i on the right.  Lever arms are single bonds, nothing
+// cancels, float32 is enough (errors random-walk to ~2e-6 relative over 750 steps, the tolerance is 1e-5), and
+// the formulas of the two ends are mirror images: with e1 = x(a_{i+1}) - x(a_i), e2 = x(a_{i+2}) - x(a_{i+1})
+//     dihedral term = -<unit(e2), M_i>,   angle term = <unit(e1 x e2), M_i>,   length term = -<unit(e1), S_i>
+// on both sides (tools/proto_backmap.py derives them; tests compare with float64 autograd of the reference order).
+// Chunks of consecutive walk steps per thread; chunk aggregates are combined by a scan whose operator shifts the
+// pivot:  (S_A, M_A about p_A) then (S_C, M_C about p_C)  ->  (S_A + S_C, M_C + M_A - (p_C - p_A) x S_A).
+// Left of the anchor an angle / length also moves the anchor itself along the planar chain, i.e. the whole
+// molecule: + (-1)^k <e_z, total torque about planar atom k+1>  and  + <planar bond direction, total force>; the
+// planar chain is an SE(2) scan in float64 (left threads only).
+// The term of the cut behind atom a_i overwrites g(a_i) in place; the three output rows are gathered from there.
+// ====================================================================================================
+struct WrenchF {
+  float s[3];
+  float m[3];
+};
+
+// A then C (C further along the walk): pivot moves from pa to pc
+__device__ __forceinline__ void wrench_append(WrenchF& c, const WrenchF& a, const float* pa, const float* pc) {
+  const float d0 = pc[0] - pa[0], d1 = pc[1] - pa[1], d2 = pc[2] - pa[2];
+  c.m[0] += a.m[0] - (d1 * a.s[2] - d2 * a.s[1]);
+  c.m[1] += a.m[1] - (d2 * a.s[0] - d0 * a.s[2]);
+  c.m[2] += a.m[2] - (d0 * a.s[1] - d1 * a.s[0]);
+  c.s[0] += a.s[0];
+  c.s[1] += a.s[1];
+  c.s[2] += a.s[2];
+}
+
+template <int T>
+__global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const BwdParams p, const double2* __restrict__ tab) {
+  constexpr int CTA = T < 128 ? 128 : T;
+  constexpr int FPC = CTA / T;
+  constexpr int WPF = T / 32;
+  static_assert(T >= 32 && T % 32 == 0, "whole warps per frame");
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float wagg[FPC][WPF][9];      // per-warp inclusive aggregate: S, M, end pivot
+  __shared__ float side_tot[FPC][2][6];    // per-side total wrench about x_{dr0}
+  __shared__ double psum[FPC][WPF][4];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid / T, t = tid % T, wf = t >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * FPC + g;
+  const bool active = frame < p.b;
+  const int64_t fr = active ? frame : 0;
+  const int n = p.n;
+  const bool extras = !p.planar && (p.grad_angles || p.grad_lengths) && p.mid > 1;   // left-of-anchor planar terms
+  const bool need_planar = p.planar || extras;
+
+  const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3;
+  float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0));
+  float* sX = base;
+  float* sG = base + rX;
+  float* sL = sG + rG;
+  float* sA = sL + rL;
+  if (active) {
+    sG = stage_row_async(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
+    if (!p.planar) sX = stage_row_async(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
+    if (need_planar) {
+      sL = stage_row_async(sL, p.lengths + fr * p.lstride, n - 1, t, T);
+      sA = stage_row_async(sA, p.angles + fr * (int64_t)(n - 2), n - 2, t, T);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- sides and chunks ------------------------------------------------------------------------------------
+  // left: cuts 0 .. dr0-1 (walk i = cut), right: cuts n-2 .. dr0 (walk i = n-2-cut); the walk visits a_0 .. a_{steps}
+  const int TL = p.dr0 > 0 ? T / 2 : 0;
+  const int side = t >= TL ? 1 : 0;
+  const int q = side ? t - TL : t;                    // thread index within the side
+  const int TS = side ? T - TL : TL;
+  const int W = TS < 32 ? TS : 32;                    // shuffle segment (16 only for T = 32 with two sides)
+  const int qs = q & (W - 1);                         // lane within the segment
+  const int steps = side ? n - 1 - p.dr0 : p.dr0;
+  const int C = (steps + TS - 1) / TS;
+  const int i0 = min(steps, q * C), i1 = min(steps, i0 + C);
+  const int st = side ? -3 : 3;
+  const int a0 = side ? n - 1 - i0 : i0;              // atom of walk index i0
+
+  // ---- planar chain ------------------------------------------------------------------------------------------
+  Se2 pl_ex{1.0, 0.0, 0.0, 0.0};   // left threads with extras: planar state before bond i0
+  if (p.planar) {
+    // chain_in_plane backward: recompute the planar coordinates into sX (ascending chunks of BWD_CA atoms)
+    const int k0 = min(n, t * BWD_CA), k1 = min(n, k0 + BWD_CA);
+    Se2 part{1.0, 0.0, 0.0, 0.0};
+    if (active)
+      for (int k = k0; k < k1 && k < n - 1; k++) planar_step(part, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+    Se2 inc = part;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Se2 up = se2_shfl_up(inc, d);
+      if (lane >= d) inc = se2_mul(up, inc);
+    }
+    Se2 ex = se2_shfl_up(inc, 1);
+    if (lane == 0) ex = Se2{1.0, 0.0, 0.0, 0.0};
+    if (lane == 31) { psum[g][wf][0] = inc.c; psum[g][wf][1] = inc.s; psum[g][wf][2] = inc.x; psum[g][wf][3] = inc.y; }
+    __syncthreads();
+    Se2 run{1.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < wf; w++) run = se2_mul(run, Se2{psum[g][w][0], psum[g][w][1], psum[g][w][2], psum[g][w][3]});
+    run = se2_mul(run, ex);
+    if (active) {
+      if (t == 0) { sX[0] = 0.f; sX[1] = 0.f; sX[2] = 0.f; }
+      for (int k = k0; k < k1 && k < n - 1; k++) {
+        planar_step(run, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+        sX[3 * (k + 1)] = (float)run.x; sX[3 * (k + 1) + 1] = (float)run.y; sX[3 * (k + 1) + 2] = 0.f;
+      }
+    }
+    __syncthreads();
+  } else if (extras) {
+    // planar SE(2) product of this left thread's bonds, exclusive prefix over the left threads (they are the low ones)
+    Se2 part{1.0, 0.0, 0.0, 0.0};
+    if (active && side == 0)
+      for (int k = i0; k < i1; k++) {
+        part.x = fma((double)sL[k], part.c, part.x);
+        part.y = fma((double)sL[k], part.s, part.y);
+        double sn, cs;
+        sincos_tab(sA[k], tab, &sn, &cs);   // k <= dr0 - 1 = n/2 - 2 < n - 2: every left bond is followed by a turn
+        const double cw = -cs, sw = (k & 1) ? sn : -sn;
+        const double c2 = part.c * cw - part.s * sw, s2 = part.c * sw + part.s * cw;
+        part.c = c2; part.s = s2;
+      }
+    Se2 inc = part;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Se2 up = se2_shfl_up(inc, d);
+      if (lane >= d) inc = se2_mul(up, inc);
+    }
+    Se2 ex = se2_shfl_up(inc, 1);
+    if (lane == 0) ex = Se2{1.0, 0.0, 0.0, 0.0};
+    if (lane == 31) { psum[g][wf][0] = inc.c; psum[g][wf][1] = inc.s; psum[g][wf][2] = inc.x; psum[g][wf][3] = inc.y; }
+    __syncthreads();
+    Se2 prev{1.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < wf; w++) prev = se2_mul(prev, Se2{psum[g][w][0], psum[g][w][1], psum[g][w][2], psum[g][w][3]});
+    pl_ex = se2_mul(prev, ex);
+  }
+
+  // ---- pass 1: wrench of this thread's chunk about x(a_{i1}) ------------------------------------------------------
+  WrenchF w{{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float xs[3], xe[3];   // pivots before / after the chunk: x(a_{i0}), x(a_{i1})
+  {
+    const float* px = sX + 3 * a0;
+    const float* pg = sG + 3 * a0;
+    xs[0] = px[0]; xs[1] = px[1]; xs[2] = px[2];
+    float xc0 = xs[0], xc1 = xs[1], xc2 = xs[2];
+    if (active)
+      for (int i = i0; i < i1; i++) {
+        const float xn0 = px[st], xn1 = px[st + 1], xn2 = px[st + 2];
+        w.s[0] += pg[0]; w.s[1] += pg[1]; w.s[2] += pg[2];
+        const float e0 = xn0 - xc0, e1 = xn1 - xc1, e2 = xn2 - xc2;
+        w.m[0] = fmaf(-e1, w.s[2], fmaf(e2, w.s[1], w.m[0]));
+        w.m[1] = fmaf(-e2, w.s[0], fmaf(e0, w.s[2], w.m[1]));
+        w.m[2] = fmaf(-e0, w.s[1], fmaf(e1, w.s[0], w.m[2]));
+        xc0 = xn0; xc1 = xn1; xc2 = xn2;
+        px += st; pg += st;
+      }
+    xe[0] = xc0; xe[1] = xc1; xe[2] = xc2;
+  }
+
+  // ---- inclusive scan over the side's threads (segments of W lanes, then warps through shared memory) -------------
+  WrenchF inc = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    if (d < W) {
+      WrenchF up;
+      float pa[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        up.s[i] = __shfl_up_sync(0xffffffffu, inc.s[i], d);
+        up.m[i] = __shfl_up_sync(0xffffffffu, inc.m[i], d);
+        pa[i] = __shfl_up_sync(0xffffffffu, xe[i], d);
+      }
+      if (qs >= d) wrench_append(inc, up, pa, xe);
+    }
+  }
+  WrenchF ex;   // exclusive prefix inside the segment, about xs
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    ex.s[i] = __shfl_up_sync(0xffffffffu, inc.s[i], 1);
+    ex.m[i] = __shfl_up_sync(0xffffffffu, inc.m[i], 1);
+    if (qs == 0) { ex.s[i] = 0.f; ex.m[i] = 0.f; }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { wagg[g][wf][i] = inc.s[i]; wagg[g][wf][3 + i] = inc.m[i]; wagg[g][wf][6 + i] = xe[i]; }
+  }
+  __syncthreads();
+  if (WPF > 2 || (WPF == 2 && TL == 0)) {
+    // earlier warps of the same side (left warps are 0 .. TL/32-1, right warps follow)
+    const int wfirst = side ? TL / 32 : 0;
+    WrenchF acc{{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    float pacc[3] = {0.f, 0.f, 0.f};
+    for (int wq = wfirst; wq < wf; wq++) {
+      WrenchF c{{wagg[g][wq][0], wagg[g][wq][1], wagg[g][wq][2]}, {wagg[g][wq][3], wagg[g][wq][4], wagg[g][wq][5]}};
+      const float pc[3] = {wagg[g][wq][6], wagg[g][wq][7], wagg[g][wq][8]};
+      wrench_append(c, acc, pacc, pc);
+      acc = c;
+      pacc[0] = pc[0]; pacc[1] = pc[1]; pacc[2] = pc[2];
+    }
+    if (wf > wfirst) {
+      wrench_append(ex, acc, pacc, xs);
+      wrench_append(inc, acc, pacc, xe);
+    }
+  }
+  if (extras) {
+    if (q == TS - 1) {   // last thread of the side: total wrench of the side about x(a_steps) = x_{dr0}
+#pragma unroll
+      for (int i = 0; i < 3; i++) { side_tot[g][side][i] = inc.s[i]; side_tot[g][side][3 + i] = inc.m[i]; }
+    }
+    __syncthreads();
+  }
+
+  // ---- pass 2: walk the chunk again from the prefix, emit the three terms of every cut ---------------------------
+  const bool wantD = p.grad_dihedrals != nullptr, wantA = p.grad_angles != nullptr, wantL = p.grad_lengths != nullptr;
+  if (active && i0 < i1) {
+    float ft[3] = {0.f, 0.f, 0.f}, mt[3] = {0.f, 0.f, 0.f}, xr[3] = {0.f, 0.f, 0.f};
+    const bool lext = extras && side == 0;
+    if (lext) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xr[i] = sX[3 * p.dr0 + i];
+        ft[i] = side_tot[g][0][i] + side_tot[g][1][i] + sG[3 * p.dr0 + i];   // g of atom dr0 belongs to neither end
+        mt[i] = side_tot[g][0][3 + i] + side_tot[g][1][3 + i];
+      }
+    }
+    Se2 pl = pl_ex;
+    float s0 = ex.s[0], s1 = ex.s[1], s2 = ex.s[2], m0 = ex.m[0], m1 = ex.m[1], m2 = ex.m[2];
+    const float* px = sX + 3 * a0;
+    float* pg = sG + 3 * a0;
+    float xc0 = px[0], xc1 = px[1], xc2 = px[2];
+    float xn0 = px[st], xn1 = px[st + 1], xn2 = px[st + 2];
+    const int alast = side ? 0 : n - 1;   // clamp of a_{i+2} at the end of the chain (its terms are never gathered)
+#pragma unroll 1
+    for (int i = i0; i < i1; i++) {
+      const int a2 = side ? max(n - 3 - i, alast) : min(i + 2, alast);
+      const float xq0 = sX[3 * a2], xq1 = sX[3 * a2 + 1], xq2 = sX[3 * a2 + 2];
+      s0 += pg[0]; s1 += pg[1]; s2 += pg[2];
+      const float e10 = xn0 - xc0, e11 = xn1 - xc1, e12 = xn2 - xc2;
+      m0 = fmaf(-e11, s2, fmaf(e12, s1, m0));
+      m1 = fmaf(-e12, s0, fmaf(e10, s2, m1));
+      m2 = fmaf(-e10, s1, fmaf(e11, s0, m2));
+      const float e20 = xq0 - xn0, e21 = xq1 - xn1, e22 = xq2 - xn2;
+      float rD = 0.f, rA = 0.f, rL = 0.f;
+      if (wantD) rD = -(e20 * m0 + e21 * m1 + e22 * m2) * rsqrtf(fmaf(e20, e20, fmaf(e21, e21, e22 * e22)));
+      if (wantA) {
+        if (p.planar) {
+          const int k = n - 2 - i;                      // cut index (planar mode has only the right side)
+          rA = ((k - 1) & 1) ? -m2 : m2;                // hinge normal -(-1)^(k-1) e_z, term = -<normal, M>
+        } else {
+          const float c0 = e11 * e22 - e12 * e21, c1 = e12 * e20 - e10 * e22, c2 = e10 * e21 - e11 * e20;
+          rA = (c0 * m0 + c1 * m1 + c2 * m2) * rsqrtf(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)));
+        }
+      }
+      if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrtf(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
+      if (lext) {
+        // planar direction of bond k = i, planar position of atom k+1, then the turn at atom k+1
+        const double pd0 = pl.c, pd1 = pl.s;
+        pl.x = fma((double)sL[i], pl.c, pl.x);
+        pl.y = fma((double)sL[i], pl.s, pl.y);
+        double sn, cs;
+        sincos_tab(sA[i], tab, &sn, &cs);
+        const double cw = -cs, sw = (i & 1) ? sn : -sn;
+        const double c2 = pl.c * cw - pl.s * sw, s2d = pl.c * sw + pl.s * cw;
+        pl.c = c2; pl.s = s2d;
+        // z-torque of the whole molecule about planar atom k+1
+        const float dx = xr[0] - (float)pl.x, dy = xr[1] - (float)pl.y;
+        const float tz = mt[2] + (dx * ft[1] - dy * ft[0]);
+        rA += (i & 1) ? -tz : tz;
+        rL += (float)pd0 * ft[0] + (float)pd1 * ft[1];
+      }
+      pg[0] = rD; pg[1] = rA; pg[2] = rL;
+      xc0 = xn0; xc1 = xn1; xc2 = xn2;
+      xn0 = xq0; xn1 = xq1; xn2 = xq2;
+      pg += st;
+    }
+  }
+  __syncthreads();
+
+  // ---- gather: the term of cut k sits in slot k (left, k < dr0) or k+1 (right) ---------------------------------------
+  if (active) {
+    const int dr0 = p.dr0;
+    if (wantD) {
+      float* gD = p.grad_dihedrals + fr * (int64_t)(n - 3);
+      for (int d = t; d < n - 3; d += T) gD[d] = sG[3 * (d < dr0 ? d : d + 3)];            // left: cut d, right: cut d+2
+    }
+    if (wantA) {
+      float* gA = p.grad_angles + fr * (int64_t)(n - 2);
+      for (int j = t; j < n - 2; j += T) gA[j] = sG[3 * (j < dr0 ? j : j + 2) + 1];        // left: cut j, right: cut j+1
+    }
+    if (wantL) {
+      float* gL = p.grad_lengths + fr * (int64_t)(n - 1);
+      for (int k = t; k < n - 1; k += T) gL[k] = sG[3 * (k < dr0 ? k : k + 1) + 2];        // cut k
+    }
+  }
+}
+
+// ====================================================================================================
 // host launchers
 // ====================================================================================================
 static int pick_warps(size_t floats_per_warp, size_t shared_floats, int* warps, size_t* smem_bytes) {
@@ -839,15 +1409,17 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
   const double2* tab;
   int rc = get_sincos_table(&tab);
   if (rc) return rc;
-  constexpr int FPC = FWD_THREADS / 64;
-  const size_t per_frame = (((size_t)n - 1 + 7) & ~(size_t)3) + (((size_t)n - 2 + 7) & ~(size_t)3) + (((size_t)n - 3 + 7) & ~(size_t)3) + ((3 * (size_t)n + 7) & ~(size_t)3);
-  const size_t smem = (size_t)FPC * per_frame * sizeof(float);
-  EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "emk_backmap: chain of %lld atoms needs %zu bytes of staging shared memory", (long long)n, smem);
+  const size_t per_group = (3 * (size_t)n + 7) & ~(size_t)3;
+  const size_t smem = SC_SMALL * sizeof(double2) + (size_t)FWD5_GROUPS * per_group * sizeof(float);
+  EMK_REQUIRE(smem <= 224 * 1024, EMK_E_UNSUPPORTED, "emk_backmap: chain of %lld atoms needs %zu bytes of staging shared memory", (long long)n, smem);
   static bool cfg[kMaxDevices] = {false};
-  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(backmap_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  const int64_t blocks = (b + FPC - 1) / FPC;
-  backmap_fwd3_kernel<<<(unsigned)blocks, FWD_THREADS, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz, tab);
-  return launch_status("backmap_fwd3_kernel");
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(backmap_fwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  // persistent CTAs: as many as can be resident (2 per SM at 500 residues), each group strides over the frames
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 2048)));
+  const int64_t want = (b + FWD5_GROUPS - 1) / FWD5_GROUPS;
+  const int64_t blocks = std::min<int64_t>(want, (int64_t)sm_count() * per_sm);
+  backmap_fwd5_kernel<<<(unsigned)blocks, FWD5_THREADS, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz, tab);
+  return launch_status("backmap_fwd5_kernel");
 }
 
 int chain_in_plane_device(const float* lengths, int64_t lstride, const float* angles, int64_t b, int64_t n, float* xyz, cudaStream_t st) {
@@ -892,12 +1464,12 @@ static int launch_bwd2(const BwdParams& p, const double2* tab, bool need_planar,
                            (need_planar ? ((n - 1 + 7) & ~(size_t)3) + ((n - 2 + 7) & ~(size_t)3) : 0);
   const size_t smem = FPC * per_frame * sizeof(float);
   EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "back-mapping backward: chain of %d atoms needs %zu bytes of staging shared memory", p.n, smem);
-  auto kern = backmap_bwd2_kernel<T>;
+  auto kern = backmap_bwd3_kernel<T>;
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t blocks = (p.b + FPC - 1) / FPC;
   kern<<<(unsigned)blocks, CTA, smem, st>>>(p, tab);
-  return launch_status("backmap_bwd2_kernel");
+  return launch_status("backmap_bwd3_kernel");
 }
 
 int backmap_bwd_device(const BwdParams& p, cudaStream_t st) {
