@@ -342,28 +342,33 @@ def secondary_metrics(dev, peaks):
     out["backmap_fwd"] = {"frames_per_s": fps, "frames": BACKMAP_FRAMES, "n_atoms": n, "ms": ms,
                           "roofline": {"bound": "hbm", "achieved": fps * bytes_per_frame / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": fps * bytes_per_frame / 1e9 / peaks["hbm_gbs"], "bytes_per_frame": bytes_per_frame,
-                                       "note": "float64 SE(3) scan: FP64-pipe-bound below the HBM roofline (DESIGN.md)"}}
-    # fwd + bwd on one chunk
+                                       "note": "float64 SE(3) scan: bound by FP64 latency and L1 data-pipe wavefronts below the HBM roofline (DESIGN.md)"}}
+    # fwd + bwd on one chunk: dihedral gradients only (the ADC default, use_backbone_angles=False:
+    # reference parameters.py:803) and with bond-angle gradients as well
     chunk = 1 << 15
     g = torch.Generator(device=dev).manual_seed(556)
     lengths = (0.13 + 0.02 * torch.rand(1, n - 1, device=dev, generator=g)).contiguous()
-    ang = (1.9 + 0.3 * torch.rand(chunk, n - 2, device=dev, generator=g)).requires_grad_(True)
-    dih = ((torch.rand(chunk, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).requires_grad_(True)
     w = torch.randn(chunk, n, 3, device=dev, generator=g)
-    n_warm, n_timed = 3, 5
-    for it in range(n_warm + n_timed):
-        if it == n_warm:
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        xyz = _ops.BackMap.apply(lengths, ang, dih)
-        xyz.backward(w)
-        ang.grad = dih.grad = None
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n_timed
-    out["backmap_fwd_bwd"] = {"frames_per_s": chunk / (ms * 1e-3), "frames": chunk, "ms": ms,
-                              "bytes_per_frame": bytes_per_frame + 41960}
+    for key, with_angles in (("backmap_fwd_bwd", False), ("backmap_fwd_bwd_angles", True)):
+        ang = (1.9 + 0.3 * torch.rand(chunk, n - 2, device=dev, generator=g)).requires_grad_(with_angles)
+        dih = ((torch.rand(chunk, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).requires_grad_(True)
+        n_warm, n_timed = 3, 5
+        for it in range(n_warm + n_timed):
+            if it == n_warm:
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            xyz = _ops.BackMap.apply(lengths, ang, dih)
+            xyz.backward(w)
+            ang.grad = dih.grad = None
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_timed
+        # forward bytes + backward: xyz and grad_xyz in, grad_dihedrals out (+ lengths, angles in and grad_angles out)
+        bpf = bytes_per_frame + 24 * n + 4 * (n - 3) + (4 * (n - 1) + 8 * (n - 2) if with_angles else 0)
+        out[key] = {"frames_per_s": chunk / (ms * 1e-3), "frames": chunk, "ms": ms, "bytes_per_frame": bpf,
+                    "frac_hbm": chunk / (ms * 1e-3) * bpf / 1e9 / peaks["hbm_gbs"],
+                    "gradients": "dihedrals + angles" if with_angles else "dihedrals (ADC default)"}
     # configs[1]: per-batch cost, 4096 x 1024
     x, z = synth_high(4096, 1024, dev, 1234)
     for it in range(6):

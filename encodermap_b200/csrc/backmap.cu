@@ -1,12 +1,11 @@
 // Back-mapping kernels for sm_100a: internal coordinates -> Cartesian as an SE(3) prefix product
-// along the atom chain, and the exact VJP from prefix sums of force and torque.
+// along the atom chain, and the exact VJP from wrench (force / torque) recurrences.
 //
-// One warp owns one frame.  The chain is cut into per-lane contiguous chunks; each lane multiplies its
-// chunk's transforms sequentially (pass 1), the chunk aggregates are combined with a shuffle scan, and
-// each lane maps its chunk-local results through its prefix (pass 2).  All arithmetic is float64
-// (inputs/outputs float32): in float32 the orientation error random-walks along the chain and exceeds
-// the 1e-4 nm parity budget beyond ~100 residues; B200's FP64 pipe runs at half the
-// FP32 rate, so the kernel stays within ~2x of its HBM roofline.
+// Forward: the chain is cut into per-lane contiguous chunks; each lane multiplies its chunk's transforms
+// sequentially (pass 1), the chunk aggregates are combined with a shuffle scan, and each lane maps its
+// chunk-local results through its prefix (pass 2).  The transform chain is float64 (inputs/outputs float32): in
+// float32 the orientation error random-walks along the chain and exceeds the 1e-4 nm parity budget beyond ~100
+// residues.
 //
 // Forward formulations (tools/proto_backmap.py checks all of them against the oracle):
 //   * emk_backmap   : BackMapLayer.  NeRF placement from (L, theta, phi) with LOCAL transforms
@@ -15,17 +14,16 @@
 //   * emk_dihedrals_to_cartesian : arbitrary start chain.  A_i = rotation by dihedral_i about the bond
 //                     (t_{i+1}, t_{i+2}) of the START chain, C_i = C_{i-1} o A_i, out_k = C_{k-3}(start_k).
 //   * emk_chain_in_plane : SE(2) prefix product (alternating-sign turns) + prefix sum of bond vectors.
-// Backward: for every internal coordinate the downstream body moves rigidly (twist about a bond, hinge
-// about the normal of a bond angle, slide along a bond; left of the anchor the whole molecule also
-// follows the planar chain), so each gradient is <axis, torque> or <direction, force> of a prefix sum.
+// Backward: for every internal coordinate one end of the chain moves rigidly (twist about a bond, hinge
+// about the normal of a bond angle, slide along a bond; left of the anchor the whole molecule also follows the
+// planar chain), so each gradient is <axis, torque> or <direction, force> of that end's wrench, carried in
+// float32 about a pivot that moves with the walk (see "backward, version 3").
 #include <algorithm>
 #include <mutex>
 
 #include "emk_common.cuh"
 
 namespace emk {
-
-constexpr double kPi = 3.14159265358979323846;
 
 // ---- float64 sin/cos of a float32-exact argument, ~1e-14 absolute -----------------------------------
 __device__ __forceinline__ void sincos_d(double x, double* s, double* c) {
@@ -273,18 +271,10 @@ __global__ void chain_in_plane_kernel(const float* __restrict__ lengths, int64_t
 }
 
 // ====================================================================================================
-// BackMapLayer forward (NeRF from the planar anchor).
-//   * 64 threads per frame: one warp builds the left half outward from the middle, one the right half;
-//     two frames per 128-thread CTA.  Inputs and outputs are staged through shared memory so that every
-//     global access is coalesced.
-//   * pass 1: each lane multiplies the local transforms of its contiguous chunk in float64 and leaves
-//     chunk-local positions (float32, |x| < 4 nm) in the output buffer; the left warp builds the planar
-//     SE(2) product of the same bonds on the side, re-using the sin/cos of the bond angles.
-//   * warp scan of the chunk aggregates (5 shuffle steps), anchor frame from the planar product.
-//   * pass 2: out = prefix(local) -- rotation in float32 (local coordinates are small), translation as a
-//     float32 hi/lo pair, so this pass needs no FP64 and no conversions.
-//   * sin/cos: float32 Cody-Waite reduction to |r| <= pi/1024, float32 2-term corrections, float64 table +
-//     4 DFMA: 2.3e-10 absolute error (tools/gen_golden.py-independent check in tests), 4 FP64 ops instead of 30.
+// sin/cos of a float32 argument in float64, by table: float32 Cody-Waite reduction to |r| <= pi/1024 (the first two
+// steps are exact), float32 two-term corrections, a float64 table entry and 4 DFMA -- 2.3e-10 absolute error with 4
+// FP64 instructions instead of ~30.  The 1024-entry table lives in global memory (backward kernels); the forward
+// kernel copies every fourth entry into shared memory (sincos_tab256 below).
 // ====================================================================================================
 constexpr int SC_TABLE = 1024;               // table step 2 pi / 1024
 __global__ void sincos_table_kernel(double2* tab) {
@@ -314,155 +304,6 @@ __device__ __forceinline__ void sincos_tab(float x, const double2* __restrict__ 
   const double2 t = __ldg(tab + (__float_as_int(km) & (SC_TABLE - 1)));
   *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
   *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
-}
-
-constexpr int FWD_THREADS = 128;
-
-__global__ void __launch_bounds__(FWD_THREADS, 3) backmap_fwd3_kernel(const float* __restrict__ lengths, int64_t lstride,
-                                                                      const float* __restrict__ angles,
-                                                                      const float* __restrict__ dihedrals, int64_t b, int n,
-                                                                      float* __restrict__ xyz, const double2* __restrict__ tab) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ double anchor[FWD_THREADS / 64][2][12];
-  __shared__ float dump_s[FWD_THREADS][3];   // sink for the stores of out-of-range steps
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int g = tid >> 6, t = tid & 63, side = (tid >> 5) & 1;
-  const int64_t frame = (int64_t)blockIdx.x * (FWD_THREADS / 64) + g;
-  const bool active = frame < b;
-  // per-frame shared-memory regions (each 16-byte aligned, 4 floats of slack): lengths, angles, dihedrals, xyz
-  const int out_floats = 3 * n;
-  const int rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3, rD = (n - 3 + 7) & ~3, rO = (out_floats + 7) & ~3;
-  float* base = smem + (size_t)g * (rL + rA + rD + rO);
-  float *sL = base, *sA = base + rL, *sD = base + rL + rA, *sO = base + rL + rA + rD;
-  float* dst = xyz + (active ? frame : 0) * (int64_t)out_floats;
-  sO += (int)((reinterpret_cast<uintptr_t>(dst) & 15) >> 2);   // congruent with the global row modulo 16 bytes
-
-  if (active) {
-    sL = stage_row_async(sL, lengths + frame * lstride, n - 1, t, 64);
-    sA = stage_row_async(sA, angles + frame * (int64_t)(n - 2), n - 2, t, 64);
-    sD = stage_row_async(sD, dihedrals + frame * (int64_t)(n - 3), n - 3, t, 64);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int s = n / 2;
-  const int steps = side == 0 ? (s - 1) : (n - s - 2);
-  const int ch = ((max(s - 1, n - s - 2) + 31) / 32) | 1;   // odd chunk length: conflict-free strided smem access
-  const int i0 = lane * ch;
-
-  // ---- pass 1 (branch-free body: out-of-range steps load zeros and store nothing, so the unrolled
-  //      iterations can be software-pipelined: the sin/cos of step c+1 overlap the matrix chain of step c)
-  Se3 f;
-  se3_identity(f);
-  Se2 pl{1.0, 0.0, 0.0, 0.0};   // planar product of this lane's bonds (left warp only), ascending bond order
-  const int nvalid = active ? max(0, min(ch, steps - i0)) : 0;
-  float* dump = dump_s[tid];
-  const int dk = side == 0 ? -1 : 1;
-  const int kfirst = side == 0 ? s - 2 - i0 : s + 2 + i0;
-  {
-    const float* pD = sD + (side == 0 ? kfirst : kfirst - 3);
-    const float* pA = sA + (side == 0 ? kfirst : kfirst - 2);
-    const float* pL = sL + (side == 0 ? kfirst : kfirst - 1);
-    float* pO = sO + 3 * kfirst;
-    int kpar = kfirst;
-#pragma unroll 5
-    for (int c = 0; c < ch; c++) {
-      const bool ok = c < nvalid;
-      const float fd = ok ? *pD : 0.f, fa = ok ? *pA : 0.f, fl = ok ? *pL : 0.f;
-      double sw, cw, sg, cg;
-      sincos_tab(fd, tab, &sw, &cw);
-      sincos_tab(fa, tab, &sg, &cg);
-      const double L = (double)fl;
-      nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
-      float* po = ok ? pO : dump;
-      po[0] = (float)f.p[0];
-      po[1] = (float)f.p[1];
-      po[2] = (float)f.p[2];
-      if (side == 0) {
-        // planar bond k: advance L along the current direction, then turn by -(-1)^k (pi - theta_k);
-        // this lane walks k downwards, so the step is prepended: pl <- step_k o pl
-        const double tc = ok ? -cg : 1.0, ts = ok ? ((kpar & 1) ? sg : -sg) : 0.0;
-        const double nc = tc * pl.c - ts * pl.s, ns = tc * pl.s + ts * pl.c;
-        const double nx = L + tc * pl.x - ts * pl.y, ny = ts * pl.x + tc * pl.y;
-        pl.c = nc; pl.s = ns; pl.x = nx; pl.y = ny;
-      }
-      pD += dk; pA += dk; pL += dk; pO += 3 * dk; kpar += dk;
-    }
-  }
-
-  // ---- scan of the chunk aggregates inside the warp ---------------------------------------------------
-  Se3 inc = f;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Se3 up = se3_shfl_up(inc, d, 32);
-    if (lane >= d) inc = se3_mul(up, inc);
-  }
-  Se3 ex = se3_shfl_up(inc, 1, 32);
-  if (lane == 0) se3_identity(ex);
-
-  // ---- anchor: the left warp reduces the planar product (higher lanes hold lower bonds => go on the left)
-  if (side == 0) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      Se2 o = se2_shfl_down(pl, d);
-      if (lane + d < 32) pl = se2_mul(o, pl);
-    }
-    if (lane == 0 && active) {
-      // pl: direction of bond s-1 and position of atom s-1 in the plane
-      const double dm_c = pl.c, dm_s = pl.s, am_x = pl.x, am_y = pl.y;
-      Se2 mid = pl;
-      planar_step(mid, (double)sL[s - 1], true, sA[s - 1], s - 1);
-      const double a0_x = mid.x, a0_y = mid.y, dp_c = mid.c, dp_s = mid.s;
-      const double ap_x = fma((double)sL[s], dp_c, a0_x), ap_y = fma((double)sL[s], dp_s, a0_y);
-      const double zs = (dm_c * dp_s - dm_s * dp_c) >= 0.0 ? 1.0 : -1.0;
-      sO[3 * (s - 1)] = (float)am_x; sO[3 * (s - 1) + 1] = (float)am_y; sO[3 * (s - 1) + 2] = 0.f;
-      sO[3 * s] = (float)a0_x;       sO[3 * s + 1] = (float)a0_y;       sO[3 * s + 2] = 0.f;
-      sO[3 * (s + 1)] = (float)ap_x; sO[3 * (s + 1) + 1] = (float)ap_y; sO[3 * (s + 1) + 2] = 0.f;
-      // anchor frames: x along the last anchored bond, z = +-e_z, y = z x x, origin at the last anchor atom
-#pragma unroll
-      for (int sd = 0; sd < 2; sd++) {
-        const double xx = sd == 0 ? -dm_c : dp_c, xy = sd == 0 ? -dm_s : dp_s, zz = sd == 0 ? -zs : zs;
-        double* a = anchor[g][sd];
-        a[0] = xx; a[1] = -zz * xy; a[2] = 0.0;
-        a[3] = xy; a[4] = zz * xx;  a[5] = 0.0;
-        a[6] = 0.0; a[7] = 0.0;     a[8] = zz;
-        a[9] = sd == 0 ? am_x : ap_x; a[10] = sd == 0 ? am_y : ap_y; a[11] = 0.0;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- pass 2: out = (anchor o prefix)(local), float32 -------------------------------------------------
-  if (active) {
-    Se3 carry;
-#pragma unroll
-    for (int i = 0; i < 9; i++) carry.r[i] = anchor[g][side][i];
-#pragma unroll
-    for (int i = 0; i < 3; i++) carry.p[i] = anchor[g][side][9 + i];
-    const Se3 pre = se3_mul(carry, ex);
-    float rf[9], ph[3], plo[3];
-#pragma unroll
-    for (int i = 0; i < 9; i++) rf[i] = (float)pre.r[i];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      ph[i] = (float)pre.p[i];
-      plo[i] = (float)(pre.p[i] - (double)ph[i]);
-    }
-    float* pO = sO + 3 * kfirst;
-#pragma unroll 5
-    for (int c = 0; c < ch; c++) {
-      if (c < nvalid) {
-        const float lx = pO[0], ly = pO[1], lz = pO[2];
-        pO[0] = ph[0] + (fmaf(rf[0], lx, fmaf(rf[1], ly, rf[2] * lz)) + plo[0]);
-        pO[1] = ph[1] + (fmaf(rf[3], lx, fmaf(rf[4], ly, rf[5] * lz)) + plo[1]);
-        pO[2] = ph[2] + (fmaf(rf[6], lx, fmaf(rf[7], ly, rf[8] * lz)) + plo[2]);
-      }
-      pO += 3 * dk;
-    }
-  }
-  __syncthreads();
-  if (active) store_row(dst, sO, out_floats, t, 64);
 }
 
 // ====================================================================================================
@@ -798,260 +639,7 @@ __global__ void d2c_general_kernel(const float* __restrict__ dihedrals, const fl
   for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
 }
 
-// ====================================================================================================
-// backward: force / torque prefix sums
-//   T threads per frame (64 ... 1024, 12 atoms per thread), inputs staged with cp.async, outputs staged
-//   through shared memory.  Sums of (g, x cross g) and the reduced torque about the pivot are float64; the
-//   geometry (bond directions, bond-angle normals) and the final dot products are float32 -- they only
-//   scale a correctly reduced torque, so their 1e-7 relative error is the error of the result.
-// ====================================================================================================
-struct Wrench {
-  double f[3];
-  double t[3];
-};
-constexpr int BWD_CA = 13;   // atoms per thread; odd => the strided shared-memory walks are conflict-free
-
-__device__ __forceinline__ void unit3(float x, float y, float z, float* u) {
-  const float inv = rsqrtf(fmaf(x, x, fmaf(y, y, z * z)));
-  u[0] = x * inv; u[1] = y * inv; u[2] = z * inv;
-}
-
-template <int T>
-__global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd2_kernel(const BwdParams p, const double2* __restrict__ tab) {
-  constexpr int CTA = T < 128 ? 128 : T;
-  constexpr int FPC = CTA / T;
-  constexpr int WPF = T / 32;
-  static_assert(T >= 32 && T % 32 == 0, "whole warps per frame");
-  extern __shared__ __align__(16) float smem[];
-  __shared__ double wsum[FPC][WPF][6];
-  __shared__ double psum[FPC][WPF][4];
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int g = tid / T, t = tid % T, wf = t >> 5;
-  const int64_t frame = (int64_t)blockIdx.x * FPC + g;
-  const bool active = frame < p.b;
-  const int64_t fr = active ? frame : 0;
-  const int n = p.n;
-  const bool need_planar = p.planar || ((p.grad_angles || p.grad_lengths) && p.mid > 1);
-
-  const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3;
-  float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0));
-  float* sX = base;
-  float* sG = base + rX;
-  float* sL = sG + rG;
-  float* sA = sL + rL;
-  if (active) {
-    sG = stage_row_async(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
-    if (!p.planar) sX = stage_row_async(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
-    if (need_planar) {
-      sL = stage_row_async(sL, p.lengths + fr * p.lstride, n - 1, t, T);
-      sA = stage_row_async(sA, p.angles + fr * (int64_t)(n - 2), n - 2, t, T);
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int k0 = min(n, t * BWD_CA), k1 = min(n, k0 + BWD_CA);
-
-  // ---- planar chain: state before bond k0 (direction of bond k0, position of atom k0) -----------------------
-  Se2 pl_ex{1.0, 0.0, 0.0, 0.0};
-  if (need_planar) {
-    Se2 part{1.0, 0.0, 0.0, 0.0};
-    if (active)
-      for (int k = k0; k < k1 && k < n - 1; k++) {
-        part.x = fma((double)sL[k], part.c, part.x);
-        part.y = fma((double)sL[k], part.s, part.y);
-        if (k < n - 2) {
-          double st, ct;
-          sincos_tab(sA[k], tab, &st, &ct);
-          const double cw = -ct, sw = (k & 1) ? st : -st;
-          const double c2 = part.c * cw - part.s * sw, s2 = part.c * sw + part.s * cw;
-          part.c = c2; part.s = s2;
-        }
-      }
-    Se2 inc = part;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      Se2 up = se2_shfl_up(inc, d);
-      if (lane >= d) inc = se2_mul(up, inc);
-    }
-    Se2 ex = se2_shfl_up(inc, 1);
-    if (lane == 0) ex = Se2{1.0, 0.0, 0.0, 0.0};
-    if (lane == 31) {
-      psum[g][wf][0] = inc.c; psum[g][wf][1] = inc.s; psum[g][wf][2] = inc.x; psum[g][wf][3] = inc.y;
-    }
-    __syncthreads();
-    Se2 prev{1.0, 0.0, 0.0, 0.0};
-    for (int w = 0; w < wf; w++) prev = se2_mul(prev, Se2{psum[g][w][0], psum[g][w][1], psum[g][w][2], psum[g][w][3]});
-    pl_ex = se2_mul(prev, ex);
-    if (p.planar) {
-      // chain_in_plane backward: the planar coordinates are the "final" coordinates
-      Se2 run = pl_ex;
-      if (active) {
-        if (t == 0) { sX[0] = 0.f; sX[1] = 0.f; sX[2] = 0.f; }
-        for (int k = k0; k < k1 && k < n - 1; k++) {
-          run.x = fma((double)sL[k], run.c, run.x);
-          run.y = fma((double)sL[k], run.s, run.y);
-          if (k < n - 2) {
-            double st, ct;
-            sincos_tab(sA[k], tab, &st, &ct);
-            const double cw = -ct, sw = (k & 1) ? st : -st;
-            const double c2 = run.c * cw - run.s * sw, s2 = run.c * sw + run.s * cw;
-            run.c = c2; run.s = s2;
-          }
-          sX[3 * (k + 1)] = (float)run.x; sX[3 * (k + 1) + 1] = (float)run.y; sX[3 * (k + 1) + 2] = 0.f;
-        }
-      }
-      __syncthreads();
-    }
-  }
-
-  // ---- pass 1: wrench of this thread's atoms, block-wide prefix ------------------------------------------------
-  Wrench w{};
-  if (active)
-    for (int k = k0; k < k1; k++) {
-      const double x0 = sX[3 * k], x1 = sX[3 * k + 1], x2 = sX[3 * k + 2];
-      const double g0 = sG[3 * k], g1 = sG[3 * k + 1], g2 = sG[3 * k + 2];
-      w.f[0] += g0; w.f[1] += g1; w.f[2] += g2;
-      w.t[0] += x1 * g2 - x2 * g1;
-      w.t[1] += x2 * g0 - x0 * g2;
-      w.t[2] += x0 * g1 - x1 * g0;
-    }
-  Wrench inc = w;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      const double uf = __shfl_up_sync(0xffffffffu, inc.f[i], d), ut = __shfl_up_sync(0xffffffffu, inc.t[i], d);
-      if (lane >= d) { inc.f[i] += uf; inc.t[i] += ut; }
-    }
-  }
-  if (lane == 31) {
-#pragma unroll
-    for (int i = 0; i < 3; i++) { wsum[g][wf][i] = inc.f[i]; wsum[g][wf][3 + i] = inc.t[i]; }
-  }
-  Wrench lo;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    lo.f[i] = __shfl_up_sync(0xffffffffu, inc.f[i], 1);
-    lo.t[i] = __shfl_up_sync(0xffffffffu, inc.t[i], 1);
-    if (lane == 0) { lo.f[i] = 0.0; lo.t[i] = 0.0; }
-  }
-  __syncthreads();
-  Wrench tot{};
-#pragma unroll
-  for (int wq = 0; wq < WPF; wq++) {
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      const double a = wsum[g][wq][i], b2 = wsum[g][wq][3 + i];
-      tot.f[i] += a; tot.t[i] += b2;
-      if (wq < wf) { lo.f[i] += a; lo.t[i] += b2; }
-    }
-  }
-
-  // ---- pass 2: walk the chunk with a sliding window of positions; results overwrite g_k in place ---------------
-  //      (sG[3k] <- dihedral term, sG[3k+1] <- angle term, sG[3k+2] <- bond term of the cut after atom k)
-  const bool wantD = p.grad_dihedrals != nullptr, wantA = p.grad_angles != nullptr, wantL = p.grad_lengths != nullptr;
-  if (active && k0 < k1) {
-    Se2 pl = pl_ex;
-    auto ld = [&](int k, float* v) {
-      const int kk = min(max(k, 0), n - 1);
-      v[0] = sX[3 * kk]; v[1] = sX[3 * kk + 1]; v[2] = sX[3 * kk + 2];
-    };
-    float xm[3], xk[3], xp[3], xq[3];
-    ld(k0 - 1, xm); ld(k0, xk); ld(k0 + 1, xp);
-    double xkd[3] = {xk[0], xk[1], xk[2]}, xpd[3] = {xp[0], xp[1], xp[2]};
-#pragma unroll 1
-    for (int k = k0; k < k1; k++) {
-      ld(k + 2, xq);
-      const double xqd[3] = {xq[0], xq[1], xq[2]};
-      {
-        const double g0 = sG[3 * k], g1 = sG[3 * k + 1], g2 = sG[3 * k + 2];
-        lo.f[0] += g0; lo.f[1] += g1; lo.f[2] += g2;
-        lo.t[0] += xkd[1] * g2 - xkd[2] * g1;
-        lo.t[1] += xkd[2] * g0 - xkd[0] * g2;
-        lo.t[2] += xkd[0] * g1 - xkd[1] * g0;
-      }
-      const bool left = k < p.dr0;
-      // wrench of the moving body and its pivot: atoms <= k about x_{k+1} (left of the anchor), atoms > k about x_k
-      double wf0, wf1, wf2, wt0, wt1, wt2, pv0, pv1, pv2;
-      if (left) {
-        wf0 = lo.f[0]; wf1 = lo.f[1]; wf2 = lo.f[2]; wt0 = lo.t[0]; wt1 = lo.t[1]; wt2 = lo.t[2];
-        pv0 = xpd[0]; pv1 = xpd[1]; pv2 = xpd[2];
-      } else {
-        wf0 = tot.f[0] - lo.f[0]; wf1 = tot.f[1] - lo.f[1]; wf2 = tot.f[2] - lo.f[2];
-        wt0 = tot.t[0] - lo.t[0]; wt1 = tot.t[1] - lo.t[1]; wt2 = tot.t[2] - lo.t[2];
-        pv0 = xkd[0]; pv1 = xkd[1]; pv2 = xkd[2];
-      }
-      const float tq0 = (float)(wt0 - (pv1 * wf2 - pv2 * wf1));
-      const float tq1 = (float)(wt1 - (pv2 * wf0 - pv0 * wf2));
-      const float tq2 = (float)(wt2 - (pv0 * wf1 - pv1 * wf0));
-      const float b00 = xk[0] - xm[0], b01 = xk[1] - xm[1], b02 = xk[2] - xm[2];   // bond k-1
-      const float b10 = xp[0] - xk[0], b11 = xp[1] - xk[1], b12 = xp[2] - xk[2];   // bond k
-      const float b20 = xq[0] - xp[0], b21 = xq[1] - xp[1], b22 = xq[2] - xp[2];   // bond k+1
-      // planar direction of bond k and planar position of atom k+1
-      const double pdir0 = pl.c, pdir1 = pl.s;
-      double cn0 = 0.0, cn1 = 0.0;
-      if (need_planar && k < n - 1) {
-        pl.x = fma((double)sL[k], pl.c, pl.x);
-        pl.y = fma((double)sL[k], pl.s, pl.y);
-        if (k < n - 2) {
-          double st, ct;
-          sincos_tab(sA[k], tab, &st, &ct);
-          const double cw = -ct, sw = (k & 1) ? st : -st;
-          const double c2 = pl.c * cw - pl.s * sw, s2 = pl.c * sw + pl.s * cw;
-          pl.c = c2; pl.s = s2;
-        }
-        cn0 = pl.x; cn1 = pl.y;
-      }
-      float rD = 0.f, rA = 0.f, rL = 0.f;
-      if (wantD) {
-        float u[3];
-        if (left) unit3(b20, b21, b22, u); else unit3(b00, b01, b02, u);
-        const float v = u[0] * tq0 + u[1] * tq1 + u[2] * tq2;
-        rD = left ? -v : v;
-      }
-      if (wantA) {
-        float nr[3];
-        if (p.planar) { nr[0] = 0.f; nr[1] = 0.f; nr[2] = ((k - 1) & 1) ? 1.f : -1.f; }
-        else if (left) unit3(b11 * b22 - b12 * b21, b12 * b20 - b10 * b22, b10 * b21 - b11 * b20, nr);
-        else unit3(b01 * b12 - b02 * b11, b02 * b10 - b00 * b12, b00 * b11 - b01 * b10, nr);
-        const float v = nr[0] * tq0 + nr[1] * tq1 + nr[2] * tq2;
-        rA = left ? (float)(((k & 1) ? -1.0 : 1.0) * (tot.t[2] - (cn0 * tot.f[1] - cn1 * tot.f[0]))) + v : -v;
-      }
-      if (wantL) {
-        float bd[3];
-        if (p.planar) { bd[0] = (float)pdir0; bd[1] = (float)pdir1; bd[2] = 0.f; }
-        else unit3(b10, b11, b12, bd);
-        const float v = bd[0] * (float)wf0 + bd[1] * (float)wf1 + bd[2] * (float)wf2;
-        rL = left ? (float)(pdir0 * tot.f[0] + pdir1 * tot.f[1]) - v : v;
-      }
-      sG[3 * k] = rD; sG[3 * k + 1] = rA; sG[3 * k + 2] = rL;
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        xm[i] = xk[i]; xk[i] = xp[i]; xp[i] = xq[i];
-        xkd[i] = xpd[i]; xpd[i] = xqd[i];
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- gather the per-cut results into the three output rows (coalesced global stores) -----------------------------
-  if (active) {
-    if (wantD) {
-      float* gD = p.grad_dihedrals + fr * (int64_t)(n - 3);
-      for (int d = t; d < n - 3; d += T) gD[d] = sG[3 * (d < p.dr0 ? d : d + 2)];      // left: cut d, right: cut d+2
-    }
-    if (wantA) {
-      float* gA = p.grad_angles + fr * (int64_t)(n - 2);
-      for (int j = t; j < n - 2; j += T) gA[j] = sG[3 * (j + 1 < p.mid ? j : j + 1) + 1];  // left: cut j, right: cut j+1
-    }
-    if (wantL) {
-      float* gL = p.grad_lengths + fr * (int64_t)(n - 1);
-      for (int k = t; k < n - 1; k += T) gL[k] = sG[3 * k + 2];
-    }
-  }
-}
+constexpr int BWD_CA = 13;   // atoms per thread that size the thread count per frame; odd => conflict-free strided walks
 
 // ====================================================================================================
 // backward, version 3: float32 wrench recurrences about a MOVING pivot.
@@ -1090,7 +678,42 @@ __device__ __forceinline__ void wrench_append(WrenchF& c, const WrenchF& a, cons
   c.s[2] += a.s[2];
 }
 
-template <int T>
+// 16-byte staging of one row by NT threads: uniform trip count, four predicated copies with immediate offsets per
+// iteration.  Same contract as stage_row_async (starts at the 16-byte boundary at or below src).
+__device__ __forceinline__ void cp_async16_s(uint32_t dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int NT>
+__device__ __forceinline__ float* stage_row16(float* region, const float* __restrict__ src, int len, int t) {
+  const int sh = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
+  const float* asrc = src - sh;
+  const int total = sh + len;
+  const int nvec = total >> 2;
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(region) + 16u * (uint32_t)t;
+  const float* s = asrc + 4 * t;
+  int left = nvec - t;                          // copy i of this thread is in range iff NT * i < left
+  const int iters = (nvec + NT - 1) / NT;
+  int i = 0;
+#pragma unroll 1
+  for (; i + 4 <= iters; i += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (NT * u < left) cp_async16_s(d + 16u * NT * u, s + 4 * NT * u);
+    d += 64u * NT;
+    s += 16 * NT;
+    left -= 4 * NT;
+  }
+#pragma unroll
+  for (int u = 0; u < 3; u++)
+    if (i + u < iters && NT * u < left) cp_async16_s(d + 16u * NT * u, s + 4 * NT * u);
+  const int e = (nvec << 2) + t;
+  if (e < total) cp_async4(region + e, asrc + e);
+  return region + sh;
+}
+
+// GEN = false: only dihedral gradients, no planar terms (the default ADC training step and the standalone
+// dihedrals_to_cartesian op); GEN = true: everything (angle / length gradients, planar mode).
+template <int T, bool GEN>
 __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const BwdParams p, const double2* __restrict__ tab) {
   constexpr int CTA = T < 128 ? 128 : T;
   constexpr int FPC = CTA / T;
@@ -1107,21 +730,22 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
   const bool active = frame < p.b;
   const int64_t fr = active ? frame : 0;
   const int n = p.n;
-  const bool extras = !p.planar && (p.grad_angles || p.grad_lengths) && p.mid > 1;   // left-of-anchor planar terms
-  const bool need_planar = p.planar || extras;
+  const bool planar = GEN && p.planar;
+  const bool extras = GEN && !p.planar && (p.grad_angles || p.grad_lengths) && p.mid > 1;   // left-of-anchor planar terms
+  const bool need_planar = planar || extras;
 
   const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3;
   float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0));
-  float* sX = base;
+  float* sX = base + 4;   // 4 floats of slack in front: the walk may read (never use) one atom before the chain
   float* sG = base + rX;
   float* sL = sG + rG;
   float* sA = sL + rL;
   if (active) {
-    sG = stage_row_async(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
-    if (!p.planar) sX = stage_row_async(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t, T);
+    sG = stage_row16<T>(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t);
+    if (!planar) sX = stage_row16<T>(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t);
     if (need_planar) {
-      sL = stage_row_async(sL, p.lengths + fr * p.lstride, n - 1, t, T);
-      sA = stage_row_async(sA, p.angles + fr * (int64_t)(n - 2), n - 2, t, T);
+      sL = stage_row16<T>(sL, p.lengths + fr * p.lstride, n - 1, t);
+      sA = stage_row16<T>(sA, p.angles + fr * (int64_t)(n - 2), n - 2, t);
     }
   }
   cp_async_wait_all();
@@ -1136,14 +760,14 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
   const int W = TS < 32 ? TS : 32;                    // shuffle segment (16 only for T = 32 with two sides)
   const int qs = q & (W - 1);                         // lane within the segment
   const int steps = side ? n - 1 - p.dr0 : p.dr0;
-  const int C = (steps + TS - 1) / TS;
+  const int C = ((steps + TS - 1) / TS) | 1;          // odd: the strided shared-memory walks are conflict-free
   const int i0 = min(steps, q * C), i1 = min(steps, i0 + C);
   const int st = side ? -3 : 3;
   const int a0 = side ? n - 1 - i0 : i0;              // atom of walk index i0
 
   // ---- planar chain ------------------------------------------------------------------------------------------
   Se2 pl_ex{1.0, 0.0, 0.0, 0.0};   // left threads with extras: planar state before bond i0
-  if (p.planar) {
+  if (planar) {
     // chain_in_plane backward: recompute the planar coordinates into sX (ascending chunks of BWD_CA atoms)
     const int k0 = min(n, t * BWD_CA), k1 = min(n, k0 + BWD_CA);
     Se2 part{1.0, 0.0, 0.0, 0.0};
@@ -1273,8 +897,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     __syncthreads();
   }
 
-  // ---- pass 2: walk the chunk again from the prefix, emit the three terms of every cut ---------------------------
-  const bool wantD = p.grad_dihedrals != nullptr, wantA = p.grad_angles != nullptr, wantL = p.grad_lengths != nullptr;
+  // ---- pass 2: walk the chunk again from the prefix, emit the terms of every cut ----------------------------------
+  const bool wantD = p.grad_dihedrals != nullptr, wantA = GEN && p.grad_angles != nullptr, wantL = GEN && p.grad_lengths != nullptr;
   if (active && i0 < i1) {
     float ft[3] = {0.f, 0.f, 0.f}, mt[3] = {0.f, 0.f, 0.f}, xr[3] = {0.f, 0.f, 0.f};
     const bool lext = extras && side == 0;
@@ -1288,53 +912,52 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     }
     Se2 pl = pl_ex;
     float s0 = ex.s[0], s1 = ex.s[1], s2 = ex.s[2], m0 = ex.m[0], m1 = ex.m[1], m2 = ex.m[2];
-    const float* px = sX + 3 * a0;
+    const float* px = sX + 3 * a0 + 2 * st;   // x(a_{i+2}); one atom beyond the chain end is slack / the neighbouring row
     float* pg = sG + 3 * a0;
-    float xc0 = px[0], xc1 = px[1], xc2 = px[2];
-    float xn0 = px[st], xn1 = px[st + 1], xn2 = px[st + 2];
-    const int alast = side ? 0 : n - 1;   // clamp of a_{i+2} at the end of the chain (its terms are never gathered)
-#pragma unroll 1
+    float xn0 = px[-st], xn1 = px[-st + 1], xn2 = px[-st + 2];
+    float e10 = xn0 - xs[0], e11 = xn1 - xs[1], e12 = xn2 - xs[2];
+#pragma unroll 2
     for (int i = i0; i < i1; i++) {
-      const int a2 = side ? max(n - 3 - i, alast) : min(i + 2, alast);
-      const float xq0 = sX[3 * a2], xq1 = sX[3 * a2 + 1], xq2 = sX[3 * a2 + 2];
+      const float xq0 = px[0], xq1 = px[1], xq2 = px[2];
       s0 += pg[0]; s1 += pg[1]; s2 += pg[2];
-      const float e10 = xn0 - xc0, e11 = xn1 - xc1, e12 = xn2 - xc2;
       m0 = fmaf(-e11, s2, fmaf(e12, s1, m0));
       m1 = fmaf(-e12, s0, fmaf(e10, s2, m1));
       m2 = fmaf(-e10, s1, fmaf(e11, s0, m2));
       const float e20 = xq0 - xn0, e21 = xq1 - xn1, e22 = xq2 - xn2;
-      float rD = 0.f, rA = 0.f, rL = 0.f;
-      if (wantD) rD = -(e20 * m0 + e21 * m1 + e22 * m2) * rsqrtf(fmaf(e20, e20, fmaf(e21, e21, e22 * e22)));
-      if (wantA) {
-        if (p.planar) {
-          const int k = n - 2 - i;                      // cut index (planar mode has only the right side)
-          rA = ((k - 1) & 1) ? -m2 : m2;                // hinge normal -(-1)^(k-1) e_z, term = -<normal, M>
-        } else {
-          const float c0 = e11 * e22 - e12 * e21, c1 = e12 * e20 - e10 * e22, c2 = e10 * e21 - e11 * e20;
-          rA = (c0 * m0 + c1 * m1 + c2 * m2) * rsqrtf(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)));
+      if (wantD) pg[0] = -(e20 * m0 + e21 * m1 + e22 * m2) * rsqrtf(fmaf(e20, e20, fmaf(e21, e21, e22 * e22)));
+      if (GEN) {
+        float rA = 0.f, rL = 0.f;
+        if (wantA) {
+          if (planar) {
+            const int k = n - 2 - i;                      // cut index (planar mode has only the right side)
+            rA = ((k - 1) & 1) ? -m2 : m2;                // hinge normal -(-1)^(k-1) e_z, term = -<normal, M>
+          } else {
+            const float c0 = e11 * e22 - e12 * e21, c1 = e12 * e20 - e10 * e22, c2 = e10 * e21 - e11 * e20;
+            rA = (c0 * m0 + c1 * m1 + c2 * m2) * rsqrtf(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)));
+          }
         }
+        if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrtf(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
+        if (lext) {
+          // planar direction of bond k = i, planar position of atom k+1, then the turn at atom k+1
+          const double pd0 = pl.c, pd1 = pl.s;
+          pl.x = fma((double)sL[i], pl.c, pl.x);
+          pl.y = fma((double)sL[i], pl.s, pl.y);
+          double sn, cs;
+          sincos_tab(sA[i], tab, &sn, &cs);
+          const double cw = -cs, sw = (i & 1) ? sn : -sn;
+          const double c2 = pl.c * cw - pl.s * sw, s2d = pl.c * sw + pl.s * cw;
+          pl.c = c2; pl.s = s2d;
+          // z-torque of the whole molecule about planar atom k+1
+          const float dx = xr[0] - (float)pl.x, dy = xr[1] - (float)pl.y;
+          const float tz = mt[2] + (dx * ft[1] - dy * ft[0]);
+          rA += (i & 1) ? -tz : tz;
+          rL += (float)pd0 * ft[0] + (float)pd1 * ft[1];
+        }
+        pg[1] = rA; pg[2] = rL;
       }
-      if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrtf(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
-      if (lext) {
-        // planar direction of bond k = i, planar position of atom k+1, then the turn at atom k+1
-        const double pd0 = pl.c, pd1 = pl.s;
-        pl.x = fma((double)sL[i], pl.c, pl.x);
-        pl.y = fma((double)sL[i], pl.s, pl.y);
-        double sn, cs;
-        sincos_tab(sA[i], tab, &sn, &cs);
-        const double cw = -cs, sw = (i & 1) ? sn : -sn;
-        const double c2 = pl.c * cw - pl.s * sw, s2d = pl.c * sw + pl.s * cw;
-        pl.c = c2; pl.s = s2d;
-        // z-torque of the whole molecule about planar atom k+1
-        const float dx = xr[0] - (float)pl.x, dy = xr[1] - (float)pl.y;
-        const float tz = mt[2] + (dx * ft[1] - dy * ft[0]);
-        rA += (i & 1) ? -tz : tz;
-        rL += (float)pd0 * ft[0] + (float)pd1 * ft[1];
-      }
-      pg[0] = rD; pg[1] = rA; pg[2] = rL;
-      xc0 = xn0; xc1 = xn1; xc2 = xn2;
       xn0 = xq0; xn1 = xq1; xn2 = xq2;
-      pg += st;
+      e10 = e20; e11 = e21; e12 = e22;
+      px += st; pg += st;
     }
   }
   __syncthreads();
@@ -1455,8 +1078,8 @@ int d2c_general_device(const float* dihedrals, const float* chain, int64_t cstri
   return launch_status("d2c_general_kernel");
 }
 
-template <int T>
-static int launch_bwd2(const BwdParams& p, const double2* tab, bool need_planar, cudaStream_t st) {
+template <int T, bool GEN>
+static int launch_bwd3(const BwdParams& p, const double2* tab, bool need_planar, cudaStream_t st) {
   constexpr int CTA = T < 128 ? 128 : T;
   constexpr int FPC = CTA / T;
   const size_t n = (size_t)p.n;
@@ -1464,7 +1087,7 @@ static int launch_bwd2(const BwdParams& p, const double2* tab, bool need_planar,
                            (need_planar ? ((n - 1 + 7) & ~(size_t)3) + ((n - 2 + 7) & ~(size_t)3) : 0);
   const size_t smem = FPC * per_frame * sizeof(float);
   EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "back-mapping backward: chain of %d atoms needs %zu bytes of staging shared memory", p.n, smem);
-  auto kern = backmap_bwd3_kernel<T>;
+  auto kern = backmap_bwd3_kernel<T, GEN>;
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t blocks = (p.b + FPC - 1) / FPC;
@@ -1480,13 +1103,16 @@ int backmap_bwd_device(const BwdParams& p, cudaStream_t st) {
   if (rc) return rc;
   const bool need_planar = p.planar || ((p.grad_angles || p.grad_lengths) && p.mid > 1);
   const int n = p.n;
-  if (n <= 32 * BWD_CA) return launch_bwd2<32>(p, tab, need_planar, st);
-  if (n <= 64 * BWD_CA) return launch_bwd2<64>(p, tab, need_planar, st);
-  if (n <= 128 * BWD_CA) return launch_bwd2<128>(p, tab, need_planar, st);
-  if (n <= 256 * BWD_CA) return launch_bwd2<256>(p, tab, need_planar, st);
-  if (n <= 512 * BWD_CA) return launch_bwd2<512>(p, tab, need_planar, st);
+  const bool gen = p.planar || p.grad_angles || p.grad_lengths;
+#define EMK_BWD3(TT) return gen ? launch_bwd3<TT, true>(p, tab, need_planar, st) : launch_bwd3<TT, false>(p, tab, need_planar, st)
+  if (n <= 32 * BWD_CA) EMK_BWD3(32);
+  if (n <= 64 * BWD_CA) EMK_BWD3(64);
+  if (n <= 128 * BWD_CA) EMK_BWD3(128);
+  if (n <= 256 * BWD_CA) EMK_BWD3(256);
+  if (n <= 512 * BWD_CA) EMK_BWD3(512);
   EMK_REQUIRE(n <= 1024 * BWD_CA, EMK_E_UNSUPPORTED, "back-mapping backward: chains above %d atoms are not supported", 1024 * BWD_CA);
-  return launch_bwd2<1024>(p, tab, need_planar, st);
+  EMK_BWD3(1024);
+#undef EMK_BWD3
 }
 
 }  // namespace emk

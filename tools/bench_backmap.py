@@ -35,20 +35,26 @@ def run(n, b, reps=5):
         xyz = _ops.BackMap.apply(lengths, ang, dih)
     ga, gd = torch.empty_like(ang), torch.empty_like(dih)
     args = [_lib.DL(v) for v in (lengths, ang.detach(), xyz, w, ga, gd)]
-    def bwd():
-        _lib.check(_lib.lib().emk_dl_backmap_bwd(args[0], args[1], args[2], args[3], args[4], args[5], None, _lib.stream_of(xyz)))
-    bwd(); bwd()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        bwd()
-    e1.record()
-    torch.cuda.synchronize()
-    both = fwd + e0.elapsed_time(e1) / reps
+
+    def time_bwd(with_angles):
+        def bwd():
+            _lib.check(_lib.lib().emk_dl_backmap_bwd(args[0], args[1], args[2], args[3], args[4] if with_angles else None, args[5], None, _lib.stream_of(xyz)))
+        bwd(); bwd()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            bwd()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    bwd_d, bwd_ad = time_bwd(False), time_bwd(True)
     bf = 4 * ((n - 2) + (n - 3)) + 12 * n
-    bb = bf + 12 * n * 2 + 4 * (n - 2) * 2 + 4 * (n - 3)
+    bd = 24 * n + 4 * (n - 3)                      # dihedral-only backward: xyz + grad_xyz in, grad_dihedrals out
+    bad = bd + 4 * (n - 1) + 8 * (n - 2)           # + lengths, angles in, grad_angles out
     print(f"n={n} b={b}: fwd {fwd:.3f} ms {b / fwd / 1e3:.2f} Mframes/s {b * bf / fwd / 1e6 / HBM:.3f} of HBM | "
-          f"fwd+bwd {both:.3f} ms {b / both / 1e3:.2f} Mframes/s {b * bb / both / 1e6 / HBM:.3f} of HBM (bwd alone {both - fwd:.3f} ms)")
+          f"bwd(dih) {bwd_d:.3f} ms {b * bd / bwd_d / 1e6 / HBM:.3f} of HBM | bwd(ang+dih) {bwd_ad:.3f} ms {b * bad / bwd_ad / 1e6 / HBM:.3f} of HBM | "
+          f"fwd+bwd(dih) {b / (fwd + bwd_d) / 1e3:.2f} Mframes/s")
 
 
 for n, b in ((300, 1024), (300, 65536), (1500, 65536), (999, 32768), (3000, 8192)):

@@ -16,6 +16,8 @@ ang = (1.9 + 0.3 * torch.rand(b, n - 2, device=dev, generator=g)).requires_grad_
 dih = ((torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).requires_grad_(True)
 w = torch.randn(b, n, 3, device=dev, generator=g)
 xyz = _ops.BackMap.apply(lengths, ang, dih)
-xyz.backward(w)
+xyz.backward(w)                                   # angle + dihedral gradients (use_backbone_angles=True)
+xyz2 = _ops.BackMap.apply(lengths, ang.detach(), dih)
+xyz2.backward(w)                                  # dihedral gradients only (the ADC default)
 torch.cuda.synchronize()
 print("ok", xyz.shape)
