@@ -806,6 +806,10 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
         const double cw = -cs, sw = (k & 1) ? sn : -sn;
         const double c2 = part.c * cw - part.s * sw, s2 = part.c * sw + part.s * cw;
         part.c = c2; part.s = s2;
+        // planar atom k+1 in the frame of this thread's first bond replaces (L_k, theta_k): pass 2 only needs
+        // float32 arithmetic on these chunk-local coordinates (< 2 nm) and the float64 prefix of the chunk
+        sL[k] = (float)part.x;
+        sA[k] = (float)part.y;
       }
     Se2 inc = part;
 #pragma unroll
@@ -910,7 +914,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
         mt[i] = side_tot[g][0][3 + i] + side_tot[g][1][3 + i];
       }
     }
-    Se2 pl = pl_ex;
+    const float plc = (float)pl_ex.c, pls = (float)pl_ex.s, plx = (float)pl_ex.x, ply = (float)pl_ex.y;
+    float llx = 0.f, lly = 0.f;   // chunk-local planar position of atom i (the chunk starts at its own origin)
     float s0 = ex.s[0], s1 = ex.s[1], s2 = ex.s[2], m0 = ex.m[0], m1 = ex.m[1], m2 = ex.m[2];
     const float* px = sX + 3 * a0 + 2 * st;   // x(a_{i+2}); one atom beyond the chain end is slack / the neighbouring row
     float* pg = sG + 3 * a0;
@@ -938,20 +943,19 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
         }
         if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrtf(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
         if (lext) {
-          // planar direction of bond k = i, planar position of atom k+1, then the turn at atom k+1
-          const double pd0 = pl.c, pd1 = pl.s;
-          pl.x = fma((double)sL[i], pl.c, pl.x);
-          pl.y = fma((double)sL[i], pl.s, pl.y);
-          double sn, cs;
-          sincos_tab(sA[i], tab, &sn, &cs);
-          const double cw = -cs, sw = (i & 1) ? sn : -sn;
-          const double c2 = pl.c * cw - pl.s * sw, s2d = pl.c * sw + pl.s * cw;
-          pl.c = c2; pl.s = s2d;
+          // planar atom k+1 (k = i) from its chunk-local coordinates; planar direction of bond k from two of them
+          const float lx = sL[i], ly = sA[i];
+          const float cn0 = fmaf(plc, lx, fmaf(-pls, ly, plx)), cn1 = fmaf(pls, lx, fmaf(plc, ly, ply));
           // z-torque of the whole molecule about planar atom k+1
-          const float dx = xr[0] - (float)pl.x, dy = xr[1] - (float)pl.y;
-          const float tz = mt[2] + (dx * ft[1] - dy * ft[0]);
+          const float tz = mt[2] + ((xr[0] - cn0) * ft[1] - (xr[1] - cn1) * ft[0]);
           rA += (i & 1) ? -tz : tz;
-          rL += (float)pd0 * ft[0] + (float)pd1 * ft[1];
+          if (wantL) {
+            const float dlx = lx - llx, dly = ly - lly;
+            const float inv = rsqrtf(fmaf(dlx, dlx, dly * dly));
+            const float q0 = dlx * inv, q1 = dly * inv;
+            rL += (plc * q0 - pls * q1) * ft[0] + (pls * q0 + plc * q1) * ft[1];
+          }
+          llx = lx; lly = ly;
         }
         pg[1] = rA; pg[2] = rL;
       }
