@@ -56,31 +56,72 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ r, int64_t count, S
 }
 
 // ---- PeriodicInput -----------------------------------------------------------------------------------
-__global__ void periodic_input_kernel(const float* __restrict__ x, int64_t rows, int64_t d, float scale, int rescale,
-                                      float* __restrict__ out) {
-  const int64_t total = rows * d;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / d, k = i - r * d;
-    float v = x[i];
-    if (rescale) v = v * scale;
-    float s, c;
-    sincosf(v, &s, &c);
-    out[r * 2 * d + k] = s;
-    out[r * 2 * d + d + k] = c;
+// (rows, d) -> (rows, 2d) = [sin x | cos x].  CTAs stride over rows, threads over the columns of a row: no index
+// division, and 16-byte loads / stores when d is a multiple of 4 and the bases are aligned (VEC).
+template <bool VEC>
+__global__ void __launch_bounds__(256) periodic_input_kernel(const float* __restrict__ x, int64_t rows, int d, float scale, int rescale,
+                                                             float* __restrict__ out) {
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* xr = x + r * d;
+    float* so = out + r * 2 * d;
+    float* co = so + d;
+    if (VEC) {
+      for (int k = threadIdx.x * 4; k < d; k += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(xr + k);
+        if (rescale) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+        float4 s4, c4;
+        sincosf(v.x, &s4.x, &c4.x);
+        sincosf(v.y, &s4.y, &c4.y);
+        sincosf(v.z, &s4.z, &c4.z);
+        sincosf(v.w, &s4.w, &c4.w);
+        *reinterpret_cast<float4*>(so + k) = s4;
+        *reinterpret_cast<float4*>(co + k) = c4;
+      }
+    } else {
+      for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        float v = xr[k];
+        if (rescale) v *= scale;
+        float sn, cs;
+        sincosf(v, &sn, &cs);
+        so[k] = sn;
+        co[k] = cs;
+      }
+    }
   }
 }
-__global__ void periodic_input_bwd_kernel(const float* __restrict__ x, int64_t rows, int64_t d, float scale, int rescale,
-                                          const float* __restrict__ go, float* __restrict__ gx) {
-  const int64_t total = rows * d;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / d, k = i - r * d;
-    float v = x[i];
-    if (rescale) v = v * scale;
-    float s, c;
-    sincosf(v, &s, &c);
-    float g = go[r * 2 * d + k] * c - go[r * 2 * d + d + k] * s;
-    if (rescale) g *= scale;
-    gx[i] = g;
+template <bool VEC>
+__global__ void __launch_bounds__(256) periodic_input_bwd_kernel(const float* __restrict__ x, int64_t rows, int d, float scale, int rescale,
+                                                                 const float* __restrict__ go, float* __restrict__ gx) {
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* xr = x + r * d;
+    const float* gs = go + r * 2 * d;
+    const float* gc = gs + d;
+    float* gr = gx + r * d;
+    if (VEC) {
+      for (int k = threadIdx.x * 4; k < d; k += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(xr + k);
+        const float4 a = *reinterpret_cast<const float4*>(gs + k), c = *reinterpret_cast<const float4*>(gc + k);
+        if (rescale) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+        float sn, cs;
+        float4 o;
+        sincosf(v.x, &sn, &cs); o.x = a.x * cs - c.x * sn;
+        sincosf(v.y, &sn, &cs); o.y = a.y * cs - c.y * sn;
+        sincosf(v.z, &sn, &cs); o.z = a.z * cs - c.z * sn;
+        sincosf(v.w, &sn, &cs); o.w = a.w * cs - c.w * sn;
+        if (rescale) { o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale; }
+        *reinterpret_cast<float4*>(gr + k) = o;
+      }
+    } else {
+      for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        float v = xr[k];
+        if (rescale) v *= scale;
+        float sn, cs;
+        sincosf(v, &sn, &cs);
+        float g = gs[k] * cs - gc[k] * sn;
+        if (rescale) g *= scale;
+        gr[k] = g;
+      }
+    }
   }
 }
 
@@ -176,11 +217,62 @@ __global__ void pairwise_small_kernel(const float* __restrict__ x, int64_t b, in
   }
 }
 
+// PairwiseDistances layer, forward: flat upper triangle of 3-d points, up to PWT_MAX_N selected atoms (the Calpha
+// selections of the ADC models).  One thread per output element with coalesced 4-byte stores; the pair (i, j) of
+// flat index p comes from a 16-bit table in shared memory that the CTA builds once and reuses for every frame it
+// processes (no per-element decode, no divergence).  G frames are staged per barrier pair.
+constexpr int PWF_THREADS = 256;
+constexpr int PWT_MAX_N = 181;   // i, j < 256 and a table of at most 32 KB
+
+__global__ void __launch_bounds__(PWF_THREADS) pairwise_flat3_tab_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                         int64_t rstride, int squared, int G, float* __restrict__ out) {
+  extern __shared__ float sx[];   // [G][3][n] positions, then per x uint16 pair table
+  const int per = n * (n - 1) / 2;
+  unsigned short* tab = reinterpret_cast<unsigned short*>(sx + (size_t)G * 3 * n);
+  const int tid = threadIdx.x;
+  {
+    const int nn = 2 * n - 1;
+    for (int p = tid; p < per; p += PWF_THREADS) {
+      int i = (int)(((float)nn - sqrtf((float)(nn * nn - 8 * p))) * 0.5f);
+      i = max(0, min(i, n - 2));
+      if (i * (nn - i) / 2 > p) --i;
+      if ((i + 1) * (nn - i - 1) / 2 <= p) ++i;
+      const int j = p - i * (nn - i) / 2 + i + 1;
+      tab[p] = (unsigned short)((i << 8) | j);
+    }
+  }
+  for (int64_t g0 = (int64_t)blockIdx.x * G; g0 < b; g0 += (int64_t)gridDim.x * G) {
+    const int gc = (int)min((int64_t)G, b - g0);
+    __syncthreads();
+    for (int f = 0; f < gc; f++) {
+      const float* xb = x + (g0 + f) * bstride;
+      float* sf = sx + f * 3 * n;
+      for (int idx = tid; idx < 3 * n; idx += PWF_THREADS) {
+        const int a = idx / 3, c = idx - 3 * a;
+        sf[c * n + a] = xb[a * rstride + c];
+      }
+    }
+    __syncthreads();
+    for (int f = 0; f < gc; f++) {
+      const float* sf = sx + f * 3 * n;
+      float* ob = out + (g0 + f) * per;
+#pragma unroll 4
+      for (int p = tid; p < per; p += PWF_THREADS) {
+        const unsigned ij = tab[p];
+        const int i = ij >> 8, j = ij & 255;
+        const float dx = sf[i] - sf[j], dy = sf[n + i] - sf[n + j], dz = sf[2 * n + i] - sf[2 * n + j];
+        const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        ob[p] = squared ? s2 : (s2 > 0.f ? s2 * rsqrtf(s2) : 0.f);   // sqrt as s2 * rsqrt(s2): MUFU + FMUL, 2 ulp
+      }
+    }
+  }
+}
+
 // PairwiseDistances layer, forward: flat upper triangle of 3-d points.  One CTA per frame: the selected atoms are
 // staged in shared memory (SoA), each warp walks whole rows of the triangle, lanes over j, so that the output
 // writes are contiguous runs and no per-element index decode is needed.
 constexpr int PW_THREADS = 128;
-__global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+__global__ void __launch_bounds__(PW_THREADS) pairwise_rows3_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
                                                                     int64_t rstride, int squared, float* __restrict__ out) {
   extern __shared__ float sx[];   // [3][n]
   const int64_t per = (int64_t)n * (n - 1) / 2;
@@ -364,7 +456,12 @@ int periodic_input_device(const float* x, int64_t rows, int64_t d, double P, flo
   if (rows * d == 0) return EMK_OK;
   float sc; int rs;
   periodic_scale(P, &sc, &rs);
-  periodic_input_kernel<<<grid_for(rows * d), 256, 0, st>>>(x, rows, d, sc, rs, out);
+  EMK_REQUIRE(d < (1LL << 30), EMK_E_UNSUPPORTED, "emk_periodic_input: more than 2^30 columns");
+  const bool vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int threads = (int)std::min<int64_t>(256, std::max<int64_t>(32, ((vec ? d / 4 : d) + 31) / 32 * 32));
+  const unsigned grid = (unsigned)std::min<int64_t>(rows, (int64_t)sm_count() * 32);
+  if (vec) periodic_input_kernel<true><<<grid, threads, 0, st>>>(x, rows, (int)d, sc, rs, out);
+  else periodic_input_kernel<false><<<grid, threads, 0, st>>>(x, rows, (int)d, sc, rs, out);
   return launch_status("periodic_input_kernel");
 }
 int periodic_input_bwd_device(const float* x, int64_t rows, int64_t d, double P, const float* go, float* gx, cudaStream_t st) {
@@ -373,7 +470,12 @@ int periodic_input_bwd_device(const float* x, int64_t rows, int64_t d, double P,
   if (rows * d == 0) return EMK_OK;
   float sc; int rs;
   periodic_scale(P, &sc, &rs);
-  periodic_input_bwd_kernel<<<grid_for(rows * d), 256, 0, st>>>(x, rows, d, sc, rs, go, gx);
+  EMK_REQUIRE(d < (1LL << 30), EMK_E_UNSUPPORTED, "emk_periodic_input_bwd: more than 2^30 columns");
+  const bool vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(go) | reinterpret_cast<uintptr_t>(gx)) & 15) == 0;
+  const int threads = (int)std::min<int64_t>(256, std::max<int64_t>(32, ((vec ? d / 4 : d) + 31) / 32 * 32));
+  const unsigned grid = (unsigned)std::min<int64_t>(rows, (int64_t)sm_count() * 32);
+  if (vec) periodic_input_bwd_kernel<true><<<grid, threads, 0, st>>>(x, rows, (int)d, sc, rs, go, gx);
+  else periodic_input_bwd_kernel<false><<<grid, threads, 0, st>>>(x, rows, (int)d, sc, rs, go, gx);
   return launch_status("periodic_input_bwd_kernel");
 }
 int rotation_matrix_device(const float* axis, const float* angle, int64_t b, float* out, cudaStream_t st) {
@@ -403,10 +505,20 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
   if (b * per == 0) return EMK_OK;
   if (flat && d == 3 && n >= 2 && n <= 8192) {
+    if (n <= PWT_MAX_N) {
+      const int64_t per3 = n * (n - 1) / 2;
+      const int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, 32768 / per3 + 1), b));
+      const size_t smem = (size_t)G * 3 * (size_t)n * sizeof(float) + (((size_t)per3 * 2 + 15) & ~(size_t)15);
+      static bool cfg[kMaxDevices] = {false};
+      if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      const unsigned grid = (unsigned)std::min<int64_t>((b + G - 1) / G, (int64_t)sm_count() * 8);
+      pairwise_flat3_tab_kernel<<<grid, PWF_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, G, out);
+      return launch_status("pairwise_flat3_tab_kernel");
+    }
     const size_t smem = 3 * (size_t)n * sizeof(float);
     const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);
-    pairwise_flat3_kernel<<<grid, PW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, out);
-    return launch_status("pairwise_flat3_kernel");
+    pairwise_rows3_kernel<<<grid, PW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, out);
+    return launch_status("pairwise_rows3_kernel");
   }
   const int64_t bx = std::min<int64_t>((per + 255) / 256, 1024);
   dim3 grid((unsigned)bx, (unsigned)std::min<int64_t>(b, 65535));
