@@ -229,48 +229,6 @@ __device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ s
 }
 
 // ====================================================================================================
-// chain_in_plane forward
-// ====================================================================================================
-__global__ void chain_in_plane_kernel(const float* __restrict__ lengths, int64_t lstride, const float* __restrict__ angles,
-                                      int64_t b, int n, float* __restrict__ xyz) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
-  if (frame >= b) return;
-  const int per_warp = (n - 1) + (n - 2) + 3 * n;
-  float* sL = smem + (size_t)warp * per_warp;
-  float* sA = sL + (n - 1);
-  float* sO = sA + (n - 2);
-  stage_in(sL, lengths + frame * lstride, n - 1, lane);
-  stage_in(sA, angles + frame * (int64_t)(n - 2), n - 2, lane);
-  __syncwarp();
-  const int nb = n - 1;                 // bonds
-  const int cs = (nb + 31) / 32;
-  const int k0 = lane * cs, k1 = min(nb, k0 + cs);
-  Se2 t{1.0, 0.0, 0.0, 0.0};
-  for (int k = k0; k < k1; k++) planar_step(t, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
-  Se2 ex;
-  se2_scan(t, lane, &ex);
-  Se2 run = ex;
-  if (lane == 0) {
-    sO[0] = 0.f;
-    sO[1] = 0.f;
-    sO[2] = 0.f;
-  }
-  for (int k = k0; k < k1; k++) {
-    Se2 step{1.0, 0.0, 0.0, 0.0};
-    planar_step(step, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
-    run = se2_mul(run, step);
-    sO[3 * (k + 1)] = (float)run.x;
-    sO[3 * (k + 1) + 1] = (float)run.y;
-    sO[3 * (k + 1) + 2] = 0.f;
-  }
-  __syncwarp();
-  float* dst = xyz + frame * (int64_t)(3 * n);
-  for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
-}
-
-// ====================================================================================================
 // sin/cos of a float32 argument in float64, by table: float32 Cody-Waite reduction to |r| <= pi/1024 (the first two
 // steps are exact), float32 two-term corrections, a float64 table entry and 4 DFMA -- 2.3e-10 absolute error with 4
 // FP64 instructions instead of ~30.  The 1024-entry table lives in global memory (backward kernels); the forward
@@ -304,6 +262,62 @@ __device__ __forceinline__ void sincos_tab(float x, const double2* __restrict__ 
   const double2 t = __ldg(tab + (__float_as_int(km) & (SC_TABLE - 1)));
   *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
   *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
+}
+
+// planar bond k with the table sin/cos (same step as planar_step)
+__device__ __forceinline__ void planar_step_tab(Se2& t, double L, bool has_turn, float theta, int k, const double2* __restrict__ tab) {
+  t.x = fma(L, t.c, t.x);
+  t.y = fma(L, t.s, t.y);
+  if (has_turn) {
+    double st, ct;
+    sincos_tab(theta, tab, &st, &ct);
+    const double cw = -ct, sw = (k & 1) ? st : -st;
+    const double c2 = t.c * cw - t.s * sw, s2 = t.c * sw + t.s * cw;
+    t.c = c2;
+    t.s = s2;
+  }
+}
+
+// ====================================================================================================
+// chain_in_plane forward
+// ====================================================================================================
+__global__ void chain_in_plane_kernel(const float* __restrict__ lengths, int64_t lstride, const float* __restrict__ angles,
+                                      int64_t b, int n, float* __restrict__ xyz, const double2* __restrict__ tab) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
+  if (frame >= b) return;
+  const int per_warp = (n - 1) + (n - 2) + 3 * n;
+  float* sL = smem + (size_t)warp * per_warp;
+  float* sA = sL + (n - 1);
+  float* sO = sA + (n - 2);
+  stage_in(sL, lengths + frame * lstride, n - 1, lane);
+  stage_in(sA, angles + frame * (int64_t)(n - 2), n - 2, lane);
+  __syncwarp();
+  const int nb = n - 1;                 // bonds
+  const int cs = (nb + 31) / 32;
+  const int k0 = lane * cs, k1 = min(nb, k0 + cs);
+  Se2 t{1.0, 0.0, 0.0, 0.0};
+  for (int k = k0; k < k1; k++) planar_step_tab(t, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k, tab);
+  Se2 ex;
+  se2_scan(t, lane, &ex);
+  Se2 run = ex;
+  if (lane == 0) {
+    sO[0] = 0.f;
+    sO[1] = 0.f;
+    sO[2] = 0.f;
+  }
+  for (int k = k0; k < k1; k++) {
+    Se2 step{1.0, 0.0, 0.0, 0.0};
+    planar_step_tab(step, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k, tab);
+    run = se2_mul(run, step);
+    sO[3 * (k + 1)] = (float)run.x;
+    sO[3 * (k + 1) + 1] = (float)run.y;
+    sO[3 * (k + 1) + 2] = 0.f;
+  }
+  __syncwarp();
+  float* dst = xyz + frame * (int64_t)(3 * n);
+  for (int i = lane; i < 3 * n; i += 32) dst[i] = sO[i];
 }
 
 // ====================================================================================================
@@ -348,6 +362,26 @@ __device__ __forceinline__ void sincos_tab256(float x, const double2* tabS, doub
   *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
 }
 
+// both table sin/cos of one NeRF step at once: the float32 argument reduction and the two short polynomials run as
+// packed FP32x2 instructions (FFMA2 / FMUL2 / FADD2), one lane of the pair per angle -- 10 issue slots instead of 20
+__device__ __forceinline__ void sincos_tab256_x2(float xa, float xb, const double2* tabS, double* sa, double* ca, double* sb, double* cb) {
+  const float2 x = make_float2(xa, xb);
+  const float2 km = __ffma2_rn(x, make_float2(40.74366543152521f, 40.74366543152521f), make_float2(12582912.f, 12582912.f));
+  const float2 kf = __fadd2_rn(km, make_float2(-12582912.f, -12582912.f));
+  float2 r = __ffma2_rn(kf, make_float2(-0.0245361328125f, -0.0245361328125f), x);
+  r = __ffma2_rn(kf, make_float2(-7.558614015579224e-06f, -7.558614015579224e-06f), r);
+  r = __ffma2_rn(kf, make_float2(-1.1796547072506768e-09f, -1.1796547072506768e-09f), r);
+  const float2 r2 = __fmul2_rn(r, r);
+  const float2 sr = __ffma2_rn(__fmul2_rn(r, r2), make_float2(-0.16666667f, -0.16666667f), r);
+  const float2 cm = __fmul2_rn(r2, __ffma2_rn(r2, make_float2(0.041666668f, 0.041666668f), make_float2(-0.5f, -0.5f)));
+  const double2 ta = tabS[__float_as_int(km.x) & (SC_SMALL - 1)];
+  const double2 tb = tabS[__float_as_int(km.y) & (SC_SMALL - 1)];
+  *sa = fma(ta.x, (double)cm.x, fma(ta.y, (double)sr.x, ta.x));
+  *ca = fma(ta.y, (double)cm.x, fma(-ta.x, (double)sr.x, ta.y));
+  *sb = fma(tb.x, (double)cm.y, fma(tb.y, (double)sr.y, tb.x));
+  *cb = fma(tb.y, (double)cm.y, fma(-tb.x, (double)sr.y, tb.y));
+}
+
 template <bool LEFT, bool SLOW>
 __device__ __forceinline__ void fwd5_step(float* pT, int& kpar, const double2* tabS, Se3& f, Se2& pl, float& amax) {
   const float fd = pT[0], fa = pT[1], fl = pT[2];
@@ -357,8 +391,7 @@ __device__ __forceinline__ void fwd5_step(float* pT, int& kpar, const double2* t
     sincos_d((double)fa, &sg, &cg);
   } else {
     amax = fmaxf(amax, fmaxf(fabsf(fd), fabsf(fa)));
-    sincos_tab256(fd, tabS, &sw, &cw);
-    sincos_tab256(fa, tabS, &sg, &cg);
+    sincos_tab256_x2(fd, fa, tabS, &sw, &cw, &sg, &cg);
   }
   const double L = (double)fl;
   nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
@@ -568,7 +601,7 @@ __device__ __forceinline__ void load3(const float* p, double* v) {
 }
 
 __global__ void d2c_general_kernel(const float* __restrict__ dihedrals, const float* __restrict__ chain, int64_t cstride,
-                                   int64_t b, int n, int one_way, float* __restrict__ xyz) {
+                                   int64_t b, int n, int one_way, float* __restrict__ xyz, const double2* __restrict__ tab) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int64_t frame = (int64_t)blockIdx.x * wpc + warp;
@@ -609,7 +642,7 @@ __global__ void d2c_general_kernel(const float* __restrict__ dihedrals, const fl
     const double inv = rsqrt(ux * ux + uy * uy + uz * uz);
     ux *= inv; uy *= inv; uz *= inv;
     double sw, cw;
-    sincos_d((double)sD[d0 + dir * i], &sw, &cw);
+    sincos_tab(sD[d0 + dir * i], tab, &sw, &cw);
     const double oc = 1.0 - cw;
     Se3 a;
     a.r[0] = cw + oc * ux * ux;      a.r[1] = oc * ux * uy - sw * uz; a.r[2] = oc * ux * uz + sw * uy;
@@ -772,7 +805,7 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     const int k0 = min(n, t * BWD_CA), k1 = min(n, k0 + BWD_CA);
     Se2 part{1.0, 0.0, 0.0, 0.0};
     if (active)
-      for (int k = k0; k < k1 && k < n - 1; k++) planar_step(part, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+      for (int k = k0; k < k1 && k < n - 1; k++) planar_step_tab(part, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k, tab);
     Se2 inc = part;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -789,7 +822,7 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     if (active) {
       if (t == 0) { sX[0] = 0.f; sX[1] = 0.f; sX[2] = 0.f; }
       for (int k = k0; k < k1 && k < n - 1; k++) {
-        planar_step(run, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k);
+        planar_step_tab(run, (double)sL[k], k < n - 2, k < n - 2 ? sA[k] : 0.f, k, tab);
         sX[3 * (k + 1)] = (float)run.x; sX[3 * (k + 1) + 1] = (float)run.y; sX[3 * (k + 1) + 2] = 0.f;
       }
     }
@@ -1061,7 +1094,10 @@ int chain_in_plane_device(const float* lengths, int64_t lstride, const float* an
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) { rc = set_smem(chain_in_plane_kernel, smem); if (rc) return rc; }
   const int64_t blocks = (b + warps - 1) / warps;
-  chain_in_plane_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(lengths, lstride, angles, b, (int)n, xyz);
+  const double2* tab;
+  rc = get_sincos_table(&tab);
+  if (rc) return rc;
+  chain_in_plane_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(lengths, lstride, angles, b, (int)n, xyz, tab);
   return launch_status("chain_in_plane_kernel");
 }
 
@@ -1078,7 +1114,10 @@ int d2c_general_device(const float* dihedrals, const float* chain, int64_t cstri
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) { rc = set_smem(d2c_general_kernel, smem); if (rc) return rc; }
   const int64_t blocks = (b + warps - 1) / warps;
-  d2c_general_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(dihedrals, chain, cstride, b, (int)n, one_way, xyz);
+  const double2* tab;
+  rc = get_sincos_table(&tab);
+  if (rc) return rc;
+  d2c_general_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(dihedrals, chain, cstride, b, (int)n, one_way, xyz, tab);
   return launch_status("d2c_general_kernel");
 }
 

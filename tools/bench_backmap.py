@@ -79,3 +79,37 @@ def autograd_path(n=1500, b=32768, reps=4):
 
 
 autograd_path()
+
+
+def standalone(n=1500, b=32768, reps=5):
+    """chain_in_plane and dihedrals_to_cartesian on an explicit start chain (the ops the reference's eager code and tests call)."""
+    from encodermap_b200.encodermap_tf1 import chain_in_plane, dihedrals_to_cartesian_tf
+
+    g = torch.Generator(device=dev).manual_seed(2)
+    lengths = (0.13 + 0.02 * torch.rand(1, n - 1, device=dev, generator=g)).contiguous()
+    ang = (1.9 + 0.3 * torch.rand(b, n - 2, device=dev, generator=g))
+    dih = ((torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    with torch.no_grad():
+        t_chain = timeit(lambda: chain_in_plane(lengths, ang))
+        chain = chain_in_plane(lengths, ang)
+        t_d2c = timeit(lambda: dihedrals_to_cartesian_tf(dih, chain))
+    bc = 4 * (n - 2) + 12 * n
+    bd = 4 * (n - 3) + 24 * n
+    print(f"standalone n={n} b={b}: chain_in_plane {t_chain:.3f} ms {b * bc / t_chain / 1e6 / HBM:.3f} of HBM | "
+          f"dihedrals_to_cartesian {t_d2c:.3f} ms {b * bd / t_d2c / 1e6 / HBM:.3f} of HBM")
+
+
+standalone()
+standalone(300, 65536)
