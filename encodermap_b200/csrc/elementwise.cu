@@ -363,6 +363,102 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_bwd_kernel(const fl
   }
 }
 
+// PairwiseDistances layer, backward, up to 32 * C selected atoms: every pair is visited ONCE.  A warp walks whole rows
+// i of the triangle with its lanes on FIXED columns j = 32 c + lane, so that (a) the upstream gradient of a row is
+// read straight from global memory in contiguous runs (no staging), (b) x_j and the column sums sum_i -coef_ij d_ij
+// live in registers, (c) the row sum sum_j coef_ij d_ij is one shuffle reduction per row.  The four warps' column
+// sums and the row sums meet in shared memory.  (The thread-per-atom version visited every pair twice and read the
+// row part of g with a stride of ~n floats between lanes: 0.09 of the HBM roofline at 300 atoms.)
+template <int C>
+__global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_bwd_cols_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                             int64_t rstride, int squared, const float* __restrict__ go,
+                                                                             float* __restrict__ gx) {
+  extern __shared__ float sm[];
+  float* xs = sm;                 // [3][n]
+  float* racc = sm + 3 * n;       // [3][n] row sums
+  float* cacc = sm + 6 * n;       // [4][3][n] column sums per warp
+  const int per = n * (n - 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t bi = blockIdx.x; bi < b; bi += gridDim.x) {
+    const float* xb = x + bi * bstride;
+    const float* g = go + bi * per;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 3 * n; idx += PW_THREADS) {
+      const int a = idx / 3, c = idx - 3 * a;
+      xs[c * n + a] = xb[a * rstride + c];
+    }
+    if (threadIdx.x < 3) racc[threadIdx.x * n + n - 1] = 0.f;   // the last atom has no row
+    __syncthreads();
+    float xj[C][3], ca[C][3];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const int j = 32 * c + lane;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        xj[c][k] = j < n ? xs[k * n + j] : 0.f;
+        ca[c][k] = 0.f;
+      }
+    }
+    // the upstream gradient of the NEXT row of this warp is in flight while the current row is processed (one row is
+    // a dependent chain of global latency + shuffle reduction otherwise)
+    float gcur[C], gnxt[C];
+    auto load_row = [&](int i, float* dstv) {
+      const float* grow = g + i * (2 * n - i - 1) / 2 - i - 1;   // + j
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int j = 32 * c + lane;
+        dstv[c] = (i < n - 1 && j > i && j < n) ? __ldg(grow + j) : 0.f;
+      }
+    };
+    load_row(warp, gcur);
+    for (int i = warp; i < n - 1; i += PW_THREADS / 32) {
+      load_row(i + PW_THREADS / 32, gnxt);
+      const float xi = xs[i], yi = xs[n + i], zi = xs[2 * n + i];
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int j = 32 * c + lane;
+        if (j > i && j < n) {
+          const float gij = gcur[c];
+          const float dx = xi - xj[c][0], dy = yi - xj[c][1], dz = zi - xj[c][2];
+          const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+          const float coef = squared ? 2.f * gij : (s2 > 0.f ? gij * rsqrtf(s2) : 0.f);
+          r0 = fmaf(coef, dx, r0); r1 = fmaf(coef, dy, r1); r2 = fmaf(coef, dz, r2);
+          ca[c][0] = fmaf(-coef, dx, ca[c][0]); ca[c][1] = fmaf(-coef, dy, ca[c][1]); ca[c][2] = fmaf(-coef, dz, ca[c][2]);
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, d);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, d);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, d);
+      }
+      if (lane == 0) { racc[i] = r0; racc[n + i] = r1; racc[2 * n + i] = r2; }
+#pragma unroll
+      for (int c = 0; c < C; c++) gcur[c] = gnxt[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const int j = 32 * c + lane;
+      if (j < n) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) cacc[(warp * 3 + k) * n + j] = ca[c][k];
+      }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += PW_THREADS) {
+      float* o = gx + bi * bstride + (int64_t)a * rstride;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float v = racc[k * n + a];
+#pragma unroll
+        for (int w = 0; w < PW_THREADS / 32; w++) v += cacc[(w * 3 + k) * n + a];
+        o[k] = v;
+      }
+    }
+  }
+}
+
 // one thread per (frame, atom i): grad_x[i] = sum_j coef_ij (x_i - x_j); coef = g/dist (or 2g when squared).
 // Threads of a warp own consecutive atoms of one frame: x_j is a broadcast read, g[pair(j,i)] for j < i is
 // contiguous across the warp; the running flat offsets avoid any per-pair index arithmetic.
@@ -528,6 +624,18 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
 int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
                               int flat, const float* go, float* gx, cudaStream_t st) {
   if (b * n == 0) return EMK_OK;
+  // 129 .. 320 atoms: pair-once kernel (2.5x the thread-per-atom kernel at 300 atoms); up to 128 atoms the whole
+  // upstream gradient of a frame fits in shared memory next to the coordinates and the thread-per-atom kernel is as fast
+  if (flat && d == 3 && n > 128 && n <= 320) {
+    const size_t smem = 18 * (size_t)n * sizeof(float);
+    const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);
+#define EMK_PWB(CC) pairwise_flat3_bwd_cols_kernel<CC><<<grid, PW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, go, gx)
+    if (n <= 192) EMK_PWB(6);
+    else if (n <= 256) EMK_PWB(8);
+    else EMK_PWB(10);
+#undef EMK_PWB
+    return launch_status("pairwise_flat3_bwd_cols_kernel");
+  }
   if (flat && d == 3 && n >= 2 && n <= 8192) {
     const size_t sx = ((3 * (size_t)n + 3) & ~(size_t)3) * sizeof(float);
     const size_t sg = (size_t)n * (n - 1) / 2 * sizeof(float);
