@@ -16,7 +16,10 @@ value   : inputs resident in HBM, device-timed (CUDA events, max over ranks)
 e2e     : same through the public API (`sigmoid_loss(...)(y_true, y_pred)` + backward) with HOST pinned
           buffers: H2D of both inputs and D2H of loss and gradient inside the timed region
 roofline: the pair-tile kernel against the FP32 issue roofline of SURVEY.md section 8d
-          (4 lane-instructions per (pair, dim) + 60 per pair;  148 SM x 128 lanes x sm_max clock)
+          (4 lane-instructions per (pair, dim) + 60 per pair;  peak = 148 SM x 128 lanes x sm_max clock from
+          MEASURED_PEAKS.json, peak_measured = FFMA rate probed live on the device; the kernel is neither
+          HBM- nor tensor-bound, so "bound" says "fp32-issue"; the HBM-bound back-mapping kernels carry their
+          own rooflines under "extra")
 cpu_baseline / --impl reference: the op-for-op float32 torch-CPU restatement of the reference (oracle/),
           all host threads, on a bounded sample (N=512 rows of the same data) -- TensorFlow is not installed
           in this image, so the reference itself cannot be run.
@@ -271,6 +274,16 @@ def run_ours(args):
         lane_instr = pairs * (4 * N_DIMS + 60)
         peak = 148 * 128 * peaks["sm_max_mhz"] * 1e6
         achieved = (lane_instr / world) / (kernel_ms * 1e-3)
+        # measured FP32 denominator: register-only FFMA chains on this device, right now (emk_probe_fp32)
+        import ctypes
+
+        probe = ctypes.c_double(0.0)
+        _lib.check(L.emk_probe_fp32(ctypes.byref(probe)))
+        # DRAM bytes of one launch from the committed ncu capture of this kernel (profiles/, tools/profile_r1.sh)
+        traffic = None
+        tp = ROOT / "profiles" / "r01_pair_tile_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         cpu_v, cpu_t, cores = (None, None, None)
         cpu_baseline = None
         if world == 1 and not args.no_cpu:
@@ -286,7 +299,9 @@ def run_ours(args):
                        "ordered_pairs_per_s": value * 2 * N_ROWS / (N_ROWS + 1), "l2": "inputs (268 MB) larger than L2 (126 MB); no flush needed",
                        "parallelism": f"tile-shard x{world}", "loss": loss_value},
             "roofline": {"bound": "fp32-issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-instr/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "peak_measured": probe.value / 1e12, "frac_of_measured": achieved / probe.value if probe.value else None,
+                         "peak_measured_how": "emk_probe_fp32: register-only FFMA chains, 8 CTAs x 256 threads per SM, best of 3, CUDA events",
                          "kernel": "pair_tile_kernel<periodic,cost>", "kernel_ms": kernel_ms,
                          "algorithmic": "4 FP32 lane-instr per (unique pair, dim) + 60 per unique pair (SURVEY.md 8d); per GPU = total / n_gpus",
                          "peak_source": f"148 SM x 128 lanes x {peaks['sm_max_mhz']} MHz ({peaks['source']}); no FP32 figure is measured there"},

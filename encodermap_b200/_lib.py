@@ -44,6 +44,7 @@ SIGNATURES = {
     "emk_version": ([], C.c_int),
     "emk_last_error": ([], C.c_char_p),
     "emk_build_info": ([], C.c_char_p),
+    "emk_probe_fp32": ([C.POINTER(C.c_double)], C.c_int),
     "emk_triu_pair_count": ([i64], i64),
     "emk_triu_pair_indices": ([i64, c_i32p, c_i32p], C.c_int),
     "emk_backmap_split_counts": ([i64, c_i64p], C.c_int),

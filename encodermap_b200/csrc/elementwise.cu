@@ -14,6 +14,53 @@ static inline int grid_for(int64_t work, int threads = 256) {
   return (int)blocks;
 }
 
+// ---- FP32 pipe probe ---------------------------------------------------------------------------------
+// Measured denominator of the pair-tile kernel's roofline: register-only FFMA chains (16 independent accumulators
+// per thread, 8 CTAs of 256 threads per SM), i.e. what the FP32 pipe of this very device issues per second when
+// nothing else is in the way.  Used by bench.py; not part of the hot path.
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* __restrict__ sink, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int i = 0; i < 16; i++) acc[i] = fmaf(acc[i], a, b);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) sum += acc[i];
+  if (sum == 12345.678f) sink[0] = sum;   // never true: keeps the chains alive
+}
+int fp32_probe_device(double* lane_instr_per_s) {
+  EMK_REQUIRE(lane_instr_per_s, EMK_E_NULL, "emk_probe_fp32: NULL output");
+  float* sink = nullptr;
+  EMK_CUDA(cudaMalloc(&sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  EMK_CUDA(cudaEventCreate(&e0));
+  EMK_CUDA(cudaEventCreate(&e1));
+  const int iters = 1 << 14, blocks = sm_count() * 8;
+  fp32_probe_kernel<<<blocks, 256>>>(sink, 256, 0.999f, 0.001f);   // warm-up
+  double best = 0.0;
+  int rc = launch_status("fp32_probe_kernel");
+  for (int rep = 0; rep < 3 && rc == EMK_OK; rep++) {
+    cudaEventRecord(e0);
+    fp32_probe_kernel<<<blocks, 256>>>(sink, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { rc = fail(EMK_E_ARG, "emk_probe_fp32: kernel failed"); break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double)blocks * 256.0 * (double)iters * 64.0 / (ms * 1e-3);
+    if (rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *lane_instr_per_s = best;
+  return rc;
+}
+
 // ---- periodic_distance -----------------------------------------------------------------------------
 __global__ void periodic_distance_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count, float P,
                                          float* __restrict__ out) {

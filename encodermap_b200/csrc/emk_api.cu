@@ -68,6 +68,7 @@ int column_mean_device(const float*, int64_t, int64_t, float*, cudaStream_t);
 int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float*, cudaStream_t);
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
 int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
+int fp32_probe_device(double*);
 int chain_in_plane_device(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 int d2c_general_device(const float*, const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
 int backmap_bwd_device(const BwdParams&, cudaStream_t);
@@ -160,6 +161,8 @@ const char* emk_build_info(void) {
   snprintf(info, sizeof(info), "sm_100a;nvcc %d.%d;%s", __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, __DATE__);
   return info;
 }
+
+int emk_probe_fp32(double* lane_instr_per_s) { return fp32_probe_device(lane_instr_per_s); }
 
 // ---- host-only index construction --------------------------------------------------------------------------
 int64_t emk_triu_pair_count(int64_t n) { return n < 2 ? 0 : n * (n - 1) / 2; }

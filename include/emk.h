@@ -55,6 +55,9 @@ EMK_API int emk_version(void);
 EMK_API const char* emk_last_error(void);
 /* "sm_100a;<nvcc version>;<build date>" */
 EMK_API const char* emk_build_info(void);
+/* Measurement aid (bench.py): FP32 FMA lane-instructions per second this device sustains on register-only FFMA
+ * chains -- the measured denominator of the pair-tile kernel's FP32-issue roofline.  Synchronises the device. */
+EMK_API int emk_probe_fp32(double* lane_instr_per_s);
 
 /* ------------------------------------------------------------------------------------------
  * Host-only index construction (integer work: bit-exact contracts; no GPU needed)
