@@ -397,3 +397,29 @@ def dihedral_of(p0, p1, p2, p3):
     y = torch.sum(b1 * c1, dim=-1) * torch.linalg.norm(b2, dim=-1)
     x = torch.sum(c1 * c2, dim=-1)
     return torch.atan2(y, x)
+
+
+def dihedral_vjp_from_xyz(xyz, grad_xyz):
+    """Closed form of d<grad_xyz, BackMapLayer(...)>/d(dihedrals), float64, evaluated ON THE GIVEN coordinates
+    (test infrastructure for chains where float32 coordinates limit what any backward can know: at 60 nm from the
+    origin a float32 coordinate carries 4e-6 nm of rounding, 3e-5 relative on a 0.14 nm bond vector).
+    Dihedral d twists the end of the chain that does not hold the three middle atoms (reference
+    misc/backmapping.py:259-309: the middle atoms keep their planar positions) about its bond:
+    left of the anchor (d < n/2 - 1) atoms 0..d about the bond (d+1, d+2), else atoms d+3.. about the bond (d+1, d+2).
+    Checked against float64 autograd of back_map_layer to 1e-11 (tests/test_oracle_kats.py)."""
+    x = np.asarray(xyz, dtype=np.float64)
+    g = np.asarray(grad_xyz, dtype=np.float64)
+    n = x.shape[-2]
+    dr0 = n // 2 - 1
+    out = np.zeros(x.shape[:-2] + (n - 3,))
+    for d in range(n - 3):
+        if d < dr0:
+            tq = np.cross(x[..., : d + 1, :] - x[..., d + 1 : d + 2, :], g[..., : d + 1, :]).sum(-2)
+            u = x[..., d + 2, :] - x[..., d + 1, :]
+            out[..., d] = -(u * tq).sum(-1) / np.linalg.norm(u, axis=-1)
+        else:
+            k = d + 2
+            tq = np.cross(x[..., k + 1 :, :] - x[..., k : k + 1, :], g[..., k + 1 :, :]).sum(-2)
+            u = x[..., k, :] - x[..., k - 1, :]
+            out[..., d] = (u * tq).sum(-1) / np.linalg.norm(u, axis=-1)
+    return out

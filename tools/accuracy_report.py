@@ -40,3 +40,27 @@ for n, d in ((256, 51), (1024, 256)):
     rel = lambda a, b: np.linalg.norm(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) / np.linalg.norm(np.asarray(b, dtype=np.float64))  # noqa: E731
     print(f"{n:6d} {d:5d} {abs(lo.item() - l64.item()) / l64.item():10.2e} {abs(l32.item() - l64.item()) / l64.item():10.2e} "
           f"{rel(go.cpu().numpy(), g64.numpy()):10.2e} {rel(g32.numpy(), g64.numpy()):10.2e}")
+
+print("\nback-mapping gradients d<w,xyz>/d(dihedrals), d/d(angles): norm-wise relative error vs float64 autograd of the restated")
+print("reference; 'floor' = exact float64 VJP evaluated on float32-rounded coordinates (what any backward fed float32 xyz can know);")
+print("'ref32' = float32 autograd of the reference's own op order")
+print(f"{'atoms':>6} {'dih ours':>10} {'dih floor':>10} {'dih ref32':>10} {'ang ours':>10} {'ang ref32':>10}")
+rel = lambda a, b: np.linalg.norm(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) / np.linalg.norm(np.asarray(b, dtype=np.float64))  # noqa: E731
+for n, b in ((300, 4), (1500, 2)):
+    rng = np.random.default_rng(100 + n)
+    dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+    w = rng.normal(size=(b, n, 3))
+    res = {}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        a = torch.from_numpy(ang).to(dt).requires_grad_(True)
+        h = torch.from_numpy(dih).to(dt).requires_grad_(True)
+        x = O.back_map_layer(torch.from_numpy(dist).to(dt), a, h)
+        (x * torch.from_numpy(w).to(dt)).sum().backward()
+        res[tag] = (a.grad.double().numpy(), h.grad.double().numpy(), x.detach().double().numpy())
+    ag, hg = (torch.from_numpy(v).to(dev).requires_grad_(True) for v in (ang, dih))
+    (back_map(torch.from_numpy(dist).to(dev), ag, hg) * torch.from_numpy(w).to(dev, torch.float32)).sum().backward()
+    floor = O.dihedral_vjp_from_xyz(res["f64"][2].astype(np.float32), w)
+    print(f"{n:6d} {rel(hg.grad.cpu().numpy(), res['f64'][1]):10.2e} {rel(floor, res['f64'][1]):10.2e} {rel(res['f32'][1], res['f64'][1]):10.2e} "
+          f"{rel(ag.grad.cpu().numpy(), res['f64'][0]):10.2e} {rel(res['f32'][0], res['f64'][0]):10.2e}")
