@@ -632,7 +632,10 @@ int column_mean_device(const float* x, int64_t rows, int64_t cols, float* out, c
   EMK_REQUIRE(rows >= 1 && cols >= 1, EMK_E_SHAPE, "emk_column_mean: need rows, cols >= 1");
   const int split = (int)min((int64_t)CM_SPLIT, (rows + 255) / 256);
   double* part = nullptr;
-  EMK_CUDA(cudaMallocAsync(&part, (size_t)split * cols * sizeof(double), st));
+  {
+    int rc0 = scratch_alloc(reinterpret_cast<void**>(&part), (size_t)split * cols * sizeof(double), st);
+    if (rc0) return rc0;
+  }
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)split);
   column_partial_kernel<<<grid, 256, 0, st>>>(x, rows, cols, part);
   int rc = launch_status("column_partial_kernel");

@@ -35,6 +35,8 @@ inline int launch_status(const char* what) {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();
+// stream-ordered scratch from a private per-device pool that keeps its memory (release with cudaFreeAsync)
+int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st);
 
 // one-time per-device kernel configuration (cudaFuncSetAttribute is per device): returns true exactly once
 // per (call site, device); call sites pass their own static flag array

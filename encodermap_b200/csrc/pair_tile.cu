@@ -135,7 +135,150 @@ __host__ __device__ inline void tile_decode(int64_t t, int64_t tc, int64_t tr, i
   }
 }
 
-template <bool PERIODIC, Epi EPI>
+// ---- cost epilogue of NI row groups (rows ty + 16 (i0 + i)) x 4 column groups of this thread ------------------
+// NI = 8: the whole micro-tile (no cluster); NI = 8 / S: this CTA's share after the reduce-scatter over a cluster.
+template <int NI>
+__device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const int i0, const PairParams& p, const float* zA,
+                                              const float* zB, float* colsum, double* red_d, const int64_t row0,
+                                              const int64_t col0, const bool diag, const int ty, const int tx, const int tid,
+                                              const int lane, const int warp) {
+  // low-d squared distances, summed in the SAME order as the main loop sums the high-d ones (even
+  // components in one fused chain, odd components in the other, then one add): identical inputs and
+  // sigmoids on both sides then cancel exactly, as they do in the reference (tests/test_losses.py:897-904)
+  float dl2[NI][4];
+#pragma unroll
+  for (int i = 0; i < NI; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) dl2[i][j] = 0.f;
+#pragma unroll 1
+  for (int par = 0; par < 2; par++) {
+    float part[NI][4];
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) part[i][j] = 0.f;
+#pragma unroll 1
+    for (int c = par; c < p.l; c += 2) {
+      float za[NI], zb[4];
+#pragma unroll
+      for (int i = 0; i < NI; i++) za[i] = zA[c * TM + ty + 16 * (i0 + i)];
+#pragma unroll
+      for (int j = 0; j < 4; j++) zb[j] = zB[c * TN + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < NI; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float t = za[i] - zb[j];
+          part[i][j] = fmaf(t, t, part[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dl2[i][j] += part[i][j];
+  }
+
+  float lsum = 0.f;
+  // after this loop dl2 holds the gradient coefficient (s_l - s_h) * s_l'(d_l) / d_l
+#pragma unroll
+  for (int i = 0; i < NI; i++) {
+    const bool rv = row0 + ty + 16 * (i0 + i) < p.n;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const bool valid = rv && (col0 + tx + 16 * j < p.n);
+      const float sh = sig_eval<false>(d2h[i][j], p.sh, nullptr);
+      float w;
+      const float sl = sig_eval<true>(dl2[i][j], p.sl, &w);
+      float diff = sh - sl;
+      if (!valid) diff = 0.f;
+      if (dl2[i][j] == 0.f || !valid) w = 0.f;
+      lsum = fmaf(diff, diff, lsum);
+      dl2[i][j] = -diff * w;
+    }
+  }
+
+  // loss: per-thread float (<= 32 terms) -> double across the CTA
+  double ld = (double)lsum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+  if (lane == 0) red_d[warp] = ld;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < NTHREADS / 32; w++) t += red_d[w];
+    atomicAdd(p.loss, t * (diag ? 1.0 : 2.0) * p.loss_scale);
+  }
+
+  if (p.grad == nullptr) return;
+  const float gs = p.grad_scale;
+#pragma unroll 1
+  for (int c = 0; c < p.l; c++) {
+    float za[NI], zb[4], rs[NI], cs[4];
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+      za[i] = zA[c * TM + ty + 16 * (i0 + i)];
+      rs[i] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      zb[j] = zB[c * TN + tx + 16 * j];
+      cs[j] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float t = dl2[i][j] * (za[i] - zb[j]);
+        rs[i] += t;
+        cs[j] -= t;
+      }
+    // row side: the 16 lanes of a half-warp share ty
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+      const int64_t r = row0 + ty + 16 * (i0 + i);
+      if (tx == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c], rs[i] * gs);
+    }
+    // column side (mirror image of the tile); diagonal tiles already visit both orders
+    if (!diag) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
+      }
+    }
+  }
+  if (!diag) {
+    __syncthreads();
+    for (int idx = tid; idx < p.l * TN; idx += NTHREADS) {
+      const int c = idx / TN, r = idx - c * TN;
+      if (col0 + r < p.n) atomicAdd(&p.grad[(col0 + r) * p.l + c], colsum[idx] * gs);
+    }
+  }
+}
+
+// this CTA's share of the cluster's partial sums: row groups [i0, i0 + NI) summed over all ranks through DSMEM
+template <int NI>
+__device__ __forceinline__ void cluster_reduce_scatter(cooperative_groups::cluster_group& cluster, float* part, const int S, const int i0,
+                                                       const int tid, float (&out)[NI][4]) {
+#pragma unroll
+  for (int i = 0; i < NI; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[i][j] = 0.f;
+  for (int r = 0; r < S; r++) {
+    const float* peer = cluster.map_shared_rank(part, r);
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) out[i][j] += peer[((i0 + i) * 4 + j) * NTHREADS + tid];
+  }
+}
+
+// CLUSTERED = false: one CTA per tile (large problems; none of the cluster code is compiled in -- the extra epilogue
+// variants cost the big kernel 3 % when they shared one instantiation)
+template <bool PERIODIC, Epi EPI, bool CLUSTERED>
 __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
@@ -156,8 +299,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
   // cluster: the S CTAs of a cluster own the same tile and S interleaved shares of the k-chunks; partial squared
   // distances are summed into rank 0 through distributed shared memory, rank 0 runs the epilogue.
   cg::cluster_group cluster = cg::this_cluster();
-  const int S = (int)cluster.num_blocks();
-  const int crank = (int)cluster.block_rank();
+  const int S = CLUSTERED ? (int)cluster.num_blocks() : 1;
+  const int crank = CLUSTERED ? (int)cluster.block_rank() : 0;
   int64_t I, J;
   tile_decode(p.tile_begin + blockIdx.x / S, p.tiles_per_row, p.tile_rows, &I, &J);
   const int64_t row0 = I * TM;
@@ -243,8 +386,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
     }
   }
 
-  if (S > 1) {
-    // partial sums -> own shared memory ([value][thread], conflict-free), then rank 0 gathers over DSMEM
+  if (CLUSTERED && S > 1) {
+    // partial sums -> own shared memory ([value][thread], conflict-free)
     __syncthreads();   // all TMA data of this CTA has been consumed: the stage buffers are free
     float* part = stage_base;
 #pragma unroll
@@ -252,17 +395,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < 4; j++) part[(i * 4 + j) * NTHREADS + tid] = acc[i][j].x + acc[i][j].y;
     cluster.sync();
-    if (crank == 0) {
-      for (int r = 1; r < S; r++) {
-        const float* peer = cluster.map_shared_rank(part, r);
+    if (EPI == Epi::kDistMatrix) {
+      // distance matrices: rank 0 gathers over DSMEM and writes the tile
+      if (crank == 0) {
+        for (int r = 1; r < S; r++) {
+          const float* peer = cluster.map_shared_rank(part, r);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+          for (int i = 0; i < 8; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) acc[i][j].x += peer[(i * 4 + j) * NTHREADS + tid];
+            for (int j = 0; j < 4; j++) acc[i][j].x += peer[(i * 4 + j) * NTHREADS + tid];
+        }
       }
+      cluster.sync();    // peers stay resident until rank 0 has read their partials
+      if (crank != 0) return;
     }
-    cluster.sync();    // peers stay resident until rank 0 has read their partials
-    if (crank != 0) return;
+    // cost: reduce-scatter below -- every rank sums and finishes 8/S of the 8 row groups, so the epilogue (sigmoids,
+    // gradient reductions, atomics) is spread over the cluster instead of idling S-1 CTAs behind rank 0
   }
 
   // ------------------------------------------------------------------------------------------
@@ -291,126 +439,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
   }
 
   // ---- cost epilogue --------------------------------------------------------------------------
-  float d2h[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) d2h[i][j] = acc[i][j].x + acc[i][j].y;
-
-  // low-d squared distances, summed in the SAME order as the main loop sums the high-d ones (even
-  // components in one fused chain, odd components in the other, then one add): identical inputs and
-  // sigmoids on both sides then cancel exactly, as they do in the reference (tests/test_losses.py:897-904)
-  float dl2[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) dl2[i][j] = 0.f;
-#pragma unroll 1
-  for (int par = 0; par < 2; par++) {
-    float part[8][4];
+  if (!CLUSTERED || S == 1) {
+    float d2h[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) part[i][j] = 0.f;
-#pragma unroll 1
-    for (int c = par; c < p.l; c += 2) {
-      float za[8], zb[4];
-#pragma unroll
-      for (int i = 0; i < 8; i++) za[i] = zA[c * TM + ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; j++) zb[j] = zB[c * TN + tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float t = za[i] - zb[j];
-          part[i][j] = fmaf(t, t, part[i][j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) dl2[i][j] += part[i][j];
-  }
-
-  float lsum = 0.f;
-  // after this loop dl2 holds the gradient coefficient (s_l - s_h) * s_l'(d_l) / d_l
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const bool rv = row0 + ty + 16 * i < p.n;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const bool valid = rv && (col0 + tx + 16 * j < p.n);
-      const float sh = sig_eval<false>(d2h[i][j], p.sh, nullptr);
-      float w;
-      const float sl = sig_eval<true>(dl2[i][j], p.sl, &w);
-      float diff = sh - sl;
-      if (!valid) diff = 0.f;
-      if (dl2[i][j] == 0.f || !valid) w = 0.f;
-      lsum = fmaf(diff, diff, lsum);
-      dl2[i][j] = -diff * w;
-    }
-  }
-
-  // loss: per-thread float (32 terms) -> double across the CTA
-  double ld = (double)lsum;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
-  if (lane == 0) red_d[warp] = ld;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0;
-#pragma unroll
-    for (int w = 0; w < NTHREADS / 32; w++) t += red_d[w];
-    atomicAdd(p.loss, t * (diag ? 1.0 : 2.0) * p.loss_scale);
-  }
-
-  if (p.grad == nullptr) return;
-  const float gs = p.grad_scale;
-#pragma unroll 1
-  for (int c = 0; c < p.l; c++) {
-    float za[8], zb[4], rs[8], cs[4];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      za[i] = zA[c * TM + ty + 16 * i];
-      rs[i] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      zb[j] = zB[c * TN + tx + 16 * j];
-      cs[j] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const float t = dl2[i][j] * (za[i] - zb[j]);
-        rs[i] += t;
-        cs[j] -= t;
-      }
-    // row side: the 16 lanes of a half-warp share ty
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
-      const int64_t r = row0 + ty + 16 * i;
-      if (tx == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c], rs[i] * gs);
-    }
-    // column side (mirror image of the tile); diagonal tiles already visit both orders
-    if (!diag) {
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
-        if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
-      }
-    }
-  }
-  if (!diag) {
-    __syncthreads();
-    for (int idx = tid; idx < p.l * TN; idx += NTHREADS) {
-      const int c = idx / TN, r = idx - c * TN;
-      if (col0 + r < p.n) atomicAdd(&p.grad[(col0 + r) * p.l + c], colsum[idx] * gs);
-    }
+      for (int j = 0; j < 4; j++) d2h[i][j] = acc[i][j].x + acc[i][j].y;
+    cost_epilogue<8>(d2h, 0, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+  } else if (S == 2) {
+    float d2h[4][4];
+    cluster_reduce_scatter<4>(cluster, stage_base, S, 4 * crank, tid, d2h);
+    cluster.sync();   // every rank has read what it needs: shared memory may be released
+    cost_epilogue<4>(d2h, 4 * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+  } else if (S == 4) {
+    float d2h[2][4];
+    cluster_reduce_scatter<2>(cluster, stage_base, S, 2 * crank, tid, d2h);
+    cluster.sync();
+    cost_epilogue<2>(d2h, 2 * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+  } else {
+    float d2h[1][4];
+    cluster_reduce_scatter<1>(cluster, stage_base, S, crank, tid, d2h);
+    cluster.sync();
+    cost_epilogue<1>(d2h, crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
   }
 }
 
@@ -477,7 +527,10 @@ static int prepare_high(const float* high, int64_t n, int64_t d, cudaStream_t st
     return EMK_OK;
   }
   const int64_t d_pad = (d + 3) / 4 * 4;
-  EMK_CUDA(cudaMallocAsync(&v->scratch, (size_t)(n * d_pad) * sizeof(float), st));
+  {
+    int rc0 = scratch_alloc(reinterpret_cast<void**>(&v->scratch), (size_t)(n * d_pad) * sizeof(float), st);
+    if (rc0) return rc0;
+  }
   const int64_t total = n * d_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   pad_rows_kernel<<<blocks, 256, 0, st>>>(high, v->scratch, n, d, d_pad);
@@ -488,27 +541,39 @@ static int prepare_high(const float* high, int64_t n, int64_t d, cudaStream_t st
   return EMK_OK;
 }
 
-// cluster size for a launch of `n_tiles` tiles with `n_chunks` k-chunks each: split until every SM has a CTA
-// (measured: 256 x 1024 periodic 189 -> 63 us, 1024 x 4950 euclidean 438 -> 309 us; no gain once tiles >= SMs)
+// Cluster size (K-split) for a launch of `n_tiles` tiles with `n_chunks` k-chunks each.  Every rank of a cluster runs
+// 1/S of the main loop AND 1/S of the epilogue (reduce-scatter over DSMEM), so the cost of splitting is the per-CTA
+// fixed work (barrier set-up, latent staging, pipeline fill, two cluster syncs): measured ~0 % at S = 2, 9 % at 4,
+// 27 % at 8 on 4096 x 1024.  Measured on B200 (tools/bench_small_cost.py, EMK_CLUSTER sweep):
+//   * up to 37 tiles (N <= 640): S = 8 fills at most the 296 CTA slots            256 x 1024: 185 -> 38 us
+//   * up to 127 tiles: the smallest S that gives every SM a CTA (clusters of 4 / 8 no longer fit in one wave: GPCs
+//     hold whole clusters only)                                                   1024 x 1024: 186 -> 115 us, 1024 x 4950: 450 -> 247 us
+//   * 297 .. 2048 tiles: S = 2 halves the work unit of the ragged last wave       4096 x 1024: 1205 -> 1168 us
+//   * otherwise one CTA per tile                                                  8192 x 1024: 4265 us (S = 2: 4358)
 static int pick_cluster(int64_t n_tiles, int n_chunks) {
+  int s = 1;
   if (const char* e = getenv("EMK_CLUSTER")) {   // experiments only: force a cluster size (1, 2, 4, 8)
     const int v = atoi(e);
-    if (v >= 1 && v <= 8 && (v & (v - 1)) == 0 && 2 * v <= std::max(2, n_chunks)) return v;
+    if (v >= 1 && v <= 8 && (v & (v - 1)) == 0) s = v;
+  } else if (n_tiles * 8 <= 2 * (int64_t)sm_count()) {
+    s = 8;
+  } else if (n_tiles < 128) {
+    while (s < 8 && n_tiles * s < 128) s *= 2;
+  } else if (n_tiles > 2 * (int64_t)sm_count() && n_tiles <= 2048) {
+    s = 2;
   }
-  int s = 1;
-  while (s < 8 && n_tiles * s < (int64_t)sm_count() && 2 * s <= n_chunks) s *= 2;
+  while (s > 1 && 2 * s > n_chunks) s /= 2;   // every rank needs at least two k-chunks
   return s;
 }
 
-template <bool PERIODIC, Epi EPI>
-static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, cudaStream_t st) {
-  auto kern = pair_tile_kernel<PERIODIC, EPI>;
+template <bool PERIODIC, Epi EPI, bool CLUSTERED>
+static int launch_pair_c(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, int cluster, cudaStream_t st) {
+  auto kern = pair_tile_kernel<PERIODIC, EPI, CLUSTERED>;
   static bool configured[kMaxDevices] = {false};
   if (first_use_on_device(configured)) {
     EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
-  const int cluster = pick_cluster(n_tiles, p.n_chunks);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(n_tiles * cluster));
   cfg.blockDim = dim3(NTHREADS);
@@ -523,6 +588,12 @@ static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_ti
   cfg.numAttrs = 1;
   EMK_CUDA(cudaLaunchKernelEx(&cfg, kern, map, p));
   return launch_status("pair_tile_kernel");
+}
+template <bool PERIODIC, Epi EPI>
+static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, cudaStream_t st) {
+  const int cluster = pick_cluster(n_tiles, p.n_chunks);
+  return cluster > 1 ? launch_pair_c<PERIODIC, EPI, true>(map, p, n_tiles, cluster, st)
+                     : launch_pair_c<PERIODIC, EPI, false>(map, p, n_tiles, 1, st);
 }
 
 void tile_decode_host(int64_t t, int64_t n_rows, int64_t* I, int64_t* J) {
