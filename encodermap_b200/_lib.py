@@ -57,6 +57,8 @@ SIGNATURES = {
     "emk_sigmoid_cost_host": ([vp, i64, i64, vp, i64, dbl, c_f32p, C.POINTER(dbl), vp], C.c_int),
     "emk_pairwise_dist_periodic": ([vp, i64, i64, dbl, vp, vp], C.c_int),
     "emk_dl_pairwise_dist_periodic": ([vp, dbl, vp, vp], C.c_int),
+    "emk_pairwise_dist_periodic_bwd": ([vp, i64, i64, dbl, vp, vp, vp, vp], C.c_int),
+    "emk_dl_pairwise_dist_periodic_bwd": ([vp, dbl, vp, vp, vp, vp], C.c_int),
     "emk_pairwise_dist": ([vp, i64, i64, i64, i64, i64, C.c_int, C.c_int, vp, vp], C.c_int),
     "emk_pairwise_dist_bwd": ([vp, i64, i64, i64, i64, i64, C.c_int, C.c_int, vp, vp, vp], C.c_int),
     "emk_dl_pairwise_dist": ([vp, i64, i64, i64, C.c_int, C.c_int, vp, vp], C.c_int),

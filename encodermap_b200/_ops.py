@@ -112,6 +112,26 @@ def pairwise_dist_periodic_raw(x: torch.Tensor, periodicity: float) -> torch.Ten
     return out
 
 
+class PairwiseDistPeriodic(torch.autograd.Function):
+    """pairwise_dist_periodic with the reference's autodiff conventions (encodermap/misc/distances.py:144-176)."""
+
+    @staticmethod
+    def forward(ctx, x, periodicity):
+        out = pairwise_dist_periodic_raw(x, periodicity)
+        ctx.save_for_backward(f32c(x), out)
+        ctx.periodicity = float(periodicity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        grad_out = f32c(grad_out)
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().emk_dl_pairwise_dist_periodic_bwd(DL(x), ctx.periodicity, DL(out), DL(grad_out), DL(gx), stream_of(x)))
+        return gx, None
+
+
 # ---------------------------------------------------------------------------------------------------
 # elementwise
 # ---------------------------------------------------------------------------------------------------

@@ -767,7 +767,9 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
   const bool extras = GEN && !p.planar && (p.grad_angles || p.grad_lengths) && p.mid > 1;   // left-of-anchor planar terms
   const bool need_planar = planar || extras;
 
-  const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (n - 1 + 7) & ~3, rA = (n - 2 + 7) & ~3;
+  // planar inputs: the whole rows in planar mode, only the bonds / angles left of the anchor for the left-side terms
+  const int nL = planar ? n - 1 : p.dr0, nA = planar ? n - 2 : p.dr0;
+  const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (nL + 7) & ~3, rA = (nA + 7) & ~3;
   float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0));
   float* sX = base + 4;   // 4 floats of slack in front: the walk may read (never use) one atom before the chain
   float* sG = base + rX;
@@ -777,8 +779,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     sG = stage_row16<T>(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t);
     if (!planar) sX = stage_row16<T>(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t);
     if (need_planar) {
-      sL = stage_row16<T>(sL, p.lengths + fr * p.lstride, n - 1, t);
-      sA = stage_row16<T>(sA, p.angles + fr * (int64_t)(n - 2), n - 2, t);
+      sL = stage_row16<T>(sL, p.lengths + fr * p.lstride, nL, t);
+      sA = stage_row16<T>(sA, p.angles + fr * (int64_t)(n - 2), nA, t);
     }
   }
   cp_async_wait_all();
@@ -1126,8 +1128,9 @@ static int launch_bwd3(const BwdParams& p, const double2* tab, bool need_planar,
   constexpr int CTA = T < 128 ? 128 : T;
   constexpr int FPC = CTA / T;
   const size_t n = (size_t)p.n;
+  const size_t nL = p.planar ? n - 1 : (size_t)p.dr0, nA = p.planar ? n - 2 : (size_t)p.dr0;
   const size_t per_frame = ((3 * n + 27) & ~(size_t)3) + ((3 * n + 7) & ~(size_t)3) +
-                           (need_planar ? ((n - 1 + 7) & ~(size_t)3) + ((n - 2 + 7) & ~(size_t)3) : 0);
+                           (need_planar ? ((nL + 7) & ~(size_t)3) + ((nA + 7) & ~(size_t)3) : 0);
   const size_t smem = FPC * per_frame * sizeof(float);
   EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "back-mapping backward: chain of %d atoms needs %zu bytes of staging shared memory", p.n, smem);
   auto kern = backmap_bwd3_kernel<T, GEN>;

@@ -14,6 +14,78 @@ static inline int grid_for(int64_t work, int threads = 256) {
   return (int)blocks;
 }
 
+// ---- pairwise_dist_periodic backward -------------------------------------------------------------------
+// Reference autodiff of distances.py:164-175 (TF conventions): Dist_ij = sqrt(sum_k V^2) + 1e-12,
+// V = min(d, P - d) (+1e-12 where exactly 0), d = |x_jk - x_ik|; abs' = sign, minimum routes to its first operand on
+// ties.  Both orders of a pair touch row i:
+//     grad_x[i,k] = - sum_j (G_ij + G_ji) * V_ijk / S_ij * m_ijk * sign(x_jk - x_ik),   S = Dist - 1e-12, m = +1 if d <= P - d else -1.
+// One CTA owns PDB_ROWS rows i and 128 columns k; the pair weights w_ij = (G_ij + G_ji) / S_ij of a block of 128 rows j
+// are staged in shared memory, x_j is read coalesced.  O(N^2 D); the models never need it (the high-d side is input
+// data), it exists so that the operator is differentiable like the reference's.
+constexpr int PDB_ROWS = 8;
+__global__ void __launch_bounds__(128) pairwise_periodic_bwd_kernel(const float* __restrict__ x, int64_t n, int64_t d, float P,
+                                                                    const float* __restrict__ dist, const float* __restrict__ go,
+                                                                    float* __restrict__ gx) {
+  __shared__ float w[PDB_ROWS][128];
+  const int64_t i0 = (int64_t)blockIdx.y * PDB_ROWS;
+  const int64_t k = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const bool kv = k < d;
+  float xi[PDB_ROWS], acc[PDB_ROWS];
+#pragma unroll
+  for (int r = 0; r < PDB_ROWS; r++) {
+    xi[r] = (kv && i0 + r < n) ? x[(i0 + r) * d + k] : 0.f;
+    acc[r] = 0.f;
+  }
+  for (int64_t j0 = 0; j0 < n; j0 += 128) {
+    __syncthreads();
+    {
+      const int64_t j = j0 + threadIdx.x;
+#pragma unroll
+      for (int r = 0; r < PDB_ROWS; r++) {
+        const int64_t i = i0 + r;
+        float v = 0.f;
+        if (i < n && j < n) {
+          const float sij = fmaxf(dist[i * n + j] - 1e-12f, 1e-30f);
+          v = (go[i * n + j] + go[j * n + i]) / sij;
+        }
+        w[r][threadIdx.x] = v;
+      }
+    }
+    __syncthreads();
+    if (kv) {
+      const int jn = (int)min((int64_t)128, n - j0);
+      for (int jj = 0; jj < jn; jj++) {
+        const float xj = x[(j0 + jj) * d + k];
+#pragma unroll
+        for (int r = 0; r < PDB_ROWS; r++) {
+          const float df = xj - xi[r];
+          const float ad = fabsf(df), pd = P - ad;
+          float v = fminf(ad, pd);
+          v = v == 0.f ? 1e-12f : v;
+          // m * sign(x_j - x_i): +-1, 0 where the difference is exactly 0
+          const float sg = df == 0.f ? 0.f : ((ad <= pd) == (df > 0.f) ? 1.f : -1.f);
+          acc[r] = fmaf(-w[r][jj] * v, sg, acc[r]);
+        }
+      }
+    }
+  }
+  if (kv) {
+#pragma unroll
+    for (int r = 0; r < PDB_ROWS; r++)
+      if (i0 + r < n) gx[(i0 + r) * d + k] = acc[r];
+  }
+}
+int pairwise_periodic_bwd_device(const float* x, int64_t n, int64_t d, double P, const float* dist, const float* go, float* gx,
+                                 cudaStream_t st) {
+  EMK_REQUIRE(x && dist && go && gx, EMK_E_NULL, "emk_pairwise_dist_periodic_bwd: NULL pointer argument");
+  EMK_REQUIRE(n >= 0 && d >= 0 && P > 0, EMK_E_ARG, "emk_pairwise_dist_periodic_bwd: bad arguments");
+  if (n * d == 0) return EMK_OK;
+  EMK_REQUIRE((n + PDB_ROWS - 1) / PDB_ROWS <= 65535, EMK_E_UNSUPPORTED, "emk_pairwise_dist_periodic_bwd: more than %d rows", 65535 * PDB_ROWS);
+  dim3 grid((unsigned)((d + 127) / 128), (unsigned)((n + PDB_ROWS - 1) / PDB_ROWS));
+  pairwise_periodic_bwd_kernel<<<grid, 128, 0, st>>>(x, n, d, std::isinf(P) ? INFINITY : (float)P, dist, go, gx);
+  return launch_status("pairwise_periodic_bwd_kernel");
+}
+
 // ---- FP32 pipe probe ---------------------------------------------------------------------------------
 // Measured denominator of the pair-tile kernel's roofline: register-only FFMA chains (16 independent accumulators
 // per thread, 8 CTAs of 256 threads per SM), i.e. what the FP32 pipe of this very device issues per second when

@@ -98,6 +98,7 @@ int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int6
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
 int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
 int fp32_probe_device(double*);
+int pairwise_periodic_bwd_device(const float*, int64_t, int64_t, double, const float*, const float*, float*, cudaStream_t);
 int chain_in_plane_device(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 int d2c_general_device(const float*, const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
 int backmap_bwd_device(const BwdParams&, cudaStream_t);
@@ -327,6 +328,23 @@ int emk_dl_pairwise_dist_periodic(const DLManagedTensor* x, double periodicity, 
   VIEW(ov, out, "out", 2, 2);
   EMK_REQUIRE(ov.shape[0] == xv.shape[0] && ov.shape[1] == xv.shape[0], EMK_E_SHAPE, "emk_dl_pairwise_dist_periodic: out must be (n,n)");
   return dist_matrix_device(F(xv), xv.shape[0], xv.shape[1], periodicity, true, 0, F(ov), as_stream(stream));
+}
+
+int emk_pairwise_dist_periodic_bwd(const float* x, int64_t n, int64_t d, double periodicity, const float* dist, const float* grad_out,
+                                   float* grad_x, void* stream) {
+  return pairwise_periodic_bwd_device(x, n, d, periodicity, dist, grad_out, grad_x, as_stream(stream));
+}
+int emk_dl_pairwise_dist_periodic_bwd(const DLManagedTensor* x, double periodicity, const DLManagedTensor* dist,
+                                      const DLManagedTensor* grad_out, DLManagedTensor* grad_x, void* stream) {
+  VIEW(xv, x, "positions", 2, 2);
+  VIEW(dv, dist, "dist", 2, 2);
+  VIEW(gv, grad_out, "grad_out", 2, 2);
+  VIEW(ov, grad_x, "grad_x", 2, 2);
+  const int64_t n = xv.shape[0];
+  EMK_REQUIRE(dv.shape[0] == n && dv.shape[1] == n && gv.shape[0] == n && gv.shape[1] == n, EMK_E_SHAPE,
+              "emk_dl_pairwise_dist_periodic_bwd: dist and grad_out must be (n,n)");
+  EMK_REQUIRE(ov.shape[0] == n && ov.shape[1] == xv.shape[1], EMK_E_SHAPE, "emk_dl_pairwise_dist_periodic_bwd: grad_x must be (n,d)");
+  return pairwise_periodic_bwd_device(F(xv), n, xv.shape[1], periodicity, F(dv), F(gv), F(ov), as_stream(stream));
 }
 
 int emk_pairwise_dist(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride, int squared,

@@ -43,9 +43,12 @@ def periodic_distance(a, b, periodicity: float = 2 * pi) -> torch.Tensor:
 
 
 def pairwise_dist_periodic(positions, periodicity: float) -> torch.Tensor:
-    """Reference: encodermap/misc/distances.py:144-176.  (n,d) -> (n,n); not differentiable here (in the
-    models it only ever sees input data)."""
-    return _ops.pairwise_dist_periodic_raw(_as_cuda(positions), periodicity)
+    """Reference: encodermap/misc/distances.py:144-176.  (n,d) -> (n,n), differentiable w.r.t. ``positions``
+    with TensorFlow's autodiff conventions (in the models it only ever sees input data)."""
+    positions = _as_cuda(positions)
+    if positions.requires_grad:
+        return _ops.PairwiseDistPeriodic.apply(positions, float(periodicity))
+    return _ops.pairwise_dist_periodic_raw(positions, periodicity)
 
 
 def pairwise_dist(positions, squared: bool = False, flat: bool = False) -> torch.Tensor:

@@ -119,6 +119,12 @@ EMK_API int emk_sigmoid_cost_host(const float* high_host, int64_t n, int64_t d, 
 /* pairwise_dist_periodic(positions (n,d), periodicity) -> (n,n)   encodermap/misc/distances.py:144-176 */
 EMK_API int emk_pairwise_dist_periodic(const float* x, int64_t n, int64_t d, double periodicity, float* out, void* stream);
 EMK_API int emk_dl_pairwise_dist_periodic(const DLManagedTensor* x, double periodicity, DLManagedTensor* out, void* stream);
+/* VJP of pairwise_dist_periodic w.r.t. positions (TensorFlow's autodiff of distances.py:164-175: abs' = sign, minimum routes
+ * to its first operand on ties); dist is the forward output, grad_out the upstream (n,n) gradient. */
+EMK_API int emk_pairwise_dist_periodic_bwd(const float* x, int64_t n, int64_t d, double periodicity, const float* dist,
+                                           const float* grad_out, float* grad_x, void* stream);
+EMK_API int emk_dl_pairwise_dist_periodic_bwd(const DLManagedTensor* x, double periodicity, const DLManagedTensor* dist,
+                                              const DLManagedTensor* grad_out, DLManagedTensor* grad_x, void* stream);
 
 /* pairwise_dist(positions (b,n,d), squared, flat)   encodermap/misc/distances.py:179-255
  *   x is addressed as x[bi*batch_stride + i*row_stride + k] (element strides) so that the atom

@@ -367,6 +367,25 @@ def test_pairwise_flat_kernel_variants(em, b, n):
         assert relnorm(xs.grad.cpu().numpy(), ref_in.grad.numpy()) < 2e-5
 
 
+def test_pairwise_dist_periodic_backward(em):
+    """VJP of pairwise_dist_periodic against float64 autograd of the restated reference (distances.py:144-176)."""
+    from encodermap_b200.misc import distances as D
+
+    rng = np.random.default_rng(31)
+    for n, d, period in ((5, 3, 2 * pi), (33, 17, 2 * pi), (130, 140, 360.0), (64, 8, float("inf"))):
+        scale = 1.0 if np.isinf(period) else period / 2
+        x = rng.uniform(-1, 1, size=(n, d)).astype(np.float32) * scale
+        w = rng.normal(size=(n, n))
+        xg = cu(x).requires_grad_(True)
+        out = D.pairwise_dist_periodic(xg, period)
+        (out * cu(w)).sum().backward()
+        xo = torch.from_numpy(x).double().requires_grad_(True)
+        ref = O.pairwise_dist_periodic(xo, period)
+        (ref * torch.from_numpy(w)).sum().backward()
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+        assert relnorm(xg.grad.cpu().numpy(), xo.grad.numpy()) < 2e-5
+
+
 def test_periodic_input_shapes(em):
     """Vectorised (d % 4 == 0) and scalar column paths, rescaled periodicity, forward and backward."""
     from encodermap_b200 import Parameters
