@@ -338,16 +338,21 @@ __global__ void pairwise_small_kernel(const float* __restrict__ x, int64_t b, in
 
 // PairwiseDistances layer, forward: flat upper triangle of 3-d points, up to PWT_MAX_N selected atoms (the Calpha
 // selections of the ADC models).  One thread per output element with coalesced 4-byte stores; the pair (i, j) of
-// flat index p comes from a 16-bit table in shared memory that the CTA builds once and reuses for every frame it
-// processes (no per-element decode, no divergence).  G frames are staged per barrier pair.
+// flat index p comes from a table in shared memory that the CTA builds once and reuses for every frame it
+// processes (no per-element decode, no divergence).  The table holds BYTE OFFSETS: i * 16 into a float4 copy of the
+// coordinates (x_i is one mostly-broadcast LDS.128) and j * 4 into a component-major copy (x_j is three conflict-free
+// LDS.32 on consecutive lanes), so an output costs ~20 instructions and ~5 shared-memory wavefronts per warp.
+// G frames are staged per barrier pair.
 constexpr int PWF_THREADS = 256;
-constexpr int PWT_MAX_N = 181;   // i, j < 256 and a table of at most 32 KB
+constexpr int PWT_MAX_N = 181;   // table of at most 64 KB / 4
 
 __global__ void __launch_bounds__(PWF_THREADS) pairwise_flat3_tab_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
                                                                          int64_t rstride, int squared, int G, float* __restrict__ out) {
-  extern __shared__ float sx[];   // [G][3][n] positions, then per x uint16 pair table
+  extern __shared__ __align__(16) float sx[];   // [G][n] float4 (x, y, z, 0), then [G][3][n] component-major, then per x uint32
   const int per = n * (n - 1) / 2;
-  unsigned short* tab = reinterpret_cast<unsigned short*>(sx + (size_t)G * 3 * n);
+  float4* s4 = reinterpret_cast<float4*>(sx);
+  float* ssoa = sx + (size_t)G * 4 * n;
+  unsigned* tab = reinterpret_cast<unsigned*>(ssoa + (size_t)G * 3 * n);
   const int tid = threadIdx.x;
   {
     const int nn = 2 * n - 1;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(PWF_THREADS) pairwise_flat3_tab_kernel(const f
       if (i * (nn - i) / 2 > p) --i;
       if ((i + 1) * (nn - i - 1) / 2 <= p) ++i;
       const int j = p - i * (nn - i) / 2 + i + 1;
-      tab[p] = (unsigned short)((i << 8) | j);
+      tab[p] = (unsigned)(i * 16) | ((unsigned)(j * 4) << 16);
     }
   }
   for (int64_t g0 = (int64_t)blockIdx.x * G; g0 < b; g0 += (int64_t)gridDim.x * G) {
@@ -365,21 +370,29 @@ __global__ void __launch_bounds__(PWF_THREADS) pairwise_flat3_tab_kernel(const f
     __syncthreads();
     for (int f = 0; f < gc; f++) {
       const float* xb = x + (g0 + f) * bstride;
-      float* sf = sx + f * 3 * n;
-      for (int idx = tid; idx < 3 * n; idx += PWF_THREADS) {
-        const int a = idx / 3, c = idx - 3 * a;
-        sf[c * n + a] = xb[a * rstride + c];
+      for (int a = tid; a < n; a += PWF_THREADS) {
+        const float vx = xb[a * rstride], vy = xb[a * rstride + 1], vz = xb[a * rstride + 2];
+        s4[f * n + a] = make_float4(vx, vy, vz, 0.f);
+        ssoa[(f * 3 + 0) * n + a] = vx;
+        ssoa[(f * 3 + 1) * n + a] = vy;
+        ssoa[(f * 3 + 2) * n + a] = vz;
       }
     }
     __syncthreads();
     for (int f = 0; f < gc; f++) {
-      const float* sf = sx + f * 3 * n;
+      const char* a4 = reinterpret_cast<const char*>(s4 + f * n);
+      const char* cx = reinterpret_cast<const char*>(ssoa + (f * 3 + 0) * n);
+      const char* cy = reinterpret_cast<const char*>(ssoa + (f * 3 + 1) * n);
+      const char* cz = reinterpret_cast<const char*>(ssoa + (f * 3 + 2) * n);
       float* ob = out + (g0 + f) * per;
 #pragma unroll 4
       for (int p = tid; p < per; p += PWF_THREADS) {
-        const unsigned ij = tab[p];
-        const int i = ij >> 8, j = ij & 255;
-        const float dx = sf[i] - sf[j], dy = sf[n + i] - sf[n + j], dz = sf[2 * n + i] - sf[2 * n + j];
+        const unsigned e = tab[p];
+        const unsigned oi = e & 0xffffu, oj = e >> 16;
+        const float4 pi = *reinterpret_cast<const float4*>(a4 + oi);
+        const float dx = pi.x - *reinterpret_cast<const float*>(cx + oj);
+        const float dy = pi.y - *reinterpret_cast<const float*>(cy + oj);
+        const float dz = pi.z - *reinterpret_cast<const float*>(cz + oj);
         const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         ob[p] = squared ? s2 : (s2 > 0.f ? s2 * rsqrtf(s2) : 0.f);   // sqrt as s2 * rsqrt(s2): MUFU + FMUL, 2 ulp
       }
@@ -726,9 +739,9 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
     if (n <= PWT_MAX_N) {
       const int64_t per3 = n * (n - 1) / 2;
       const int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, 32768 / per3 + 1), b));
-      const size_t smem = (size_t)G * 3 * (size_t)n * sizeof(float) + (((size_t)per3 * 2 + 15) & ~(size_t)15);
+      const size_t smem = (size_t)G * 7 * (size_t)n * sizeof(float) + (size_t)per3 * 4;
       static bool cfg[kMaxDevices] = {false};
-      if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       const unsigned grid = (unsigned)std::min<int64_t>((b + G - 1) / G, (int64_t)sm_count() * 8);
       pairwise_flat3_tab_kernel<<<grid, PWF_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, G, out);
       return launch_status("pairwise_flat3_tab_kernel");
