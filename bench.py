@@ -40,6 +40,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# NCCL writes its version banner / debug log to stdout by default; stdout carries exactly one JSON line here
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N_ROWS, N_DIMS, N_LATENT = 65536, 1024, 2
 SIG = (4.5, 12, 6, 1, 2, 6)
