@@ -964,7 +964,7 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
       m1 = fmaf(-e12, s0, fmaf(e10, s2, m1));
       m2 = fmaf(-e10, s1, fmaf(e11, s0, m2));
       const float e20 = xq0 - xn0, e21 = xq1 - xn1, e22 = xq2 - xn2;
-      if (wantD) pg[0] = -(e20 * m0 + e21 * m1 + e22 * m2) * rsqrtf(fmaf(e20, e20, fmaf(e21, e21, e22 * e22)));
+      if (wantD) pg[0] = -(e20 * m0 + e21 * m1 + e22 * m2) * rsqrt_fast(fmaf(e20, e20, fmaf(e21, e21, e22 * e22)));
       if (GEN) {
         float rA = 0.f, rL = 0.f;
         if (wantA) {
@@ -973,10 +973,10 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
             rA = ((k - 1) & 1) ? -m2 : m2;                // hinge normal -(-1)^(k-1) e_z, term = -<normal, M>
           } else {
             const float c0 = e11 * e22 - e12 * e21, c1 = e12 * e20 - e10 * e22, c2 = e10 * e21 - e11 * e20;
-            rA = (c0 * m0 + c1 * m1 + c2 * m2) * rsqrtf(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)));
+            rA = (c0 * m0 + c1 * m1 + c2 * m2) * rsqrt_fast(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)));
           }
         }
-        if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrtf(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
+        if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrt_fast(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
         if (lext) {
           // planar atom k+1 (k = i) from its chunk-local coordinates; planar direction of bond k from two of them
           const float lx = sL[i], ly = sA[i];
@@ -986,7 +986,7 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
           rA += (i & 1) ? -tz : tz;
           if (wantL) {
             const float dlx = lx - llx, dly = ly - lly;
-            const float inv = rsqrtf(fmaf(dlx, dlx, dly * dly));
+            const float inv = rsqrt_fast(fmaf(dlx, dlx, dly * dly));
             const float q0 = dlx * inv, q1 = dly * inv;
             rL += (plc * q0 - pls * q1) * ft[0] + (pls * q0 + plc * q1) * ft[1];
           }

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(PWF_THREADS) pairwise_flat3_tab_kernel(const f
         const float dy = pi.y - *reinterpret_cast<const float*>(cy + oj);
         const float dz = pi.z - *reinterpret_cast<const float*>(cz + oj);
         const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        ob[p] = squared ? s2 : (s2 > 0.f ? s2 * rsqrtf(s2) : 0.f);   // sqrt as s2 * rsqrt(s2): MUFU + FMUL, 2 ulp
+        ob[p] = squared ? s2 : (s2 >= EMK_TINY ? s2 * rsqrt_fast(s2) : 0.f);   // sqrt as s2 * rsqrt(s2): MUFU + FMUL, 2 ulp
       }
     }
   }
@@ -432,25 +432,28 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_rows3_kernel(const float*
           const float dx1 = xi - sx[j + 32], dy1 = yi - sx[n + j + 32], dz1 = zi - sx[2 * n + j + 32];
           const float a0 = fmaf(dx0, dx0, fmaf(dy0, dy0, dz0 * dz0));
           const float a1 = fmaf(dx1, dx1, fmaf(dy1, dy1, dz1 * dz1));
-          orow[j] = squared ? a0 : (a0 > 0.f ? a0 * rsqrtf(a0) : 0.f);
-          orow[j + 32] = squared ? a1 : (a1 > 0.f ? a1 * rsqrtf(a1) : 0.f);
+          orow[j] = squared ? a0 : (a0 >= EMK_TINY ? a0 * rsqrt_fast(a0) : 0.f);
+          orow[j + 32] = squared ? a1 : (a1 >= EMK_TINY ? a1 * rsqrt_fast(a1) : 0.f);
         }
         if (j < n) {
           const float dx = xi - sx[j], dy = yi - sx[n + j], dz = zi - sx[2 * n + j];
           const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-          orow[j] = squared ? s2 : (s2 > 0.f ? s2 * rsqrtf(s2) : 0.f);
+          orow[j] = squared ? s2 : (s2 >= EMK_TINY ? s2 * rsqrt_fast(s2) : 0.f);
         }
       }
     }
   }
 }
 
-// PairwiseDistances layer, backward: one CTA per frame, one thread per atom i looping over j; positions (and the
-// upstream gradient when it fits) are staged in shared memory, so the inner loop is ~20 instructions with no
-// global traffic.  grad_x[i] = sum_j coef_ij (x_i - x_j), coef = g/dist (2g when squared), 0 at zero distance.
-template <bool G_IN_SMEM>
+// PairwiseDistances layer, backward: one CTA per frame, one thread per atom i looping over ALL j (uniform trip
+// count, unrolled by 4); positions (and the upstream gradient when it fits) are staged in shared memory.
+// grad_x[i] = sum_j coef_ij (x_i - x_j), coef = g/dist (2g when squared), 0 at zero distance.
+// The flat index of the pair {i, j} is walked incrementally: it starts at i - 1 (pair (0, i)), advances by n - j - 2
+// while j < i (down column i of the triangle) and by 1 afterwards (along row i); at j == i the walk passes through
+// rowstart(i) - 1, an unrelated element whose weight is multiplied by x_i - x_i = 0.
+template <bool G_IN_SMEM, bool SQUARED>
 __global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
-                                                                        int64_t rstride, int squared, const float* __restrict__ go,
+                                                                        int64_t rstride, const float* __restrict__ go,
                                                                         float* __restrict__ gx) {
   extern __shared__ float sm[];   // [3][n] positions, then (optionally) the frame's upstream gradient
   float* sx = sm;
@@ -471,22 +474,14 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_bwd_kernel(const fl
     for (int i = threadIdx.x; i < n; i += PW_THREADS) {
       const float xi = sx[i], yi = sx[n + i], zi = sx[2 * n + i];
       float ax = 0.f, ay = 0.f, az = 0.f;
-      // pair (j,i), j < i, sits at j(2n-j-1)/2 + (i-j-1): starts at i-1 and advances by n-j-2 per j
       int off = i - 1;
-      for (int j = 0; j < i; j++) {
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
         const float dx = xi - sx[j], dy = yi - sx[n + j], dz = zi - sx[2 * n + j];
         const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        const float gij = gg[off];
-        off += n - j - 2;
-        const float coef = squared ? 2.f * gij : (s2 > 0.f ? gij * rsqrtf(s2) : 0.f);
-        ax = fmaf(coef, dx, ax); ay = fmaf(coef, dy, ay); az = fmaf(coef, dz, az);
-      }
-      const float* grow = gg + (int64_t)i * (2 * n - i - 1) / 2 - i - 1;   // + j for j > i
-      for (int j = i + 1; j < n; j++) {
-        const float dx = xi - sx[j], dy = yi - sx[n + j], dz = zi - sx[2 * n + j];
-        const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        const float gij = grow[j];
-        const float coef = squared ? 2.f * gij : (s2 > 0.f ? gij * rsqrtf(s2) : 0.f);
+        const float gij = gg[max(off, 0)];
+        off += j < i ? n - j - 2 : 1;
+        const float coef = SQUARED ? 2.f * gij : (s2 >= EMK_TINY ? gij * rsqrt_fast(s2) : 0.f);
         ax = fmaf(coef, dx, ax); ay = fmaf(coef, dy, ay); az = fmaf(coef, dz, az);
       }
       float* o = gx + bi * bstride + (int64_t)i * rstride;
@@ -554,7 +549,7 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_flat3_bwd_cols_kernel(con
           const float gij = gcur[c];
           const float dx = xi - xj[c][0], dy = yi - xj[c][1], dz = zi - xj[c][2];
           const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-          const float coef = squared ? 2.f * gij : (s2 > 0.f ? gij * rsqrtf(s2) : 0.f);
+          const float coef = squared ? 2.f * gij : (s2 >= EMK_TINY ? gij * rsqrt_fast(s2) : 0.f);
           r0 = fmaf(coef, dx, r0); r1 = fmaf(coef, dy, r1); r2 = fmaf(coef, dz, r2);
           ca[c][0] = fmaf(-coef, dx, ca[c][0]); ca[c][1] = fmaf(-coef, dy, ca[c][1]); ca[c][2] = fmaf(-coef, dz, ca[c][2]);
         }
@@ -631,7 +626,7 @@ __global__ void pairwise_small_bwd_kernel(const float* __restrict__ x, int64_t b
           } else {
             for (int64_t k = 0; k < d; k++) { const float t = xi[k] - xj[k]; s = fmaf(t, t, s); }
           }
-          const float coef = squared ? 2.f * gij : (s > 0.f ? gij * rsqrtf(s) : 0.f);
+          const float coef = squared ? 2.f * gij : (s >= EMK_TINY ? gij * rsqrt_fast(s) : 0.f);
 #pragma unroll
           for (int k = 0; k < 8; k++)
             if (k < kc) acc[k] = fmaf(coef, xik[k] - xj[k0 + k], acc[k]);
@@ -775,17 +770,21 @@ int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, i
     const size_t sx = ((3 * (size_t)n + 3) & ~(size_t)3) * sizeof(float);
     const size_t sg = (size_t)n * (n - 1) / 2 * sizeof(float);
     const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);
+#define EMK_PWB1(GS, SQ, SMEM)                                                                                              \
+  do {                                                                                                                      \
+    static bool cfg[kMaxDevices] = {false};                                                                                 \
+    if (first_use_on_device(cfg))                                                                                           \
+      EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_bwd_kernel<GS, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+    pairwise_flat3_bwd_kernel<GS, SQ><<<grid, PW_THREADS, SMEM, st>>>(x, b, (int)n, bstride, rstride, go, gx);               \
+  } while (0)
     if (sx + sg <= 96 * 1024) {
-      static bool cfg[kMaxDevices] = {false};
-      if (first_use_on_device(cfg))
-        EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      pairwise_flat3_bwd_kernel<true><<<grid, PW_THREADS, sx + sg, st>>>(x, b, (int)n, bstride, rstride, squared, go, gx);
+      if (squared) EMK_PWB1(true, true, sx + sg);
+      else EMK_PWB1(true, false, sx + sg);
     } else {
-      static bool cfg[kMaxDevices] = {false};
-      if (first_use_on_device(cfg))
-        EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      pairwise_flat3_bwd_kernel<false><<<grid, PW_THREADS, sx, st>>>(x, b, (int)n, bstride, rstride, squared, go, gx);
+      if (squared) EMK_PWB1(false, true, sx);
+      else EMK_PWB1(false, false, sx);
     }
+#undef EMK_PWB1
     return launch_status("pairwise_flat3_bwd_kernel");
   }
   const int threads = n >= 128 ? 128 : (int)((n + 31) / 32 * 32);

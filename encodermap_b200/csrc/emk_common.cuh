@@ -78,6 +78,15 @@ struct BwdParams {
 };
 
 #ifdef __CUDACC__
+// 1/sqrt(x) as ONE MUFU.RSQ (2 ulp).  CUDA's rsqrtf() wraps the same instruction in a denormal fix-up (two compares,
+// a select and three multiplies on every call); distances below 1e-19 are zero for every purpose here, so callers
+// guard with x >= EMK_TINY instead.
+#define EMK_TINY 1.17549435e-38f
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // x^n for a kernel-uniform n in [0,15]: branch-free binary exponentiation (3 squarings, no MUFU).  Kept tiny on
 // purpose: the pair-tile epilogue instantiates it 128 times and must stay inside the instruction cache.
 __device__ __forceinline__ float ipow_uniform(float x, int n) {
