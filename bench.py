@@ -182,7 +182,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner with printf to stdout when the communicator comes up (NCCL_DEBUG=VERSION in the
+        # launch environment); stdout must carry exactly one JSON line, so fd 1 points at stderr until NCCL is initialised
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     L = _lib.lib()  # fails loudly if libemk.so is missing
     peaks = measured_peaks()
 
