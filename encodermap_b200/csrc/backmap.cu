@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(FWD5_THREADS, 2) backmap_fwd5_kernel(const flo
   const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid >> 6, t = tid & 63, side = (tid >> 5) & 1;
   double2* tabS = reinterpret_cast<double2*>(smem);
-  for (int i = tid; i < SC_SMALL; i += FWD5_THREADS) tabS[i] = __ldg(tab + i * (SC_TABLE / SC_SMALL));
+  const int ngroups = blockDim.x >> 6;   // 6 at <= 3000 atoms, fewer for longer chains (shared memory)
+  for (int i = tid; i < SC_SMALL; i += blockDim.x) tabS[i] = __ldg(tab + i * (SC_TABLE / SC_SMALL));
   __syncthreads();
 
   const int out_floats = 3 * n;
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(FWD5_THREADS, 2) backmap_fwd5_kernel(const flo
   const int nvalid = max(0, min(ch, steps - i0));
   const int kfirst = side == 0 ? s - 2 - i0 : s + 2 + i0;
 
-  for (int64_t frame = (int64_t)blockIdx.x * FWD5_GROUPS + g; frame < b; frame += (int64_t)gridDim.x * FWD5_GROUPS) {
+  for (int64_t frame = (int64_t)blockIdx.x * ngroups + g; frame < b; frame += (int64_t)gridDim.x * ngroups) {
     float* dst = xyz + frame * (int64_t)out_floats;
     // congruent with the global row modulo 16 bytes, so that the final copy is float4 on both sides
     float* T = region + (int)((reinterpret_cast<uintptr_t>(dst) & 15) >> 2);
@@ -1071,16 +1072,18 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
   const double2* tab;
   int rc = get_sincos_table(&tab);
   if (rc) return rc;
-  const size_t per_group = (3 * (size_t)n + 7) & ~(size_t)3;
-  const size_t smem = SC_SMALL * sizeof(double2) + (size_t)FWD5_GROUPS * per_group * sizeof(float);
-  EMK_REQUIRE(smem <= 224 * 1024, EMK_E_UNSUPPORTED, "emk_backmap: chain of %lld atoms needs %zu bytes of staging shared memory", (long long)n, smem);
+  const size_t per_group = ((3 * (size_t)n + 7) & ~(size_t)3) * sizeof(float);
+  const size_t budget = 224 * 1024 - SC_SMALL * sizeof(double2);
+  const int groups = (int)std::min<size_t>(FWD5_GROUPS, budget / per_group);   // frames in flight per CTA
+  EMK_REQUIRE(groups >= 1, EMK_E_UNSUPPORTED, "emk_backmap: chain of %lld atoms needs %zu bytes of staging shared memory", (long long)n, per_group);
+  const size_t smem = SC_SMALL * sizeof(double2) + (size_t)groups * per_group;
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(backmap_fwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   // persistent CTAs: as many as can be resident (2 per SM at 500 residues), each group strides over the frames
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 2048)));
-  const int64_t want = (b + FWD5_GROUPS - 1) / FWD5_GROUPS;
+  const int64_t want = (b + groups - 1) / groups;
   const int64_t blocks = std::min<int64_t>(want, (int64_t)sm_count() * per_sm);
-  backmap_fwd5_kernel<<<(unsigned)blocks, FWD5_THREADS, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz, tab);
+  backmap_fwd5_kernel<<<(unsigned)blocks, 64 * groups, smem, st>>>(lengths, lstride, angles, dihedrals, b, (int)n, xyz, tab);
   return launch_status("backmap_fwd5_kernel");
 }
 

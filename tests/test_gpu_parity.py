@@ -510,7 +510,8 @@ def test_helix_kat(em, golden):
     np.testing.assert_allclose(dihedrals_to_cartesian_tf(dih, start).cpu().numpy(), g["helix_twosided"], atol=2e-5)
 
 
-@pytest.mark.parametrize("n,b", [(4, 3), (5, 3), (6, 2), (7, 2), (8, 5), (33, 4), (64, 3), (100, 130), (301, 2), (1500, 2)])
+# 3500 and 6000 atoms: fewer than six frames fit in one CTA's shared memory (forward), eight / sixteen warps per frame (backward)
+@pytest.mark.parametrize("n,b", [(4, 3), (5, 3), (6, 2), (7, 2), (8, 5), (33, 4), (64, 3), (100, 130), (301, 2), (1500, 2), (3500, 7), (6000, 2)])
 def test_backmap_vs_oracle(em, n, b):
     from encodermap_b200.models.layers import back_map
 
@@ -551,7 +552,7 @@ def test_backmap_unwrapped_angles(em):
 
 # 4..416 atoms: one warp per frame (both ends in one warp), 417..832: two warps, ..1664: four, ..3328: eight (the
 # scan then crosses warps through shared memory)
-@pytest.mark.parametrize("n,b", [(4, 2), (5, 2), (9, 3), (10, 3), (30, 4), (31, 4), (300, 3), (417, 2), (700, 2), (1500, 2), (1700, 1)])
+@pytest.mark.parametrize("n,b", [(4, 2), (5, 2), (9, 3), (10, 3), (30, 4), (31, 4), (300, 3), (417, 2), (700, 2), (1500, 2), (1700, 1), (3400, 1)])
 def test_backmap_backward(em, n, b):
     from encodermap_b200.models.layers import back_map
 
