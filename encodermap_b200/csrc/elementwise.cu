@@ -269,8 +269,20 @@ __global__ void column_partial_kernel(const float* __restrict__ x, int64_t rows,
   const int64_t slab = (rows + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = (int64_t)blockIdx.y * slab, r1 = min(rows, r0 + slab);
   double acc = 0.0;
-  if (col < cols)
-    for (int64_t r = r0 + ry; r < r1; r += 8) acc += (double)x[r * cols + col];
+  if (col < cols) {
+    // eight independent loads in flight per thread (the one-load-per-iteration loop reached 0.5 of the HBM rate);
+    // groups of four are summed in float32 first (relative 1e-7 on bond lengths, averaged away over the column)
+    int64_t r = r0 + ry;
+    const float* px = x + r * cols + col;
+    const int64_t step = 8 * cols;
+    for (; r + 56 < r1; r += 64, px += 8 * step) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldg(px + u * step);
+      acc += (double)((v[0] + v[1]) + (v[2] + v[3])) + (double)((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; r < r1; r += 8, px += step) acc += (double)__ldg(px);
+  }
   sm[ry][cx] = acc;
   __syncthreads();
   if (ry == 0 && col < cols) {
