@@ -155,14 +155,6 @@ __device__ __forceinline__ Se2 se2_shfl_down(const Se2& a, int d) {
   o.y = __shfl_down_sync(0xffffffffu, a.y, d);
   return o;
 }
-__device__ __forceinline__ Se2 se2_shfl(const Se2& a, int src) {
-  Se2 o;
-  o.c = __shfl_sync(0xffffffffu, a.c, src);
-  o.s = __shfl_sync(0xffffffffu, a.s, src);
-  o.x = __shfl_sync(0xffffffffu, a.x, src);
-  o.y = __shfl_sync(0xffffffffu, a.y, src);
-  return o;
-}
 // inclusive scan over the 32 lanes; *excl receives the exclusive prefix
 __device__ __forceinline__ Se2 se2_scan(Se2 t, int lane, Se2* excl) {
   for (int d = 1; d < 32; d <<= 1) {
@@ -200,18 +192,6 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-// `region` is 16-byte aligned with 4 floats of slack.  The copy starts at the 16-byte boundary at or below
-// `src` (those <= 3 leading floats belong to the previous row of the same tensor), so that the body moves
-// 16 bytes per request with every request in flight at once; returns the address of element 0.
-__device__ __forceinline__ float* stage_row_async(float* region, const float* __restrict__ src, int len, int t, int nthreads) {
-  const int sh = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);
-  const float* asrc = src - sh;
-  const int total = sh + len;
-  const int nvec = total >> 2;
-  for (int v = t; v < nvec; v += nthreads) cp_async16(region + 4 * v, asrc + 4 * v);
-  for (int e = (nvec << 2) + t; e < total; e += nthreads) cp_async4(region + e, asrc + e);
-  return region + sh;
 }
 // coalesced copy of `len` floats from shared to global; sm and dst are congruent modulo 16 bytes
 __device__ __forceinline__ void store_row(float* __restrict__ dst, const float* sm, int len, int t, int nthreads) {
@@ -346,23 +326,7 @@ constexpr float SC_FAST_LIMIT = 48.f;
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); }
 
-// table path without the range check (|x| < SC_FAST_LIMIT is the caller's business); tabS in shared memory
-__device__ __forceinline__ void sincos_tab256(float x, const double2* tabS, double* s, double* c) {
-  const float km = fmaf(x, 40.74366543152521f, 12582912.f);   // 256 / 2pi; low mantissa bits = rint(x * 256 / 2pi)
-  const float kf = km - 12582912.f;
-  // 2pi/256 = C1 + C2 + C3 with 8- and 11-bit C1, C2: the first two reductions are exact in float32
-  float r = fmaf(-kf, 0.0245361328125f, x);
-  r = fmaf(-kf, 7.558614015579224e-06f, r);
-  r = fmaf(-kf, 1.1796547072506768e-09f, r);
-  const float r2 = r * r;
-  const float sr = fmaf(r * r2, -0.16666667f, r);                  // sin r      (|r| <= pi/256: r^5/120 < 3e-12)
-  const float cm = r2 * fmaf(r2, 0.041666668f, -0.5f);             // cos r - 1
-  const double2 t = tabS[__float_as_int(km) & (SC_SMALL - 1)];
-  *s = fma(t.x, (double)cm, fma(t.y, (double)sr, t.x));
-  *c = fma(t.y, (double)cm, fma(-t.x, (double)sr, t.y));
-}
-
-// both table sin/cos of one NeRF step at once: the float32 argument reduction and the two short polynomials run as
+// both table sin/cos of one NeRF step at once (|x| < SC_FAST_LIMIT is the caller's business; tabS in shared memory): the float32 argument reduction and the two short polynomials run as
 // packed FP32x2 instructions (FFMA2 / FMUL2 / FADD2), one lane of the pair per angle -- 10 issue slots instead of 20
 __device__ __forceinline__ void sincos_tab256_x2(float xa, float xb, const double2* tabS, double* sa, double* ca, double* sb, double* cb) {
   const float2 x = make_float2(xa, xb);
@@ -713,7 +677,9 @@ __device__ __forceinline__ void wrench_append(WrenchF& c, const WrenchF& a, cons
 }
 
 // 16-byte staging of one row by NT threads: uniform trip count, four predicated copies with immediate offsets per
-// iteration.  Same contract as stage_row_async (starts at the 16-byte boundary at or below src).
+// iteration.  `region` is 16-byte aligned with 4 floats of slack; the copy starts at the 16-byte boundary at or below
+// `src` (those <= 3 leading floats belong to the previous row of the same tensor), so the body moves 16 bytes per request;
+// returns the address of element 0.
 __device__ __forceinline__ void cp_async16_s(uint32_t dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
