@@ -253,9 +253,12 @@ def run_ours(args):
     f = sigmoid_loss(None, periodicity_overwrite=PERIOD, dist_dig_parameters_overwrite=SIG,
                      process_group=(dist.group.WORLD if world > 1 else None))
 
+    from encodermap_b200 import parallel
+
     def e2e_step():
-        xd = xh.to(dev, non_blocking=True)
-        zd = zh.to(dev, non_blocking=True).requires_grad_(True)
+        # N > 1: every rank moves 1/N of the (replicated) input over its own host link, NVLink all-gathers the rest
+        xd = parallel.replicate_from_host(xh, dev)
+        zd = parallel.replicate_from_host(zh, dev).requires_grad_(True)
         l = f(xd, zd)
         l.backward()
         gh.copy_(zd.grad, non_blocking=True)
@@ -322,8 +325,8 @@ def run_ours(args):
                          "peak_source": f"148 SM x 128 lanes x {peaks['sm_max_mhz']} MHz ({peaks['source']}); no FP32 figure is measured there"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "unique pairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": (xh.numel() + zh.numel()) * 4, "d2h_bytes_per_step": gh.numel() * 4 + 4,
-                    "note": "per rank: inputs are replicated, every rank copies them in and reads loss + gradient back"},
+                    "h2d_bytes_per_step": (xh.numel() + zh.numel()) * 4 // world, "d2h_bytes_per_step": gh.numel() * 4 + 4,
+                    "note": "per rank: 1/n_gpus of the replicated input over the host link + NCCL all-gather over NVLink (parallel.replicate_from_host); every rank reads loss + gradient back"},
             "gpu_launches": args.steps * world,
             "cpu_baseline": cpu_baseline,
             "extra": extra,

@@ -101,3 +101,25 @@ def data_parallel_sigmoid_cost(high_local: torch.Tensor, low_local: torch.Tensor
     latent rows.  The value is the same on every rank; averaging of the dense-layer gradients is the host
     framework's usual data-parallel all-reduce."""
     return _DataParallelCost.apply(high_local, low_local, periodicity, tuple(sig), group, partial_fn)
+
+
+def replicate_from_host(x_host: torch.Tensor, device: torch.device, group=None) -> torch.Tensor:
+    """Device copy of a host tensor that every rank holds (the replicated input of the full-set cost), built from
+    one slice per rank: each rank copies rows [r n / G, (r+1) n / G) over its own PCIe link and the slices are
+    all-gathered over NVLink.  At 8 ranks this moves 1/8 of the bytes per host link (268 MB -> 34 MB at 65 536 x 1 024)
+    and the exchange runs at NVSwitch speed.  Falls back to a plain copy for a single rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return x_host.to(device, non_blocking=True)
+    rank = dist.get_rank(group)
+    n = x_host.shape[0]
+    per = (n + world - 1) // world
+    out = torch.empty((per * world,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=device)
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    mine = out[rank * per:(rank + 1) * per]
+    if hi > lo:
+        mine[:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+    if hi - lo < per:
+        mine[hi - lo:].zero_()
+    dist.all_gather_into_tensor(out, mine, group=group)   # in place: `mine` is this rank's slice of `out`
+    return out[:n]

@@ -65,6 +65,9 @@ def _worker(rank, world, port, q):
         zl = low[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
         dp = parallel.data_parallel_sigmoid_cost(high[rank * rows:(rank + 1) * rows], zl, 2 * math.pi, SIG, partial_fn=_oracle_partial)
         dp.backward()
+        # host -> device replication from one slice per rank (7 rows over 2 ranks: a ragged last slice)
+        xh = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
+        assert torch.equal(parallel.replicate_from_host(xh, torch.device("cpu")), xh)
         q.put((rank, loss.item(), grad.numpy(), parallel.tile_range(n, rank, world), fr, dp.item(), zl.grad.numpy()))
     finally:
         dist.destroy_process_group()
