@@ -652,7 +652,8 @@ constexpr int BWD_CA = 13;   // atoms per thread that size the thread count per 
 // cancels, float32 is enough (errors random-walk to ~2e-6 relative over 750 steps, the tolerance is 1e-5), and
 // the formulas of the two ends are mirror images: with e1 = x(a_{i+1}) - x(a_i), e2 = x(a_{i+2}) - x(a_{i+1})
 //     dihedral term = -<unit(e2), M_i>,   angle term = <unit(e1 x e2), M_i>,   length term = -<unit(e1), S_i>
-// on both sides (tools/proto_backmap.py derives them; tests compare with float64 autograd of the reference order).
+// on both sides (tests/test_oracle_kats.py::test_moving_pivot_backward_formulas states this algorithm sequentially in
+// float64 and pins it to float64 autograd of the reference order; the GPU tests compare the kernel itself).
 // Chunks of consecutive walk steps per thread; chunk aggregates are combined by a scan whose operator shifts the
 // pivot:  (S_A, M_A about p_A) then (S_C, M_C about p_C)  ->  (S_A + S_C, M_C + M_A - (p_C - p_A) x S_A).
 // Left of the anchor an angle / length also moves the anchor itself along the planar chain, i.e. the whole

@@ -208,3 +208,63 @@ def test_dihedral_vjp_closed_form_matches_autograd():
         (xyz * torch.from_numpy(w)).sum().backward()
         got = O.dihedral_vjp_from_xyz(xyz.detach().numpy(), w)
         np.testing.assert_allclose(got, dih.grad.numpy(), rtol=1e-9, atol=1e-11)
+
+
+def _moving_pivot_vjp(xyz, g, lengths, angles):
+    """Sequential float64 statement of the backward kernel's algorithm (backmap.cu, "backward, version 3"): both ends
+    are walked towards the anchor, the wrench (S, M) of the end is kept about the atom the walk has reached, and the
+    three terms of a cut are  -<unit(e2), M>,  <unit(e1 x e2), M>,  -<unit(e1), S>;  left of the anchor an angle /
+    length also moves the whole molecule along the planar chain."""
+    n = xyz.shape[0]
+    dr0 = n // 2 - 1
+    rD, rA, rL = np.zeros(n), np.zeros(n), np.zeros(n)          # per cut
+    tot = {}
+    for side in (0, 1):
+        steps = dr0 if side == 0 else n - 1 - dr0
+        a = (lambda i: i) if side == 0 else (lambda i: n - 1 - i)
+        S, M = np.zeros(3), np.zeros(3)
+        for i in range(steps):
+            S = S + g[a(i)]
+            e1 = xyz[a(i + 1)] - xyz[a(i)]
+            M = M - np.cross(e1, S)
+            j2 = a(i + 2)
+            e2 = xyz[min(max(j2, 0), n - 1)] - xyz[a(i + 1)]
+            cut = i if side == 0 else n - 2 - i
+            with np.errstate(all="ignore"):
+                rD[cut] = -np.dot(e2, M) / np.linalg.norm(e2)
+                c = np.cross(e1, e2)
+                rA[cut] = np.dot(c, M) / np.linalg.norm(c)
+            rL[cut] = -np.dot(e1, S) / np.linalg.norm(e1)
+        tot[side] = (S, M)
+    # left-of-anchor planar terms: total wrench about x_{dr0}, planar chain from (lengths, angles)
+    F = tot[0][0] + tot[1][0] + g[dr0]
+    Mref = tot[0][1] + tot[1][1]
+    pos, ang_dir = np.zeros(2), 0.0
+    for k in range(dr0):
+        d = np.array([np.cos(ang_dir), np.sin(ang_dir)])
+        pos = pos + lengths[k] * d                                 # planar atom k+1
+        tz = Mref[2] + ((xyz[dr0][0] - pos[0]) * F[1] - (xyz[dr0][1] - pos[1]) * F[0])
+        rA[k] += -tz if k & 1 else tz
+        rL[k] += d[0] * F[0] + d[1] * F[1]
+        ang_dir += -((-1) ** k) * (np.pi - angles[k])              # turn at atom k+1
+    gD = np.array([rD[d] if d < dr0 else rD[d + 2] for d in range(n - 3)])
+    gA = np.array([rA[j] if j < dr0 else rA[j + 1] for j in range(n - 2)])
+    gL = np.array([rL[k] for k in range(n - 1)])
+    return gD, gA, gL
+
+
+def test_moving_pivot_backward_formulas():
+    """The formulas the CUDA backward implements, stated sequentially in float64, equal float64 autograd of the
+    restated BackMapLayer (per-frame bond lengths so that d/d(lengths) is checked too)."""
+    rng = np.random.default_rng(11)
+    for n in (6, 7, 8, 9, 30, 31):
+        dist = torch.from_numpy(rng.uniform(0.13, 0.15, size=(1, n - 1))).requires_grad_(True)
+        ang = torch.from_numpy(rng.uniform(1.9, 2.2, size=(1, n - 2))).requires_grad_(True)
+        dih = torch.from_numpy(rng.uniform(-np.pi, np.pi, size=(1, n - 3))).requires_grad_(True)
+        w = rng.normal(size=(1, n, 3))
+        xyz = O.back_map_layer(dist, ang, dih)
+        (xyz * torch.from_numpy(w)).sum().backward()
+        gD, gA, gL = _moving_pivot_vjp(xyz.detach().numpy()[0], w[0], dist.detach().numpy()[0], ang.detach().numpy()[0])
+        np.testing.assert_allclose(gD, dih.grad.numpy()[0], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(gA, ang.grad.numpy()[0], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(gL, dist.grad.numpy()[0], rtol=1e-8, atol=1e-10)
