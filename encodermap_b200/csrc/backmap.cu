@@ -738,11 +738,13 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
   // planar inputs: the whole rows in planar mode, only the bonds / angles left of the anchor for the left-side terms
   const int nL = planar ? n - 1 : p.dr0, nA = planar ? n - 2 : p.dr0;
   const int rX = (3 * n + 27) & ~3, rG = (3 * n + 7) & ~3, rL = (nL + 7) & ~3, rA = (nA + 7) & ~3;
-  float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0));
+  const int rP = extras ? 8 * (T / 2) : 0;   // one SE(2) element (4 doubles) per left thread: planar halves computed by the right threads
+  float* base = smem + (size_t)g * (rX + rG + (need_planar ? rL + rA : 0) + rP);
   float* sX = base + 4;   // 4 floats of slack in front: the walk may read (never use) one atom before the chain
   float* sG = base + rX;
   float* sL = sG + rG;
   float* sA = sL + rL;
+  double* pexch = reinterpret_cast<double*>(sA + rA);   // (rX + rG + rL + rA) is a multiple of 4 floats: 16-byte aligned
   if (active) {
     sG = stage_row16<T>(sG, p.grad_xyz + fr * (int64_t)(3 * n), 3 * n, t);
     if (!planar) sX = stage_row16<T>(sX, p.xyz + fr * (int64_t)(3 * n), 3 * n, t);
@@ -769,7 +771,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
   const int a0 = side ? n - 1 - i0 : i0;              // atom of walk index i0
 
   // ---- planar chain ------------------------------------------------------------------------------------------
-  Se2 pl_ex{1.0, 0.0, 0.0, 0.0};   // left threads with extras: planar state before bond i0
+  Se2 pl_ex{1.0, 0.0, 0.0, 0.0}, pl_ex2{1.0, 0.0, 0.0, 0.0};   // left threads with extras: planar state before bond i0 / imid
+  int imid = 0;
   if (planar) {
     // chain_in_plane backward: recompute the planar coordinates into sX (ascending chunks of BWD_CA atoms)
     const int k0 = min(n, t * BWD_CA), k1 = min(n, k0 + BWD_CA);
@@ -798,10 +801,17 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     }
     __syncthreads();
   } else if (extras) {
-    // planar SE(2) product of this left thread's bonds, exclusive prefix over the left threads (they are the low ones)
+    // Planar SE(2) chain of the bonds left of the anchor.  The chunk of left thread q is cut in two: the left thread
+    // walks the first half, its idle partner on the right side (thread q + T/2) the second half, each leaving the planar
+    // atoms in the frame of its own first bond in the slots of (L_k, theta_k); pass 2 then only needs float32 arithmetic on
+    // these local coordinates (< 1 nm) and the float64 prefix of the half it is in.
+    const int CLs = ((p.dr0 + TL - 1) / TL) | 1;
+    const int lo = min(p.dr0, q * CLs), hi = min(p.dr0, lo + CLs);
+    imid = lo + (hi - lo + 1) / 2;
+    const int ka = side == 0 ? lo : imid, kb = side == 0 ? imid : hi;
     Se2 part{1.0, 0.0, 0.0, 0.0};
-    if (active && side == 0)
-      for (int k = i0; k < i1; k++) {
+    if (active)
+      for (int k = ka; k < kb; k++) {
         part.x = fma((double)sL[k], part.c, part.x);
         part.y = fma((double)sL[k], part.s, part.y);
         double sn, cs;
@@ -809,12 +819,14 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
         const double cw = -cs, sw = (k & 1) ? sn : -sn;
         const double c2 = part.c * cw - part.s * sw, s2 = part.c * sw + part.s * cw;
         part.c = c2; part.s = s2;
-        // planar atom k+1 in the frame of this thread's first bond replaces (L_k, theta_k): pass 2 only needs
-        // float32 arithmetic on these chunk-local coordinates (< 2 nm) and the float64 prefix of the chunk
         sL[k] = (float)part.x;
         sA[k] = (float)part.y;
       }
-    Se2 inc = part;
+    if (side == 1) { pexch[4 * q] = part.c; pexch[4 * q + 1] = part.s; pexch[4 * q + 2] = part.x; pexch[4 * q + 3] = part.y; }
+    __syncthreads();
+    // scan over the left threads of (first half o second half); right threads carry the identity
+    Se2 inc{1.0, 0.0, 0.0, 0.0};
+    if (side == 0) inc = se2_mul(part, Se2{pexch[4 * q], pexch[4 * q + 1], pexch[4 * q + 2], pexch[4 * q + 3]});
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       Se2 up = se2_shfl_up(inc, d);
@@ -826,7 +838,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
     __syncthreads();
     Se2 prev{1.0, 0.0, 0.0, 0.0};
     for (int w = 0; w < wf; w++) prev = se2_mul(prev, Se2{psum[g][w][0], psum[g][w][1], psum[g][w][2], psum[g][w][3]});
-    pl_ex = se2_mul(prev, ex);
+    pl_ex = se2_mul(prev, ex);         // before the first half
+    pl_ex2 = se2_mul(pl_ex, part);     // before the second half (left threads: part is the first half)
   }
 
   // ---- pass 1: wrench of this thread's chunk about x(a_{i1}) ------------------------------------------------------
@@ -917,8 +930,8 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
         mt[i] = side_tot[g][0][3 + i] + side_tot[g][1][3 + i];
       }
     }
-    const float plc = (float)pl_ex.c, pls = (float)pl_ex.s, plx = (float)pl_ex.x, ply = (float)pl_ex.y;
-    float llx = 0.f, lly = 0.f;   // chunk-local planar position of atom i (the chunk starts at its own origin)
+    float plc = (float)pl_ex.c, pls = (float)pl_ex.s, plx = (float)pl_ex.x, ply = (float)pl_ex.y;
+    float llx = 0.f, lly = 0.f;   // local planar position of atom i (each half of the chunk starts at its own origin)
     float s0 = ex.s[0], s1 = ex.s[1], s2 = ex.s[2], m0 = ex.m[0], m1 = ex.m[1], m2 = ex.m[2];
     const float* px = sX + 3 * a0 + 2 * st;   // x(a_{i+2}); one atom beyond the chain end is slack / the neighbouring row
     float* pg = sG + 3 * a0;
@@ -946,7 +959,11 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
         }
         if (wantL) rL = -(e10 * s0 + e11 * s1 + e12 * s2) * rsqrt_fast(fmaf(e10, e10, fmaf(e11, e11, e12 * e12)));
         if (lext) {
-          // planar atom k+1 (k = i) from its chunk-local coordinates; planar direction of bond k from two of them
+          if (i == imid) {   // second half of the chunk: its own prefix and origin
+            plc = (float)pl_ex2.c; pls = (float)pl_ex2.s; plx = (float)pl_ex2.x; ply = (float)pl_ex2.y;
+            llx = 0.f; lly = 0.f;
+          }
+          // planar atom k+1 (k = i) from its local coordinates; planar direction of bond k from two of them
           const float lx = sL[i], ly = sA[i];
           const float cn0 = fmaf(plc, lx, fmaf(-pls, ly, plx)), cn1 = fmaf(pls, lx, fmaf(plc, ly, ply));
           // z-torque of the whole molecule about planar atom k+1
@@ -1100,7 +1117,8 @@ static int launch_bwd3(const BwdParams& p, const double2* tab, bool need_planar,
   const size_t n = (size_t)p.n;
   const size_t nL = p.planar ? n - 1 : (size_t)p.dr0, nA = p.planar ? n - 2 : (size_t)p.dr0;
   const size_t per_frame = ((3 * n + 27) & ~(size_t)3) + ((3 * n + 7) & ~(size_t)3) +
-                           (need_planar ? ((nL + 7) & ~(size_t)3) + ((nA + 7) & ~(size_t)3) : 0);
+                           (need_planar ? ((nL + 7) & ~(size_t)3) + ((nA + 7) & ~(size_t)3) : 0) +
+                           (need_planar && !p.planar ? 8 * (size_t)(T / 2) : 0);
   const size_t smem = FPC * per_frame * sizeof(float);
   EMK_REQUIRE(smem <= 200 * 1024, EMK_E_UNSUPPORTED, "back-mapping backward: chain of %d atoms needs %zu bytes of staging shared memory", p.n, smem);
   auto kern = backmap_bwd3_kernel<T, GEN>;
