@@ -529,6 +529,33 @@ def test_backmap_vs_oracle(em, n, b):
     assert np.abs(diff).max() < 2e-3
 
 
+def test_backmap_nan_and_inf_propagate(em):
+    """A NaN / Inf internal coordinate poisons exactly the atoms the reference's rotate-the-tail loop would move
+    (so that the models' finite asserts fire), and leaves every other frame untouched."""
+    from encodermap_b200.models.layers import back_map
+
+    rng = np.random.default_rng(9)
+    n, b = 200, 4
+    dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+    clean = back_map(cu(dist), cu(ang), cu(dih)).cpu().numpy()
+    dih[1, 150] = np.nan        # right of the anchor
+    dih[2, 20] = np.inf         # left of the anchor (sin/cos of inf is NaN)
+    ang[3, 120] = np.nan
+    got = back_map(cu(dist), cu(ang), cu(dih)).cpu().numpy()
+    want = O.back_map_layer(dist.astype(np.float64), ang.astype(np.float64), dih.astype(np.float64)).numpy()
+    np.testing.assert_allclose(got[0], clean[0], atol=0)                     # untouched frame: bit-identical
+    # dihedral NaN: the atoms the reference moves.  The reference also turns the PIVOT of that rotation into NaN
+    # ((pivot - pivot) * NaN in `pivot + (t - pivot) R`, misc/backmapping.py:1907-1909); the NeRF form never touches it.
+    for f in (1, 2):
+        ours, ref = np.isnan(got[f]).any(axis=1), np.isnan(want[f]).any(axis=1)
+        assert ours.any() and not (ours & ~ref).any() and (ref & ~ours).sum() <= 1
+        both = ~ours & ~ref
+        assert np.abs(got[f][both] - want[f][both]).max() < COORD_ATOL
+    assert np.isnan(got[3]).any() and np.isnan(want[3]).any()                # an angle NaN enters the planar chain too
+
+
 def test_backmap_unwrapped_angles(em):
     """Angles far outside (-pi, pi] (the reference accepts any float): forward and backward still match float64."""
     from encodermap_b200.models.layers import back_map
