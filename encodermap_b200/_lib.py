@@ -92,6 +92,8 @@ SIGNATURES = {
     "emk_dihedrals_to_cartesian_bwd": ([vp, vp, i64, i64, C.c_int, vp, vp], C.c_int),
     "emk_dl_dihedrals_to_cartesian": ([vp, vp, C.c_int, vp, vp], C.c_int),
     "emk_dl_dihedrals_to_cartesian_bwd": ([vp, vp, C.c_int, vp, vp], C.c_int),
+    "emk_dihedrals_to_cartesian_chain_bwd": ([vp, i64, vp, vp, i64, i64, C.c_int, vp, vp], C.c_int),
+    "emk_dl_dihedrals_to_cartesian_chain_bwd": ([vp, vp, vp, C.c_int, vp, vp], C.c_int),
 }
 
 

@@ -289,30 +289,34 @@ class ChainInPlane(torch.autograd.Function):
 
 
 class DihedralsToCartesian(torch.autograd.Function):
-    """Arbitrary start chain.  Differentiable w.r.t. the dihedrals; the gradient w.r.t. the start chain
-    is not implemented (in the models the chain comes from chain_in_plane and the fused BackMap op
-    carries that gradient)."""
+    """Arbitrary start chain, differentiable w.r.t. the dihedrals and the start chain (a rank-2 chain is shared by
+    all frames, as the reference tiles it: its gradient is the sum over frames)."""
 
     @staticmethod
     def forward(ctx, dihedrals, cartesian, one_way):
         require_cuda(dihedrals, "dihedrals")
         dihedrals, cartesian = f32c(dihedrals), f32c(cartesian)
-        if cartesian.requires_grad:
-            raise NotImplementedError("dihedrals_to_cartesian: gradient w.r.t. the start chain is not implemented; "
-                                      "use BackMapLayer / back_map for the differentiable composition")
         b, n = dihedrals.shape[0], dihedrals.shape[1] + 3
         xyz = _empty_like_shape(dihedrals, (b, n, 3))
         with torch.cuda.device(dihedrals.device):
             check(_lib.lib().emk_dl_dihedrals_to_cartesian(DL(dihedrals), DL(cartesian), int(one_way), DL(xyz), stream_of(dihedrals)))
-        ctx.save_for_backward(xyz)
+        ctx.save_for_backward(xyz, cartesian)
         ctx.one_way = int(one_way)
         return xyz
 
     @staticmethod
     def backward(ctx, grad_xyz):
-        (xyz,) = ctx.saved_tensors
+        xyz, cartesian = ctx.saved_tensors
         grad_xyz = f32c(grad_xyz)
-        gd = _empty_like_shape(xyz, (xyz.shape[0], xyz.shape[1] - 3))
+        need_d, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gd = gc = None
         with torch.cuda.device(xyz.device):
-            check(_lib.lib().emk_dl_dihedrals_to_cartesian_bwd(DL(xyz), DL(grad_xyz), ctx.one_way, DL(gd), stream_of(xyz)))
-        return gd, None, None
+            if need_d:
+                gd = _empty_like_shape(xyz, (xyz.shape[0], xyz.shape[1] - 3))
+                check(_lib.lib().emk_dl_dihedrals_to_cartesian_bwd(DL(xyz), DL(grad_xyz), ctx.one_way, DL(gd), stream_of(xyz)))
+            if need_c:
+                gc = torch.empty_like(xyz)
+                check(_lib.lib().emk_dl_dihedrals_to_cartesian_chain_bwd(DL(cartesian), DL(xyz), DL(grad_xyz), ctx.one_way, DL(gc), stream_of(xyz)))
+                if cartesian.dim() == 2:
+                    gc = gc.sum(dim=0)
+        return gd, gc, None

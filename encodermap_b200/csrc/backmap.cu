@@ -1005,6 +1005,146 @@ __global__ void __launch_bounds__((T < 128 ? 128 : T)) backmap_bwd3_kernel(const
 }
 
 // ====================================================================================================
+// dihedrals_to_cartesian: gradient w.r.t. the START chain (the models never need it -- BackMapLayer carries the
+// gradient of the fused composition -- but the reference's operator is differentiable in both arguments).
+//
+// Twisting about bonds keeps every bond length and bond angle and shifts every dihedral by its twist, so the build is
+//     out_k = place(out_{k-3}, out_{k-2}, out_{k-1};  L_{k-1}(start), theta_{k-2}(start), delta_{k-3}(start) + twist_{k-3}),   out_{0,1,2} = start_{0,1,2}
+// (per side, in the side's chain order).  Its reverse mode is one walk from the chain end to the anchor: the adjoint of
+// out_k is pushed through `place` onto the three previous atoms and onto (L, theta, Delta), and those three scalars are
+// pushed through the internal coordinates of the START window (start_{k-3..k}).  Everything `place` needs is read off the
+// final coordinates.  Sequential along the chain: one thread per frame, float64, sliding windows in registers.
+// tests/test_oracle_kats.py::test_start_chain_vjp_prototype states the same algorithm in numpy (1e-15 from autograd).
+// ====================================================================================================
+struct D3 {
+  double x, y, z;
+};
+__device__ __forceinline__ D3 d3(double x, double y, double z) { return D3{x, y, z}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return D3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return D3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ double dot3(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 cross3(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ D3 ldf3(const float* p) { return D3{(double)p[0], (double)p[1], (double)p[2]}; }
+
+struct FrameD {
+  D3 u, n, m, ab;
+  double lbc, ln;
+};
+// u = unit(c - b), n = unit((b - a) x u), m = n x u
+__device__ __forceinline__ FrameD frame_of(D3 a, D3 b, D3 c) {
+  FrameD f;
+  const D3 bc = c - b;
+  f.ab = b - a;
+  f.lbc = sqrt(dot3(bc, bc));
+  f.u = (1.0 / f.lbc) * bc;
+  const D3 nraw = cross3(f.ab, f.u);
+  f.ln = sqrt(dot3(nraw, nraw));
+  f.n = (1.0 / f.ln) * nraw;
+  f.m = cross3(f.n, f.u);
+  return f;
+}
+// adjoint of frame_of: (ubar, nbar, mbar) -> (abar, bbar, cbar)
+__device__ __forceinline__ void frame_vjp(const FrameD& f, D3 ub, D3 nb, D3 mb, D3* ab_, D3* bb_, D3* cb_) {
+  nb = nb + cross3(f.u, mb);
+  ub = ub + cross3(mb, f.n);
+  const D3 nrawb = (1.0 / f.ln) * (nb - dot3(f.n, nb) * f.n);
+  const D3 abb = cross3(f.u, nrawb);
+  ub = ub + cross3(nrawb, f.ab);
+  const D3 bcb = (1.0 / f.lbc) * (ub - dot3(f.u, ub) * f.u);
+  *ab_ = -1.0 * abb;
+  *bb_ = abb - bcb;
+  *cb_ = bcb;
+}
+
+// one side.  Chain position p is atom first + dir * p; `len` positions.  gscale0 = 0 drops the upstream gradient of the
+// first three positions (the right build's anchor outputs are discarded by the reference's concat); add_first3 adds
+// to grad_chain there instead of storing (the two sides share the three middle atoms).
+__device__ void chain_bwd_side(const float* __restrict__ start, const float* __restrict__ fin, const float* __restrict__ g,
+                               float* __restrict__ out, int first, int dir, int len, double gscale0, bool add_first3) {
+  auto at = [&](int pidx) { return 3 * (first + dir * pidx); };
+  D3 P0 = d3(0, 0, 0), P1 = P0, P2 = P0;   // propagated adjoints of final points k, k-1, k-2
+  D3 S0 = P0, S1 = P0, S2 = P0;             // start adjoints of points k, k-1, k-2 (from the windows already visited)
+  for (int k = len - 1; k >= 3; k--) {
+    const D3 fa = ldf3(fin + at(k - 3)), fb = ldf3(fin + at(k - 2)), fc = ldf3(fin + at(k - 1)), fd = ldf3(fin + at(k));
+    const D3 db = ldf3(g + at(k)) + P0;
+    // ---- adjoint of place() at the final points
+    const FrameD f = frame_of(fa, fb, fc);
+    const D3 w = fd - fc;
+    const double L = sqrt(dot3(w, w));
+    const double ct = -dot3(w, f.u) / L, st = sqrt(fmax(0.0, 1.0 - ct * ct));
+    const double xx = dot3(w, f.m), yy = dot3(w, f.n);
+    const double cd = xx / (L * st), sd = yy / (L * st);
+    const double Lb = dot3(db, w) / L;
+    const double tb = L * dot3(db, st * f.u + ct * (cd * f.m + sd * f.n));
+    const double Db = L * st * dot3(db, cd * f.n - sd * f.m);
+    D3 ab_, bb_, cb_;
+    frame_vjp(f, (-L * ct) * db, (L * st * sd) * db, (L * st * cd) * db, &ab_, &bb_, &cb_);
+    P0 = P1 + cb_ + db;
+    P1 = P2 + bb_;
+    P2 = ab_;
+    // ---- adjoint of (L, theta, Delta) of the START window
+    const D3 sa = ldf3(start + at(k - 3)), sb = ldf3(start + at(k - 2)), sc = ldf3(start + at(k - 1)), sdp = ldf3(start + at(k));
+    const FrameD fs = frame_of(sa, sb, sc);
+    const D3 ws = sdp - sc;
+    const double Ls = sqrt(dot3(ws, ws));
+    const double wu = dot3(ws, fs.u);
+    const double q = -wu / Ls, sts = sqrt(fmax(1e-300, 1.0 - q * q));
+    const double xs_ = dot3(ws, fs.m), ys_ = dot3(ws, fs.n);
+    const double qb = -tb / sts;
+    const double r2 = xs_ * xs_ + ys_ * ys_;
+    const double xb = -ys_ / r2 * Db, yb = xs_ / r2 * Db;
+    const D3 wb = (Lb / Ls) * ws + qb * ((-1.0 / Ls) * fs.u + (wu / (Ls * Ls * Ls)) * ws) + xb * fs.m + yb * fs.n;
+    D3 a2, b2, c2;
+    frame_vjp(fs, (-qb / Ls) * ws, yb * ws, xb * ws, &a2, &b2, &c2);
+    const D3 outk = S0 + wb;
+    float* o = out + at(k);
+    o[0] = (float)outk.x; o[1] = (float)outk.y; o[2] = (float)outk.z;
+    S0 = S1 + (c2 - wb);
+    S1 = S2 + b2;
+    S2 = a2;
+  }
+  // the three anchor positions of the side (positions 2, 1, 0 hold P0/S0, P1/S1, P2/S2 when len > 3; shorter chains
+  // never entered the loop and all six are zero)
+  const D3 Pk[3] = {P0, P1, P2}, Sk[3] = {S0, S1, S2};
+  for (int j = 0; j < 3 && 2 - j < len; j++) {
+    const int k = 2 - j;
+    const D3 v = Sk[j] + Pk[j] + gscale0 * ldf3(g + at(k));
+    float* o = out + at(k);
+    if (add_first3) { o[0] += (float)v.x; o[1] += (float)v.y; o[2] += (float)v.z; }
+    else { o[0] = (float)v.x; o[1] = (float)v.y; o[2] = (float)v.z; }
+  }
+}
+
+__global__ void __launch_bounds__(128) d2c_chain_bwd_kernel(const float* __restrict__ chain, int64_t cstride, const float* __restrict__ xyz,
+                                                           const float* __restrict__ grad_xyz, int64_t b, int n, int one_way,
+                                                           float* __restrict__ grad_chain) {
+  const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= b) return;
+  const float* st = chain + frame * cstride;
+  const float* fin = xyz + frame * (int64_t)(3 * n);
+  const float* g = grad_xyz + frame * (int64_t)(3 * n);
+  float* out = grad_chain + frame * (int64_t)(3 * n);
+  if (one_way) {
+    chain_bwd_side(st, fin, g, out, 0, 1, n, 1.0, false);
+  } else {
+    const int s = n / 2;
+    chain_bwd_side(st, fin, g, out, s + 1, -1, s + 2, 1.0, false);          // atoms s+1 .. 0
+    chain_bwd_side(st, fin, g, out, s - 1, 1, n - s + 1, 0.0, true);        // atoms s-1 .. n-1; its first three outputs are dropped
+  }
+}
+
+int d2c_chain_bwd_device(const float* chain, int64_t cstride, const float* xyz, const float* grad_xyz, int64_t b, int64_t n, int one_way,
+                         float* grad_chain, cudaStream_t st) {
+  EMK_REQUIRE(chain && xyz && grad_xyz && grad_chain, EMK_E_NULL, "emk_dihedrals_to_cartesian_chain_bwd: NULL pointer argument");
+  EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_dihedrals_to_cartesian_chain_bwd: need 4 <= n_atoms < 2^20");
+  EMK_REQUIRE(b >= 0 && (cstride == 0 || cstride == 3 * n), EMK_E_ARG, "emk_dihedrals_to_cartesian_chain_bwd: chain_batch_stride must be 0 or 3*n_atoms");
+  if (b == 0) return EMK_OK;
+  d2c_chain_bwd_kernel<<<(unsigned)((b + 127) / 128), 128, 0, st>>>(chain, cstride, xyz, grad_xyz, b, (int)n, one_way, grad_chain);
+  return launch_status("d2c_chain_bwd_kernel");
+}
+
+// ====================================================================================================
 // host launchers
 // ====================================================================================================
 static int pick_warps(size_t floats_per_warp, size_t shared_floats, int* warps, size_t* smem_bytes) {

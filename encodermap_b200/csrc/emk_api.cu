@@ -98,6 +98,7 @@ int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int6
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
 int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
 int fp32_probe_device(double*);
+int d2c_chain_bwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int pairwise_periodic_bwd_device(const float*, int64_t, int64_t, double, const float*, const float*, float*, cudaStream_t);
 int chain_in_plane_device(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 int d2c_general_device(const float*, const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
@@ -680,6 +681,30 @@ int emk_dl_dihedrals_to_cartesian_bwd(const DLManagedTensor* xyz, const DLManage
   const int64_t b = xv.shape[0], n = xv.shape[1];
   EMK_REQUIRE(xv.shape[2] == 3 && gv.numel == xv.numel && ov.shape[0] == b && ov.shape[1] == n - 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian_bwd: shape mismatch");
   return emk_dihedrals_to_cartesian_bwd(F(xv), F(gv), b, n, one_way, F(ov), stream);
+}
+
+int emk_dihedrals_to_cartesian_chain_bwd(const float* chain, int64_t chain_batch_stride, const float* xyz, const float* grad_xyz, int64_t b,
+                                         int64_t n_atoms, int one_way, float* grad_chain, void* stream) {
+  return d2c_chain_bwd_device(chain, chain_batch_stride, xyz, grad_xyz, b, n_atoms, one_way, grad_chain, as_stream(stream));
+}
+int emk_dl_dihedrals_to_cartesian_chain_bwd(const DLManagedTensor* chain, const DLManagedTensor* xyz, const DLManagedTensor* grad_xyz,
+                                            int one_way, DLManagedTensor* grad_chain, void* stream) {
+  VIEW(cv, chain, "cartesian", 2, 3);
+  VIEW(xv, xyz, "xyz", 3, 3);
+  VIEW(gv, grad_xyz, "grad_xyz", 3, 3);
+  VIEW(ov, grad_chain, "grad_chain", 3, 3);
+  const int64_t b = xv.shape[0], n = xv.shape[1];
+  EMK_REQUIRE(xv.shape[2] == 3 && gv.numel == xv.numel && ov.numel == xv.numel, EMK_E_SHAPE,
+              "emk_dl_dihedrals_to_cartesian_chain_bwd: xyz, grad_xyz and grad_chain must be (b, n_atoms, 3)");
+  int64_t cs;
+  if (cv.ndim == 2) {
+    EMK_REQUIRE(cv.shape[0] == n && cv.shape[1] == 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian_chain_bwd: cartesian must be (n_atoms,3)");
+    cs = 0;
+  } else {
+    EMK_REQUIRE(cv.shape[0] == b && cv.shape[1] == n && cv.shape[2] == 3, EMK_E_SHAPE, "emk_dl_dihedrals_to_cartesian_chain_bwd: cartesian must be (b,n_atoms,3)");
+    cs = 3 * n;
+  }
+  return d2c_chain_bwd_device(F(cv), cs, F(xv), F(gv), b, n, one_way, F(ov), as_stream(stream));
 }
 
 }  // extern "C"

@@ -220,6 +220,13 @@ EMK_API int emk_dl_dihedrals_to_cartesian(const DLManagedTensor* dihedrals, cons
                                   DLManagedTensor* xyz, void* stream);
 EMK_API int emk_dl_dihedrals_to_cartesian_bwd(const DLManagedTensor* xyz, const DLManagedTensor* grad_xyz, int one_way,
                                       DLManagedTensor* grad_dihedrals, void* stream);
+/* VJP of dihedrals_to_cartesian w.r.t. the START chain (grad_chain is (b, n_atoms, 3), one row per frame even when the
+ * chain is shared: the caller sums over frames).  xyz is the forward output.  Reverse mode of the placement recursion,
+ * one thread per frame in float64 (encodermap_tf1/backmapping.py:164-214 is differentiable in both arguments). */
+EMK_API int emk_dihedrals_to_cartesian_chain_bwd(const float* chain, int64_t chain_batch_stride, const float* xyz, const float* grad_xyz,
+                                                 int64_t b, int64_t n_atoms, int one_way, float* grad_chain, void* stream);
+EMK_API int emk_dl_dihedrals_to_cartesian_chain_bwd(const DLManagedTensor* chain, const DLManagedTensor* xyz,
+                                                    const DLManagedTensor* grad_xyz, int one_way, DLManagedTensor* grad_chain, void* stream);
 
 #ifdef __cplusplus
 }

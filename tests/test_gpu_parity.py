@@ -635,6 +635,19 @@ def test_chain_and_d2c_backward(em):
             (oo * torch.from_numpy(w)).sum().backward()
             assert np.abs(out.detach().cpu().numpy() - oo.detach().numpy()).max() < COORD_ATOL
             assert relnorm(hg.grad.cpu().numpy(), ho.grad.numpy()) < GRAD_RTOL
+            # gradient w.r.t. the start chain: shared (rank 2, summed over frames) and per frame (rank 3)
+            for shared in (True, False):
+                s_np = start if shared else np.repeat(start[None], b, axis=0) + rng.normal(scale=0.01, size=(b, n, 3)).astype(np.float32)
+                sg = cu(s_np).requires_grad_(True)
+                hg2 = cu(dih).requires_grad_(True)
+                (fn(hg2, sg) * cu(w)).sum().backward()
+                so = torch.from_numpy(s_np).double().requires_grad_(True)
+                ho2 = torch.from_numpy(dih).double().requires_grad_(True)
+                ref = ofn(ho2, so) if shared else (O.dihedrals_to_cartesian_tf1(ho2, so) if fn is dihedrals_to_cartesian_tf else O.dihedral_to_cartesian_one_way(ho2, so))
+                (ref * torch.from_numpy(w)).sum().backward()
+                assert sg.grad.shape == sg.shape
+                assert relnorm(sg.grad.cpu().numpy(), so.grad.numpy()) < 2e-5
+                assert relnorm(hg2.grad.cpu().numpy(), ho2.grad.numpy()) < 2e-5
 
 
 def test_index_construction_bit_exact(em, golden):

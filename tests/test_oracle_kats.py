@@ -268,3 +268,101 @@ def test_moving_pivot_backward_formulas():
         np.testing.assert_allclose(gD, dih.grad.numpy()[0], rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(gA, ang.grad.numpy()[0], rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(gL, dist.grad.numpy()[0], rtol=1e-8, atol=1e-10)
+
+
+# ---- start-chain VJP of dihedrals_to_cartesian: the algorithm of d2c_chain_bwd_kernel (backmap.cu) in numpy float64 ----
+def _cv_frame(a, b, c):
+    bc = c - b; ab = b - a
+    lbc = np.linalg.norm(bc); u = bc / lbc
+    nraw = np.cross(ab, u); ln = np.linalg.norm(nraw); nn = nraw / ln
+    m = np.cross(nn, u)
+    return u, nn, m, lbc, ln, ab
+
+def _cv_frame_vjp(a, b, c, ub, nb, mb):
+    """adjoint of (u, n, m) = _cv_frame(a, b, c)"""
+    u, nn, m, lbc, ln, ab = _cv_frame(a, b, c)
+    nb = nb + np.cross(u, mb)            # m = n x u
+    ub = ub + np.cross(mb, nn)
+    nrawb = (nb - nn * np.dot(nn, nb)) / ln
+    abb = np.cross(u, nrawb)             # nraw = ab x u
+    ub = ub + np.cross(nrawb, ab)
+    bcb = (ub - u * np.dot(u, ub)) / lbc
+    return -abb, abb - bcb, bcb          # a, b, c
+
+def _cv_place_vjp(a, b, c, d, db):
+    """d = place(a,b,c; L,theta,Delta): adjoint w.r.t. (a,b,c) and the three scalars, everything read off the FINAL points"""
+    u, nn, m, _, _, _ = _cv_frame(a, b, c)
+    w = d - c; L = np.linalg.norm(w)
+    ct = -np.dot(w, u) / L; st = np.sqrt(max(0.0, 1 - ct * ct))
+    x, y = np.dot(w, m), np.dot(w, nn)
+    cd, sd = x / (L * st), y / (L * st)
+    Lb = np.dot(db, w) / L
+    tb = np.dot(db, L * (st * u + ct * (cd * m + sd * nn)))
+    Db = np.dot(db, L * st * (-sd * m + cd * nn))
+    ub = -L * ct * db; mb = L * st * cd * db; nb = L * st * sd * db
+    ab_, bb_, cb_ = _cv_frame_vjp(a, b, c, ub, nb, mb)
+    return ab_, bb_, cb_ + db, Lb, tb, Db
+
+def _cv_internal_vjp(a, b, c, d, Lb, tb, Db):
+    """adjoint of (L, theta, Delta)(a,b,c,d) with the conventions of place()"""
+    u, nn, m, _, _, _ = _cv_frame(a, b, c)
+    w = d - c; L = np.linalg.norm(w)
+    q = -np.dot(w, u) / L; st = np.sqrt(max(1e-300, 1 - q * q))
+    x, y = np.dot(w, m), np.dot(w, nn)
+    wb = Lb * w / L
+    qb = -tb / st
+    wb = wb + qb * (-u / L + np.dot(w, u) * w / L ** 3)
+    ub = qb * (-w / L)
+    r2 = x * x + y * y
+    xb, yb = -y / r2 * Db, x / r2 * Db
+    wb = wb + xb * m + yb * nn
+    mb = xb * w; nb = yb * w
+    ab_, bb_, cb_ = _cv_frame_vjp(a, b, c, ub, nb, mb)
+    return ab_, bb_, cb_ - wb, wb
+
+def _cv_one_way(start, final, g):
+    """grad w.r.t. the start chain of one one-way build (float64): start, final, g are (m,3) in chain order"""
+    m_ = start.shape[0]
+    sbar = np.zeros_like(start)
+    acc = np.zeros_like(start)           # propagated adjoints of the final points
+    for k in range(m_ - 1, 2, -1):
+        db = g[k] + acc[k]
+        ab_, bb_, cb_, Lb, tb, Db = _cv_place_vjp(final[k - 3], final[k - 2], final[k - 1], final[k], db)
+        acc[k - 3] += ab_; acc[k - 2] += bb_; acc[k - 1] += cb_
+        sa, sb, sc, sd = _cv_internal_vjp(start[k - 3], start[k - 2], start[k - 1], start[k], Lb, tb, Db)
+        sbar[k - 3] += sa; sbar[k - 2] += sb; sbar[k - 1] += sc; sbar[k] += sd
+    for k in range(3):
+        sbar[k] += g[k] + acc[k]
+    return sbar
+
+def _start_chain_vjp(start, final, g, one_way):
+    n = start.shape[0]
+    if one_way:
+        return _cv_one_way(start, final, g)
+    s = n // 2
+    out = np.zeros_like(start)
+    li = np.arange(s + 1, -1, -1)                       # left chain order
+    out[li] += _cv_one_way(start[li], final[li], g[li])
+    ri = np.arange(s - 1, n)
+    gr = g[ri].copy(); gr[:3] = 0.0                     # the right build's first three outputs are dropped
+    out[ri] += _cv_one_way(start[ri], final[ri], gr)
+    return out
+
+
+
+def test_start_chain_vjp_prototype():
+    """Twisting about bonds keeps lengths and angles and shifts dihedrals, so the build is a placement recursion on the
+    start chain's internal coordinates; its reverse mode (what the CUDA kernel runs) equals float64 autograd of the
+    restated reference for the one-way and the two-sided op."""
+    rng = np.random.default_rng(0)
+    for n, one_way in ((4, True), (6, True), (9, True), (4, False), (5, False), (12, False), (13, False), (40, False)):
+        b = 2
+        start = O.straight_tetrahedral_chain(n).astype(np.float64)[None] + rng.normal(scale=0.05, size=(b, n, 3))
+        dih = rng.uniform(-np.pi, np.pi, size=(b, n - 3))
+        w = rng.normal(size=(b, n, 3))
+        st = torch.from_numpy(start).requires_grad_(True)
+        fn = (lambda d, c: O.dihedral_to_cartesian_one_way(d, c)) if one_way else O.dihedrals_to_cartesian_tf1
+        out = fn(torch.from_numpy(dih), st)
+        (out * torch.from_numpy(w)).sum().backward()
+        got = np.stack([_start_chain_vjp(start[f], out.detach().numpy()[f], w[f], one_way) for f in range(b)])
+        np.testing.assert_allclose(got, st.grad.numpy(), rtol=1e-9, atol=1e-11)
