@@ -650,6 +650,28 @@ def test_chain_and_d2c_backward(em):
                 assert relnorm(hg2.grad.cpu().numpy(), ho2.grad.numpy()) < 2e-5
 
 
+def test_standalone_composition_matches_back_map_layer(em):
+    """chain_in_plane -> dihedrals_to_cartesian_tf composed from the standalone ops (what BackMapLayer.call does,
+    models/layers.py:970-985): values and the gradients w.r.t. angles AND dihedrals flow through the start chain."""
+    from encodermap_b200.encodermap_tf1 import chain_in_plane, dihedrals_to_cartesian_tf
+
+    rng = np.random.default_rng(21)
+    for n, b in ((30, 3), (301, 2)):
+        L = rng.uniform(0.13, 0.15, size=(1, n - 1)).astype(np.float32)
+        ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+        dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+        w = rng.normal(size=(b, n, 3))
+        ag, hg = cu(ang).requires_grad_(True), cu(dih).requires_grad_(True)
+        out = dihedrals_to_cartesian_tf(hg + pi, chain_in_plane(cu(L), ag))
+        (out * cu(w)).sum().backward()
+        ao, ho = torch.from_numpy(ang).double().requires_grad_(True), torch.from_numpy(dih).double().requires_grad_(True)
+        ref = O.dihedrals_to_cartesian_tf1(ho + pi, O.chain_in_plane(torch.from_numpy(L).double(), ao))
+        (ref * torch.from_numpy(w)).sum().backward()
+        assert np.abs(out.detach().cpu().numpy() - ref.detach().numpy()).max() < COORD_ATOL
+        assert relnorm(hg.grad.cpu().numpy(), ho.grad.numpy()) < 2e-5
+        assert relnorm(ag.grad.cpu().numpy(), ao.grad.numpy()) < 5e-5   # float32 planar chain handed from op to op
+
+
 def test_index_construction_bit_exact(em, golden):
     from encodermap_b200.misc.backmapping import split_and_reverse_cartesians, split_and_reverse_dihedrals
 
