@@ -14,7 +14,9 @@ all-reduced over NCCL -- total work is fixed, so this is STRONG scaling.
 metric  : unique unordered pairs (incl. diagonal) per second, N(N+1)/2 / step time, whole job
 value   : inputs resident in HBM, device-timed (CUDA events, max over ranks)
 e2e     : same through the public API (`sigmoid_loss(...)(y_true, y_pred)` + backward) with HOST pinned
-          buffers: H2D of both inputs and D2H of loss and gradient inside the timed region
+          buffers: H2D of both inputs and D2H of loss and gradient inside the timed region (one GPU: y_true is
+          handed over as the pinned host tensor and streamed in behind the pair tiles; N GPUs: 1/N per host
+          link + NVLink all-gather)
 roofline: the pair-tile kernel against the FP32 issue roofline of SURVEY.md section 8d
           (4 lane-instructions per (pair, dim) + 60 per pair;  peak = 148 SM x 128 lanes x sm_max clock from
           MEASURED_PEAKS.json, peak_measured = FFMA rate probed live on the device; the kernel is neither
@@ -256,8 +258,9 @@ def run_ours(args):
     from encodermap_b200 import parallel
 
     def e2e_step():
+        # N = 1: the public API takes the pinned host tensor itself and streams it in behind the pair tiles;
         # N > 1: every rank moves 1/N of the (replicated) input over its own host link, NVLink all-gathers the rest
-        xd = parallel.replicate_from_host(xh, dev)
+        xd = xh if world == 1 else parallel.replicate_from_host(xh, dev)
         zd = parallel.replicate_from_host(zh, dev).requires_grad_(True)
         l = f(xd, zd)
         l.backward()
@@ -326,7 +329,9 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "unique pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": (xh.numel() + zh.numel()) * 4 // world, "d2h_bytes_per_step": gh.numel() * 4 + 4,
-                    "note": "per rank: 1/n_gpus of the replicated input over the host link + NCCL all-gather over NVLink (parallel.replicate_from_host); every rank reads loss + gradient back"},
+                    "note": ("sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward: rows are copied in chunks on a side stream behind the pair tiles that need them; loss + gradient read back"
+                             if world == 1 else
+                             "per rank: 1/n_gpus of the replicated input over the host link + NCCL all-gather over NVLink (parallel.replicate_from_host); every rank reads loss + gradient back")},
             "gpu_launches": args.steps * world,
             "cpu_baseline": cpu_baseline,
             "extra": extra,

@@ -42,6 +42,92 @@ def sigmoid_cost_raw(high: torch.Tensor, low: torch.Tensor, periodicity: float, 
     return loss, grad
 
 
+_CHUNK_CACHE = {}
+
+
+def _row_chunk_tiles(n: int, rows_per_chunk: int):
+    """[(first_row, tile_begin)] of consecutive row chunks (multiples of the kernel's 1024-row bands): tile ids are
+    band-major, a tile of the band starting at row r touches rows and columns >= r only, so tiles from tile_begin on
+    need nothing before first_row.  Host-side bisection over emk_pair_tile_decode, cached per (n, rows_per_chunk)."""
+    key = (n, rows_per_chunk)
+    if key not in _CHUNK_CACHE:
+        total = _lib.pair_tile_count(n)
+        out = []
+        for first_row in range(0, n, rows_per_chunk):
+            block = first_row // 128        # first 128-row tile row of the chunk
+            lo, hi = 0, total               # smallest tile whose tile row is >= block (tile rows are band-monotone)
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if _lib.pair_tile_decode(n, mid)[0] >= block:
+                    hi = mid
+                else:
+                    lo = mid + 1
+            out.append((first_row, lo))
+        _CHUNK_CACHE[key] = out
+    return _CHUNK_CACHE[key]
+
+
+def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicity: float, sig: Sequence[float],
+                          need_grad: bool = True, rows_per_chunk: int = 8192):
+    """Same result as ``sigmoid_cost_raw`` with the high-d input in (pinned) HOST memory: rows are copied to the device in
+    chunks from the LAST row backwards on a side stream while the pair tiles that only need the rows already there run
+    on the current stream (tile ids are band-major, so every chunk of rows unlocks one contiguous tile range).  The copy
+    of a 65 536 x 1 024 input (268 MB, ~5 ms over PCIe) hides completely behind the first 16 ms of tiles."""
+    require_cuda(low, "y_pred")
+    if high_host.is_cuda:
+        return sigmoid_cost_raw(high_host, low, periodicity, sig, None, need_grad)
+    if high_host.dtype != torch.float32 or not high_host.is_contiguous() or high_host.dim() != 2:
+        raise EmkError(-4, "streamed sigmoid cost needs a contiguous rank-2 float32 host tensor")
+    low = f32c(low)
+    n, d = high_host.shape
+    rows_per_chunk = max(1024, (rows_per_chunk // 1024) * 1024)
+    chunks = _row_chunk_tiles(n, rows_per_chunk)
+    total = _lib.pair_tile_count(n)
+    dev = low.device
+    high = torch.empty((n, d), dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    grad = torch.empty_like(low) if need_grad else None
+    base_flags = 0 if need_grad else _lib.EMK_COST_NO_GRAD
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    first = True
+    with torch.cuda.device(dev):
+        for idx in range(len(chunks) - 1, -1, -1):
+            r0, t0 = chunks[idx]
+            r1 = min(n, r0 + rows_per_chunk)
+            t1 = chunks[idx + 1][1] if idx + 1 < len(chunks) else total
+            with torch.cuda.stream(side):
+                high[r0:r1].copy_(high_host[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            main.wait_event(ev)
+            if t1 > t0:
+                flags = base_flags | (_lib.EMK_COST_ZERO_OUTPUTS if first else 0)
+                check(_lib.lib().emk_dl_sigmoid_cost(DL(high), DL(low), float(periodicity), sig_array(sig), t0, t1,
+                                                     DL(loss), DL(grad), flags, stream_of(low)))
+                first = False
+    high.record_stream(side)   # allocated on the current stream, written on the side stream
+    return loss, grad
+
+
+class SigmoidCostStreamed(torch.autograd.Function):
+    """SigmoidCost with a pinned host tensor as the high-d input (copy overlapped with the pair tiles)."""
+
+    @staticmethod
+    def forward(ctx, high_host, low, periodicity, sig):
+        loss, grad = sigmoid_cost_streamed(high_host, low, periodicity, sig, ctx.needs_input_grad[1])
+        ctx.save_for_backward(grad)
+        ctx.low_dtype = low.dtype
+        return loss[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        g = None if grad is None else (grad * grad_output).to(ctx.low_dtype)
+        return None, g, None, None
+
+
 class SigmoidCost(torch.autograd.Function):
     """loss = mean_ij (s_h(D^h_ij) - s_l(D^l_ij))^2 ; forward and dL/d(low) come out of the same launch."""
 

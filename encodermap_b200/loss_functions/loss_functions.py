@@ -36,7 +36,8 @@ def sigmoid_loss(
     Extra keyword-only arguments (not in the reference): ``process_group`` shards the pair tiles of
     one evaluation over the ranks of a torch.distributed group (inputs replicated, one all-reduce of
     the loss and dL/d(latent)); ``check_finite`` enables the reference's finite assertion, which
-    costs a device synchronisation."""
+    costs a device synchronisation.  ``y_true`` may also be a PINNED host tensor: it is then copied to the
+    device in row chunks on a side stream while the pair tiles that need only the rows already there run."""
     p = Parameters() if parameters is None else parameters
     periodicity = periodicity_overwrite if periodicity_overwrite is not None else p.periodicity
     sig = tuple(dist_dig_parameters_overwrite) if dist_dig_parameters_overwrite is not None else tuple(p.dist_sig_parameters)
@@ -47,7 +48,12 @@ def sigmoid_loss(
             from ..parallel import tile_shard
 
             tile_range, reduce_fn = tile_shard(int(y_true.shape[0]), process_group)
-        cost = _ops.SigmoidCost.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
+        if process_group is None and not y_true.is_cuda and y_true.is_pinned():
+            # high-d input still in pinned host memory: streamed to the device behind the pair tiles (not a CPU path --
+            # unpinned CPU tensors are rejected like everywhere else)
+            cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig)
+        else:
+            cost = _ops.SigmoidCost.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
         if check_finite:
             _assert_all_finite(cost, "Sigmoid cost became infinite or NaN.")
         return cost

@@ -683,6 +683,30 @@ def test_index_construction_bit_exact(em, golden):
         assert np.array_equal(dl[0].cpu().numpy(), g[f"n{n}_split_dih_left"]) and np.array_equal(dr[0].cpu().numpy(), g[f"n{n}_split_dih_right"])
 
 
+def test_streamed_host_input_matches_device_input(em):
+    """sigmoid_loss with the high-d input in pinned host memory (row chunks copied behind the pair tiles) gives the same
+    loss and gradient as the device-resident call, for sizes with one and with several row chunks."""
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    rng = np.random.default_rng(12)
+    for n, d, chunk in ((300, 40, 8192), (2500, 64, 1024), (4097, 36, 2048)):
+        h = rng.uniform(-pi, pi, size=(n, d)).astype(np.float32)
+        z = rng.normal(size=(n, 2)).astype(np.float32)
+        zd = cu(z).requires_grad_(True)
+        ld = sigmoid_loss()(cu(h), zd)
+        ld.backward()
+        hp = torch.from_numpy(h).pin_memory()
+        from encodermap_b200 import _ops
+        ls, gs = _ops.sigmoid_cost_streamed(hp, cu(z), 2 * pi, (4.5, 12, 6, 1, 2, 6), True, chunk)
+        np.testing.assert_allclose(ls.item(), ld.item(), rtol=1e-6)
+        assert relnorm(gs.cpu().numpy(), zd.grad.cpu().numpy()) < 1e-6
+        zs = cu(z).requires_grad_(True)
+        lp = sigmoid_loss()(hp, zs)           # public API with the pinned tensor
+        lp.backward()
+        np.testing.assert_allclose(lp.item(), ld.item(), rtol=1e-6)
+        assert relnorm(zs.grad.cpu().numpy(), zd.grad.cpu().numpy()) < 1e-6
+
+
 def test_no_cpu_fallback(em):
     from encodermap_b200.loss_functions import sigmoid_loss
     from encodermap_b200.models.layers import back_map
