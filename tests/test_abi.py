@@ -161,3 +161,22 @@ def test_product_does_not_import_oracle():
         assert not pat.search(path.read_text()), f"{path} reaches into oracle/"
     for path in (ROOT / "encodermap_b200" / "csrc").glob("*"):
         assert "#include \"../../oracle" not in path.read_text() and "em_oracle" not in path.read_text()
+
+
+def test_row_chunk_tile_ranges_for_streamed_input(L):
+    """Host logic of sigmoid_cost_streamed: tile ids are band-major, so the tiles from chunk c's tile_begin on touch no row
+    (and no column) before the chunk's first row -- checked exhaustively against emk_pair_tile_decode."""
+    from encodermap_b200 import _ops
+
+    for n, rows in ((300, 1024), (2500, 1024), (4097, 2048), (9000, 3072)):
+        chunks = _ops._row_chunk_tiles(n, rows)
+        total = L.pair_tile_count(n)
+        assert chunks[0] == (0, 0)
+        for (r0, t0), nxt in zip(chunks, chunks[1:] + [(n, total)]):
+            assert t0 <= nxt[1]
+            for t in range(t0, nxt[1]):
+                i, j = L.pair_tile_decode(n, t)
+                assert i * 128 >= r0 and j * 64 >= r0
+            if t0 > 0:
+                i, _ = L.pair_tile_decode(n, t0 - 1)
+                assert i * 128 < r0
