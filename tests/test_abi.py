@@ -180,3 +180,23 @@ def test_row_chunk_tile_ranges_for_streamed_input(L):
             if t0 > 0:
                 i, _ = L.pair_tile_decode(n, t0 - 1)
                 assert i * 128 < r0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints exactly one JSON line with the keys
+    of the measurement contract; it runs here because it only times the oracle port on the host cores."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sigmoid_cost_pairs_per_s_fwd_bwd" and d["unit"] == "unique pairs/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
