@@ -43,6 +43,7 @@ def sigmoid_cost_raw(high: torch.Tensor, low: torch.Tensor, periodicity: float, 
 
 
 _CHUNK_CACHE = {}
+_SIDE_STREAMS = {}
 
 
 def _row_chunk_tiles(n: int, rows_per_chunk: int):
@@ -89,7 +90,9 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
     grad = torch.empty_like(low) if need_grad else None
     base_flags = 0 if need_grad else _lib.EMK_COST_NO_GRAD
     main = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)   # one copy stream per device, reused by every call
     side.wait_stream(main)
     first = True
     with torch.cuda.device(dev):

@@ -200,3 +200,52 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_streamed_cost_control_flow(L, monkeypatch):
+    """Host logic of sigmoid_cost_streamed with the CUDA pieces stubbed out (no GPU here): the launches walk the tile list
+    from the last row chunk to the first, the ranges chain without gaps, and only the first launch zeroes the outputs."""
+    from encodermap_b200 import _ops
+
+    calls = []
+
+    class FakeStream:
+        def wait_stream(self, s): pass
+        def wait_event(self, e): pass
+
+    class FakeEvent:
+        def record(self, s): pass
+
+    class Ctx:
+        def __init__(self, *a): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    real = L.lib()
+
+    class FakeLib:
+        def __getattr__(self, k):
+            return getattr(real, k)
+
+        def emk_dl_sigmoid_cost(self, high, low, per, sig, t0, t1, loss, grad, flags, st):
+            calls.append((t0, t1, flags))
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda d=None: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", Ctx)
+    monkeypatch.setattr(torch.cuda, "device", Ctx)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    monkeypatch.setattr(_ops, "require_cuda", lambda t, n: t)
+    monkeypatch.setattr(_ops, "stream_of", lambda t: None)
+    monkeypatch.setattr(_ops, "DL", lambda t: t)
+    monkeypatch.setattr(L, "lib", lambda: fake)
+    monkeypatch.setattr(_ops, "_SIDE_STREAMS", {})
+    n = 5000
+    _ops.sigmoid_cost_streamed(torch.zeros(n, 8), torch.zeros(n, 2), 6.28, (4.5, 12, 6, 1, 2, 6), True, 1024)
+    total = int(real.emk_pair_tile_count(n))
+    assert calls[0][1] == total and calls[-1][0] == 0 and len(calls) == 5
+    assert all(a[0] == b[1] for a, b in zip(calls, calls[1:]))
+    assert calls[0][2] & L.EMK_COST_ZERO_OUTPUTS and not any(c[2] & L.EMK_COST_ZERO_OUTPUTS for c in calls[1:])
