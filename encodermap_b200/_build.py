@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 BUILD = PKG / "_build"
 LIB = PKG / "libemk.so"
-SOURCES = ["emk_api.cu", "pair_tile.cu", "backmap.cu", "elementwise.cu"]
+SOURCES = ["emk_api.cu", "pair_tile.cu", "backmap.cu", "elementwise.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC", "-o", str(LIB), *map(str, objs)]
+            "-Xcompiler", "-fPIC", "-o", str(LIB), *map(str, objs), "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")

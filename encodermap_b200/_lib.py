@@ -94,6 +94,13 @@ SIGNATURES = {
     "emk_dl_dihedrals_to_cartesian_bwd": ([vp, vp, C.c_int, vp, vp], C.c_int),
     "emk_dihedrals_to_cartesian_chain_bwd": ([vp, i64, vp, vp, i64, i64, C.c_int, vp, vp], C.c_int),
     "emk_dl_dihedrals_to_cartesian_chain_bwd": ([vp, vp, vp, C.c_int, vp, vp], C.c_int),
+    "emk_comm_unique_id": ([vp], C.c_int),
+    "emk_comm_init": ([C.c_int, C.c_int, vp], C.c_int),
+    "emk_comm_info": ([C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    "emk_comm_allreduce": ([vp, vp, i64, vp], C.c_int),
+    "emk_comm_allgather2": ([vp, vp, i64, vp, vp, i64, vp], C.c_int),
+    "emk_comm_reduce_cost_scatter": ([vp, vp, vp, i64, vp], C.c_int),
+    "emk_comm_destroy": ([], C.c_int),
 }
 
 

@@ -6,6 +6,7 @@ the hot path is produced by a kernel in libemk.so, reached through ctypes with D
 from __future__ import annotations
 
 import math
+import threading
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -44,6 +45,16 @@ def sigmoid_cost_raw(high: torch.Tensor, low: torch.Tensor, periodicity: float, 
 
 _CHUNK_CACHE = {}
 _SIDE_STREAMS = {}
+_CACHE_LOCK = threading.Lock()   # both caches are filled lazily and may be reached from several host threads
+
+
+def _reject_high_grad(needs_grad: bool) -> None:
+    """The reference's sigmoid_loss is differentiable through pairwise_dist(_periodic)(y_true) as well; every caller
+    on the hot path feeds input DATA there and the fused kernel does not produce that gradient.
+    Dropping it silently would train a different model, so a y_true that requires grad is an error."""
+    if needs_grad:
+        raise EmkError(-7, "sigmoid cost: y_true requires grad, but the fused kernel only differentiates w.r.t. y_pred "
+                           "(detach y_true, or build the cost from pairwise_dist(_periodic) + sigmoid, which are differentiable)")
 
 
 def _row_chunk_tiles(n: int, rows_per_chunk: int):
@@ -51,7 +62,9 @@ def _row_chunk_tiles(n: int, rows_per_chunk: int):
     band-major, a tile of the band starting at row r touches rows and columns >= r only, so tiles from tile_begin on
     need nothing before first_row.  Host-side bisection over emk_pair_tile_decode, cached per (n, rows_per_chunk)."""
     key = (n, rows_per_chunk)
-    if key not in _CHUNK_CACHE:
+    with _CACHE_LOCK:
+        cached = _CHUNK_CACHE.get(key)
+    if cached is None:
         total = _lib.pair_tile_count(n)
         out = []
         for first_row in range(0, n, rows_per_chunk):
@@ -64,8 +77,9 @@ def _row_chunk_tiles(n: int, rows_per_chunk: int):
                 else:
                     lo = mid + 1
             out.append((first_row, lo))
-        _CHUNK_CACHE[key] = out
-    return _CHUNK_CACHE[key]
+        with _CACHE_LOCK:
+            cached = _CHUNK_CACHE.setdefault(key, out)
+    return cached
 
 
 def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicity: float, sig: Sequence[float],
@@ -81,6 +95,10 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
         raise EmkError(-4, "streamed sigmoid cost needs a contiguous rank-2 float32 host tensor")
     low = f32c(low)
     n, d = high_host.shape
+    if d % 4 != 0:
+        # the kernel would re-pad the whole (n, d) matrix into TMA-legal scratch on every chunk call (and read rows the
+        # side stream is still writing): one plain copy, then the ordinary path, which pads once
+        return sigmoid_cost_raw(high_host.to(low.device, non_blocking=True), low, periodicity, sig, None, need_grad)
     rows_per_chunk = max(1024, (rows_per_chunk // 1024) * 1024)
     chunks = _row_chunk_tiles(n, rows_per_chunk)
     total = _lib.pair_tile_count(n)
@@ -90,9 +108,10 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
     grad = torch.empty_like(low) if need_grad else None
     base_flags = 0 if need_grad else _lib.EMK_COST_NO_GRAD
     main = torch.cuda.current_stream(dev)
-    side = _SIDE_STREAMS.get(dev)
-    if side is None:
-        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)   # one copy stream per device, reused by every call
+    with _CACHE_LOCK:
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)   # one copy stream per device, reused by every call
     side.wait_stream(main)
     first = True
     with torch.cuda.device(dev):
@@ -119,6 +138,7 @@ class SigmoidCostStreamed(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, high_host, low, periodicity, sig):
+        _reject_high_grad(ctx.needs_input_grad[0])
         loss, grad = sigmoid_cost_streamed(high_host, low, periodicity, sig, ctx.needs_input_grad[1])
         ctx.save_for_backward(grad)
         ctx.low_dtype = low.dtype
@@ -136,6 +156,7 @@ class SigmoidCost(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, high, low, periodicity, sig, tile_range, reduce_fn):
+        _reject_high_grad(ctx.needs_input_grad[0])
         need_grad = ctx.needs_input_grad[1]
         loss, grad = sigmoid_cost_raw(high, low, periodicity, sig, tile_range, need_grad)
         if reduce_fn is not None:  # multi-GPU: sum the partial results of all ranks

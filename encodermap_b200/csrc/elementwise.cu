@@ -753,7 +753,9 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
       pairwise_flat3_tab_kernel<<<grid, PWF_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, G, out);
       return launch_status("pairwise_flat3_tab_kernel");
     }
-    const size_t smem = 3 * (size_t)n * sizeof(float);
+    const size_t smem = 3 * (size_t)n * sizeof(float);   // up to 96 KB at n = 8192: above the 48 KB default limit
+    static bool cfg_rows[kMaxDevices] = {false};
+    if (first_use_on_device(cfg_rows)) EMK_CUDA(cudaFuncSetAttribute(pairwise_rows3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);
     pairwise_rows3_kernel<<<grid, PW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, squared, out);
     return launch_status("pairwise_rows3_kernel");

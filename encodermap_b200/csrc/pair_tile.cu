@@ -137,45 +137,72 @@ __host__ __device__ inline void tile_decode(int64_t t, int64_t tc, int64_t tr, i
 
 // ---- cost epilogue of NI row groups (rows ty + 16 (i0 + i)) x 4 column groups of this thread ------------------
 // NI = 8: the whole micro-tile (no cluster); NI = 8 / S: this CTA's share after the reduce-scatter over a cluster.
+// stage latent components [c0, c0 + lc) of the tile's rows / columns (component-major, zero for out-of-range rows)
+__device__ __forceinline__ void stage_latent(const PairParams& p, float* zA, float* zB, float* colsum, const int64_t row0,
+                                             const int64_t col0, const int c0, const int lc, const int tid) {
+  for (int idx = tid; idx < lc * TM; idx += NTHREADS) {
+    const int c = idx / TM, r = idx - c * TM;
+    zA[c * TM + r] = (row0 + r < p.n) ? p.low[(row0 + r) * p.l + c0 + c] : 0.f;
+  }
+  for (int idx = tid; idx < lc * TN; idx += NTHREADS) {
+    const int c = idx / TN, r = idx - c * TN;
+    zB[c * TN + r] = (col0 + r < p.n) ? p.low[(col0 + r) * p.l + c0 + c] : 0.f;
+    colsum[c * TN + r] = 0.f;
+  }
+}
+
 template <int NI>
-__device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const int i0, const PairParams& p, const float* zA,
-                                              const float* zB, float* colsum, double* red_d, const int64_t row0,
+__device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const int i0, const PairParams& p, float* zA,
+                                              float* zB, float* colsum, double* red_d, const int64_t row0,
                                               const int64_t col0, const bool diag, const int ty, const int tx, const int tid,
                                               const int lane, const int warp) {
   // low-d squared distances, summed in the SAME order as the main loop sums the high-d ones (even
   // components in one fused chain, odd components in the other, then one add): identical inputs and
-  // sigmoids on both sides then cancel exactly, as they do in the reference (tests/test_losses.py:897-904)
+  // sigmoids on both sides then cancel exactly, as they do in the reference (tests/test_losses.py:897-904).
+  // Latent widths above MAX_LATENT (the reference accepts any n_neurons[-1], parameters.py:612) are walked in chunks of
+  // MAX_LATENT components that are re-staged into the same shared-memory rows; the usual 2..8-wide latent never loops.
   float dl2[NI][4];
 #pragma unroll
   for (int i = 0; i < NI; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) dl2[i][j] = 0.f;
+  int staged = 0;   // first component of the chunk that sits in zA / zB
 #pragma unroll 1
-  for (int par = 0; par < 2; par++) {
-    float part[NI][4];
-#pragma unroll
-    for (int i = 0; i < NI; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) part[i][j] = 0.f;
+  for (int c0 = 0; c0 < p.l; c0 += MAX_LATENT) {
+    const int lc = min(MAX_LATENT, p.l - c0);
+    if (c0 != staged) {
+      __syncthreads();
+      stage_latent(p, zA, zB, colsum, row0, col0, c0, lc, tid);
+      staged = c0;
+      __syncthreads();
+    }
 #pragma unroll 1
-    for (int c = par; c < p.l; c += 2) {
-      float za[NI], zb[4];
-#pragma unroll
-      for (int i = 0; i < NI; i++) za[i] = zA[c * TM + ty + 16 * (i0 + i)];
-#pragma unroll
-      for (int j = 0; j < 4; j++) zb[j] = zB[c * TN + tx + 16 * j];
+    for (int par = 0; par < 2; par++) {
+      float part[NI][4];
 #pragma unroll
       for (int i = 0; i < NI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float t = za[i] - zb[j];
-          part[i][j] = fmaf(t, t, part[i][j]);
-        }
+        for (int j = 0; j < 4; j++) part[i][j] = 0.f;
+#pragma unroll 1
+      for (int c = par; c < lc; c += 2) {
+        float za[NI], zb[4];
+#pragma unroll
+        for (int i = 0; i < NI; i++) za[i] = zA[c * TM + ty + 16 * (i0 + i)];
+#pragma unroll
+        for (int j = 0; j < 4; j++) zb[j] = zB[c * TN + tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float t = za[i] - zb[j];
+            part[i][j] = fmaf(t, t, part[i][j]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < NI; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dl2[i][j] += part[i][j];
     }
-#pragma unroll
-    for (int i = 0; i < NI; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) dl2[i][j] += part[i][j];
   }
 
   float lsum = 0.f;
@@ -212,49 +239,60 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const i
 
   if (p.grad == nullptr) return;
   const float gs = p.grad_scale;
+  // gradient: chunks in descending order, so that the chunk staged last by the distance loop is used first
 #pragma unroll 1
-  for (int c = 0; c < p.l; c++) {
-    float za[NI], zb[4], rs[NI], cs[4];
-#pragma unroll
-    for (int i = 0; i < NI; i++) {
-      za[i] = zA[c * TM + ty + 16 * (i0 + i)];
-      rs[i] = 0.f;
+  for (int c0 = ((p.l - 1) / MAX_LATENT) * MAX_LATENT; c0 >= 0; c0 -= MAX_LATENT) {
+    const int lc = min(MAX_LATENT, p.l - c0);
+    if (c0 != staged) {
+      __syncthreads();   // the previous chunk's column sums have been flushed
+      stage_latent(p, zA, zB, colsum, row0, col0, c0, lc, tid);
+      staged = c0;
+      __syncthreads();
     }
+#pragma unroll 1
+    for (int c = 0; c < lc; c++) {
+      float za[NI], zb[4], rs[NI], cs[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      zb[j] = zB[c * TN + tx + 16 * j];
-      cs[j] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < NI; i++)
+      for (int i = 0; i < NI; i++) {
+        za[i] = zA[c * TM + ty + 16 * (i0 + i)];
+        rs[i] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const float t = dl2[i][j] * (za[i] - zb[j]);
-        rs[i] += t;
-        cs[j] -= t;
+        zb[j] = zB[c * TN + tx + 16 * j];
+        cs[j] = 0.f;
       }
-    // row side: the 16 lanes of a half-warp share ty
 #pragma unroll
-    for (int i = 0; i < NI; i++) {
+      for (int i = 0; i < NI; i++)
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
-      const int64_t r = row0 + ty + 16 * (i0 + i);
-      if (tx == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c], rs[i] * gs);
+        for (int j = 0; j < 4; j++) {
+          const float t = dl2[i][j] * (za[i] - zb[j]);
+          rs[i] += t;
+          cs[j] -= t;
+        }
+      // row side: the 16 lanes of a half-warp share ty
+#pragma unroll
+      for (int i = 0; i < NI; i++) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+        const int64_t r = row0 + ty + 16 * (i0 + i);
+        if (tx == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c0 + c], rs[i] * gs);
+      }
+      // column side (mirror image of the tile); diagonal tiles already visit both orders
+      if (!diag) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+          if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
+        }
+      }
     }
-    // column side (mirror image of the tile); diagonal tiles already visit both orders
     if (!diag) {
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
-        if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
+      __syncthreads();
+      for (int idx = tid; idx < lc * TN; idx += NTHREADS) {
+        const int c = idx / TN, r = idx - c * TN;
+        if (col0 + r < p.n) atomicAdd(&p.grad[(col0 + r) * p.l + c0 + c], colsum[idx] * gs);
       }
-    }
-  }
-  if (!diag) {
-    __syncthreads();
-    for (int idx = tid; idx < p.l * TN; idx += NTHREADS) {
-      const int c = idx / TN, r = idx - c * TN;
-      if (col0 + r < p.n) atomicAdd(&p.grad[(col0 + r) * p.l + c], colsum[idx] * gs);
     }
   }
 }
@@ -330,18 +368,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
     for (int kc = 0; kc < STAGES - 1 && kc < nk; kc++) issue(kc);
   }
 
-  if (EPI == Epi::kCost) {
-    // latent rows of this tile, component-major, zero for out-of-range rows
-    for (int idx = tid; idx < p.l * TM; idx += NTHREADS) {
-      const int c = idx / TM, r = idx - c * TM;
-      zA[c * TM + r] = (row0 + r < p.n) ? p.low[(row0 + r) * p.l + c] : 0.f;
-    }
-    for (int idx = tid; idx < p.l * TN; idx += NTHREADS) {
-      const int c = idx / TN, r = idx - c * TN;
-      zB[c * TN + r] = (col0 + r < p.n) ? p.low[(col0 + r) * p.l + c] : 0.f;
-      colsum[c * TN + r] = 0.f;
-    }
-  }
+  if (EPI == Epi::kCost) stage_latent(p, zA, zB, colsum, row0, col0, 0, min(MAX_LATENT, p.l), tid);   // first chunk of the latent
 
   float2 acc[8][4];
 #pragma unroll
@@ -552,9 +579,13 @@ static int prepare_high(const float* high, int64_t n, int64_t d, cudaStream_t st
 //   * otherwise one CTA per tile                                                  8192 x 1024: 4265 us (S = 2: 4358)
 static int pick_cluster(int64_t n_tiles, int n_chunks) {
   int s = 1;
-  if (const char* e = getenv("EMK_CLUSTER")) {   // experiments only: force a cluster size (1, 2, 4, 8)
-    const int v = atoi(e);
-    if (v >= 1 && v <= 8 && (v & (v - 1)) == 0) s = v;
+  static const int forced = [] {   // experiments only: EMK_CLUSTER forces a cluster size (1, 2, 4, 8); read once per process
+    const char* e = getenv("EMK_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 8 && (v & (v - 1)) == 0) ? v : 0;
+  }();
+  if (forced) {
+    s = forced;
   } else if (n_tiles * 8 <= 2 * (int64_t)sm_count()) {
     s = 8;
   } else if (n_tiles < 128) {
@@ -612,7 +643,7 @@ int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* lo
   EMK_REQUIRE(high && low && sig && loss, EMK_E_NULL, "emk_sigmoid_cost: NULL pointer argument");
   EMK_REQUIRE((flags & EMK_COST_NO_GRAD) || grad_low, EMK_E_NULL, "emk_sigmoid_cost: grad_low is NULL without EMK_COST_NO_GRAD");
   EMK_REQUIRE(n >= 0 && d >= 1, EMK_E_SHAPE, "emk_sigmoid_cost: bad shape n=%lld d=%lld", (long long)n, (long long)d);
-  EMK_REQUIRE(l >= 1 && l <= MAX_LATENT, EMK_E_UNSUPPORTED, "emk_sigmoid_cost: latent width %lld outside [1,%d]", (long long)l, MAX_LATENT);
+  EMK_REQUIRE(l >= 1 && l < (1 << 20), EMK_E_SHAPE, "emk_sigmoid_cost: latent width %lld outside [1,2^20)", (long long)l);
   EMK_REQUIRE(n < (int64_t)1 << 30, EMK_E_UNSUPPORTED, "emk_sigmoid_cost: n=%lld too large", (long long)n);
   EMK_REQUIRE(periodicity > 0 || std::isinf(periodicity), EMK_E_ARG, "emk_sigmoid_cost: periodicity must be > 0");
   for (int k = 0; k < 6; k++) EMK_REQUIRE(sig[k] > 0.f && std::isfinite(sig[k]), EMK_E_ARG, "emk_sigmoid_cost: sig[%d]=%g must be finite and > 0", k, sig[k]);

@@ -16,11 +16,45 @@ from .. import _ops
 from ..parameters import ADCParameters, Parameters
 
 
-def _assert_all_finite(x: torch.Tensor, message: str) -> None:
-    # tf.debugging.assert_all_finite of the reference (loss_functions.py:293-295, 364-366, 939-941);
-    # one scalar read-back per call, only when requested
-    if not torch.isfinite(x).all():
-        raise FloatingPointError(message)
+class _FiniteCheck:
+    """``tf.debugging.assert_all_finite`` of the reference (loss_functions.py:293-295, 364-366, 939-941) without a
+    device synchronisation per step.
+
+    ``mode`` True: read the scalar back now (one synchronisation per call, the reference's behaviour to the step);
+    ``"deferred"`` (default): the finite flag of this call is copied to pinned host memory behind the kernels and
+    examined when the NEXT call comes in (or by ``flush()``), so a NaN cost still stops training with the reference's
+    message, one step late and at no cost to the launch pipeline; False: never.  While a CUDA graph is being captured
+    nothing can be read back, so the check is skipped (the scalar still carries the NaN to whoever consumes it)."""
+
+    def __init__(self, mode, message: str) -> None:
+        if mode not in (True, False, "deferred"):
+            raise ValueError("check_finite must be True, False or 'deferred'")
+        self.mode, self.message = mode, message
+        self._pending = None   # (pinned flag tensor, event)
+
+    def flush(self) -> None:
+        if self._pending is not None:
+            flag, event = self._pending
+            self._pending = None
+            event.synchronize()
+            if not bool(flag.item()):
+                raise FloatingPointError(self.message)
+
+    def __call__(self, x: torch.Tensor) -> None:
+        if self.mode is False:
+            return
+        if x.is_cuda and torch.cuda.is_current_stream_capturing():
+            return
+        if self.mode is True or not x.is_cuda:
+            if not torch.isfinite(x).all():
+                raise FloatingPointError(self.message)
+            return
+        self.flush()
+        flag = torch.empty((), dtype=torch.bool, pin_memory=True)
+        flag.copy_(torch.isfinite(x.detach()).all(), non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(x.device))
+        self._pending = (flag, event)
 
 
 def sigmoid_loss(
@@ -29,18 +63,26 @@ def sigmoid_loss(
     dist_dig_parameters_overwrite: Optional[Sequence[float]] = None,
     *,
     process_group=None,
-    check_finite: bool = False,
+    check_finite="deferred",
 ) -> Callable:
     """Sigmoid loss closure.  Reference: encodermap/loss_functions/loss_functions.py:301-369.
 
     Extra keyword-only arguments (not in the reference): ``process_group`` shards the pair tiles of
     one evaluation over the ranks of a torch.distributed group (inputs replicated, one all-reduce of
-    the loss and dL/d(latent)); ``check_finite`` enables the reference's finite assertion, which
-    costs a device synchronisation.  ``y_true`` may also be a PINNED host tensor: it is then copied to the
-    device in row chunks on a side stream while the pair tiles that need only the rows already there run."""
+    the loss and dL/d(latent)); ``check_finite`` selects how the reference's finite assertion runs: ``"deferred"``
+    (default -- checked one call late, no synchronisation), ``True`` (checked now, one synchronisation per call) or
+    ``False``; the closure's ``flush_finite_check()`` examines the last pending flag.  ``y_true`` may also be a PINNED
+    host tensor: it is then copied to the device in row chunks on a side stream while the pair tiles that need only the
+    rows already there run.
+
+    Narrower than the reference in one respect: the cost is differentiable w.r.t. ``y_pred`` only.  ``y_true`` is input
+    data in every caller on the hot path (models/models.py:2419-2422, loss_functions.py:277-287); a ``y_true`` that
+    requires grad raises instead of silently dropping that gradient.  Any latent width works (``n_neurons[-1]``,
+    parameters/parameters.py:612)."""
     p = Parameters() if parameters is None else parameters
     periodicity = periodicity_overwrite if periodicity_overwrite is not None else p.periodicity
     sig = tuple(dist_dig_parameters_overwrite) if dist_dig_parameters_overwrite is not None else tuple(p.dist_sig_parameters)
+    finite = _FiniteCheck(check_finite, "Sigmoid cost became infinite or NaN.")
 
     def sigmoid_loss_func(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
         tile_range, reduce_fn = None, None
@@ -54,10 +96,10 @@ def sigmoid_loss(
             cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig)
         else:
             cost = _ops.SigmoidCost.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
-        if check_finite:
-            _assert_all_finite(cost, "Sigmoid cost became infinite or NaN.")
+        finite(cost)
         return cost
 
+    sigmoid_loss_func.flush_finite_check = finite.flush
     return sigmoid_loss_func
 
 
@@ -68,13 +110,14 @@ def _latent_of(model) -> Callable:
     return enc
 
 
-def distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite: bool = False) -> Callable:
+def distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite="deferred") -> Callable:
     """Encodermap distance_loss.  Reference: encodermap/loss_functions/loss_functions.py:200-298.
     ``model.encoder`` maps the (tuple of) inputs to the latent; ``callback`` is accepted for signature
     compatibility (summary writing stays in the host framework)."""
     p = Parameters() if parameters is None else parameters
     latent = _latent_of(model)
-    dist_loss = sigmoid_loss(p, process_group=process_group)
+    dist_loss = sigmoid_loss(p, process_group=process_group, check_finite=False)   # one check, on the scaled cost below
+    finite = _FiniteCheck(check_finite, "Dist cost became infinite or NaN.")
 
     def distance_loss_func(y_true, y_pred=None) -> torch.Tensor:
         distance_loss_func.name = "distance_loss"
@@ -88,20 +131,22 @@ def distance_loss(model, parameters=None, callback=None, *, process_group=None, 
             dist_cost = dist_loss(y_true, y_pred) * p.distance_cost_scale
         else:
             dist_cost = torch.zeros((), dtype=torch.float32, device=y_pred.device)
-        if check_finite:
-            _assert_all_finite(dist_cost, "Dist cost became infinite or NaN.")
+        finite(dist_cost)
         return dist_cost
 
+    distance_loss_func.flush_finite_check = finite.flush
     return distance_loss_func
 
 
-def cartesian_distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite: bool = False) -> Callable:
+def cartesian_distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite="deferred") -> Callable:
     """Encodermap cartesian distance loss.  Reference: encodermap/loss_functions/loss_functions.py:873-944
     (non-periodic, ``cartesian_dist_sig_parameters``; called as ``(input pairwise distances, latent)``,
     models/models.py:2419-2422)."""
     p = ADCParameters() if parameters is None else parameters
     dist_loss = sigmoid_loss(p, periodicity_overwrite=float("inf"),
-                             dist_dig_parameters_overwrite=p.cartesian_dist_sig_parameters, process_group=process_group)
+                             dist_dig_parameters_overwrite=p.cartesian_dist_sig_parameters, process_group=process_group,
+                             check_finite=False)
+    finite = _FiniteCheck(check_finite, "Cartesian distance cost became infinite or NaN.")
 
     def cartesian_distance_loss_func(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
         cartesian_distance_loss_func.name = "cartesian_distance_loss"
@@ -109,8 +154,8 @@ def cartesian_distance_loss(model, parameters=None, callback=None, *, process_gr
             dist_cost = dist_loss(y_true, y_pred) * p.cartesian_distance_cost_scale
         else:
             dist_cost = torch.zeros((), dtype=torch.float32, device=y_pred.device)
-        if check_finite:
-            _assert_all_finite(dist_cost, "Cartesian distance cost became infinite or NaN.")
+        finite(dist_cost)
         return dist_cost
 
+    cartesian_distance_loss_func.flush_finite_check = finite.flush
     return cartesian_distance_loss_func

@@ -94,7 +94,7 @@ EMK_API int emk_pair_tile_range(int64_t n_rows, int rank, int world, int64_t* be
  *   pairwise_dist_periodic / pairwise_dist (encodermap/misc/distances.py:144-255) and
  *   sigmoid (:66-88).  No N x N matrix is written.
  *
- *   high (n,d)   high-dimensional rows;   low (n,l) latent rows, 1 <= l <= 8
+ *   high (n,d)   high-dimensional rows;   low (n,l) latent rows, any l >= 1 (walked in chunks of 8 components)
  *   periodicity  +inf => Euclidean high-d distances
  *   sig[6]       sig_h, a_h, b_h, sig_l, a_l, b_l
  *   tile_begin/tile_end   slice of the tile list to evaluate (0, emk_pair_tile_count(n) for all)
@@ -227,6 +227,28 @@ EMK_API int emk_dihedrals_to_cartesian_chain_bwd(const float* chain, int64_t cha
                                                  int64_t b, int64_t n_atoms, int one_way, float* grad_chain, void* stream);
 EMK_API int emk_dl_dihedrals_to_cartesian_chain_bwd(const DLManagedTensor* chain, const DLManagedTensor* xyz,
                                                     const DLManagedTensor* grad_xyz, int one_way, DLManagedTensor* grad_chain, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU exchange (one process per GPU).  libemk keeps its own NCCL communicator, bound at run time
+ * with dlopen("libnccl.so.2") -- the reference has no counterpart: its multi-device story is tf.distribute inside Keras
+ * (encodermap/models/models.py:3367-3401 runs under whatever strategy the caller set up).
+ *   emk_comm_unique_id : rank 0 fills 128 bytes (ncclUniqueId) and ships them to the other ranks by any means
+ *   emk_comm_init      : every rank, with its CUDA device current; collective
+ *   emk_comm_allreduce : full-set cost: sum of the float64 loss scalar and of grad_count float32 gradient values over all
+ *                        ranks, in place, as ONE fused NCCL launch on `stream` (either pointer may be NULL)
+ *   emk_comm_allgather2: data-parallel batch cost, exchange in: recv = concatenation over ranks of send, for two tensors
+ *                        (high-d rows and latent rows) in one fused launch; counts are float32 elements per rank
+ *   emk_comm_reduce_cost_scatter : exchange out: all-reduce of the loss + reduce-scatter of the (n,l) gradient (this rank keeps
+ *                        count_per_rank values starting at rank * count_per_rank) in one fused launch
+ * ---------------------------------------------------------------------------------------- */
+EMK_API int emk_comm_unique_id(void* id_out_128_bytes);
+EMK_API int emk_comm_init(int rank, int world, const void* nccl_unique_id);
+EMK_API int emk_comm_info(int* rank, int* world);
+EMK_API int emk_comm_allreduce(double* loss, float* grad, int64_t grad_count, void* stream);
+EMK_API int emk_comm_allgather2(const float* a_send, float* a_recv, int64_t a_count, const float* b_send, float* b_recv,
+                                int64_t b_count, void* stream);
+EMK_API int emk_comm_reduce_cost_scatter(double* loss, const float* grad_full, float* grad_mine, int64_t count_per_rank, void* stream);
+EMK_API int emk_comm_destroy(void);
 
 #ifdef __cplusplus
 }

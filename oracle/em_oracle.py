@@ -107,6 +107,36 @@ def pairwise_dist(positions, squared: bool = False, flat: bool = False):
     return dist
 
 
+def periodic_distance_vjp_tf(a, b, periodicity, grad_out):
+    """VJP of ``periodic_distance`` under TENSORFLOW's autodiff tie rules, stated explicitly (torch's own autograd
+    splits the gradient of ``minimum`` evenly on ties, TensorFlow does not): ``abs' = sign`` (0 at 0) and
+    ``minimum(x, y)`` routes the whole gradient to ``x`` where ``x <= y`` (tensorflow/python/ops/math_grad.py,
+    ``_MinimumGrad`` -> ``_MaximumMinimumGrad(op, grad, math_ops.less_equal)``).
+    For d = |b - a|, out = minimum(d, P - d):  d(out)/dd = +1 where d <= P - d, else -1.  Returns (grad_a, grad_b)."""
+    a, b, g = np.asarray(a, np.float64), np.asarray(b, np.float64), np.asarray(grad_out, np.float64)
+    diff = b - a
+    d = np.abs(diff)
+    branch = np.where(d <= periodicity - d, 1.0, -1.0)
+    gb = g * branch * np.sign(diff)
+    return -gb, gb
+
+
+def pairwise_dist_periodic_vjp_tf(positions, periodicity, grad_out):
+    """VJP of ``pairwise_dist_periodic`` (encodermap/misc/distances.py:164-175) w.r.t. ``positions`` under TensorFlow's
+    tie rules (see ``periodic_distance_vjp_tf``): a = x_i (axis 1 expanded), b = x_j (axis 0 expanded),
+    V = min(d, P - d) + 1e-12 [V == 0], Dist = sqrt(sum_k V^2) + 1e-12, so d(Dist_ij)/d(V_ijk) = V_ijk / sqrt(sum V^2)."""
+    x, g = np.asarray(positions, np.float64), np.asarray(grad_out, np.float64)
+    a, b = x[:, None, :], x[None, :, :]
+    diff = b - a
+    d = np.abs(diff)
+    v = np.minimum(d, periodicity - d)
+    v = v + (v == 0.0) * 1e-12
+    s = np.sqrt(np.sum(v * v, axis=2))
+    gv = g[:, :, None] * v / s[:, :, None]
+    gdiff = gv * np.where(d <= periodicity - d, 1.0, -1.0) * np.sign(diff)
+    return gdiff.sum(axis=0) - gdiff.sum(axis=1)   # b = x_j collects +, a = x_i collects -
+
+
 # ----------------------------------------------------------------------------------------
 # encodermap/loss_functions/loss_functions.py
 # ----------------------------------------------------------------------------------------

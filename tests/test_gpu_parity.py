@@ -782,3 +782,201 @@ def test_config4_full_size_invariants(em):
                                            O.chain_in_plane(dist.cpu().double().mean(0)[None], ang[pick].cpu().double()),
                                            *O.split_counts(n))
     assert (xyz[pick].cpu().double() - want).abs().max().item() < COORD_ATOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: parity holes named by the round-1 review
+# ---------------------------------------------------------------------------------------------------
+def _clustered(rng, n, d, spread, lo=0.4, hi=8.0, k=8):
+    """rows around k centres with inter-row distances ~ sqrt(2 d) * spread (keeps the high-d sigmoid off its plateau)"""
+    centres = rng.uniform(lo, hi, size=(k, d))
+    return (centres[rng.integers(0, k, n)] + rng.normal(scale=spread, size=(n, d))).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,d", [(1024, 4950), (700, 4951), (256, 44850)])
+def test_cartesian_distance_loss_adc_shape(em, n, d):
+    """configs[2]: cartesian_distance_loss on (1024, 4950) input pair distances (100 C-alpha atoms), value AND dL/dz through
+    the closure (reference loss_functions.py:873-944 called as models.py:2419-2422).  4950 % 4 == 2 goes through the padded
+    TMA copy and the cluster split; 4951 is the odd case; 44 850 = all 300 backbone atoms (cartesian_pwd_* = None)."""
+    from encodermap_b200 import ADCParameters
+    from encodermap_b200.loss_functions import cartesian_distance_loss
+
+    rng = np.random.default_rng(n + d)
+    sig = DEFAULT_SIG   # ADCParameters default: cartesian_dist_sig_parameters = dist_sig_parameters (parameters.py:822)
+    pair = _clustered(rng, n, d, 4.5 / math.sqrt(2 * d))
+    lat = (rng.normal(size=(n, 2)) * 1.5).astype(np.float32)
+    p = ADCParameters(cartesian_distance_cost_scale=3.0)
+    f = cartesian_distance_loss(object(), p)
+    z = cu(lat).requires_grad_(True)
+    loss = f(cu(pair), z)
+    loss.backward()
+    lref, gref = O.sigmoid_loss_and_grad(pair, lat, float("inf"), sig)
+    want = O.cartesian_distance_loss_value(pair.astype(np.float64), lat.astype(np.float64), sig, 3.0).item()
+    np.testing.assert_allclose(want, 3.0 * lref.item(), rtol=1e-12)
+    assert 1e-3 < lref.item() < 1.0          # the sigmoids are not saturated: the test can see the high-d side
+    np.testing.assert_allclose(loss.item(), want, rtol=LOSS_RTOL)
+    assert relnorm(z.grad.cpu().numpy(), 3.0 * gref.numpy()) < GRAD_RTOL
+
+
+def test_periodic_vjp_tie_points(em):
+    """The VJP conventions include/emk.h states for pairwise_dist_periodic / periodic_distance, AT the kinks: rows exactly
+    P/2 apart (minimum's tie goes to its first operand), identical rows and zero components (abs'(0) = 0, zero distance
+    keeps the 1e-12 epsilons and gets no gradient).  Expected values: TensorFlow's rules stated explicitly in the oracle."""
+    from encodermap_b200.misc import distances as D
+
+    P = 1.0   # 0.25 / 0.75 / 0.5 are exact in float32, so the ties are exact
+    x = np.array([[0.25, 0.125, 0.5, 0.0],
+                  [0.75, 0.125, 0.0, 0.5],     # every moving component exactly P/2 from row 0
+                  [0.25, 0.125, 0.5, 0.0],     # identical to row 0
+                  [0.75, 0.625, 0.0, 0.5],     # P/2 from row 0 in all four components
+                  [0.3125, 0.0625, 0.9375, 0.4375]], dtype=np.float32)
+    rng = np.random.default_rng(12)
+    G = rng.normal(size=(5, 5))
+    xg = cu(x).requires_grad_(True)
+    out = D.pairwise_dist_periodic(xg, P)
+    (out * cu(G)).sum().backward()
+    want = O.pairwise_dist_periodic_vjp_tf(x, P, G)
+    ref = O.pairwise_dist_periodic(torch.from_numpy(x).double(), P).numpy()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=1e-6, atol=1e-12)
+    assert out[0, 2].item() == pytest.approx(2e-12 + 1e-12, rel=1e-3)     # sqrt(4) * 1e-12 + 1e-12
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), want, rtol=2e-6, atol=1e-7)
+    # the tie really is decisive here: routing it to the second operand flips the sign of these terms
+    flipped = O.pairwise_dist_periodic_vjp_tf(x, np.nextafter(P, 0), G)
+    assert np.abs(flipped - want).max() > 0.1
+    # elementwise op at the same points
+    a = np.array([0.25, 0.25, 0.75, 0.125, 0.5], dtype=np.float32)
+    b = np.array([0.75, 0.25, 0.25, 0.625, 0.5], dtype=np.float32)
+    g = rng.normal(size=5)
+    ag, bg = cu(a).requires_grad_(True), cu(b).requires_grad_(True)
+    (D.periodic_distance(ag, bg, P) * cu(g)).sum().backward()
+    ga, gb = O.periodic_distance_vjp_tf(a, b, P, g)
+    np.testing.assert_allclose(ag.grad.cpu().numpy(), ga, rtol=1e-6, atol=0)
+    np.testing.assert_allclose(bg.grad.cpu().numpy(), gb, rtol=1e-6, atol=0)
+    assert ga[1] == 0 and ga[4] == 0 and gb[0] == g[0] and gb[2] == -g[2]
+
+
+@pytest.mark.parametrize("l", [9, 16, 19])
+def test_latent_wider_than_eight(em, l):
+    """n_neurons[-1] is unrestricted in the reference (parameters/parameters.py:612): the epilogue walks the latent in
+    chunks of 8 components.  513 rows: diagonal + off-diagonal tiles and a ragged edge; 96 rows: the cluster split."""
+    rng = np.random.default_rng(l)
+    for n, d in ((513, 40), (96, 130)):
+        h = _clustered(rng, n, d, 4.5 / math.sqrt(2 * d), lo=-3, hi=3, k=5)
+        low = (rng.normal(size=(n, l)) * 0.6).astype(np.float32)
+        loss, grad = cost_and_grad(em, h, low, 2 * pi, DEFAULT_SIG)
+        lref, gref = O.sigmoid_loss_and_grad(h, low, 2 * pi, DEFAULT_SIG)
+        np.testing.assert_allclose(loss, lref.item(), rtol=LOSS_RTOL)
+        assert relnorm(grad, gref.numpy()) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("n", [4097, 5000, 8192])
+def test_pairwise_flat_long_chains(em, n):
+    """pairwise_rows3_kernel needs up to 96 KB of dynamic shared memory for 4097..8192 selected atoms."""
+    from encodermap_b200.misc import distances as D
+
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(1, n, 3)).astype(np.float32) * 3
+    got = D.pairwise_dist(cu(x), flat=True).cpu().numpy()
+    i, j = np.triu_indices(n, k=1)
+    want = np.sqrt(((x[0, i].astype(np.float64) - x[0, j]) ** 2).sum(-1))
+    np.testing.assert_allclose(got[0], want, rtol=2e-6, atol=1e-6)
+
+
+def test_high_side_gradient_is_refused(em):
+    """sigmoid_loss differentiates w.r.t. y_pred only; a y_true that requires grad must not be dropped silently."""
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    rng = np.random.default_rng(1)
+    h = cu(rng.normal(size=(40, 6))).requires_grad_(True)
+    z = cu(rng.normal(size=(40, 2))).requires_grad_(True)
+    with pytest.raises(em.EmkError):
+        sigmoid_loss()(h, z)
+    sigmoid_loss()(h.detach(), z).backward()
+    assert z.grad is not None
+
+
+def test_deferred_finite_check(em):
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    rng = np.random.default_rng(2)
+    h, low = rng.normal(size=(64, 6)).astype(np.float32), rng.normal(size=(64, 2)).astype(np.float32)
+    f = sigmoid_loss()                       # default: deferred
+    assert math.isfinite(f(cu(h), cu(low)).item())
+    low[3, 1] = np.nan
+    bad = f(cu(h), cu(low))                  # enqueues the flag, raises nothing yet
+    assert math.isnan(bad.item())
+    with pytest.raises(FloatingPointError, match="Sigmoid cost became infinite or NaN"):
+        f(cu(h), cu(np.nan_to_num(low)))     # the next call examines the pending flag
+    f2 = sigmoid_loss()
+    f2(cu(h), cu(low))
+    with pytest.raises(FloatingPointError):
+        f2.flush_finite_check()
+
+
+def test_streamed_input_with_unaligned_width(em):
+    """pinned host y_true whose width is not a multiple of 4: one plain copy + the padded path (no per-chunk re-padding)."""
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    rng = np.random.default_rng(5)
+    h = rng.uniform(-pi, pi, size=(2100, 30)).astype(np.float32)
+    low = rng.normal(size=(2100, 2)).astype(np.float32)
+    z = cu(low).requires_grad_(True)
+    loss = sigmoid_loss()(torch.from_numpy(h).pin_memory(), z)
+    loss.backward()
+    l2, g2 = cost_and_grad(em, h, low, 2 * pi, DEFAULT_SIG)
+    assert loss.item() == pytest.approx(l2, rel=1e-6)
+    assert relnorm(z.grad.cpu().numpy(), g2) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# the sharded / data-parallel cost on CUDA with the real kernel, through NCCL (a one-rank group: what the 1-GPU test box has;
+# bench.py --gpus N drives the same functions at 2/4/8 ranks and checks the value against the one-GPU result)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def nccl_world1(cuda_device):
+    import socket
+
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        yield dist.group.WORLD
+        return
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=torch.device("cuda:0"))
+    yield dist.group.WORLD
+    from encodermap_b200 import parallel
+
+    parallel.destroy_comm()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("own_comm", [False, True])
+def test_parallel_cost_on_nccl(em, nccl_world1, own_comm):
+    from encodermap_b200 import parallel
+    from encodermap_b200.loss_functions import sigmoid_loss
+
+    if own_comm:
+        assert parallel.init_comm(force_single=True)     # libemk's communicator: fused {loss, gradient} launch
+    rng = np.random.default_rng(17)
+    n, d = 700, 52
+    h = _clustered(rng, n, d, 4.5 / math.sqrt(2 * d), lo=-3, hi=3)
+    low = (rng.normal(size=(n, 2)) * 1.5).astype(np.float32)
+    lref, gref = O.sigmoid_loss_and_grad(h, low, 2 * pi, DEFAULT_SIG)
+    # full-set form: tile range of this rank + all-reduce
+    loss, grad = parallel.sharded_sigmoid_cost(cu(h), cu(low), 2 * pi, DEFAULT_SIG)
+    np.testing.assert_allclose(loss.item(), lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(grad.cpu().numpy(), gref.numpy()) < GRAD_RTOL
+    # through the public closure
+    z = cu(low).requires_grad_(True)
+    sigmoid_loss(process_group=nccl_world1)(cu(h), z).backward()
+    assert relnorm(z.grad.cpu().numpy(), gref.numpy()) < GRAD_RTOL
+    # data-parallel form: all-gather, tile slice, all-reduce + reduce-scatter
+    for red in ("mean", "sum"):
+        z = cu(low).requires_grad_(True)
+        dp = parallel.data_parallel_sigmoid_cost(cu(h), z, 2 * pi, DEFAULT_SIG, grad_reduction=red)
+        dp.backward()
+        np.testing.assert_allclose(dp.item(), lref.item(), rtol=LOSS_RTOL)
+        assert relnorm(z.grad.cpu().numpy(), gref.numpy()) < GRAD_RTOL    # world = 1: both reductions coincide

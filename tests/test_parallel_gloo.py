@@ -65,10 +65,26 @@ def _worker(rank, world, port, q):
         zl = low[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
         dp = parallel.data_parallel_sigmoid_cost(high[rank * rows:(rank + 1) * rows], zl, 2 * math.pi, SIG, partial_fn=_oracle_partial)
         dp.backward()
+        # a training step's parameter gradient: replicated weights, local-mean term + the global-batch cost, then the
+        # host framework's data-parallel MEAN all-reduce (DDP / Horovod / tf.distribute).  grad_reduction="mean" must make
+        # that average equal the single-process gradient on the global batch (the round-1 version was world_size too small).
+        w = torch.from_numpy(np.random.default_rng(6).normal(size=(d, 2)) * 0.3).requires_grad_(True)
+        xl = high[rank * rows:(rank + 1) * rows]
+        zl2 = torch.tanh(xl @ w)
+        (500.0 * parallel.data_parallel_sigmoid_cost(xl, zl2, 2 * math.pi, SIG, partial_fn=_oracle_partial) + (zl2 ** 2).mean()).backward()
+        wg = w.grad.clone()
+        dist.all_reduce(wg)
+        wg /= world
+        w2 = w.detach().clone().requires_grad_(True)
+        zl3 = torch.tanh(xl @ w2)
+        (500.0 * parallel.data_parallel_sigmoid_cost(xl, zl3, 2 * math.pi, SIG, partial_fn=_oracle_partial, grad_reduction="sum")
+         + (zl3 ** 2).mean() / world).backward()
+        wg_sum = w2.grad.clone()
+        dist.all_reduce(wg_sum)    # a framework that SUMS the ranks' gradients (local means pre-divided by the caller)
         # host -> device replication from one slice per rank (7 rows over 2 ranks: a ragged last slice)
         xh = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
         assert torch.equal(parallel.replicate_from_host(xh, torch.device("cpu")), xh)
-        q.put((rank, loss.item(), grad.numpy(), parallel.tile_range(n, rank, world), fr, dp.item(), zl.grad.numpy()))
+        q.put((rank, loss.item(), grad.numpy(), parallel.tile_range(n, rank, world), fr, dp.item(), zl.grad.numpy(), wg.numpy(), wg_sum.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -93,11 +109,17 @@ def test_sharded_cost_world2_gloo():
     high = rng.uniform(-math.pi, math.pi, size=(300, 12))
     low = rng.normal(size=(300, 2))
     lref, gref = O.sigmoid_loss_and_grad(high, low, 2 * math.pi, SIG)
-    for rank, loss, grad, tr, fr, dp_loss, dp_grad in results:
+    # single-process training-step gradient on the global batch
+    wref = torch.from_numpy(np.random.default_rng(6).normal(size=(12, 2)) * 0.3).requires_grad_(True)
+    zz = torch.tanh(torch.from_numpy(high) @ wref)
+    (500.0 * O.sigmoid_loss(2 * math.pi, SIG)(high, zz) + (zz ** 2).mean()).backward()
+    for rank, loss, grad, tr, fr, dp_loss, dp_grad, wg, wg_sum in results:
+        assert np.linalg.norm(wg - wref.grad.numpy()) <= 1e-9 * np.linalg.norm(wref.grad.numpy())
+        assert np.linalg.norm(wg_sum - wref.grad.numpy()) <= 1e-9 * np.linalg.norm(wref.grad.numpy())
         np.testing.assert_allclose(loss, lref.item(), rtol=1e-9)          # every rank holds the reduced result
         assert np.linalg.norm(grad - gref.numpy()) <= 1e-8 * np.linalg.norm(gref.numpy())
         np.testing.assert_allclose(dp_loss, lref.item(), rtol=1e-6)       # float32 scalar out of the autograd op
-        mine = gref.numpy()[rank * 150:(rank + 1) * 150]
+        mine = 2 * gref.numpy()[rank * 150:(rank + 1) * 150]   # grad_reduction="mean" (default): scaled by world_size = 2
         assert np.linalg.norm(dp_grad - mine) <= 1e-6 * np.linalg.norm(mine)
     (b0, e0), (b1, e1) = results[0][3], results[1][3]
     assert b0 == 0 and e0 == b1 and abs((e0 - b0) - (e1 - b1)) <= 1
