@@ -173,7 +173,7 @@ class SigmoidCost(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------------
-# distance matrices
+# raw forward / backward calls (no autograd): shared by the torch adapter below and by tf_adapter.py
 # ---------------------------------------------------------------------------------------------------
 def _slice_count(n: int, start, stop, step) -> int:
     return len(range(*slice(start, stop, step).indices(n)))
@@ -183,33 +183,27 @@ def _idx(v) -> int:
     return _lib.NONE_INDEX if v is None else int(v)
 
 
-class PairwiseDist(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, squared, flat, start, stop, step):
-        require_cuda(x, "positions")
-        x = f32c(x)
-        if x.dim() not in (2, 3):
-            raise EmkError(-4, f"pairwise_dist needs rank 2 or 3, got {tuple(x.shape)}")
-        n_all = x.shape[0] if x.dim() == 2 else x.shape[1]
-        b = 1 if x.dim() == 2 else x.shape[0]
-        n = _slice_count(n_all, start, stop, step)
-        shape = (b, n * (n - 1) // 2) if flat else (b, n, n)
-        out = _empty_like_shape(x, shape)
-        with torch.cuda.device(x.device):
-            check(_lib.lib().emk_dl_pairwise_dist(DL(x), _idx(start), _idx(stop), _idx(step), int(squared), int(flat), DL(out), stream_of(x)))
-        ctx.save_for_backward(x)
-        ctx.args = (squared, flat, start, stop, step)
-        return out
+def pairwise_dist_raw(x: torch.Tensor, squared=False, flat=False, start=None, stop=None, step=None) -> torch.Tensor:
+    require_cuda(x, "positions")
+    x = f32c(x)
+    if x.dim() not in (2, 3):
+        raise EmkError(-4, f"pairwise_dist needs rank 2 or 3, got {tuple(x.shape)}")
+    n_all = x.shape[0] if x.dim() == 2 else x.shape[1]
+    b = 1 if x.dim() == 2 else x.shape[0]
+    n = _slice_count(n_all, start, stop, step)
+    shape = (b, n * (n - 1) // 2) if flat else (b, n, n)
+    out = _empty_like_shape(x, shape)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_pairwise_dist(DL(x), _idx(start), _idx(stop), _idx(step), int(squared), int(flat), DL(out), stream_of(x)))
+    return out
 
-    @staticmethod
-    def backward(ctx, grad_out):
-        (x,) = ctx.saved_tensors
-        squared, flat, start, stop, step = ctx.args
-        grad_out = f32c(grad_out)
-        gx = torch.zeros_like(x)
-        with torch.cuda.device(x.device):
-            check(_lib.lib().emk_dl_pairwise_dist_bwd(DL(x), _idx(start), _idx(stop), _idx(step), int(squared), int(flat), DL(grad_out), DL(gx), stream_of(x)))
-        return gx, None, None, None, None, None
+
+def pairwise_dist_bwd_raw(x: torch.Tensor, grad_out: torch.Tensor, squared=False, flat=False, start=None, stop=None, step=None) -> torch.Tensor:
+    x, grad_out = f32c(x), f32c(grad_out)
+    gx = torch.zeros_like(x)   # unselected atoms (strided selection) receive zero
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_pairwise_dist_bwd(DL(x), _idx(start), _idx(stop), _idx(step), int(squared), int(flat), DL(grad_out), DL(gx), stream_of(x)))
+    return gx
 
 
 def pairwise_dist_periodic_raw(x: torch.Tensor, periodicity: float) -> torch.Tensor:
@@ -222,91 +216,63 @@ def pairwise_dist_periodic_raw(x: torch.Tensor, periodicity: float) -> torch.Ten
     return out
 
 
-class PairwiseDistPeriodic(torch.autograd.Function):
-    """pairwise_dist_periodic with the reference's autodiff conventions (encodermap/misc/distances.py:144-176)."""
-
-    @staticmethod
-    def forward(ctx, x, periodicity):
-        out = pairwise_dist_periodic_raw(x, periodicity)
-        ctx.save_for_backward(f32c(x), out)
-        ctx.periodicity = float(periodicity)
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        x, out = ctx.saved_tensors
-        grad_out = f32c(grad_out)
-        gx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            check(_lib.lib().emk_dl_pairwise_dist_periodic_bwd(DL(x), ctx.periodicity, DL(out), DL(grad_out), DL(gx), stream_of(x)))
-        return gx, None
+def pairwise_dist_periodic_bwd_raw(x: torch.Tensor, periodicity: float, out: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    x, out, grad_out = f32c(x), f32c(out), f32c(grad_out)
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_pairwise_dist_periodic_bwd(DL(x), float(periodicity), DL(out), DL(grad_out), DL(gx), stream_of(x)))
+    return gx
 
 
-# ---------------------------------------------------------------------------------------------------
-# elementwise
-# ---------------------------------------------------------------------------------------------------
-class PeriodicDistance(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, a, b, periodicity):
-        out = torch.empty_like(a)
-        with torch.cuda.device(a.device):
-            check(_lib.lib().emk_dl_periodic_distance(DL(a), DL(b), float(periodicity), DL(out), stream_of(a)))
-        ctx.save_for_backward(a, b)
-        ctx.periodicity = float(periodicity)
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        a, b = ctx.saved_tensors
-        grad_out = f32c(grad_out)
-        ga, gb = torch.empty_like(a), torch.empty_like(b)
-        with torch.cuda.device(a.device):
-            check(_lib.lib().emk_dl_periodic_distance_bwd(DL(a), DL(b), ctx.periodicity, DL(grad_out), DL(ga), DL(gb), stream_of(a)))
-        return ga, gb, None
+def periodic_distance_raw(a: torch.Tensor, b: torch.Tensor, periodicity: float) -> torch.Tensor:
+    a, b = f32c(require_cuda(a, "a")), f32c(require_cuda(b, "b"))
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        check(_lib.lib().emk_dl_periodic_distance(DL(a), DL(b), float(periodicity), DL(out), stream_of(a)))
+    return out
 
 
-class Sigmoid(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, r, sig, a, b):
-        out = torch.empty_like(r)
-        with torch.cuda.device(r.device):
-            check(_lib.lib().emk_dl_sigmoid(DL(r), float(sig), float(a), float(b), DL(out), stream_of(r)))
-        ctx.save_for_backward(r)
-        ctx.params = (float(sig), float(a), float(b))
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        (r,) = ctx.saved_tensors
-        grad_out = f32c(grad_out)
-        gr = torch.empty_like(r)
-        with torch.cuda.device(r.device):
-            check(_lib.lib().emk_dl_sigmoid_bwd(DL(r), *ctx.params, DL(grad_out), DL(gr), stream_of(r)))
-        return gr, None, None, None
+def periodic_distance_bwd_raw(a: torch.Tensor, b: torch.Tensor, periodicity: float, grad_out: torch.Tensor):
+    a, b, grad_out = f32c(a), f32c(b), f32c(grad_out)
+    ga, gb = torch.empty_like(a), torch.empty_like(b)
+    with torch.cuda.device(a.device):
+        check(_lib.lib().emk_dl_periodic_distance_bwd(DL(a), DL(b), float(periodicity), DL(grad_out), DL(ga), DL(gb), stream_of(a)))
+    return ga, gb
 
 
-class PeriodicInputFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, periodicity):
-        require_cuda(x, "inputs")
-        x = f32c(x)
-        if x.dim() != 2:
-            raise EmkError(-4, f"PeriodicInput needs rank-2 input, got {tuple(x.shape)}")
-        out = _empty_like_shape(x, (x.shape[0], 2 * x.shape[1]))
-        with torch.cuda.device(x.device):
-            check(_lib.lib().emk_dl_periodic_input(DL(x), float(periodicity), DL(out), stream_of(x)))
-        ctx.save_for_backward(x)
-        ctx.periodicity = float(periodicity)
-        return out
+def sigmoid_raw(r: torch.Tensor, sig: float, a: float, b: float) -> torch.Tensor:
+    r = f32c(require_cuda(r, "r"))
+    out = torch.empty_like(r)
+    with torch.cuda.device(r.device):
+        check(_lib.lib().emk_dl_sigmoid(DL(r), float(sig), float(a), float(b), DL(out), stream_of(r)))
+    return out
 
-    @staticmethod
-    def backward(ctx, grad_out):
-        (x,) = ctx.saved_tensors
-        grad_out = f32c(grad_out)
-        gx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            check(_lib.lib().emk_dl_periodic_input_bwd(DL(x), ctx.periodicity, DL(grad_out), DL(gx), stream_of(x)))
-        return gx, None
+
+def sigmoid_bwd_raw(r: torch.Tensor, sig: float, a: float, b: float, grad_out: torch.Tensor) -> torch.Tensor:
+    r, grad_out = f32c(r), f32c(grad_out)
+    gr = torch.empty_like(r)
+    with torch.cuda.device(r.device):
+        check(_lib.lib().emk_dl_sigmoid_bwd(DL(r), float(sig), float(a), float(b), DL(grad_out), DL(gr), stream_of(r)))
+    return gr
+
+
+def periodic_input_raw(x: torch.Tensor, periodicity: float) -> torch.Tensor:
+    require_cuda(x, "inputs")
+    x = f32c(x)
+    if x.dim() != 2:
+        raise EmkError(-4, f"PeriodicInput needs rank-2 input, got {tuple(x.shape)}")
+    out = _empty_like_shape(x, (x.shape[0], 2 * x.shape[1]))
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_periodic_input(DL(x), float(periodicity), DL(out), stream_of(x)))
+    return out
+
+
+def periodic_input_bwd_raw(x: torch.Tensor, periodicity: float, grad_out: torch.Tensor) -> torch.Tensor:
+    x, grad_out = f32c(x), f32c(grad_out)
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().emk_dl_periodic_input_bwd(DL(x), float(periodicity), DL(grad_out), DL(gx), stream_of(x)))
+    return gx
 
 
 def rotation_matrix_raw(axis: torch.Tensor, angle: torch.Tensor) -> torch.Tensor:
@@ -327,9 +293,6 @@ def column_mean_raw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-# ---------------------------------------------------------------------------------------------------
-# back-mapping
-# ---------------------------------------------------------------------------------------------------
 def _lengths_2d(lengths: torch.Tensor, b: int, n: int) -> torch.Tensor:
     lengths = f32c(lengths)
     if lengths.dim() == 1:
@@ -339,62 +302,199 @@ def _lengths_2d(lengths: torch.Tensor, b: int, n: int) -> torch.Tensor:
     return lengths
 
 
+def backmap_raw(lengths: torch.Tensor, angles: torch.Tensor, dihedrals: torch.Tensor) -> torch.Tensor:
+    """(lengths (1|b, n-1), angles (b, n-2), dihedrals (b, n-3)) -> xyz (b, n, 3); the +pi of BackMapLayer.call is inside."""
+    require_cuda(angles, "angles")
+    angles, dihedrals = f32c(angles), f32c(dihedrals)
+    b, n = angles.shape[0], angles.shape[1] + 2
+    lengths = _lengths_2d(lengths, b, n)
+    xyz = _empty_like_shape(angles, (b, n, 3))
+    with torch.cuda.device(angles.device):
+        check(_lib.lib().emk_dl_backmap(DL(lengths), DL(angles), DL(dihedrals), DL(xyz), stream_of(angles)))
+    return xyz
+
+
+def backmap_bwd_raw(lengths: torch.Tensor, angles: torch.Tensor, xyz: torch.Tensor, grad_xyz: torch.Tensor,
+                    need_lengths: bool = False, need_angles: bool = True, need_dihedrals: bool = True):
+    """Exact VJP from the final coordinates -> (grad_lengths (1|b, n-1) | None, grad_angles | None, grad_dihedrals | None)."""
+    angles, xyz, grad_xyz = f32c(angles), f32c(xyz), f32c(grad_xyz)
+    b, n = xyz.shape[0], xyz.shape[1]
+    lengths = _lengths_2d(lengths, b, n)
+    ga = torch.empty_like(angles) if need_angles else None
+    gd = _empty_like_shape(xyz, (b, n - 3)) if need_dihedrals else None
+    gl = _empty_like_shape(xyz, (b, n - 1)) if need_lengths else None
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_dl_backmap_bwd(DL(lengths), DL(angles), DL(xyz), DL(grad_xyz), DL(ga), DL(gd), DL(gl), stream_of(xyz)))
+    if gl is not None and lengths.shape[0] == 1:
+        gl = gl.sum(dim=0, keepdim=True)  # shared bond lengths: every frame contributes
+    return gl, ga, gd
+
+
+def chain_in_plane_raw(lengths: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
+    require_cuda(angles, "angles")
+    angles = f32c(angles)
+    b, n = angles.shape[0], angles.shape[1] + 2
+    lengths = _lengths_2d(lengths, b, n)
+    xyz = _empty_like_shape(angles, (b, n, 3))
+    with torch.cuda.device(angles.device):
+        check(_lib.lib().emk_dl_chain_in_plane(DL(lengths), DL(angles), DL(xyz), stream_of(angles)))
+    return xyz
+
+
+def chain_in_plane_bwd_raw(lengths: torch.Tensor, angles: torch.Tensor, grad_xyz: torch.Tensor, need_lengths: bool = True,
+                           need_angles: bool = True):
+    angles, grad_xyz = f32c(angles), f32c(grad_xyz)
+    b, n = angles.shape[0], angles.shape[1] + 2
+    lengths = _lengths_2d(lengths, b, n)
+    ga = torch.empty_like(angles) if need_angles else None
+    gl = _empty_like_shape(angles, (b, n - 1)) if need_lengths else None
+    with torch.cuda.device(angles.device):
+        check(_lib.lib().emk_dl_chain_in_plane_bwd(DL(lengths), DL(angles), DL(grad_xyz), DL(ga), DL(gl), stream_of(angles)))
+    if gl is not None and lengths.shape[0] == 1:
+        gl = gl.sum(dim=0, keepdim=True)
+    return gl, ga
+
+
+def d2c_raw(dihedrals: torch.Tensor, cartesian: torch.Tensor, one_way: int) -> torch.Tensor:
+    require_cuda(dihedrals, "dihedrals")
+    dihedrals, cartesian = f32c(dihedrals), f32c(cartesian)
+    b, n = dihedrals.shape[0], dihedrals.shape[1] + 3
+    xyz = _empty_like_shape(dihedrals, (b, n, 3))
+    with torch.cuda.device(dihedrals.device):
+        check(_lib.lib().emk_dl_dihedrals_to_cartesian(DL(dihedrals), DL(cartesian), int(one_way), DL(xyz), stream_of(dihedrals)))
+    return xyz
+
+
+def d2c_bwd_raw(xyz: torch.Tensor, grad_xyz: torch.Tensor, one_way: int) -> torch.Tensor:
+    xyz, grad_xyz = f32c(xyz), f32c(grad_xyz)
+    gd = _empty_like_shape(xyz, (xyz.shape[0], xyz.shape[1] - 3))
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_dl_dihedrals_to_cartesian_bwd(DL(xyz), DL(grad_xyz), int(one_way), DL(gd), stream_of(xyz)))
+    return gd
+
+
+def d2c_chain_bwd_raw(cartesian: torch.Tensor, xyz: torch.Tensor, grad_xyz: torch.Tensor, one_way: int) -> torch.Tensor:
+    """Gradient w.r.t. the START chain; a rank-2 (shared) chain receives the sum over frames, as the reference's tiling implies.
+    One thread per frame in float64 (a correctness path: the models use the fused BackMapLayer op, whose gradient w.r.t. the
+    planar chain never exists as a tensor)."""
+    cartesian, xyz, grad_xyz = f32c(cartesian), f32c(xyz), f32c(grad_xyz)
+    gc = torch.empty_like(xyz)
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_dl_dihedrals_to_cartesian_chain_bwd(DL(cartesian), DL(xyz), DL(grad_xyz), int(one_way), DL(gc), stream_of(xyz)))
+    if cartesian.dim() == 2:
+        gc = gc.sum(dim=0)
+    return gc
+
+
+# ---------------------------------------------------------------------------------------------------
+# torch.autograd adapters
+# ---------------------------------------------------------------------------------------------------
+class PairwiseDist(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, squared, flat, start, stop, step):
+        out = pairwise_dist_raw(x, squared, flat, start, stop, step)
+        ctx.save_for_backward(f32c(x))
+        ctx.args = (squared, flat, start, stop, step)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        return pairwise_dist_bwd_raw(x, grad_out, *ctx.args), None, None, None, None, None
+
+
+class PairwiseDistPeriodic(torch.autograd.Function):
+    """pairwise_dist_periodic with the reference's autodiff conventions (encodermap/misc/distances.py:144-176)."""
+
+    @staticmethod
+    def forward(ctx, x, periodicity):
+        out = pairwise_dist_periodic_raw(x, periodicity)
+        ctx.save_for_backward(f32c(x), out)
+        ctx.periodicity = float(periodicity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        return pairwise_dist_periodic_bwd_raw(x, ctx.periodicity, out, grad_out), None
+
+
+class PeriodicDistance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, periodicity):
+        out = periodic_distance_raw(a, b, periodicity)
+        ctx.save_for_backward(a, b)
+        ctx.periodicity = float(periodicity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b = ctx.saved_tensors
+        ga, gb = periodic_distance_bwd_raw(a, b, ctx.periodicity, grad_out)
+        return ga, gb, None
+
+
+class Sigmoid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, sig, a, b):
+        out = sigmoid_raw(r, sig, a, b)
+        ctx.save_for_backward(r)
+        ctx.params = (float(sig), float(a), float(b))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (r,) = ctx.saved_tensors
+        return sigmoid_bwd_raw(r, *ctx.params, grad_out), None, None, None
+
+
+class PeriodicInputFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, periodicity):
+        out = periodic_input_raw(x, periodicity)
+        ctx.save_for_backward(f32c(x))
+        ctx.periodicity = float(periodicity)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        return periodic_input_bwd_raw(x, ctx.periodicity, grad_out), None
+
+
 class BackMap(torch.autograd.Function):
     """(lengths, angles, dihedrals) -> xyz with the exact VJP from force/torque prefix sums."""
 
     @staticmethod
     def forward(ctx, lengths, angles, dihedrals):
-        require_cuda(angles, "angles")
-        angles, dihedrals = f32c(angles), f32c(dihedrals)
-        b, n = angles.shape[0], angles.shape[1] + 2
-        lengths = _lengths_2d(lengths, b, n)
-        xyz = _empty_like_shape(angles, (b, n, 3))
-        with torch.cuda.device(angles.device):
-            check(_lib.lib().emk_dl_backmap(DL(lengths), DL(angles), DL(dihedrals), DL(xyz), stream_of(angles)))
+        xyz = backmap_raw(lengths, angles, dihedrals)
         ctx.save_for_backward(lengths, angles, xyz)
         return xyz
 
     @staticmethod
     def backward(ctx, grad_xyz):
         lengths, angles, xyz = ctx.saved_tensors
-        grad_xyz = f32c(grad_xyz)
-        b, n = xyz.shape[0], xyz.shape[1]
         need_l, need_a, need_d = ctx.needs_input_grad
-        ga = torch.empty_like(angles) if need_a else None
-        gd = _empty_like_shape(xyz, (b, n - 3)) if need_d else None
-        gl = _empty_like_shape(xyz, (b, n - 1)) if need_l else None
-        with torch.cuda.device(xyz.device):
-            check(_lib.lib().emk_dl_backmap_bwd(DL(lengths), DL(angles), DL(xyz), DL(grad_xyz), DL(ga), DL(gd), DL(gl), stream_of(xyz)))
-        if gl is not None and lengths.shape[0] == 1:
-            gl = gl.sum(dim=0, keepdim=True)  # shared bond lengths: every frame contributes
+        gl, ga, gd = backmap_bwd_raw(lengths, angles, xyz, grad_xyz, need_l, need_a, need_d)
+        if gl is not None:
+            gl = gl.reshape(lengths.shape) if gl.numel() == lengths.numel() else gl
         return gl, ga, gd
 
 
 class ChainInPlane(torch.autograd.Function):
     @staticmethod
     def forward(ctx, lengths, angles):
-        require_cuda(angles, "angles")
-        angles = f32c(angles)
-        b, n = angles.shape[0], angles.shape[1] + 2
-        lengths = _lengths_2d(lengths, b, n)
-        xyz = _empty_like_shape(angles, (b, n, 3))
-        with torch.cuda.device(angles.device):
-            check(_lib.lib().emk_dl_chain_in_plane(DL(lengths), DL(angles), DL(xyz), stream_of(angles)))
+        xyz = chain_in_plane_raw(lengths, angles)
         ctx.save_for_backward(lengths, angles)
         return xyz
 
     @staticmethod
     def backward(ctx, grad_xyz):
         lengths, angles = ctx.saved_tensors
-        grad_xyz = f32c(grad_xyz)
-        b, n = angles.shape[0], angles.shape[1] + 2
         need_l, need_a = ctx.needs_input_grad
-        ga = torch.empty_like(angles) if need_a else None
-        gl = _empty_like_shape(angles, (b, n - 1)) if need_l else None
-        with torch.cuda.device(angles.device):
-            check(_lib.lib().emk_dl_chain_in_plane_bwd(DL(lengths), DL(angles), DL(grad_xyz), DL(ga), DL(gl), stream_of(angles)))
-        if gl is not None and lengths.shape[0] == 1:
-            gl = gl.sum(dim=0, keepdim=True)
+        gl, ga = chain_in_plane_bwd_raw(lengths, angles, grad_xyz, need_l, need_a)
+        if gl is not None:
+            gl = gl.reshape(lengths.shape) if gl.numel() == lengths.numel() else gl
         return gl, ga
 
 
@@ -404,29 +504,15 @@ class DihedralsToCartesian(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, dihedrals, cartesian, one_way):
-        require_cuda(dihedrals, "dihedrals")
-        dihedrals, cartesian = f32c(dihedrals), f32c(cartesian)
-        b, n = dihedrals.shape[0], dihedrals.shape[1] + 3
-        xyz = _empty_like_shape(dihedrals, (b, n, 3))
-        with torch.cuda.device(dihedrals.device):
-            check(_lib.lib().emk_dl_dihedrals_to_cartesian(DL(dihedrals), DL(cartesian), int(one_way), DL(xyz), stream_of(dihedrals)))
-        ctx.save_for_backward(xyz, cartesian)
+        xyz = d2c_raw(dihedrals, cartesian, one_way)
+        ctx.save_for_backward(xyz, f32c(cartesian))
         ctx.one_way = int(one_way)
         return xyz
 
     @staticmethod
     def backward(ctx, grad_xyz):
         xyz, cartesian = ctx.saved_tensors
-        grad_xyz = f32c(grad_xyz)
         need_d, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gd = gc = None
-        with torch.cuda.device(xyz.device):
-            if need_d:
-                gd = _empty_like_shape(xyz, (xyz.shape[0], xyz.shape[1] - 3))
-                check(_lib.lib().emk_dl_dihedrals_to_cartesian_bwd(DL(xyz), DL(grad_xyz), ctx.one_way, DL(gd), stream_of(xyz)))
-            if need_c:
-                gc = torch.empty_like(xyz)
-                check(_lib.lib().emk_dl_dihedrals_to_cartesian_chain_bwd(DL(cartesian), DL(xyz), DL(grad_xyz), ctx.one_way, DL(gc), stream_of(xyz)))
-                if cartesian.dim() == 2:
-                    gc = gc.sum(dim=0)
+        gd = d2c_bwd_raw(xyz, grad_xyz, ctx.one_way) if need_d else None
+        gc = d2c_chain_bwd_raw(cartesian, xyz, grad_xyz, ctx.one_way) if need_c else None
         return gd, gc, None

@@ -253,7 +253,7 @@ def test_raw_pointer_and_host_entry_points(em):
     torch.cuda.synchronize()
     np.testing.assert_allclose(ld.item(), lref.item(), rtol=LOSS_RTOL)
     # argument errors come back as codes + message, never as a crash
-    assert L.emk_sigmoid_cost(hd.data_ptr(), n, d, zd.data_ptr(), 9, 2 * pi, _lib.sig_array(DEFAULT_SIG), 0, 1, ld.data_ptr(), gd.data_ptr(), 0, None) == -7
+    assert L.emk_sigmoid_cost(hd.data_ptr(), n, d, zd.data_ptr(), 0, 2 * pi, _lib.sig_array(DEFAULT_SIG), 0, 1, ld.data_ptr(), gd.data_ptr(), 0, None) == -4
     assert b"latent width" in L.emk_last_error()
     assert L.emk_sigmoid_cost(None, n, d, zd.data_ptr(), 2, 2 * pi, _lib.sig_array(DEFAULT_SIG), 0, 1, ld.data_ptr(), gd.data_ptr(), 0, None) == -1
     # DLPack validation: non-contiguous and wrong-dtype tensors are refused with a code, not copied silently
