@@ -9,14 +9,15 @@ Workload (BASELINE.json configs[3], the configuration the north-star target is q
 GPU): the full-set sketch-map sigmoid cost, forward + backward, over 65 536 synthetic frames x 1 024
 periodic dims -> 2-d latent.  One step = one evaluation of loss and dL/d(latent) over all pair tiles; with
 N GPUs the tile list is cut into N contiguous ranges (inputs replicated) and the partial loss/gradient are
-all-reduced over NCCL -- total work is fixed, so this is STRONG scaling.
+summed by ONE fused NCCL launch of libemk's own communicator -- total work is fixed, so this is STRONG scaling.
+`per_rank` attributes the step time (kernel / collective incl. the wait for the slowest rank) rank by rank.
 
 metric  : unique unordered pairs (incl. diagonal) per second, N(N+1)/2 / step time, whole job
 value   : inputs resident in HBM, device-timed (CUDA events, max over ranks)
 e2e     : same through the public API (`sigmoid_loss(...)(y_true, y_pred)` + backward) with HOST pinned
-          buffers: H2D of both inputs and D2H of loss and gradient inside the timed region (one GPU: y_true is
-          handed over as the pinned host tensor and streamed in behind the pair tiles; N GPUs: 1/N per host
-          link + NVLink all-gather)
+          buffers: H2D of both inputs and D2H of loss and gradient inside the timed region (y_true is handed
+          over as the pinned host tensor; every rank streams the rows ITS tile range touches over its own host
+          link, in chunks behind the pair tiles that need them)
 roofline: the pair-tile kernel against the FP32 issue roofline of SURVEY.md section 8d
           (4 lane-instructions per (pair, dim) + 60 per pair;  peak = 148 SM x 128 lanes x sm_max clock from
           MEASURED_PEAKS.json, peak_measured = FFMA rate probed live on the device; the kernel is neither
@@ -126,15 +127,15 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_value(steps, warmup):
-    """pairs/s of the float32 torch-CPU restatement (op for op, (N,N,D) broadcast + autograd backward)."""
+def cpu_reference_value(steps, warmup, rows=CPU_SAMPLE_ROWS):
+    """pairs/s of the float32 torch-CPU restatement (op for op, (N,N,D) broadcast + autograd backward) on `rows` rows."""
     import torch
 
     from oracle import em_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x, z = synth_high(CPU_SAMPLE_ROWS, N_DIMS, "cpu", 4321)
+    x, z = synth_high(rows, N_DIMS, "cpu", 4321)
     f = O.sigmoid_loss(PERIOD, SIG)
     times = []
     for it in range(warmup + steps):
@@ -144,7 +145,7 @@ def cpu_reference_value(steps, warmup):
         loss.backward()
         times.append(time.perf_counter() - t0)
     t = statistics.median(times[warmup:])
-    pairs = CPU_SAMPLE_ROWS * (CPU_SAMPLE_ROWS + 1) / 2
+    pairs = rows * (rows + 1) / 2
     return pairs / t, t, cores
 
 
@@ -213,6 +214,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    from encodermap_b200 import parallel
+
+    if world > 1:
+        parallel.init_comm()    # libemk's own NCCL communicator: loss + gradient summed in ONE fused launch per step
     x, z = synth_high(N_ROWS, N_DIMS, dev, 4321)
     tr = _lib.pair_tile_range(N_ROWS, rank, world)
     pairs = N_ROWS * (N_ROWS + 1) / 2
@@ -220,49 +225,69 @@ def run_ours(args):
     def step():
         loss, grad = _ops.sigmoid_cost_raw(x, z, PERIOD, SIG, tr, True)
         if world > 1:
-            dist.all_reduce(loss)
-            dist.all_reduce(grad)
+            parallel.allreduce_cost(loss, grad)
         return loss, grad
 
     for _ in range(args.warmup):
         step()
     barrier()
-    kern_ms = []
+    marks = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record()
         for _ in range(args.steps):
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0, k1, c1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             k0.record()
             loss, grad = _ops.sigmoid_cost_raw(x, z, PERIOD, SIG, tr, True)
             k1.record()
             if world > 1:
-                dist.all_reduce(loss)
-                dist.all_reduce(grad)
-            kern_ms.append((k0, k1))
+                parallel.allreduce_cost(loss, grad)
+            c1.record()
+            marks.append((k0, k1, c1))
         e1.record()
         barrier()
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = total_ms / args.steps
     value = pairs / (ms_per_step * 1e-3)
-    kernel_ms = max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in kern_ms))
+    kernel_ms = max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b, _ in marks))
     loss_value = float(loss.item())
+    # attribution of the step time: per rank and per step, the kernel and the collective (incl. the wait for the slowest rank)
+    per_rank = None
+    multi_gpu_check = None
+    if world > 1:
+        mine = torch.tensor([[a.elapsed_time(b), b.elapsed_time(c)] for a, b, c in marks], dtype=torch.float64, device=dev)
+        allm = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        allm = torch.stack(allm).cpu()               # (rank, step, {kernel, collective})
+        kern, coll = allm[:, :, 0], allm[:, :, 1]
+        per_rank = {"kernel_ms_mean": [round(v, 4) for v in kern.mean(1).tolist()],
+                    "kernel_ms_max": [round(v, 4) for v in kern.max(1).values.tolist()],
+                    "collective_ms_mean": [round(v, 4) for v in coll.mean(1).tolist()],
+                    "collective_ms_min": [round(v, 4) for v in coll.min(1).values.tolist()],
+                    "step_max_kernel_ms_mean": round(kern.max(0).values.mean().item(), 4),
+                    "skew_ms_mean": round((kern.max(0).values - kern.min(0).values).mean().item(), 4),
+                    "note": "collective_ms of a rank = its wait for the slowest rank of that step + the fused NCCL launch; "
+                            "collective_ms_min over steps and ranks is the cost of the collective itself"}
+        # the sharded result equals the one-GPU result (rank 0 evaluates every tile once, outside the timed region)
+        if rank == 0:
+            lfull, gfull = _ops.sigmoid_cost_raw(x, z, PERIOD, SIG, None, True)
+            multi_gpu_check = {"loss_rel_diff": abs(loss_value - lfull.item()) / lfull.item(),
+                               "grad_rel_diff": ((grad - gfull).norm() / gfull.norm()).item()}
+            del lfull, gfull
+        barrier()
 
     # ---- end to end: host pinned buffers in, loss + gradient out, through the public API --------------------
     xh = x.cpu().pin_memory()
     zh = z.cpu().pin_memory()
     gh = torch.empty_like(zh).pin_memory()
     f = sigmoid_loss(None, periodicity_overwrite=PERIOD, dist_dig_parameters_overwrite=SIG,
-                     process_group=(dist.group.WORLD if world > 1 else None))
-
-    from encodermap_b200 import parallel
+                     process_group=(dist.group.WORLD if world > 1 else None), check_finite=False)
 
     def e2e_step():
-        # N = 1: the public API takes the pinned host tensor itself and streams it in behind the pair tiles;
-        # N > 1: every rank moves 1/N of the (replicated) input over its own host link, NVLink all-gathers the rest
-        xd = xh if world == 1 else parallel.replicate_from_host(xh, dev)
-        zd = parallel.replicate_from_host(zh, dev).requires_grad_(True)
-        l = f(xd, zd)
+        # the public API takes the pinned host tensor itself: every rank streams the rows ITS tile range touches over its
+        # own host link, in chunks behind the pair tiles that need them (no exchange of inputs between GPUs)
+        zd = zh.to(dev, non_blocking=True).requires_grad_(True)
+        l = f(xh, zd)
         l.backward()
         gh.copy_(zd.grad, non_blocking=True)
         return l.item()
@@ -277,6 +302,10 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = pairs / (e2e_ms * 1e-3)
+    # bytes this rank copies in per step: the rows from the band of its first tile to the end + the latent
+    first_row = min(N_ROWS, (_lib.pair_tile_decode(N_ROWS, tr[0])[0] * 128 // 8192) * 8192) if tr[1] > tr[0] else N_ROWS
+    h2d_mine = (N_ROWS - first_row) * N_DIMS * 4 + zh.numel() * 4
+    h2d_max = max_over_ranks(float(h2d_mine))
 
     extra = {}
     if rank == 0 and not args.no_extra:
@@ -289,7 +318,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             extra["backmap_sharded"] = {"frames_per_s": BACKMAP_FRAMES // world * world / (t.item() * 1e-3), "n_gpus": world,
-                                        "frames": BACKMAP_FRAMES // world * world, "scaling": "strong"}
+                                        "frames": BACKMAP_FRAMES // world * world, "scaling": "strong", "ms": t.item()}
+        # third metric at N GPUs: data-parallel training of configs[1] (global batch 4096 fixed, and 4096 per GPU)
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import train_harness
+
+            dp = {"strong_global_batch_4096": train_harness.run_dp(dev, dist.group.WORLD, steps=20, batch_global=4096, weak=False),
+                  "weak_4096_per_gpu": train_harness.run_dp(dev, dist.group.WORLD, steps=20, batch_global=4096, weak=True)}
+        except Exception as e:  # noqa: BLE001
+            dp = {"error": repr(e)[:300]}
+        if rank == 0:
+            extra["train_steps_data_parallel"] = dp
 
     if rank == 0:
         lane_instr = pairs * (4 * N_DIMS + 60)
@@ -300,17 +340,23 @@ def run_ours(args):
 
         probe = ctypes.c_double(0.0)
         _lib.check(L.emk_probe_fp32(ctypes.byref(probe)))
-        # DRAM bytes of one launch from the committed ncu capture of this kernel (profiles/, tools/profile_r1.sh)
-        traffic = None
-        tp = ROOT / "profiles" / "r01_pair_tile_traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        # DRAM bytes of one launch: NOT measured in this run -- read from the committed ncu --set full capture of this kernel
+        traffic, traffic_source = None, None
+        for name in ("r02_pair_tile_traffic.json", "r01_pair_tile_traffic.json"):
+            tp = ROOT / "profiles" / name
+            if tp.exists():
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+                traffic_source = f"committed ncu capture profiles/{name} (dram__bytes_read.sum + dram__bytes_write.sum of one launch at n_gpus=1), not a live measurement"
+                break
         cpu_v, cpu_t, cores = (None, None, None)
         cpu_baseline = None
         if world == 1 and not args.no_cpu:
             cpu_v, cpu_t, cores = cpu_reference_value(5, 1)
+            v256, t256, _ = cpu_reference_value(5, 1, 256)
+            v1024, t1024, _ = cpu_reference_value(2, 1, 1024)
             cpu_baseline = {"value": cpu_v, "unit": "unique pairs/s", "cores": cores, "kind": "port",
-                            "sample": f"N={CPU_SAMPLE_ROWS} x {N_DIMS} of the same data, float32 torch-CPU restatement (oracle/), median of 5, {cpu_t * 1e3:.0f} ms/eval"}
+                            "sample": f"N={CPU_SAMPLE_ROWS} x {N_DIMS} of the same data, float32 torch-CPU restatement (oracle/), median of 5, {cpu_t * 1e3:.0f} ms/eval",
+                            "other_samples": {"N=256": {"value": v256, "ms_per_eval": t256 * 1e3}, "N=1024": {"value": v1024, "ms_per_eval": t1024 * 1e3}}}
         line = {
             "metric": "sigmoid_cost_pairs_per_s_fwd_bwd", "value": value, "unit": "unique pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -320,7 +366,8 @@ def run_ours(args):
                        "ordered_pairs_per_s": value * 2 * N_ROWS / (N_ROWS + 1), "l2": "inputs (268 MB) larger than L2 (126 MB); no flush needed",
                        "parallelism": f"tile-shard x{world}", "loss": loss_value},
             "roofline": {"bound": "fp32-issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-instr/s",
-                         "frac": achieved / peak, "traffic": traffic,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                         "traffic_note": "30x the algorithmic 0.27 GB: column blocks are re-read from DRAM once per 1024-row band (L2 keeps the band); 0.4 % of DRAM bandwidth, irrelevant for a kernel bound by FP32 issue",
                          "peak_measured": probe.value / 1e12, "frac_of_measured": achieved / probe.value if probe.value else None,
                          "peak_measured_how": "emk_probe_fp32: register-only FFMA chains, 8 CTAs x 256 threads per SM, best of 3, CUDA events",
                          "kernel": "pair_tile_kernel<periodic,cost>", "kernel_ms": kernel_ms,
@@ -328,17 +375,38 @@ def run_ours(args):
                          "peak_source": f"148 SM x 128 lanes x {peaks['sm_max_mhz']} MHz ({peaks['source']}); no FP32 figure is measured there"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "unique pairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": (xh.numel() + zh.numel()) * 4 // world, "d2h_bytes_per_step": gh.numel() * 4 + 4,
-                    "note": ("sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward: rows are copied in chunks on a side stream behind the pair tiles that need them; loss + gradient read back"
-                             if world == 1 else
-                             "per rank: 1/n_gpus of the replicated input over the host link + NCCL all-gather over NVLink (parallel.replicate_from_host); every rank reads loss + gradient back")},
+                    "h2d_bytes_per_step": int(h2d_max), "d2h_bytes_per_step": gh.numel() * 4 + 4,
+                    "note": "sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward: every rank copies the rows its tile range touches (h2d_bytes_per_step = the largest rank's share) in chunks on a side stream behind the pair tiles that need them; loss + gradient read back"},
             "gpu_launches": args.steps * world,
+            "per_rank": per_rank,
+            "multi_gpu_check": multi_gpu_check,
             "cpu_baseline": cpu_baseline,
+            "secondary": secondary_summary(extra, world),
             "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
+        parallel.destroy_comm()
         dist.destroy_process_group()
+
+
+def secondary_summary(extra, world):
+    """The other two metrics of BASELINE.json lifted out of `extra`: back-mapped frames/s (with its HBM roofline) and train
+    steps/s.  Whole-job numbers at this n_gpus; the driver can compute scaling from the per-N lines."""
+    out = {}
+    bm = extra.get("backmap_sharded") if world > 1 else extra.get("backmap_fwd")
+    if bm:
+        out["backmap_frames_per_s"] = {"value": bm["frames_per_s"], "unit": "frames/s", "n_gpus": world, "n_atoms": BACKMAP_ATOMS,
+                                       "frames": bm["frames"], "scaling": "strong (1M frames split by frame range, no communication)"}
+        if "roofline" in bm:
+            out["backmap_frames_per_s"]["roofline"] = bm["roofline"]
+    ts = extra.get("train_steps")
+    if isinstance(ts, dict) and "error" not in ts:
+        out["train_steps_per_s"] = {k: {m: v[m]["steps_per_s"] for m in v} for k, v in ts.items()}
+    dp = extra.get("train_steps_data_parallel")
+    if isinstance(dp, dict) and "error" not in dp:
+        out["train_steps_per_s_data_parallel"] = {k: {m: (v[m].get("steps_per_s") if isinstance(v[m], dict) else v[m]) for m in v} for k, v in dp.items()}
+    return out
 
 
 def backmap_frames_per_s(dev, frames):

@@ -20,6 +20,6 @@ def __getattr__(name):
     # heavier submodules are imported on first use so that `import encodermap_b200` works without a GPU
     import importlib
 
-    if name in ("misc", "loss_functions", "models", "encodermap_tf1", "parallel", "tf_adapter", "_ops"):
+    if name in ("misc", "loss_functions", "models", "encodermap_tf1", "parallel", "tf_adapter", "graph", "_ops"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -83,14 +83,18 @@ def _row_chunk_tiles(n: int, rows_per_chunk: int):
 
 
 def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicity: float, sig: Sequence[float],
-                          need_grad: bool = True, rows_per_chunk: int = 8192):
+                          need_grad: bool = True, rows_per_chunk: int = 8192, tile_range: Optional[Tuple[int, int]] = None):
     """Same result as ``sigmoid_cost_raw`` with the high-d input in (pinned) HOST memory: rows are copied to the device in
     chunks from the LAST row backwards on a side stream while the pair tiles that only need the rows already there run
     on the current stream (tile ids are band-major, so every chunk of rows unlocks one contiguous tile range).  The copy
-    of a 65 536 x 1 024 input (268 MB, ~5 ms over PCIe) hides completely behind the first 16 ms of tiles."""
+    of a 65 536 x 1 024 input (268 MB, ~5 ms over PCIe) hides completely behind the first 16 ms of tiles.
+
+    With a ``tile_range`` (one rank's share of a multi-GPU evaluation) only the rows that range touches are copied --
+    tiles from tile t on need no row before the band of t, so the last of 8 ranks moves 35 % of the matrix -- and every
+    rank streams its own rows over its own host link behind its own tiles: no exchange of inputs between GPUs at all."""
     require_cuda(low, "y_pred")
     if high_host.is_cuda:
-        return sigmoid_cost_raw(high_host, low, periodicity, sig, None, need_grad)
+        return sigmoid_cost_raw(high_host, low, periodicity, sig, tile_range, need_grad)
     if high_host.dtype != torch.float32 or not high_host.is_contiguous() or high_host.dim() != 2:
         raise EmkError(-4, "streamed sigmoid cost needs a contiguous rank-2 float32 host tensor")
     low = f32c(low)
@@ -98,10 +102,11 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
     if d % 4 != 0:
         # the kernel would re-pad the whole (n, d) matrix into TMA-legal scratch on every chunk call (and read rows the
         # side stream is still writing): one plain copy, then the ordinary path, which pads once
-        return sigmoid_cost_raw(high_host.to(low.device, non_blocking=True), low, periodicity, sig, None, need_grad)
+        return sigmoid_cost_raw(high_host.to(low.device, non_blocking=True), low, periodicity, sig, tile_range, need_grad)
     rows_per_chunk = max(1024, (rows_per_chunk // 1024) * 1024)
     chunks = _row_chunk_tiles(n, rows_per_chunk)
     total = _lib.pair_tile_count(n)
+    tb, te = (0, total) if tile_range is None else tile_range
     dev = low.device
     high = torch.empty((n, d), dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float64, device=dev)
@@ -115,10 +120,17 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
     side.wait_stream(main)
     first = True
     with torch.cuda.device(dev):
+        if te <= tb:   # an empty share: the outputs are still defined (zero)
+            loss.zero_()
+            if grad is not None:
+                grad.zero_()
         for idx in range(len(chunks) - 1, -1, -1):
             r0, t0 = chunks[idx]
             r1 = min(n, r0 + rows_per_chunk)
             t1 = chunks[idx + 1][1] if idx + 1 < len(chunks) else total
+            if t1 <= tb or te <= tb:
+                break         # every remaining chunk lies before this rank's first tile: its rows are never read
+            t0, t1 = max(t0, tb), min(t1, te)
             with torch.cuda.stream(side):
                 high[r0:r1].copy_(high_host[r0:r1], non_blocking=True)
                 ev = torch.cuda.Event()
@@ -137,9 +149,11 @@ class SigmoidCostStreamed(torch.autograd.Function):
     """SigmoidCost with a pinned host tensor as the high-d input (copy overlapped with the pair tiles)."""
 
     @staticmethod
-    def forward(ctx, high_host, low, periodicity, sig):
+    def forward(ctx, high_host, low, periodicity, sig, tile_range=None, reduce_fn=None):
         _reject_high_grad(ctx.needs_input_grad[0])
-        loss, grad = sigmoid_cost_streamed(high_host, low, periodicity, sig, ctx.needs_input_grad[1])
+        loss, grad = sigmoid_cost_streamed(high_host, low, periodicity, sig, ctx.needs_input_grad[1], tile_range=tile_range)
+        if reduce_fn is not None:  # multi-GPU: sum the partial results of all ranks
+            loss, grad = reduce_fn(loss, grad)
         ctx.save_for_backward(grad)
         ctx.low_dtype = low.dtype
         return loss[0].to(torch.float32)
@@ -148,7 +162,7 @@ class SigmoidCostStreamed(torch.autograd.Function):
     def backward(ctx, grad_output):
         (grad,) = ctx.saved_tensors
         g = None if grad is None else (grad * grad_output).to(ctx.low_dtype)
-        return None, g, None, None
+        return None, g, None, None, None, None
 
 
 class SigmoidCost(torch.autograd.Function):

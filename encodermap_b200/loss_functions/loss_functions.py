@@ -63,6 +63,7 @@ def sigmoid_loss(
     dist_dig_parameters_overwrite: Optional[Sequence[float]] = None,
     *,
     process_group=None,
+    data_parallel: bool = False,
     check_finite="deferred",
 ) -> Callable:
     """Sigmoid loss closure.  Reference: encodermap/loss_functions/loss_functions.py:301-369.
@@ -71,7 +72,10 @@ def sigmoid_loss(
     one evaluation over the ranks of a torch.distributed group (inputs replicated, one all-reduce of
     the loss and dL/d(latent)); ``check_finite`` selects how the reference's finite assertion runs: ``"deferred"``
     (default -- checked one call late, no synchronisation), ``True`` (checked now, one synchronisation per call) or
-    ``False``; the closure's ``flush_finite_check()`` examines the last pending flag.  ``y_true`` may also be a PINNED
+    ``False``; the closure's ``flush_finite_check()`` examines the last pending flag.  ``data_parallel=True`` (with a
+    ``process_group``) is the form for data-parallel TRAINING: ``y_true`` / ``y_pred`` are this rank's rows of the global
+    batch, the value is the cost of the global batch and the gradient is pre-scaled for a mean-reducing framework
+    (``parallel.data_parallel_sigmoid_cost``).  ``y_true`` may also be a PINNED
     host tensor: it is then copied to the device in row chunks on a side stream while the pair tiles that need only the
     rows already there run.
 
@@ -86,14 +90,21 @@ def sigmoid_loss(
 
     def sigmoid_loss_func(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
         tile_range, reduce_fn = None, None
+        if data_parallel and process_group is not None:
+            from ..parallel import data_parallel_sigmoid_cost
+
+            cost = data_parallel_sigmoid_cost(y_true, y_pred, periodicity, sig, group=process_group)
+            finite(cost)
+            return cost
         if process_group is not None:
             from ..parallel import tile_shard
 
             tile_range, reduce_fn = tile_shard(int(y_true.shape[0]), process_group)
-        if process_group is None and not y_true.is_cuda and y_true.is_pinned():
+        if not y_true.is_cuda and y_true.is_pinned():
             # high-d input still in pinned host memory: streamed to the device behind the pair tiles (not a CPU path --
-            # unpinned CPU tensors are rejected like everywhere else)
-            cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig)
+            # unpinned CPU tensors are rejected like everywhere else); with a process group every rank streams only the
+            # rows its own tile range touches
+            cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
         else:
             cost = _ops.SigmoidCost.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
         finite(cost)
@@ -110,13 +121,14 @@ def _latent_of(model) -> Callable:
     return enc
 
 
-def distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite="deferred") -> Callable:
+def distance_loss(model, parameters=None, callback=None, *, process_group=None, data_parallel: bool = False,
+                  check_finite="deferred") -> Callable:
     """Encodermap distance_loss.  Reference: encodermap/loss_functions/loss_functions.py:200-298.
     ``model.encoder`` maps the (tuple of) inputs to the latent; ``callback`` is accepted for signature
     compatibility (summary writing stays in the host framework)."""
     p = Parameters() if parameters is None else parameters
     latent = _latent_of(model)
-    dist_loss = sigmoid_loss(p, process_group=process_group, check_finite=False)   # one check, on the scaled cost below
+    dist_loss = sigmoid_loss(p, process_group=process_group, data_parallel=data_parallel, check_finite=False)   # one check, below
     finite = _FiniteCheck(check_finite, "Dist cost became infinite or NaN.")
 
     def distance_loss_func(y_true, y_pred=None) -> torch.Tensor:
@@ -138,14 +150,15 @@ def distance_loss(model, parameters=None, callback=None, *, process_group=None, 
     return distance_loss_func
 
 
-def cartesian_distance_loss(model, parameters=None, callback=None, *, process_group=None, check_finite="deferred") -> Callable:
+def cartesian_distance_loss(model, parameters=None, callback=None, *, process_group=None, data_parallel: bool = False,
+                            check_finite="deferred") -> Callable:
     """Encodermap cartesian distance loss.  Reference: encodermap/loss_functions/loss_functions.py:873-944
     (non-periodic, ``cartesian_dist_sig_parameters``; called as ``(input pairwise distances, latent)``,
     models/models.py:2419-2422)."""
     p = ADCParameters() if parameters is None else parameters
     dist_loss = sigmoid_loss(p, periodicity_overwrite=float("inf"),
                              dist_dig_parameters_overwrite=p.cartesian_dist_sig_parameters, process_group=process_group,
-                             check_finite=False)
+                             data_parallel=data_parallel, check_finite=False)
     finite = _FiniteCheck(check_finite, "Cartesian distance cost became infinite or NaN.")
 
     def cartesian_distance_loss_func(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:

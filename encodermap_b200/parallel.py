@@ -211,6 +211,26 @@ def data_parallel_sigmoid_cost(high_local: torch.Tensor, low_local: torch.Tensor
     return _DataParallelCost.apply(high_local, low_local, periodicity, tuple(sig), group, partial_fn, scale)
 
 
+def average_gradients(params, group=None) -> None:
+    """The data-parallel all-reduce of the dense layers' gradients (what DDP / Horovod / tf.distribute do for the host
+    framework; SURVEY.md 8e last row: "replicas only"): one flat float32 buffer, one collective, mean over ranks, in place.
+    Goes through libemk's communicator when it is up (capturable in a CUDA graph next to the hot ops), else through
+    torch.distributed."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    world = dist.get_world_size(group)
+    flat = torch._utils._flatten_dense_tensors(grads)
+    if _use_emk_comm(flat, group) and flat.dtype == torch.float32:
+        with torch.cuda.device(flat.device):
+            _lib.check(_lib.lib().emk_comm_allreduce(None, ctypes.c_void_p(flat.data_ptr()), flat.numel(), _lib.stream_of(flat)))
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    for g, v in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(v)
+
+
 def replicate_from_host(x_host: torch.Tensor, device: torch.device, group=None) -> torch.Tensor:
     """Device copy of a host tensor that every rank holds (the replicated input of the full-set cost), built from
     one slice per rank: each rank copies rows [r n / G, (r+1) n / G) over its own PCIe link and the slices are

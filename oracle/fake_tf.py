@@ -39,6 +39,20 @@ class Tensor(torch.Tensor):
     def get_shape(self):
         return tuple(self.shape)
 
+    # tf.Tensor is an immutable value: `x *= s` REBINDS x to a new tensor (the reference scales its losses that way,
+    # loss_functions.py:283, 929); torch would modify storage in place, which autograd forbids on custom-op outputs
+    def __imul__(self, other):
+        return self * other
+
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
+    def __itruediv__(self, other):
+        return self / other
+
     def numpy(self):
         return torch.Tensor.numpy(self.detach().cpu().as_subclass(torch.Tensor))
 
@@ -279,10 +293,7 @@ def custom_gradient(f: Callable) -> Callable:
                     out, grad_fn = f(*full)
                 ctx.grad_fn = grad_fn
                 ctx.multi = isinstance(out, (tuple, list))
-                # TF tensors are immutable values; the reference scales losses with `cost *= scale`, which torch would
-                # apply IN PLACE to a view of this Function's output (forbidden) -- hand out fresh tensors instead
-                own = lambda t: t.clone() if isinstance(t, torch.Tensor) and t._is_view() else t   # noqa: E731
-                return tuple(own(o) for o in out) if ctx.multi else own(out)
+                return tuple(out) if ctx.multi else out
 
             @staticmethod
             def backward(ctx, *upstream):

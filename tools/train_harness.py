@@ -21,7 +21,8 @@ import torch
 from torch import nn
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from encodermap_b200 import ADCParameters, Parameters  # noqa: E402
+from encodermap_b200 import ADCParameters, Parameters, parallel  # noqa: E402
+from encodermap_b200.graph import graphed_train_step  # noqa: E402
 from encodermap_b200.loss_functions import cartesian_distance_loss, distance_loss  # noqa: E402
 from encodermap_b200.misc.distances import periodic_distance  # noqa: E402
 from encodermap_b200.models.layers import BackMapLayer, PairwiseDistances, PeriodicInput  # noqa: E402
@@ -37,7 +38,9 @@ def mlp(sizes, final_activation=False):
 
 
 class EncoderMapStep(nn.Module):
-    def __init__(self, input_dim: int, p: Parameters):
+    def __init__(self, input_dim: int, p: Parameters, dp_group=None):
+        """dp_group: data-parallel training -- every rank holds its rows of the global batch, the distance cost is the
+        cost of the GLOBAL batch (parallel.data_parallel_sigmoid_cost), all other terms are local means."""
         super().__init__()
         self.p = p
         self.periodic = p.periodicity < float("inf")
@@ -45,7 +48,7 @@ class EncoderMapStep(nn.Module):
         self.periodic_input = PeriodicInput(p, "input")
         self.encoder_model = mlp([d_in, *p.n_neurons])
         self.decoder_model = mlp([p.n_neurons[-1], *p.n_neurons[-2::-1], d_in])
-        self.dist_loss = distance_loss(self, p)
+        self.dist_loss = distance_loss(self, p, process_group=dp_group, data_parallel=dp_group is not None)
 
     def encoder(self, x, training=False):
         if self.periodic:
@@ -74,7 +77,7 @@ class EncoderMapStep(nn.Module):
 
 
 class ADCStep(nn.Module):
-    def __init__(self, n_atoms: int, p: ADCParameters):
+    def __init__(self, n_atoms: int, p: ADCParameters, dp_group=None):
         super().__init__()
         self.p = p
         self.n = n_atoms
@@ -85,7 +88,8 @@ class ADCStep(nn.Module):
         self.decoder_model = mlp([p.n_neurons[-1], *p.n_neurons[-2::-1], d_in])
         self.backmap = BackMapLayer(n_atoms // 2 - 1, (n_atoms - 3) // 2)
         self.pairwise = PairwiseDistances(p, "pairwise")
-        self.cart_dist_loss = cartesian_distance_loss(self, p)
+        self.cart_dist_loss = cartesian_distance_loss(self, p, process_group=dp_group, data_parallel=dp_group is not None)
+        self.dp_group = dp_group
 
     def encoder(self, inputs, training=False):
         angles, dihedrals = inputs[:2]
@@ -97,6 +101,11 @@ class ADCStep(nn.Module):
         na, nd = self.n - 2, self.n - 3
         sa, sd, ca, cd = torch.split(y, [na, nd, na, nd], dim=1)
         out_angles, out_dihedrals = torch.atan2(sa, ca), torch.atan2(sd, cd)
+        if self.dp_group is not None:
+            # BackMapLayer uses the mean bond lengths of the BATCH (layers.py:970): the global batch in data-parallel training
+            lengths = distances.mean(dim=0, keepdim=True)
+            torch.distributed.all_reduce(lengths, group=self.dp_group)
+            distances = (lengths / torch.distributed.get_world_size(self.dp_group)).expand_as(distances)
         back = self.backmap((distances, out_angles, out_dihedrals))
         inp_pair = self.pairwise(cartesians)
         out_pair = self.pairwise(back)
@@ -108,17 +117,20 @@ class ADCStep(nn.Module):
         return dihedral_loss + angle_loss + cartesian_loss + self.cart_dist_loss(inp_pair, z) + center + reg
 
 
-def time_steps(model, batch_fn, steps=20, warmup=5, graph=False):
-    """steps/s of a full training step.  graph=True captures the whole step (forward, backward, clip, Adam) in one
-    CUDA graph with static input buffers and replays it: the step is launch-bound otherwise."""
+def time_steps(model, batch_fn, steps=20, warmup=5, graph=False, grad_sync=None):
+    """steps/s of a full training step (forward, backward, [data-parallel gradient averaging], clip, Adam).  graph=True
+    captures the whole step in one CUDA graph (encodermap_b200.graph.graphed_train_step) and replays it."""
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    params = [p for p in model.parameters() if p.requires_grad]
 
     def step(batch):
         opt.zero_grad(set_to_none=True)
         loss = model.loss(*batch)
         loss.backward()
-        torch.nn.utils.clip_grad_value_(model.parameters(), 1.0)
+        if grad_sync is not None:
+            grad_sync(params)
+        torch.nn.utils.clip_grad_value_(params, 1.0)
         opt.step()
         return loss.detach()
 
@@ -134,30 +146,18 @@ def time_steps(model, batch_fn, steps=20, warmup=5, graph=False):
         ms = e0.elapsed_time(e1) / steps
         return 1e3 / ms, ms, float(losses[warmup]), float(losses[-1])
 
-    static = [b.clone() for b in batch_fn(0)]
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for it in range(3):
-            step(static)
-    torch.cuda.current_stream().wait_stream(side)
-    g = torch.cuda.CUDAGraph()
-    opt.zero_grad(set_to_none=True)
-    with torch.cuda.graph(g):
-        static_loss = step(static)
-    first = last = None
+    gstep = graphed_train_step(model, model.loss, opt, batch_fn(0), clip_value=1.0, grad_sync=grad_sync)
+    first = None
     for it in range(warmup + steps):
         if it == warmup:
             torch.cuda.synchronize()
             e0.record()
-        for dst, src in zip(static, batch_fn(it)):
-            dst.copy_(src)
-        g.replay()
+        out = gstep(*batch_fn(it))
         if it == warmup:
-            first = static_loss.clone()
+            first = out.clone()
     e1.record()
     torch.cuda.synchronize()
-    last = static_loss.clone()
+    last = gstep.outputs.clone()
     ms = e0.elapsed_time(e1) / steps
     return 1e3 / ms, ms, float(first), float(last)
 
@@ -204,3 +204,38 @@ if __name__ == "__main__":
     import json
 
     print(json.dumps(run_all(torch.device("cuda:0")), indent=1))
+
+
+def run_dp(dev, group, steps=20, batch_global=4096, weak=False):
+    """configs[1] as DATA-PARALLEL training over the ranks of `group`: every rank owns batch/G rows
+    (strong scaling: global batch fixed) or `batch_global` rows (weak scaling: per-GPU batch fixed); the distance cost is the
+    cost of the global batch (all-gather rows -> this rank's pair-tile slice -> all-reduce loss + reduce-scatter dL/dz), the
+    dense-layer gradients are averaged with one flat all-reduce.  Returns steps/s (max over ranks), eager and graph-replayed."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rows = batch_global if weak else batch_global // world
+    g = torch.Generator(device=dev).manual_seed(7)   # same data set on every rank; each rank reads its own rows
+    n_data = 4 * rows * world
+    centres = (torch.rand(16, 1024, device=dev, generator=g) * 2 - 1) * math.pi
+    data = centres[torch.randint(0, 16, (n_data,), device=dev, generator=g)] + 0.3 * torch.randn(n_data, 1024, device=dev, generator=g)
+    data = torch.remainder(data + math.pi, 2 * math.pi) - math.pi
+
+    def batch_fn(it):
+        start = ((it % 4) * world + rank) * rows
+        return (data[start:start + rows],)
+
+    res = {"rows_per_gpu": rows, "global_batch": rows * world, "scaling": "weak" if weak else "strong"}
+    for mode in ("eager", "cuda_graph"):
+        torch.manual_seed(0)   # identical initial weights on every rank
+        model = EncoderMapStep(1024, Parameters(), dp_group=group).to(dev)
+        try:
+            sps, ms, l0, l1 = time_steps(model, batch_fn, steps, graph=(mode == "cuda_graph"),
+                                         grad_sync=lambda params: parallel.average_gradients(params, group))
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            res[mode] = {"steps_per_s": 1e3 / t.item(), "ms_per_step": t.item(), "loss_first": l0, "loss_last": l1}
+        except Exception as e:  # noqa: BLE001 - reported, the other mode still runs
+            res[mode] = {"error": repr(e)[:300]}
+            torch.cuda.synchronize()
+    return res
