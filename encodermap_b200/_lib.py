@@ -45,6 +45,8 @@ SIGNATURES = {
     "emk_last_error": ([], C.c_char_p),
     "emk_build_info": ([], C.c_char_p),
     "emk_probe_fp32": ([C.POINTER(C.c_double)], C.c_int),
+    "emk_set_option": ([C.c_char_p, i64], C.c_int),
+    "emk_get_option": ([C.c_char_p, c_i64p], C.c_int),
     "emk_triu_pair_count": ([i64], i64),
     "emk_triu_pair_indices": ([i64, c_i32p, c_i32p], C.c_int),
     "emk_backmap_split_counts": ([i64, c_i64p], C.c_int),
@@ -179,6 +181,16 @@ def sig_array(sig) -> "ctypes.Array":
     if len(vals) != 6:
         raise ValueError(f"dist_sig_parameters must have 6 entries, got {len(vals)}")
     return (ctypes.c_float * 6)(*vals)
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().emk_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = ctypes.c_int64()
+    check(lib().emk_get_option(name.encode(), ctypes.byref(v)))
+    return int(v.value)
 
 
 # ---- host-only helpers (no GPU needed) ---------------------------------------------------------------------

@@ -19,6 +19,8 @@
 // planar chain), so each gradient is <axis, torque> or <direction, force> of that end's wrench, carried in
 // float32 about a pivot that moves with the walk (see "backward, version 3").
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "emk_common.cuh"
@@ -554,6 +556,308 @@ __global__ void __launch_bounds__(FWD5_THREADS, 2) backmap_fwd5_kernel(const flo
     store_row(dst, T, out_floats, t, 64);
     group_barrier(g);   // the next frame's staging overwrites T
   }
+}
+
+// ====================================================================================================
+// BackMapLayer forward, version 6 (large batches): one LANE per (frame, side) -- the chain is walked sequentially in
+// GLOBAL coordinates, 32 frames per warp, and the parallelism comes from the frames instead of from cutting one chain
+// into 32 chunks.  What disappears against version 5: the SE(3) scan (21 % of the FP64 work, 26 % of the L1 wavefronts),
+// pass 2 and its shared-memory round trip, the chunk-local / hi-lo bookkeeping, every barrier inside a frame.
+//   * work item = (tile of 32 consecutive frames, side); the two warps of a tile are neighbours in the CTA and split the
+//     planar prologue: the anchor frame needs the SE(2) product of the bonds LEFT of the middle before either side can
+//     start in global coordinates; each warp multiplies half of those bonds (angles only: 10 FP64 per bond), they swap
+//     the two partial products through shared memory (one named barrier per tile) and compose them.
+//   * inputs: rows of `dihedrals` / `angles` are streamed through per-warp shared-memory tiles of 8 steps x 32 frames with
+//     4-byte cp.async (a warp instruction moves four 32-byte row segments; tile row pitch 36 words makes both the scatter
+//     and the per-step read -- lane = frame -- conflict free), double buffered: the tile of the next 8 steps is in flight
+//     while the current one is consumed.  Bond lengths (shared by all frames) sit in shared memory as float64.
+//   * outputs: each lane keeps the float32 positions of 4 atoms in registers, writes them as 3 STS.128 into its row of a
+//     per-warp group buffer (8 atoms = 96 bytes per frame; row pitch 112 bytes: conflict free), and every 8 atoms each
+//     lane hands its row to the bulk-copy engine (cp.async.bulk shared -> global, 96 bytes, 16-byte aligned because
+//     n % 4 == 0): the stores cost one instruction per 8 atoms and no LSU wavefronts.  Atoms outside whole 8-groups of a
+//     side (<= 14 per frame) are stored directly.
+//   * sin/cos: 64-entry float64 table, replicated 8x so that lane l reads replica l & 7: a warp-wide 16-byte lookup with
+//     random indices is 4 wavefronts instead of 8.2; float32 argument reduction (exact Cody-Waite steps) and degree-5/6
+//     corrections run packed (FFMA2) for the two angles of a step.  4.7e-9 absolute error per value.
+// Used when the batch is large enough to fill the machine with (frame, side) lanes; version 5 stays the path for small
+// batches, n % 4 != 0, per-frame bond lengths and very long chains.
+// ====================================================================================================
+constexpr int F6_WARPS = 24;                       // one persistent CTA per SM
+constexpr int F6_THREADS = 32 * F6_WARPS;
+constexpr int F6_TILE = 8;                         // steps per input tile = atoms per output group
+constexpr int F6_IN_PITCH = 36;                    // words per tile row
+constexpr int F6_IN_TILE = F6_TILE * F6_IN_PITCH;  // words per (array, buffer)
+constexpr int F6_OUT_PITCH = 28;                   // words per frame row of the output group (24 used)
+constexpr int F6_OUT_TILE = 32 * F6_OUT_PITCH;
+constexpr int F6_WARP_WORDS = 4 * F6_IN_TILE + F6_OUT_TILE;   // D/A x two buffers + output group
+constexpr int SC6 = 64;                            // table entries (step 2 pi / 64), 8 replicas
+
+// table sin/cos of two angles (|x| < SC_FAST_LIMIT): tabL already points at this lane's replica (entry stride 8)
+__device__ __forceinline__ void sincos_tab64_x2(float xa, float xb, const double2* tabL, double* sa, double* ca, double* sb, double* cb) {
+  const float2 x = make_float2(xa, xb);
+  const float2 km = __ffma2_rn(x, make_float2(10.185916357881302f, 10.185916357881302f), make_float2(12582912.f, 12582912.f));
+  const float2 kf = __fadd2_rn(km, make_float2(-12582912.f, -12582912.f));
+  float2 r = __ffma2_rn(kf, make_float2(-0.09814453125f, -0.09814453125f), x);
+  r = __ffma2_rn(kf, make_float2(-3.0234456062316895e-05f, -3.0234456062316895e-05f), r);
+  r = __ffma2_rn(kf, make_float2(-4.7186188290027076e-09f, -4.7186188290027076e-09f), r);
+  const float2 r2 = __fmul2_rn(r, r);
+  const float2 sp = __ffma2_rn(r2, make_float2(8.3333333e-03f, 8.3333333e-03f), make_float2(-0.16666667f, -0.16666667f));
+  const float2 sr = __ffma2_rn(__fmul2_rn(r, r2), sp, r);                                                      // sin r
+  float2 cp = __ffma2_rn(r2, make_float2(-1.3888889e-03f, -1.3888889e-03f), make_float2(0.041666668f, 0.041666668f));
+  cp = __ffma2_rn(r2, cp, make_float2(-0.5f, -0.5f));
+  const float2 cm = __fmul2_rn(r2, cp);                                                                        // cos r - 1
+  const double2 ta = tabL[(__float_as_int(km.x) & (SC6 - 1)) << 3];
+  const double2 tb = tabL[(__float_as_int(km.y) & (SC6 - 1)) << 3];
+  *sa = fma(ta.x, (double)cm.x, fma(ta.y, (double)sr.x, ta.x));
+  *ca = fma(ta.y, (double)cm.x, fma(-ta.x, (double)sr.x, ta.y));
+  *sb = fma(tb.x, (double)cm.y, fma(tb.y, (double)sr.y, tb.x));
+  *cb = fma(tb.y, (double)cm.y, fma(-tb.x, (double)sr.y, tb.y));
+}
+// out of line on purpose: the step body is instantiated ~20 times and must stay inside the instruction cache
+static __device__ __noinline__ double2 sincos_slow(float x) {   // by value: pointer outputs would pin the caller's results to local memory
+  double s, c;
+  sincos_d((double)x, &s, &c);
+  return make_double2(s, c);
+}
+__device__ __forceinline__ void sincos_f6_x2(float xa, float xb, const double2* tabL, double* sa, double* ca, double* sb, double* cb) {
+  if (fmaxf(fabsf(xa), fabsf(xb)) < SC_FAST_LIMIT) {
+    sincos_tab64_x2(xa, xb, tabL, sa, ca, sb, cb);
+  } else {   // beyond the exact range of the float32 reduction (never produced by the models), or NaN
+    const double2 a = sincos_slow(xa), bb = sincos_slow(xb);
+    *sa = a.x; *ca = a.y; *sb = bb.x; *cb = bb.y;
+  }
+}
+
+// stage elements [e0, e0 + 8) of 32 consecutive rows (frames frame0 ..) into a tile: lane -> (element q = lane & 7,
+// frame lane >> 3 + 4 j).  Rows beyond the batch are skipped (their tile columns keep the zeros written at start-up);
+// elements outside [0, len) are clamped to the row (read, never used).
+__device__ __forceinline__ void f6_issue(uint32_t tile, const float* __restrict__ base, int64_t pitch, int64_t frame0, int64_t b,
+                                         int e0, int len, int lane) {
+  const int q = lane & 7, fr0 = lane >> 3;
+  const int e = min(max(e0 + q, 0), len - 1);
+  const float* src = base + (frame0 + fr0) * pitch + e;
+  const int64_t hop = 4 * pitch;
+  uint32_t dst = tile + 4u * (uint32_t)(q * F6_IN_PITCH + fr0);
+  int64_t fr = frame0 + fr0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (fr < b) cp_async4_s(dst, src);
+    src += hop;
+    dst += 16u;
+    fr += 4;
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store96(float* gdst, const float* ssrc) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one NeRF step of a lane in global coordinates; returns the float32 position of the atom it placed
+__device__ __forceinline__ void f6_step(float fd, float fa, double L, const double2* tabL, Se3& f, float& ox, float& oy, float& oz) {
+  double sw, cw, sg, cg;
+  sincos_f6_x2(fd, fa, tabL, &sw, &cw, &sg, &cg);
+  nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
+  ox = (float)f.p[0];
+  oy = (float)f.p[1];
+  oz = (float)f.p[2];
+}
+
+// the chain of one side: atoms k = s-2 .. 0 (SIDE 0: inputs d[k], a[k], L[k]) or s+2 .. n-1 (SIDE 1: d[k-3], a[k-2], L[k-1]).
+// tD0 / tA0: this warp's dihedral / angle tiles (buffer 1 follows buffer 0 at + F6_IN_TILE words).
+template <int SIDE>
+__device__ __forceinline__ void f6_chain(Se3& f, const float* __restrict__ angles, const float* __restrict__ dihedrals, const double* L64,
+                                         const double2* tabL, float* tD0, float* tA0, float* myrow, float* __restrict__ dst, int64_t frame0,
+                                         int64_t b, int n, bool valid, int lane) {
+  const int s = n / 2, nd = n - 3, na = n - 2;
+  constexpr int dir = SIDE ? 1 : -1;
+  constexpr int sh_d = SIDE ? -3 : 0, sh_a = SIDE ? -2 : 0, sh_l = SIDE ? -1 : 0;
+  const int k_first = SIDE ? s + 2 : s - 2, k_last = SIDE ? n - 1 : 0;     // inclusive
+  if (SIDE ? (k_first > k_last) : (k_first < k_last)) return;
+  const int g_first = k_first >> 3, g_last = k_last >> 3;
+  const uint32_t sD0 = (uint32_t)__cvta_generic_to_shared(tD0), sA0 = (uint32_t)__cvta_generic_to_shared(tA0);
+  int buf = 0;
+  f6_issue(sD0, dihedrals, nd, frame0, b, 8 * g_first + sh_d, nd, lane);
+  f6_issue(sA0, angles, na, frame0, b, 8 * g_first + sh_a, na, lane);
+  cp_async_commit();
+  for (int g = g_first; g != g_last + dir; g += dir) {
+    const int gn = g + dir;
+    if (gn != g_last + dir) {
+      f6_issue(sD0 + 4u * F6_IN_TILE * (buf ^ 1), dihedrals, nd, frame0, b, 8 * gn + sh_d, nd, lane);
+      f6_issue(sA0 + 4u * F6_IN_TILE * (buf ^ 1), angles, na, frame0, b, 8 * gn + sh_a, na, lane);
+    }
+    cp_async_commit();
+    cp_async_wait1();
+    __syncwarp();
+    const float* td = tD0 + buf * F6_IN_TILE + lane;
+    const float* ta = tA0 + buf * F6_IN_TILE + lane;
+    // atoms of this group that belong to the side, in walking order
+    const int ka = SIDE ? max(8 * g, k_first) : min(8 * g + 7, k_first);
+    const int kb = SIDE ? min(8 * g + 7, k_last) : max(8 * g, k_last);    // inclusive
+    const bool whole = SIDE ? (ka == 8 * g && kb == 8 * g + 7) : (ka == 8 * g + 7 && kb == 8 * g);
+    if (whole) {
+      bulk_wait_read0();          // the previous group's rows have left the buffer
+      float4* row4 = reinterpret_cast<float4*>(myrow);
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        float pend[12];           // atoms 4 h .. 4 h + 3 of the group in memory order (h = half on the right, 1 - half on the left)
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int slot = SIDE ? 4 * half + u : 7 - (4 * half + u);
+          const int pu = SIDE ? u : 3 - u;
+          f6_step(td[slot * F6_IN_PITCH], ta[slot * F6_IN_PITCH], L64[8 * g + slot + sh_l], tabL, f, pend[3 * pu], pend[3 * pu + 1],
+                  pend[3 * pu + 2]);
+        }
+        const int q4 = SIDE ? 3 * half : 3 * (1 - half);
+        row4[q4] = make_float4(pend[0], pend[1], pend[2], pend[3]);
+        row4[q4 + 1] = make_float4(pend[4], pend[5], pend[6], pend[7]);
+        row4[q4 + 2] = make_float4(pend[8], pend[9], pend[10], pend[11]);
+      }
+      fence_async_smem();
+      if (valid) bulk_store96(dst + 24 * g, myrow);
+      bulk_commit();
+    } else {
+      for (int k = ka; k != kb + dir; k += dir) {
+        const int slot = k & 7;
+        float ox, oy, oz;
+        f6_step(td[slot * F6_IN_PITCH], ta[slot * F6_IN_PITCH], L64[k + sh_l], tabL, f, ox, oy, oz);
+        if (valid) { dst[3 * k] = ox; dst[3 * k + 1] = oy; dst[3 * k + 2] = oz; }
+      }
+    }
+    __syncwarp();
+    buf ^= 1;
+  }
+  cp_async_wait0();
+}
+
+__global__ void __launch_bounds__(F6_THREADS, 1) backmap_fwd6_kernel(const float* __restrict__ lengths, const float* __restrict__ angles,
+                                                                     const float* __restrict__ dihedrals, int64_t b, int n,
+                                                                     float* __restrict__ xyz, const double2* __restrict__ tab) {
+  extern __shared__ __align__(16) float smem[];
+  double2* tabS = reinterpret_cast<double2*>(smem);                        // [SC6][8]
+  double* L64 = reinterpret_cast<double*>(smem + SC6 * 8 * 4);             // [n - 1], padded to an even count
+  const int lwords = 2 * ((n - 1 + 1) & ~1);
+  float* warp_base = smem + SC6 * 8 * 4 + lwords;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int side = warp & 1, pair = warp >> 1;
+  for (int i = tid; i < SC6 * 8; i += F6_THREADS) tabS[i] = __ldg(tab + (i >> 3) * (SC_TABLE / SC6));
+  for (int i = tid; i < n - 1; i += F6_THREADS) L64[i] = (double)__ldg(lengths + i);
+  float* wmem = warp_base + (size_t)warp * F6_WARP_WORDS;
+  for (int i = lane; i < F6_WARP_WORDS; i += 32) wmem[i] = 0.f;
+  __syncthreads();
+
+  const double2* tabL = tabS + (lane & 7);
+  float* tD0 = wmem;                                                       // dihedral tiles: buffer 1 at + F6_IN_TILE
+  float* tA0 = wmem + 2 * F6_IN_TILE;                                      // angle tiles
+  float* outT = wmem + 4 * F6_IN_TILE;                                     // 16-byte aligned: all pieces are multiples of 4 words
+  float* partner_out = warp_base + (size_t)(warp ^ 1) * F6_WARP_WORDS + 4 * F6_IN_TILE;
+  const uint32_t sA0 = (uint32_t)__cvta_generic_to_shared(tA0);
+  float* myrow = outT + lane * F6_OUT_PITCH;
+
+  const int s = n / 2;
+  const int na = n - 2;
+  const int64_t n_tiles = (b + 31) >> 5;
+  const int pairs_per_cta = F6_WARPS / 2;
+
+  for (int64_t tile = (int64_t)blockIdx.x * pairs_per_cta + pair; tile < n_tiles; tile += (int64_t)gridDim.x * pairs_per_cta) {
+    const int64_t frame0 = tile << 5;
+    const int64_t frame = frame0 + lane;
+    const bool valid = frame < b;
+    float* dst = xyz + (valid ? frame : frame0) * (int64_t)(3 * n);
+
+    // ---- planar prologue: SE(2) product of bonds 0 .. s-2, split between the two warps of the pair ---------------------
+    // right warp: bonds [0, h), left warp: bonds [h, s-1); h is a multiple of 8 (tile aligned)
+    const int h = ((s - 1) / 2) & ~7;
+    const int k_lo = side ? 0 : h, k_hi = side ? h : s - 1;
+    Se2 pl{1.0, 0.0, 0.0, 0.0};
+    {
+      int buf = 0;
+      if (k_lo < k_hi) f6_issue(sA0, angles, na, frame0, b, k_lo, na, lane);
+      cp_async_commit();
+      for (int k0 = k_lo; k0 < k_hi; k0 += F6_TILE) {
+        if (k0 + F6_TILE < k_hi) f6_issue(sA0 + 4u * F6_IN_TILE * (buf ^ 1), angles, na, frame0, b, k0 + F6_TILE, na, lane);
+        cp_async_commit();
+        cp_async_wait1();
+        __syncwarp();
+        const float* t = tA0 + buf * F6_IN_TILE + lane;
+        const int cnt = min(F6_TILE, k_hi - k0);
+        int q = 0;
+        for (; q + 1 < cnt; q += 2) {   // two bonds per iteration: their sin/cos are computed as one packed pair
+          const int k = k0 + q;
+          double s0, c0, s1, c1;
+          sincos_f6_x2(t[q * F6_IN_PITCH], t[(q + 1) * F6_IN_PITCH], tabL, &s0, &c0, &s1, &c1);
+          const double La = L64[k], Lb = L64[k + 1];
+          pl.x = fma(La, pl.c, pl.x);
+          pl.y = fma(La, pl.s, pl.y);
+          {   // turn by -(-1)^k (pi - theta_k): cos = -cos(theta), sin = -(-1)^k sin(theta)
+            const double cw = -c0, sw = (k & 1) ? s0 : -s0;
+            const double c2 = pl.c * cw - pl.s * sw, s2 = pl.c * sw + pl.s * cw;
+            pl.c = c2; pl.s = s2;
+          }
+          pl.x = fma(Lb, pl.c, pl.x);
+          pl.y = fma(Lb, pl.s, pl.y);
+          {
+            const double cw = -c1, sw = (k & 1) ? -s1 : s1;   // bond k + 1 has the opposite parity
+            const double c2 = pl.c * cw - pl.s * sw, s2 = pl.c * sw + pl.s * cw;
+            pl.c = c2; pl.s = s2;
+          }
+        }
+        if (q < cnt) planar_step(pl, L64[k0 + q], true, t[q * F6_IN_PITCH], k0 + q);
+        __syncwarp();
+        buf ^= 1;
+      }
+      cp_async_wait0();
+    }
+    // swap the partial products: mine goes into my output buffer, the partner reads it from there
+    {
+      double* x = reinterpret_cast<double*>(outT) + 4 * lane;
+      x[0] = pl.c; x[1] = pl.s; x[2] = pl.x; x[3] = pl.y;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+      const double* y = reinterpret_cast<const double*>(partner_out) + 4 * lane;
+      const Se2 other{y[0], y[1], y[2], y[3]};
+      pl = side ? se2_mul(pl, other) : se2_mul(other, pl);   // bonds [0, h) first, then [h, s-1)
+      asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");   // both have read: the buffers may be reused
+    }
+
+    // ---- anchor: the three middle atoms at their planar positions, anchor frame of this side ---------------------------
+    Se3 f;
+    {
+      const double dm_c = pl.c, dm_s = pl.s, am_x = pl.x, am_y = pl.y;      // direction of bond s-1, position of atom s-1
+      const float th_mid = valid ? __ldg(angles + frame * na + (s - 1)) : 2.f;
+      Se2 mid = pl;
+      planar_step(mid, L64[s - 1], true, th_mid, s - 1);
+      const double a0_x = mid.x, a0_y = mid.y, dp_c = mid.c, dp_s = mid.s;
+      const double ap_x = fma(L64[s], dp_c, a0_x), ap_y = fma(L64[s], dp_s, a0_y);
+      const double zs = (dm_c * dp_s - dm_s * dp_c) >= 0.0 ? 1.0 : -1.0;
+      const double xx = side == 0 ? -dm_c : dp_c, xy = side == 0 ? -dm_s : dp_s, zz = side == 0 ? -zs : zs;
+      f.r[0] = xx; f.r[1] = -zz * xy; f.r[2] = 0.0;
+      f.r[3] = xy; f.r[4] = zz * xx;  f.r[5] = 0.0;
+      f.r[6] = 0.0; f.r[7] = 0.0;     f.r[8] = zz;
+      f.p[0] = side == 0 ? am_x : ap_x; f.p[1] = side == 0 ? am_y : ap_y; f.p[2] = 0.0;
+      if (valid) {
+        if (side == 0) {
+          float* o = dst + 3 * (s - 1);
+          o[0] = (float)am_x; o[1] = (float)am_y; o[2] = 0.f;
+          o[3] = (float)a0_x; o[4] = (float)a0_y; o[5] = 0.f;
+        } else {
+          float* o = dst + 3 * (s + 1);
+          o[0] = (float)ap_x; o[1] = (float)ap_y; o[2] = 0.f;
+        }
+      }
+    }
+
+    // ---- the chain of this side (side is warp uniform: two instantiations keep every register index static) ----------
+    if (side) f6_chain<1>(f, angles, dihedrals, L64, tabL, tD0, tA0, myrow, dst, frame0, b, n, valid, lane);
+    else f6_chain<0>(f, angles, dihedrals, L64, tabL, tD0, tA0, myrow, dst, frame0, b, n, valid, lane);
+    bulk_wait_read0();   // the output buffer doubles as the exchange buffer of the next tile
+  }
+  bulk_wait0();
 }
 
 // ====================================================================================================
@@ -1187,6 +1491,30 @@ static int get_sincos_table(const double2** out) {
   return EMK_OK;
 }
 
+// version 6 (lane per frame and side): shared bond lengths, n % 4 == 0 (16-byte aligned 8-atom output groups), 16-byte aligned
+// output, bond lengths + per-warp tiles within the shared memory of one SM, and a batch that fills the machine
+static size_t fwd6_smem_bytes(int64_t n) {
+  return (size_t)(SC6 * 8 * 4 + 2 * ((n - 1 + 1) & ~(int64_t)1) + F6_WARPS * F6_WARP_WORDS) * sizeof(float);
+}
+// batch size from which the lane-per-frame kernel takes over (emk_set_option("backmap_fwd6_min_batch", v); 0 = whenever
+// eligible, negative = never).  Default from EMK_BACKMAP_FWD6_MIN_BATCH or the measured cross-over.
+static std::atomic<int64_t> g_fwd6_min_batch{[] {
+  const char* e = getenv("EMK_BACKMAP_FWD6_MIN_BATCH");
+  return e ? (int64_t)atoll(e) : (int64_t)4096;
+}()};
+int64_t fwd6_min_batch() { return g_fwd6_min_batch.load(); }
+void set_fwd6_min_batch(int64_t v) { g_fwd6_min_batch.store(v); }
+static int backmap_fwd6_launch(const float* lengths, const float* angles, const float* dihedrals, int64_t b, int64_t n, float* xyz,
+                               const double2* tab, cudaStream_t st) {
+  const size_t smem = fwd6_smem_bytes(n);
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(backmap_fwd6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int64_t tiles = (b + 31) / 32;
+  const int64_t blocks = std::min<int64_t>((tiles + F6_WARPS / 2 - 1) / (F6_WARPS / 2), (int64_t)sm_count());
+  backmap_fwd6_kernel<<<(unsigned)blocks, F6_THREADS, smem, st>>>(lengths, angles, dihedrals, b, (int)n, xyz, tab);
+  return launch_status("backmap_fwd6_kernel");
+}
+
 int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angles, const float* dihedrals, int64_t b,
                        int64_t n, float* xyz, cudaStream_t st) {
   EMK_REQUIRE(lengths && angles && dihedrals && xyz, EMK_E_NULL, "emk_backmap: NULL pointer argument");
@@ -1196,6 +1524,9 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
   const double2* tab;
   int rc = get_sincos_table(&tab);
   if (rc) return rc;
+  if (lstride == 0 && n % 4 == 0 && n >= 16 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0 && fwd6_smem_bytes(n) <= 227 * 1024 &&
+      fwd6_min_batch() >= 0 && b >= fwd6_min_batch())
+    return backmap_fwd6_launch(lengths, angles, dihedrals, b, n, xyz, tab, st);
   const size_t per_group = ((3 * (size_t)n + 7) & ~(size_t)3) * sizeof(float);
   const size_t budget = 224 * 1024 - SC_SMALL * sizeof(double2);
   const int groups = (int)std::min<size_t>(FWD5_GROUPS, budget / per_group);   // frames in flight per CTA

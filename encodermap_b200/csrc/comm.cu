@@ -8,7 +8,7 @@
 //
 // NCCL is bound at run time with dlopen (the process that calls in here -- torch -- has libnccl.so.2 loaded already), so
 // libemk.so keeps linking against libc/libm only and single-GPU users never touch NCCL.  Types and enum values below are
-// the stable NCCL 2.x ABI (nccl.h: ncclUniqueId is 128 bytes, ncclFloat32 = 7, ncclFloat64 = 8, ncclUint8 = 1, ncclSum = 0).
+// the stable NCCL 2.x ABI (nccl.h: ncclUniqueId is 128 bytes, ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0).
 #include <dlfcn.h>
 
 #include <cstdlib>
@@ -22,7 +22,7 @@ namespace emk {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-constexpr int kNcclUint8 = 1, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
 
 struct NcclApi {
   void* handle = nullptr;

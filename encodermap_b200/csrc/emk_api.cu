@@ -98,6 +98,8 @@ int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int6
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
 int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
 int fp32_probe_device(double*);
+int64_t fwd6_min_batch();
+void set_fwd6_min_batch(int64_t);
 int d2c_chain_bwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int pairwise_periodic_bwd_device(const float*, int64_t, int64_t, double, const float*, const float*, float*, cudaStream_t);
 int chain_in_plane_device(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
@@ -194,6 +196,23 @@ const char* emk_build_info(void) {
 }
 
 int emk_probe_fp32(double* lane_instr_per_s) { return fp32_probe_device(lane_instr_per_s); }
+
+int emk_set_option(const char* name, int64_t value) {
+  EMK_REQUIRE(name, EMK_E_NULL, "emk_set_option: NULL name");
+  if (strcmp(name, "backmap_fwd6_min_batch") == 0) {
+    set_fwd6_min_batch(value);
+    return EMK_OK;
+  }
+  return fail(EMK_E_ARG, "emk_set_option: unknown option '%s'", name);
+}
+int emk_get_option(const char* name, int64_t* value) {
+  EMK_REQUIRE(name && value, EMK_E_NULL, "emk_get_option: NULL argument");
+  if (strcmp(name, "backmap_fwd6_min_batch") == 0) {
+    *value = fwd6_min_batch();
+    return EMK_OK;
+  }
+  return fail(EMK_E_ARG, "emk_get_option: unknown option '%s'", name);
+}
 
 // ---- host-only index construction --------------------------------------------------------------------------
 int64_t emk_triu_pair_count(int64_t n) { return n < 2 ? 0 : n * (n - 1) / 2; }

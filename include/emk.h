@@ -58,6 +58,11 @@ EMK_API const char* emk_build_info(void);
 /* Measurement aid (bench.py): FP32 FMA lane-instructions per second this device sustains on register-only FFMA
  * chains -- the measured denominator of the pair-tile kernel's FP32-issue roofline.  Synchronises the device. */
 EMK_API int emk_probe_fp32(double* lane_instr_per_s);
+/* Process-wide tuning knobs (kernel selection thresholds; results do not depend on them beyond float32 rounding):
+ *   "backmap_fwd6_min_batch"  batch size from which emk_backmap uses the lane-per-frame kernel (default 4096; 0 = whenever
+ *                             the shape is eligible, negative = never) */
+EMK_API int emk_set_option(const char* name, int64_t value);
+EMK_API int emk_get_option(const char* name, int64_t* value);
 
 /* ------------------------------------------------------------------------------------------
  * Host-only index construction (integer work: bit-exact contracts; no GPU needed)

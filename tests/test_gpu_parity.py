@@ -980,3 +980,59 @@ def test_parallel_cost_on_nccl(em, nccl_world1, own_comm):
         dp.backward()
         np.testing.assert_allclose(dp.item(), lref.item(), rtol=LOSS_RTOL)
         assert relnorm(z.grad.cpu().numpy(), gref.numpy()) < GRAD_RTOL    # world = 1: both reductions coincide
+
+
+# ---------------------------------------------------------------------------------------------------
+# back-mapping forward, lane-per-frame kernel (large batches): same numbers as the chunk-scan kernel and the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,b", [(16, 70), (20, 33), (24, 64), (300, 200), (1500, 45), (2000, 40)])
+def test_backmap_lane_per_frame_kernel(em, n, b):
+    from encodermap_b200 import _lib
+    from encodermap_b200.models.layers import BackMapLayer
+
+    rng = np.random.default_rng(n + b)
+    dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+    ang[3, 5] = 60.0            # beyond the table path's range: the float64 polynomial path of that lane
+    dih[b - 1, n - 4] = -75.0
+    layer = BackMapLayer(n // 2 - 1, (n - 3) // 2)
+    old = _lib.get_option("backmap_fwd6_min_batch")
+    try:
+        _lib.set_option("backmap_fwd6_min_batch", 0)
+        got6 = layer((cu(dist), cu(ang), cu(dih))).cpu().numpy()
+        _lib.set_option("backmap_fwd6_min_batch", -1)
+        got5 = layer((cu(dist), cu(ang), cu(dih))).cpu().numpy()
+    finally:
+        _lib.set_option("backmap_fwd6_min_batch", old)
+    ref = O.back_map_layer(torch.from_numpy(dist).double(), torch.from_numpy(ang).double(), torch.from_numpy(dih).double()).numpy()
+    assert np.abs(got6 - ref).max() < COORD_ATOL
+    assert np.abs(got5 - ref).max() < COORD_ATOL
+    assert np.abs(got6 - got5).max() < 2e-5
+
+
+def test_backmap_lane_per_frame_nan_and_partial_tiles(em):
+    """NaN / Inf inputs stay inside their frame; a batch that is not a multiple of 32 frames leaves no trace outside."""
+    from encodermap_b200 import _lib, _ops
+
+    rng = np.random.default_rng(3)
+    n, b = 64, 75
+    lengths = rng.uniform(0.13, 0.15, size=(1, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
+    dih[7, 20] = np.nan
+    ang[40, 50] = np.inf
+    old = _lib.get_option("backmap_fwd6_min_batch")
+    try:
+        _lib.set_option("backmap_fwd6_min_batch", 0)
+        buf = torch.full((b + 1, n, 3), 123.0, device="cuda")
+        out = _ops.backmap_raw(cu(lengths), cu(ang), cu(dih))
+        buf[:b] = out
+        got = out.cpu().numpy()
+    finally:
+        _lib.set_option("backmap_fwd6_min_batch", old)
+    bad = ~np.isfinite(got).all(axis=(1, 2))
+    assert bad[7] and bad[40] and bad.sum() == 2
+    ok = ~bad
+    ref = O.back_map_layer(torch.from_numpy(np.repeat(lengths, b, 0)).double(), torch.from_numpy(ang).double(), torch.from_numpy(dih).double()).numpy()
+    assert np.abs(got[ok] - ref[ok]).max() < COORD_ATOL
