@@ -23,6 +23,8 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <cuda.h>
+
 #include "emk_common.cuh"
 
 namespace emk {
@@ -582,36 +584,40 @@ __global__ void __launch_bounds__(FWD5_THREADS, 2) backmap_fwd5_kernel(const flo
 // Used when the batch is large enough to fill the machine with (frame, side) lanes; version 5 stays the path for small
 // batches, n % 4 != 0, per-frame bond lengths and very long chains.
 // ====================================================================================================
-constexpr int F6_WARPS = 24;                       // one persistent CTA per SM
-constexpr int F6_THREADS = 32 * F6_WARPS;
+// one persistent CTA per SM with 8 .. 20 warps (4 .. 10 tile pairs): the per-SM rate is the same from 12 to 20 warps (it is set
+// by issue slots, FP64 instructions counting twice), so the count is chosen per launch to make the tile count come out as
+// whole waves; emk_set_option("backmap_fwd6_warps", w) forces one (0 = automatic)
 constexpr int F6_TILE = 8;                         // steps per input tile = atoms per output group
-constexpr int F6_IN_PITCH = 36;                    // words per tile row
-constexpr int F6_IN_TILE = F6_TILE * F6_IN_PITCH;  // words per (array, buffer)
-constexpr int F6_OUT_PITCH = 28;                   // words per frame row of the output group (24 used)
-constexpr int F6_OUT_TILE = 32 * F6_OUT_PITCH;
-constexpr int F6_WARP_WORDS = 4 * F6_IN_TILE + F6_OUT_TILE;   // D/A x two buffers + output group
+constexpr int F6_IN_TILE = 32 * F6_TILE;           // words per (array, buffer): [frame][8 elements], dense
+constexpr int F6_OUT_TILE = 32 * 24;               // output group [frame][8 atoms x 3], dense: the box of the TMA tensor store
+constexpr int F6_WARP_WORDS = 4 * F6_IN_TILE + F6_OUT_TILE;   // D/A x two buffers + output group = 7 KB
 constexpr int SC6 = 64;                            // table entries (step 2 pi / 64), 8 replicas
 
-// table sin/cos of two angles (|x| < SC_FAST_LIMIT): tabL already points at this lane's replica (entry stride 8)
-__device__ __forceinline__ void sincos_tab64_x2(float xa, float xb, const double2* tabL, double* sa, double* ca, double* sb, double* cb) {
-  const float2 x = make_float2(xa, xb);
-  const float2 km = __ffma2_rn(x, make_float2(10.185916357881302f, 10.185916357881302f), make_float2(12582912.f, 12582912.f));
-  const float2 kf = __fadd2_rn(km, make_float2(-12582912.f, -12582912.f));
-  float2 r = __ffma2_rn(kf, make_float2(-0.09814453125f, -0.09814453125f), x);
-  r = __ffma2_rn(kf, make_float2(-3.0234456062316895e-05f, -3.0234456062316895e-05f), r);
-  r = __ffma2_rn(kf, make_float2(-4.7186188290027076e-09f, -4.7186188290027076e-09f), r);
-  const float2 r2 = __fmul2_rn(r, r);
-  const float2 sp = __ffma2_rn(r2, make_float2(8.3333333e-03f, 8.3333333e-03f), make_float2(-0.16666667f, -0.16666667f));
-  const float2 sr = __ffma2_rn(__fmul2_rn(r, r2), sp, r);                                                      // sin r
-  float2 cp = __ffma2_rn(r2, make_float2(-1.3888889e-03f, -1.3888889e-03f), make_float2(0.041666668f, 0.041666668f));
-  cp = __ffma2_rn(r2, cp, make_float2(-0.5f, -0.5f));
-  const float2 cm = __fmul2_rn(r2, cp);                                                                        // cos r - 1
-  const double2 ta = tabL[(__float_as_int(km.x) & (SC6 - 1)) << 3];
-  const double2 tb = tabL[(__float_as_int(km.y) & (SC6 - 1)) << 3];
-  *sa = fma(ta.x, (double)cm.x, fma(ta.y, (double)sr.x, ta.x));
-  *ca = fma(ta.y, (double)cm.x, fma(-ta.x, (double)sr.x, ta.y));
-  *sb = fma(tb.x, (double)cm.y, fma(tb.y, (double)sr.y, tb.x));
-  *cb = fma(tb.y, (double)cm.y, fma(-tb.x, (double)sr.y, tb.y));
+// The float32 Cody-Waite reduction below is exact while k * C1 fits 24 bits: C1 = 2 pi / 64 rounded to 11 bits, |k| < 2^13,
+// i.e. |x| < 804 rad.  Larger finite angles (absurd, but legal for the reference) take the float64 path; NaN / Inf pass
+// through the table path as NaN on their own.
+constexpr float SC6_LIMIT = 800.f;
+
+// table sin/cos of one angle (|x| < SC6_LIMIT): tabB = this lane's replica as a byte address (entry stride 128 bytes).
+// Scalar FFMA with literal constants: the packed FFMA2 form needs every constant in a register PAIR, which at 80 registers
+// were re-materialised with two moves per use.
+__device__ __forceinline__ void sincos_tab64(float x, uint32_t tabB, double* sn, double* cs) {
+  const float km = fmaf(x, 10.185916357881302f, 12582912.f);
+  const float kf = km - 12582912.f;
+  float r = fmaf(kf, -0.09814453125f, x);
+  r = fmaf(kf, -3.0234456062316895e-05f, r);
+  r = fmaf(kf, -4.7186188290027076e-09f, r);
+  const float r2 = r * r;
+  const float sr = fmaf(r * r2, fmaf(r2, 8.3333333e-03f, -0.16666667f), r);                       // sin r
+  const float cm = r2 * fmaf(r2, fmaf(r2, -1.3888889e-03f, 0.041666668f), -0.5f);                 // cos r - 1
+  double tx, ty;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tabB + (((uint32_t)__float_as_int(km) & (SC6 - 1)) << 7)));
+  *sn = fma(tx, (double)cm, fma(ty, (double)sr, tx));
+  *cs = fma(ty, (double)cm, fma(-tx, (double)sr, ty));
+}
+__device__ __forceinline__ void sincos_tab64_x2(float xa, float xb, uint32_t tabB, double* sa, double* ca, double* sb, double* cb) {
+  sincos_tab64(xa, tabB, sa, ca);
+  sincos_tab64(xb, tabB, sb, cb);
 }
 // out of line on purpose: the step body is instantiated ~20 times and must stay inside the instruction cache
 static __device__ __noinline__ double2 sincos_slow(float x) {   // by value: pointer outputs would pin the caller's results to local memory
@@ -619,39 +625,81 @@ static __device__ __noinline__ double2 sincos_slow(float x) {   // by value: poi
   sincos_d((double)x, &s, &c);
   return make_double2(s, c);
 }
-__device__ __forceinline__ void sincos_f6_x2(float xa, float xb, const double2* tabL, double* sa, double* ca, double* sb, double* cb) {
-  if (fmaxf(fabsf(xa), fabsf(xb)) < SC_FAST_LIMIT) {
-    sincos_tab64_x2(xa, xb, tabL, sa, ca, sb, cb);
+__device__ __forceinline__ void sincos_f6_x2(float xa, float xb, uint32_t tabB, double* sa, double* ca, double* sb, double* cb) {
+  if (!(fmaxf(fabsf(xa), fabsf(xb)) >= SC6_LIMIT)) {   // NaN takes the table path too (and comes out as NaN)
+    sincos_tab64_x2(xa, xb, tabB, sa, ca, sb, cb);
   } else {   // beyond the exact range of the float32 reduction (never produced by the models), or NaN
     const double2 a = sincos_slow(xa), bb = sincos_slow(xb);
     *sa = a.x; *ca = a.y; *sb = bb.x; *cb = bb.y;
   }
 }
 
-// stage elements [e0, e0 + 8) of 32 consecutive rows (frames frame0 ..) into a tile: lane -> (element q = lane & 7,
-// frame lane >> 3 + 4 j).  Rows beyond the batch are skipped (their tile columns keep the zeros written at start-up);
-// elements outside [0, len) are clamped to the row (read, never used).
+// stage elements [e0, e0 + 8) of 32 consecutive rows (frames frame0 ..) into a dense [frame][8] tile: lane -> (element
+// q = lane & 7, frame lane >> 3 + 4 j), i.e. a warp instruction moves four 32-byte row segments into 128 consecutive bytes
+// of shared memory.  Rows beyond the batch are skipped (their tile rows keep the zeros written at start-up); elements outside
+// [0, len) are clamped to the row (read, never used).
 __device__ __forceinline__ void f6_issue(uint32_t tile, const float* __restrict__ base, int64_t pitch, int64_t frame0, int64_t b,
                                          int e0, int len, int lane) {
   const int q = lane & 7, fr0 = lane >> 3;
   const int e = min(max(e0 + q, 0), len - 1);
   const float* src = base + (frame0 + fr0) * pitch + e;
   const int64_t hop = 4 * pitch;
-  uint32_t dst = tile + 4u * (uint32_t)(q * F6_IN_PITCH + fr0);
-  int64_t fr = frame0 + fr0;
+  // rows fr with (fr >> 2) & 1 (= j & 1 here) keep their two 16-byte halves swapped, so that the per-lane LDS.128 of one
+  // half (lane = frame) hits eight different 16-byte bank groups per quarter warp
+  const uint32_t dst = tile + 4u * (uint32_t)lane;
+  const uint32_t dst_swapped = tile + 4u * (uint32_t)(lane ^ 4);
+  // a tile takes 32 bytes of each row; L2::128B makes L2 fetch the whole 128-byte line from DRAM, so that the next three
+  // tiles of the row hit in L2 and DRAM sees full-line reads instead of four scattered 32-byte sectors
+  if (frame0 + 32 <= b) {   // all 32 rows exist (every tile but the last of the batch): no per-copy predicate
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    if (fr < b) cp_async4_s(dst, src);
-    src += hop;
-    dst += 16u;
-    fr += 4;
+    for (int j = 0; j < 8; j++) {
+      asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 4;" ::"r"(((j & 1) ? dst_swapped : dst) + 128u * j), "l"(src) : "memory");
+      src += hop;
+    }
+  } else {
+    int64_t fr = frame0 + fr0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (fr < b) asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 4;" ::"r"(((j & 1) ? dst_swapped : dst) + 128u * j), "l"(src) : "memory");
+      src += hop;
+      fr += 4;
+    }
+  }
+}
+// same for an array whose rows are 8-byte aligned (even pitch, even e0): lane -> (element pair q = lane & 3, frame lane >> 2 + 8 j),
+// four 8-byte-per-lane instructions instead of eight 4-byte ones
+__device__ __forceinline__ void f6_issue8(uint32_t tile, const float* __restrict__ base, int64_t pitch, int64_t frame0, int64_t b,
+                                          int e0, int len, int lane) {
+  const int q = lane & 3, fr0 = lane >> 2;
+  const int e = min(max(e0 + 2 * q, 0), len - 2);   // stays even: len is even
+  const float* src = base + (frame0 + fr0) * pitch + e;
+  const int64_t hop = 8 * pitch;
+  // row fr = fr0 + 8 j: swapped halves when (fr >> 2) & 1 = (fr0 >> 2) & 1
+  const uint32_t dst = tile + 4u * (uint32_t)((8 * fr0 + 2 * q) ^ (((fr0 >> 2) & 1) << 2));
+  if (frame0 + 32 <= b) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 8;" ::"r"(dst + 256u * j), "l"(src) : "memory");
+      src += hop;
+    }
+  } else {
+    int64_t fr = frame0 + fr0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (fr < b) asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 8;" ::"r"(dst + 256u * j), "l"(src) : "memory");
+      src += hop;
+      fr += 8;
+    }
   }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store96(float* gdst, const float* ssrc) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 96;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)) : "memory");
+// one 2-d TMA tensor store per 8-atom group and warp: box = 24 floats x 32 frames; rows beyond the batch are clipped by the unit
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const float* ssrc, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(x), "r"(y)
+               : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -659,9 +707,9 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // one NeRF step of a lane in global coordinates; returns the float32 position of the atom it placed
-__device__ __forceinline__ void f6_step(float fd, float fa, double L, const double2* tabL, Se3& f, float& ox, float& oy, float& oz) {
+__device__ __forceinline__ void f6_step(float fd, float fa, double L, uint32_t tabB, Se3& f, float& ox, float& oy, float& oz) {
   double sw, cw, sg, cg;
-  sincos_f6_x2(fd, fa, tabL, &sw, &cw, &sg, &cg);
+  sincos_f6_x2(fd, fa, tabB, &sw, &cw, &sg, &cg);
   nerf_step(f, cw, sw, -cg, sg, L);   // bend by pi - theta: cos = -cos(theta), sin = sin(theta)
   ox = (float)f.p[0];
   oy = (float)f.p[1];
@@ -669,63 +717,89 @@ __device__ __forceinline__ void f6_step(float fd, float fa, double L, const doub
 }
 
 // the chain of one side: atoms k = s-2 .. 0 (SIDE 0: inputs d[k], a[k], L[k]) or s+2 .. n-1 (SIDE 1: d[k-3], a[k-2], L[k-1]).
-// tD0 / tA0: this warp's dihedral / angle tiles (buffer 1 follows buffer 0 at + F6_IN_TILE words).
-template <int SIDE>
-__device__ __forceinline__ void f6_chain(Se3& f, const float* __restrict__ angles, const float* __restrict__ dihedrals, const double* L64,
-                                         const double2* tabL, float* tD0, float* tA0, float* myrow, float* __restrict__ dst, int64_t frame0,
-                                         int64_t b, int n, bool valid, int lane) {
+// tD0 / tA0: this warp's dihedral / angle tiles (buffer 1 follows buffer 0 at + F6_IN_TILE words); outT: the output group.
+// ROBUST = false: whole 8-atom groups run the table path unconditionally and only track max |angle| (returned): the caller
+// repeats the tile with ROBUST = true -- every step tests its angles -- if any lane saw an angle beyond the table path's range.
+template <int SIDE, bool A8, bool ROBUST>
+__device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angles, const float* __restrict__ dihedrals, const double* L64,
+                                          uint32_t tabB, float* tD0, float* tA0, float* outT, const CUtensorMap* omap,
+                                          float* __restrict__ dst, int64_t frame0, int64_t b, int n, bool valid, int lane) {
   const int s = n / 2, nd = n - 3, na = n - 2;
   constexpr int dir = SIDE ? 1 : -1;
   constexpr int sh_d = SIDE ? -3 : 0, sh_a = SIDE ? -2 : 0, sh_l = SIDE ? -1 : 0;
   const int k_first = SIDE ? s + 2 : s - 2, k_last = SIDE ? n - 1 : 0;     // inclusive
-  if (SIDE ? (k_first > k_last) : (k_first < k_last)) return;
+  float amax = 0.f;
+  if (SIDE ? (k_first > k_last) : (k_first < k_last)) return amax;
   const int g_first = k_first >> 3, g_last = k_last >> 3;
   const uint32_t sD0 = (uint32_t)__cvta_generic_to_shared(tD0), sA0 = (uint32_t)__cvta_generic_to_shared(tA0);
+  float4* row4 = reinterpret_cast<float4*>(outT + lane * 24);
+  const int swz = (lane >> 2) & 1;                           // this row's halves are swapped in the tiles
+  auto issue_a = [&](uint32_t tile, int e0) {
+    if (A8) f6_issue8(tile, angles, na, frame0, b, e0, na, lane);
+    else f6_issue(tile, angles, na, frame0, b, e0, na, lane);
+  };
   int buf = 0;
   f6_issue(sD0, dihedrals, nd, frame0, b, 8 * g_first + sh_d, nd, lane);
-  f6_issue(sA0, angles, na, frame0, b, 8 * g_first + sh_a, na, lane);
+  issue_a(sA0, 8 * g_first + sh_a);
   cp_async_commit();
   for (int g = g_first; g != g_last + dir; g += dir) {
     const int gn = g + dir;
     if (gn != g_last + dir) {
       f6_issue(sD0 + 4u * F6_IN_TILE * (buf ^ 1), dihedrals, nd, frame0, b, 8 * gn + sh_d, nd, lane);
-      f6_issue(sA0 + 4u * F6_IN_TILE * (buf ^ 1), angles, na, frame0, b, 8 * gn + sh_a, na, lane);
+      issue_a(sA0 + 4u * F6_IN_TILE * (buf ^ 1), 8 * gn + sh_a);
     }
     cp_async_commit();
     cp_async_wait1();
     __syncwarp();
-    const float* td = tD0 + buf * F6_IN_TILE + lane;
-    const float* ta = tA0 + buf * F6_IN_TILE + lane;
+    const float* td = tD0 + buf * F6_IN_TILE + lane * 8;     // this lane's (frame's) eight dihedrals / angles of the group
+    const float* ta = tA0 + buf * F6_IN_TILE + lane * 8;
     // atoms of this group that belong to the side, in walking order
     const int ka = SIDE ? max(8 * g, k_first) : min(8 * g + 7, k_first);
     const int kb = SIDE ? min(8 * g + 7, k_last) : max(8 * g, k_last);    // inclusive
     const bool whole = SIDE ? (ka == 8 * g && kb == 8 * g + 7) : (ka == 8 * g + 7 && kb == 8 * g);
     if (whole) {
-      bulk_wait_read0();          // the previous group's rows have left the buffer
-      float4* row4 = reinterpret_cast<float4*>(myrow);
 #pragma unroll 1
       for (int half = 0; half < 2; half++) {
-        float pend[12];           // atoms 4 h .. 4 h + 3 of the group in memory order (h = half on the right, 1 - half on the left)
+        const int hm = SIDE ? half : 1 - half;   // memory half of the group: atoms 8 g + 4 hm .. + 3
+        const float4 d4 = *reinterpret_cast<const float4*>(td + 4 * (hm ^ swz));
+        const float4 a4 = *reinterpret_cast<const float4*>(ta + 4 * (hm ^ swz));
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const double* Lp = L64 + (8 * g + 4 * hm + sh_l);
+        float pend[12];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const int slot = SIDE ? 4 * half + u : 7 - (4 * half + u);
-          const int pu = SIDE ? u : 3 - u;
-          f6_step(td[slot * F6_IN_PITCH], ta[slot * F6_IN_PITCH], L64[8 * g + slot + sh_l], tabL, f, pend[3 * pu], pend[3 * pu + 1],
-                  pend[3 * pu + 2]);
+          const int pu = SIDE ? u : 3 - u;       // atom 4 hm + pu is placed by step u of this half
+          double sw, cw, sg, cg;
+          if (ROBUST) {
+            sincos_f6_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
+          } else {
+            amax = fmaxf(amax, fmaxf(fabsf(dv[pu]), fabsf(av[pu])));
+            sincos_tab64_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
+          }
+          nerf_step(f, cw, sw, -cg, sg, Lp[pu]);
+          pend[3 * pu] = (float)f.p[0];
+          pend[3 * pu + 1] = (float)f.p[1];
+          pend[3 * pu + 2] = (float)f.p[2];
         }
-        const int q4 = SIDE ? 3 * half : 3 * (1 - half);
-        row4[q4] = make_float4(pend[0], pend[1], pend[2], pend[3]);
-        row4[q4 + 1] = make_float4(pend[4], pend[5], pend[6], pend[7]);
-        row4[q4 + 2] = make_float4(pend[8], pend[9], pend[10], pend[11]);
+        if (half == 0) {                         // first store into the group buffer: the previous group must have left it
+          if (lane == 0) bulk_wait_read0();      // (the storing lane tracks the bulk groups); four steps after the store was issued
+          __syncwarp();
+        }
+        row4[3 * hm] = make_float4(pend[0], pend[1], pend[2], pend[3]);
+        row4[3 * hm + 1] = make_float4(pend[4], pend[5], pend[6], pend[7]);
+        row4[3 * hm + 2] = make_float4(pend[8], pend[9], pend[10], pend[11]);
       }
       fence_async_smem();
-      if (valid) bulk_store96(dst + 24 * g, myrow);
-      bulk_commit();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(omap, outT, 24 * g, (int)frame0);
+        bulk_commit();
+      }
     } else {
       for (int k = ka; k != kb + dir; k += dir) {
         const int slot = k & 7;
         float ox, oy, oz;
-        f6_step(td[slot * F6_IN_PITCH], ta[slot * F6_IN_PITCH], L64[k + sh_l], tabL, f, ox, oy, oz);
+        f6_step(td[slot ^ (4 * swz)], ta[slot ^ (4 * swz)], L64[k + sh_l], tabB, f, ox, oy, oz);
         if (valid) { dst[3 * k] = ox; dst[3 * k + 1] = oy; dst[3 * k + 2] = oz; }
       }
     }
@@ -733,18 +807,23 @@ __device__ __forceinline__ void f6_chain(Se3& f, const float* __restrict__ angle
     buf ^= 1;
   }
   cp_async_wait0();
+  return amax;
 }
 
-__global__ void __launch_bounds__(F6_THREADS, 1) backmap_fwd6_kernel(const float* __restrict__ lengths, const float* __restrict__ angles,
-                                                                     const float* __restrict__ dihedrals, int64_t b, int n,
-                                                                     float* __restrict__ xyz, const double2* __restrict__ tab) {
-  extern __shared__ __align__(16) float smem[];
-  double2* tabS = reinterpret_cast<double2*>(smem);                        // [SC6][8]
-  double* L64 = reinterpret_cast<double*>(smem + SC6 * 8 * 4);             // [n - 1], padded to an even count
-  const int lwords = 2 * ((n - 1 + 1) & ~1);
-  float* warp_base = smem + SC6 * 8 * 4 + lwords;
+template <bool A8, int F6_WARPS>
+__global__ void __launch_bounds__(32 * F6_WARPS, 1) backmap_fwd6_kernel(const __grid_constant__ CUtensorMap omap, const float* __restrict__ lengths,
+                                                                     const float* __restrict__ angles, const float* __restrict__ dihedrals,
+                                                                     int64_t b, int n, float* __restrict__ xyz, const double2* __restrict__ tab) {
+  extern __shared__ __align__(1024) float smem6[];
+  double2* tabS = reinterpret_cast<double2*>(smem6);                       // [SC6][8]
+  double* L64 = reinterpret_cast<double*>(smem6 + SC6 * 8 * 4);            // [n - 1], region rounded up to 128 bytes
+  const int lwords = ((2 * (n - 1) + 31) / 32) * 32;
+  float* warp_base = smem6 + SC6 * 8 * 4 + lwords;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int F6_THREADS = 32 * F6_WARPS;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  int lane = tid & 31;
+  asm volatile("mov.u32 %0, %0;" : "+r"(lane));   // opaque: keeps ptxas from re-reading SR_TID.X inside the loops
   const int side = warp & 1, pair = warp >> 1;
   for (int i = tid; i < SC6 * 8; i += F6_THREADS) tabS[i] = __ldg(tab + (i >> 3) * (SC_TABLE / SC6));
   for (int i = tid; i < n - 1; i += F6_THREADS) L64[i] = (double)__ldg(lengths + i);
@@ -752,13 +831,12 @@ __global__ void __launch_bounds__(F6_THREADS, 1) backmap_fwd6_kernel(const float
   for (int i = lane; i < F6_WARP_WORDS; i += 32) wmem[i] = 0.f;
   __syncthreads();
 
-  const double2* tabL = tabS + (lane & 7);
+  const uint32_t tabB = (uint32_t)__cvta_generic_to_shared(tabS + (lane & 7));   // this lane's table replica
   float* tD0 = wmem;                                                       // dihedral tiles: buffer 1 at + F6_IN_TILE
   float* tA0 = wmem + 2 * F6_IN_TILE;                                      // angle tiles
-  float* outT = wmem + 4 * F6_IN_TILE;                                     // 16-byte aligned: all pieces are multiples of 4 words
+  float* outT = wmem + 4 * F6_IN_TILE;                                     // 128-byte aligned: 4 KB into a 7 KB region
   float* partner_out = warp_base + (size_t)(warp ^ 1) * F6_WARP_WORDS + 4 * F6_IN_TILE;
   const uint32_t sA0 = (uint32_t)__cvta_generic_to_shared(tA0);
-  float* myrow = outT + lane * F6_OUT_PITCH;
 
   const int s = n / 2;
   const int na = n - 2;
@@ -770,6 +848,9 @@ __global__ void __launch_bounds__(F6_THREADS, 1) backmap_fwd6_kernel(const float
     const int64_t frame = frame0 + lane;
     const bool valid = frame < b;
     float* dst = xyz + (valid ? frame : frame0) * (int64_t)(3 * n);
+    // pass 0: table path without per-step range tests; pass 1 (only if some angle of the tile was beyond the table path's
+    // range -- never for model outputs): the same with every step tested
+    for (int pass = 0; pass < 2; pass++) {
 
     // ---- planar prologue: SE(2) product of bonds 0 .. s-2, split between the two warps of the pair ---------------------
     // right warp: bonds [0, h), left warp: bonds [h, s-1); h is a multiple of 8 (tile aligned)
@@ -778,37 +859,45 @@ __global__ void __launch_bounds__(F6_THREADS, 1) backmap_fwd6_kernel(const float
     Se2 pl{1.0, 0.0, 0.0, 0.0};
     {
       int buf = 0;
-      if (k_lo < k_hi) f6_issue(sA0, angles, na, frame0, b, k_lo, na, lane);
+      auto issue_a = [&](uint32_t tile_addr, int e0) {
+        if (A8) f6_issue8(tile_addr, angles, na, frame0, b, e0, na, lane);
+        else f6_issue(tile_addr, angles, na, frame0, b, e0, na, lane);
+      };
+      if (k_lo < k_hi) issue_a(sA0, k_lo);
       cp_async_commit();
       for (int k0 = k_lo; k0 < k_hi; k0 += F6_TILE) {
-        if (k0 + F6_TILE < k_hi) f6_issue(sA0 + 4u * F6_IN_TILE * (buf ^ 1), angles, na, frame0, b, k0 + F6_TILE, na, lane);
+        if (k0 + F6_TILE < k_hi) issue_a(sA0 + 4u * F6_IN_TILE * (buf ^ 1), k0 + F6_TILE);
         cp_async_commit();
         cp_async_wait1();
         __syncwarp();
-        const float* t = tA0 + buf * F6_IN_TILE + lane;
+        const float* t = tA0 + buf * F6_IN_TILE + lane * 8;
         const int cnt = min(F6_TILE, k_hi - k0);
-        int q = 0;
-        for (; q + 1 < cnt; q += 2) {   // two bonds per iteration: their sin/cos are computed as one packed pair
-          const int k = k0 + q;
-          double s0, c0, s1, c1;
-          sincos_f6_x2(t[q * F6_IN_PITCH], t[(q + 1) * F6_IN_PITCH], tabL, &s0, &c0, &s1, &c1);
-          const double La = L64[k], Lb = L64[k + 1];
-          pl.x = fma(La, pl.c, pl.x);
-          pl.y = fma(La, pl.s, pl.y);
-          {   // turn by -(-1)^k (pi - theta_k): cos = -cos(theta), sin = -(-1)^k sin(theta)
-            const double cw = -c0, sw = (k & 1) ? s0 : -s0;
-            const double c2 = pl.c * cw - pl.s * sw, s2 = pl.c * sw + pl.s * cw;
-            pl.c = c2; pl.s = s2;
-          }
-          pl.x = fma(Lb, pl.c, pl.x);
-          pl.y = fma(Lb, pl.s, pl.y);
-          {
-            const double cw = -c1, sw = (k & 1) ? -s1 : s1;   // bond k + 1 has the opposite parity
-            const double c2 = pl.c * cw - pl.s * sw, s2 = pl.c * sw + pl.s * cw;
-            pl.c = c2; pl.s = s2;
+        const int swz = (lane >> 2) & 1;
+        const float4 t0 = *reinterpret_cast<const float4*>(t + 4 * swz), t1 = *reinterpret_cast<const float4*>(t + 4 * (swz ^ 1));
+        const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int q = 0; q < F6_TILE; q += 2) {   // two bonds per iteration: their sin/cos are computed as one packed pair
+          if (q + 1 < cnt) {
+            const int k = k0 + q;                // even (k0 is a multiple of 8)
+            double s0, c0, s1, c1;
+            sincos_f6_x2(tv[q], tv[q + 1], tabB, &s0, &c0, &s1, &c1);
+            const double La = L64[k], Lb = L64[k + 1];
+            pl.x = fma(La, pl.c, pl.x);
+            pl.y = fma(La, pl.s, pl.y);
+            {   // turn by -(-1)^k (pi - theta_k): cos = -cos(theta), sin = -(-1)^k sin(theta); k even
+              const double c2 = -(pl.c * c0) + pl.s * s0, s2 = -(pl.c * s0) - pl.s * c0;
+              pl.c = c2; pl.s = s2;
+            }
+            pl.x = fma(Lb, pl.c, pl.x);
+            pl.y = fma(Lb, pl.s, pl.y);
+            {   // bond k + 1 (odd): sin = +sin(theta)
+              const double c2 = -(pl.c * c1) - pl.s * s1, s2 = pl.c * s1 - pl.s * c1;
+              pl.c = c2; pl.s = s2;
+            }
+          } else if (q < cnt) {
+            planar_step(pl, L64[k0 + q], true, tv[q], k0 + q);
           }
         }
-        if (q < cnt) planar_step(pl, L64[k0 + q], true, t[q * F6_IN_PITCH], k0 + q);
         __syncwarp();
         buf ^= 1;
       }
@@ -852,12 +941,32 @@ __global__ void __launch_bounds__(F6_THREADS, 1) backmap_fwd6_kernel(const float
       }
     }
 
-    // ---- the chain of this side (side is warp uniform: two instantiations keep every register index static) ----------
-    if (side) f6_chain<1>(f, angles, dihedrals, L64, tabL, tD0, tA0, myrow, dst, frame0, b, n, valid, lane);
-    else f6_chain<0>(f, angles, dihedrals, L64, tabL, tD0, tA0, myrow, dst, frame0, b, n, valid, lane);
-    bulk_wait_read0();   // the output buffer doubles as the exchange buffer of the next tile
+    // ---- the chain of this side (side is warp uniform: the instantiations keep every register index static) ----------
+    float amax;
+    if (pass == 0) {
+      if (side) amax = f6_chain<1, A8, false>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
+      else amax = f6_chain<0, A8, false>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
+    } else {
+      if (side) amax = f6_chain<1, A8, true>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
+      else amax = f6_chain<0, A8, true>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
+    }
+    if (lane == 0) bulk_wait_read0();   // the output buffer doubles as the exchange buffer of the next tile / pass
+    __syncwarp();
+    // both warps of the pair must agree on repeating (they meet at the named barrier of the prologue): the flag travels
+    // through the exchange buffers
+    if (pass == 0) {
+      const bool bad = __any_sync(0xffffffffu, amax >= SC6_LIMIT);
+      if (lane == 0) reinterpret_cast<int*>(outT)[0] = bad ? 1 : 0;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+      const bool redo = bad || reinterpret_cast<const int*>(partner_out)[0] != 0;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+      if (!redo) break;
+      if (lane == 0) bulk_wait0();   // the first pass's tensor stores must have landed before the second pass rewrites them
+      __syncwarp();
+    }
+    }   // pass
   }
-  bulk_wait0();
+  if (lane == 0) bulk_wait0();
 }
 
 // ====================================================================================================
@@ -1493,9 +1602,14 @@ static int get_sincos_table(const double2** out) {
 
 // version 6 (lane per frame and side): shared bond lengths, n % 4 == 0 (16-byte aligned 8-atom output groups), 16-byte aligned
 // output, bond lengths + per-warp tiles within the shared memory of one SM, and a batch that fills the machine
-static size_t fwd6_smem_bytes(int64_t n) {
-  return (size_t)(SC6 * 8 * 4 + 2 * ((n - 1 + 1) & ~(int64_t)1) + F6_WARPS * F6_WARP_WORDS) * sizeof(float);
+static std::atomic<int64_t> g_fwd6_warps{0};
+int64_t fwd6_warps() { return g_fwd6_warps.load(); }
+void set_fwd6_warps(int64_t v) { g_fwd6_warps.store(v); }
+static size_t fwd6_smem_bytes(int64_t n, int warps) {
+  return (size_t)(SC6 * 8 * 4 + ((2 * (n - 1) + 31) / 32) * 32 + warps * F6_WARP_WORDS) * sizeof(float);
 }
+int encode_f32_map_2d(void* map_out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_cols,
+                      uint32_t box_rows, int swizzle_128b);   // pair_tile.cu
 // batch size from which the lane-per-frame kernel takes over (emk_set_option("backmap_fwd6_min_batch", v); 0 = whenever
 // eligible, negative = never).  Default from EMK_BACKMAP_FWD6_MIN_BATCH or the measured cross-over.
 static std::atomic<int64_t> g_fwd6_min_batch{[] {
@@ -1504,15 +1618,35 @@ static std::atomic<int64_t> g_fwd6_min_batch{[] {
 }()};
 int64_t fwd6_min_batch() { return g_fwd6_min_batch.load(); }
 void set_fwd6_min_batch(int64_t v) { g_fwd6_min_batch.store(v); }
-static int backmap_fwd6_launch(const float* lengths, const float* angles, const float* dihedrals, int64_t b, int64_t n, float* xyz,
-                               const double2* tab, cudaStream_t st) {
-  const size_t smem = fwd6_smem_bytes(n);
+
+template <bool A8, int W>
+static int fwd6_launch_w(const CUtensorMap& omap, const float* lengths, const float* angles, const float* dihedrals, int64_t b, int64_t n,
+                         float* xyz, const double2* tab, cudaStream_t st) {
+  auto kern = backmap_fwd6_kernel<A8, W>;
   static bool cfg[kMaxDevices] = {false};
-  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(backmap_fwd6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t tiles = (b + 31) / 32;
-  const int64_t blocks = std::min<int64_t>((tiles + F6_WARPS / 2 - 1) / (F6_WARPS / 2), (int64_t)sm_count());
-  backmap_fwd6_kernel<<<(unsigned)blocks, F6_THREADS, smem, st>>>(lengths, angles, dihedrals, b, (int)n, xyz, tab);
+  const int64_t blocks = std::min<int64_t>((tiles + W / 2 - 1) / (W / 2), (int64_t)sm_count());
+  kern<<<(unsigned)blocks, 32 * W, fwd6_smem_bytes(n, W), st>>>(omap, lengths, angles, dihedrals, b, (int)n, xyz, tab);
   return launch_status("backmap_fwd6_kernel");
+}
+static int backmap_fwd6_launch(const float* lengths, const float* angles, const float* dihedrals, int64_t b, int64_t n, float* xyz,
+                               const double2* tab, int warps, cudaStream_t st) {
+  // output viewed as (b, 3 n) float32 rows: a warp stores 8 atoms (24 floats) of its 32 frames with one tensor copy
+  alignas(64) CUtensorMap omap;
+  int rc = encode_f32_map_2d(&omap, xyz, (uint64_t)(3 * n), (uint64_t)b, (uint64_t)(12 * n), 24, 32, 0);
+  if (rc) return rc;
+  // n % 4 == 0 makes the rows of `angles` (n - 2 floats) 8-byte aligned whenever the base is: 8-byte cp.async for that array
+  const bool a8 = (reinterpret_cast<uintptr_t>(angles) & 7) == 0;
+#define EMK_F6(W) return a8 ? fwd6_launch_w<true, W>(omap, lengths, angles, dihedrals, b, n, xyz, tab, st) \
+                            : fwd6_launch_w<false, W>(omap, lengths, angles, dihedrals, b, n, xyz, tab, st)
+  if (warps <= 8) EMK_F6(8);
+  if (warps <= 12) EMK_F6(12);
+  if (warps <= 14) EMK_F6(14);
+  if (warps <= 16) EMK_F6(16);
+  if (warps <= 18) EMK_F6(18);
+  EMK_F6(20);
+#undef EMK_F6
 }
 
 int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angles, const float* dihedrals, int64_t b,
@@ -1524,9 +1658,23 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
   const double2* tab;
   int rc = get_sincos_table(&tab);
   if (rc) return rc;
-  if (lstride == 0 && n % 4 == 0 && n >= 16 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0 && fwd6_smem_bytes(n) <= 227 * 1024 &&
-      fwd6_min_batch() >= 0 && b >= fwd6_min_batch())
-    return backmap_fwd6_launch(lengths, angles, dihedrals, b, n, xyz, tab, st);
+  if (lstride == 0 && n % 4 == 0 && n >= 16 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0 && fwd6_min_batch() >= 0 && b >= fwd6_min_batch()) {
+    // warps per CTA: the candidate whose waves are fullest (time ~ rounds x pairs: the per-SM rate does not depend on the count)
+    const int64_t tiles = (b + 31) / 32, sms = sm_count();
+    static const int cand[] = {20, 18, 16, 14, 12, 8};
+    int best = 0;
+    double best_eff = 0.0;
+    for (int w : cand) {
+      if (fwd6_smem_bytes(n, w) > 227 * 1024) continue;   // long chains: the bond lengths take the room of warps
+      if (fwd6_warps() != 0 && w != fwd6_warps()) continue;
+      const int64_t cap = sms * (w / 2);
+      const double eff = (double)tiles / (double)(((tiles + cap - 1) / cap) * cap) * (w == 8 ? 0.85 : 1.0);   // 8 warps hide less latency
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+    }
+    // the chunk-scan kernel reaches ~0.8 of this kernel's full-wave rate at any batch size
+    if (best != 0 && (best_eff >= 0.8 || fwd6_min_batch() == 0))
+      return backmap_fwd6_launch(lengths, angles, dihedrals, b, n, xyz, tab, best, st);
+  }
   const size_t per_group = ((3 * (size_t)n + 7) & ~(size_t)3) * sizeof(float);
   const size_t budget = 224 * 1024 - SC_SMALL * sizeof(double2);
   const int groups = (int)std::min<size_t>(FWD5_GROUPS, budget / per_group);   // frames in flight per CTA

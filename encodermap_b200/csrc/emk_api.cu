@@ -100,6 +100,8 @@ int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_
 int fp32_probe_device(double*);
 int64_t fwd6_min_batch();
 void set_fwd6_min_batch(int64_t);
+int64_t fwd6_warps();
+void set_fwd6_warps(int64_t);
 int d2c_chain_bwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int pairwise_periodic_bwd_device(const float*, int64_t, int64_t, double, const float*, const float*, float*, cudaStream_t);
 int chain_in_plane_device(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
@@ -203,12 +205,22 @@ int emk_set_option(const char* name, int64_t value) {
     set_fwd6_min_batch(value);
     return EMK_OK;
   }
+  if (strcmp(name, "backmap_fwd6_warps") == 0) {
+    EMK_REQUIRE(value == 0 || value == 8 || value == 12 || value == 14 || value == 16 || value == 18 || value == 20, EMK_E_ARG,
+                "emk_set_option: backmap_fwd6_warps must be 0 (automatic), 8, 12, 14, 16, 18 or 20");
+    set_fwd6_warps(value);
+    return EMK_OK;
+  }
   return fail(EMK_E_ARG, "emk_set_option: unknown option '%s'", name);
 }
 int emk_get_option(const char* name, int64_t* value) {
   EMK_REQUIRE(name && value, EMK_E_NULL, "emk_get_option: NULL argument");
   if (strcmp(name, "backmap_fwd6_min_batch") == 0) {
     *value = fwd6_min_batch();
+    return EMK_OK;
+  }
+  if (strcmp(name, "backmap_fwd6_warps") == 0) {
+    *value = fwd6_warps();
     return EMK_OK;
   }
   return fail(EMK_E_ARG, "emk_get_option: unknown option '%s'", name);

@@ -513,6 +513,25 @@ static int get_encode_fn(EncodeTiledFn* fn) {
   return EMK_OK;
 }
 
+// generic 2-d float32 tiled map (rows x cols, row pitch in bytes a multiple of 16) -- also used by backmap.cu for its
+// output rows.  `map_out` is a CUtensorMap (128 bytes, 64-byte aligned).
+int encode_f32_map_2d(void* map_out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_cols,
+                      uint32_t box_rows, int swizzle_128b) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_128b ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EMK_REQUIRE(r == CUDA_SUCCESS, EMK_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (cols=%llu rows=%llu pitch=%llu)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_pitch_bytes);
+  return EMK_OK;
+}
+
 // (n, d_pad) row-major float32, 16-byte aligned base, d_pad % 4 == 0
 static int make_tensor_map(CUtensorMap* map, const float* base, int64_t n, int64_t d_pad) {
   EncodeTiledFn enc;

@@ -60,7 +60,9 @@ EMK_API const char* emk_build_info(void);
 EMK_API int emk_probe_fp32(double* lane_instr_per_s);
 /* Process-wide tuning knobs (kernel selection thresholds; results do not depend on them beyond float32 rounding):
  *   "backmap_fwd6_min_batch"  batch size from which emk_backmap uses the lane-per-frame kernel (default 4096; 0 = whenever
- *                             the shape is eligible, negative = never) */
+ *                             the shape is eligible, negative = never)
+ *   "backmap_fwd6_warps"      warps per CTA of that kernel: 0 (default: chosen per launch so that the frame tiles fill whole
+ *                             waves), or one of 8, 12, 14, 16, 18, 20 */
 EMK_API int emk_set_option(const char* name, int64_t value);
 EMK_API int emk_get_option(const char* name, int64_t* value);
 

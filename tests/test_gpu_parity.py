@@ -994,8 +994,10 @@ def test_backmap_lane_per_frame_kernel(em, n, b):
     dist = rng.uniform(0.13, 0.15, size=(b, n - 1)).astype(np.float32)
     ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
     dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)
-    ang[3, 5] = 60.0            # beyond the table path's range: the float64 polynomial path of that lane
+    ang[3, 5] = 60.0            # beyond the chunk-scan kernel's table range (48 rad)
     dih[b - 1, n - 4] = -75.0
+    ang[min(b - 1, 40), 2] = 1000.0       # beyond the lane-per-frame kernel's range (800 rad): the tile is repeated with tested steps
+    dih[1, n // 2] = -2500.0
     layer = BackMapLayer(n // 2 - 1, (n - 3) // 2)
     old = _lib.get_option("backmap_fwd6_min_batch")
     try:
