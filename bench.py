@@ -50,7 +50,7 @@ N_ROWS, N_DIMS, N_LATENT = 65536, 1024, 2
 SIG = (4.5, 12, 6, 1, 2, 6)
 PERIOD = 2 * math.pi
 CPU_SAMPLE_ROWS = 512
-BACKMAP_ATOMS, BACKMAP_FRAMES, BACKMAP_CHUNK = 1500, 1 << 20, 1 << 16
+BACKMAP_ATOMS, BACKMAP_FRAMES, BACKMAP_CHUNK = 1500, 1 << 20, 1 << 18
 
 
 def measured_peaks():
@@ -448,7 +448,7 @@ def secondary_metrics(dev, peaks):
     out["backmap_fwd"] = {"frames_per_s": fps, "frames": BACKMAP_FRAMES, "n_atoms": n, "ms": ms,
                           "roofline": {"bound": "hbm", "achieved": fps * bytes_per_frame / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": fps * bytes_per_frame / 1e9 / peaks["hbm_gbs"], "bytes_per_frame": bytes_per_frame,
-                                       "note": "float64 SE(3) scan: bound by FP64 latency and L1 data-pipe wavefronts below the HBM roofline (DESIGN.md)"}}
+                                       "note": "float64 NeRF chain, one lane per (frame, side): bound by issue slots (FP64 instructions count twice), not by HBM (DESIGN.md 4.2); 262144-frame chunks"}}
     # fwd + bwd on one chunk: dihedral gradients only (the ADC default, use_backbone_angles=False:
     # reference parameters.py:803) and with bond-angle gradients as well
     chunk = 1 << 15

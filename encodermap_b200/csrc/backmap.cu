@@ -564,25 +564,33 @@ __global__ void __launch_bounds__(FWD5_THREADS, 2) backmap_fwd5_kernel(const flo
 // BackMapLayer forward, version 6 (large batches): one LANE per (frame, side) -- the chain is walked sequentially in
 // GLOBAL coordinates, 32 frames per warp, and the parallelism comes from the frames instead of from cutting one chain
 // into 32 chunks.  What disappears against version 5: the SE(3) scan (21 % of the FP64 work, 26 % of the L1 wavefronts),
-// pass 2 and its shared-memory round trip, the chunk-local / hi-lo bookkeeping, every barrier inside a frame.
+// pass 2 and its shared-memory round trip, the chunk-local / hi-lo bookkeeping, every barrier inside a frame:
+// 6.2 k instead of 8.0 k warp instructions per 500-residue frame.
 //   * work item = (tile of 32 consecutive frames, side); the two warps of a tile are neighbours in the CTA and split the
 //     planar prologue: the anchor frame needs the SE(2) product of the bonds LEFT of the middle before either side can
 //     start in global coordinates; each warp multiplies half of those bonds (angles only: 10 FP64 per bond), they swap
 //     the two partial products through shared memory (one named barrier per tile) and compose them.
-//   * inputs: rows of `dihedrals` / `angles` are streamed through per-warp shared-memory tiles of 8 steps x 32 frames with
-//     4-byte cp.async (a warp instruction moves four 32-byte row segments; tile row pitch 36 words makes both the scatter
-//     and the per-step read -- lane = frame -- conflict free), double buffered: the tile of the next 8 steps is in flight
-//     while the current one is consumed.  Bond lengths (shared by all frames) sit in shared memory as float64.
-//   * outputs: each lane keeps the float32 positions of 4 atoms in registers, writes them as 3 STS.128 into its row of a
-//     per-warp group buffer (8 atoms = 96 bytes per frame; row pitch 112 bytes: conflict free), and every 8 atoms each
-//     lane hands its row to the bulk-copy engine (cp.async.bulk shared -> global, 96 bytes, 16-byte aligned because
-//     n % 4 == 0): the stores cost one instruction per 8 atoms and no LSU wavefronts.  Atoms outside whole 8-groups of a
-//     side (<= 14 per frame) are stored directly.
-//   * sin/cos: 64-entry float64 table, replicated 8x so that lane l reads replica l & 7: a warp-wide 16-byte lookup with
-//     random indices is 4 wavefronts instead of 8.2; float32 argument reduction (exact Cody-Waite steps) and degree-5/6
-//     corrections run packed (FFMA2) for the two angles of a step.  4.7e-9 absolute error per value.
-// Used when the batch is large enough to fill the machine with (frame, side) lanes; version 5 stays the path for small
-// batches, n % 4 != 0, per-frame bond lengths and very long chains.
+//   * inputs: rows of `dihedrals` / `angles` are streamed through per-warp shared-memory tiles of 8 steps x 32 frames,
+//     dense [frame][8] with the two 16-byte halves of every other group of four rows swapped (the per-lane LDS.128 of a
+//     half -- lane = frame -- is then conflict free), filled by cp.async (4 bytes per lane for the dihedrals, whose row pitch
+//     n - 3 is odd; 8 bytes per lane for the angles, whose rows are 8-byte aligned when n % 4 == 0) with the L2::128B
+//     prefetch hint, double buffered: the tile of the next 8 steps is in flight while the current one is consumed.  Neither
+//     array can use the bulk-copy engine: its tensor maps need row pitches that are multiples of 16 bytes.
+//     Bond lengths (shared by all frames) sit in shared memory as float64.
+//   * outputs: a lane keeps the float32 positions of the 8 atoms of a group in registers, writes them as 6 STS.128 into its
+//     96-byte row of the warp's group buffer, and ONE 2-d TMA tensor store per group and warp (box 24 floats x 32 frames of
+//     xyz viewed as (b, 3 n); 16-byte aligned because n % 4 == 0; rows beyond the batch are clipped by the unit) sends the
+//     buffer off: one instruction per 8 atoms x 32 frames and no LSU wavefronts.  The buffer is rewritten a full group later
+//     (waiting for the store's shared-memory read any earlier cost 20 %).  Atoms outside whole 8-groups of a side
+//     (<= 14 per frame) are stored directly.
+//   * sin/cos: 128-entry float64 table replicated 8x (lane l reads replica l & 7: 4 wavefronts per warp-wide lookup), float32
+//     Cody-Waite reduction and degree-3/4 corrections with literal constants; angles beyond +-384 rad are only noticed
+//     (max |angle| per lane) and make the pair of warps repeat the tile with every step range-tested.
+// Measured (profiles/r02_*): bound by issue slots with FP64 instructions counting twice -- (2 x 35 FP64 + 48 other) / 4
+// schedulers = 29.6 cycles per warp-step is the measured compute-only rate (no copies in or out: 137 M frames/s = 0.63 of the
+// HBM roofline at 500 residues); copies in add 21 %, stores 15 %.  The per-SM rate is the same for 12 .. 16 warps.
+// Used when the batch fills whole waves of (frame tile, side) warps; version 5 stays the path for small batches,
+// n % 4 != 0, per-frame bond lengths and very long chains.
 // ====================================================================================================
 // one persistent CTA per SM with 8 .. 20 warps (4 .. 10 tile pairs): the per-SM rate is the same from 12 to 20 warps (it is set
 // by issue slots, FP64 instructions counting twice), so the count is chosen per launch to make the tile count come out as
@@ -591,25 +599,27 @@ constexpr int F6_TILE = 8;                         // steps per input tile = ato
 constexpr int F6_IN_TILE = 32 * F6_TILE;           // words per (array, buffer): [frame][8 elements], dense
 constexpr int F6_OUT_TILE = 32 * 24;               // output group [frame][8 atoms x 3], dense: the box of the TMA tensor store
 constexpr int F6_WARP_WORDS = 4 * F6_IN_TILE + F6_OUT_TILE;   // D/A x two buffers + output group = 7 KB
-constexpr int SC6 = 64;                            // table entries (step 2 pi / 64), 8 replicas
+constexpr int SC6 = 128;                           // table entries (step 2 pi / 128), 8 replicas: 16 KB
 
-// The float32 Cody-Waite reduction below is exact while k * C1 fits 24 bits: C1 = 2 pi / 64 rounded to 11 bits, |k| < 2^13,
-// i.e. |x| < 804 rad.  Larger finite angles (absurd, but legal for the reference) take the float64 path; NaN / Inf pass
-// through the table path as NaN on their own.
-constexpr float SC6_LIMIT = 800.f;
+// The float32 Cody-Waite reduction below is exact while k * C1 fits 24 bits: C1 = 2 pi / 128 rounded to 11 bits, |k| < 2^13,
+// i.e. |x| < 402 rad.  Larger finite angles (legal for the reference, never produced by the models) take the float64 path;
+// NaN / Inf pass through the table path as NaN on their own.
+constexpr float SC6_LIMIT = 384.f;
 
-// table sin/cos of one angle (|x| < SC6_LIMIT): tabB = this lane's replica as a byte address (entry stride 128 bytes).
-// Scalar FFMA with literal constants: the packed FFMA2 form needs every constant in a register PAIR, which at 80 registers
-// were re-materialised with two moves per use.
+// table sin/cos of one angle (|x| < SC6_LIMIT): tabB = byte address of THIS LANE's replica of the 128-entry float64 (sin, cos)
+// table in shared memory (entry stride 8 x 16 bytes: lane l reads replica l & 7, so a warp-wide 16-byte lookup with random
+// indices is 4 wavefronts instead of ~8 -- the shared-memory pipe is the busiest unit of this kernel next to the issue slots).
+// |r| <= pi / 128: sin r = r - r^3 / 6 (+7e-11) and cos r - 1 = -r^2 / 2 + r^4 / 24 (+3e-13); the float32 evaluation adds
+// 1.5e-9.  Scalar FFMA with literal constants: the packed FFMA2 form needs every constant in a register PAIR.
 __device__ __forceinline__ void sincos_tab64(float x, uint32_t tabB, double* sn, double* cs) {
-  const float km = fmaf(x, 10.185916357881302f, 12582912.f);
+  const float km = fmaf(x, 20.371832715762604f, 12582912.f);
   const float kf = km - 12582912.f;
-  float r = fmaf(kf, -0.09814453125f, x);
-  r = fmaf(kf, -3.0234456062316895e-05f, r);
-  r = fmaf(kf, -4.7186188290027076e-09f, r);
+  float r = fmaf(kf, -0.0490722656250f, x);
+  r = fmaf(kf, -1.5117228031158447e-05f, r);
+  r = fmaf(kf, -2.3593094145013538e-09f, r);
   const float r2 = r * r;
-  const float sr = fmaf(r * r2, fmaf(r2, 8.3333333e-03f, -0.16666667f), r);                       // sin r
-  const float cm = r2 * fmaf(r2, fmaf(r2, -1.3888889e-03f, 0.041666668f), -0.5f);                 // cos r - 1
+  const float sr = fmaf(r * r2, -0.16666667f, r);                       // sin r
+  const float cm = r2 * fmaf(r2, 0.041666668f, -0.5f);                  // cos r - 1
   double tx, ty;
   asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tabB + (((uint32_t)__float_as_int(km) & (SC6 - 1)) << 7)));
   *sn = fma(tx, (double)cm, fma(ty, (double)sr, tx));
@@ -703,6 +713,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const float
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -732,7 +743,6 @@ __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angl
   if (SIDE ? (k_first > k_last) : (k_first < k_last)) return amax;
   const int g_first = k_first >> 3, g_last = k_last >> 3;
   const uint32_t sD0 = (uint32_t)__cvta_generic_to_shared(tD0), sA0 = (uint32_t)__cvta_generic_to_shared(tA0);
-  float4* row4 = reinterpret_cast<float4*>(outT + lane * 24);
   const int swz = (lane >> 2) & 1;                           // this row's halves are swapped in the tiles
   auto issue_a = [&](uint32_t tile, int e0) {
     if (A8) f6_issue8(tile, angles, na, frame0, b, e0, na, lane);
@@ -758,14 +768,17 @@ __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angl
     const int kb = SIDE ? min(8 * g + 7, k_last) : max(8 * g, k_last);    // inclusive
     const bool whole = SIDE ? (ka == 8 * g && kb == 8 * g + 7) : (ka == 8 * g + 7 && kb == 8 * g);
     if (whole) {
-#pragma unroll 1
+      // the eight positions of the group stay in registers until all are known: the buffer is written (and handed to the
+      // tensor store) at the END of the group, i.e. a full group after the previous store was issued -- waiting for that
+      // store's shared-memory read any earlier cost 20 % of the kernel
+      float pend[24];
+#pragma unroll
       for (int half = 0; half < 2; half++) {
         const int hm = SIDE ? half : 1 - half;   // memory half of the group: atoms 8 g + 4 hm .. + 3
         const float4 d4 = *reinterpret_cast<const float4*>(td + 4 * (hm ^ swz));
         const float4 a4 = *reinterpret_cast<const float4*>(ta + 4 * (hm ^ swz));
         const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
         const double* Lp = L64 + (8 * g + 4 * hm + sh_l);
-        float pend[12];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int pu = SIDE ? u : 3 - u;       // atom 4 hm + pu is placed by step u of this half
@@ -777,18 +790,16 @@ __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angl
             sincos_tab64_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
           }
           nerf_step(f, cw, sw, -cg, sg, Lp[pu]);
-          pend[3 * pu] = (float)f.p[0];
-          pend[3 * pu + 1] = (float)f.p[1];
-          pend[3 * pu + 2] = (float)f.p[2];
+          pend[12 * hm + 3 * pu] = (float)f.p[0];
+          pend[12 * hm + 3 * pu + 1] = (float)f.p[1];
+          pend[12 * hm + 3 * pu + 2] = (float)f.p[2];
         }
-        if (half == 0) {                         // first store into the group buffer: the previous group must have left it
-          if (lane == 0) bulk_wait_read0();      // (the storing lane tracks the bulk groups); four steps after the store was issued
-          __syncwarp();
-        }
-        row4[3 * hm] = make_float4(pend[0], pend[1], pend[2], pend[3]);
-        row4[3 * hm + 1] = make_float4(pend[4], pend[5], pend[6], pend[7]);
-        row4[3 * hm + 2] = make_float4(pend[8], pend[9], pend[10], pend[11]);
       }
+      if (lane == 0) bulk_wait_read0();          // the previous group has left the buffer (the storing lane tracks the bulk groups)
+      __syncwarp();
+      float4* row4 = reinterpret_cast<float4*>(outT + lane * 24);
+#pragma unroll
+      for (int q = 0; q < 6; q++) row4[q] = make_float4(pend[4 * q], pend[4 * q + 1], pend[4 * q + 2], pend[4 * q + 3]);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
