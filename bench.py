@@ -303,8 +303,11 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = pairs / (e2e_ms * 1e-3)
     # bytes this rank copies in per step: the rows from the band of its first tile to the end + the latent
-    first_row = min(N_ROWS, (_lib.pair_tile_decode(N_ROWS, tr[0])[0] * 128 // 8192) * 8192) if tr[1] > tr[0] else N_ROWS
-    h2d_mine = (N_ROWS - first_row) * N_DIMS * 4 + zh.numel() * 4
+    if world > 2:   # 1/G of the rows per host link + NVLink all-gather (sigmoid_loss picks this above two ranks)
+        h2d_mine = -(-N_ROWS // world) * N_DIMS * 4 + zh.numel() * 4
+    else:
+        first_row = min(N_ROWS, (_lib.pair_tile_decode(N_ROWS, tr[0])[0] * 128 // 8192) * 8192) if tr[1] > tr[0] else N_ROWS
+        h2d_mine = (N_ROWS - first_row) * N_DIMS * 4 + zh.numel() * 4
     h2d_max = max_over_ranks(float(h2d_mine))
 
     extra = {}
@@ -376,7 +379,7 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "unique pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d_max), "d2h_bytes_per_step": gh.numel() * 4 + 4,
-                    "note": "sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward: every rank copies the rows its tile range touches (h2d_bytes_per_step = the largest rank's share) in chunks on a side stream behind the pair tiles that need them; loss + gradient read back"},
+                    "note": "sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward; h2d_bytes_per_step = the largest rank's share. n_gpus <= 2: every rank copies the rows its tile range touches in chunks on a side stream behind the pair tiles that need them; n_gpus > 2: 1/n_gpus of the rows per host link + all-gather over NVLink; loss + gradient read back"},
             "gpu_launches": args.steps * world,
             "per_rank": per_rank,
             "multi_gpu_check": multi_gpu_check,

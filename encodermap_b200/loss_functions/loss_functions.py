@@ -101,10 +101,18 @@ def sigmoid_loss(
 
             tile_range, reduce_fn = tile_shard(int(y_true.shape[0]), process_group)
         if not y_true.is_cuda and y_true.is_pinned():
-            # high-d input still in pinned host memory: streamed to the device behind the pair tiles (not a CPU path --
-            # unpinned CPU tensors are rejected like everywhere else); with a process group every rank streams only the
-            # rows its own tile range touches
-            cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
+            # high-d input still in pinned host memory (not a CPU path -- unpinned CPU tensors are rejected like everywhere
+            # else).  One or two ranks: streamed to the device behind the pair tiles, every rank only the rows its own tile
+            # range touches.  More ranks: the rank that owns the first tile band needs every row before its first tile, so
+            # streaming would expose a full 1/1 copy on that rank; instead every rank copies 1/G of the rows over its own
+            # host link and the slices are all-gathered over NVLink (parallel.replicate_from_host).
+            if process_group is not None and torch.distributed.get_world_size(process_group) > 2:
+                from ..parallel import replicate_from_host
+
+                y_dev = replicate_from_host(y_true, y_pred.device, process_group)
+                cost = _ops.SigmoidCost.apply(y_dev, y_pred, periodicity, sig, tile_range, reduce_fn)
+            else:
+                cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
         else:
             cost = _ops.SigmoidCost.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
         finite(cost)
