@@ -530,3 +530,51 @@ class DihedralsToCartesian(torch.autograd.Function):
         gd = d2c_bwd_raw(xyz, grad_xyz, ctx.one_way) if need_d else None
         gc = d2c_chain_bwd_raw(cartesian, xyz, grad_xyz, ctx.one_way) if need_c else None
         return gd, gc, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused Cartesian branch: pairwise distances of the selected atoms + cartesian loss (+ clash count)
+# ---------------------------------------------------------------------------------------------------
+CART_VARIANTS = {"mean_abs": 0, "mean_square": 1, "mean_norm": 2}
+
+
+def cartesian_pair_loss_raw(xyz: torch.Tensor, target: torch.Tensor, start=None, stop=None, step=None, variant: str = "mean_abs",
+                            clash_distance: float = 0.0, need_grad: bool = True, need_clashes: bool = False):
+    """One launch: (loss_sum float64[1], d(loss_sum)/d(xyz) (b,n,3) | None, clashes (b) int64 | None).  ``target`` is either the
+    input coordinates (b,n,3) or their flat pair distances (b, n_sel (n_sel-1)/2); ``loss_sum`` is un-normalised (sum over
+    frames and pairs of |diff| / diff^2, or sum over frames of the pair-wise 2-norm)."""
+    require_cuda(xyz, "cartesians")
+    require_cuda(target, "target")
+    xyz, target = f32c(xyz), f32c(target)
+    if xyz.dim() != 3 or xyz.shape[2] != 3:
+        raise EmkError(-4, f"cartesian pair loss needs (b, n_atoms, 3) coordinates, got {tuple(xyz.shape)}")
+    if variant not in CART_VARIANTS:
+        raise ValueError(f"cartesian_cost_variant {variant} not available")
+    loss = torch.zeros(1, dtype=torch.float64, device=xyz.device)
+    grad = torch.empty_like(xyz) if need_grad else None
+    clashes = torch.empty(xyz.shape[0], dtype=torch.int64, device=xyz.device) if need_clashes else None
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_dl_cartesian_pair_loss(DL(xyz), _idx(start), _idx(stop), _idx(step), DL(target), CART_VARIANTS[variant],
+                                                    float(clash_distance), DL(loss), DL(grad), DL(clashes), stream_of(xyz)))
+    return loss, grad, clashes
+
+
+class CartesianPairLoss(torch.autograd.Function):
+    """mean over frames (and pairs) of the cartesian cost between the pair distances of ``xyz`` and of ``target``;
+    forward value and d/d(xyz) come out of the same launch."""
+
+    @staticmethod
+    def forward(ctx, xyz, target, start, stop, step, variant):
+        loss, grad, _ = cartesian_pair_loss_raw(xyz, target, start, stop, step, variant, 0.0, ctx.needs_input_grad[0])
+        n_sel = _slice_count(xyz.shape[1], start, stop, step)
+        count = xyz.shape[0] * (1 if variant == "mean_norm" else max(1, n_sel * (n_sel - 1) // 2))
+        ctx.save_for_backward(grad)
+        ctx.count = count
+        ctx.dtype = xyz.dtype
+        return (loss[0] / count).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        g = None if grad is None else (grad * (grad_output / ctx.count)).to(ctx.dtype)
+        return g, None, None, None, None, None

@@ -1,0 +1,202 @@
+// Fused Cartesian branch of the ADC model:
+//   PairwiseDistances("output")  ->  cartesian_loss  (+ ADCClashMetric)
+// i.e. encodermap/models/layers.py:1252-1267 (atom selection + flat upper-triangle pairwise distances),
+// encodermap/loss_functions/loss_functions.py:1020-1065 (mean |d_in - d_out|, mean square, or mean per-frame norm) and
+// encodermap/callbacks/metrics.py:512-520 (pairs closer than clash_distance), forward AND the gradient w.r.t. the
+// back-mapped coordinates from one launch.  The (frames, n_pairs) matrix of output distances, its gradient, and -- when the
+// input coordinates are passed instead of their distance matrix -- the (frames, n_pairs) input matrix never exist in HBM:
+// per frame the kernel reads 12 bytes per atom and writes 12 bytes per atom instead of moving ~5 x 4 bytes per PAIR
+// (100 C-alpha atoms: 3.6 KB instead of 99 KB per frame; the step's five launches become one).
+//
+// One WARP per frame.  The selected atoms are staged in shared memory (SoA); lane l owns the fixed columns j = l + 32 c
+// (positions and column sums of the gradient in registers), the warp walks the rows i of the upper triangle: x_i is a
+// broadcast read, a stored target row is read coalesced (the pairs (i, j > i) are contiguous in the flat order), the row sum
+// of the gradient is one butterfly reduction per row.  Every pair is visited once.
+#include "emk_common.cuh"
+
+namespace emk {
+
+constexpr int CL_THREADS = 128;   // four frames per CTA
+
+enum CartVariant : int { kMeanAbs = 0, kMeanSquare = 1, kMeanNorm = 2 };
+
+struct CartLossParams {
+  const float* xyz;        // (b, n_atoms, 3) back-mapped coordinates
+  const float* target;     // (b, n_pairs) input pair distances, or (b, n_atoms, 3) input coordinates
+  int64_t b;
+  int n_atoms;
+  int first, ns, step;     // selected atoms: first + a * step, a < ns
+  int target_is_xyz;
+  int variant;
+  float clash2;            // squared clash distance (< 0: no clash count)
+  double* loss_sum;        // += sum over frames of: sum_p |diff| (abs), sum_p diff^2 (square), sqrt(sum_p diff^2) (norm)
+  float* grad_xyz;         // (b, n_atoms, 3) or null: d(loss_sum)/d(xyz), zero for unselected atoms
+  long long* clashes;      // (b) or null
+};
+
+template <int C>
+__global__ void __launch_bounds__(CL_THREADS) cart_pair_loss_kernel(const CartLossParams p) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t frame = (int64_t)blockIdx.x * (CL_THREADS / 32) + warp;
+  const int ns = p.ns;
+  const int per_warp = 9 * ns;                    // out coords [3][ns], in coords [3][ns], row sums [3][ns]
+  float* so = sm + (size_t)warp * per_warp;
+  float* si = so + 3 * ns;
+  float* sr = si + 3 * ns;
+  __shared__ double wsum[CL_THREADS / 32];
+  double frame_loss = 0.0;
+  if (frame < p.b) {
+    const float* xo = p.xyz + frame * (int64_t)(3 * p.n_atoms);
+    const float* xi = p.target_is_xyz ? p.target + frame * (int64_t)(3 * p.n_atoms) : nullptr;
+    for (int a = lane; a < ns; a += 32) {
+      const int at = 3 * (p.first + a * p.step);
+      so[a] = xo[at]; so[ns + a] = xo[at + 1]; so[2 * ns + a] = xo[at + 2];
+      if (xi) { si[a] = xi[at]; si[ns + a] = xi[at + 1]; si[2 * ns + a] = xi[at + 2]; }
+      sr[a] = 0.f; sr[ns + a] = 0.f; sr[2 * ns + a] = 0.f;
+    }
+    __syncwarp();
+    float co[C][3], ci[C][3], ca[C][3];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const int j = 32 * c + lane;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        co[c][k] = j < ns ? so[k * ns + j] : 0.f;
+        ci[c][k] = (xi && j < ns) ? si[k * ns + j] : 0.f;
+        ca[c][k] = 0.f;
+      }
+    }
+    const int64_t n_pairs = (int64_t)ns * (ns - 1) / 2;
+    const float* trow_base = p.target_is_xyz ? nullptr : p.target + frame * n_pairs;
+    const bool want_grad = p.grad_xyz != nullptr;
+    // mean_norm needs the frame's norm before any gradient term: a first sweep sums the squares
+    float inv_norm = 1.f;
+    const int sweeps = p.variant == kMeanNorm ? 2 : 1;
+    float lsum = 0.f;
+    int clash = 0;
+    for (int sweep = 0; sweep < sweeps; sweep++) {
+      const bool grad_sweep = want_grad && sweep == sweeps - 1;
+      const bool loss_sweep = sweep == 0;
+      for (int i = 0; i < ns - 1; i++) {
+        const float xo0 = so[i], xo1 = so[ns + i], xo2 = so[2 * ns + i];
+        float xi0 = 0.f, xi1 = 0.f, xi2 = 0.f;
+        if (xi) { xi0 = si[i]; xi1 = si[ns + i]; xi2 = si[2 * ns + i]; }
+        const float* trow = trow_base ? trow_base + ((int64_t)i * (2 * ns - i - 1) / 2 - i - 1) : nullptr;   // + j
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const int j = 32 * c + lane;
+          if (j > i && j < ns) {
+            const float dx = xo0 - co[c][0], dy = xo1 - co[c][1], dz = xo2 - co[c][2];
+            const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float rinv = s2 >= EMK_TINY ? rsqrt_fast(s2) : 0.f;
+            const float dout = s2 * rinv;                       // pairwise_dist: 0 at zero distance (distances.py:244-253)
+            float din;
+            if (trow) {
+              din = __ldg(trow + j);
+            } else {
+              const float ex = xi0 - ci[c][0], ey = xi1 - ci[c][1], ez = xi2 - ci[c][2];
+              const float t2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+              din = t2 >= EMK_TINY ? t2 * rsqrt_fast(t2) : 0.f;
+            }
+            const float diff = dout - din;                      // the reference forms y_true - y_pred = -(diff): same |.| and square
+            if (loss_sweep) {
+              lsum += p.variant == kMeanAbs ? fabsf(diff) : diff * diff;
+              if (s2 < p.clash2) clash++;
+            }
+            if (grad_sweep) {
+              // d/d(dout): sign(diff) (abs; 0 at 0 as tf.abs), 2 diff (square), diff / norm (norm); d(dout)/dx_i = (x_i - x_j)/dout,
+              // zero at zero distance (the reference's mask)
+              const float w = p.variant == kMeanAbs ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f))
+                                                    : (p.variant == kMeanSquare ? 2.f * diff : diff * inv_norm);
+              const float coef = w * rinv;
+              r0 = fmaf(coef, dx, r0); r1 = fmaf(coef, dy, r1); r2 = fmaf(coef, dz, r2);
+              ca[c][0] = fmaf(-coef, dx, ca[c][0]); ca[c][1] = fmaf(-coef, dy, ca[c][1]); ca[c][2] = fmaf(-coef, dz, ca[c][2]);
+            }
+          }
+        }
+        if (grad_sweep) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            r0 += __shfl_xor_sync(0xffffffffu, r0, d);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, d);
+            r2 += __shfl_xor_sync(0xffffffffu, r2, d);
+          }
+          if (lane == 0) { sr[i] = r0; sr[ns + i] = r1; sr[2 * ns + i] = r2; }
+        }
+      }
+      if (loss_sweep) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+          clash += __shfl_xor_sync(0xffffffffu, clash, d);
+        }
+        if (p.variant == kMeanNorm) {
+          const float nrm = sqrtf(lsum);
+          frame_loss = (double)nrm;
+          inv_norm = nrm > 0.f ? 1.f / nrm : 0.f;               // tf.norm's gradient at 0 is NaN in TensorFlow; 0 here
+        } else {
+          frame_loss = (double)lsum;
+        }
+        if (lane == 0 && p.clashes) p.clashes[frame] = clash;
+      }
+    }
+    if (want_grad) {
+      float* g = p.grad_xyz + frame * (int64_t)(3 * p.n_atoms);
+      // unselected atoms get zero; the whole row is cleared first (coalesced), then the selected atoms are filled in
+      for (int e = lane; e < 3 * p.n_atoms; e += 32) g[e] = 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int j = 32 * c + lane;
+        if (j < ns) {
+          float* o = g + 3 * (p.first + j * p.step);
+          o[0] = ca[c][0] + sr[j]; o[1] = ca[c][1] + sr[ns + j]; o[2] = ca[c][2] + sr[2 * ns + j];
+        }
+      }
+    }
+  }
+  if (lane == 0) wsum[warp] = frame_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < CL_THREADS / 32; w++) t += wsum[w];
+    if (t != 0.0) atomicAdd(p.loss_sum, t);
+  }
+}
+
+int cart_pair_loss_device(const CartLossParams& p, cudaStream_t st) {
+  EMK_REQUIRE(p.xyz && p.target && p.loss_sum, EMK_E_NULL, "emk_cartesian_pair_loss: NULL pointer argument");
+  EMK_REQUIRE(p.b >= 0 && p.n_atoms >= 1 && p.ns >= 0 && p.step >= 1 && p.first >= 0 &&
+                  (p.ns == 0 || p.first + (int64_t)(p.ns - 1) * p.step < p.n_atoms),
+              EMK_E_SHAPE, "emk_cartesian_pair_loss: atom selection (first %d, count %d, step %d) outside %d atoms", p.first, p.ns, p.step,
+              p.n_atoms);
+  EMK_REQUIRE(p.variant >= 0 && p.variant <= 2, EMK_E_ARG, "emk_cartesian_pair_loss: variant must be 0 (mean_abs), 1 (mean_square) or 2 (mean_norm)");
+  EMK_REQUIRE(p.ns <= 320, EMK_E_UNSUPPORTED, "emk_cartesian_pair_loss: more than 320 selected atoms per frame (got %d)", p.ns);
+  if (p.b == 0) return EMK_OK;
+  if (p.ns < 2) {   // no pairs: zero loss, zero gradient
+    if (p.grad_xyz) EMK_CUDA(cudaMemsetAsync(p.grad_xyz, 0, (size_t)p.b * p.n_atoms * 3 * sizeof(float), st));
+    if (p.clashes) EMK_CUDA(cudaMemsetAsync(p.clashes, 0, (size_t)p.b * sizeof(long long), st));
+    return EMK_OK;
+  }
+  const size_t smem = (size_t)(CL_THREADS / 32) * 9 * p.ns * sizeof(float);
+  const unsigned grid = (unsigned)((p.b + CL_THREADS / 32 - 1) / (CL_THREADS / 32));
+#define EMK_CL(CC)                                                                                                        \
+  do {                                                                                                                    \
+    static bool cfg[kMaxDevices] = {false};                                                                               \
+    if (first_use_on_device(cfg))                                                                                         \
+      EMK_CUDA(cudaFuncSetAttribute(cart_pair_loss_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));  \
+    cart_pair_loss_kernel<CC><<<grid, CL_THREADS, smem, st>>>(p);                                                         \
+  } while (0)
+  if (p.ns <= 32) EMK_CL(1);
+  else if (p.ns <= 64) EMK_CL(2);
+  else if (p.ns <= 128) EMK_CL(4);
+  else if (p.ns <= 192) EMK_CL(6);
+  else EMK_CL(10);
+#undef EMK_CL
+  return launch_status("cart_pair_loss_kernel");
+}
+
+}  // namespace emk

@@ -98,6 +98,20 @@ int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int6
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
 int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
 int fp32_probe_device(double*);
+struct CartLossParams {
+  const float* xyz;
+  const float* target;
+  int64_t b;
+  int n_atoms;
+  int first, ns, step;
+  int target_is_xyz;
+  int variant;
+  float clash2;
+  double* loss_sum;
+  float* grad_xyz;
+  long long* clashes;
+};
+int cart_pair_loss_device(const CartLossParams&, cudaStream_t);
 int64_t fwd6_min_batch();
 void set_fwd6_min_batch(int64_t);
 int64_t fwd6_warps();
@@ -444,6 +458,58 @@ int emk_dl_pairwise_dist_bwd(const DLManagedTensor* x, int64_t start, int64_t st
   EMK_REQUIRE(gv.numel == want, EMK_E_SHAPE, "emk_dl_pairwise_dist_bwd: grad_out has %lld elements, expected %lld", (long long)gv.numel, (long long)want);
   EMK_REQUIRE(gx.numel == xv.numel, EMK_E_SHAPE, "emk_dl_pairwise_dist_bwd: grad_x shape differs from positions");
   return emk_pairwise_dist_bwd(F(xv) + first, b, n, d, bs, rs, squared, flat, F(gv), F(gx) + first, stream);
+}
+
+// ---- fused Cartesian branch: pairwise distances of selected atoms + cartesian loss (+ clash count), forward and gradient ---------
+int emk_cartesian_pair_loss(const float* xyz, int64_t b, int64_t n_atoms, int64_t first, int64_t count, int64_t step, const float* target,
+                            int target_is_xyz, int variant, float clash_distance, double* loss_sum, float* grad_xyz, int64_t* clashes,
+                            void* stream) {
+  EMK_REQUIRE(n_atoms >= 1 && n_atoms < (1 << 24) && count >= 0 && count < (1 << 24) && step >= 1 && step < (1 << 24) && first >= 0 &&
+                  first < (1 << 24),
+              EMK_E_SHAPE, "emk_cartesian_pair_loss: bad selection / atom count");
+  CartLossParams p{xyz, target, b, (int)n_atoms, (int)first, (int)count, (int)step, target_is_xyz, variant,
+                   clash_distance > 0.f ? clash_distance * clash_distance : -1.f, loss_sum, grad_xyz, reinterpret_cast<long long*>(clashes)};
+  return cart_pair_loss_device(p, as_stream(stream));
+}
+int emk_dl_cartesian_pair_loss(const DLManagedTensor* xyz, int64_t start, int64_t stop, int64_t step, const DLManagedTensor* target, int variant,
+                               float clash_distance, DLManagedTensor* loss_sum, DLManagedTensor* grad_xyz, DLManagedTensor* clashes,
+                               void* stream) {
+  VIEW(xv, xyz, "xyz", 3, 3);
+  EMK_REQUIRE(xv.shape[2] == 3, EMK_E_SHAPE, "emk_dl_cartesian_pair_loss: xyz must be (b, n_atoms, 3)");
+  const int64_t b = xv.shape[0], n = xv.shape[1];
+  int64_t first, cnt, st;
+  int rc = resolve_slice(n, start, stop, step, &first, &cnt, &st);
+  if (rc) return rc;
+  VIEW(tv, target, "target", 2, 3);
+  int is_xyz;
+  if (tv.ndim == 3) {
+    EMK_REQUIRE(tv.shape[0] == b && tv.shape[1] == n && tv.shape[2] == 3, EMK_E_SHAPE, "emk_dl_cartesian_pair_loss: input coordinates must be (b, n_atoms, 3)");
+    is_xyz = 1;
+  } else {
+    EMK_REQUIRE(tv.shape[0] == b && tv.shape[1] == cnt * (cnt - 1) / 2, EMK_E_SHAPE,
+                "emk_dl_cartesian_pair_loss: input pair distances must be (b, %lld) for %lld selected atoms, got (%lld, %lld)",
+                (long long)(cnt * (cnt - 1) / 2), (long long)cnt, (long long)tv.shape[0], (long long)tv.shape[1]);
+    is_xyz = 0;
+  }
+  View lv;
+  rc = view_of(loss_sum, "loss_sum", kDLFloat, 64, 0, 1, &lv);
+  if (rc) return rc;
+  EMK_REQUIRE(lv.numel == 1, EMK_E_SHAPE, "emk_dl_cartesian_pair_loss: loss_sum must hold exactly one float64");
+  float* g = nullptr;
+  if (grad_xyz) {
+    VIEW(gv, grad_xyz, "grad_xyz", 3, 3);
+    EMK_REQUIRE(gv.numel == xv.numel, EMK_E_SHAPE, "emk_dl_cartesian_pair_loss: grad_xyz shape differs from xyz");
+    g = F(gv);
+  }
+  int64_t* cl = nullptr;
+  if (clashes) {
+    View cv;
+    rc = view_of(clashes, "clashes", kDLInt, 64, 1, 1, &cv);
+    if (rc) return rc;
+    EMK_REQUIRE(cv.numel == b, EMK_E_SHAPE, "emk_dl_cartesian_pair_loss: clashes must be (b) int64");
+    cl = static_cast<int64_t*>(cv.data);
+  }
+  return emk_cartesian_pair_loss(F(xv), b, n, first, cnt, st, F(tv), is_xyz, variant, clash_distance, static_cast<double*>(lv.data), g, cl, stream);
 }
 
 // ---- elementwise ---------------------------------------------------------------------------------------------------------

@@ -180,3 +180,40 @@ def cartesian_distance_loss(model, parameters=None, callback=None, *, process_gr
 
     cartesian_distance_loss_func.flush_finite_check = finite.flush
     return cartesian_distance_loss_func
+
+
+def fused_cartesian_loss(model=None, scale_callback=None, parameters=None, log_callback=None, *, check_finite="deferred") -> Callable:
+    """The Cartesian branch of the ADC step as ONE op: ``PairwiseDistances`` on the back-mapped coordinates + ``cartesian_loss``
+    (reference: encodermap/models/layers.py:1252-1267 + encodermap/loss_functions/loss_functions.py:947-1067, called as
+    ``cartesian_loss_func(inp_pair, out_pair)`` in models/models.py:2385-2387).
+
+    ``f(y_true, out_cartesians)``: ``out_cartesians`` are the BackMapLayer output (b, n_atoms, 3); ``y_true`` is either the
+    input coordinates (b, n_atoms, 3) -- their pair distances are then formed on the fly -- or the stored input pair distances
+    (b, n_pairs), as the reference passes them.  Atom selection (``cartesian_pwd_start/stop/step``), cost variant
+    (``cartesian_cost_variant``), ``cartesian_cost_reference`` and the current scale (``scale_callback.current_cartesian_cost_scale``
+    or ``cartesian_cost_scale``) follow the reference.  Neither (b, n_pairs) matrix of the output side exists in memory;
+    d(cost)/d(out_cartesians) comes out of the same launch and feeds ``BackMapLayer``'s backward."""
+    p = ADCParameters() if parameters is None else parameters
+    finite = _FiniteCheck(check_finite, "Cartesian cost became infinite or NaN.")
+
+    def cartesian_loss_func(y_true: torch.Tensor, out_cartesians: torch.Tensor) -> torch.Tensor:
+        scale = scale_callback.current_cartesian_cost_scale if scale_callback is not None else p.cartesian_cost_scale
+        cost = _ops.CartesianPairLoss.apply(out_cartesians, y_true, p.cartesian_pwd_start, p.cartesian_pwd_stop, p.cartesian_pwd_step,
+                                            p.cartesian_cost_variant)
+        cost = cost / getattr(p, "cartesian_cost_reference", 1) * scale
+        finite(cost)
+        return cost
+
+    cartesian_loss_func.flush_finite_check = finite.flush
+    return cartesian_loss_func
+
+
+def clash_count(cartesians: torch.Tensor, clash_distance: float = 0.1, parameters=None) -> torch.Tensor:
+    """Pairs of (selected) atoms closer than ``clash_distance`` per frame, (b) int64: the quantity ``ADCClashMetric.update_state``
+    logs (reference: encodermap/callbacks/metrics.py:512-520, 0.1 nm for C-alpha selections) without the (b, n_pairs) matrix.
+    The metric looks at ALL atoms the output layer produced unless ``parameters`` carries a selection."""
+    start = stop = step = None
+    if parameters is not None:
+        start, stop, step = parameters.cartesian_pwd_start, parameters.cartesian_pwd_stop, parameters.cartesian_pwd_step
+    _, _, clashes = _ops.cartesian_pair_loss_raw(cartesians, cartesians, start, stop, step, "mean_abs", clash_distance, False, True)
+    return clashes

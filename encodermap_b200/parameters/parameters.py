@@ -46,6 +46,7 @@ class ADCParameters(Parameters):
         use_sidechains=False,
         cartesian_cost_scale=1,
         cartesian_cost_variant="mean_abs",
+        cartesian_cost_reference=1,
         cartesian_dist_sig_parameters=Parameters._defaults["dist_sig_parameters"],
         cartesian_distance_cost_scale=1,
         auto_cost_scale=None,

@@ -149,6 +149,29 @@ EMK_API int emk_dl_pairwise_dist_bwd(const DLManagedTensor* x, int64_t start, in
                              const DLManagedTensor* grad_out, DLManagedTensor* grad_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused Cartesian branch of the ADC model: PairwiseDistances("output") -> cartesian_loss (+ ADCClashMetric),
+ * forward and gradient w.r.t. the coordinates in ONE launch; the (b, n_pairs) distance matrices never exist in HBM.
+ *   replaces, as a unit, PairwiseDistances.call (encodermap/models/layers.py:1252-1267) on the back-mapped coordinates,
+ *   cartesian_loss_func (encodermap/loss_functions/loss_functions.py:1020-1065) and the clash count of ADCClashMetric.update_state
+ *   (encodermap/callbacks/metrics.py:512-520) -- the caller, ADCFunctionalModel.get_loss (encodermap/models/models.py:2385-2387),
+ *   passes the two coordinate tensors instead of the two distance matrices.
+ *   xyz (b,n_atoms,3) back-mapped coordinates; selected atoms first + a * step, a < count (inputs[:, start:stop:step])
+ *   target       target_is_xyz = 1: input coordinates (b,n_atoms,3) (their pair distances are formed on the fly)
+ *                target_is_xyz = 0: input pair distances (b, count (count-1)/2) in emk_triu_pair_indices order
+ *   variant      0 mean_abs, 1 mean_square, 2 mean_norm (p.cartesian_cost_variant)
+ *   loss_sum     device double[1]: += sum over frames and pairs of |d_in - d_out| (0), (d_in - d_out)^2 (1), or sum over frames of
+ *                the 2-norm over pairs (2); the caller divides by the element count and applies cost_reference / scale
+ *   grad_xyz     (b,n_atoms,3) or NULL: d(loss_sum)/d(xyz), zero for unselected atoms (written, not accumulated)
+ *   clashes      (b) int64 or NULL: pairs closer than clash_distance per frame (clash_distance <= 0: not counted)
+ * ---------------------------------------------------------------------------------------- */
+EMK_API int emk_cartesian_pair_loss(const float* xyz, int64_t b, int64_t n_atoms, int64_t first, int64_t count, int64_t step,
+                                    const float* target, int target_is_xyz, int variant, float clash_distance, double* loss_sum,
+                                    float* grad_xyz, int64_t* clashes, void* stream);
+EMK_API int emk_dl_cartesian_pair_loss(const DLManagedTensor* xyz, int64_t start, int64_t stop, int64_t step, const DLManagedTensor* target,
+                                       int variant, float clash_distance, DLManagedTensor* loss_sum, DLManagedTensor* grad_xyz,
+                                       DLManagedTensor* clashes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Elementwise ops
  * ---------------------------------------------------------------------------------------- */
 

@@ -1038,3 +1038,52 @@ def test_backmap_lane_per_frame_nan_and_partial_tiles(em):
     ok = ~bad
     ref = O.back_map_layer(torch.from_numpy(np.repeat(lengths, b, 0)).double(), torch.from_numpy(ang).double(), torch.from_numpy(dih).double()).numpy()
     assert np.abs(got[ok] - ref[ok]).max() < COORD_ATOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused Cartesian branch: PairwiseDistances + cartesian_loss + clash count in one launch
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,b,sel,variant", [(30, 5, (1, None, 3), "mean_abs"), (300, 9, (1, None, 3), "mean_abs"), (300, 3, (None, None, None), "mean_abs"),
+                                              (90, 6, (2, 80, 4), "mean_square"), (45, 7, (None, None, None), "mean_norm"),
+                                              (300, 4, (1, None, 3), "mean_norm"), (600, 2, (1, None, 3), "mean_square")])
+def test_fused_cartesian_loss(em, n, b, sel, variant):
+    from encodermap_b200 import ADCParameters
+    from encodermap_b200.loss_functions.loss_functions import clash_count, fused_cartesian_loss
+
+    rng = np.random.default_rng(n * 7 + b)
+    # two conformations per frame: the "input" coordinates and the "back-mapped" ones (a chain-like random walk, 0.38 nm steps)
+    def walk():
+        steps = rng.normal(size=(b, n, 3))
+        steps /= np.linalg.norm(steps, axis=2, keepdims=True)
+        return np.cumsum(0.15 * steps, axis=1).astype(np.float32)
+
+    x_in, x_out = walk(), walk()
+    x_out[0, 4] = x_out[0, 1]          # a zero distance between two selected atoms (1 and 4 for start 1 step 3): masked, no NaN
+    p = ADCParameters(cartesian_pwd_start=sel[0], cartesian_pwd_stop=sel[1], cartesian_pwd_step=sel[2], cartesian_cost_variant=variant,
+                      cartesian_cost_scale=2.5, cartesian_cost_reference=0.7)
+    f = fused_cartesian_loss(None, None, p)
+    # float64 oracle of the unfused composition (reference layers.py:1252-1267 + loss_functions.py:1020-1065)
+    xo = torch.from_numpy(x_out).double().requires_grad_(True)
+    d_out = O.pairwise_distances_layer(xo, *sel)
+    d_in = O.pairwise_distances_layer(torch.from_numpy(x_in).double(), *sel)
+    if variant == "mean_abs":
+        ref = (d_in - d_out).abs().mean()
+    elif variant == "mean_square":
+        ref = ((d_in - d_out) ** 2).mean()
+    else:
+        ref = torch.linalg.norm(d_in - d_out, dim=1).mean()
+    ref = ref / 0.7 * 2.5
+    ref.backward()
+    for target in (cu(x_in), cu(d_in.numpy())):          # input coordinates, or the stored pair matrix as the reference passes it
+        xg = cu(x_out).requires_grad_(True)
+        loss = f(target, xg)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-5)
+        assert relnorm(xg.grad.cpu().numpy(), xo.grad.numpy()) < 5e-5
+        unsel = np.ones(n, bool)
+        unsel[slice(*sel)] = False
+        assert not xg.grad.cpu().numpy()[:, unsel].any()      # unselected atoms: exactly zero
+    # clash count of the metric (all pairs of the selection closer than 0.1 nm ... here 0.3 to have some)
+    got = clash_count(cu(x_out), 0.3, p).cpu().numpy()
+    want = (d_out.detach().numpy() < 0.3).sum(axis=1)
+    assert np.array_equal(got, want)

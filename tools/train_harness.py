@@ -24,6 +24,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from encodermap_b200 import ADCParameters, Parameters, parallel  # noqa: E402
 from encodermap_b200.graph import graphed_train_step  # noqa: E402
 from encodermap_b200.loss_functions import cartesian_distance_loss, distance_loss  # noqa: E402
+from encodermap_b200.loss_functions.loss_functions import fused_cartesian_loss  # noqa: E402
 from encodermap_b200.misc.distances import periodic_distance  # noqa: E402
 from encodermap_b200.models.layers import BackMapLayer, PairwiseDistances, PeriodicInput  # noqa: E402
 
@@ -77,8 +78,11 @@ class EncoderMapStep(nn.Module):
 
 
 class ADCStep(nn.Module):
-    def __init__(self, n_atoms: int, p: ADCParameters, dp_group=None):
+    def __init__(self, n_atoms: int, p: ADCParameters, dp_group=None, fused_cartesian: bool = False):
+        """fused_cartesian: PairwiseDistances("output") + cartesian_loss as one launch (loss_functions.fused_cartesian_loss)
+        instead of the reference's two layers + elementwise loss."""
         super().__init__()
+        self.fused_cartesian = fused_cartesian
         self.p = p
         self.n = n_atoms
         d_in = 2 * ((n_atoms - 2) + (n_atoms - 3))
@@ -89,6 +93,7 @@ class ADCStep(nn.Module):
         self.backmap = BackMapLayer(n_atoms // 2 - 1, (n_atoms - 3) // 2)
         self.pairwise = PairwiseDistances(p, "pairwise")
         self.cart_dist_loss = cartesian_distance_loss(self, p, process_group=dp_group, data_parallel=dp_group is not None)
+        self.fused_loss = fused_cartesian_loss(None, None, p)
         self.dp_group = dp_group
 
     def encoder(self, inputs, training=False):
@@ -108,10 +113,13 @@ class ADCStep(nn.Module):
             distances = (lengths / torch.distributed.get_world_size(self.dp_group)).expand_as(distances)
         back = self.backmap((distances, out_angles, out_dihedrals))
         inp_pair = self.pairwise(cartesians)
-        out_pair = self.pairwise(back)
         dihedral_loss = periodic_distance(dihedrals, out_dihedrals, self.p.periodicity).mean()
         angle_loss = periodic_distance(angles, out_angles, self.p.periodicity).mean()
-        cartesian_loss = (inp_pair - out_pair).abs().mean()
+        if self.fused_cartesian:
+            cartesian_loss = self.fused_loss(cartesians, back)
+        else:
+            out_pair = self.pairwise(back)
+            cartesian_loss = (inp_pair - out_pair).abs().mean()
         reg = sum((m.weight ** 2).sum() for m in self.modules() if isinstance(m, nn.Linear)) * self.p.l2_reg_constant
         center = (z ** 2).mean() * self.p.center_cost_scale
         return dihedral_loss + angle_loss + cartesian_loss + self.cart_dist_loss(inp_pair, z) + center + reg
@@ -187,6 +195,10 @@ def run_all(dev, steps=20):
         # configs[2]: ADC, 100-residue chain, batch 1024
         "train_cfg2_adc_100res_batch1024":
             (lambda: ADCStep(n, ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True)),
+             lambda it: (ang, dih, cart, dist)),
+        # same with the Cartesian branch fused
+        "train_cfg2_adc_100res_batch1024_fused_cartesian":
+            (lambda: ADCStep(n, ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True), fused_cartesian=True),
              lambda it: (ang, dih, cart, dist)),
     }
     for name, (make, batch_fn) in cases.items():
