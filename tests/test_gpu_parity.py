@@ -1051,11 +1051,13 @@ def test_fused_cartesian_loss(em, n, b, sel, variant):
     from encodermap_b200.loss_functions.loss_functions import clash_count, fused_cartesian_loss
 
     rng = np.random.default_rng(n * 7 + b)
-    # two conformations per frame: the "input" coordinates and the "back-mapped" ones (a chain-like random walk, 0.38 nm steps)
+    # two conformations per frame: the "input" coordinates and the "back-mapped" ones (a chain-like random walk).  The step
+    # LENGTHS vary: with equal bond lengths in both walks every adjacent pair would have d_in == d_out up to rounding, and the
+    # sign(d_out - d_in) that mean_abs differentiates through would be noise in float32 and float64 alike
     def walk():
         steps = rng.normal(size=(b, n, 3))
-        steps /= np.linalg.norm(steps, axis=2, keepdims=True)
-        return np.cumsum(0.15 * steps, axis=1).astype(np.float32)
+        steps *= rng.uniform(0.12, 0.18, size=(b, n, 1)) / np.linalg.norm(steps, axis=2, keepdims=True)
+        return np.cumsum(steps, axis=1).astype(np.float32)
 
     x_in, x_out = walk(), walk()
     x_out[0, 4] = x_out[0, 1]          # a zero distance between two selected atoms (1 and 4 for start 1 step 3): masked, no NaN

@@ -30,10 +30,11 @@ def raw(rep):
 
 
 def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     OUT.mkdir(exist_ok=True)
-    lines = ["# ncu --set full --clock-control none summaries, round 1 (B200, sm_100a). Source: tools/profile_r1.sh + tools/profile_summarise.py", ""]
+    lines = [f"# ncu --set full --clock-control none summaries, round {tag[1:]} (B200, sm_100a). Source: tools/profile_{tag[0]}{int(tag[1:])}.sh + tools/profile_summarise.py", ""]
     traffic = None
-    for name in ("r01_pair_tile", "r01_backmap"):
+    for name in sorted(p.stem for p in GP.glob(f"{tag}_*.ncu-rep")):
         rep = GP / f"{name}.ncu-rep"
         if not rep.exists():
             continue
@@ -56,13 +57,13 @@ def main():
                     return float(vals[key]) * scale
                 traffic = {"kernel": kn, "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum")}
                 traffic["dram_bytes_per_launch"] = traffic["dram_bytes_read"] + traffic["dram_bytes_write"]
-                traffic["source"] = "ncu --set full, one launch of the bench.py workload (65536 x 1024), tools/profile_r1.sh"
-    (OUT / "r01_ncu_summary.txt").write_text("\n".join(lines) + "\n")
+                traffic["source"] = "ncu --set full, one launch of the bench.py workload (65536 x 1024), tools/profile_" + tag[0] + str(int(tag[1:])) + ".sh"
+    (OUT / f"{tag}_ncu_summary.txt").write_text("\n".join(lines) + "\n")
     if traffic:
-        (OUT / "r01_pair_tile_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
-    if (GP / "r01_launches.csv").exists():
-        shutil.copy(GP / "r01_launches.csv", OUT / "r01_launches.csv")
-    print("wrote", sorted(p.name for p in OUT.glob("r01_*")))
+        (OUT / f"{tag}_pair_tile_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    if (GP / f"{tag}_launches.csv").exists():
+        shutil.copy(GP / f"{tag}_launches.csv", OUT / f"{tag}_launches.csv")
+    print("wrote", sorted(p.name for p in OUT.glob(f"{tag}_*")))
 
 
 if __name__ == "__main__":

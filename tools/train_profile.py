@@ -1,4 +1,4 @@
-"""Eager training steps of the harness for an ncu launch list (python tools/train_profile.py cfg1|adc)."""
+"""Eager training steps of the harness for an ncu launch list (python tools/train_profile.py cfg1|adc|adc_fused)."""
 import math
 import sys
 from pathlib import Path
@@ -22,6 +22,6 @@ else:
     dih = (torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi
     with torch.no_grad():
         cart = H.BackMapLayer(n // 2 - 1, (n - 3) // 2)((dist, ang, dih))
-    m = H.ADCStep(n, H.ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True)).to(dev)
+    m = H.ADCStep(n, H.ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True), fused_cartesian=(which == "adc_fused")).to(dev)
     batch = (ang, dih, cart, dist)
 print(H.time_steps(m, lambda it: batch, steps=3, warmup=2))
