@@ -651,6 +651,181 @@ __global__ void pairwise_small_bwd_kernel(const float* __restrict__ x, int64_t b
   }
 }
 
+// ---- PairwiseDistances layer, up to 128 selected atoms (the C-alpha selections of the ADC models): one WARP per frame ----
+// Lane l owns the fixed columns j = 32 c + l (C = ceil(n / 32) chunks), positions in registers; the warp walks the rows i of
+// the strict upper triangle, x_i is one broadcast LDS.128, and chunks that lie entirely on or below the diagonal are
+// skipped (warp-uniform).  Two chunks are processed per instruction with the packed FADD2 / FMUL2 / FFMA2 forms.  The
+// outputs of a row are contiguous in the flat order, so every store (forward) or load of the upstream gradient (backward)
+// is one contiguous run per chunk, addressed from ONE per-lane pointer with the chunk as an immediate offset.  No index
+// table, no per-element decode, no barrier: ~12 instructions per two chunk visits.
+constexpr int PWW_THREADS = 128;
+constexpr int PWW_MAX_N = 128;
+
+__device__ __forceinline__ float sqrt_fast(float x) {   // one MUFU.SQRT (2 ulp), exact 0 at 0; no denormal fix-up
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <int C, bool SQUARED>
+__global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                          int64_t rstride, float* __restrict__ out) {
+  __shared__ float4 sx4[PWW_THREADS / 32][PWW_MAX_N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = n * (n - 1) / 2;
+  float4* sx = sx4[warp];
+  for (int64_t f = (int64_t)blockIdx.x * (PWW_THREADS / 32) + warp; f < b; f += (int64_t)gridDim.x * (PWW_THREADS / 32)) {
+    const float* xb = x + f * bstride;
+    float nx[C], ny[C], nz[C];       // -x_j of this lane's columns
+    int jj[C];                       // the column, or -1 beyond the last atom (never "right of the diagonal")
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const int j = 32 * c + lane;
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (j < n) {
+        const float* a = xb + (int64_t)j * rstride;
+        vx = a[0]; vy = a[1]; vz = a[2];
+        sx[j] = make_float4(vx, vy, vz, 0.f);
+      }
+      nx[c] = -vx; ny[c] = -vy; nz[c] = -vz;
+      jj[c] = j < n ? j : -1;
+    }
+    __syncwarp();
+    float* orow = out + f * per - 1 + lane;   // orow[32 c] is the element (i, 32 c + lane) of the current row
+#pragma unroll 1
+    for (int i = 0; i < n - 1; i++) {
+      const float4 xi = sx[i];
+#pragma unroll
+      for (int c = 0; c + 1 < C; c += 2) {
+        if (32 * c + 63 <= i) continue;    // both chunks lie on or below the diagonal
+        const float2 dx = __fadd2_rn(make_float2(xi.x, xi.x), make_float2(nx[c], nx[c + 1]));
+        const float2 dy = __fadd2_rn(make_float2(xi.y, xi.y), make_float2(ny[c], ny[c + 1]));
+        const float2 dz = __fadd2_rn(make_float2(xi.z, xi.z), make_float2(nz[c], nz[c + 1]));
+        const float2 s2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+        const float v0 = SQUARED ? s2.x : sqrt_fast(s2.x), v1 = SQUARED ? s2.y : sqrt_fast(s2.y);
+        if (jj[c] > i) orow[32 * c] = v0;
+        if (jj[c + 1] > i) orow[32 * c + 32] = v1;
+      }
+      if (C & 1) {
+        constexpr int c = C - 1;
+        const float dx = xi.x + nx[c], dy = xi.y + ny[c], dz = xi.z + nz[c];
+        const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float v = SQUARED ? s2 : sqrt_fast(s2);
+        if (jj[c] > i) orow[32 * c] = v;
+      }
+      orow += n - i - 2;
+    }
+  }
+}
+
+// backward of the same: grad_x[a] = sum_b coef_ab (x_a - x_b), coef = g / dist (2 g when squared), 0 at zero distance.
+// Every pair is visited once: its contribution to the COLUMN atom accumulates in the owning lane's registers; the
+// contributions to the ROW atom are per-lane partial sums that have to be added across the warp -- not by a butterfly per
+// row (30 instructions for three values) but through shared memory, 32 rows at a time: every lane stores its three partials
+// of a row (conflict-free), and after 32 rows lane l adds up row l with eight LDS.128 per component.
+constexpr int PWW_RPAD = 36;   // floats per row of the transpose tile: 16-byte aligned rows, conflict-free LDS.128 per quarter-warp
+
+template <int C, bool SQUARED>
+__global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                              int64_t rstride, const float* __restrict__ go,
+                                                                              float* __restrict__ gx) {
+  extern __shared__ __align__(16) float smw[];
+  constexpr int PER_WARP = 4 * PWW_MAX_N + 3 * PWW_MAX_N + 3 * 32 * PWW_RPAD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* sx = reinterpret_cast<float4*>(smw + (size_t)warp * PER_WARP);
+  float* sr = smw + (size_t)warp * PER_WARP + 4 * PWW_MAX_N;     // [3][PWW_MAX_N] row sums
+  float* tr = sr + 3 * PWW_MAX_N;                                 // [3][32][PWW_RPAD] transpose tile
+  const int per = n * (n - 1) / 2;
+  for (int64_t f = (int64_t)blockIdx.x * (PWW_THREADS / 32) + warp; f < b; f += (int64_t)gridDim.x * (PWW_THREADS / 32)) {
+    const float* xb = x + f * bstride;
+    float nx[C], ny[C], nz[C], ax[C], ay[C], az[C];   // -x_j and the column sums of +coef * d (subtracted at the end)
+    int jj[C];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const int j = 32 * c + lane;
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (j < n) {
+        const float* a = xb + (int64_t)j * rstride;
+        vx = a[0]; vy = a[1]; vz = a[2];
+        sx[j] = make_float4(vx, vy, vz, 0.f);
+      }
+      nx[c] = -vx; ny[c] = -vy; nz[c] = -vz;
+      ax[c] = ay[c] = az[c] = 0.f;
+      jj[c] = j < n ? j : -1;
+    }
+    if (lane < 3) sr[lane * PWW_MAX_N + n - 1] = 0.f;   // the last atom has no row
+    __syncwarp();
+    const float* grow = go + f * per - 1 + lane;    // grow[32 c] is the element (i, 32 c + lane) of the current row
+    // g / dist as g * rsqrt(max(s2, tiny)): a masked lane (g = 0) and a zero distance (d = 0 multiplies it) both give 0
+    auto coef_of = [](float g, float s2) { return SQUARED ? 2.f * g : g * rsqrt_fast(fmaxf(s2, EMK_TINY)); };
+#pragma unroll 1
+    for (int i0 = 0; i0 < n - 1; i0 += 32) {
+      const int rows = min(32, n - 1 - i0);
+#pragma unroll 1
+      for (int ii = 0; ii < rows; ii++) {
+        const int i = i0 + ii;
+        const float4 xi = sx[i];
+        float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
+#pragma unroll
+        for (int c = 0; c + 1 < C; c += 2) {
+          if (32 * c + 63 <= i) continue;
+          const float g0 = jj[c] > i ? __ldg(grow + 32 * c) : 0.f;
+          const float g1 = jj[c + 1] > i ? __ldg(grow + 32 * c + 32) : 0.f;
+          const float2 dx = __fadd2_rn(make_float2(xi.x, xi.x), make_float2(nx[c], nx[c + 1]));
+          const float2 dy = __fadd2_rn(make_float2(xi.y, xi.y), make_float2(ny[c], ny[c + 1]));
+          const float2 dz = __fadd2_rn(make_float2(xi.z, xi.z), make_float2(nz[c], nz[c + 1]));
+          const float2 s2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+          const float2 cf = make_float2(coef_of(g0, s2.x), coef_of(g1, s2.y));
+          r0 = __ffma2_rn(cf, dx, r0); r1 = __ffma2_rn(cf, dy, r1); r2 = __ffma2_rn(cf, dz, r2);
+          float2 t;
+          t = __ffma2_rn(cf, dx, make_float2(ax[c], ax[c + 1])); ax[c] = t.x; ax[c + 1] = t.y;
+          t = __ffma2_rn(cf, dy, make_float2(ay[c], ay[c + 1])); ay[c] = t.x; ay[c + 1] = t.y;
+          t = __ffma2_rn(cf, dz, make_float2(az[c], az[c + 1])); az[c] = t.x; az[c + 1] = t.y;
+        }
+        float q0 = r0.x + r0.y, q1 = r1.x + r1.y, q2 = r2.x + r2.y;
+        if (C & 1) {
+          constexpr int c = C - 1;
+          const float g = jj[c] > i ? __ldg(grow + 32 * c) : 0.f;
+          const float dx = xi.x + nx[c], dy = xi.y + ny[c], dz = xi.z + nz[c];
+          const float cf = coef_of(g, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+          q0 = fmaf(cf, dx, q0); q1 = fmaf(cf, dy, q1); q2 = fmaf(cf, dz, q2);
+          ax[c] = fmaf(cf, dx, ax[c]); ay[c] = fmaf(cf, dy, ay[c]); az[c] = fmaf(cf, dz, az[c]);
+        }
+        tr[(0 * 32 + ii) * PWW_RPAD + lane] = q0;
+        tr[(1 * 32 + ii) * PWW_RPAD + lane] = q1;
+        tr[(2 * 32 + ii) * PWW_RPAD + lane] = q2;
+        grow += n - i - 2;
+      }
+      __syncwarp();
+      if (lane < rows) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const float4* rowp = reinterpret_cast<const float4*>(tr + (k * 32 + lane) * PWW_RPAD);
+          float4 acc = rowp[0];
+#pragma unroll
+          for (int q = 1; q < 8; q++) {
+            const float4 v = rowp[q];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          sr[k * PWW_MAX_N + i0 + lane] = (acc.x + acc.y) + (acc.z + acc.w);
+        }
+      }
+      __syncwarp();
+    }
+    float* gb = gx + f * bstride;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const int j = 32 * c + lane;
+      if (j < n) {
+        float* o = gb + (int64_t)j * rstride;
+        o[0] = sr[j] - ax[c]; o[1] = sr[PWW_MAX_N + j] - ay[c]; o[2] = sr[2 * PWW_MAX_N + j] - az[c];
+      }
+    }
+  }
+}
+
 // ---- host launchers -------------------------------------------------------------------------------------------
 int periodic_distance_device(const float* a, const float* b, int64_t count, double P, float* out, cudaStream_t st) {
   EMK_REQUIRE(a && b && out, EMK_E_NULL, "emk_periodic_distance: NULL pointer argument");
@@ -742,6 +917,21 @@ int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64
                           int flat, float* out, cudaStream_t st) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
   if (b * per == 0) return EMK_OK;
+  if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) {
+    // one warp per frame; grid sized for whole waves of resident CTAs
+    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 16);
+#define EMK_PWW(CC)                                                                                                      \
+  do {                                                                                                                   \
+    if (squared) pairwise_flat3_warp_kernel<CC, true><<<grid, PWW_THREADS, 0, st>>>(x, b, (int)n, bstride, rstride, out); \
+    else pairwise_flat3_warp_kernel<CC, false><<<grid, PWW_THREADS, 0, st>>>(x, b, (int)n, bstride, rstride, out);        \
+  } while (0)
+    if (n <= 32) EMK_PWW(1);
+    else if (n <= 64) EMK_PWW(2);
+    else if (n <= 96) EMK_PWW(3);
+    else EMK_PWW(4);
+#undef EMK_PWW
+    return launch_status("pairwise_flat3_warp_kernel");
+  }
   if (flat && d == 3 && n >= 2 && n <= 8192) {
     if (n <= PWT_MAX_N) {
       const int64_t per3 = n * (n - 1) / 2;
@@ -770,6 +960,25 @@ int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, i
   if (b * n == 0) return EMK_OK;
   // 129 .. 320 atoms: pair-once kernel (2.5x the thread-per-atom kernel at 300 atoms); up to 128 atoms the whole
   // upstream gradient of a frame fits in shared memory next to the coordinates and the thread-per-atom kernel is as fast
+  if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) {
+    constexpr size_t smem = (size_t)(PWW_THREADS / 32) * (7 * PWW_MAX_N + 3 * 32 * PWW_RPAD) * sizeof(float);   // 69.6 KB: 3 CTAs / SM
+    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 3);
+#define EMK_PWWB(CC, SQ)                                                                                                             \
+  do {                                                                                                                               \
+    static bool cfg[kMaxDevices] = {false};                                                                                          \
+    if (first_use_on_device(cfg))                                                                                                    \
+      EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_warp_bwd_kernel<CC, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    pairwise_flat3_warp_bwd_kernel<CC, SQ><<<grid, PWW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, go, gx);                  \
+  } while (0)
+#define EMK_PWWB2(CC) do { if (squared) EMK_PWWB(CC, true); else EMK_PWWB(CC, false); } while (0)
+    if (n <= 32) EMK_PWWB2(1);
+    else if (n <= 64) EMK_PWWB2(2);
+    else if (n <= 96) EMK_PWWB2(3);
+    else EMK_PWWB2(4);
+#undef EMK_PWWB2
+#undef EMK_PWWB
+    return launch_status("pairwise_flat3_warp_bwd_kernel");
+  }
   if (flat && d == 3 && n > 128 && n <= 320) {
     const size_t smem = 18 * (size_t)n * sizeof(float);
     const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 16);

@@ -86,6 +86,8 @@ void tile_decode_host(int64_t t, int64_t n_rows, int64_t* I, int64_t* J);
 int sigmoid_cost_device(const float*, int64_t, int64_t, const float*, int64_t, double, const float*, int64_t, int64_t, double*,
                         float*, uint32_t, cudaStream_t);
 int dist_matrix_device(const float*, int64_t, int64_t, double, bool, int, float*, cudaStream_t);
+void set_cost_small_d_max(int64_t v);
+int64_t cost_small_d_max();
 int periodic_distance_device(const float*, const float*, int64_t, double, float*, cudaStream_t);
 int periodic_distance_bwd_device(const float*, const float*, int64_t, double, const float*, float*, float*, cudaStream_t);
 int sigmoid_device(const float*, int64_t, float, float, float, float*, cudaStream_t);
@@ -225,6 +227,10 @@ int emk_set_option(const char* name, int64_t value) {
     set_fwd6_warps(value);
     return EMK_OK;
   }
+  if (strcmp(name, "cost_small_d_max") == 0) {
+    set_cost_small_d_max(value);
+    return EMK_OK;
+  }
   return fail(EMK_E_ARG, "emk_set_option: unknown option '%s'", name);
 }
 int emk_get_option(const char* name, int64_t* value) {
@@ -235,6 +241,10 @@ int emk_get_option(const char* name, int64_t* value) {
   }
   if (strcmp(name, "backmap_fwd6_warps") == 0) {
     *value = fwd6_warps();
+    return EMK_OK;
+  }
+  if (strcmp(name, "cost_small_d_max") == 0) {
+    *value = cost_small_d_max();
     return EMK_OK;
   }
   return fail(EMK_E_ARG, "emk_get_option: unknown option '%s'", name);

@@ -491,6 +491,90 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
   }
 }
 
+// ---- narrow inputs (D <= SMALL_D: the cube example's 3-d points, 2-d projections) ---------------------------------------
+// No TMA, no padded copy, no 32-wide k-chunk that is mostly zeros: the D columns of the tile's 128 + 64 rows are staged
+// component-major in shared memory with plain loads and every thread forms its squared distances in registers.  The tile
+// numbering, the micro-tile layout (rows ty + 16 i, columns tx + 16 j), the even/odd summation order and the epilogue are
+// those of pair_tile_kernel, so tile ranges (multi-GPU) and results carry over.  A launch with few tiles (a training batch
+// of 256 rows is 6 tiles) is spread over 8 / NI CTAs per tile, each finishing NI of the eight 16-row groups: there is no
+// feature axis worth splitting, so no cluster and no reduction is needed.  The epilogue (two sigmoids per pair, MUFU) is
+// the whole cost.
+constexpr int SMALL_D = 8;
+
+template <bool PERIODIC, int NI>
+__global__ void __launch_bounds__(NTHREADS) small_cost_kernel(const PairParams p, const float* __restrict__ high, const int d) {
+  __shared__ float hA[SMALL_D * TM];
+  __shared__ float hB[SMALL_D * TN];
+  __shared__ float zA[MAX_LATENT * TM];
+  __shared__ float zB[MAX_LATENT * TN];
+  __shared__ float colsum[MAX_LATENT * TN];
+  __shared__ double red_d[NTHREADS / 32];
+  constexpr int S = 8 / NI;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ty = tid >> 4, tx = tid & 15;
+  const int i0 = (int)(blockIdx.x % S) * NI;
+  int64_t I, J;
+  tile_decode(p.tile_begin + blockIdx.x / S, p.tiles_per_row, p.tile_rows, &I, &J);
+  const int64_t row0 = I * TM, col0 = J * TN;
+  const bool diag = (J >> 1) == I;
+  for (int idx = tid; idx < d * TM; idx += NTHREADS) {
+    const int r = idx / d, k = idx - r * d;      // consecutive threads read consecutive floats of the row block
+    hA[k * TM + r] = (row0 + r < p.n) ? high[(row0 + r) * d + k] : 0.f;
+  }
+  for (int idx = tid; idx < d * TN; idx += NTHREADS) {
+    const int r = idx / d, k = idx - r * d;
+    hB[k * TN + r] = (col0 + r < p.n) ? high[(col0 + r) * d + k] : 0.f;
+  }
+  stage_latent(p, zA, zB, colsum, row0, col0, 0, min(MAX_LATENT, p.l), tid);
+  __syncthreads();
+  const float P = p.period;
+  float even[NI][4], odd[NI][4];
+#pragma unroll
+  for (int i = 0; i < NI; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) even[i][j] = odd[i][j] = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < d; k++) {
+    float a[NI], b[4];
+#pragma unroll
+    for (int i = 0; i < NI; i++) a[i] = hA[k * TM + ty + 16 * (i0 + i)];
+#pragma unroll
+    for (int j = 0; j < 4; j++) b[j] = hB[k * TN + tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float t = a[i] - b[j];
+        if (PERIODIC) t = fminf(fabsf(t), P - fabsf(t));
+        if (k & 1) odd[i][j] = fmaf(t, t, odd[i][j]);
+        else even[i][j] = fmaf(t, t, even[i][j]);
+      }
+  }
+  float d2h[NI][4];
+#pragma unroll
+  for (int i = 0; i < NI; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) d2h[i][j] = even[i][j] + odd[i][j];
+  cost_epilogue<NI>(d2h, i0, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+}
+
+// emk_set_option("cost_small_d_max", v): widest input that takes the register path (default SMALL_D; 0 sends everything
+// through the TMA kernel -- the parity tests compare the two)
+static int g_small_d_max = SMALL_D;
+void set_cost_small_d_max(int64_t v) { g_small_d_max = (int)std::max<int64_t>(0, std::min<int64_t>(SMALL_D, v)); }
+int64_t cost_small_d_max() { return g_small_d_max; }
+
+template <bool PERIODIC>
+static int launch_small_cost(const PairParams& p, const float* high, int d, int64_t n_tiles, cudaStream_t st) {
+  // CTAs per tile: enough to give every SM a few CTAs while a tile's fixed work (staging, one loss atomic, the column
+  // flush) is not repeated more often than needed
+  const int64_t slots = 4 * (int64_t)sm_count();
+  if (n_tiles * 8 <= slots) small_cost_kernel<PERIODIC, 1><<<(unsigned)(n_tiles * 8), NTHREADS, 0, st>>>(p, high, d);
+  else if (n_tiles * 4 <= slots) small_cost_kernel<PERIODIC, 2><<<(unsigned)(n_tiles * 4), NTHREADS, 0, st>>>(p, high, d);
+  else if (n_tiles * 2 <= slots) small_cost_kernel<PERIODIC, 4><<<(unsigned)(n_tiles * 2), NTHREADS, 0, st>>>(p, high, d);
+  else small_cost_kernel<PERIODIC, 8><<<(unsigned)n_tiles, NTHREADS, 0, st>>>(p, high, d);
+  return launch_status("small_cost_kernel");
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + (MAX_LATENT * (TM + 2 * TN)) * 4;
@@ -676,27 +760,32 @@ int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* lo
   }
   if (tile_end == tile_begin) return EMK_OK;
 
+  PairParams p{};
+  p.n = n;
+  p.n_chunks = (int)((d + KC - 1) / KC);
+  p.tiles_per_row = (int)((n + TN - 1) / TN);
+  p.tile_rows = (int)((n + TM - 1) / TM);
+  p.tile_begin = tile_begin;
+  p.period = std::isinf(periodicity) ? INFINITY : (float)periodicity;
+  p.low = low;
+  p.l = (int)l;
+  p.sh = make_sig_spec(sig[0], sig[1], sig[2]);
+  p.sl = make_sig_spec(sig[3], sig[4], sig[5]);
+  p.loss = loss;
+  p.grad = want_grad ? grad_low : nullptr;
+  p.loss_scale = 1.0 / ((double)n * (double)n);
+  p.grad_scale = (float)(4.0 / ((double)n * (double)n));
+  if (d <= g_small_d_max) {   // narrow inputs: register path, no TMA, no padded copy
+    return std::isinf(periodicity) ? launch_small_cost<false>(p, high, (int)d, tile_end - tile_begin, st)
+                                   : launch_small_cost<true>(p, high, (int)d, tile_end - tile_begin, st);
+  }
+
   HighView hv;
   int rc = prepare_high(high, n, d, st, &hv);
   if (rc) return rc;
   CUtensorMap map;
   rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad);
   if (rc == EMK_OK) {
-    PairParams p{};
-    p.n = n;
-    p.n_chunks = (int)((d + KC - 1) / KC);
-    p.tiles_per_row = (int)((n + TN - 1) / TN);
-    p.tile_rows = (int)((n + TM - 1) / TM);
-    p.tile_begin = tile_begin;
-    p.period = std::isinf(periodicity) ? INFINITY : (float)periodicity;
-    p.low = low;
-    p.l = (int)l;
-    p.sh = make_sig_spec(sig[0], sig[1], sig[2]);
-    p.sl = make_sig_spec(sig[3], sig[4], sig[5]);
-    p.loss = loss;
-    p.grad = want_grad ? grad_low : nullptr;
-    p.loss_scale = 1.0 / ((double)n * (double)n);
-    p.grad_scale = (float)(4.0 / ((double)n * (double)n));
     if (std::isinf(periodicity))
       rc = launch_pair<false, Epi::kCost>(map, p, tile_end - tile_begin, st);
     else

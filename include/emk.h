@@ -62,7 +62,9 @@ EMK_API int emk_probe_fp32(double* lane_instr_per_s);
  *   "backmap_fwd6_min_batch"  batch size from which emk_backmap uses the lane-per-frame kernel (default 4096; 0 = whenever
  *                             the shape is eligible, negative = never)
  *   "backmap_fwd6_warps"      warps per CTA of that kernel: 0 (default: chosen per launch so that the frame tiles fill whole
- *                             waves), or one of 8, 12, 14, 16, 18, 20 */
+ *                             waves), or one of 8, 12, 14, 16, 18, 20
+ *   "cost_small_d_max"        widest high-d input (columns) for which emk_sigmoid_cost uses the register kernel instead of
+ *                             the TMA pair-tile kernel (default 8; 0..8) */
 EMK_API int emk_set_option(const char* name, int64_t value);
 EMK_API int emk_get_option(const char* name, int64_t* value);
 

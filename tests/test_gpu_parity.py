@@ -130,6 +130,42 @@ def test_sigmoid_cost_duplicate_rows_and_nan(em):
         sigmoid_loss(check_finite=True)(cu(h), cu(low))
 
 
+@pytest.mark.parametrize("n,d,l,per,sig", [(256, 3, 2, float("inf"), DEFAULT_SIG), (256, 3, 2, float("inf"), (0.3, 6, 6, 1, 4, 6)),
+                                            (6000, 3, 2, float("inf"), (0.2, 3, 6, 1, 2, 6)), (300, 2, 2, 2 * pi, (1.0, 6, 6, 1, 4, 6)),
+                                            (1000, 8, 3, 1.0, (0.3, 6, 6, 1, 4, 6)), (77, 1, 2, 360.0, (60.0, 6, 6, 1, 4, 6)),
+                                            (641, 5, 12, float("inf"), (0.9, 6, 6, 1, 4, 6)), (2500, 7, 2, float("inf"), (0.9, 4, 6, 1, 2, 6))])
+def test_sigmoid_cost_narrow_inputs(em, n, d, l, per, sig):
+    """The register kernel for D <= 8 (cube example, reference examples/cube.py:1-20): against the float64 oracle, against the
+    TMA kernel on the same data, and over a partition of the tile list (1, 2, 4 or 8 CTAs per tile depending on the count)."""
+    from encodermap_b200 import _lib, _ops
+
+    rng = np.random.default_rng(n * 31 + d)
+    scale = per if np.isfinite(per) else 1.0
+    h = (rng.uniform(-0.5, 0.5, size=(n, d)) * scale).astype(np.float32)
+    low = (rng.normal(size=(n, l)) * 1.5).astype(np.float32)
+    assert _lib.get_option("cost_small_d_max") == 8
+    loss, grad = cost_and_grad(em, h, low, per, sig)
+    lref, gref = O.sigmoid_loss_and_grad(h, low, per, sig)
+    np.testing.assert_allclose(loss, lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(grad, gref.numpy()) < GRAD_RTOL
+    try:
+        _lib.set_option("cost_small_d_max", 0)
+        loss_tma, grad_tma = cost_and_grad(em, h, low, per, sig)
+    finally:
+        _lib.set_option("cost_small_d_max", 8)
+    np.testing.assert_allclose(loss, loss_tma, rtol=2e-6)
+    assert relnorm(grad, grad_tma) < 2e-6
+    total = _lib.pair_tile_count(n)
+    cuts = sorted({0, total // 3, total // 2 + 1, total})
+    lsum, gsum = 0.0, 0.0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lp, gp = _ops.sigmoid_cost_raw(cu(h), cu(low), per, sig, (a, b), True)
+        lsum += lp.item()
+        gsum = gsum + gp.double().cpu().numpy()
+    np.testing.assert_allclose(lsum, loss, rtol=1e-9)
+    assert relnorm(gsum, grad) < 1e-6
+
+
 def test_tile_partition_sums_to_full(em):
     """The multi-GPU split: partial results over a partition of the tile list add up to the full result."""
     from encodermap_b200 import _lib, _ops
@@ -333,10 +369,12 @@ def test_pairwise_dist_backward(em):
         assert relnorm(xg.grad.cpu().numpy(), xo.grad.numpy()) < 2e-5
 
 
-@pytest.mark.parametrize("b,n", [(3, 2), (5, 33), (9, 100), (3, 181), (3, 182), (2, 300), (2, 321), (1, 700)])
+@pytest.mark.parametrize("b,n", [(3, 2), (4, 32), (5, 33), (4, 64), (3, 65), (3, 96), (3, 97), (9, 100), (3, 128), (3, 129), (9000, 40),
+                                  (3, 181), (3, 182), (2, 300), (2, 321), (1, 700)])
 def test_pairwise_flat_kernel_variants(em, b, n):
-    """flat=True on (b, n, 3): sizes that select each forward (pair table <= 181 atoms, row walk above) and backward
-    (thread per atom <= 128, pair-once 129..320, thread per atom above) kernel; strided atom selection included."""
+    """flat=True on (b, n, 3): sizes that select each forward (warp per frame with 1..4 column chunks <= 128 atoms, pair table
+    <= 181, row walk above) and backward (warp per frame <= 128, pair-once 129..320, thread per atom above) kernel, a batch
+    larger than the grid (frame loop), the squared form, and the layer's strided atom selection."""
     from encodermap_b200 import ADCParameters
     from encodermap_b200.misc import distances as D
     from encodermap_b200.models.layers import PairwiseDistances
@@ -353,7 +391,13 @@ def test_pairwise_flat_kernel_variants(em, b, n):
     xo = torch.from_numpy(x).double().requires_grad_(True)
     (O.pairwise_dist(xo, flat=True) * torch.from_numpy(w)).sum().backward()
     assert relnorm(xg.grad.cpu().numpy(), xo.grad.numpy()) < 2e-5
-    np.testing.assert_allclose(D.pairwise_dist(cu(x), squared=True, flat=True).cpu().numpy(), want ** 2, rtol=1e-5, atol=1e-5)
+    xq = cu(x).requires_grad_(True)
+    sq = D.pairwise_dist(xq, squared=True, flat=True)
+    np.testing.assert_allclose(sq.detach().cpu().numpy(), want ** 2, rtol=1e-5, atol=1e-5)
+    (sq * cu(w)).sum().backward()
+    xo2 = torch.from_numpy(x).double().requires_grad_(True)
+    (O.pairwise_dist(xo2, squared=True, flat=True) * torch.from_numpy(w)).sum().backward()
+    assert relnorm(xq.grad.cpu().numpy(), xo2.grad.numpy()) < 2e-5
     if n >= 9:                                         # the layer's strided selection (every third atom from atom 1)
         p = ADCParameters(cartesian_pwd_start=1, cartesian_pwd_stop=None, cartesian_pwd_step=3)
         xs = cu(x).requires_grad_(True)
