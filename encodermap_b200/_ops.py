@@ -298,6 +298,58 @@ def rotation_matrix_raw(axis: torch.Tensor, angle: torch.Tensor) -> torch.Tensor
     return out
 
 
+def _host_indices(idx):
+    """index list -> (numpy int64 array kept alive by the caller, ctypes pointer, count)"""
+    import numpy as np
+
+    a = np.ascontiguousarray(np.asarray(idx.detach().cpu() if isinstance(idx, torch.Tensor) else idx, dtype=np.int64).reshape(-1))
+    return a, a.ctypes.data_as(_lib.c_i64p), int(a.size)
+
+
+def guess_sp2_raw(xyz: torch.Tensor, indices, angle: float, bond_length: float) -> torch.Tensor:
+    """(b, n, 3) backbone, centre-atom indices -> (b, len(indices), 3) guessed atoms (reference misc/backmapping.py:1920-1941)."""
+    require_cuda(xyz, "cartesians")
+    xyz = f32c(xyz)
+    if xyz.dim() != 3 or xyz.shape[2] != 3:
+        raise EmkError(-4, f"guess_sp2_atom needs (b, n_atoms, 3) coordinates, got {tuple(xyz.shape)}")
+    keep, ptr, cnt = _host_indices(indices)
+    out = _empty_like_shape(xyz, (xyz.shape[0], cnt, 3))
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_guess_sp2_atoms(xyz.data_ptr(), xyz.shape[0], xyz.shape[1], ptr, cnt, float(angle), float(bond_length),
+                                             out.data_ptr(), stream_of(xyz)))
+    return out
+
+
+def merge_cartesians_raw(central: torch.Tensor, h_after, o_after, h_xyz: torch.Tensor, o_xyz: torch.Tensor) -> torch.Tensor:
+    """Reference merge loop (misc/backmapping.py:1970-1990) with the two membership lists it tests against."""
+    require_cuda(central, "central_cartesians")
+    central, h_xyz, o_xyz = f32c(central), f32c(require_cuda(h_xyz, "H_cartesians")), f32c(require_cuda(o_xyz, "O_cartesians"))
+    kh, ph, nh = _host_indices(h_after)
+    ko, po, no = _host_indices(o_after)
+    out = _empty_like_shape(central, (central.shape[0], central.shape[1] + h_xyz.shape[1] + o_xyz.shape[1], 3))
+    with torch.cuda.device(central.device):
+        check(_lib.lib().emk_merge_cartesians(central.data_ptr(), central.shape[0], central.shape[1], ph, nh, po, no, h_xyz.data_ptr(),
+                                              h_xyz.shape[1], o_xyz.data_ptr(), o_xyz.shape[1], out.data_ptr(), stream_of(central)))
+    return out
+
+
+def backbone_amide_raw(central: torch.Tensor, h_after, o_after, h_angle: float, h_length: float, o_angle: float, o_length: float) -> torch.Tensor:
+    """guess_amide_H + guess_amide_O + merge_cartesians in one launch."""
+    require_cuda(central, "central_cartesians")
+    central = f32c(central)
+    kh, ph, nh = _host_indices(h_after)
+    ko, po, no = _host_indices(o_after)
+    n_out = int(_lib.lib().emk_merged_atom_count(central.shape[1], ph, nh, po, no))
+    if n_out < 0:
+        raise EmkError(-5, "backbone_with_amide_atoms: index outside the backbone")
+    out = _empty_like_shape(central, (central.shape[0], n_out, 3))
+    with torch.cuda.device(central.device):
+        check(_lib.lib().emk_backbone_amide_atoms(central.data_ptr(), central.shape[0], central.shape[1], ph, nh, po, no, float(h_angle),
+                                                  float(h_length), float(o_angle), float(o_length), out.data_ptr(), n_out,
+                                                  stream_of(central)))
+    return out
+
+
 def column_mean_raw(x: torch.Tensor) -> torch.Tensor:
     require_cuda(x, "distances")
     x = f32c(x)

@@ -757,46 +757,66 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_bwd_kernel(co
     }
     if (lane < 3) sr[lane * PWW_MAX_N + n - 1] = 0.f;   // the last atom has no row
     __syncwarp();
-    const float* grow = go + f * per - 1 + lane;    // grow[32 c] is the element (i, 32 c + lane) of the current row
     // g / dist as g * rsqrt(max(s2, tiny)): a masked lane (g = 0) and a zero distance (d = 0 multiplies it) both give 0
     auto coef_of = [](float g, float s2) { return SQUARED ? 2.f * g : g * rsqrt_fast(fmaxf(s2, EMK_TINY)); };
+    // the upstream gradient of the next PF rows is in flight while a row is processed: a row is ~40 instructions, a global
+    // load ~700 cycles, and nothing else in the row loop can cover it (2.7 ms instead of 1 ms at 65 536 x 100 atoms when
+    // every row waited for its own load)
+    constexpr int PF = 4;
+    const float* gpre = go + f * per - 1 + lane;    // gpre[32 c] is the element (row, 32 c + lane) of the row being prefetched
+    int pre_row = 0;
+    float gq[PF][C];
+    auto prefetch = [&](float (&dst)[C]) {
+#pragma unroll
+      for (int c = 0; c < C; c++) dst[c] = (pre_row < n - 1 && jj[c] > pre_row) ? __ldg(gpre + 32 * c) : 0.f;
+      gpre += n - pre_row - 2;
+      ++pre_row;
+    };
+#pragma unroll
+    for (int u = 0; u < PF; u++) prefetch(gq[u]);
 #pragma unroll 1
     for (int i0 = 0; i0 < n - 1; i0 += 32) {
       const int rows = min(32, n - 1 - i0);
 #pragma unroll 1
-      for (int ii = 0; ii < rows; ii++) {
-        const int i = i0 + ii;
-        const float4 xi = sx[i];
-        float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
+      for (int i4 = 0; i4 < rows; i4 += PF) {
 #pragma unroll
-        for (int c = 0; c + 1 < C; c += 2) {
-          if (32 * c + 63 <= i) continue;
-          const float g0 = jj[c] > i ? __ldg(grow + 32 * c) : 0.f;
-          const float g1 = jj[c + 1] > i ? __ldg(grow + 32 * c + 32) : 0.f;
-          const float2 dx = __fadd2_rn(make_float2(xi.x, xi.x), make_float2(nx[c], nx[c + 1]));
-          const float2 dy = __fadd2_rn(make_float2(xi.y, xi.y), make_float2(ny[c], ny[c + 1]));
-          const float2 dz = __fadd2_rn(make_float2(xi.z, xi.z), make_float2(nz[c], nz[c + 1]));
-          const float2 s2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
-          const float2 cf = make_float2(coef_of(g0, s2.x), coef_of(g1, s2.y));
-          r0 = __ffma2_rn(cf, dx, r0); r1 = __ffma2_rn(cf, dy, r1); r2 = __ffma2_rn(cf, dz, r2);
-          float2 t;
-          t = __ffma2_rn(cf, dx, make_float2(ax[c], ax[c + 1])); ax[c] = t.x; ax[c + 1] = t.y;
-          t = __ffma2_rn(cf, dy, make_float2(ay[c], ay[c + 1])); ay[c] = t.x; ay[c + 1] = t.y;
-          t = __ffma2_rn(cf, dz, make_float2(az[c], az[c + 1])); az[c] = t.x; az[c + 1] = t.y;
+        for (int u = 0; u < PF; u++) {
+          const int ii = i4 + u;
+          if (ii < rows) {
+            const int i = i0 + ii;
+            const float4 xi = sx[i];
+            float g[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) g[c] = gq[u][c];
+            prefetch(gq[u]);
+            float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
+#pragma unroll
+            for (int c = 0; c + 1 < C; c += 2) {
+              if (32 * c + 63 <= i) continue;
+              const float2 dx = __fadd2_rn(make_float2(xi.x, xi.x), make_float2(nx[c], nx[c + 1]));
+              const float2 dy = __fadd2_rn(make_float2(xi.y, xi.y), make_float2(ny[c], ny[c + 1]));
+              const float2 dz = __fadd2_rn(make_float2(xi.z, xi.z), make_float2(nz[c], nz[c + 1]));
+              const float2 s2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+              const float2 cf = make_float2(coef_of(g[c], s2.x), coef_of(g[c + 1], s2.y));
+              r0 = __ffma2_rn(cf, dx, r0); r1 = __ffma2_rn(cf, dy, r1); r2 = __ffma2_rn(cf, dz, r2);
+              float2 t;
+              t = __ffma2_rn(cf, dx, make_float2(ax[c], ax[c + 1])); ax[c] = t.x; ax[c + 1] = t.y;
+              t = __ffma2_rn(cf, dy, make_float2(ay[c], ay[c + 1])); ay[c] = t.x; ay[c + 1] = t.y;
+              t = __ffma2_rn(cf, dz, make_float2(az[c], az[c + 1])); az[c] = t.x; az[c + 1] = t.y;
+            }
+            float q0 = r0.x + r0.y, q1 = r1.x + r1.y, q2 = r2.x + r2.y;
+            if (C & 1) {
+              constexpr int c = C - 1;
+              const float dx = xi.x + nx[c], dy = xi.y + ny[c], dz = xi.z + nz[c];
+              const float cf = coef_of(g[c], fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+              q0 = fmaf(cf, dx, q0); q1 = fmaf(cf, dy, q1); q2 = fmaf(cf, dz, q2);
+              ax[c] = fmaf(cf, dx, ax[c]); ay[c] = fmaf(cf, dy, ay[c]); az[c] = fmaf(cf, dz, az[c]);
+            }
+            tr[(0 * 32 + ii) * PWW_RPAD + lane] = q0;
+            tr[(1 * 32 + ii) * PWW_RPAD + lane] = q1;
+            tr[(2 * 32 + ii) * PWW_RPAD + lane] = q2;
+          }
         }
-        float q0 = r0.x + r0.y, q1 = r1.x + r1.y, q2 = r2.x + r2.y;
-        if (C & 1) {
-          constexpr int c = C - 1;
-          const float g = jj[c] > i ? __ldg(grow + 32 * c) : 0.f;
-          const float dx = xi.x + nx[c], dy = xi.y + ny[c], dz = xi.z + nz[c];
-          const float cf = coef_of(g, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-          q0 = fmaf(cf, dx, q0); q1 = fmaf(cf, dy, q1); q2 = fmaf(cf, dz, q2);
-          ax[c] = fmaf(cf, dx, ax[c]); ay[c] = fmaf(cf, dy, ay[c]); az[c] = fmaf(cf, dz, az[c]);
-        }
-        tr[(0 * 32 + ii) * PWW_RPAD + lane] = q0;
-        tr[(1 * 32 + ii) * PWW_RPAD + lane] = q1;
-        tr[(2 * 32 + ii) * PWW_RPAD + lane] = q2;
-        grow += n - i - 2;
       }
       __syncwarp();
       if (lane < rows) {

@@ -95,6 +95,12 @@ int sigmoid_bwd_device(const float*, int64_t, float, float, float, const float*,
 int periodic_input_device(const float*, int64_t, int64_t, double, float*, cudaStream_t);
 int periodic_input_bwd_device(const float*, int64_t, int64_t, double, const float*, float*, cudaStream_t);
 int rotation_matrix_device(const float*, const float*, int64_t, float*, cudaStream_t);
+int guess_sp2_device(const float*, int64_t, int64_t, const int64_t*, int64_t, double, double, float*, cudaStream_t);
+int merge_cartesians_device(const float*, int64_t, int64_t, const int64_t*, int64_t, const int64_t*, int64_t, const float*, int64_t,
+                            const float*, int64_t, float*, cudaStream_t);
+int backbone_amide_device(const float*, int64_t, int64_t, const int64_t*, int64_t, const int64_t*, int64_t, double, double, double, double,
+                          float*, int64_t, cudaStream_t);
+int64_t merged_atom_count(int64_t, const int64_t*, int64_t, const int64_t*, int64_t);
 int column_mean_device(const float*, int64_t, int64_t, float*, cudaStream_t);
 int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float*, cudaStream_t);
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
@@ -812,6 +818,24 @@ int emk_dl_dihedrals_to_cartesian_chain_bwd(const DLManagedTensor* chain, const 
     cs = 3 * n;
   }
   return d2c_chain_bwd_device(F(cv), cs, F(xv), F(gv), b, n, one_way, F(ov), as_stream(stream));
+}
+
+int emk_guess_sp2_atoms(const float* xyz, int64_t b, int64_t n_atoms, const int64_t* indices, int64_t n_idx, double angle_to_previous,
+                        double bond_length, float* out, void* stream) {
+  return guess_sp2_device(xyz, b, n_atoms, indices, n_idx, angle_to_previous, bond_length, out, as_stream(stream));
+}
+int emk_merge_cartesians(const float* central, int64_t b, int64_t n_atoms, const int64_t* h_after, int64_t n_h_after, const int64_t* o_after,
+                         int64_t n_o_after, const float* h_xyz, int64_t n_h, const float* o_xyz, int64_t n_o, float* out, void* stream) {
+  return merge_cartesians_device(central, b, n_atoms, h_after, n_h_after, o_after, n_o_after, h_xyz, n_h, o_xyz, n_o, out, as_stream(stream));
+}
+int emk_backbone_amide_atoms(const float* central, int64_t b, int64_t n_atoms, const int64_t* h_after, int64_t n_h_after, const int64_t* o_after,
+                             int64_t n_o_after, double h_angle, double h_length, double o_angle, double o_length, float* out, int64_t n_out,
+                             void* stream) {
+  return backbone_amide_device(central, b, n_atoms, h_after, n_h_after, o_after, n_o_after, h_angle, h_length, o_angle, o_length, out, n_out,
+                               as_stream(stream));
+}
+int64_t emk_merged_atom_count(int64_t n_atoms, const int64_t* h_after, int64_t n_h_after, const int64_t* o_after, int64_t n_o_after) {
+  return merged_atom_count(n_atoms, h_after, n_h_after, o_after, n_o_after);
 }
 
 }  // extern "C"

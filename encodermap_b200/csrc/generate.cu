@@ -1,0 +1,199 @@
+// Generation-side back-mapping (the part of it that is tensor arithmetic): amide hydrogens and
+// carbonyl oxygens guessed from the backbone, and the merge of backbone + guessed atoms into one coordinate array --
+// encodermap/misc/backmapping.py:1920-1990 (guess_sp2_atom, guess_amide_H, guess_amide_O, merge_cartesians; TF1 twins
+// encodermap/encodermap_tf1/backmapping.py:256-318).  The reference builds them from ~10 TensorFlow ops per guessed atom
+// inside Python loops over the atoms; here ONE launch writes the merged (frames, n + n_H + n_O, 3) array straight from the
+// backbone, one thread per output atom, following a small "plan" (one 32-bit word per output atom: what it is and where it
+// comes from) that the host builds from the index lists with the reference's own loop.  HBM-bound: 12 n bytes read and
+// 12 (n + n_H + n_O) written per frame.
+//
+// guess_sp2_atom for centre atom i (reference order of operations):
+//   prev = x[i-1] - x[i];  next = x[i+1] - x[i]   (x[i-2] - x[i] when i is the last atom)
+//   u = prev x next / |prev x next|
+//   bond = prev . R(u, angle)     R = cos I + sin [u]x + (1 - cos) u u^T, row vector on the left:  cos prev + sin (prev x u) + (1 - cos)(prev . u) u
+//   out = x[i] + bond * bond_length / |bond|
+// Negative indices wrap as Python / TensorFlow slicing does (i - 1 at i = 0 is the last atom).
+#include <vector>
+
+#include "emk_common.cuh"
+
+namespace emk {
+
+enum PlanKind : uint32_t { kCopy0 = 0, kGuessA = 1, kGuessB = 2, kCopy1 = 3, kCopy2 = 4 };
+constexpr int PLAN_SHIFT = 28;
+constexpr uint32_t PLAN_MASK = (1u << PLAN_SHIFT) - 1;
+
+struct Sp2Params { float c, s, len; };
+
+struct GenParams {
+  const float* src0;   // (b, n0, 3) backbone
+  const float* src1;   // (b, n1, 3) or null (merge of given hydrogens)
+  const float* src2;   // (b, n2, 3) or null
+  int n0, n1, n2;
+  const uint32_t* plan;
+  int n_out;
+  int64_t b;
+  Sp2Params a, bb;
+  float* out;          // (b, n_out, 3)
+};
+
+__device__ __forceinline__ void sp2_atom(const float* __restrict__ xf, int n, int i, const Sp2Params& q, float* o) {
+  const int ip = i - 1 < 0 ? i - 1 + n : i - 1;
+  int in = i + 1;
+  if (in >= n) in = i - 2 < 0 ? i - 2 + n : i - 2;
+  const float cx = xf[3 * i], cy = xf[3 * i + 1], cz = xf[3 * i + 2];
+  const float px = xf[3 * ip] - cx, py = xf[3 * ip + 1] - cy, pz = xf[3 * ip + 2] - cz;
+  const float nx = xf[3 * in] - cx, ny = xf[3 * in + 1] - cy, nz = xf[3 * in + 2] - cz;
+  float ux = py * nz - pz * ny, uy = pz * nx - px * nz, uz = px * ny - py * nx;
+  const float inv = 1.f / sqrtf(ux * ux + uy * uy + uz * uz);
+  ux *= inv; uy *= inv; uz *= inv;
+  const float wx = py * uz - pz * uy, wy = pz * ux - px * uz, wz = px * uy - py * ux;   // prev x u
+  const float pu = (1.f - q.c) * (px * ux + py * uy + pz * uz);
+  float bx = q.c * px + q.s * wx + pu * ux, by = q.c * py + q.s * wy + pu * uy, bz = q.c * pz + q.s * wz + pu * uz;
+  const float sc = q.len / sqrtf(bx * bx + by * by + bz * bz);
+  o[0] = cx + bx * sc; o[1] = cy + by * sc; o[2] = cz + bz * sc;
+}
+
+__global__ void __launch_bounds__(256) generate_atoms_kernel(const GenParams p) {
+  const int64_t total = p.b * p.n_out;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = idx / p.n_out;
+    const int k = (int)(idx - f * p.n_out);
+    const uint32_t e = __ldg(p.plan + k);
+    const uint32_t kind = e >> PLAN_SHIFT;
+    const int i = (int)(e & PLAN_MASK);
+    float o[3];
+    if (kind == kCopy0 || kind == kCopy1 || kind == kCopy2) {
+      const float* s = kind == kCopy0 ? p.src0 + (f * p.n0 + i) * 3 : (kind == kCopy1 ? p.src1 + (f * p.n1 + i) * 3 : p.src2 + (f * p.n2 + i) * 3);
+      o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+    } else {
+      sp2_atom(p.src0 + f * p.n0 * 3, p.n0, i, kind == kGuessA ? p.a : p.bb, o);
+    }
+    float* d = p.out + idx * 3;
+    d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+  }
+}
+
+static int run_plan(GenParams p, const std::vector<uint32_t>& plan, cudaStream_t st) {
+  p.n_out = (int)plan.size();
+  if (p.b == 0 || p.n_out == 0) return EMK_OK;
+  uint32_t* dplan = nullptr;
+  int rc = scratch_alloc(reinterpret_cast<void**>(&dplan), plan.size() * sizeof(uint32_t), st);
+  if (rc) return rc;
+  // pageable source: the runtime stages it before the call returns, so `plan` may go out of scope afterwards
+  cudaError_t e = cudaMemcpyAsync(dplan, plan.data(), plan.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(dplan, st);
+    return fail((int)e, "generation plan upload failed: %s", cudaGetErrorString(e));
+  }
+  p.plan = dplan;
+  const int64_t total = p.b * p.n_out;
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  generate_atoms_kernel<<<grid, 256, 0, st>>>(p);
+  rc = launch_status("generate_atoms_kernel");
+  cudaFreeAsync(dplan, st);
+  return rc;
+}
+
+static Sp2Params sp2_params(double angle, double len) { return Sp2Params{(float)std::cos(angle), (float)std::sin(angle), (float)len}; }
+
+static int check_indices(const char* what, const int64_t* idx, int64_t count, int64_t n) {
+  EMK_REQUIRE(count == 0 || idx, EMK_E_NULL, "%s: NULL index list", what);
+  for (int64_t k = 0; k < count; k++)
+    EMK_REQUIRE(idx[k] >= 0 && idx[k] < n, EMK_E_ARG, "%s: index %lld outside [0,%lld)", what, (long long)idx[k], (long long)n);
+  return EMK_OK;
+}
+
+// guess_sp2_atom(cartesians, indices, angle_to_previous, bond_length) -> (b, n_idx, 3)
+int guess_sp2_device(const float* xyz, int64_t b, int64_t n, const int64_t* indices, int64_t n_idx, double angle, double bond_length,
+                     float* out, cudaStream_t st) {
+  EMK_REQUIRE(xyz && out, EMK_E_NULL, "emk_guess_sp2_atoms: NULL pointer argument");
+  EMK_REQUIRE(b >= 0 && n >= 3 && n < (int64_t)PLAN_MASK, EMK_E_SHAPE, "emk_guess_sp2_atoms: need (b, n >= 3, 3) coordinates");
+  int rc = check_indices("emk_guess_sp2_atoms", indices, n_idx, n);
+  if (rc) return rc;
+  std::vector<uint32_t> plan((size_t)n_idx);
+  for (int64_t k = 0; k < n_idx; k++) plan[(size_t)k] = ((uint32_t)kGuessA << PLAN_SHIFT) | (uint32_t)indices[k];
+  GenParams p{};
+  p.src0 = xyz; p.n0 = (int)n; p.b = b; p.a = sp2_params(angle, bond_length); p.bb = p.a; p.out = out;
+  return run_plan(p, plan, st);
+}
+
+// The merge loop of the reference (misc/backmapping.py:1970-1990): atom 0, then for i = 1 .. n-1: atom i, followed by the next
+// hydrogen if i is in h_after, ELSE by the next oxygen if i is in o_after.  `h_after` / `o_after` are what the reference
+// tests membership against (N_indices[1:] and O_indices in the TF2 form, the positions of "N" / "C" in the TF1 form).
+static int merge_plan(int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after, int64_t no_after, bool guess,
+                      std::vector<uint32_t>* plan, int64_t* nh_used, int64_t* no_used) {
+  std::vector<uint8_t> in_h((size_t)n, 0), in_o((size_t)n, 0);
+  for (int64_t k = 0; k < nh_after; k++) in_h[(size_t)h_after[k]] = 1;
+  for (int64_t k = 0; k < no_after; k++) in_o[(size_t)o_after[k]] = 1;
+  plan->clear();
+  plan->push_back(((uint32_t)kCopy0 << PLAN_SHIFT) | 0u);
+  int64_t h = 0, o = 0;
+  for (int64_t i = 1; i < n; i++) {
+    plan->push_back(((uint32_t)kCopy0 << PLAN_SHIFT) | (uint32_t)i);
+    if (in_h[(size_t)i]) {
+      plan->push_back(guess ? (((uint32_t)kGuessA << PLAN_SHIFT) | (uint32_t)i) : (((uint32_t)kCopy1 << PLAN_SHIFT) | (uint32_t)h));
+      ++h;
+    } else if (in_o[(size_t)i]) {
+      plan->push_back(guess ? (((uint32_t)kGuessB << PLAN_SHIFT) | (uint32_t)i) : (((uint32_t)kCopy2 << PLAN_SHIFT) | (uint32_t)o));
+      ++o;
+    }
+  }
+  *nh_used = h;
+  *no_used = o;
+  return EMK_OK;
+}
+
+int merge_cartesians_device(const float* central, int64_t b, int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after,
+                            int64_t no_after, const float* h_xyz, int64_t n_h, const float* o_xyz, int64_t n_o, float* out,
+                            cudaStream_t st) {
+  EMK_REQUIRE(central && out && (n_h == 0 || h_xyz) && (n_o == 0 || o_xyz), EMK_E_NULL, "emk_merge_cartesians: NULL pointer argument");
+  EMK_REQUIRE(b >= 0 && n >= 1 && n < (int64_t)PLAN_MASK && n_h >= 0 && n_o >= 0, EMK_E_SHAPE, "emk_merge_cartesians: bad shape");
+  int rc = check_indices("emk_merge_cartesians (h_after)", h_after, nh_after, n);
+  if (rc) return rc;
+  rc = check_indices("emk_merge_cartesians (o_after)", o_after, no_after, n);
+  if (rc) return rc;
+  std::vector<uint32_t> plan;
+  int64_t h, o;
+  merge_plan(n, h_after, nh_after, o_after, no_after, false, &plan, &h, &o);
+  // the reference's closing assert: every supplied atom is used exactly once (h > n_h would already have raised in the loop)
+  EMK_REQUIRE(h == n_h && o == n_o, EMK_E_SHAPE,
+              "emk_merge_cartesians: the index lists place %lld hydrogens and %lld oxygens, %lld and %lld were supplied", (long long)h,
+              (long long)o, (long long)n_h, (long long)n_o);
+  GenParams p{};
+  p.src0 = central; p.src1 = h_xyz; p.src2 = o_xyz; p.n0 = (int)n; p.n1 = (int)n_h; p.n2 = (int)n_o; p.b = b; p.out = out;
+  return run_plan(p, plan, st);
+}
+
+// guess_amide_H + guess_amide_O + merge_cartesians in one launch: the H / O arrays never exist
+int backbone_amide_device(const float* central, int64_t b, int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after,
+                          int64_t no_after, double h_angle, double h_len, double o_angle, double o_len, float* out, int64_t n_out,
+                          cudaStream_t st) {
+  EMK_REQUIRE(central && out, EMK_E_NULL, "emk_backbone_amide_atoms: NULL pointer argument");
+  EMK_REQUIRE(b >= 0 && n >= 3 && n < (int64_t)PLAN_MASK, EMK_E_SHAPE, "emk_backbone_amide_atoms: need (b, n >= 3, 3) coordinates");
+  int rc = check_indices("emk_backbone_amide_atoms (h_after)", h_after, nh_after, n);
+  if (rc) return rc;
+  rc = check_indices("emk_backbone_amide_atoms (o_after)", o_after, no_after, n);
+  if (rc) return rc;
+  std::vector<uint32_t> plan;
+  int64_t h, o;
+  merge_plan(n, h_after, nh_after, o_after, no_after, true, &plan, &h, &o);
+  EMK_REQUIRE((int64_t)plan.size() == n_out, EMK_E_SHAPE, "emk_backbone_amide_atoms: output holds %lld atoms, the index lists make %lld",
+              (long long)n_out, (long long)plan.size());
+  GenParams p{};
+  p.src0 = central; p.n0 = (int)n; p.b = b; p.a = sp2_params(h_angle, h_len); p.bb = sp2_params(o_angle, o_len); p.out = out;
+  return run_plan(p, plan, st);
+}
+
+// number of atoms the merge produces (host only)
+int64_t merged_atom_count(int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after, int64_t no_after) {
+  if (n < 1) return 0;
+  for (int64_t k = 0; k < nh_after; k++) if (h_after[k] < 0 || h_after[k] >= n) return -1;
+  for (int64_t k = 0; k < no_after; k++) if (o_after[k] < 0 || o_after[k] >= n) return -1;
+  std::vector<uint32_t> plan;
+  int64_t h, o;
+  merge_plan(n, h_after, nh_after, o_after, no_after, true, &plan, &h, &o);
+  return (int64_t)plan.size();
+}
+
+}  // namespace emk

@@ -1,8 +1,9 @@
 """Drop-in for the TF part of ``encodermap.misc.backmapping`` (reference file
-encodermap/misc/backmapping.py:179-309, 1873-1912, 1950-1968)."""
+encodermap/misc/backmapping.py:179-309, 1873-1912, 1920-1990)."""
 from __future__ import annotations
 
-from typing import Tuple
+from math import pi
+from typing import Sequence, Tuple
 
 import torch
 
@@ -45,3 +46,36 @@ def dihedral_to_cartesian_tf_one_way_layers(dihedrals: torch.Tensor, cartesian: 
 def rotation_matrix(axis_unit_vec: torch.Tensor, angle: torch.Tensor) -> torch.Tensor:
     """Reference: encodermap/misc/backmapping.py:1950-1968 (applied to row vectors on the right)."""
     return _ops.rotation_matrix_raw(axis_unit_vec, angle)
+
+
+# ---- generation side: amide H / carbonyl O guessed from the backbone (forward only, as on the reference's generate path) ----
+AMIDE_H = (123 / 180 * pi, 1.10)   # angle to the previous bond, bond length: misc/backmapping.py:1943-1944
+AMIDE_O = (121 / 180 * pi, 1.24)   # misc/backmapping.py:1946-1947
+
+
+def guess_sp2_atom(cartesians: torch.Tensor, indices: Sequence[int], angle_to_previous: float, bond_length: float) -> torch.Tensor:
+    """Reference: encodermap/misc/backmapping.py:1920-1941.  One atom per entry of ``indices`` (the centre atom), in the plane
+    of its two neighbours, ``angle_to_previous`` away from the bond to the previous atom."""
+    return _ops.guess_sp2_raw(cartesians, indices, angle_to_previous, bond_length)
+
+
+def guess_amide_H(cartesians: torch.Tensor, N_indices: Sequence[int]) -> torch.Tensor:
+    """Reference: encodermap/misc/backmapping.py:1943-1944 (the first nitrogen gets no hydrogen: ``N_indices[1::]``)."""
+    return guess_sp2_atom(cartesians, list(N_indices)[1::], *AMIDE_H)
+
+
+def guess_amide_O(cartesians: torch.Tensor, C_indices: Sequence[int]) -> torch.Tensor:
+    """Reference: encodermap/misc/backmapping.py:1946-1947."""
+    return guess_sp2_atom(cartesians, list(C_indices), *AMIDE_O)
+
+
+def merge_cartesians(central_cartesians: torch.Tensor, N_indices: Sequence[int], O_indices: Sequence[int], H_cartesians: torch.Tensor,
+                     O_cartesians: torch.Tensor) -> torch.Tensor:
+    """Reference: encodermap/misc/backmapping.py:1970-1990: after atom i >= 1 comes the next H if ``i in N_indices[1::]``,
+    else the next O if ``i in O_indices``; the reference's closing assert on the atom count is EmkError(EMK_E_SHAPE) here."""
+    return _ops.merge_cartesians_raw(central_cartesians, list(N_indices)[1::], list(O_indices), H_cartesians, O_cartesians)
+
+
+def backbone_with_amide_atoms(cartesians: torch.Tensor, N_indices: Sequence[int], C_indices: Sequence[int]) -> torch.Tensor:
+    """``merge_cartesians(c, N, C, guess_amide_H(c, N), guess_amide_O(c, C))`` as ONE launch (the H and O arrays never exist)."""
+    return _ops.backbone_amide_raw(cartesians, list(N_indices)[1::], list(C_indices), *AMIDE_H, *AMIDE_O)

@@ -201,6 +201,30 @@ EMK_API int emk_dl_periodic_input_bwd(const DLManagedTensor* x, double periodici
 EMK_API int emk_rotation_matrix(const float* axis, const float* angle, int64_t b, float* out, void* stream);
 EMK_API int emk_dl_rotation_matrix(const DLManagedTensor* axis, const DLManagedTensor* angle, DLManagedTensor* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Generation-side back-mapping: amide H / carbonyl O guessed from the backbone, and the merge of backbone + guessed atoms
+ *   encodermap/misc/backmapping.py:1920-1947 (guess_sp2_atom, guess_amide_H: angle 123 deg, length 1.10; guess_amide_O: 121 deg,
+ *   1.24), :1970-1990 (merge_cartesians); TF1 twins encodermap/encodermap_tf1/backmapping.py:256-318.
+ * Index lists are HOST arrays (int64).  Forward only (the reference uses these on the generate / summary path).  The index
+ * lists are uploaded with a pageable copy, so these calls cannot be captured into a CUDA graph.
+ *   emk_guess_sp2_atoms       out (b, n_idx, 3): one atom per entry of `indices` (centre atom i; neighbours i-1 and i+1, or
+ *                             i-2 when i is the last atom; negative positions wrap as Python indexing does)
+ *   emk_merge_cartesians      out (b, n + n_h + n_o, 3): atom 0, then for i = 1..n-1 atom i followed by the next hydrogen if i
+ *                             is in h_after, else by the next oxygen if i is in o_after (h_after = N_indices[1:], o_after =
+ *                             O_indices in the reference's call); EMK_E_SHAPE unless every supplied atom is placed exactly once
+ *   emk_backbone_amide_atoms  guess_amide_H + guess_amide_O + merge_cartesians in one launch (the H / O arrays never exist);
+ *                             n_out must equal emk_merged_atom_count(...)
+ * ---------------------------------------------------------------------------------------- */
+EMK_API int emk_guess_sp2_atoms(const float* xyz, int64_t b, int64_t n_atoms, const int64_t* indices, int64_t n_idx, double angle_to_previous,
+                                double bond_length, float* out, void* stream);
+EMK_API int emk_merge_cartesians(const float* central, int64_t b, int64_t n_atoms, const int64_t* h_after, int64_t n_h_after,
+                                 const int64_t* o_after, int64_t n_o_after, const float* h_xyz, int64_t n_h, const float* o_xyz, int64_t n_o,
+                                 float* out, void* stream);
+EMK_API int emk_backbone_amide_atoms(const float* central, int64_t b, int64_t n_atoms, const int64_t* h_after, int64_t n_h_after,
+                                     const int64_t* o_after, int64_t n_o_after, double h_angle, double h_length, double o_angle,
+                                     double o_length, float* out, int64_t n_out, void* stream);
+EMK_API int64_t emk_merged_atom_count(int64_t n_atoms, const int64_t* h_after, int64_t n_h_after, const int64_t* o_after, int64_t n_o_after);
+
 /* mean over rows: (rows,cols) -> (cols)   the `tf.reduce_mean(distances, 0)` of BackMapLayer.call, layers.py:970 */
 EMK_API int emk_column_mean(const float* x, int64_t rows, int64_t cols, float* out, void* stream);
 EMK_API int emk_dl_column_mean(const DLManagedTensor* x, DLManagedTensor* out, void* stream);

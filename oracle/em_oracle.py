@@ -370,6 +370,54 @@ def back_map_layer(distances, angles, dihedrals, left_split: Optional[int] = Non
 # ----------------------------------------------------------------------------------------
 
 
+# ---- generation side: guessed amide H / carbonyl O and the merge --------------------------------------
+def guess_sp2_atom(cartesians, indices, angle_to_previous: float, bond_length: float):
+    """Reference: encodermap/misc/backmapping.py:1920-1941.  ``cartesians[:, i + 1]`` past the last atom raises in
+    TensorFlow and the reference falls back to atom i - 2 (:1926-1929); negative positions wrap as Python indexing does."""
+    x = _t(cartesians)
+    n = x.shape[1]
+    added = []
+    for i in indices:
+        prev_vec = x[:, i - 1] - x[:, i]
+        next_vec = (x[:, i + 1] if i + 1 < n else x[:, i - 2]) - x[:, i]
+        axis = torch.linalg.cross(prev_vec, next_vec)
+        axis = axis / torch.sqrt((axis * axis).sum(dim=1, keepdim=True))
+        ang = torch.full((x.shape[0],), angle_to_previous, dtype=x.dtype)
+        bond = torch.matmul(prev_vec[:, None, :], rotation_matrix(axis, ang))[:, 0, :]
+        bond = bond * (bond_length / torch.sqrt((bond * bond).sum(dim=1, keepdim=True)))
+        added.append(x[:, i] + bond)
+    return torch.stack(added, dim=1)
+
+
+def guess_amide_H(cartesians, N_indices):
+    """Reference: encodermap/misc/backmapping.py:1943-1944."""
+    return guess_sp2_atom(cartesians, list(N_indices)[1::], 123 / 180 * pi, 1.10)
+
+
+def guess_amide_O(cartesians, C_indices):
+    """Reference: encodermap/misc/backmapping.py:1946-1947."""
+    return guess_sp2_atom(cartesians, list(C_indices), 121 / 180 * pi, 1.24)
+
+
+def merge_cartesians(central_cartesians, N_indices, O_indices, H_cartesians, O_cartesians):
+    """Reference: encodermap/misc/backmapping.py:1970-1990."""
+    c, h, o = _t(central_cartesians), _t(H_cartesians), _t(O_cartesians)
+    n_tail, o_set = set(list(N_indices)[1::]), set(O_indices)
+    out = [c[:, 0]]
+    h_i = o_i = 0
+    for i in range(1, c.shape[1]):
+        out.append(c[:, i])
+        if i in n_tail:
+            out.append(h[:, h_i])
+            h_i += 1
+        elif i in o_set:
+            out.append(o[:, o_i])
+            o_i += 1
+    out = torch.stack(out, dim=1)
+    assert out.shape[1] == c.shape[1] + h.shape[1] + o.shape[1]
+    return out
+
+
 def sigmoid_loss_and_grad(y_true, y_pred, periodicity=2 * pi, sig=DEFAULT_SIG, dtype=torch.float64):
     """Loss and dL/d(y_pred) by autograd over the restated forward (the reference relies on
     tf.GradientTape; only the latent side needs a gradient)."""

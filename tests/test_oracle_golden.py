@@ -124,3 +124,26 @@ def test_layers_golden(golden):
     np.testing.assert_allclose(O.periodic_input(g["pi_x"] * 50, 360.0).numpy(), g["pi_360"], atol=1e-14)
     for tag, sl in {"ca": (1, None, 3), "all": (None, None, None), "odd": (2, 25, 4)}.items():
         np.testing.assert_allclose(O.pairwise_distances_layer(g["pd_xyz"], *sl).numpy(), g[f"pd_{tag}"], rtol=1e-12, atol=1e-14)
+
+
+def test_generation_golden(golden):
+    """guess_amide_H / guess_amide_O / merge_cartesians (reference misc/backmapping.py:1920-1990) restated in the oracle against
+    the reference's own function bodies; bond geometry as a known-answer check on top (length and angle to the previous bond)."""
+    g = golden["generation"]
+    for n in (9, 30, 300):
+        xyz = g[f"n{n}_xyz"]
+        n_idx, c_idx = np.arange(n)[::3], np.arange(n)[2::3]
+        h = O.guess_amide_H(xyz, n_idx)
+        o = O.guess_amide_O(xyz, c_idx)
+        np.testing.assert_allclose(h.numpy(), g[f"n{n}_H"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(o.numpy(), g[f"n{n}_O"], rtol=0, atol=1e-12)
+        merged = O.merge_cartesians(xyz, n_idx, c_idx, h, o)
+        np.testing.assert_allclose(merged.numpy(), g[f"n{n}_merged"], rtol=0, atol=1e-12)
+        assert merged.shape[1] == n + (n // 3 - 1) + n // 3
+        # N-H bond: 1.10 long, 123 degrees from the bond to the previous atom (the C of the preceding residue)
+        bond = g[f"n{n}_H"] - xyz[:, n_idx[1:]]
+        prev = xyz[:, n_idx[1:] - 1] - xyz[:, n_idx[1:]]
+        np.testing.assert_allclose(np.linalg.norm(bond, axis=2), 1.10, rtol=1e-12)
+        cosang = (bond * prev).sum(2) / np.linalg.norm(bond, axis=2) / np.linalg.norm(prev, axis=2)
+        np.testing.assert_allclose(np.arccos(cosang), 123 / 180 * pi, rtol=1e-9)
+    np.testing.assert_allclose(O.guess_sp2_atom(g["n30_xyz"], g["n30_sel"].tolist(), 1.9, 0.101).numpy(), g["n30_sp2_generic"], rtol=0, atol=1e-12)

@@ -7,7 +7,9 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 from encodermap_b200 import _ops  # noqa: E402
+from _timing import eager_time, graph_time  # noqa: E402
 
 dev = torch.device("cuda:0")
 SIG = (4.5, 12, 6, 1, 2, 6)
@@ -16,18 +18,9 @@ for n, d, per in ((256, 3, float("inf")), (256, 1024, 2 * math.pi), (512, 1024, 
     g = torch.Generator(device=dev).manual_seed(1)
     x = (torch.rand(n, d, device=dev, generator=g) * 2 - 1) * math.pi
     z = torch.randn(n, 2, device=dev, generator=g)
-    for _ in range(3):
-        _ops.sigmoid_cost_raw(x, z, per, SIG)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    e0.record()
-    for _ in range(reps):
-        _ops.sigmoid_cost_raw(x, z, per, SIG)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    ms_eager = eager_time(lambda: _ops.sigmoid_cost_raw(x, z, per, SIG))
+    ms = graph_time(lambda: _ops.sigmoid_cost_raw(x, z, per, SIG))     # device time (incl. the two output memsets)
     pairs = n * (n + 1) / 2
     instr = pairs * ((4 if per < 1e30 else 2) * d + 60)
-    print(f"EMK_CLUSTER={os.environ.get('EMK_CLUSTER', 'auto'):>4} n={n:5d} d={d:5d} {'periodic' if per < 1e30 else 'euclid  '}: {ms * 1e3:8.1f} us  "
+    print(f"EMK_CLUSTER={os.environ.get('EMK_CLUSTER', 'auto'):>4} n={n:5d} d={d:5d} {'periodic' if per < 1e30 else 'euclid  '}: {ms * 1e3:8.1f} us (graph replay; eager from Python {ms_eager * 1e3:6.1f} us)  "
           f"{pairs / ms / 1e6:8.2f} Gpairs/s  {instr / (ms * 1e-3) / (148 * 128 * 1.965e9):.3f} of FP32 issue roofline")

@@ -6,25 +6,18 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 from encodermap_b200 import ADCParameters, Parameters, _lib, _ops  # noqa: E402
 from encodermap_b200.misc.distances import periodic_distance  # noqa: E402
+from _timing import graph_time  # noqa: E402
 
 dev = torch.device("cuda:0")
-HBM = 6464.3
+HBM = 6450.3   # MEASURED_PEAKS.json hbm_gbs
 g = torch.Generator(device=dev).manual_seed(0)
 
 
 def timeit(fn, reps=20):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    return graph_time(fn, reps)     # device time: below ~40 us an eager call from Python measures the host
 
 
 def report(name, ms, nbytes):
@@ -60,3 +53,11 @@ dist = torch.rand(65536, 1499, device=dev, generator=g)
 o = torch.empty(1499, device=dev)
 a = [_lib.DL(dist), _lib.DL(o)]
 report("column_mean (65536x1499)", timeit(lambda: L.emk_dl_column_mean(a[0], a[1], st(dist))), 4 * dist.numel())
+# fused Cartesian branch (PairwiseDistances("output") + cartesian_loss + gradient in one launch)
+for bsz, n, sel in ((1024, 300, (1, None, 3)), (65536, 300, (1, None, 3))):
+    xyz = torch.randn(bsz, n, 3, device=dev, generator=g)
+    tgt = torch.randn(bsz, n, 3, device=dev, generator=g)
+    ns = len(range(*slice(*sel).indices(n)))
+    ms = timeit(lambda: _ops.cartesian_pair_loss_raw(xyz, tgt, *sel, "mean_abs", 0.0, True))
+    # bytes of the unfused composition it replaces: two pair matrices written + read, their gradient written + read
+    report(f"fused cartesian loss+grad (b={bsz}, n_sel={ns})", ms, bsz * (24 * ns + 12 * n))

@@ -46,6 +46,16 @@ class T(np.ndarray):
     def numpy(self):
         return np.asarray(self)
 
+    # tf.Tensor is immutable: `r += x` rebinds r to a new (broadcast) tensor
+    def __iadd__(self, other):
+        return self + other
+
+    def __imul__(self, other):
+        return self * other
+
+    def __itruediv__(self, other):
+        return self / other
+
 
 def _w(x, dtype=None):
     a = np.asarray(x, dtype=dtype)
@@ -87,10 +97,16 @@ class _Math:
         return _w(np.mod(a, b))
 
 
+class _Errors:
+    # `cartesians[:, i + 1]` past the last atom raises InvalidArgumentError in TensorFlow; numpy raises IndexError
+    InvalidArgumentError = IndexError
+
+
 class _TFShim:
     """Only what distances.py / loss_functions.py / backmapping.py / layers.py use on the path."""
 
     debugging = _Debugging()
+    errors = _Errors()
     linalg = _Linalg()
     math = _Math()
     float32 = np.float32
@@ -232,7 +248,8 @@ def load_reference(dtype):
              ["sigmoid", "periodic_distance_np", "periodic_distance", "pairwise_dist_periodic", "pairwise_dist"], ns)
     _extract(REF / "encodermap/misc/backmapping.py",
              ["split_and_reverse_dihedrals", "split_and_reverse_cartesians", "dihedrals_to_cartesian_tf_layers",
-              "dihedral_to_cartesian_tf_one_way_layers", "rotation_matrix"], ns)
+              "dihedral_to_cartesian_tf_one_way_layers", "rotation_matrix", "guess_sp2_atom", "guess_amide_H", "guess_amide_O",
+              "merge_cartesians"], ns)
     ns1 = dict(ns)  # TF1 twins live in their own namespace (same names, different bodies)
     _extract(REF / "encodermap/encodermap_tf1/backmapping.py",
              ["straight_tetrahedral_chain", "chain_in_plane", "dihedrals_to_cartesian_tf",
@@ -417,6 +434,32 @@ def main():
         p = _Self(reconstruct_sidechains=False, cartesian_pwd_start=a_, cartesian_pwd_stop=b_, cartesian_pwd_step=c_)
         g[f"pd_{tag}"] = np.asarray(R["PairwiseDistances_call"](_Self(p=p), tf64.convert_to_tensor(xyz)))
     np.savez_compressed(OUT / "layers.npz", **g)
+
+    # ---- generation side: guessed amide H / O and the merge (own generator: the files above stay byte-identical) ----
+    g = {}
+    rng2 = np.random.default_rng(20261018)
+    for n_atoms, batch in ((9, 3), (30, 4), (300, 2)):
+        dist = rng2.uniform(0.13, 0.15, size=(batch, n_atoms - 1)).astype(np.float32).astype(np.float64)
+        ang = rng2.uniform(1.9, 2.2, size=(batch, n_atoms - 2)).astype(np.float32).astype(np.float64)
+        dih = rng2.uniform(-math.pi, math.pi, size=(batch, n_atoms - 3)).astype(np.float32).astype(np.float64)
+        me = _Self(left_split=n_atoms // 2 - 1, right_split=(n_atoms - 3) // 2)
+        xyz = np.asarray(R["BackMapLayer_call"](me, (tf64.convert_to_tensor(dist), tf64.convert_to_tensor(ang), tf64.convert_to_tensor(dih))))
+        xyz = xyz.astype(np.float32).astype(np.float64)   # float32-representable backbone
+        n_idx, c_idx = np.arange(n_atoms)[::3], np.arange(n_atoms)[2::3]   # reference tests/test_backmapping_em1_em2.py:571-591
+        k = f"n{n_atoms}"
+        g[f"{k}_xyz"] = xyz
+        h = R["guess_amide_H"](tf64.convert_to_tensor(xyz), n_idx)
+        o = R["guess_amide_O"](tf64.convert_to_tensor(xyz), c_idx)
+        g[f"{k}_H"], g[f"{k}_O"] = np.asarray(h), np.asarray(o)
+        g[f"{k}_merged"] = np.asarray(R["merge_cartesians"](tf64.convert_to_tensor(xyz), n_idx, c_idx, h, o))
+        h32 = R32["guess_amide_H"](tf32.convert_to_tensor(xyz.astype(np.float32)), n_idx)
+        g[f"{k}_H_f32"] = np.asarray(h32)
+    # an irregular selection: arbitrary centre atoms incl. the last one (falls back to atom i - 2) and generic angle / length
+    xyz = g["n30_xyz"]
+    sel = np.array([1, 4, 5, 17, 28, 29])
+    g["n30_sel"] = sel
+    g["n30_sp2_generic"] = np.asarray(R["guess_sp2_atom"](tf64.convert_to_tensor(xyz), sel, 1.9, 0.101))
+    np.savez_compressed(OUT / "generation.npz", **g)
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size} bytes")
 
