@@ -67,6 +67,8 @@ SIGNATURES = {
     "emk_dl_pairwise_dist_bwd": ([vp, i64, i64, i64, C.c_int, C.c_int, vp, vp, vp], C.c_int),
     "emk_cartesian_pair_loss": ([vp, i64, i64, i64, i64, i64, vp, C.c_int, C.c_int, f32, vp, vp, vp, vp], C.c_int),
     "emk_dl_cartesian_pair_loss": ([vp, i64, i64, i64, vp, C.c_int, f32, vp, vp, vp, vp], C.c_int),
+    "emk_cartesian_distance_cost": ([vp, i64, i64, i64, i64, i64, vp, i64, c_f32p, i64, i64, vp, vp, C.c_uint32, vp], C.c_int),
+    "emk_dl_cartesian_distance_cost": ([vp, i64, i64, i64, vp, c_f32p, i64, i64, vp, vp, C.c_uint32, vp], C.c_int),
     "emk_periodic_distance": ([vp, vp, i64, dbl, vp, vp], C.c_int),
     "emk_periodic_distance_bwd": ([vp, vp, i64, dbl, vp, vp, vp, vp], C.c_int),
     "emk_dl_periodic_distance": ([vp, vp, dbl, vp, vp], C.c_int),

@@ -630,3 +630,47 @@ class CartesianPairLoss(torch.autograd.Function):
         (grad,) = ctx.saved_tensors
         g = None if grad is None else (grad * (grad_output / ctx.count)).to(ctx.dtype)
         return g, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# cartesian_distance_loss straight from the coordinates
+# ---------------------------------------------------------------------------------------------------
+def cartesian_distance_cost_raw(xyz: torch.Tensor, low: torch.Tensor, sig: Sequence[float], start=None, stop=None, step=None,
+                                tile_range: Optional[Tuple[int, int]] = None, need_grad: bool = True):
+    """(loss float64[1], d(loss)/d(low) | None) of the sketch-map cost between the flat pair distances of the selected atoms of
+    every frame (high-d side, Euclidean) and the latent rows; the (frames, n_pairs) matrix only exists as library scratch."""
+    require_cuda(xyz, "cartesians")
+    require_cuda(low, "y_pred")
+    xyz, low = f32c(xyz), f32c(low)
+    if xyz.dim() != 3 or xyz.shape[2] != 3 or low.dim() != 2:
+        raise EmkError(-4, f"cartesian distance cost needs (b, n_atoms, 3) coordinates and a rank-2 latent, got {tuple(xyz.shape)} and {tuple(low.shape)}")
+    if tile_range is None:
+        tile_range = (0, _lib.pair_tile_count(xyz.shape[0]))
+    loss = torch.empty(1, dtype=torch.float64, device=xyz.device)
+    grad = torch.empty_like(low) if need_grad else None
+    flags = _lib.EMK_COST_ZERO_OUTPUTS | (0 if need_grad else _lib.EMK_COST_NO_GRAD)
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_dl_cartesian_distance_cost(DL(xyz), _idx(start), _idx(stop), _idx(step), DL(low), sig_array(sig), tile_range[0],
+                                                        tile_range[1], DL(loss), DL(grad), flags, stream_of(xyz)))
+    return loss, grad
+
+
+class CartesianDistanceCost(torch.autograd.Function):
+    """sigmoid cost of (pair distances of the input coordinates, latent): differentiable w.r.t. the latent; the coordinates are
+    input data (a ``cartesians`` that requires grad is refused, as ``y_true`` is in SigmoidCost)."""
+
+    @staticmethod
+    def forward(ctx, xyz, low, sig, start, stop, step, tile_range, reduce_fn):
+        _reject_high_grad(ctx.needs_input_grad[0])
+        loss, grad = cartesian_distance_cost_raw(xyz, low, sig, start, stop, step, tile_range, ctx.needs_input_grad[1])
+        if reduce_fn is not None:
+            loss, grad = reduce_fn(loss, grad)
+        ctx.save_for_backward(grad)
+        ctx.low_dtype = low.dtype
+        return loss[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        g = None if grad is None else (grad * grad_output).to(ctx.low_dtype)
+        return None, g, None, None, None, None, None, None

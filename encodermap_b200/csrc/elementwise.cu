@@ -669,7 +669,7 @@ __device__ __forceinline__ float sqrt_fast(float x) {   // one MUFU.SQRT (2 ulp)
 
 template <int C, bool SQUARED>
 __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
-                                                                          int64_t rstride, float* __restrict__ out) {
+                                                                          int64_t rstride, float* __restrict__ out, int64_t out_pitch) {
   __shared__ float4 sx4[PWW_THREADS / 32][PWW_MAX_N];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = n * (n - 1) / 2;
@@ -692,7 +692,10 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const 
       jj[c] = j < n ? j : -1;
     }
     __syncwarp();
-    float* orow = out + f * per - 1 + lane;   // orow[32 c] is the element (i, 32 c + lane) of the current row
+    // out_pitch >= per floats per frame; the tail [per, out_pitch) is zero-filled (a 16-byte row pitch lets the pair-tile
+    // kernel read the matrix through TMA as it stands: emk_cartesian_distance_cost)
+    for (int64_t k = per + lane; k < out_pitch; k += 32) out[f * out_pitch + k] = 0.f;
+    float* orow = out + f * out_pitch - 1 + lane;   // orow[32 c] is the element (i, 32 c + lane) of the current row
 #pragma unroll 1
     for (int i = 0; i < n - 1; i++) {
       const float4 xi = sx[i];
@@ -722,20 +725,24 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const 
 // backward of the same: grad_x[a] = sum_b coef_ab (x_a - x_b), coef = g / dist (2 g when squared), 0 at zero distance.
 // Every pair is visited once: its contribution to the COLUMN atom accumulates in the owning lane's registers; the
 // contributions to the ROW atom are per-lane partial sums that have to be added across the warp -- not by a butterfly per
-// row (30 instructions for three values) but through shared memory, 32 rows at a time: every lane stores its three partials
-// of a row (conflict-free), and after 32 rows lane l adds up row l with eight LDS.128 per component.
+// row (30 instructions for three values) but through shared memory, PWW_TR rows at a time: every lane stores its three
+// partials of a row (conflict-free), and after PWW_TR rows 3 x PWW_TR lanes each add up one (component, row) with eight
+// LDS.128.  The kernel is latency-bound (dependent FADD2 -> FFMA2 -> MUFU -> FFMA2 chains, one row after the other), so what
+// matters is resident warps: 7 KB of shared memory per warp and <= 64 registers give 32 warps per SM (the first version,
+// with a 32-row tile of 14 KB per warp, had 12 and ran at 0.12 of the HBM rate).
 constexpr int PWW_RPAD = 36;   // floats per row of the transpose tile: 16-byte aligned rows, conflict-free LDS.128 per quarter-warp
+constexpr int PWW_TR = 8;      // rows per transposition
+constexpr int PWW_BWD_PER_WARP = 4 * PWW_MAX_N + 3 * PWW_MAX_N + 3 * PWW_TR * PWW_RPAD;   // floats
 
 template <int C, bool SQUARED>
-__global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
-                                                                              int64_t rstride, const float* __restrict__ go,
-                                                                              float* __restrict__ gx) {
+__global__ void __launch_bounds__(PWW_THREADS, 8) pairwise_flat3_warp_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                                 int64_t rstride, const float* __restrict__ go,
+                                                                                 float* __restrict__ gx) {
   extern __shared__ __align__(16) float smw[];
-  constexpr int PER_WARP = 4 * PWW_MAX_N + 3 * PWW_MAX_N + 3 * 32 * PWW_RPAD;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4* sx = reinterpret_cast<float4*>(smw + (size_t)warp * PER_WARP);
-  float* sr = smw + (size_t)warp * PER_WARP + 4 * PWW_MAX_N;     // [3][PWW_MAX_N] row sums
-  float* tr = sr + 3 * PWW_MAX_N;                                 // [3][32][PWW_RPAD] transpose tile
+  float4* sx = reinterpret_cast<float4*>(smw + (size_t)warp * PWW_BWD_PER_WARP);
+  float* sr = smw + (size_t)warp * PWW_BWD_PER_WARP + 4 * PWW_MAX_N;     // [3][PWW_MAX_N] row sums
+  float* tr = sr + 3 * PWW_MAX_N;                                         // [3][PWW_TR][PWW_RPAD] transpose tile
   const int per = n * (n - 1) / 2;
   for (int64_t f = (int64_t)blockIdx.x * (PWW_THREADS / 32) + warp; f < b; f += (int64_t)gridDim.x * (PWW_THREADS / 32)) {
     const float* xb = x + f * bstride;
@@ -759,10 +766,8 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_bwd_kernel(co
     __syncwarp();
     // g / dist as g * rsqrt(max(s2, tiny)): a masked lane (g = 0) and a zero distance (d = 0 multiplies it) both give 0
     auto coef_of = [](float g, float s2) { return SQUARED ? 2.f * g : g * rsqrt_fast(fmaxf(s2, EMK_TINY)); };
-    // the upstream gradient of the next PF rows is in flight while a row is processed: a row is ~40 instructions, a global
-    // load ~700 cycles, and nothing else in the row loop can cover it (2.7 ms instead of 1 ms at 65 536 x 100 atoms when
-    // every row waited for its own load)
-    constexpr int PF = 4;
+    // the upstream gradient of the next PF rows is in flight while a row is processed
+    constexpr int PF = 2;
     const float* gpre = go + f * per - 1 + lane;    // gpre[32 c] is the element (row, 32 c + lane) of the row being prefetched
     int pre_row = 0;
     float gq[PF][C];
@@ -775,8 +780,8 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_bwd_kernel(co
 #pragma unroll
     for (int u = 0; u < PF; u++) prefetch(gq[u]);
 #pragma unroll 1
-    for (int i0 = 0; i0 < n - 1; i0 += 32) {
-      const int rows = min(32, n - 1 - i0);
+    for (int i0 = 0; i0 < n - 1; i0 += PWW_TR) {
+      const int rows = min(PWW_TR, n - 1 - i0);
 #pragma unroll 1
       for (int i4 = 0; i4 < rows; i4 += PF) {
 #pragma unroll
@@ -812,24 +817,24 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_bwd_kernel(co
               q0 = fmaf(cf, dx, q0); q1 = fmaf(cf, dy, q1); q2 = fmaf(cf, dz, q2);
               ax[c] = fmaf(cf, dx, ax[c]); ay[c] = fmaf(cf, dy, ay[c]); az[c] = fmaf(cf, dz, az[c]);
             }
-            tr[(0 * 32 + ii) * PWW_RPAD + lane] = q0;
-            tr[(1 * 32 + ii) * PWW_RPAD + lane] = q1;
-            tr[(2 * 32 + ii) * PWW_RPAD + lane] = q2;
+            tr[(0 * PWW_TR + ii) * PWW_RPAD + lane] = q0;
+            tr[(1 * PWW_TR + ii) * PWW_RPAD + lane] = q1;
+            tr[(2 * PWW_TR + ii) * PWW_RPAD + lane] = q2;
           }
         }
       }
       __syncwarp();
-      if (lane < rows) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const float4* rowp = reinterpret_cast<const float4*>(tr + (k * 32 + lane) * PWW_RPAD);
+      {
+        const int k = lane / PWW_TR, ii = lane % PWW_TR;     // lanes 0 .. 3 PWW_TR - 1: one (component, row) each
+        if (k < 3 && ii < rows) {
+          const float4* rowp = reinterpret_cast<const float4*>(tr + (k * PWW_TR + ii) * PWW_RPAD);
           float4 acc = rowp[0];
 #pragma unroll
           for (int q = 1; q < 8; q++) {
             const float4 v = rowp[q];
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
           }
-          sr[k * PWW_MAX_N + i0 + lane] = (acc.x + acc.y) + (acc.z + acc.w);
+          sr[k * PWW_MAX_N + i0 + ii] = (acc.x + acc.y) + (acc.z + acc.w);
         }
       }
       __syncwarp();
@@ -933,25 +938,31 @@ int column_mean_device(const float* x, int64_t rows, int64_t cols, float* out, c
   cudaFreeAsync(part, st);
   return rc;
 }
+// flat upper triangle of (b, n <= 128, 3) points, one warp per frame, `out_pitch` floats per output row (>= n (n-1) / 2)
+int pairwise_flat3_warp_device(const float* x, int64_t b, int64_t n, int64_t bstride, int64_t rstride, int squared, float* out,
+                               int64_t out_pitch, cudaStream_t st) {
+  EMK_REQUIRE(n >= 2 && n <= PWW_MAX_N && out_pitch >= n * (n - 1) / 2, EMK_E_ARG, "pairwise (warp per frame): bad geometry");
+  if (b == 0) return EMK_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 16);
+#define EMK_PWW(CC)                                                                                                                 \
+  do {                                                                                                                              \
+    if (squared) pairwise_flat3_warp_kernel<CC, true><<<grid, PWW_THREADS, 0, st>>>(x, b, (int)n, bstride, rstride, out, out_pitch); \
+    else pairwise_flat3_warp_kernel<CC, false><<<grid, PWW_THREADS, 0, st>>>(x, b, (int)n, bstride, rstride, out, out_pitch);        \
+  } while (0)
+  if (n <= 32) EMK_PWW(1);
+  else if (n <= 64) EMK_PWW(2);
+  else if (n <= 96) EMK_PWW(3);
+  else EMK_PWW(4);
+#undef EMK_PWW
+  return launch_status("pairwise_flat3_warp_kernel");
+}
+int pairwise_warp_max_atoms() { return PWW_MAX_N; }
+
 int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
                           int flat, float* out, cudaStream_t st) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
   if (b * per == 0) return EMK_OK;
-  if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) {
-    // one warp per frame; grid sized for whole waves of resident CTAs
-    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 16);
-#define EMK_PWW(CC)                                                                                                      \
-  do {                                                                                                                   \
-    if (squared) pairwise_flat3_warp_kernel<CC, true><<<grid, PWW_THREADS, 0, st>>>(x, b, (int)n, bstride, rstride, out); \
-    else pairwise_flat3_warp_kernel<CC, false><<<grid, PWW_THREADS, 0, st>>>(x, b, (int)n, bstride, rstride, out);        \
-  } while (0)
-    if (n <= 32) EMK_PWW(1);
-    else if (n <= 64) EMK_PWW(2);
-    else if (n <= 96) EMK_PWW(3);
-    else EMK_PWW(4);
-#undef EMK_PWW
-    return launch_status("pairwise_flat3_warp_kernel");
-  }
+  if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) return pairwise_flat3_warp_device(x, b, n, bstride, rstride, squared, out, per, st);
   if (flat && d == 3 && n >= 2 && n <= 8192) {
     if (n <= PWT_MAX_N) {
       const int64_t per3 = n * (n - 1) / 2;
@@ -981,8 +992,8 @@ int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, i
   // 129 .. 320 atoms: pair-once kernel (2.5x the thread-per-atom kernel at 300 atoms); up to 128 atoms the whole
   // upstream gradient of a frame fits in shared memory next to the coordinates and the thread-per-atom kernel is as fast
   if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) {
-    constexpr size_t smem = (size_t)(PWW_THREADS / 32) * (7 * PWW_MAX_N + 3 * 32 * PWW_RPAD) * sizeof(float);   // 69.6 KB: 3 CTAs / SM
-    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 3);
+    constexpr size_t smem = (size_t)(PWW_THREADS / 32) * PWW_BWD_PER_WARP * sizeof(float);   // 27.5 KB: 8 CTAs / SM
+    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 8);
 #define EMK_PWWB(CC, SQ)                                                                                                             \
   do {                                                                                                                               \
     static bool cfg[kMaxDevices] = {false};                                                                                          \

@@ -86,6 +86,8 @@ void tile_decode_host(int64_t t, int64_t n_rows, int64_t* I, int64_t* J);
 int sigmoid_cost_device(const float*, int64_t, int64_t, const float*, int64_t, double, const float*, int64_t, int64_t, double*,
                         float*, uint32_t, cudaStream_t);
 int dist_matrix_device(const float*, int64_t, int64_t, double, bool, int, float*, cudaStream_t);
+int pairwise_flat3_warp_device(const float*, int64_t, int64_t, int64_t, int64_t, int, float*, int64_t, cudaStream_t);
+int pairwise_warp_max_atoms();
 void set_cost_small_d_max(int64_t v);
 int64_t cost_small_d_max();
 int periodic_distance_device(const float*, const float*, int64_t, double, float*, cudaStream_t);
@@ -379,6 +381,63 @@ int emk_sigmoid_cost_host(const float* high_host, int64_t n, int64_t d, const fl
   }
   cleanup();
   return rc;
+}
+
+// ---- cartesian_distance_loss straight from coordinates ------------------------------------------------------
+// The high-d side of cartesian_distance_loss is the matrix of flat pair distances of the selected atoms, one row per frame
+// (models/models.py:837-839: inp_pair = PairwiseDistances(...)(inp_cartesians); :2419-2422: loss(inp_pair, latent)).  Here the
+// caller hands over the COORDINATES: the matrix is formed into stream-ordered scratch (16-byte row pitch, zero-filled tail, so
+// the pair-tile kernel reads it through TMA without the re-padding pass that D % 4 != 0 inputs otherwise need -- 4 950 and
+// 44 850 both are), consumed once and released; it never becomes a tensor of the host framework (no activation kept for the
+// backward pass, the largest one of the ADC step) and at training sizes (1 024 x 4 950: 20 MB) it lives in L2 between the two
+// kernels.  Forming the pair distances inside the pair-tile kernel instead was considered and rejected: a 128 x 64 tile would
+// recompute 192 frames' distances (13x redundantly over the 72 tiles of a 1 024-frame batch), ~25 % more issue slots on a
+// kernel that is bound by them, and 3x the L2 -> SM traffic of loading the finished rows.
+int emk_cartesian_distance_cost(const float* xyz, int64_t b, int64_t n_atoms, int64_t first, int64_t count, int64_t step, const float* low,
+                                int64_t l, const float sig[6], int64_t tile_begin, int64_t tile_end, double* loss, float* grad_low,
+                                uint32_t flags, void* stream) {
+  EMK_REQUIRE(xyz && low && sig && loss, EMK_E_NULL, "emk_cartesian_distance_cost: NULL pointer argument");
+  EMK_REQUIRE(b >= 0 && n_atoms >= 1 && count >= 2 && step >= 1 && first >= 0 && first + (count - 1) * step < n_atoms, EMK_E_SHAPE,
+              "emk_cartesian_distance_cost: atom selection (first %lld, count %lld, step %lld) needs >= 2 of %lld atoms", (long long)first,
+              (long long)count, (long long)step, (long long)n_atoms);
+  cudaStream_t st = as_stream(stream);
+  const int64_t per = count * (count - 1) / 2;
+  const bool pitched = count <= pairwise_warp_max_atoms();
+  const int64_t pitch = pitched ? (per + 3) / 4 * 4 : per;
+  if (b == 0) return sigmoid_cost_device(xyz, 0, pitch, low, l, INFINITY, sig, tile_begin, tile_end, loss, grad_low, flags, st);
+  float* pairs = nullptr;
+  int rc = scratch_alloc(reinterpret_cast<void**>(&pairs), (size_t)(b * pitch) * sizeof(float), st);
+  if (rc) return rc;
+  rc = pitched ? pairwise_flat3_warp_device(xyz + 3 * first, b, count, 3 * n_atoms, 3 * step, 0, pairs, pitch, st)
+               : pairwise_small_device(xyz + 3 * first, b, count, 3, 3 * n_atoms, 3 * step, 0, 1, pairs, st);
+  if (rc == EMK_OK) rc = sigmoid_cost_device(pairs, b, pitch, low, l, INFINITY, sig, tile_begin, tile_end, loss, grad_low, flags, st);
+  cudaFreeAsync(pairs, st);
+  return rc;
+}
+
+int emk_dl_cartesian_distance_cost(const DLManagedTensor* xyz, int64_t start, int64_t stop, int64_t step, const DLManagedTensor* low,
+                                   const float sig[6], int64_t tile_begin, int64_t tile_end, DLManagedTensor* loss, DLManagedTensor* grad_low,
+                                   uint32_t flags, void* stream) {
+  VIEW(xv, xyz, "cartesians", 3, 3);
+  VIEW(z, low, "low", 2, 2);
+  EMK_REQUIRE(xv.shape[2] == 3, EMK_E_SHAPE, "emk_dl_cartesian_distance_cost: cartesians must be (b, n_atoms, 3)");
+  EMK_REQUIRE(xv.shape[0] == z.shape[0], EMK_E_SHAPE, "emk_dl_cartesian_distance_cost: %lld frames, low has %lld rows", (long long)xv.shape[0],
+              (long long)z.shape[0]);
+  int64_t first, cnt, st;
+  int rc = resolve_slice(xv.shape[1], start, stop, step, &first, &cnt, &st);
+  if (rc) return rc;
+  View lv;
+  rc = view_of(loss, "loss", kDLFloat, 64, 0, 1, &lv);
+  if (rc) return rc;
+  EMK_REQUIRE(lv.numel == 1, EMK_E_SHAPE, "emk_dl_cartesian_distance_cost: loss must hold exactly one float64");
+  float* g = nullptr;
+  if (!(flags & EMK_COST_NO_GRAD)) {
+    VIEW(gv, grad_low, "grad_low", 2, 2);
+    EMK_REQUIRE(gv.shape[0] == z.shape[0] && gv.shape[1] == z.shape[1], EMK_E_SHAPE, "emk_dl_cartesian_distance_cost: grad_low shape differs from low");
+    g = F(gv);
+  }
+  return emk_cartesian_distance_cost(F(xv), xv.shape[0], xv.shape[1], first, cnt, st, F(z), z.shape[1], sig, tile_begin, tile_end,
+                                     static_cast<double*>(lv.data), g, flags, stream);
 }
 
 // ---- distance matrices -----------------------------------------------------------------------------------------------

@@ -107,7 +107,7 @@ static int check_indices(const char* what, const int64_t* idx, int64_t count, in
 // guess_sp2_atom(cartesians, indices, angle_to_previous, bond_length) -> (b, n_idx, 3)
 int guess_sp2_device(const float* xyz, int64_t b, int64_t n, const int64_t* indices, int64_t n_idx, double angle, double bond_length,
                      float* out, cudaStream_t st) {
-  EMK_REQUIRE(xyz && out, EMK_E_NULL, "emk_guess_sp2_atoms: NULL pointer argument");
+  EMK_REQUIRE((xyz && out) || b == 0 || (xyz && n_idx == 0), EMK_E_NULL, "emk_guess_sp2_atoms: NULL pointer argument");
   EMK_REQUIRE(b >= 0 && n >= 3 && n < (int64_t)PLAN_MASK, EMK_E_SHAPE, "emk_guess_sp2_atoms: need (b, n >= 3, 3) coordinates");
   int rc = check_indices("emk_guess_sp2_atoms", indices, n_idx, n);
   if (rc) return rc;
@@ -147,7 +147,7 @@ static int merge_plan(int64_t n, const int64_t* h_after, int64_t nh_after, const
 int merge_cartesians_device(const float* central, int64_t b, int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after,
                             int64_t no_after, const float* h_xyz, int64_t n_h, const float* o_xyz, int64_t n_o, float* out,
                             cudaStream_t st) {
-  EMK_REQUIRE(central && out && (n_h == 0 || h_xyz) && (n_o == 0 || o_xyz), EMK_E_NULL, "emk_merge_cartesians: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (central && out && (n_h == 0 || h_xyz) && (n_o == 0 || o_xyz)), EMK_E_NULL, "emk_merge_cartesians: NULL pointer argument");
   EMK_REQUIRE(b >= 0 && n >= 1 && n < (int64_t)PLAN_MASK && n_h >= 0 && n_o >= 0, EMK_E_SHAPE, "emk_merge_cartesians: bad shape");
   int rc = check_indices("emk_merge_cartesians (h_after)", h_after, nh_after, n);
   if (rc) return rc;
@@ -169,7 +169,7 @@ int merge_cartesians_device(const float* central, int64_t b, int64_t n, const in
 int backbone_amide_device(const float* central, int64_t b, int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after,
                           int64_t no_after, double h_angle, double h_len, double o_angle, double o_len, float* out, int64_t n_out,
                           cudaStream_t st) {
-  EMK_REQUIRE(central && out, EMK_E_NULL, "emk_backbone_amide_atoms: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (central && out), EMK_E_NULL, "emk_backbone_amide_atoms: NULL pointer argument");
   EMK_REQUIRE(b >= 0 && n >= 3 && n < (int64_t)PLAN_MASK, EMK_E_SHAPE, "emk_backbone_amide_atoms: need (b, n >= 3, 3) coordinates");
   int rc = check_indices("emk_backbone_amide_atoms (h_after)", h_after, nh_after, n);
   if (rc) return rc;

@@ -182,6 +182,37 @@ def cartesian_distance_loss(model, parameters=None, callback=None, *, process_gr
     return cartesian_distance_loss_func
 
 
+def cartesian_distance_loss_from_coordinates(model, parameters=None, callback=None, *, process_group=None, check_finite="deferred") -> Callable:
+    """``cartesian_distance_loss`` fed with the input COORDINATES instead of their stored pair distances.
+
+    Reference composition: ``inp_pair = PairwiseDistances(p, "input")(inp_cartesians)`` (models/models.py:837-839) followed by
+    ``cartesian_distance_loss(model, p)(inp_pair, latent)`` (:2419-2422, loss_functions.py:873-944).  ``f(cartesians, y_pred)``
+    returns the same value; the (batch, n_pairs) matrix -- the largest activation of the ADC step, 20 MB at 1 024 x 4 950 and
+    184 MB at 1 024 x 44 850 -- is library scratch that is gone when the call returns.  Atom selection: ``cartesian_pwd_start /
+    stop / step`` as in PairwiseDistances.  ``process_group`` shards the pair tiles over ranks as in ``sigmoid_loss``."""
+    p = ADCParameters() if parameters is None else parameters
+    sig = tuple(p.cartesian_dist_sig_parameters)
+    finite = _FiniteCheck(check_finite, "Cartesian distance cost became infinite or NaN.")
+
+    def cartesian_distance_loss_func(cartesians: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+        cartesian_distance_loss_func.name = "cartesian_distance_loss"
+        if p.cartesian_distance_cost_scale is not None:
+            tile_range, reduce_fn = None, None
+            if process_group is not None:
+                from ..parallel import tile_shard
+
+                tile_range, reduce_fn = tile_shard(int(cartesians.shape[0]), process_group)
+            dist_cost = _ops.CartesianDistanceCost.apply(cartesians, y_pred, sig, p.cartesian_pwd_start, p.cartesian_pwd_stop,
+                                                         p.cartesian_pwd_step, tile_range, reduce_fn) * p.cartesian_distance_cost_scale
+        else:
+            dist_cost = torch.zeros((), dtype=torch.float32, device=y_pred.device)
+        finite(dist_cost)
+        return dist_cost
+
+    cartesian_distance_loss_func.flush_finite_check = finite.flush
+    return cartesian_distance_loss_func
+
+
 def fused_cartesian_loss(model=None, scale_callback=None, parameters=None, log_callback=None, *, check_finite="deferred") -> Callable:
     """The Cartesian branch of the ADC step as ONE op: ``PairwiseDistances`` on the back-mapped coordinates + ``cartesian_loss``
     (reference: encodermap/models/layers.py:1252-1267 + encodermap/loss_functions/loss_functions.py:947-1067, called as

@@ -174,6 +174,22 @@ EMK_API int emk_dl_cartesian_pair_loss(const DLManagedTensor* xyz, int64_t start
                                        DLManagedTensor* clashes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * cartesian_distance_loss straight from the coordinates (no stored pair matrix)
+ *   reference: encodermap/models/models.py:837-839 (inp_pair = PairwiseDistances(p, "input")(inp_cartesians)) followed by
+ *   :2419-2422 (cartesian_distance_loss(model, p)(inp_pair, latent)), loss_functions.py:873-944.
+ * Same result as emk_pairwise_dist(flat) on the selected atoms + emk_sigmoid_cost(periodicity = +inf); the (frames, n_pairs)
+ * matrix lives in stream-ordered scratch between the two kernels (16-byte row pitch for TMA, zero-filled tail) and is released
+ * before the call returns.  Arguments as emk_sigmoid_cost with the frames as the rows of the pair problem; tile ranges refer to
+ * emk_pair_tile_count(b).  The selection needs at least two atoms.
+ * ---------------------------------------------------------------------------------------- */
+EMK_API int emk_cartesian_distance_cost(const float* xyz, int64_t b, int64_t n_atoms, int64_t first, int64_t count, int64_t step,
+                                        const float* low, int64_t l, const float sig[6], int64_t tile_begin, int64_t tile_end, double* loss,
+                                        float* grad_low, uint32_t flags, void* stream);
+EMK_API int emk_dl_cartesian_distance_cost(const DLManagedTensor* xyz, int64_t start, int64_t stop, int64_t step, const DLManagedTensor* low,
+                                           const float sig[6], int64_t tile_begin, int64_t tile_end, DLManagedTensor* loss,
+                                           DLManagedTensor* grad_low, uint32_t flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Elementwise ops
  * ---------------------------------------------------------------------------------------- */
 

@@ -1193,3 +1193,52 @@ def test_generation_generic_selection_and_errors(em, golden):
                              O.guess_amide_H(big[sub].astype(np.float64), np.arange(12)[::3]),
                              O.guess_amide_O(big[sub].astype(np.float64), np.arange(12)[2::3])).numpy()
     assert np.abs(out[sub] - ref).max() < 1e-4      # random geometry: nearly collinear neighbours amplify float32 rounding
+
+
+# ---------------------------------------------------------------------------------------------------
+# cartesian_distance_loss straight from the coordinates, reference models/models.py:837-839 + :2419-2422
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,n,sel", [(300, 30, (1, None, 3)), (1024, 300, (1, None, 3)), (130, 45, (None, None, None)),
+                                      (64, 402, (None, None, 3)), (200, 9, (2, 8, 2))])
+def test_cartesian_distance_loss_from_coordinates(em, b, n, sel):
+    """Value and d/d(latent) against the float64 oracle of the reference composition, and against the two-step GPU path
+    (PairwiseDistances + cartesian_distance_loss).  1024 x 300 with every third atom is BASELINE configs[2] (4 950 pair
+    dims: row pitch padded to 4 952); 402 atoms / step 3 = 134 atoms selects the unpitched fallback (> 128 atoms)."""
+    from encodermap_b200 import ADCParameters, _ops
+    from encodermap_b200.loss_functions import cartesian_distance_loss
+    from encodermap_b200.loss_functions.loss_functions import cartesian_distance_loss_from_coordinates
+    from encodermap_b200.models.layers import PairwiseDistances
+
+    rng = np.random.default_rng(b + n)
+    steps = rng.normal(size=(b, n, 3))
+    steps *= rng.uniform(0.12, 0.18, size=(b, n, 1)) / np.linalg.norm(steps, axis=2, keepdims=True)
+    # a few conformational families so that the high-d sigmoid is not saturated everywhere
+    fam = np.cumsum(steps[:6], axis=1)
+    xyz = (fam[rng.integers(0, 6, b)] + 0.02 * rng.normal(size=(b, n, 3))).astype(np.float32)
+    z = rng.normal(size=(b, 2)).astype(np.float32)
+    p = ADCParameters(cartesian_pwd_start=sel[0], cartesian_pwd_stop=sel[1], cartesian_pwd_step=sel[2], cartesian_distance_cost_scale=3.0,
+                      cartesian_dist_sig_parameters=(0.6, 6, 3, 1, 2, 6))
+    f = cartesian_distance_loss_from_coordinates(None, p)
+    zg = cu(z).requires_grad_(True)
+    loss = f(cu(xyz), zg)
+    loss.backward()
+    pairs = O.pairwise_distances_layer(torch.from_numpy(xyz).double(), *sel)
+    lref, gref = O.sigmoid_loss_and_grad(pairs.numpy(), z, float("inf"), p.cartesian_dist_sig_parameters)
+    np.testing.assert_allclose(loss.item(), 3.0 * lref.item(), rtol=LOSS_RTOL)
+    assert relnorm(zg.grad.cpu().numpy(), 3.0 * gref.numpy()) < GRAD_RTOL
+    # the reference composition on the GPU: stored pair matrix, then the loss
+    z2 = cu(z).requires_grad_(True)
+    loss2 = cartesian_distance_loss(None, p)(PairwiseDistances(p, "input")(cu(xyz)), z2)
+    loss2.backward()
+    np.testing.assert_allclose(loss.item(), loss2.item(), rtol=2e-6)
+    assert relnorm(zg.grad.cpu().numpy(), z2.grad.cpu().numpy()) < 2e-6
+    # tile ranges (multi-GPU split) add up
+    total = em._lib.pair_tile_count(b)
+    lsum, gsum = 0.0, 0.0
+    for a_, b_ in ((0, total // 2), (total // 2, total)):
+        lp, gp = _ops.cartesian_distance_cost_raw(cu(xyz), cu(z), p.cartesian_dist_sig_parameters, *sel, (a_, b_), True)
+        lsum += lp.item()
+        gsum = gsum + gp.double().cpu().numpy()
+    np.testing.assert_allclose(3.0 * lsum, loss.item(), rtol=3e-7)
+    with pytest.raises(em._lib.EmkError):
+        f(cu(xyz).requires_grad_(True), zg)            # the coordinates are data: their gradient is refused, not dropped

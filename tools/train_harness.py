@@ -24,7 +24,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from encodermap_b200 import ADCParameters, Parameters, parallel  # noqa: E402
 from encodermap_b200.graph import graphed_train_step  # noqa: E402
 from encodermap_b200.loss_functions import cartesian_distance_loss, distance_loss  # noqa: E402
-from encodermap_b200.loss_functions.loss_functions import fused_cartesian_loss  # noqa: E402
+from encodermap_b200.loss_functions.loss_functions import cartesian_distance_loss_from_coordinates, fused_cartesian_loss  # noqa: E402
 from encodermap_b200.misc.distances import periodic_distance  # noqa: E402
 from encodermap_b200.models.layers import BackMapLayer, PairwiseDistances, PeriodicInput  # noqa: E402
 
@@ -94,6 +94,9 @@ class ADCStep(nn.Module):
         self.pairwise = PairwiseDistances(p, "pairwise")
         self.cart_dist_loss = cartesian_distance_loss(self, p, process_group=dp_group, data_parallel=dp_group is not None)
         self.fused_loss = fused_cartesian_loss(None, None, p)
+        # fused mode also takes cartesian_distance_loss straight from the input coordinates: with both, the
+        # step holds no (batch, n_pairs) tensor at all
+        self.cart_dist_loss_xyz = cartesian_distance_loss_from_coordinates(self, p)
         self.dp_group = dp_group
 
     def encoder(self, inputs, training=False):
@@ -112,7 +115,8 @@ class ADCStep(nn.Module):
             torch.distributed.all_reduce(lengths, group=self.dp_group)
             distances = (lengths / torch.distributed.get_world_size(self.dp_group)).expand_as(distances)
         back = self.backmap((distances, out_angles, out_dihedrals))
-        inp_pair = self.pairwise(cartesians)
+        fused_all = self.fused_cartesian and self.dp_group is None
+        inp_pair = None if fused_all else self.pairwise(cartesians)
         dihedral_loss = periodic_distance(dihedrals, out_dihedrals, self.p.periodicity).mean()
         angle_loss = periodic_distance(angles, out_angles, self.p.periodicity).mean()
         if self.fused_cartesian:
@@ -122,7 +126,8 @@ class ADCStep(nn.Module):
             cartesian_loss = (inp_pair - out_pair).abs().mean()
         reg = sum((m.weight ** 2).sum() for m in self.modules() if isinstance(m, nn.Linear)) * self.p.l2_reg_constant
         center = (z ** 2).mean() * self.p.center_cost_scale
-        return dihedral_loss + angle_loss + cartesian_loss + self.cart_dist_loss(inp_pair, z) + center + reg
+        cart_dist = self.cart_dist_loss_xyz(cartesians, z) if fused_all else self.cart_dist_loss(inp_pair, z)
+        return dihedral_loss + angle_loss + cartesian_loss + cart_dist + center + reg
 
 
 def time_steps(model, batch_fn, steps=20, warmup=5, graph=False, grad_sync=None):
