@@ -728,14 +728,15 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const 
 // row (30 instructions for three values) but through shared memory, PWW_TR rows at a time: every lane stores its three
 // partials of a row (conflict-free), and after PWW_TR rows 3 x PWW_TR lanes each add up one (component, row) with eight
 // LDS.128.  The kernel is latency-bound (dependent FADD2 -> FFMA2 -> MUFU -> FFMA2 chains, one row after the other), so what
-// matters is resident warps: 7 KB of shared memory per warp and <= 64 registers give 32 warps per SM (the first version,
-// with a 32-row tile of 14 KB per warp, had 12 and ran at 0.12 of the HBM rate).
+// matters is resident warps: 7 KB of shared memory per warp and <= 80 registers give 24 warps per SM (the first version,
+// with a 32-row tile of 14 KB per warp, had 12 and ran at 0.12 of the HBM rate; capping at 64 registers for 32 warps spilled
+// into the row loop and every row waited for local-memory loads).
 constexpr int PWW_RPAD = 36;   // floats per row of the transpose tile: 16-byte aligned rows, conflict-free LDS.128 per quarter-warp
 constexpr int PWW_TR = 8;      // rows per transposition
 constexpr int PWW_BWD_PER_WARP = 4 * PWW_MAX_N + 3 * PWW_MAX_N + 3 * PWW_TR * PWW_RPAD;   // floats
 
 template <int C, bool SQUARED>
-__global__ void __launch_bounds__(PWW_THREADS, 8) pairwise_flat3_warp_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+__global__ void __launch_bounds__(PWW_THREADS, 6) pairwise_flat3_warp_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
                                                                                  int64_t rstride, const float* __restrict__ go,
                                                                                  float* __restrict__ gx) {
   extern __shared__ __align__(16) float smw[];
@@ -993,7 +994,7 @@ int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, i
   // upstream gradient of a frame fits in shared memory next to the coordinates and the thread-per-atom kernel is as fast
   if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) {
     constexpr size_t smem = (size_t)(PWW_THREADS / 32) * PWW_BWD_PER_WARP * sizeof(float);   // 27.5 KB: 8 CTAs / SM
-    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 8);
+    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 6);
 #define EMK_PWWB(CC, SQ)                                                                                                             \
   do {                                                                                                                               \
     static bool cfg[kMaxDevices] = {false};                                                                                          \
