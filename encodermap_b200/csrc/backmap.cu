@@ -644,6 +644,63 @@ __device__ __forceinline__ void sincos_f6_x2(float xa, float xb, uint32_t tabB, 
   }
 }
 
+// ---- float32 chain (first pass of version 6, round 2) ---------------------------------------------------------------
+// The float64 chain is bound by issue slots with FP64 instructions counting twice (118 issue cycles per warp-step).  A
+// float32 chain in coordinates RELATIVE TO THE SIDE'S ANCHOR ATOM needs ~50: rotation columns as FFMA2 pairs (rows 0 and
+// 1 packed, row 2 scalar), correctly rounded float32 sin/cos from a hi/lo table, no conversions.  Its error is a random walk
+// of the orientation: measured <= 4e-6 x (extent of the side) over 4 096 chains of 750 steps (random coils, helices,
+// extended chains; tools/experiments/f32_chain_error.py), i.e. 2.6e-5 nm for a 16 nm side against the 1e-4 nm tolerance.
+// Every lane therefore tracks the extent of its side (max |p - anchor|^2 at the group ends); if any lane of a tile pair
+// exceeds the limit (emk_set_option("backmap_fwd6_f32_extent_nm"): 16 keeps the error below 7e-5 nm), the pair repeats the
+// tile with the float64 chain -- the same second pass that catches angles beyond the table range.  The planar prologue
+// (anchor frame) stays float64: its error would rotate the whole side.  OPT-IN: measured on B200 it does not pay (see
+// g_fwd6_f32_extent below); kept as the tested answer to "would a float32 chain be faster".
+struct Se3f {
+  float2 x01, y01, z01, p01;   // rows 0 and 1 of the columns x, y, z of R, and of the position
+  float x2, y2, z2, p2;        // row 2
+};
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
+
+// sin / cos of two angles, correctly rounded to float32 up to ~1e-9: entry {s_hi, c_hi, s_lo, c_lo} of the 128-entry table
+// (8 replicas, lane l reads replica l & 7), sin(a + r) = s_hi + (s_lo + s_hi (cos r - 1) + c_hi sin r) and the like for cos;
+// the bracket is below 0.025 in magnitude, so its float32 rounding is 1.5e-9.  |x| < SC6_LIMIT as for the float64 form.
+__device__ __forceinline__ void sincos_tab32_x2(float xa, float xb, uint32_t tabF, float& sa, float& ca, float& sb, float& cb) {
+  const float2 x = make_float2(xa, xb);
+  const float2 km = __ffma2_rn(x, bc2(20.371832715762604f), bc2(12582912.f));
+  const float2 kf = __fadd2_rn(km, bc2(-12582912.f));
+  float2 r = __ffma2_rn(kf, bc2(-0.0490722656250f), x);
+  r = __ffma2_rn(kf, bc2(-1.5117228031158447e-05f), r);
+  r = __ffma2_rn(kf, bc2(-2.3593094145013538e-09f), r);
+  const float2 r2 = __fmul2_rn(r, r);
+  const float2 sr = __ffma2_rn(__fmul2_rn(r, r2), bc2(-0.16666667f), r);                 // sin r
+  const float2 cm = __fmul2_rn(r2, __ffma2_rn(r2, bc2(0.041666668f), bc2(-0.5f)));       // cos r - 1
+  float4 ta, tb;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ta.x), "=f"(ta.y), "=f"(ta.z), "=f"(ta.w)
+      : "r"(tabF + (((uint32_t)__float_as_int(km.x) & (SC6 - 1)) << 7)));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(tb.x), "=f"(tb.y), "=f"(tb.z), "=f"(tb.w)
+      : "r"(tabF + (((uint32_t)__float_as_int(km.y) & (SC6 - 1)) << 7)));
+  const float2 ua = __ffma2_rn(make_float2(ta.x, ta.y), bc2(cm.x), make_float2(ta.z, ta.w));
+  const float2 ub = __ffma2_rn(make_float2(tb.x, tb.y), bc2(cm.y), make_float2(tb.z, tb.w));
+  sa = ta.x + fmaf(ta.y, sr.x, ua.x);
+  ca = ta.y + fmaf(-ta.x, sr.x, ua.y);
+  sb = tb.x + fmaf(tb.y, sr.y, ub.x);
+  cb = tb.y + fmaf(-tb.x, sr.y, ub.y);
+}
+
+// NeRF step in float32: R <- R Rx(phi) Rz(g), p <- p + L R e_x   (cw, sw = cos / sin phi; cg, sg = cos / sin g)
+__device__ __forceinline__ void nerf_step32(Se3f& f, float cw, float sw, float cg, float sg, float L) {
+  const float2 y1 = __ffma2_rn(f.z01, bc2(sw), __fmul2_rn(f.y01, bc2(cw)));    // column y of R Rx
+  const float2 z1 = __ffma2_rn(f.y01, bc2(-sw), __fmul2_rn(f.z01, bc2(cw)));   // column z of R Rx
+  const float y1s = fmaf(f.z2, sw, f.y2 * cw), z1s = fmaf(-f.y2, sw, f.z2 * cw);
+  const float2 xn = __ffma2_rn(y1, bc2(sg), __fmul2_rn(f.x01, bc2(cg)));       // column x of (R Rx) Rz
+  const float2 yn = __ffma2_rn(f.x01, bc2(-sg), __fmul2_rn(y1, bc2(cg)));
+  const float xns = fmaf(y1s, sg, f.x2 * cg), yns = fmaf(-f.x2, sg, y1s * cg);
+  f.x01 = xn; f.y01 = yn; f.z01 = z1;
+  f.x2 = xns; f.y2 = yns; f.z2 = z1s;
+  f.p01 = __ffma2_rn(bc2(L), xn, f.p01);
+  f.p2 = fmaf(L, xns, f.p2);
+}
+
 // stage elements [e0, e0 + 8) of 32 consecutive rows (frames frame0 ..) into a dense [frame][8] tile: lane -> (element
 // q = lane & 7, frame lane >> 3 + 4 j), i.e. a warp instruction moves four 32-byte row segments into 128 consecutive bytes
 // of shared memory.  Rows beyond the batch are skipped (their tile rows keep the zeros written at start-up); elements outside
@@ -731,16 +788,29 @@ __device__ __forceinline__ void f6_step(float fd, float fa, double L, uint32_t t
 // tD0 / tA0: this warp's dihedral / angle tiles (buffer 1 follows buffer 0 at + F6_IN_TILE words); outT: the output group.
 // ROBUST = false: whole 8-atom groups run the table path unconditionally and only track max |angle| (returned): the caller
 // repeats the tile with ROBUST = true -- every step tests its angles -- if any lane saw an angle beyond the table path's range.
-template <int SIDE, bool A8, bool ROBUST>
+// F32 = true: the float32 chain relative to the anchor (see above); *ext2 receives the squared extent of this lane's side
+template <int SIDE, bool A8, bool ROBUST, bool F32>
 __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angles, const float* __restrict__ dihedrals, const double* L64,
-                                          uint32_t tabB, float* tD0, float* tA0, float* outT, const CUtensorMap* omap,
-                                          float* __restrict__ dst, int64_t frame0, int64_t b, int n, bool valid, int lane) {
+                                          const float* L32, uint32_t tabB, uint32_t tabF, float* tD0, float* tA0, float* outT,
+                                          const CUtensorMap* omap, float* __restrict__ dst, int64_t frame0, int64_t b, int n, bool valid,
+                                          int lane, float* ext2) {
   const int s = n / 2, nd = n - 3, na = n - 2;
   constexpr int dir = SIDE ? 1 : -1;
   constexpr int sh_d = SIDE ? -3 : 0, sh_a = SIDE ? -2 : 0, sh_l = SIDE ? -1 : 0;
   const int k_first = SIDE ? s + 2 : s - 2, k_last = SIDE ? n - 1 : 0;     // inclusive
   float amax = 0.f;
   if (SIDE ? (k_first > k_last) : (k_first < k_last)) return amax;
+  // float32 state: orientation as packed columns, position relative to the anchor atom, the anchor as a float32 hi/lo pair
+  Se3f g32;
+  float ahx = 0.f, ahy = 0.f, ahz = 0.f, alx = 0.f, aly = 0.f, alz = 0.f, e2 = 0.f;
+  if (F32) {
+    g32.x01 = make_float2((float)f.r[0], (float)f.r[3]); g32.x2 = (float)f.r[6];
+    g32.y01 = make_float2((float)f.r[1], (float)f.r[4]); g32.y2 = (float)f.r[7];
+    g32.z01 = make_float2((float)f.r[2], (float)f.r[5]); g32.z2 = (float)f.r[8];
+    g32.p01 = make_float2(0.f, 0.f); g32.p2 = 0.f;
+    ahx = (float)f.p[0]; ahy = (float)f.p[1]; ahz = (float)f.p[2];
+    alx = (float)(f.p[0] - (double)ahx); aly = (float)(f.p[1] - (double)ahy); alz = (float)(f.p[2] - (double)ahz);
+  }
   const int g_first = k_first >> 3, g_last = k_last >> 3;
   const uint32_t sD0 = (uint32_t)__cvta_generic_to_shared(tD0), sA0 = (uint32_t)__cvta_generic_to_shared(tA0);
   const int swz = (lane >> 2) & 1;                           // this row's halves are swapped in the tiles
@@ -778,23 +848,40 @@ __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angl
         const float4 d4 = *reinterpret_cast<const float4*>(td + 4 * (hm ^ swz));
         const float4 a4 = *reinterpret_cast<const float4*>(ta + 4 * (hm ^ swz));
         const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
-        const double* Lp = L64 + (8 * g + 4 * hm + sh_l);
+        if (F32) {
+          const float* Lp = L32 + (8 * g + 4 * hm + sh_l);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int pu = SIDE ? u : 3 - u;       // atom 4 hm + pu is placed by step u of this half
-          double sw, cw, sg, cg;
-          if (ROBUST) {
-            sincos_f6_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
-          } else {
+          for (int u = 0; u < 4; u++) {
+            const int pu = SIDE ? u : 3 - u;       // atom 4 hm + pu is placed by step u of this half
+            float sw, cw, sg, cg;
             amax = fmaxf(amax, fmaxf(fabsf(dv[pu]), fabsf(av[pu])));
-            sincos_tab64_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
+            sincos_tab32_x2(dv[pu], av[pu], tabF, sw, cw, sg, cg);
+            nerf_step32(g32, cw, sw, -cg, sg, Lp[pu]);
+            const float2 o01 = __fadd2_rn(make_float2(ahx, ahy), __fadd2_rn(make_float2(alx, aly), g32.p01));
+            pend[12 * hm + 3 * pu] = o01.x;
+            pend[12 * hm + 3 * pu + 1] = o01.y;
+            pend[12 * hm + 3 * pu + 2] = ahz + (alz + g32.p2);
           }
-          nerf_step(f, cw, sw, -cg, sg, Lp[pu]);
-          pend[12 * hm + 3 * pu] = (float)f.p[0];
-          pend[12 * hm + 3 * pu + 1] = (float)f.p[1];
-          pend[12 * hm + 3 * pu + 2] = (float)f.p[2];
+        } else {
+          const double* Lp = L64 + (8 * g + 4 * hm + sh_l);
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int pu = SIDE ? u : 3 - u;       // atom 4 hm + pu is placed by step u of this half
+            double sw, cw, sg, cg;
+            if (ROBUST) {
+              sincos_f6_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
+            } else {
+              amax = fmaxf(amax, fmaxf(fabsf(dv[pu]), fabsf(av[pu])));
+              sincos_tab64_x2(dv[pu], av[pu], tabB, &sw, &cw, &sg, &cg);
+            }
+            nerf_step(f, cw, sw, -cg, sg, Lp[pu]);
+            pend[12 * hm + 3 * pu] = (float)f.p[0];
+            pend[12 * hm + 3 * pu + 1] = (float)f.p[1];
+            pend[12 * hm + 3 * pu + 2] = (float)f.p[2];
+          }
         }
       }
+      if (F32) e2 = fmaxf(e2, fmaf(g32.p01.x, g32.p01.x, fmaf(g32.p01.y, g32.p01.y, g32.p2 * g32.p2)));
       if (lane == 0) bulk_wait_read0();          // the previous group has left the buffer (the storing lane tracks the bulk groups)
       __syncwarp();
       float4* row4 = reinterpret_cast<float4*>(outT + lane * 24);
@@ -810,26 +897,42 @@ __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angl
       for (int k = ka; k != kb + dir; k += dir) {
         const int slot = k & 7;
         float ox, oy, oz;
-        f6_step(td[slot ^ (4 * swz)], ta[slot ^ (4 * swz)], L64[k + sh_l], tabB, f, ox, oy, oz);
+        if (F32) {
+          const float fd = td[slot ^ (4 * swz)], fa = ta[slot ^ (4 * swz)];
+          float sw, cw, sg, cg;
+          amax = fmaxf(amax, fmaxf(fabsf(fd), fabsf(fa)));     // beyond the table range: the second pass redoes the tile
+          sincos_tab32_x2(fd, fa, tabF, sw, cw, sg, cg);
+          nerf_step32(g32, cw, sw, -cg, sg, L32[k + sh_l]);
+          ox = ahx + (alx + g32.p01.x); oy = ahy + (aly + g32.p01.y); oz = ahz + (alz + g32.p2);
+        } else {
+          f6_step(td[slot ^ (4 * swz)], ta[slot ^ (4 * swz)], L64[k + sh_l], tabB, f, ox, oy, oz);
+        }
         if (valid) { dst[3 * k] = ox; dst[3 * k + 1] = oy; dst[3 * k + 2] = oz; }
       }
+      if (F32) e2 = fmaxf(e2, fmaf(g32.p01.x, g32.p01.x, fmaf(g32.p01.y, g32.p01.y, g32.p2 * g32.p2)));
     }
     __syncwarp();
     buf ^= 1;
   }
   cp_async_wait0();
+  *ext2 = e2;
   return amax;
 }
 
-template <bool A8, int F6_WARPS>
+template <bool A8, int F6_WARPS, bool F32>
 __global__ void __launch_bounds__(32 * F6_WARPS, 1) backmap_fwd6_kernel(const __grid_constant__ CUtensorMap omap, const float* __restrict__ lengths,
                                                                      const float* __restrict__ angles, const float* __restrict__ dihedrals,
-                                                                     int64_t b, int n, float* __restrict__ xyz, const double2* __restrict__ tab) {
+                                                                     int64_t b, int n, float* __restrict__ xyz, const double2* __restrict__ tab,
+                                                                     float ext2_limit) {
   extern __shared__ __align__(1024) float smem6[];
   double2* tabS = reinterpret_cast<double2*>(smem6);                       // [SC6][8]
   double* L64 = reinterpret_cast<double*>(smem6 + SC6 * 8 * 4);            // [n - 1], region rounded up to 128 bytes
   const int lwords = ((2 * (n - 1) + 31) / 32) * 32;
-  float* warp_base = smem6 + SC6 * 8 * 4 + lwords;
+  // float32 first pass: hi/lo table [SC6][8] of float4 and the bond lengths as float32
+  float4* tabF4 = reinterpret_cast<float4*>(smem6 + SC6 * 8 * 4 + lwords);
+  float* L32 = smem6 + SC6 * 8 * 4 + lwords + (F32 ? SC6 * 8 * 4 : 0);
+  const int l32words = F32 ? ((n - 1 + 31) / 32) * 32 : 0;
+  float* warp_base = L32 + l32words;
 
   constexpr int F6_THREADS = 32 * F6_WARPS;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -838,11 +941,20 @@ __global__ void __launch_bounds__(32 * F6_WARPS, 1) backmap_fwd6_kernel(const __
   const int side = warp & 1, pair = warp >> 1;
   for (int i = tid; i < SC6 * 8; i += F6_THREADS) tabS[i] = __ldg(tab + (i >> 3) * (SC_TABLE / SC6));
   for (int i = tid; i < n - 1; i += F6_THREADS) L64[i] = (double)__ldg(lengths + i);
+  if (F32) {
+    for (int i = tid; i < SC6 * 8; i += F6_THREADS) {
+      const double2 t = __ldg(tab + (i >> 3) * (SC_TABLE / SC6));
+      const float sh = (float)t.x, ch = (float)t.y;
+      tabF4[i] = make_float4(sh, ch, (float)(t.x - (double)sh), (float)(t.y - (double)ch));
+    }
+    for (int i = tid; i < n - 1; i += F6_THREADS) L32[i] = __ldg(lengths + i);
+  }
   float* wmem = warp_base + (size_t)warp * F6_WARP_WORDS;
   for (int i = lane; i < F6_WARP_WORDS; i += 32) wmem[i] = 0.f;
   __syncthreads();
 
   const uint32_t tabB = (uint32_t)__cvta_generic_to_shared(tabS + (lane & 7));   // this lane's table replica
+  const uint32_t tabF = (uint32_t)__cvta_generic_to_shared(tabF4 + (lane & 7));
   float* tD0 = wmem;                                                       // dihedral tiles: buffer 1 at + F6_IN_TILE
   float* tA0 = wmem + 2 * F6_IN_TILE;                                      // angle tiles
   float* outT = wmem + 4 * F6_IN_TILE;                                     // 128-byte aligned: 4 KB into a 7 KB region
@@ -953,20 +1065,22 @@ __global__ void __launch_bounds__(32 * F6_WARPS, 1) backmap_fwd6_kernel(const __
     }
 
     // ---- the chain of this side (side is warp uniform: the instantiations keep every register index static) ----------
-    float amax;
+    // pass 0: float32 chain (F32) or float64 chain without per-step range tests; pass 1: float64 chain, every step tested
+    float amax, ext2 = 0.f;
     if (pass == 0) {
-      if (side) amax = f6_chain<1, A8, false>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
-      else amax = f6_chain<0, A8, false>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
+      if (side) amax = f6_chain<1, A8, false, F32>(f, angles, dihedrals, L64, L32, tabB, tabF, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane, &ext2);
+      else amax = f6_chain<0, A8, false, F32>(f, angles, dihedrals, L64, L32, tabB, tabF, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane, &ext2);
     } else {
-      if (side) amax = f6_chain<1, A8, true>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
-      else amax = f6_chain<0, A8, true>(f, angles, dihedrals, L64, tabB, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane);
+      if (side) amax = f6_chain<1, A8, true, false>(f, angles, dihedrals, L64, L32, tabB, tabF, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane, &ext2);
+      else amax = f6_chain<0, A8, true, false>(f, angles, dihedrals, L64, L32, tabB, tabF, tD0, tA0, outT, &omap, dst, frame0, b, n, valid, lane, &ext2);
     }
     if (lane == 0) bulk_wait_read0();   // the output buffer doubles as the exchange buffer of the next tile / pass
     __syncwarp();
     // both warps of the pair must agree on repeating (they meet at the named barrier of the prologue): the flag travels
     // through the exchange buffers
     if (pass == 0) {
-      const bool bad = __any_sync(0xffffffffu, amax >= SC6_LIMIT);
+      // rows beyond the batch hold zeros (no extent); a NaN extent compares false: NaN frames stay NaN, they need no redo
+      const bool bad = __any_sync(0xffffffffu, amax >= SC6_LIMIT || (F32 && valid && ext2 >= ext2_limit));
       if (lane == 0) reinterpret_cast<int*>(outT)[0] = bad ? 1 : 0;
       asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
       const bool redo = bad || reinterpret_cast<const int*>(partner_out)[0] != 0;
@@ -1616,8 +1730,18 @@ static int get_sincos_table(const double2** out) {
 static std::atomic<int64_t> g_fwd6_warps{0};
 int64_t fwd6_warps() { return g_fwd6_warps.load(); }
 void set_fwd6_warps(int64_t v) { g_fwd6_warps.store(v); }
-static size_t fwd6_smem_bytes(int64_t n, int warps) {
-  return (size_t)(SC6 * 8 * 4 + ((2 * (n - 1) + 31) / 32) * 32 + warps * F6_WARP_WORDS) * sizeof(float);
+// extent limit (nm) of the float32 first pass; 0 (default) = float64 chain only (emk_set_option("backmap_fwd6_f32_extent_nm", v)).
+// OFF by default, by measurement (tools/experiments/fwd6_extent_sweep.py, 65 536 x 1 500): the float32 pass takes 0.634 ms
+// against 0.661 ms for the float64 chain when no tile falls back -- the kernel is bound by the LATENCY of the dependent
+// chain of a step at 16 warps per SM, not by issue slots, so halving the issue slots buys 4 % -- and with the 16 nm limit
+// that the 1e-4 nm tolerance needs, the 0.06 % of frames beyond it make 2 % of the tiles run twice, which costs 33 %
+// through the makespan of the persistent pairs (0.843 ms).
+static std::atomic<int64_t> g_fwd6_f32_extent{0};
+int64_t fwd6_f32_extent() { return g_fwd6_f32_extent.load(); }
+void set_fwd6_f32_extent(int64_t v) { g_fwd6_f32_extent.store(v < 0 ? 0 : v); }
+static size_t fwd6_smem_bytes(int64_t n, int warps, bool f32) {
+  const int64_t extra = f32 ? SC6 * 8 * 4 + ((n - 1 + 31) / 32) * 32 : 0;   // hi/lo table + float32 bond lengths
+  return (size_t)(SC6 * 8 * 4 + ((2 * (n - 1) + 31) / 32) * 32 + extra + warps * F6_WARP_WORDS) * sizeof(float);
 }
 int encode_f32_map_2d(void* map_out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_cols,
                       uint32_t box_rows, int swizzle_128b);   // pair_tile.cu
@@ -1630,15 +1754,15 @@ static std::atomic<int64_t> g_fwd6_min_batch{[] {
 int64_t fwd6_min_batch() { return g_fwd6_min_batch.load(); }
 void set_fwd6_min_batch(int64_t v) { g_fwd6_min_batch.store(v); }
 
-template <bool A8, int W>
+template <bool A8, int W, bool F32>
 static int fwd6_launch_w(const CUtensorMap& omap, const float* lengths, const float* angles, const float* dihedrals, int64_t b, int64_t n,
-                         float* xyz, const double2* tab, cudaStream_t st) {
-  auto kern = backmap_fwd6_kernel<A8, W>;
+                         float* xyz, const double2* tab, float ext2_limit, cudaStream_t st) {
+  auto kern = backmap_fwd6_kernel<A8, W, F32>;
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t tiles = (b + 31) / 32;
   const int64_t blocks = std::min<int64_t>((tiles + W / 2 - 1) / (W / 2), (int64_t)sm_count());
-  kern<<<(unsigned)blocks, 32 * W, fwd6_smem_bytes(n, W), st>>>(omap, lengths, angles, dihedrals, b, (int)n, xyz, tab);
+  kern<<<(unsigned)blocks, 32 * W, fwd6_smem_bytes(n, W, F32), st>>>(omap, lengths, angles, dihedrals, b, (int)n, xyz, tab, ext2_limit);
   return launch_status("backmap_fwd6_kernel");
 }
 static int backmap_fwd6_launch(const float* lengths, const float* angles, const float* dihedrals, int64_t b, int64_t n, float* xyz,
@@ -1649,8 +1773,16 @@ static int backmap_fwd6_launch(const float* lengths, const float* angles, const 
   if (rc) return rc;
   // n % 4 == 0 makes the rows of `angles` (n - 2 floats) 8-byte aligned whenever the base is: 8-byte cp.async for that array
   const bool a8 = (reinterpret_cast<uintptr_t>(angles) & 7) == 0;
-#define EMK_F6(W) return a8 ? fwd6_launch_w<true, W>(omap, lengths, angles, dihedrals, b, n, xyz, tab, st) \
-                            : fwd6_launch_w<false, W>(omap, lengths, angles, dihedrals, b, n, xyz, tab, st)
+  const bool f32 = fwd6_f32_extent() > 0;
+  const float lim = (float)fwd6_f32_extent();
+  const float ext2_limit = lim * lim;
+#define EMK_F6(W)                                                                                                              \
+  do {                                                                                                                         \
+    if (f32) return a8 ? fwd6_launch_w<true, W, true>(omap, lengths, angles, dihedrals, b, n, xyz, tab, ext2_limit, st)        \
+                       : fwd6_launch_w<false, W, true>(omap, lengths, angles, dihedrals, b, n, xyz, tab, ext2_limit, st);      \
+    return a8 ? fwd6_launch_w<true, W, false>(omap, lengths, angles, dihedrals, b, n, xyz, tab, ext2_limit, st)                \
+              : fwd6_launch_w<false, W, false>(omap, lengths, angles, dihedrals, b, n, xyz, tab, ext2_limit, st);              \
+  } while (0)
   if (warps <= 8) EMK_F6(8);
   if (warps <= 12) EMK_F6(12);
   if (warps <= 14) EMK_F6(14);
@@ -1676,7 +1808,7 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
     int best = 0;
     double best_eff = 0.0;
     for (int w : cand) {
-      if (fwd6_smem_bytes(n, w) > 227 * 1024) continue;   // long chains: the bond lengths take the room of warps
+      if (fwd6_smem_bytes(n, w, fwd6_f32_extent() > 0) > 227 * 1024) continue;   // long chains: the bond lengths take the room of warps
       if (fwd6_warps() != 0 && w != fwd6_warps()) continue;
       const int64_t cap = sms * (w / 2);
       const double eff = (double)tiles / (double)(((tiles + cap - 1) / cap) * cap) * (w == 8 ? 0.85 : 1.0);   // 8 warps hide less latency

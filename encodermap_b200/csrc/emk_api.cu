@@ -124,6 +124,8 @@ struct CartLossParams {
 int cart_pair_loss_device(const CartLossParams&, cudaStream_t);
 int64_t fwd6_min_batch();
 void set_fwd6_min_batch(int64_t);
+int64_t fwd6_f32_extent();
+void set_fwd6_f32_extent(int64_t);
 int64_t fwd6_warps();
 void set_fwd6_warps(int64_t);
 int d2c_chain_bwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, int, float*, cudaStream_t);
@@ -239,6 +241,11 @@ int emk_set_option(const char* name, int64_t value) {
     set_cost_small_d_max(value);
     return EMK_OK;
   }
+  if (strcmp(name, "backmap_fwd6_f32_extent_nm") == 0) {
+    EMK_REQUIRE(value >= 0 && value <= 64, EMK_E_ARG, "emk_set_option: backmap_fwd6_f32_extent_nm must be in [0, 64]");
+    set_fwd6_f32_extent(value);
+    return EMK_OK;
+  }
   return fail(EMK_E_ARG, "emk_set_option: unknown option '%s'", name);
 }
 int emk_get_option(const char* name, int64_t* value) {
@@ -253,6 +260,10 @@ int emk_get_option(const char* name, int64_t* value) {
   }
   if (strcmp(name, "cost_small_d_max") == 0) {
     *value = cost_small_d_max();
+    return EMK_OK;
+  }
+  if (strcmp(name, "backmap_fwd6_f32_extent_nm") == 0) {
+    *value = fwd6_f32_extent();
     return EMK_OK;
   }
   return fail(EMK_E_ARG, "emk_get_option: unknown option '%s'", name);

@@ -63,6 +63,10 @@ EMK_API int emk_probe_fp32(double* lane_instr_per_s);
  *                             the shape is eligible, negative = never)
  *   "backmap_fwd6_warps"      warps per CTA of that kernel: 0 (default: chosen per launch so that the frame tiles fill whole
  *                             waves), or one of 8, 12, 14, 16, 18, 20
+ *   "backmap_fwd6_f32_extent_nm"  0 (default): float64 chain, error ~2e-6 nm.  v > 0 (opt-in, <= 64): the lane-per-frame kernel runs
+ *                             its first pass with a float32 chain relative to the anchor atom (error <= 4e-6 x extent) and repeats
+ *                             a frame tile in float64 when a side extends further than v nm from its anchor; measured slower
+ *                             than the default on B200 at v = 16
  *   "cost_small_d_max"        widest high-d input (columns) for which emk_sigmoid_cost uses the register kernel instead of
  *                             the TMA pair-tile kernel (default 8; 0..8) */
 EMK_API int emk_set_option(const char* name, int64_t value);

@@ -1044,17 +1044,52 @@ def test_backmap_lane_per_frame_kernel(em, n, b):
     dih[1, n // 2] = -2500.0
     layer = BackMapLayer(n // 2 - 1, (n - 3) // 2)
     old = _lib.get_option("backmap_fwd6_min_batch")
+    old_ext = _lib.get_option("backmap_fwd6_f32_extent_nm")
     try:
         _lib.set_option("backmap_fwd6_min_batch", 0)
-        got6 = layer((cu(dist), cu(ang), cu(dih))).cpu().numpy()
+        _lib.set_option("backmap_fwd6_f32_extent_nm", 16)
+        got6 = layer((cu(dist), cu(ang), cu(dih))).cpu().numpy()          # opt-in float32 first pass, float64 where a side is long
+        _lib.set_option("backmap_fwd6_f32_extent_nm", 0)
+        got6d = layer((cu(dist), cu(ang), cu(dih))).cpu().numpy()         # float64 chain only
         _lib.set_option("backmap_fwd6_min_batch", -1)
         got5 = layer((cu(dist), cu(ang), cu(dih))).cpu().numpy()
     finally:
         _lib.set_option("backmap_fwd6_min_batch", old)
+        _lib.set_option("backmap_fwd6_f32_extent_nm", old_ext)
     ref = O.back_map_layer(torch.from_numpy(dist).double(), torch.from_numpy(ang).double(), torch.from_numpy(dih).double()).numpy()
-    assert np.abs(got6 - ref).max() < COORD_ATOL
-    assert np.abs(got5 - ref).max() < COORD_ATOL
-    assert np.abs(got6 - got5).max() < 2e-5
+    assert np.abs(got6 - ref).max() < 0.7 * COORD_ATOL     # float32 chain: <= 4e-6 x 16 nm
+    assert np.abs(got6d - ref).max() < 0.2 * COORD_ATOL
+    assert np.abs(got5 - ref).max() < 0.2 * COORD_ATOL
+    assert np.abs(got6d - got5).max() < 2e-5
+
+
+def test_backmap_float32_pass_falls_back_on_long_sides(em):
+    """The (opt-in) float32 first pass of the lane-per-frame kernel is only trusted while a side stays within 16 nm of its anchor
+    (error <= 4e-6 x extent); extended and helical chains of 500 residues (35 .. 100 nm) must come out with the float64
+    chain's accuracy, compact ones within the float32 bound -- all in the same batch, tile by tile."""
+    from encodermap_b200 import _lib, _ops
+
+    rng = np.random.default_rng(11)
+    n, b = 1500, 160
+    lengths = rng.uniform(0.13, 0.15, size=(1, n - 1)).astype(np.float32)
+    ang = rng.uniform(1.9, 2.2, size=(b, n - 2)).astype(np.float32)
+    dih = rng.uniform(-pi, pi, size=(b, n - 3)).astype(np.float32)                                        # tiles 0, 1, 4: random coils
+    dih[64:96] = (pi + rng.normal(0, 0.02, size=(32, n - 3))).astype(np.float32)                          # tile 2: extended chains
+    dih[96:128] = (np.tile(np.array([-1.0, -0.8, pi]), (32, (n - 3) // 3)) + rng.normal(0, 0.05, size=(32, n - 3))).astype(np.float32)  # tile 3: helices
+    old, old_ext = _lib.get_option("backmap_fwd6_min_batch"), _lib.get_option("backmap_fwd6_f32_extent_nm")
+    try:
+        _lib.set_option("backmap_fwd6_min_batch", 0)
+        _lib.set_option("backmap_fwd6_f32_extent_nm", 16)
+        got = _ops.backmap_raw(cu(lengths), cu(ang), cu(dih)).cpu().numpy()
+    finally:
+        _lib.set_option("backmap_fwd6_min_batch", old)
+        _lib.set_option("backmap_fwd6_f32_extent_nm", old_ext)
+    ref = O.back_map_layer(torch.from_numpy(np.repeat(lengths, b, 0)).double(), torch.from_numpy(ang).double(), torch.from_numpy(dih).double()).numpy()
+    err = np.abs(got - ref).max(axis=(1, 2))
+    mid = ref[:, n // 2][:, None]
+    assert np.linalg.norm(ref[64:128] - mid[64:128], axis=2).max() > 30.0           # the long tiles really are long
+    assert err[64:128].max() < 2e-5                                                 # float64 second pass
+    assert err.max() < 0.7 * COORD_ATOL
 
 
 def test_backmap_lane_per_frame_nan_and_partial_tiles(em):
