@@ -1733,7 +1733,9 @@ void set_fwd6_warps(int64_t v) { g_fwd6_warps.store(v); }
 // extent limit (nm) of the float32 first pass; 0 (default) = float64 chain only (emk_set_option("backmap_fwd6_f32_extent_nm", v)).
 // OFF by default, by measurement (tools/experiments/fwd6_extent_sweep.py, 65 536 x 1 500): the float32 pass takes 0.634 ms
 // against 0.661 ms for the float64 chain when no tile falls back -- the kernel is bound by the LATENCY of the dependent
-// chain of a step at 16 warps per SM, not by issue slots, so halving the issue slots buys 4 % -- and with the 16 nm limit
+// chain of a step at 16 warps per SM, not by issue slots, so halving the issue slots buys 4 % (and more resident warps do
+// not help either: 20 warps are 30 % slower in both precisions, 24 float32 warps at 80 registers 2.5x slower:
+// profiles/r02_backmap_fwd_f32_experiment.txt) -- and with the 16 nm limit
 // that the 1e-4 nm tolerance needs, the 0.06 % of frames beyond it make 2 % of the tiles run twice, which costs 33 %
 // through the makespan of the persistent pairs (0.843 ms).
 static std::atomic<int64_t> g_fwd6_f32_extent{0};
