@@ -89,6 +89,8 @@ int dist_matrix_device(const float*, int64_t, int64_t, double, bool, int, float*
 int pairwise_flat3_warp_device(const float*, int64_t, int64_t, int64_t, int64_t, int, float*, int64_t, cudaStream_t);
 int pairwise_warp_max_atoms();
 void set_cost_small_d_max(int64_t v);
+void set_cost_small_tile_max_rows(int64_t v);
+int64_t cost_small_tile_max_rows();
 int64_t cost_small_d_max();
 int periodic_distance_device(const float*, const float*, int64_t, double, float*, cudaStream_t);
 int periodic_distance_bwd_device(const float*, const float*, int64_t, double, const float*, float*, float*, cudaStream_t);
@@ -241,6 +243,10 @@ int emk_set_option(const char* name, int64_t value) {
     set_cost_small_d_max(value);
     return EMK_OK;
   }
+  if (strcmp(name, "cost_small_tile_max_rows") == 0) {
+    set_cost_small_tile_max_rows(value);
+    return EMK_OK;
+  }
   if (strcmp(name, "backmap_fwd6_f32_extent_nm") == 0) {
     EMK_REQUIRE(value >= 0 && value <= 64, EMK_E_ARG, "emk_set_option: backmap_fwd6_f32_extent_nm must be in [0, 64]");
     set_fwd6_f32_extent(value);
@@ -260,6 +266,10 @@ int emk_get_option(const char* name, int64_t* value) {
   }
   if (strcmp(name, "cost_small_d_max") == 0) {
     *value = cost_small_d_max();
+    return EMK_OK;
+  }
+  if (strcmp(name, "cost_small_tile_max_rows") == 0) {
+    *value = cost_small_tile_max_rows();
     return EMK_OK;
   }
   if (strcmp(name, "backmap_fwd6_f32_extent_nm") == 0) {

@@ -32,15 +32,31 @@ namespace emk {
 
 namespace cg = cooperative_groups;
 
-constexpr int TM = EMK_TILE_ROWS;  // 128
-constexpr int TN = EMK_TILE_COLS;  // 64
 constexpr int KC = 32;             // floats per k-chunk (128 B = one swizzle row)
 constexpr int STAGES = 4;
 constexpr int NTHREADS = 256;
-constexpr int BOX_ROWS = 64;       // rows per TMA box
-constexpr int STAGE_FLOATS = (TM + TN) * KC;
-constexpr int STAGE_BYTES = STAGE_FLOATS * 4;  // 24 KB
 constexpr int MAX_LATENT = 8;
+
+// Tile geometry.  Threads form a 16 x 16 grid; thread (ty, tx) owns rows ty + 16 i (i < MI) and columns tx + 16 j (j < MJ).
+//   Big   (128 x 64, 8 x 4 micro-tile): the shape the public tile numbering (emk_pair_tile_count / _range / _decode) is in, best
+//         operand reuse (12 LDS.128 per 32 pair-float4 products), two CTAs per SM -- large evaluations and tile ranges.
+//   Small (64 x 32, 4 x 2 micro-tile): four times as many tiles and a quarter of the shared memory per CTA (3 CTAs per SM), for
+//         whole evaluations of up to a few thousand rows, where the big shape leaves SMs idle (1 024 rows: 72 big tiles on 296
+//         CTA slots; split over clusters each CTA still ran alone on its SM).
+template <int TM_, int TN_>
+struct Geom {
+  static constexpr int TM = TM_, TN = TN_;
+  static constexpr int MI = TM_ / 16, MJ = TN_ / 16;
+  static constexpr int BOX_ROWS = TN_;                       // rows per TMA box: one box for the columns, TM / TN for the rows
+  static constexpr int STAGE_FLOATS = (TM_ + TN_) * KC;
+  static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;       // 24 KB (big), 12 KB (small)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + (MAX_LATENT * (TM_ + 2 * TN_)) * 4;
+  static constexpr int MIN_CTAS = TM_ >= 128 ? 2 : 3;
+};
+using GeomBig = Geom<EMK_TILE_ROWS, EMK_TILE_COLS>;   // 128 x 64
+using GeomSmall = Geom<64, 32>;
+constexpr int TM = GeomBig::TM;   // the public tile shape (tile ranges, small_cost_kernel)
+constexpr int TN = GeomBig::TN;
 
 enum class Epi : int { kCost = 0, kDistMatrix = 1 };
 
@@ -138,8 +154,10 @@ __host__ __device__ inline void tile_decode(int64_t t, int64_t tc, int64_t tr, i
 // ---- cost epilogue of NI row groups (rows ty + 16 (i0 + i)) x 4 column groups of this thread ------------------
 // NI = 8: the whole micro-tile (no cluster); NI = 8 / S: this CTA's share after the reduce-scatter over a cluster.
 // stage latent components [c0, c0 + lc) of the tile's rows / columns (component-major, zero for out-of-range rows)
+template <class G = GeomBig>
 __device__ __forceinline__ void stage_latent(const PairParams& p, float* zA, float* zB, float* colsum, const int64_t row0,
                                              const int64_t col0, const int c0, const int lc, const int tid) {
+  constexpr int TM = G::TM, TN = G::TN;
   for (int idx = tid; idx < lc * TM; idx += NTHREADS) {
     const int c = idx / TM, r = idx - c * TM;
     zA[c * TM + r] = (row0 + r < p.n) ? p.low[(row0 + r) * p.l + c0 + c] : 0.f;
@@ -151,49 +169,50 @@ __device__ __forceinline__ void stage_latent(const PairParams& p, float* zA, flo
   }
 }
 
-template <int NI>
-__device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const int i0, const PairParams& p, float* zA,
+template <int NI, class G = GeomBig>
+__device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][G::MJ], const int i0, const PairParams& p, float* zA,
                                               float* zB, float* colsum, double* red_d, const int64_t row0,
                                               const int64_t col0, const bool diag, const int ty, const int tx, const int tid,
                                               const int lane, const int warp) {
+  constexpr int TM = G::TM, TN = G::TN, MJ = G::MJ;
   // low-d squared distances, summed in the SAME order as the main loop sums the high-d ones (even
   // components in one fused chain, odd components in the other, then one add): identical inputs and
   // sigmoids on both sides then cancel exactly, as they do in the reference (tests/test_losses.py:897-904).
   // Latent widths above MAX_LATENT (the reference accepts any n_neurons[-1], parameters.py:612) are walked in chunks of
   // MAX_LATENT components that are re-staged into the same shared-memory rows; the usual 2..8-wide latent never loops.
-  float dl2[NI][4];
+  float dl2[NI][MJ];
 #pragma unroll
   for (int i = 0; i < NI; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) dl2[i][j] = 0.f;
+    for (int j = 0; j < MJ; j++) dl2[i][j] = 0.f;
   int staged = 0;   // first component of the chunk that sits in zA / zB
 #pragma unroll 1
   for (int c0 = 0; c0 < p.l; c0 += MAX_LATENT) {
     const int lc = min(MAX_LATENT, p.l - c0);
     if (c0 != staged) {
       __syncthreads();
-      stage_latent(p, zA, zB, colsum, row0, col0, c0, lc, tid);
+      stage_latent<G>(p, zA, zB, colsum, row0, col0, c0, lc, tid);
       staged = c0;
       __syncthreads();
     }
 #pragma unroll 1
     for (int par = 0; par < 2; par++) {
-      float part[NI][4];
+      float part[NI][MJ];
 #pragma unroll
       for (int i = 0; i < NI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) part[i][j] = 0.f;
+        for (int j = 0; j < MJ; j++) part[i][j] = 0.f;
 #pragma unroll 1
       for (int c = par; c < lc; c += 2) {
-        float za[NI], zb[4];
+        float za[NI], zb[MJ];
 #pragma unroll
         for (int i = 0; i < NI; i++) za[i] = zA[c * TM + ty + 16 * (i0 + i)];
 #pragma unroll
-        for (int j = 0; j < 4; j++) zb[j] = zB[c * TN + tx + 16 * j];
+        for (int j = 0; j < MJ; j++) zb[j] = zB[c * TN + tx + 16 * j];
 #pragma unroll
         for (int i = 0; i < NI; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
+          for (int j = 0; j < MJ; j++) {
             const float t = za[i] - zb[j];
             part[i][j] = fmaf(t, t, part[i][j]);
           }
@@ -201,7 +220,7 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const i
 #pragma unroll
       for (int i = 0; i < NI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) dl2[i][j] += part[i][j];
+        for (int j = 0; j < MJ; j++) dl2[i][j] += part[i][j];
     }
   }
 
@@ -211,7 +230,7 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const i
   for (int i = 0; i < NI; i++) {
     const bool rv = row0 + ty + 16 * (i0 + i) < p.n;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < MJ; j++) {
       const bool valid = rv && (col0 + tx + 16 * j < p.n);
       const float sh = sig_eval<false>(d2h[i][j], p.sh, nullptr);
       float w;
@@ -245,27 +264,27 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const i
     const int lc = min(MAX_LATENT, p.l - c0);
     if (c0 != staged) {
       __syncthreads();   // the previous chunk's column sums have been flushed
-      stage_latent(p, zA, zB, colsum, row0, col0, c0, lc, tid);
+      stage_latent<G>(p, zA, zB, colsum, row0, col0, c0, lc, tid);
       staged = c0;
       __syncthreads();
     }
 #pragma unroll 1
     for (int c = 0; c < lc; c++) {
-      float za[NI], zb[4], rs[NI], cs[4];
+      float za[NI], zb[MJ], rs[NI], cs[MJ];
 #pragma unroll
       for (int i = 0; i < NI; i++) {
         za[i] = zA[c * TM + ty + 16 * (i0 + i)];
         rs[i] = 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < MJ; j++) {
         zb[j] = zB[c * TN + tx + 16 * j];
         cs[j] = 0.f;
       }
 #pragma unroll
       for (int i = 0; i < NI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < MJ; j++) {
           const float t = dl2[i][j] * (za[i] - zb[j]);
           rs[i] += t;
           cs[j] -= t;
@@ -281,7 +300,7 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const i
       // column side (mirror image of the tile); diagonal tiles already visit both orders
       if (!diag) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < MJ; j++) {
           cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
           if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
         }
@@ -298,26 +317,29 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][4], const i
 }
 
 // this CTA's share of the cluster's partial sums: row groups [i0, i0 + NI) summed over all ranks through DSMEM
-template <int NI>
+template <int NI, class G>
 __device__ __forceinline__ void cluster_reduce_scatter(cooperative_groups::cluster_group& cluster, float* part, const int S, const int i0,
-                                                       const int tid, float (&out)[NI][4]) {
+                                                       const int tid, float (&out)[NI][G::MJ]) {
+  constexpr int MJ = G::MJ;
 #pragma unroll
   for (int i = 0; i < NI; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) out[i][j] = 0.f;
+    for (int j = 0; j < MJ; j++) out[i][j] = 0.f;
   for (int r = 0; r < S; r++) {
     const float* peer = cluster.map_shared_rank(part, r);
 #pragma unroll
     for (int i = 0; i < NI; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) out[i][j] += peer[((i0 + i) * 4 + j) * NTHREADS + tid];
+      for (int j = 0; j < MJ; j++) out[i][j] += peer[((i0 + i) * MJ + j) * NTHREADS + tid];
   }
 }
 
 // CLUSTERED = false: one CTA per tile (large problems; none of the cluster code is compiled in -- the extra epilogue
 // variants cost the big kernel 3 % when they shared one instantiation)
-template <bool PERIODIC, Epi EPI, bool CLUSTERED>
-__global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
+template <bool PERIODIC, Epi EPI, bool CLUSTERED, class G>
+__global__ void __launch_bounds__(NTHREADS, G::MIN_CTAS) pair_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
+  constexpr int TM = G::TM, TN = G::TN, MI = G::MI, MJ = G::MJ, BOX_ROWS = G::BOX_ROWS, STAGE_FLOATS = G::STAGE_FLOATS,
+                STAGE_BYTES = G::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint8_t* tail = smem_raw + STAGES * STAGE_BYTES;
@@ -360,21 +382,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
     float* dst = stage_base + s * STAGE_FLOATS;
     const int kx = (kbase + kc) * KC;
     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-    tma_load_2d(dst, &tmap, kx, (int)row0, &full_bar[s]);
-    tma_load_2d(dst + BOX_ROWS * KC, &tmap, kx, (int)row0 + BOX_ROWS, &full_bar[s]);
+#pragma unroll
+    for (int q = 0; q < TM / BOX_ROWS; q++) tma_load_2d(dst + q * BOX_ROWS * KC, &tmap, kx, (int)row0 + q * BOX_ROWS, &full_bar[s]);
     tma_load_2d(dst + TM * KC, &tmap, kx, (int)col0, &full_bar[s]);
   };
   if (tid == 0) {
     for (int kc = 0; kc < STAGES - 1 && kc < nk; kc++) issue(kc);
   }
 
-  if (EPI == Epi::kCost) stage_latent(p, zA, zB, colsum, row0, col0, 0, min(MAX_LATENT, p.l), tid);   // first chunk of the latent
+  if (EPI == Epi::kCost) stage_latent<G>(p, zA, zB, colsum, row0, col0, 0, min(MAX_LATENT, p.l), tid);   // first chunk of the latent
 
-  float2 acc[8][4];
+  float2 acc[MI][MJ];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < MI; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < MJ; j++) acc[i][j] = make_float2(0.f, 0.f);
 
   const float P = p.period;
   const int swa = ty & 7, swb = tx & 7;  // TMA SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
@@ -389,15 +411,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
     const float* Bs = As + TM * KC;
 #pragma unroll 1
     for (int k4 = 0; k4 < KC / 4; k4++) {
-      float4 av[8];
+      float4 av[MI];
 #pragma unroll
-      for (int i = 0; i < 8; i++) av[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * KC + ((k4 ^ swa) << 2));
+      for (int i = 0; i < MI; i++) av[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * KC + ((k4 ^ swa) << 2));
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < MJ; j++) {
         const float4 bv = *reinterpret_cast<const float4*>(Bs + (tx + 16 * j) * KC + ((k4 ^ swb) << 2));
         const float2 nb0 = make_float2(-bv.x, -bv.y), nb1 = make_float2(-bv.z, -bv.w);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < MI; i++) {
           float2 d0 = __fadd2_rn(make_float2(av[i].x, av[i].y), nb0);
           float2 d1 = __fadd2_rn(make_float2(av[i].z, av[i].w), nb1);
           if (PERIODIC) {
@@ -418,9 +440,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
     __syncthreads();   // all TMA data of this CTA has been consumed: the stage buffers are free
     float* part = stage_base;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) part[(i * 4 + j) * NTHREADS + tid] = acc[i][j].x + acc[i][j].y;
+      for (int j = 0; j < MJ; j++) part[(i * MJ + j) * NTHREADS + tid] = acc[i][j].x + acc[i][j].y;
     cluster.sync();
     if (EPI == Epi::kDistMatrix) {
       // distance matrices: rank 0 gathers over DSMEM and writes the tile
@@ -428,9 +450,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
         for (int r = 1; r < S; r++) {
           const float* peer = cluster.map_shared_rank(part, r);
 #pragma unroll
-          for (int i = 0; i < 8; i++)
+          for (int i = 0; i < MI; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j].x += peer[(i * 4 + j) * NTHREADS + tid];
+            for (int j = 0; j < MJ; j++) acc[i][j].x += peer[(i * MJ + j) * NTHREADS + tid];
         }
       }
       cluster.sync();    // peers stay resident until rank 0 has read their partials
@@ -443,10 +465,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
   // ------------------------------------------------------------------------------------------
   if (EPI == Epi::kDistMatrix) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < MI; i++) {
       const int64_t r = row0 + ty + 16 * i;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < MJ; j++) {
         const int64_t c = col0 + tx + 16 * j;
         if (r < p.n && c < p.n) {
           float v = acc[i][j].x + acc[i][j].y;
@@ -467,27 +489,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) pair_tile_kernel(const __grid_con
 
   // ---- cost epilogue --------------------------------------------------------------------------
   if (!CLUSTERED || S == 1) {
-    float d2h[8][4];
+    float d2h[MI][MJ];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) d2h[i][j] = acc[i][j].x + acc[i][j].y;
-    cost_epilogue<8>(d2h, 0, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+      for (int j = 0; j < MJ; j++) d2h[i][j] = acc[i][j].x + acc[i][j].y;
+    cost_epilogue<MI, G>(d2h, 0, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
   } else if (S == 2) {
-    float d2h[4][4];
-    cluster_reduce_scatter<4>(cluster, stage_base, S, 4 * crank, tid, d2h);
+    constexpr int NI = MI / 2;
+    float d2h[NI][MJ];
+    cluster_reduce_scatter<NI, G>(cluster, stage_base, S, NI * crank, tid, d2h);
     cluster.sync();   // every rank has read what it needs: shared memory may be released
-    cost_epilogue<4>(d2h, 4 * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+    cost_epilogue<NI, G>(d2h, NI * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
   } else if (S == 4) {
-    float d2h[2][4];
-    cluster_reduce_scatter<2>(cluster, stage_base, S, 2 * crank, tid, d2h);
+    constexpr int NI = MI / 4;
+    float d2h[NI][MJ];
+    cluster_reduce_scatter<NI, G>(cluster, stage_base, S, NI * crank, tid, d2h);
     cluster.sync();
-    cost_epilogue<2>(d2h, 2 * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
-  } else {
-    float d2h[1][4];
-    cluster_reduce_scatter<1>(cluster, stage_base, S, crank, tid, d2h);
+    cost_epilogue<NI, G>(d2h, NI * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+  } else if (MI >= 8) {   // S == 8: one row group per rank (big tiles only; pick_cluster never asks a small tile for it)
+    constexpr int NI = MI >= 8 ? MI / 8 : 1;
+    float d2h[NI][MJ];
+    cluster_reduce_scatter<NI, G>(cluster, stage_base, S, NI * crank, tid, d2h);
     cluster.sync();
-    cost_epilogue<1>(d2h, crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
+    cost_epilogue<NI, G>(d2h, NI * crank, p, zA, zB, colsum, red_d, row0, col0, diag, ty, tx, tid, lane, warp);
   }
 }
 
@@ -577,8 +602,6 @@ static int launch_small_cost(const PairParams& p, const float* high, int d, int6
 
 // ---- host side -----------------------------------------------------------------------------------
 
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + (MAX_LATENT * (TM + 2 * TN)) * 4;
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -617,13 +640,13 @@ int encode_f32_map_2d(void* map_out, const float* base, uint64_t cols, uint64_t 
 }
 
 // (n, d_pad) row-major float32, 16-byte aligned base, d_pad % 4 == 0
-static int make_tensor_map(CUtensorMap* map, const float* base, int64_t n, int64_t d_pad) {
+static int make_tensor_map(CUtensorMap* map, const float* base, int64_t n, int64_t d_pad, int box_rows) {
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
   cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)n};
   cuuint64_t strides[1] = {(cuuint64_t)d_pad * sizeof(float)};
-  cuuint32_t box[2] = {KC, BOX_ROWS};
+  cuuint32_t box[2] = {KC, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -699,10 +722,20 @@ static int pick_cluster(int64_t n_tiles, int n_chunks) {
   while (s > 1 && 2 * s > n_chunks) s /= 2;   // every rank needs at least two k-chunks
   return s;
 }
+// small tiles (64 x 32, three CTAs per SM, at most MI = 4 ranks per cluster): split the feature axis until the launch has more
+// than half as many CTAs as the machine has slots
+static int pick_cluster_small(int64_t n_tiles, int n_chunks) {
+  const int64_t slots = (int64_t)GeomSmall::MIN_CTAS * sm_count();
+  int s = 1;
+  while (s < GeomSmall::MI && n_tiles * s * 2 <= slots) s *= 2;
+  while (s > 1 && 2 * s > n_chunks) s /= 2;
+  return s;
+}
 
-template <bool PERIODIC, Epi EPI, bool CLUSTERED>
+template <bool PERIODIC, Epi EPI, bool CLUSTERED, class G>
 static int launch_pair_c(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, int cluster, cudaStream_t st) {
-  auto kern = pair_tile_kernel<PERIODIC, EPI, CLUSTERED>;
+  auto kern = pair_tile_kernel<PERIODIC, EPI, CLUSTERED, G>;
+  constexpr int SMEM_BYTES = G::SMEM_BYTES;
   static bool configured[kMaxDevices] = {false};
   if (first_use_on_device(configured)) {
     EMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -726,9 +759,23 @@ static int launch_pair_c(const CUtensorMap& map, const PairParams& p, int64_t n_
 template <bool PERIODIC, Epi EPI>
 static int launch_pair(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, cudaStream_t st) {
   const int cluster = pick_cluster(n_tiles, p.n_chunks);
-  return cluster > 1 ? launch_pair_c<PERIODIC, EPI, true>(map, p, n_tiles, cluster, st)
-                     : launch_pair_c<PERIODIC, EPI, false>(map, p, n_tiles, 1, st);
+  return cluster > 1 ? launch_pair_c<PERIODIC, EPI, true, GeomBig>(map, p, n_tiles, cluster, st)
+                     : launch_pair_c<PERIODIC, EPI, false, GeomBig>(map, p, n_tiles, 1, st);
 }
+template <bool PERIODIC>
+static int launch_pair_small(const CUtensorMap& map, const PairParams& p, int64_t n_tiles, cudaStream_t st) {
+  const int cluster = pick_cluster_small(n_tiles, p.n_chunks);
+  return cluster > 1 ? launch_pair_c<PERIODIC, Epi::kCost, true, GeomSmall>(map, p, n_tiles, cluster, st)
+                     : launch_pair_c<PERIODIC, Epi::kCost, false, GeomSmall>(map, p, n_tiles, 1, st);
+}
+// emk_set_option("cost_small_tile_max_rows", v): whole evaluations of up to v rows (and up to SMALL_TILE_MAX_COLS columns) use
+// the 64 x 32 tile shape (0 = never).  Measured on B200, device time, small / big tiles (tools/bench_small_cost.py):
+//   256 x 1024: 23 / 37 us    512 x 1024: 43 / 53    1024 x 1024: 97 / 113    2048 x 1024: 336 / 329    3072 x 1024: 655 / 710
+//   4096 x 1024: 1166 / 1168    8192 x 1024: 4462 / 4276    1024 x 4950: 270 / 234 (a long feature axis favours operand reuse)
+static int64_t g_small_tile_max_rows = 1024;
+constexpr int64_t SMALL_TILE_MAX_COLS = 2048;
+void set_cost_small_tile_max_rows(int64_t v) { g_small_tile_max_rows = v < 0 ? 0 : v; }
+int64_t cost_small_tile_max_rows() { return g_small_tile_max_rows; }
 
 void tile_decode_host(int64_t t, int64_t n_rows, int64_t* I, int64_t* J) {
   tile_decode(t, (n_rows + TN - 1) / TN, (n_rows + TM - 1) / TM, I, J);
@@ -784,12 +831,21 @@ int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* lo
   int rc = prepare_high(high, n, d, st, &hv);
   if (rc) return rc;
   CUtensorMap map;
-  rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad);
+  // a whole evaluation of a training-size batch: the small tile shape (its own tile numbering, from 0)
+  const bool small_tiles = tile_begin == 0 && tile_end == total && n <= g_small_tile_max_rows &&
+                           (d <= SMALL_TILE_MAX_COLS || g_small_tile_max_rows >= (1 << 20));   // 2^20: forced (tests)
+  rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad, small_tiles ? GeomSmall::BOX_ROWS : GeomBig::BOX_ROWS);
   if (rc == EMK_OK) {
-    if (std::isinf(periodicity))
+    if (small_tiles) {
+      p.tiles_per_row = (int)((n + GeomSmall::TN - 1) / GeomSmall::TN);
+      p.tile_rows = (int)((n + GeomSmall::TM - 1) / GeomSmall::TM);
+      const int64_t tiles = (int64_t)p.tile_rows * p.tiles_per_row - (int64_t)p.tile_rows * (p.tile_rows - 1);
+      rc = std::isinf(periodicity) ? launch_pair_small<false>(map, p, tiles, st) : launch_pair_small<true>(map, p, tiles, st);
+    } else if (std::isinf(periodicity)) {
       rc = launch_pair<false, Epi::kCost>(map, p, tile_end - tile_begin, st);
-    else
+    } else {
       rc = launch_pair<true, Epi::kCost>(map, p, tile_end - tile_begin, st);
+    }
   }
   if (hv.scratch) cudaFreeAsync(hv.scratch, st);
   return rc;
@@ -806,7 +862,7 @@ int dist_matrix_device(const float* x, int64_t n, int64_t d, double periodicity,
   int rc = prepare_high(x, n, d, st, &hv);
   if (rc) return rc;
   CUtensorMap map;
-  rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad);
+  rc = make_tensor_map(&map, hv.ptr, n, hv.d_pad, GeomBig::BOX_ROWS);
   if (rc == EMK_OK) {
     PairParams p{};
     p.n = n;

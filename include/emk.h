@@ -67,6 +67,9 @@ EMK_API int emk_probe_fp32(double* lane_instr_per_s);
  *                             its first pass with a float32 chain relative to the anchor atom (error <= 4e-6 x extent) and repeats
  *                             a frame tile in float64 when a side extends further than v nm from its anchor; measured slower
  *                             than the default on B200 at v = 16
+ *   "cost_small_tile_max_rows"  emk_sigmoid_cost calls that cover the whole tile list of up to this many rows use 64 x 32 pair tiles
+ *                             instead of 128 x 64 (default 1024, and only up to 2048 columns; 0 = never; >= 2^20 = always).  Tile
+ *                             ranges always refer to the 128 x 64 numbering.
  *   "cost_small_d_max"        widest high-d input (columns) for which emk_sigmoid_cost uses the register kernel instead of
  *                             the TMA pair-tile kernel (default 8; 0..8) */
 EMK_API int emk_set_option(const char* name, int64_t value);
