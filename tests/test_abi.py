@@ -249,3 +249,38 @@ def test_streamed_cost_control_flow(L, monkeypatch):
     assert calls[0][1] == total and calls[-1][0] == 0 and len(calls) == 5
     assert all(a[0] == b[1] for a, b in zip(calls, calls[1:]))
     assert calls[0][2] & L.EMK_COST_ZERO_OUTPUTS and not any(c[2] & L.EMK_COST_ZERO_OUTPUTS for c in calls[1:])
+
+
+def test_merged_atom_count_follows_the_reference_loop(L):
+    """emk_merged_atom_count (host only): atom 0, then every atom i >= 1 followed by a hydrogen if i is in h_after, else by an
+    oxygen if i is in o_after -- the loop of reference misc/backmapping.py:1970-1990 -- incl. its quirks: atom 0 never gets a
+    partner, an atom in both lists gets the hydrogen only."""
+    import ctypes
+
+    import numpy as np
+
+    def count(n, h_after, o_after):
+        h = np.asarray(h_after, dtype=np.int64)
+        o = np.asarray(o_after, dtype=np.int64)
+        return int(L.lib().emk_merged_atom_count(n, h.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), h.size,
+                                           o.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), o.size))
+
+    def reference_loop(n, h_after, o_after):
+        total = 1
+        for i in range(1, n):
+            total += 1
+            if i in h_after:
+                total += 1
+            elif i in o_after:
+                total += 1
+        return total
+
+    rng = np.random.default_rng(4)
+    cases = [(9, list(range(0, 9, 3))[1:], list(range(2, 9, 3))), (30, [], []), (30, [0], [0]), (12, [3, 6, 9], [3, 5, 8, 11]), (1, [], [])]
+    for _ in range(20):
+        n = int(rng.integers(3, 60))
+        cases.append((n, rng.choice(n, size=int(rng.integers(0, n)), replace=False).tolist(),
+                      rng.choice(n, size=int(rng.integers(0, n)), replace=False).tolist()))
+    for n, h, o in cases:
+        assert count(n, h, o) == reference_loop(n, h, o), (n, h, o)
+    assert count(10, [10], []) == -1 and count(10, [], [-1]) == -1      # outside the backbone
