@@ -348,6 +348,41 @@ def rotation_matrix(axis_unit_vec, angle):
     return tf.reshape(out, [tf.shape(angle)[0], 3, 3])
 
 
+# ---- generation side: guessed amide H / O, merge (encodermap/misc/backmapping.py:1920-1990; forward only) ---------------------------
+def _indices(idx):
+    import numpy as np
+
+    return np.asarray(idx.numpy() if hasattr(idx, "numpy") else idx, dtype=np.int64).reshape(-1).tolist()
+
+
+def guess_sp2_atom(cartesians, indices, angle_to_previous, bond_length):
+    """``encodermap.misc.backmapping.guess_sp2_atom`` (:1920-1941)."""
+    _require_tf()
+    idx = _indices(indices)
+    (out,) = _eager(lambda x: (_ops.guess_sp2_raw(x, idx, angle_to_previous, bond_length),), [_f32(cartesians)], 1)
+    return tf.reshape(out, [tf.shape(cartesians)[0], len(idx), 3])
+
+
+def guess_amide_H(cartesians, N_indices):
+    """``encodermap.misc.backmapping.guess_amide_H`` (:1943-1944)."""
+    return guess_sp2_atom(cartesians, _indices(N_indices)[1::], 123 / 180 * pi, 1.10)
+
+
+def guess_amide_O(cartesians, C_indices):
+    """``encodermap.misc.backmapping.guess_amide_O`` (:1946-1947)."""
+    return guess_sp2_atom(cartesians, _indices(C_indices), 121 / 180 * pi, 1.24)
+
+
+def merge_cartesians(central_cartesians, N_indices, O_indices, H_cartesians, O_cartesians):
+    """``encodermap.misc.backmapping.merge_cartesians`` (:1970-1990)."""
+    _require_tf()
+    h_after, o_after = _indices(N_indices)[1::], _indices(O_indices)
+    n_out = int(central_cartesians.shape[1]) + int(H_cartesians.shape[1]) + int(O_cartesians.shape[1])
+    (out,) = _eager(lambda c, h, o: (_ops.merge_cartesians_raw(c, h_after, o_after, h, o),),
+                    [_f32(central_cartesians), _f32(H_cartesians), _f32(O_cartesians)], 1)
+    return tf.reshape(out, [tf.shape(central_cartesians)[0], n_out, 3])
+
+
 # ---- installation ----------------------------------------------------------------------------------------------------------------
 # (module, name) -> replacement; these are the `from ... import` sites of the reference (loss_functions.py:43-48,
 # models/layers.py:47-54, models/models.py:49-58, autoencoder/autoencoder.py:64-80): a name imported into a module is a
@@ -362,7 +397,8 @@ def _rebind_table():
                                                       dihedral_to_cartesian_tf_one_way=dihedral_to_cartesian_tf_one_way),
         "encodermap.misc.backmapping": dict(dihedrals_to_cartesian_tf_layers=dihedrals_to_cartesian_tf_layers,
                                             dihedral_to_cartesian_tf_one_way_layers=dihedral_to_cartesian_tf_one_way_layers,
-                                            rotation_matrix=rotation_matrix),
+                                            rotation_matrix=rotation_matrix, guess_sp2_atom=guess_sp2_atom, guess_amide_H=guess_amide_H,
+                                            guess_amide_O=guess_amide_O, merge_cartesians=merge_cartesians),
         "encodermap.models.layers": dict(pairwise_dist=pairwise_dist, chain_in_plane=chain_in_plane,
                                          dihedrals_to_cartesian_tf_layers=dihedrals_to_cartesian_tf_layers),
         "encodermap.models.models": dict(pairwise_dist=pairwise_dist, chain_in_plane=chain_in_plane,

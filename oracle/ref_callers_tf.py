@@ -162,7 +162,8 @@ class PairwiseDistances(Layer):
 OP_NAMES = {
     "encodermap.misc.distances": ["sigmoid", "periodic_distance", "pairwise_dist_periodic", "pairwise_dist"],
     "encodermap.misc.backmapping": ["dihedrals_to_cartesian_tf_layers", "dihedral_to_cartesian_tf_one_way_layers", "rotation_matrix",
-                                    "split_and_reverse_dihedrals", "split_and_reverse_cartesians"],
+                                    "split_and_reverse_dihedrals", "split_and_reverse_cartesians", "guess_sp2_atom", "guess_amide_H",
+                                    "guess_amide_O", "merge_cartesians"],
     "encodermap.encodermap_tf1.backmapping": ["chain_in_plane", "dihedrals_to_cartesian_tf", "dihedral_to_cartesian_tf_one_way"],
     "encodermap.loss_functions.loss_functions": ["sigmoid", "periodic_distance", "pairwise_dist_periodic", "pairwise_dist"],
     "encodermap.models.layers": ["pairwise_dist", "chain_in_plane", "dihedrals_to_cartesian_tf_layers"],
@@ -173,7 +174,8 @@ OP_SOURCES = {
     "encodermap.misc.distances": ("encodermap/misc/distances.py", ["sigmoid", "periodic_distance", "pairwise_dist_periodic", "pairwise_dist"]),
     "encodermap.misc.backmapping": ("encodermap/misc/backmapping.py",
                                     ["split_and_reverse_dihedrals", "split_and_reverse_cartesians", "dihedrals_to_cartesian_tf_layers",
-                                     "dihedral_to_cartesian_tf_one_way_layers", "rotation_matrix"]),
+                                     "dihedral_to_cartesian_tf_one_way_layers", "rotation_matrix", "guess_sp2_atom", "guess_amide_H",
+                                     "guess_amide_O", "merge_cartesians"]),
     "encodermap.encodermap_tf1.backmapping": ("encodermap/encodermap_tf1/backmapping.py",
                                               ["chain_in_plane", "dihedrals_to_cartesian_tf", "dihedral_to_cartesian_tf_one_way"]),
 }

@@ -913,7 +913,7 @@ def test_periodic_vjp_tie_points(em):
 
 
 @pytest.mark.parametrize("l", [9, 16, 19])
-def test_latent_wider_than_eight(em, l):
+def test_latent_wider_than_eight(em, l, tile_shape):
     """n_neurons[-1] is unrestricted in the reference (parameters/parameters.py:612): the epilogue walks the latent in
     chunks of 8 components.  513 rows: diagonal + off-diagonal tiles and a ragged edge; 96 rows: the cluster split."""
     rng = np.random.default_rng(l)

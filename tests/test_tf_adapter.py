@@ -293,3 +293,13 @@ def test_tf_adapter_standalone_ops_on_gpu(tf_gpu):
     axis /= np.linalg.norm(axis, axis=1, keepdims=True)
     got = mb.rotation_matrix(tf.convert_to_tensor(axis.astype(np.float32)), tf.convert_to_tensor(rng.uniform(-pi, pi, 6).astype(np.float32)))
     assert tuple(got.shape) == (6, 3, 3)
+    # generation side (misc/backmapping.py:1920-1990), called as reference tests/test_backmapping_em1_em2.py:571-591 does
+    xyz = O.back_map_layer(torch.from_numpy(np.repeat(lengths, b, 0)), torch.from_numpy(ang), torch.from_numpy(dih)).numpy()
+    n_idx, c_idx = np.arange(n)[::3], np.arange(n)[2::3]
+    x_tf = tf.convert_to_tensor(xyz.astype(np.float32))
+    h, o = mb.guess_amide_H(x_tf, n_idx), mb.guess_amide_O(x_tf, c_idx)
+    merged = mb.merge_cartesians(x_tf, n_idx, c_idx, h, o)
+    x32 = xyz.astype(np.float32).astype(np.float64)
+    want = O.merge_cartesians(x32, n_idx, c_idx, O.guess_amide_H(x32, n_idx), O.guess_amide_O(x32, c_idx)).numpy()
+    assert tuple(merged.shape) == want.shape
+    assert np.abs(merged.cpu().numpy() - want).max() < 1e-5
