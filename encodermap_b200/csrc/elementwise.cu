@@ -722,132 +722,76 @@ __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const 
   }
 }
 
-// backward of the same: grad_x[a] = sum_b coef_ab (x_a - x_b), coef = g / dist (2 g when squared), 0 at zero distance.
-// Every pair is visited once: its contribution to the COLUMN atom accumulates in the owning lane's registers; the
-// contributions to the ROW atom are per-lane partial sums that have to be added across the warp -- not by a butterfly per
-// row (30 instructions for three values) but through shared memory, PWW_TR rows at a time: every lane stores its three
-// partials of a row (conflict-free), and after PWW_TR rows 3 x PWW_TR lanes each add up one (component, row) with eight
-// LDS.128.  The kernel is latency-bound (dependent FADD2 -> FFMA2 -> MUFU -> FFMA2 chains, one row after the other), so what
-// matters is resident warps: 7 KB of shared memory per warp and <= 80 registers give 24 warps per SM (the first version,
-// with a 32-row tile of 14 KB per warp, had 12 and ran at 0.12 of the HBM rate; capping at 64 registers for 32 warps spilled
-// into the row loop and every row waited for local-memory loads).
-constexpr int PWW_RPAD = 36;   // floats per row of the transpose tile: 16-byte aligned rows, conflict-free LDS.128 per quarter-warp
-constexpr int PWW_TR = 8;      // rows per transposition
-constexpr int PWW_BWD_PER_WARP = 4 * PWW_MAX_N + 3 * PWW_MAX_N + 3 * PWW_TR * PWW_RPAD;   // floats
+// PairwiseDistances backward, <= 128 selected atoms: grad_x[a] = sum_b coef_ab (x_a - x_b), coef = g / dist (2 g when squared),
+// 0 at zero distance.  One CTA (four warps) per frame, one THREAD per atom i that walks all columns j -- every pair is visited
+// from both ends, so there is nothing to reduce across lanes -- with the two things that made round 1's thread-per-atom kernel
+// slow removed: x_j is one broadcast LDS.128 (float4 copy) instead of three scalar loads, and two columns are processed per
+// iteration with the packed FADD2 / FFMA2 forms (18 instead of 30 instructions per visit).  Measured against a warp-per-frame
+// form that visits every pair once (column sums in registers, row sums through a shared-memory transpose; removed again):
+// 65 536 x 100 atoms 783 us against 1 064 us, 1 024 x 100 15.6 against 30.4 us (profiles/r02_pairwise_bwd_forms.txt) -- the
+// single visit saves FP work but pays it back in row bookkeeping, and its 7 KB of transposes per warp cap the SM at 24 warps.  The frame's upstream gradient is staged once with 8-byte cp.async; its flat offsets are walked
+// incrementally (start at pair (0, i); advance by n - j - 2 down column i while j < i, by 1 along row i afterwards; at
+// j == i the walk passes an unrelated element whose weight is masked by the zero distance).  21 KB of shared memory per
+// CTA: ten CTAs = 40 warps per SM.
+constexpr int PWB2_THREADS = 128;
 
-template <int C, bool SQUARED>
-__global__ void __launch_bounds__(PWW_THREADS, 6) pairwise_flat3_warp_bwd_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
-                                                                                 int64_t rstride, const float* __restrict__ go,
-                                                                                 float* __restrict__ gx) {
-  extern __shared__ __align__(16) float smw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4* sx = reinterpret_cast<float4*>(smw + (size_t)warp * PWW_BWD_PER_WARP);
-  float* sr = smw + (size_t)warp * PWW_BWD_PER_WARP + 4 * PWW_MAX_N;     // [3][PWW_MAX_N] row sums
-  float* tr = sr + 3 * PWW_MAX_N;                                         // [3][PWW_TR][PWW_RPAD] transpose tile
+template <bool SQUARED>
+__global__ void __launch_bounds__(PWB2_THREADS) pairwise_flat3_bwd2_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
+                                                                           int64_t rstride, const float* __restrict__ go,
+                                                                           float* __restrict__ gx) {
+  extern __shared__ __align__(16) float smb[];
+  float4* sx = reinterpret_cast<float4*>(smb);          // [PWW_MAX_N]
+  float* sg = smb + 4 * PWW_MAX_N;                      // [n (n-1) / 2], 8-byte aligned
+  const int t = threadIdx.x;
   const int per = n * (n - 1) / 2;
-  for (int64_t f = (int64_t)blockIdx.x * (PWW_THREADS / 32) + warp; f < b; f += (int64_t)gridDim.x * (PWW_THREADS / 32)) {
-    const float* xb = x + f * bstride;
-    float nx[C], ny[C], nz[C], ax[C], ay[C], az[C];   // -x_j and the column sums of +coef * d (subtracted at the end)
-    int jj[C];
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      const int j = 32 * c + lane;
-      float vx = 0.f, vy = 0.f, vz = 0.f;
-      if (j < n) {
-        const float* a = xb + (int64_t)j * rstride;
-        vx = a[0]; vy = a[1]; vz = a[2];
-        sx[j] = make_float4(vx, vy, vz, 0.f);
-      }
-      nx[c] = -vx; ny[c] = -vy; nz[c] = -vz;
-      ax[c] = ay[c] = az[c] = 0.f;
-      jj[c] = j < n ? j : -1;
+  for (int64_t f = blockIdx.x; f < b; f += gridDim.x) {
+    const float* g = go + f * per;
+    __syncthreads();                                    // the previous frame has been consumed
+    if (t < n) {
+      const float* a = x + f * bstride + (int64_t)t * rstride;
+      sx[t] = make_float4(a[0], a[1], a[2], 0.f);
     }
-    if (lane < 3) sr[lane * PWW_MAX_N + n - 1] = 0.f;   // the last atom has no row
-    __syncwarp();
-    // g / dist as g * rsqrt(max(s2, tiny)): a masked lane (g = 0) and a zero distance (d = 0 multiplies it) both give 0
-    auto coef_of = [](float g, float s2) { return SQUARED ? 2.f * g : g * rsqrt_fast(fmaxf(s2, EMK_TINY)); };
-    // the upstream gradient of the next PF rows is in flight while a row is processed
-    constexpr int PF = 2;
-    const float* gpre = go + f * per - 1 + lane;    // gpre[32 c] is the element (row, 32 c + lane) of the row being prefetched
-    int pre_row = 0;
-    float gq[PF][C];
-    auto prefetch = [&](float (&dst)[C]) {
-#pragma unroll
-      for (int c = 0; c < C; c++) dst[c] = (pre_row < n - 1 && jj[c] > pre_row) ? __ldg(gpre + 32 * c) : 0.f;
-      gpre += n - pre_row - 2;
-      ++pre_row;
-    };
-#pragma unroll
-    for (int u = 0; u < PF; u++) prefetch(gq[u]);
-#pragma unroll 1
-    for (int i0 = 0; i0 < n - 1; i0 += PWW_TR) {
-      const int rows = min(PWW_TR, n - 1 - i0);
-#pragma unroll 1
-      for (int i4 = 0; i4 < rows; i4 += PF) {
-#pragma unroll
-        for (int u = 0; u < PF; u++) {
-          const int ii = i4 + u;
-          if (ii < rows) {
-            const int i = i0 + ii;
-            const float4 xi = sx[i];
-            float g[C];
-#pragma unroll
-            for (int c = 0; c < C; c++) g[c] = gq[u][c];
-            prefetch(gq[u]);
-            float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
-#pragma unroll
-            for (int c = 0; c + 1 < C; c += 2) {
-              if (32 * c + 63 <= i) continue;
-              const float2 dx = __fadd2_rn(make_float2(xi.x, xi.x), make_float2(nx[c], nx[c + 1]));
-              const float2 dy = __fadd2_rn(make_float2(xi.y, xi.y), make_float2(ny[c], ny[c + 1]));
-              const float2 dz = __fadd2_rn(make_float2(xi.z, xi.z), make_float2(nz[c], nz[c + 1]));
-              const float2 s2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
-              const float2 cf = make_float2(coef_of(g[c], s2.x), coef_of(g[c + 1], s2.y));
-              r0 = __ffma2_rn(cf, dx, r0); r1 = __ffma2_rn(cf, dy, r1); r2 = __ffma2_rn(cf, dz, r2);
-              float2 t;
-              t = __ffma2_rn(cf, dx, make_float2(ax[c], ax[c + 1])); ax[c] = t.x; ax[c + 1] = t.y;
-              t = __ffma2_rn(cf, dy, make_float2(ay[c], ay[c + 1])); ay[c] = t.x; ay[c + 1] = t.y;
-              t = __ffma2_rn(cf, dz, make_float2(az[c], az[c + 1])); az[c] = t.x; az[c + 1] = t.y;
-            }
-            float q0 = r0.x + r0.y, q1 = r1.x + r1.y, q2 = r2.x + r2.y;
-            if (C & 1) {
-              constexpr int c = C - 1;
-              const float dx = xi.x + nx[c], dy = xi.y + ny[c], dz = xi.z + nz[c];
-              const float cf = coef_of(g[c], fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-              q0 = fmaf(cf, dx, q0); q1 = fmaf(cf, dy, q1); q2 = fmaf(cf, dz, q2);
-              ax[c] = fmaf(cf, dx, ax[c]); ay[c] = fmaf(cf, dy, ay[c]); az[c] = fmaf(cf, dz, az[c]);
-            }
-            tr[(0 * PWW_TR + ii) * PWW_RPAD + lane] = q0;
-            tr[(1 * PWW_TR + ii) * PWW_RPAD + lane] = q1;
-            tr[(2 * PWW_TR + ii) * PWW_RPAD + lane] = q2;
-          }
-        }
-      }
-      __syncwarp();
-      {
-        const int k = lane / PWW_TR, ii = lane % PWW_TR;     // lanes 0 .. 3 PWW_TR - 1: one (component, row) each
-        if (k < 3 && ii < rows) {
-          const float4* rowp = reinterpret_cast<const float4*>(tr + (k * PWW_TR + ii) * PWW_RPAD);
-          float4 acc = rowp[0];
-#pragma unroll
-          for (int q = 1; q < 8; q++) {
-            const float4 v = rowp[q];
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-          }
-          sr[k * PWW_MAX_N + i0 + ii] = (acc.x + acc.y) + (acc.z + acc.w);
-        }
-      }
-      __syncwarp();
+    if ((reinterpret_cast<uintptr_t>(g) & 7) == 0) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sg);
+      for (int e = 2 * t; e + 1 < per; e += 2 * PWB2_THREADS)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 4u * e), "l"(g + e) : "memory");
+      if ((per & 1) && t == 0) sg[per - 1] = g[per - 1];
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    } else {
+      for (int e = t; e < per; e += PWB2_THREADS) sg[e] = g[e];
     }
-    float* gb = gx + f * bstride;
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      const int j = 32 * c + lane;
-      if (j < n) {
-        float* o = gb + (int64_t)j * rstride;
-        o[0] = sr[j] - ax[c]; o[1] = sr[PWW_MAX_N + j] - ay[c]; o[2] = sr[2 * PWW_MAX_N + j] - az[c];
+    __syncthreads();
+    if (t < n) {
+      const int i = t;
+      const float4 xi = sx[i];
+      float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
+      int off = i - 1;
+      auto coef_of = [](float gv, float s2) { return SQUARED ? 2.f * gv : (s2 >= EMK_TINY ? gv * rsqrt_fast(s2) : 0.f); };
+      int j = 0;
+#pragma unroll 2
+      for (; j + 1 < n; j += 2) {
+        const int offa = off;
+        const int offb = offa + (j < i ? n - j - 2 : 1);
+        off = offb + (j + 1 < i ? n - j - 3 : 1);
+        const float ga = sg[max(offa, 0)], gb = sg[min(max(offb, 0), per - 1)];
+        const float4 xa = sx[j], xb = sx[j + 1];
+        const float2 dx = __fadd2_rn(make_float2(xi.x, xi.x), make_float2(-xa.x, -xb.x));
+        const float2 dy = __fadd2_rn(make_float2(xi.y, xi.y), make_float2(-xa.y, -xb.y));
+        const float2 dz = __fadd2_rn(make_float2(xi.z, xi.z), make_float2(-xa.z, -xb.z));
+        const float2 s2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+        const float2 cf = make_float2(coef_of(ga, s2.x), coef_of(gb, s2.y));
+        ax = __ffma2_rn(cf, dx, ax); ay = __ffma2_rn(cf, dy, ay); az = __ffma2_rn(cf, dz, az);
       }
+      float rx = ax.x + ax.y, ry = ay.x + ay.y, rz = az.x + az.y;
+      if (j < n) {                                      // odd n: the last column
+        const float gv = sg[min(max(off, 0), per - 1)];
+        const float4 xa = sx[j];
+        const float dx = xi.x - xa.x, dy = xi.y - xa.y, dz = xi.z - xa.z;
+        const float cf = coef_of(gv, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        rx = fmaf(cf, dx, rx); ry = fmaf(cf, dy, ry); rz = fmaf(cf, dz, rz);
+      }
+      float* o = gx + f * bstride + (int64_t)i * rstride;
+      o[0] = rx; o[1] = ry; o[2] = rz;
     }
   }
 }
@@ -993,23 +937,12 @@ int pairwise_small_bwd_device(const float* x, int64_t b, int64_t n, int64_t d, i
   // 129 .. 320 atoms: pair-once kernel (2.5x the thread-per-atom kernel at 300 atoms); up to 128 atoms the whole
   // upstream gradient of a frame fits in shared memory next to the coordinates and the thread-per-atom kernel is as fast
   if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) {
-    constexpr size_t smem = (size_t)(PWW_THREADS / 32) * PWW_BWD_PER_WARP * sizeof(float);   // 27.5 KB: 8 CTAs / SM
-    const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 6);
-#define EMK_PWWB(CC, SQ)                                                                                                             \
-  do {                                                                                                                               \
-    static bool cfg[kMaxDevices] = {false};                                                                                          \
-    if (first_use_on_device(cfg))                                                                                                    \
-      EMK_CUDA(cudaFuncSetAttribute(pairwise_flat3_warp_bwd_kernel<CC, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    pairwise_flat3_warp_bwd_kernel<CC, SQ><<<grid, PWW_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, go, gx);                  \
-  } while (0)
-#define EMK_PWWB2(CC) do { if (squared) EMK_PWWB(CC, true); else EMK_PWWB(CC, false); } while (0)
-    if (n <= 32) EMK_PWWB2(1);
-    else if (n <= 64) EMK_PWWB2(2);
-    else if (n <= 96) EMK_PWWB2(3);
-    else EMK_PWWB2(4);
-#undef EMK_PWWB2
-#undef EMK_PWWB
-    return launch_status("pairwise_flat3_warp_bwd_kernel");
+    // CTA per frame, thread per atom, packed two-column walk
+    const size_t smem = (4 * (size_t)PWW_MAX_N + (size_t)((n * (n - 1) / 2 + 1) & ~(int64_t)1)) * sizeof(float);
+    const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)sm_count() * 10);
+    if (squared) pairwise_flat3_bwd2_kernel<true><<<grid, PWB2_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, go, gx);
+    else pairwise_flat3_bwd2_kernel<false><<<grid, PWB2_THREADS, smem, st>>>(x, b, (int)n, bstride, rstride, go, gx);
+    return launch_status("pairwise_flat3_bwd2_kernel");
   }
   if (flat && d == 3 && n > 128 && n <= 320) {
     const size_t smem = 18 * (size_t)n * sizeof(float);

@@ -247,6 +247,7 @@ int emk_set_option(const char* name, int64_t value) {
     set_cost_small_tile_max_rows(value);
     return EMK_OK;
   }
+
   if (strcmp(name, "backmap_fwd6_f32_extent_nm") == 0) {
     EMK_REQUIRE(value >= 0 && value <= 64, EMK_E_ARG, "emk_set_option: backmap_fwd6_f32_extent_nm must be in [0, 64]");
     set_fwd6_f32_extent(value);
@@ -272,6 +273,7 @@ int emk_get_option(const char* name, int64_t* value) {
     *value = cost_small_tile_max_rows();
     return EMK_OK;
   }
+
   if (strcmp(name, "backmap_fwd6_f32_extent_nm") == 0) {
     *value = fwd6_f32_extent();
     return EMK_OK;
