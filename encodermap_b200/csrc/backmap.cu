@@ -884,9 +884,18 @@ __device__ __forceinline__ float f6_chain(Se3& f, const float* __restrict__ angl
       if (F32) e2 = fmaxf(e2, fmaf(g32.p01.x, g32.p01.x, fmaf(g32.p01.y, g32.p01.y, g32.p2 * g32.p2)));
       if (lane == 0) bulk_wait_read0();          // the previous group has left the buffer (the storing lane tracks the bulk groups)
       __syncwarp();
+      // a lane's row is 96 bytes: lanes l and l + 4 of a quarter warp would hit the same banks with the same 16-byte chunk
+      // (half of the store wavefronts were conflict replays).  Lanes with bit 2 set write chunk q + 1 (mod 6) in the q-th
+      // instruction: the eight lanes of a phase then cover eight different bank groups; the row ends up dense all the same.
       float4* row4 = reinterpret_cast<float4*>(outT + lane * 24);
+      const bool rot = (lane >> 2) & 1;
 #pragma unroll
-      for (int q = 0; q < 6; q++) row4[q] = make_float4(pend[4 * q], pend[4 * q + 1], pend[4 * q + 2], pend[4 * q + 3]);
+      for (int q = 0; q < 6; q++) {
+        const int c1 = (q + 1) % 6;
+        const float4 v = make_float4(rot ? pend[4 * c1] : pend[4 * q], rot ? pend[4 * c1 + 1] : pend[4 * q + 1],
+                                     rot ? pend[4 * c1 + 2] : pend[4 * q + 2], rot ? pend[4 * c1 + 3] : pend[4 * q + 3]);
+        row4[rot ? c1 : q] = v;
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {

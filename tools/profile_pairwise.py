@@ -13,7 +13,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 xyz = torch.randn(b, 300, 3, device=dev, generator=g)
 tgt = torch.randn(b, 300, 3, device=dev, generator=g)
 go = torch.randn(b, 4950, device=dev, generator=g)
-for _ in range(2):
+for _ in range(2):   # launch order per iteration: forward, backward (+ a torch fill), fused loss
     out = _ops.pairwise_dist_raw(xyz, False, True, 1, None, 3)
     gx = _ops.pairwise_dist_bwd_raw(xyz, go, False, True, 1, None, 3)
     _ops.cartesian_pair_loss_raw(xyz, tgt, 1, None, 3, "mean_abs", 0.0, True)

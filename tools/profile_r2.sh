@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu evidence for round 2 (run under gpurun on one B200):  bash tools/profile_r2.sh
-# Afterwards, here:  python tools/profile_summarise.py r02   (writes profiles/r02_*)
+# The captures are summarised on the box (gpurun_out/summary/r02_*); copy those into profiles/ here.
 set -x
 mkdir -p gpurun_out
 # (1) launch list of the bench command: every kernel with its device time
@@ -18,4 +18,12 @@ ncu --set full --clock-control none --import-source on -k regex:backmap_ -c 4 -o
 # (4) the fused Cartesian branch and the PairwiseDistances kernels at the ADC training shape
 ncu --set full --clock-control none --import-source on -k regex:"cart_|pairwise_" -c 8 -o gpurun_out/r02_cart \
     python tools/train_profile.py adc_fused > gpurun_out/r02_cart.log 2>&1
-ls -la gpurun_out
+# (5) PairwiseDistances forward / backward at 65 536 x 100 atoms, and the narrow-input / small-tile cost kernels at training sizes
+ncu --set full --clock-control none --import-source on -k regex:"pairwise_flat3" -s 2 -c 2 -o gpurun_out/r02_pairwise \
+    python tools/profile_pairwise.py > gpurun_out/r02_pairwise.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"small_cost_kernel|Geom<64" -c 4 -o gpurun_out/r02_small_cost \
+    python tools/bench_small_cost.py > gpurun_out/r02_small_cost.log 2>&1
+# summarise on the box and drop the captures (gpurun_out/ is limited to 64 MiB)
+python tools/profile_summarise.py r02 gpurun_out/summary > gpurun_out/r02_summarise.log 2>&1
+rm -f gpurun_out/*.ncu-rep
+ls -la gpurun_out gpurun_out/summary

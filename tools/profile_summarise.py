@@ -30,7 +30,10 @@ def raw(rep):
 
 
 def main():
+    global OUT
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    if len(sys.argv) > 2:     # on the GPU box: summaries next to the captures (gpurun_out/ travels back, at most 64 MiB)
+        OUT = Path(sys.argv[2])
     OUT.mkdir(exist_ok=True)
     lines = [f"# ncu --set full --clock-control none summaries, round {tag[1:]} (B200, sm_100a). Source: tools/profile_{tag[0]}{int(tag[1:])}.sh + tools/profile_summarise.py", ""]
     traffic = None
