@@ -87,6 +87,7 @@ SIGNATURES = {
     "emk_merge_cartesians": ([vp, i64, i64, c_i64p, i64, c_i64p, i64, vp, i64, vp, i64, vp, vp], C.c_int),
     "emk_backbone_amide_atoms": ([vp, i64, i64, c_i64p, i64, c_i64p, i64, dbl, dbl, dbl, dbl, vp, i64, vp], C.c_int),
     "emk_merged_atom_count": ([i64, c_i64p, i64, c_i64p, i64], i64),
+    "emk_set_dihedrals": ([vp, i64, i64, c_i32p, c_i32p, c_i32p, c_i32p, i64, vp, i64, vp, vp], C.c_int),
     "emk_column_mean": ([vp, i64, i64, vp, vp], C.c_int),
     "emk_dl_column_mean": ([vp, vp, vp], C.c_int),
     "emk_backmap": ([vp, i64, vp, vp, i64, i64, vp, vp], C.c_int),

@@ -350,6 +350,37 @@ def backbone_amide_raw(central: torch.Tensor, h_after, o_after, h_angle: float, 
     return out
 
 
+def set_dihedrals_raw(start: torch.Tensor, quads, bonds, far_sides, targets: torch.Tensor) -> torch.Tensor:
+    """The rotation loop of mdtraj_backmapping (reference misc/backmapping.py:1661-1690, 1722-1745) on the GPU.
+    ``start`` (n_atoms, 3) | (frames, n_atoms, 3); ``quads`` (D, 4), ``bonds`` (D, 2) integer arrays; ``far_sides`` a list of D
+    integer index arrays; ``targets`` (frames, D) radians  ->  (frames, n_atoms, 3)."""
+    import numpy as np
+
+    require_cuda(start, "xyz")
+    require_cuda(targets, "dihedrals")
+    start, targets = f32c(start), f32c(targets)
+    if start.dim() == 2:
+        start = start[None]
+    if start.dim() != 3 or start.shape[2] != 3 or targets.dim() != 2:
+        raise EmkError(-4, f"set_dihedrals needs (n_atoms, 3) | (frames, n_atoms, 3) coordinates and (frames, D) targets, got {tuple(start.shape)}, {tuple(targets.shape)}")
+    frames, d = int(targets.shape[0]), int(targets.shape[1])
+    if start.shape[0] not in (1, frames):
+        raise EmkError(-4, f"set_dihedrals: {start.shape[0]} start structures for {frames} frames")
+    q = np.ascontiguousarray(np.asarray(quads, dtype=np.int32).reshape(-1, 4))
+    bd = np.ascontiguousarray(np.asarray(bonds, dtype=np.int32).reshape(-1, 2))
+    if len(q) != d or len(bd) != d or len(far_sides) != d:
+        raise EmkError(-4, f"set_dihedrals: {d} target columns, {len(q)} dihedral quadruplets, {len(bd)} bonds, {len(far_sides)} far sides")
+    off = np.zeros(d + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(fs) for fs in far_sides])
+    far = np.ascontiguousarray(np.concatenate([np.asarray(fs, dtype=np.int32).reshape(-1) for fs in far_sides]) if d else np.zeros(0, np.int32))
+    out = _empty_like_shape(start, (frames, start.shape[1], 3))
+    p32 = lambda a: a.ctypes.data_as(_lib.c_i32p)  # noqa: E731
+    with torch.cuda.device(start.device):
+        check(_lib.lib().emk_set_dihedrals(start.data_ptr(), start.shape[0], start.shape[1], p32(q), p32(bd), p32(off), p32(far), d,
+                                           targets.data_ptr(), frames, out.data_ptr(), stream_of(start)))
+    return out
+
+
 def column_mean_raw(x: torch.Tensor) -> torch.Tensor:
     require_cuda(x, "distances")
     x = f32c(x)

@@ -105,6 +105,8 @@ int merge_cartesians_device(const float*, int64_t, int64_t, const int64_t*, int6
 int backbone_amide_device(const float*, int64_t, int64_t, const int64_t*, int64_t, const int64_t*, int64_t, double, double, double, double,
                           float*, int64_t, cudaStream_t);
 int64_t merged_atom_count(int64_t, const int64_t*, int64_t, const int64_t*, int64_t);
+int set_dihedrals_device(const float*, int64_t, int64_t, const int32_t*, const int32_t*, const int32_t*, const int32_t*, int64_t, const float*,
+                         int64_t, float*, cudaStream_t);
 int column_mean_device(const float*, int64_t, int64_t, float*, cudaStream_t);
 int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float*, cudaStream_t);
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
@@ -918,6 +920,13 @@ int emk_backbone_amide_atoms(const float* central, int64_t b, int64_t n_atoms, c
 }
 int64_t emk_merged_atom_count(int64_t n_atoms, const int64_t* h_after, int64_t n_h_after, const int64_t* o_after, int64_t n_o_after) {
   return merged_atom_count(n_atoms, h_after, n_h_after, o_after, n_o_after);
+}
+
+int emk_set_dihedrals(const float* start, int64_t start_frames, int64_t n_atoms, const int32_t* quads, const int32_t* bonds,
+                      const int32_t* far_offsets, const int32_t* far_atoms, int64_t n_dihedrals, const float* targets, int64_t frames,
+                      float* out, void* stream) {
+  return set_dihedrals_device(start, start_frames, n_atoms, quads, bonds, far_offsets, far_atoms, n_dihedrals, targets, frames, out,
+                              as_stream(stream));
 }
 
 }  // extern "C"

@@ -185,6 +185,156 @@ int backbone_amide_device(const float* central, int64_t b, int64_t n, const int6
   return run_plan(p, plan, st);
 }
 
+// ---- topology-aware back-mapping: set the dihedrals of an all-atom structure one after the other ------------------------------
+// The numeric core of mdtraj_backmapping (encodermap/misc/backmapping.py:1661-1690 for the backbone dihedrals, :1722-1745 for
+// the side-chain dihedrals; the untested numba twin parallel_rotation_application :384-405): for every frame, for every
+// dihedral j IN ORDER: measure the current dihedral of its four atoms (misc/rotate.py:547-581), rotate the atoms on the far
+// side of its central bond by (target - current) about the bond axis through the bond's first atom (transformations'
+// rotation_matrix, restated in the reference as _rotmat_jit :356-381).  Which atoms are "far" comes from the bond graph
+// (networkx in the reference, misc/rotate.py:409-511): index lists handed over by the host.  The reference runs this as a
+// Python loop over frames x dihedrals (with a progress bar); here one CTA owns a frame, keeps its coordinates in shared memory
+// as float64 (the reference stores float32 and rounds after every rotation), warp 0 builds the rotation of the current
+// dihedral, all warps apply it to the far side.  O(frames x sum of far-side sizes); the index lists are read from L2.
+struct SetDihedralParams {
+  const float* start;        // (1 | frames, n_atoms, 3)
+  int64_t start_stride;      // 0 or 3 * n_atoms
+  const int* quads;          // (D, 4) device
+  const int* bonds;          // (D, 2) device
+  const int* far_offsets;    // (D + 1) device
+  const int* far_atoms;      // concatenated far sides, device
+  const float* targets;      // (frames, D)
+  int64_t frames;
+  int n_atoms, n_dihedrals;
+  float* out;                // (frames, n_atoms, 3)
+};
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__global__ void __launch_bounds__(256) set_dihedrals_kernel(const SetDihedralParams p) {
+  extern __shared__ double sxyz[];          // [n_atoms][3], then the 12 numbers of the current transform
+  double* xf = sxyz;
+  double* tr = sxyz + 3 * (size_t)p.n_atoms;   // R (9, row-major) and the pivot (3)
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    __syncthreads();
+    const float* src = p.start + f * p.start_stride;
+    for (int e = tid; e < 3 * p.n_atoms; e += nth) xf[e] = (double)src[e];
+    __syncthreads();
+    for (int j = 0; j < p.n_dihedrals; j++) {
+      if (tid < 32) {
+        // every lane of warp 0 computes the same numbers (no divergence, no shuffles); lane 0 publishes them
+        const int a = __ldg(p.quads + 4 * j), b = __ldg(p.quads + 4 * j + 1), c = __ldg(p.quads + 4 * j + 2), d = __ldg(p.quads + 4 * j + 3);
+        double b1[3], b2[3], b3[3], c1[3], c2[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          b1[k] = xf[3 * b + k] - xf[3 * a + k];
+          b2[k] = xf[3 * c + k] - xf[3 * b + k];
+          b3[k] = xf[3 * d + k] - xf[3 * c + k];
+        }
+        cross3(b2, b3, c1);
+        cross3(b1, b2, c2);
+        double p1 = b1[0] * c1[0] + b1[1] * c1[1] + b1[2] * c1[2];
+        p1 *= sqrt(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+        const double p2 = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
+        const double current = atan2(p1, p2);
+        const double angle = (double)__ldg(p.targets + f * p.n_dihedrals + j) - current;
+        const int u = __ldg(p.bonds + 2 * j), v = __ldg(p.bonds + 2 * j + 1);
+        double dir[3] = {xf[3 * v] - xf[3 * u], xf[3 * v + 1] - xf[3 * u + 1], xf[3 * v + 2] - xf[3 * u + 2]};
+        const double inv = 1.0 / sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        dir[0] *= inv; dir[1] *= inv; dir[2] *= inv;
+        double sa, ca;
+        sincos(angle, &sa, &ca);
+        const double oc = 1.0 - ca;
+        if (tid == 0) {
+          tr[0] = ca + dir[0] * dir[0] * oc;          tr[1] = dir[0] * dir[1] * oc - dir[2] * sa; tr[2] = dir[0] * dir[2] * oc + dir[1] * sa;
+          tr[3] = dir[1] * dir[0] * oc + dir[2] * sa; tr[4] = ca + dir[1] * dir[1] * oc;          tr[5] = dir[1] * dir[2] * oc - dir[0] * sa;
+          tr[6] = dir[2] * dir[0] * oc - dir[1] * sa; tr[7] = dir[2] * dir[1] * oc + dir[0] * sa; tr[8] = ca + dir[2] * dir[2] * oc;
+          tr[9] = xf[3 * u]; tr[10] = xf[3 * u + 1]; tr[11] = xf[3 * u + 2];
+        }
+      }
+      __syncthreads();
+      const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
+      const double px = tr[9], py = tr[10], pz = tr[11];
+      const int e0 = __ldg(p.far_offsets + j), e1 = __ldg(p.far_offsets + j + 1);
+      for (int e = e0 + tid; e < e1; e += nth) {
+        const int at = __ldg(p.far_atoms + e);
+        const double x = xf[3 * at] - px, y = xf[3 * at + 1] - py, z = xf[3 * at + 2] - pz;
+        xf[3 * at] = px + r0 * x + r1 * y + r2 * z;
+        xf[3 * at + 1] = py + r3 * x + r4 * y + r5 * z;
+        xf[3 * at + 2] = pz + r6 * x + r7 * y + r8 * z;
+      }
+      __syncthreads();
+    }
+    float* dst = p.out + f * (int64_t)(3 * p.n_atoms);
+    for (int e = tid; e < 3 * p.n_atoms; e += nth) dst[e] = (float)xf[e];
+  }
+}
+
+int set_dihedrals_device(const float* start, int64_t start_frames, int64_t n_atoms, const int32_t* quads, const int32_t* bonds,
+                         const int32_t* far_offsets, const int32_t* far_atoms, int64_t n_dihedrals, const float* targets, int64_t frames,
+                         float* out, cudaStream_t st) {
+  EMK_REQUIRE(frames == 0 || (start && out && (n_dihedrals == 0 || (quads && bonds && far_offsets && targets))), EMK_E_NULL,
+              "emk_set_dihedrals: NULL pointer argument");
+  EMK_REQUIRE(frames >= 0 && n_atoms >= 1 && n_dihedrals >= 0 && (start_frames == 1 || start_frames == frames), EMK_E_SHAPE,
+              "emk_set_dihedrals: need start (1 | frames, n_atoms, 3), targets (frames, n_dihedrals)");
+  const size_t smem = (3 * (size_t)n_atoms + 12) * sizeof(double);
+  EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_set_dihedrals: %lld atoms need %zu bytes of shared memory per frame (limit 227 KB)",
+              (long long)n_atoms, smem);
+  if (frames == 0) return EMK_OK;
+  // validate the index lists on the host (they ARE host arrays): a bad index would otherwise corrupt shared memory
+  int64_t total_far = 0;
+  for (int64_t j = 0; j < n_dihedrals; j++) {
+    for (int k = 0; k < 4; k++)
+      EMK_REQUIRE(quads[4 * j + k] >= 0 && quads[4 * j + k] < n_atoms, EMK_E_ARG, "emk_set_dihedrals: dihedral %lld names atom %d of %lld",
+                  (long long)j, quads[4 * j + k], (long long)n_atoms);
+    for (int k = 0; k < 2; k++)
+      EMK_REQUIRE(bonds[2 * j + k] >= 0 && bonds[2 * j + k] < n_atoms, EMK_E_ARG, "emk_set_dihedrals: bond %lld names atom %d of %lld",
+                  (long long)j, bonds[2 * j + k], (long long)n_atoms);
+    EMK_REQUIRE(far_offsets[j] <= far_offsets[j + 1] && far_offsets[j] >= 0, EMK_E_ARG, "emk_set_dihedrals: far_offsets must be non-decreasing");
+  }
+  if (n_dihedrals > 0) {
+    EMK_REQUIRE(far_offsets[0] == 0, EMK_E_ARG, "emk_set_dihedrals: far_offsets[0] must be 0");
+    total_far = far_offsets[n_dihedrals];
+    EMK_REQUIRE(total_far == 0 || far_atoms, EMK_E_NULL, "emk_set_dihedrals: NULL far_atoms");
+    for (int64_t e = 0; e < total_far; e++)
+      EMK_REQUIRE(far_atoms[e] >= 0 && far_atoms[e] < n_atoms, EMK_E_ARG, "emk_set_dihedrals: far side names atom %d of %lld", far_atoms[e],
+                  (long long)n_atoms);
+  }
+  // one device buffer for all four index arrays
+  const size_t n_ints = (size_t)(6 * n_dihedrals + n_dihedrals + 1 + total_far);
+  int* dbuf = nullptr;
+  int rc = scratch_alloc(reinterpret_cast<void**>(&dbuf), std::max<size_t>(n_ints, 1) * sizeof(int), st);
+  if (rc) return rc;
+  std::vector<int> host(n_ints);
+  int* hq = host.data();
+  int* hb = hq + 4 * n_dihedrals;
+  int* ho = hb + 2 * n_dihedrals;
+  int* hf = ho + n_dihedrals + 1;
+  for (int64_t k = 0; k < 4 * n_dihedrals; k++) hq[k] = quads[k];
+  for (int64_t k = 0; k < 2 * n_dihedrals; k++) hb[k] = bonds[k];
+  for (int64_t k = 0; k <= n_dihedrals; k++) ho[k] = n_dihedrals > 0 ? far_offsets[k] : 0;
+  for (int64_t k = 0; k < total_far; k++) hf[k] = far_atoms[k];
+  cudaError_t e = cudaMemcpyAsync(dbuf, host.data(), n_ints * sizeof(int), cudaMemcpyHostToDevice, st);   // pageable: staged before return
+  if (e != cudaSuccess) {
+    cudaFreeAsync(dbuf, st);
+    return fail((int)e, "emk_set_dihedrals: index upload failed: %s", cudaGetErrorString(e));
+  }
+  SetDihedralParams p{};
+  p.start = start; p.start_stride = start_frames == 1 ? 0 : 3 * n_atoms;
+  p.quads = dbuf; p.bonds = dbuf + 4 * n_dihedrals; p.far_offsets = dbuf + 6 * n_dihedrals; p.far_atoms = dbuf + 7 * n_dihedrals + 1;
+  p.targets = targets; p.frames = frames; p.n_atoms = (int)n_atoms; p.n_dihedrals = (int)n_dihedrals; p.out = out;
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(set_dihedrals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+  const unsigned grid = (unsigned)std::min<int64_t>(frames, (int64_t)sm_count() * per_sm);
+  set_dihedrals_kernel<<<grid, 256, smem, st>>>(p);
+  rc = launch_status("set_dihedrals_kernel");
+  cudaFreeAsync(dbuf, st);
+  return rc;
+}
+
 // number of atoms the merge produces (host only)
 int64_t merged_atom_count(int64_t n, const int64_t* h_after, int64_t nh_after, const int64_t* o_after, int64_t no_after) {
   if (n < 1) return 0;

@@ -79,3 +79,60 @@ def merge_cartesians(central_cartesians: torch.Tensor, N_indices: Sequence[int],
 def backbone_with_amide_atoms(cartesians: torch.Tensor, N_indices: Sequence[int], C_indices: Sequence[int]) -> torch.Tensor:
     """``merge_cartesians(c, N, C, guess_amide_H(c, N), guess_amide_O(c, C))`` as ONE launch (the H and O arrays never exist)."""
     return _ops.backbone_amide_raw(cartesians, list(N_indices)[1::], list(C_indices), *AMIDE_H, *AMIDE_O)
+
+
+# ---- topology-aware back-mapping: the rotation loop of mdtraj_backmapping -------------------------------------------------------
+def near_and_far_sides(n_atoms: int, bonds, edges):
+    """Atoms on either side of every edge of a tree-like bond graph: ``(near_sides, far_sides)``, lists of sorted integer arrays,
+    edge[0] on the near side and edge[1] on the far side.  Reference: ``_get_near_and_far_networkx``
+    (encodermap/misc/rotate.py:409-511), which removes the edge from a networkx graph and takes the two connected components;
+    here a plain breadth-first search (no networkx), same membership.  Raises as the reference does when removing the edge does
+    not split the graph in two (rings, several chains)."""
+    import numpy as np
+
+    adj = [[] for _ in range(n_atoms)]
+    for a, b in np.asarray(bonds, dtype=np.int64).reshape(-1, 2):
+        adj[a].append(int(b))
+        adj[b].append(int(a))
+    near_sides, far_sides = [], []
+    for u, v in np.asarray(edges, dtype=np.int64).reshape(-1, 2):
+        u, v = int(u), int(v)
+        if v not in adj[u]:
+            raise Exception(f"Seems like the edge {(u, v)} is not part of the graph.")
+        seen = np.zeros(n_atoms, dtype=bool)
+        seen[v] = True
+        stack = [v]
+        while stack:                       # everything reachable from edge[1] without crossing the edge
+            a = stack.pop()
+            for b in adj[a]:
+                if (a == v and b == u) or seen[b]:
+                    continue
+                seen[b] = True
+                stack.append(b)
+        if seen[u]:
+            raise Exception(f"Splitting at edge {(u, v)} does not work: the two atoms are still connected (ring?).")
+        far = np.flatnonzero(seen)
+        other = np.zeros(n_atoms, dtype=bool)
+        other[u] = True
+        stack = [u]
+        while stack:
+            a = stack.pop()
+            for b in adj[a]:
+                if (a == u and b == v) or other[b]:
+                    continue
+                other[b] = True
+                stack.append(b)
+        if other.sum() + far.size != n_atoms:
+            raise Exception("Protein might be cyclic or contain more than 1 chain.")
+        near_sides.append(np.flatnonzero(other))
+        far_sides.append(far)
+    return near_sides, far_sides
+
+
+def set_dihedrals(xyz: torch.Tensor, dihedral_indices, bond_indices, far_sides, dihedrals: torch.Tensor) -> torch.Tensor:
+    """The rotation loop of ``mdtraj_backmapping`` (encodermap/misc/backmapping.py:1661-1690 for the backbone, :1722-1745 for the
+    side chains -- concatenate the lists, backbone first): every frame starts from ``xyz`` ((n_atoms, 3) shared, or one structure
+    per frame) and has its dihedrals set to ``dihedrals[frame]`` one after the other by rotating the far side of each central
+    bond.  Returns (frames, n_atoms, 3); what is left to the caller is the topology work around it (which atoms, which bonds:
+    mdtraj / networkx in the reference) and writing the trajectory."""
+    return _ops.set_dihedrals_raw(xyz, dihedral_indices, bond_indices, far_sides, dihedrals)

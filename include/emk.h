@@ -248,6 +248,23 @@ EMK_API int emk_backbone_amide_atoms(const float* central, int64_t b, int64_t n_
                                      double o_length, float* out, int64_t n_out, void* stream);
 EMK_API int64_t emk_merged_atom_count(int64_t n_atoms, const int64_t* h_after, int64_t n_h_after, const int64_t* o_after, int64_t n_o_after);
 
+/* ------------------------------------------------------------------------------------------
+ * Topology-aware back-mapping: set the dihedrals of an all-atom structure, one after the other
+ *   the numeric core of mdtraj_backmapping -- encodermap/misc/backmapping.py:1661-1690 (backbone dihedrals), :1722-1745
+ *   (side-chain dihedrals; pass them after the backbone ones), dihedral formula misc/rotate.py:547-581, rotation matrix as in
+ *   _rotmat_jit misc/backmapping.py:356-381.  For every frame and every dihedral j in order: rotate the atoms of far side j by
+ *   (targets[frame, j] - current dihedral of quads[j]) about the axis bonds[j][0] -> bonds[j][1] through atom bonds[j][0].
+ *   start        device (1 | frames, n_atoms, 3): the structure every frame starts from (one shared, or one per frame)
+ *   quads, bonds HOST int32 (D, 4), (D, 2);  far_offsets HOST int32 (D + 1), far_atoms HOST int32: far side j is
+ *                far_atoms[far_offsets[j] .. far_offsets[j + 1])  (misc/rotate.py:409-511 builds them from the bond graph)
+ *   targets      device (frames, D) radians;   out device (frames, n_atoms, 3)
+ * Coordinates are held in float64 between the rotations.  At most 9 600 atoms (shared memory).  Forward only; not capturable
+ * (pageable index upload).
+ * ---------------------------------------------------------------------------------------- */
+EMK_API int emk_set_dihedrals(const float* start, int64_t start_frames, int64_t n_atoms, const int32_t* quads, const int32_t* bonds,
+                              const int32_t* far_offsets, const int32_t* far_atoms, int64_t n_dihedrals, const float* targets,
+                              int64_t frames, float* out, void* stream);
+
 /* mean over rows: (rows,cols) -> (cols)   the `tf.reduce_mean(distances, 0)` of BackMapLayer.call, layers.py:970 */
 EMK_API int emk_column_mean(const float* x, int64_t rows, int64_t cols, float* out, void* stream);
 EMK_API int emk_dl_column_mean(const DLManagedTensor* x, DLManagedTensor* out, void* stream);

@@ -418,6 +418,48 @@ def merge_cartesians(central_cartesians, N_indices, O_indices, H_cartesians, O_c
     return out
 
 
+# ---- topology-aware back-mapping: the rotation loop of mdtraj_backmapping (numpy; the reference's loop is numpy too) ------------
+def dihedral_np(xyz: np.ndarray, indices) -> float:
+    """Reference: encodermap/misc/rotate.py:547-581 (adapted from MDTraj there; numba twin misc/backmapping.py:329-352)."""
+    a, b, c, d = (xyz[i] for i in indices)
+    b1, b2, b3 = b - a, c - b, d - c
+    c1, c2 = np.cross(b2, b3), np.cross(b1, b2)
+    p1 = (b1 * c1).sum(-1) * (b2 * b2).sum(-1) ** 0.5
+    p2 = (c1 * c2).sum(-1)
+    return np.arctan2(p1, p2)
+
+
+def rotation_matrix_about(angle: float, direction: np.ndarray, pivot: np.ndarray) -> np.ndarray:
+    """4x4 homogeneous rotation about an axis through ``pivot``: transformations.rotation_matrix, restated by the reference as
+    _rotmat_jit (encodermap/misc/backmapping.py:356-381)."""
+    sina, cosa = np.sin(angle), np.cos(angle)
+    u = direction / (direction ** 2).sum() ** 0.5
+    r = np.identity(3) * cosa + np.outer(u, u) * (1.0 - cosa)
+    us = u * sina
+    r = r + np.array([[0.0, -us[2], us[1]], [us[2], 0.0, -us[0]], [-us[1], us[0], 0.0]])
+    m = np.identity(4)
+    m[:3, :3] = r
+    m[:3, 3] = pivot - r @ pivot
+    return m
+
+
+def set_dihedrals(xyz, dihedral_indices, bond_indices, far_sides, dihedrals) -> np.ndarray:
+    """Reference: encodermap/misc/backmapping.py:1661-1690 (and :1722-1745 for the side-chain dihedrals), in float64."""
+    xyz = np.asarray(xyz, dtype=np.float64)
+    dihedrals = np.asarray(dihedrals, dtype=np.float64)
+    frames = dihedrals.shape[0]
+    new_xyz = np.repeat(xyz[None], frames, 0).copy() if xyz.ndim == 2 else xyz.copy()
+    new_xyz = np.pad(new_xyz, ((0, 0), (0, 0), (0, 1)), mode="constant", constant_values=1)
+    for i in range(frames):
+        for j in range(dihedrals.shape[1]):
+            far_side, dihedral, bond = far_sides[j], dihedral_indices[j], bond_indices[j]
+            angle = dihedrals[i, j] - dihedral_np(new_xyz[i, :, :3], dihedral)
+            direction = np.diff(new_xyz[i, bond, :3], axis=0).flatten()
+            rotmat = rotation_matrix_about(angle, direction, new_xyz[i, bond[0], :3])
+            new_xyz[i, far_side, :3] = rotmat.dot(new_xyz[i, far_side].T).T[:, :3]
+    return new_xyz[..., :3]
+
+
 def sigmoid_loss_and_grad(y_true, y_pred, periodicity=2 * pi, sig=DEFAULT_SIG, dtype=torch.float64):
     """Loss and dL/d(y_pred) by autograd over the restated forward (the reference relies on
     tf.GradientTape; only the latent side needs a gradient)."""

@@ -1290,3 +1290,62 @@ def test_cartesian_distance_loss_from_coordinates(em, b, n, sel):
     np.testing.assert_allclose(3.0 * lsum, loss.item(), rtol=3e-7)
     with pytest.raises(em._lib.EmkError):
         f(cu(xyz).requires_grad_(True), zg)            # the coordinates are data: their gradient is refused, not dropped
+
+
+# ---------------------------------------------------------------------------------------------------
+# topology-aware back-mapping: the rotation loop of mdtraj_backmapping (reference misc/backmapping.py:1661-1690, 1722-1745)
+# ---------------------------------------------------------------------------------------------------
+def test_set_dihedrals_golden_and_oracle(em, golden):
+    from encodermap_b200 import _lib
+    from encodermap_b200.misc.backmapping import near_and_far_sides, set_dihedrals
+
+    g = golden["generation"]
+    quads, bond_idx, off, far = g["sd_quads"], g["sd_bond_idx"], g["sd_far_offsets"], g["sd_far_atoms"]
+    far_sides = [far[off[j]:off[j + 1]] for j in range(len(quads))]
+    got = set_dihedrals(cu(g["sd_start"]), quads, bond_idx, far_sides, cu(g["sd_targets"])).cpu().numpy()
+    assert np.abs(got - g["sd_out"]).max() < 2e-6          # float64 between the rotations, float32 in and out
+    # one start structure per frame, and a batch larger than the grid
+    rng = np.random.default_rng(8)
+    frames = 2500
+    starts = (g["sd_start"][None] + rng.normal(scale=0.01, size=(frames,) + g["sd_start"].shape)).astype(np.float32)
+    targets = rng.uniform(-pi, pi, size=(frames, len(quads))).astype(np.float32)
+    got = set_dihedrals(cu(starts), quads, bond_idx, far_sides, cu(targets)).cpu().numpy()
+    sub = [0, 1, 1234, frames - 1]
+    want = O.set_dihedrals(starts[sub].astype(np.float64), quads, bond_idx, far_sides, targets[sub].astype(np.float64))
+    assert np.abs(got[sub] - want).max() < 5e-6
+    # a 150-residue chain with side chains (1 650 dihedral rotations of up to 1 100 atoms each per frame)
+    n_res = 150
+    bonds, kind = [], []
+    for r in range(n_res):
+        base = len(kind)
+        kind += ["N", "CA", "C"]
+        if r:
+            bonds.append((prev_c, base))
+        bonds += [(base, base + 1), (base + 1, base + 2)]
+        prev_c = base + 2
+    n_bb = len(kind)
+    side_quads = []
+    for r in range(n_res):
+        chain = [3 * r, 3 * r + 1]
+        for _ in range(int(rng.integers(0, 5))):
+            kind.append("S")
+            bonds.append((chain[-1], len(kind) - 1))
+            chain.append(len(kind) - 1)
+        side_quads += [chain[k:k + 4] for k in range(len(chain) - 3)]
+    n_atoms = len(kind)
+    all_quads = np.vstack([np.array([[k, k + 1, k + 2, k + 3] for k in range(n_bb - 3)]), np.array(side_quads).reshape(-1, 4)])
+    _, fars = near_and_far_sides(n_atoms, bonds, all_quads[:, 1:3])
+    start = np.cumsum(rng.normal(scale=0.09, size=(n_atoms, 3)), axis=0).astype(np.float32)
+    targets = rng.uniform(-pi, pi, size=(3, len(all_quads))).astype(np.float32)
+    got = set_dihedrals(cu(start), all_quads, all_quads[:, 1:3], fars, cu(targets)).cpu().numpy()
+    want = O.set_dihedrals(start.astype(np.float64), all_quads, all_quads[:, 1:3], fars, targets.astype(np.float64))
+    assert np.abs(got - want).max() < 1e-4                 # nm tolerance of the north star; ~1e-5 in practice (float32 input angles)
+    for i in range(3):
+        reached = np.array([O.dihedral_np(got[i].astype(np.float64), q) for q in all_quads])
+        assert np.abs((reached - targets[i] + pi) % (2 * pi) - pi).max() < 2e-3      # reference's own verify tolerance is 1e-3 (:1695)
+    # errors: index outside the structure, CPU tensors
+    with pytest.raises(_lib.EmkError):
+        set_dihedrals(cu(start), [[0, 1, 2, n_atoms]], [[1, 2]], [np.array([2])], cu(np.zeros((1, 1))))
+    with pytest.raises(_lib.EmkError):
+        set_dihedrals(torch.from_numpy(start), all_quads[:1], all_quads[:1, 1:3], fars[:1], cu(targets[:, :1]))
+    assert set_dihedrals(cu(start), np.zeros((0, 4), int), np.zeros((0, 2), int), [], cu(np.zeros((2, 0)))).shape == (2, n_atoms, 3)

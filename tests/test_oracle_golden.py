@@ -147,3 +147,31 @@ def test_generation_golden(golden):
         cosang = (bond * prev).sum(2) / np.linalg.norm(bond, axis=2) / np.linalg.norm(prev, axis=2)
         np.testing.assert_allclose(np.arccos(cosang), 123 / 180 * pi, rtol=1e-9)
     np.testing.assert_allclose(O.guess_sp2_atom(g["n30_xyz"], g["n30_sel"].tolist(), 1.9, 0.101).numpy(), g["n30_sp2_generic"], rtol=0, atol=1e-12)
+
+
+def test_set_dihedrals_golden(golden):
+    """The rotation loop of mdtraj_backmapping (reference misc/backmapping.py:1661-1690) restated in the oracle, against the loop
+    run on the reference's own primitives (_dihedral, _rotmat_jit, _get_near_and_far_networkx: tools/gen_golden.py); and the
+    product's breadth-first far sides against networkx's."""
+    from encodermap_b200.misc.backmapping import near_and_far_sides
+
+    g = golden["generation"]
+    quads, bond_idx, off, far = g["sd_quads"], g["sd_bond_idx"], g["sd_far_offsets"], g["sd_far_atoms"]
+    far_sides = [far[off[j]:off[j + 1]] for j in range(len(quads))]
+    out = O.set_dihedrals(g["sd_start"], quads, bond_idx, far_sides, g["sd_targets"])
+    np.testing.assert_allclose(out, g["sd_out"], rtol=0, atol=1e-11)
+    # the unmodified _rotmat_jit builds its matrix in float32: same structure to float32 accuracy
+    assert np.abs(out - g["sd_out_f32rot"]).max() < 2e-5
+    # every dihedral ends at its target
+    for i in range(out.shape[0]):
+        got = np.array([O.dihedral_np(out[i], q) for q in quads])
+        assert np.abs((got - g["sd_targets"][i] + pi) % (2 * pi) - pi).max() < 1e-9
+    n_atoms = g["sd_start"].shape[0]
+    near, fars = near_and_far_sides(n_atoms, g["sd_bonds"], bond_idx)
+    for j in range(len(quads)):
+        assert np.array_equal(fars[j], far_sides[j])
+        assert len(near[j]) == g["sd_near_sizes"][j] and len(near[j]) + len(fars[j]) == n_atoms
+    with pytest.raises(Exception):
+        near_and_far_sides(4, [(0, 1), (1, 2), (2, 0), (2, 3)], [(0, 1)])       # a ring: removing the edge does not split it
+    with pytest.raises(Exception):
+        near_and_far_sides(4, [(0, 1), (2, 3)], [(1, 2)])                        # not a bond

@@ -222,12 +222,13 @@ class _TFShim:
 # ----------------------------------------------------------------------------------------
 
 
-def _extract(path: Path, names, ns):
-    """Compile the named top-level (or class-level) function definitions of ``path`` into ``ns``."""
+def _extract(path: Path, names, ns, take_last=()):
+    """Compile the named top-level (or class-level) function definitions of ``path`` into ``ns`` (the first definition of a
+    name, or the last for names in ``take_last``: functions preceded by ``@overload`` stubs)."""
     tree = ast.parse(path.read_text())
     found = {}
     for node in ast.walk(tree):
-        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+        if isinstance(node, ast.FunctionDef) and node.name in names and (node.name not in found or node.name in take_last):
             node.decorator_list = []  # drop @tf.function / @overload
             node.returns = None
             for a in node.args.args + node.args.kwonlyargs:
@@ -459,6 +460,97 @@ def main():
     sel = np.array([1, 4, 5, 17, 28, 29])
     g["n30_sel"] = sel
     g["n30_sp2_generic"] = np.asarray(R["guess_sp2_atom"](tf64.convert_to_tensor(xyz), sel, 1.9, 0.101))
+    # ---- the rotation loop of mdtraj_backmapping (misc/backmapping.py:1661-1690): its primitives are the reference's own --
+    # _dihedral / _displacement (misc/rotate.py:547-601), _rotmat_jit (misc/backmapping.py:356-381, the reference's restatement of
+    # transformations.rotation_matrix, which is not installed) and _get_near_and_far_networkx (misc/rotate.py:409-511), extracted
+    # and executed unmodified; the eight-line loop around them is restated here line by line.
+    import networkx as nx
+
+    gen = {"np": np, "nx": nx, "Optional": None, "Union": None, "md": None, "jit": lambda *a, **k: (lambda f: f)}
+    _extract(REF / "encodermap/misc/rotate.py", ["_displacement", "_dihedral", "_get_near_and_far_networkx"], gen,
+             take_last=("_get_near_and_far_networkx",))
+    _extract(REF / "encodermap/misc/backmapping.py", ["_rotmat_jit"], gen)
+    # _rotmat_jit builds the matrix in float32 (its three dtype="float32" literals); the sequential path that actually runs
+    # calls transformations.rotation_matrix, which is float64.  Both are evaluated: the function as it stands, and the same
+    # source with those literals promoted.
+    src = (REF / "encodermap/misc/backmapping.py").read_text()
+    node = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "_rotmat_jit")
+    node.decorator_list = []
+    gen64 = dict(gen)
+    exec(compile(ast.unparse(node).replace("'float32'", "'float64'").replace("np.float32", "np.float64"), "_rotmat_jit[float64]", "exec"), gen64)
+    # a branched, ring-free "protein": backbone of 3 R atoms, an O on every C, an H on every N but the first, side chains of
+    # 0..4 atoms on the CA (what mdtraj's bond graph looks like without rings)
+    n_res = 12
+    bonds, names = [], []
+    for r in range(n_res):
+        base = len(names)
+        names += ["N", "CA", "C"]
+        if r > 0:
+            bonds.append((prev_c, base))
+        bonds += [(base, base + 1), (base + 1, base + 2)]
+        prev_c = base + 2
+    n_bb = len(names)
+    for r in range(n_res):
+        n_i, ca_i, c_i = 3 * r, 3 * r + 1, 3 * r + 2
+        names.append("O"); bonds.append((c_i, len(names) - 1))
+        if r > 0:
+            names.append("H"); bonds.append((n_i, len(names) - 1))
+        parent = ca_i
+        for _ in range(int(rng2.integers(0, 5))):
+            names.append("S"); bonds.append((parent, len(names) - 1)); parent = len(names) - 1
+    n_all = len(names)
+    graph = nx.Graph()
+    graph.add_nodes_from(range(n_all))
+    graph.add_edges_from(bonds)
+    # backbone dihedrals psi / omega / phi: quadruplets of consecutive backbone atoms, central bond = atoms 1, 2 of each
+    quads = np.array([[k, k + 1, k + 2, k + 3] for k in range(n_bb - 3)])
+    # side-chain dihedrals: N-CA-S1-S2, CA-S1-S2-S3, ... wherever the chain is long enough
+    adj = {a: [] for a in range(n_all)}
+    for a, b in bonds:
+        adj[a].append(b); adj[b].append(a)
+    side_quads = []
+    for r in range(n_res):
+        chain = [3 * r, 3 * r + 1]
+        nxt = [b for b in adj[3 * r + 1] if names[b] == "S"]
+        while nxt:
+            chain.append(nxt[0])
+            nxt = [b for b in adj[chain[-1]] if names[b] == "S" and b not in chain]
+        side_quads += [chain[k:k + 4] for k in range(len(chain) - 3)]
+    all_quads = np.vstack([quads, np.array(side_quads).reshape(-1, 4)])
+    bond_idx = all_quads[:, 1:3]
+    near_sides, far_sides = gen["_get_near_and_far_networkx"](graph, bond_idx)
+    start = np.cumsum(rng2.normal(scale=0.09, size=(n_all, 3)), axis=0).astype(np.float32).astype(np.float64)
+    targets = rng2.uniform(-math.pi, math.pi, size=(5, len(all_quads))).astype(np.float32).astype(np.float64)
+    def run_loop(rotmat_fn):
+        new_xyz = np.repeat(start[None], 5, 0)
+        new_xyz = np.pad(new_xyz, ((0, 0), (0, 0), (0, 1)), mode="constant", constant_values=1)       # :1631-1633
+        for i in range(targets.shape[0]):                                                            # :1673-1690
+            for j in range(targets.shape[1]):
+                far_side, dihedral, bond = far_sides[j], all_quads[j], bond_idx[j]
+                target_angle = targets[i, j]
+                current_angle = gen["_dihedral"](new_xyz[i, :, :3], dihedral)[0][0]
+                angle = target_angle - current_angle
+                direction = np.diff(new_xyz[i, bond, :3], axis=0).flatten()
+                pivot_point = new_xyz[i, bond[0], :3]
+                rotmat = rotmat_fn(angle, direction.copy(), pivot_point)
+                new_xyz[i, far_side, :3] = rotmat.dot(new_xyz[i, far_side].T).T[:, :3]
+        return new_xyz
+
+    new_xyz = run_loop(gen64["_rotmat_jit"])
+    new_xyz_f32rot = run_loop(gen["_rotmat_jit"])
+    reached = np.array([[gen["_dihedral"](new_xyz[i, :, :3], q)[0][0] for q in all_quads] for i in range(5)])
+    # every dihedral is left where it was put unless a LATER rotation moves one of its atoms relative to the others; for this
+    # ordering (backbone along the chain, side chains afterwards) all of them survive
+    dev = np.abs((reached - targets + math.pi) % (2 * math.pi) - math.pi)
+    assert dev.max() < 1e-9, dev.max()
+    assert np.abs(new_xyz_f32rot - new_xyz).max() < 2e-5
+    g["sd_out_f32rot"] = new_xyz_f32rot[..., :3]
+    g["sd_bonds"] = np.array(bonds)
+    g["sd_quads"], g["sd_bond_idx"] = all_quads, bond_idx
+    g["sd_far_offsets"] = np.concatenate([[0], np.cumsum([len(f_) for f_ in far_sides])])
+    g["sd_far_atoms"] = np.concatenate([np.sort(np.asarray(f_)) for f_ in far_sides])
+    g["sd_near_sizes"] = np.array([len(n_) for n_ in near_sides])
+    g["sd_start"], g["sd_targets"], g["sd_out"] = start, targets, new_xyz[..., :3]
     np.savez_compressed(OUT / "generation.npz", **g)
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size} bytes")
