@@ -284,3 +284,28 @@ def test_merged_atom_count_follows_the_reference_loop(L):
     for n, h, o in cases:
         assert count(n, h, o) == reference_loop(n, h, o), (n, h, o)
     assert count(10, [10], []) == -1 and count(10, [], [-1]) == -1      # outside the backbone
+
+
+def test_near_and_far_sides_against_networkx_on_random_trees():
+    """Product host logic (breadth-first far sides) against the reference's method -- remove the edge from a networkx graph, take
+    the two connected components (misc/rotate.py:444-505) -- on random trees; membership must be identical."""
+    nx = pytest.importorskip("networkx")
+    from encodermap_b200.misc.backmapping import near_and_far_sides
+
+    rng = np.random.default_rng(12)
+    for _ in range(25):
+        n = int(rng.integers(2, 80))
+        bonds = [(int(rng.integers(0, k)), k) for k in range(1, n)]          # a random tree
+        edges = [bonds[k] if rng.random() < 0.5 else bonds[k][::-1] for k in rng.choice(len(bonds), size=min(10, len(bonds)), replace=False)]
+        near, far = near_and_far_sides(n, bonds, edges)
+        for (u, v), nr, fr in zip(edges, near, far):
+            g = nx.Graph()
+            g.add_nodes_from(range(n))
+            g.add_edges_from(bonds)
+            g.remove_edge(u, v)
+            comps = list(nx.connected_components(g))
+            assert len(comps) == 2
+            comp_u = next(c for c in comps if u in c)
+            comp_v = next(c for c in comps if v in c)
+            assert set(nr.tolist()) == comp_u and set(fr.tolist()) == comp_v
+            assert np.all(np.diff(nr) > 0) and np.all(np.diff(fr) > 0)      # sorted, unique
