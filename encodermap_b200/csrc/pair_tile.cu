@@ -37,6 +37,14 @@ constexpr int STAGES = 4;
 constexpr int NTHREADS = 256;
 constexpr int MAX_LATENT = 8;
 
+// Thread (ty, tx) of the 16 x 16 grid.  A warp covers WLY consecutive ty and WLX = 32 / WLY consecutive tx, so that a warp-wide
+// LDS.128 of the row operand touches WLY and one of the column operand WLX distinct 16-byte pieces: with 4 x 8 both are at
+// most 128 bytes = one shared-memory wavefront each (the 2 x 16 arrangement of round 1 read 256 bytes = two wavefronts per
+// column-operand load; the Euclidean main loop is co-limited by shared-memory wavefronts).  The eight warps tile the grid 4 x 2.
+constexpr int WLY = 4, WLX = 32 / WLY;
+__device__ __forceinline__ int thread_ty(int tid) { return WLY * ((tid >> 5) / (16 / WLX)) + ((tid & 31) / WLX); }
+__device__ __forceinline__ int thread_tx(int tid) { return WLX * ((tid >> 5) % (16 / WLX)) + ((tid & 31) % WLX); }
+
 // Tile geometry.  Threads form a 16 x 16 grid; thread (ty, tx) owns rows ty + 16 i (i < MI) and columns tx + 16 j (j < MJ).
 //   Big   (128 x 64, 8 x 4 micro-tile): the shape the public tile numbering (emk_pair_tile_count / _range / _decode) is in, best
 //         operand reuse (12 LDS.128 per 32 pair-float4 products), two CTAs per SM -- large evaluations and tile ranges.
@@ -289,20 +297,21 @@ __device__ __forceinline__ void cost_epilogue(const float (&d2h)[NI][G::MJ], con
           rs[i] += t;
           cs[j] -= t;
         }
-      // row side: the 16 lanes of a half-warp share ty
+      // row side: the WLX lanes of a warp that share ty
 #pragma unroll
       for (int i = 0; i < NI; i++) {
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+        for (int o = WLX / 2; o > 0; o >>= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);   // lanes that share ty
         const int64_t r = row0 + ty + 16 * (i0 + i);
-        if (tx == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c0 + c], rs[i] * gs);
+        if ((lane & (WLX - 1)) == 0 && r < p.n) atomicAdd(&p.grad[r * p.l + c0 + c], rs[i] * gs);   // one per warp and row
       }
       // column side (mirror image of the tile); diagonal tiles already visit both orders
       if (!diag) {
 #pragma unroll
         for (int j = 0; j < MJ; j++) {
-          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
-          if (lane < 16) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
+#pragma unroll
+          for (int o = WLX; o < 32; o <<= 1) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);   // lanes that share tx
+          if (lane < WLX) atomicAdd(&colsum[c * TN + tx + 16 * j], cs[j]);
         }
       }
     }
@@ -352,8 +361,8 @@ __global__ void __launch_bounds__(NTHREADS, G::MIN_CTAS) pair_tile_kernel(const 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int ty = tid >> 4;  // 0..15 -> rows ty + 16 i
-  const int tx = tid & 15;  // 0..15 -> cols tx + 16 j
+  const int ty = thread_ty(tid);  // 0..15 -> rows ty + 16 i
+  const int tx = thread_tx(tid);  // 0..15 -> cols tx + 16 j
 
   // Small problems (few tiles) are spread over the SMs by splitting the feature axis over a thread-block
   // cluster: the S CTAs of a cluster own the same tile and S interleaved shares of the k-chunks; partial squared
@@ -535,7 +544,7 @@ __global__ void __launch_bounds__(NTHREADS) small_cost_kernel(const PairParams p
   __shared__ float colsum[MAX_LATENT * TN];
   __shared__ double red_d[NTHREADS / 32];
   constexpr int S = 8 / NI;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ty = thread_ty(tid), tx = thread_tx(tid);
   const int i0 = (int)(blockIdx.x % S) * NI;
   int64_t I, J;
   tile_decode(p.tile_begin + blockIdx.x / S, p.tiles_per_row, p.tile_rows, &I, &J);
