@@ -297,10 +297,13 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        e2e_step()
+        e2e_loss = e2e_step()
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    # the end-to-end path (host input, streamed / interleaved over ranks) returns the same loss and gradient as the device path
+    e2e_check = {"loss_rel_diff": abs(e2e_loss - loss_value) / abs(loss_value),
+                 "grad_rel_diff": ((gh.to(dev) - grad).norm() / grad.norm()).item()}
     e2e_value = pairs / (e2e_ms * 1e-3)
     # bytes this rank copies in per step: the rows from the band of its first tile to the end + the latent
     if world > 2:   # 1/G of the rows per host link + NVLink all-gather (sigmoid_loss picks this above two ranks)
@@ -378,8 +381,8 @@ def run_ours(args):
                          "peak_source": f"148 SM x 128 lanes x {peaks['sm_max_mhz']} MHz ({peaks['source']}); no FP32 figure is measured there"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "unique pairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(h2d_max), "d2h_bytes_per_step": gh.numel() * 4 + 4,
-                    "note": "sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward; h2d_bytes_per_step = the largest rank's share. n_gpus <= 2: every rank copies the rows its tile range touches in chunks on a side stream behind the pair tiles that need them; n_gpus > 2: 1/n_gpus of the rows per host link + all-gather over NVLink; loss + gradient read back"},
+                    "h2d_bytes_per_step": int(h2d_max), "d2h_bytes_per_step": gh.numel() * 4 + 4, "check_vs_device_path": e2e_check,
+                    "note": "sigmoid_loss(...)(y_true pinned host tensor, y_pred) + backward; h2d_bytes_per_step = the largest rank's share. n_gpus <= 2: every rank copies the rows its tile range touches in chunks on a side stream behind the pair tiles that need them; n_gpus > 2: every rank takes 1/n_gpus of the tiles of every 8192-row chunk, copies 1/n_gpus of the chunk over its own host link and the chunk is completed by an all-gather over NVLink behind the tiles of the previous chunk; loss + gradient read back"},
             "gpu_launches": args.steps * world,
             "per_rank": per_rank,
             "multi_gpu_check": multi_gpu_check,

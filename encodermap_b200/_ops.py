@@ -83,7 +83,8 @@ def _row_chunk_tiles(n: int, rows_per_chunk: int):
 
 
 def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicity: float, sig: Sequence[float],
-                          need_grad: bool = True, rows_per_chunk: int = 8192, tile_range: Optional[Tuple[int, int]] = None):
+                          need_grad: bool = True, rows_per_chunk: int = 8192, tile_range: Optional[Tuple[int, int]] = None,
+                          interleave_group=None):
     """Same result as ``sigmoid_cost_raw`` with the high-d input in (pinned) HOST memory: rows are copied to the device in
     chunks from the LAST row backwards on a side stream while the pair tiles that only need the rows already there run
     on the current stream (tile ids are band-major, so every chunk of rows unlocks one contiguous tile range).  The copy
@@ -91,7 +92,13 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
 
     With a ``tile_range`` (one rank's share of a multi-GPU evaluation) only the rows that range touches are copied --
     tiles from tile t on need no row before the band of t, so the last of 8 ranks moves 35 % of the matrix -- and every
-    rank streams its own rows over its own host link behind its own tiles: no exchange of inputs between GPUs at all."""
+    rank streams its own rows over its own host link behind its own tiles: no exchange of inputs between GPUs at all.
+
+    With ``interleave_group`` (a torch.distributed group of G ranks that all hold the same pinned host tensor; ``tile_range`` must
+    be None) the work is split the other way round: every rank takes 1/G of the tiles of EVERY row chunk, copies 1/G of every
+    chunk over its own host link and the chunk is completed by an all-gather over NVLink on the side stream -- all ranks start
+    after the first chunk and the remaining copies hide behind tiles on every rank, where a contiguous tile range makes the rank
+    that owns the first band wait for the whole input.  The partial results still have to be summed by the caller."""
     require_cuda(low, "y_pred")
     if high_host.is_cuda:
         return sigmoid_cost_raw(high_host, low, periodicity, sig, tile_range, need_grad)
@@ -99,11 +106,22 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
         raise EmkError(-4, "streamed sigmoid cost needs a contiguous rank-2 float32 host tensor")
     low = f32c(low)
     n, d = high_host.shape
+    rows_per_chunk = max(1024, (rows_per_chunk // 1024) * 1024)
+    world = rank = 0
+    if interleave_group is not None:
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(interleave_group), dist.get_rank(interleave_group)
+        if tile_range is not None:
+            raise ValueError("interleave_group and tile_range are mutually exclusive")
+        if world == 1 or n % rows_per_chunk != 0 or rows_per_chunk % world != 0 or d % 4 != 0:
+            # ragged chunks cannot be all-gathered in equal slices: contiguous tile ranges, every rank streams what it needs
+            tile_range = _lib.pair_tile_range(n, rank, world)
+            world = 0
     if d % 4 != 0:
         # the kernel would re-pad the whole (n, d) matrix into TMA-legal scratch on every chunk call (and read rows the
         # side stream is still writing): one plain copy, then the ordinary path, which pads once
         return sigmoid_cost_raw(high_host.to(low.device, non_blocking=True), low, periodicity, sig, tile_range, need_grad)
-    rows_per_chunk = max(1024, (rows_per_chunk // 1024) * 1024)
     chunks = _row_chunk_tiles(n, rows_per_chunk)
     total = _lib.pair_tile_count(n)
     tb, te = (0, total) if tile_range is None else tile_range
@@ -132,10 +150,19 @@ def sigmoid_cost_streamed(high_host: torch.Tensor, low: torch.Tensor, periodicit
                 break         # every remaining chunk lies before this rank's first tile: its rows are never read
             t0, t1 = max(t0, tb), min(t1, te)
             with torch.cuda.stream(side):
-                high[r0:r1].copy_(high_host[r0:r1], non_blocking=True)
+                if world > 1:
+                    per = (r1 - r0) // world
+                    mine = high[r0 + rank * per:r0 + (rank + 1) * per]
+                    mine.copy_(high_host[r0 + rank * per:r0 + (rank + 1) * per], non_blocking=True)
+                    dist.all_gather_into_tensor(high[r0:r1], mine, group=interleave_group)   # in place: `mine` is this rank's slice
+                else:
+                    high[r0:r1].copy_(high_host[r0:r1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
             main.wait_event(ev)
+            if world > 1:      # this rank's share of the chunk's tiles
+                cnt = t1 - t0
+                t0, t1 = t0 + cnt * rank // world, t0 + cnt * (rank + 1) // world
             if t1 > t0:
                 flags = base_flags | (_lib.EMK_COST_ZERO_OUTPUTS if first else 0)
                 check(_lib.lib().emk_dl_sigmoid_cost(DL(high), DL(low), float(periodicity), sig_array(sig), t0, t1,
@@ -149,9 +176,10 @@ class SigmoidCostStreamed(torch.autograd.Function):
     """SigmoidCost with a pinned host tensor as the high-d input (copy overlapped with the pair tiles)."""
 
     @staticmethod
-    def forward(ctx, high_host, low, periodicity, sig, tile_range=None, reduce_fn=None):
+    def forward(ctx, high_host, low, periodicity, sig, tile_range=None, reduce_fn=None, interleave_group=None):
         _reject_high_grad(ctx.needs_input_grad[0])
-        loss, grad = sigmoid_cost_streamed(high_host, low, periodicity, sig, ctx.needs_input_grad[1], tile_range=tile_range)
+        loss, grad = sigmoid_cost_streamed(high_host, low, periodicity, sig, ctx.needs_input_grad[1], tile_range=tile_range,
+                                           interleave_group=interleave_group)
         if reduce_fn is not None:  # multi-GPU: sum the partial results of all ranks
             loss, grad = reduce_fn(loss, grad)
         ctx.save_for_backward(grad)
@@ -162,7 +190,7 @@ class SigmoidCostStreamed(torch.autograd.Function):
     def backward(ctx, grad_output):
         (grad,) = ctx.saved_tensors
         g = None if grad is None else (grad * grad_output).to(ctx.low_dtype)
-        return None, g, None, None, None, None
+        return None, g, None, None, None, None, None
 
 
 class SigmoidCost(torch.autograd.Function):

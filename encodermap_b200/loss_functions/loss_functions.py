@@ -107,10 +107,9 @@ def sigmoid_loss(
             # streaming would expose a full 1/1 copy on that rank; instead every rank copies 1/G of the rows over its own
             # host link and the slices are all-gathered over NVLink (parallel.replicate_from_host).
             if process_group is not None and torch.distributed.get_world_size(process_group) > 2:
-                from ..parallel import replicate_from_host
-
-                y_dev = replicate_from_host(y_true, y_pred.device, process_group)
-                cost = _ops.SigmoidCost.apply(y_dev, y_pred, periodicity, sig, tile_range, reduce_fn)
+                # interleaved split: every rank takes 1/G of the tiles of every row chunk, copies 1/G of every chunk over its
+                # own host link and the chunk is completed by an all-gather over NVLink behind the tiles of the previous one
+                cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig, None, reduce_fn, process_group)
             else:
                 cost = _ops.SigmoidCostStreamed.apply(y_true, y_pred, periodicity, sig, tile_range, reduce_fn)
         else:

@@ -251,6 +251,81 @@ def test_streamed_cost_control_flow(L, monkeypatch):
     assert calls[0][2] & L.EMK_COST_ZERO_OUTPUTS and not any(c[2] & L.EMK_COST_ZERO_OUTPUTS for c in calls[1:])
 
 
+def test_streamed_cost_interleaved_split(L, monkeypatch):
+    """More than two ranks with the input in pinned host memory: every rank takes 1/G of the tiles of EVERY row chunk (walked from
+    the last chunk to the first), copies 1/G of the chunk's rows and completes the chunk by an all-gather.  Host logic only
+    (CUDA and torch.distributed stubbed): the ranks' launches tile every chunk's range without gaps or overlap."""
+    import torch.distributed as dist
+
+    from encodermap_b200 import _ops
+
+    class FakeStream:
+        def wait_stream(self, s): pass
+        def wait_event(self, e): pass
+
+    class FakeEvent:
+        def record(self, s): pass
+
+    class Ctx:
+        def __init__(self, *a): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    real = L.lib()
+    calls, gathers = [], []
+
+    class FakeLib:
+        def __getattr__(self, k):
+            return getattr(real, k)
+
+        def emk_dl_sigmoid_cost(self, high, low, per, sig, t0, t1, loss, grad, flags, st):
+            calls.append((t0, t1, flags))
+            return 0
+
+    state = {"rank": 0}
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda d=None: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", Ctx)
+    monkeypatch.setattr(torch.cuda, "device", Ctx)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    monkeypatch.setattr(_ops, "require_cuda", lambda t, n: t)
+    monkeypatch.setattr(_ops, "stream_of", lambda t: None)
+    monkeypatch.setattr(_ops, "DL", lambda t: t)
+    monkeypatch.setattr(L, "lib", lambda: FakeLib())
+    monkeypatch.setattr(_ops, "_SIDE_STREAMS", {})
+    monkeypatch.setattr(dist, "get_world_size", lambda g=None: 4)
+    monkeypatch.setattr(dist, "get_rank", lambda g=None: state["rank"])
+    monkeypatch.setattr(dist, "all_gather_into_tensor", lambda out, inp, group=None: gathers.append((tuple(out.shape), tuple(inp.shape))))
+    n, rows = 8192, 2048
+    total = int(real.emk_pair_tile_count(n))
+    per_rank = []
+    for rank in range(4):
+        state["rank"] = rank
+        calls.clear()
+        gathers.clear()
+        _ops.sigmoid_cost_streamed(torch.zeros(n, 8), torch.zeros(n, 2), 6.28, (4.5, 12, 6, 1, 2, 6), True, rows, interleave_group="g")
+        assert gathers == [((rows, 8), (rows // 4, 8))] * (n // rows)         # one all-gather per chunk, equal slices
+        assert calls[0][2] & L.EMK_COST_ZERO_OUTPUTS and not any(c[2] & L.EMK_COST_ZERO_OUTPUTS for c in calls[1:])
+        per_rank.append([(a, b) for a, b, _ in calls])
+    assert all(len(c) == n // rows for c in per_rank)
+    covered = 0
+    for k in range(n // rows):                       # chunk k (from the last one backwards): ranks 0..3 chain
+        parts = [per_rank[r][k] for r in range(4)]
+        assert all(parts[r][1] == parts[r + 1][0] for r in range(3))
+        covered += parts[3][1] - parts[0][0]
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
+    assert covered == total and per_rank[3][0][1] == total and per_rank[0][-1][0] == 0
+    # ragged shapes fall back to contiguous tile ranges (every rank streams the rows its own range touches)
+    state["rank"] = 1
+    calls.clear()
+    gathers.clear()
+    _ops.sigmoid_cost_streamed(torch.zeros(5000, 8), torch.zeros(5000, 2), 6.28, (4.5, 12, 6, 1, 2, 6), True, 1024, interleave_group="g")
+    b, e = L.pair_tile_range(5000, 1, 4)
+    assert not gathers and min(a for a, _, _ in calls) == b and max(t for _, t, _ in calls) == e
+
+
 def test_merged_atom_count_follows_the_reference_loop(L):
     """emk_merged_atom_count (host only): atom 0, then every atom i >= 1 followed by a hydrogen if i is in h_after, else by an
     oxygen if i is in o_after -- the loop of reference misc/backmapping.py:1970-1990 -- incl. its quirks: atom 0 never gets a
