@@ -45,21 +45,23 @@ __device__ __forceinline__ void sp2_atom(const float* __restrict__ xf, int n, in
   const float px = xf[3 * ip] - cx, py = xf[3 * ip + 1] - cy, pz = xf[3 * ip + 2] - cz;
   const float nx = xf[3 * in] - cx, ny = xf[3 * in + 1] - cy, nz = xf[3 * in + 2] - cz;
   float ux = py * nz - pz * ny, uy = pz * nx - px * nz, uz = px * ny - py * nx;
-  const float inv = 1.f / sqrtf(ux * ux + uy * uy + uz * uz);
+  const float inv = rsqrt_fast(ux * ux + uy * uy + uz * uz);      // one MUFU (2 ulp): IEEE sqrt + divide are ~30 instructions
   ux *= inv; uy *= inv; uz *= inv;
   const float wx = py * uz - pz * uy, wy = pz * ux - px * uz, wz = px * uy - py * ux;   // prev x u
   const float pu = (1.f - q.c) * (px * ux + py * uy + pz * uz);
   float bx = q.c * px + q.s * wx + pu * ux, by = q.c * py + q.s * wy + pu * uy, bz = q.c * pz + q.s * wz + pu * uz;
-  const float sc = q.len / sqrtf(bx * bx + by * by + bz * bz);
+  const float sc = q.len * rsqrt_fast(bx * bx + by * by + bz * bz);
   o[0] = cx + bx * sc; o[1] = cy + by * sc; o[2] = cz + bz * sc;
 }
 
+// grid: x over chunks of 256 output atoms, y over frames (grid-stride): no index division; the plan entry of a thread is the
+// same for every frame it visits
 __global__ void __launch_bounds__(256) generate_atoms_kernel(const GenParams p) {
-  const int64_t total = p.b * p.n_out;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t f = idx / p.n_out;
-    const int k = (int)(idx - f * p.n_out);
-    const uint32_t e = __ldg(p.plan + k);
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= p.n_out) return;
+  const uint32_t e = __ldg(p.plan + k);
+  for (int64_t f = blockIdx.y; f < p.b; f += gridDim.y) {
+    const int64_t idx = f * p.n_out + k;
     const uint32_t kind = e >> PLAN_SHIFT;
     const int i = (int)(e & PLAN_MASK);
     float o[3];
@@ -87,9 +89,9 @@ static int run_plan(GenParams p, const std::vector<uint32_t>& plan, cudaStream_t
     return fail((int)e, "generation plan upload failed: %s", cudaGetErrorString(e));
   }
   p.plan = dplan;
-  const int64_t total = p.b * p.n_out;
-  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-  generate_atoms_kernel<<<grid, 256, 0, st>>>(p);
+  const unsigned gx = (unsigned)((p.n_out + 255) / 256);
+  const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(p.b, std::min<int64_t>(65535, (int64_t)sm_count() * 16 / gx)));
+  generate_atoms_kernel<<<dim3(gx, gy), 256, 0, st>>>(p);
   rc = launch_status("generate_atoms_kernel");
   cudaFreeAsync(dplan, st);
   return rc;
