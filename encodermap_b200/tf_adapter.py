@@ -220,6 +220,78 @@ def sigmoid_loss(parameters=None, periodicity_overwrite=None, dist_dig_parameter
     return sigmoid_loss_func
 
 
+def cartesian_distance_loss_from_coordinates(model, parameters=None, callback=None):
+    """``cartesian_distance_loss`` (loss_functions.py:873-944) fed with the input COORDINATES instead of the stored pair matrix
+    (the composition models/models.py:837-839 + :2419-2422): ``f(inp_cartesians, latent)``.  The (batch, n_pairs) matrix is
+    library scratch.  Not installed by ``install()`` -- the reference's model builders pass ``inp_pair``; a caller opts in."""
+    _require_tf()
+    p = parameters
+    sig = tuple(getattr(p, "cartesian_dist_sig_parameters", (4.5, 12, 6, 1, 2, 6)))
+    sel = (getattr(p, "cartesian_pwd_start", None), getattr(p, "cartesian_pwd_stop", None), getattr(p, "cartesian_pwd_step", None))
+
+    @tf.custom_gradient
+    def _cost(cartesians, y_pred):
+        def run(x, z):
+            loss, grad = _ops.cartesian_distance_cost_raw(x, z, sig, *sel)
+            return loss.to(torch.float32), grad
+
+        loss, grad = _eager(run, [cartesians, y_pred], 2)
+        loss = tf.reshape(loss, [])
+        grad = tf.reshape(grad, tf.shape(y_pred))
+
+        def backward(upstream):
+            return tf.zeros_like(cartesians), upstream * grad      # the coordinates are input data
+
+        return loss, backward
+
+    def cartesian_distance_loss_func(cartesians, y_pred):
+        scale = getattr(p, "cartesian_distance_cost_scale", 1)
+        cost = _cost(_f32(cartesians), _f32(y_pred)) * scale if scale is not None else tf.constant(0.0)
+        tf.debugging.assert_all_finite(cost, message="Cartesian distance cost became infinite or NaN.")
+        return cost
+
+    return cartesian_distance_loss_func
+
+
+def fused_cartesian_loss(model=None, scale_callback=None, parameters=None, log_callback=None):
+    """``PairwiseDistances("output")`` + ``cartesian_loss`` (models/layers.py:1252-1267 + loss_functions.py:947-1067, called as
+    ``cartesian_loss_func(inp_pair, out_pair)`` in models/models.py:2385-2387) as ONE op on the back-mapped coordinates:
+    ``f(inp_cartesians | inp_pair, out_cartesians)``; d(cost)/d(out_cartesians) comes out of the same launch.  Opt-in like
+    ``cartesian_distance_loss_from_coordinates``."""
+    _require_tf()
+    p = parameters
+    sel = (getattr(p, "cartesian_pwd_start", None), getattr(p, "cartesian_pwd_stop", None), getattr(p, "cartesian_pwd_step", None))
+    variant = getattr(p, "cartesian_cost_variant", "mean_abs")
+
+    @tf.custom_gradient
+    def _cost(target, out_cartesians):
+        n_atoms = int(out_cartesians.shape[1])
+        n_sel = len(range(*slice(*sel).indices(n_atoms)))
+        frames = tf.cast(tf.shape(out_cartesians)[0], tf.float32)
+        count = frames * (1.0 if variant == "mean_norm" else float(max(1, n_sel * (n_sel - 1) // 2)))
+
+        def run(t, x):
+            loss, grad, _ = _ops.cartesian_pair_loss_raw(x, t, *sel, variant, 0.0, True)
+            return loss.to(torch.float32), grad
+
+        loss, grad = _eager(run, [target, out_cartesians], 2)
+        loss = tf.reshape(loss, []) / count
+        grad = tf.reshape(grad, tf.shape(out_cartesians)) / count
+
+        def backward(upstream):
+            return tf.zeros_like(target), upstream * grad
+
+        return loss, backward
+
+    def cartesian_loss_func(y_true, out_cartesians):
+        scale = scale_callback.current_cartesian_cost_scale if scale_callback is not None else getattr(p, "cartesian_cost_scale", 1)
+        cost = _cost(_f32(y_true), _f32(out_cartesians)) / getattr(p, "cartesian_cost_reference", 1) * scale
+        tf.debugging.assert_all_finite(cost, message="Cartesian cost became infinite or NaN.")
+        return cost
+
+    return cartesian_loss_func
+
+
 # ---- encodermap/models/layers.py ---------------------------------------------------------------------------------------------
 def periodic_input(inputs, periodicity):
     """``PeriodicInput.call`` (models/layers.py:204-215): (rows, d) -> (rows, 2d) = [sin x, cos x]."""

@@ -244,6 +244,27 @@ def test_tf_adapter_adc_branch_on_gpu(tf_gpu):
     np.testing.assert_allclose(loss.item(), l64.item(), rtol=1e-5)
     assert _relnorm(ga.cpu().numpy(), wa64.grad.numpy()) < 5e-5
     assert _relnorm(gd.cpu().numpy(), wd64.grad.numpy()) < 5e-5
+    # the same branch with PairwiseDistances + loss fused into one op (opt-in): same value, same gradients
+    p.cartesian_cost_variant, p.cartesian_cost_scale, p.cartesian_cost_reference = "mean_abs", 1, 1
+    fused = adapter.fused_cartesian_loss(None, None, p)
+    with tf.GradientTape() as tape:
+        feat = layers.PeriodicInput(p, "dihedrals")(tf.convert_to_tensor(dih))
+        xyz = layers.BackMapLayer(n // 2 - 1, (n - 3) // 2)((tf.convert_to_tensor(dist), tf.convert_to_tensor(ang) + feat @ wa, feat @ wd))
+        loss_f = fused(tf.convert_to_tensor(target), xyz)
+    ga_f, gd_f = tape.gradient(loss_f, [wa, wd])
+    np.testing.assert_allclose(loss_f.item(), l64.item(), rtol=1e-5)
+    assert _relnorm(ga_f.cpu().numpy(), wa64.grad.numpy()) < 5e-5 and _relnorm(gd_f.cpu().numpy(), wd64.grad.numpy()) < 5e-5
+    # cartesian_distance_loss fed with coordinates (8f-2) against the reference composition pair matrix -> loss
+    z0 = rng.normal(size=(b, 2)).astype(np.float32)
+    z = tf.Variable(z0)
+    p.cartesian_dist_sig_parameters, p.cartesian_distance_cost_scale = (0.6, 6, 3, 1, 2, 6), 2.0
+    with tf.GradientTape() as tape:
+        lc = adapter.cartesian_distance_loss_from_coordinates(None, p)(xyz.detach(), z)
+    gz = tape.gradient(lc, z)
+    pairs64 = O.pairwise_distances_layer(xyz.detach().cpu().double(), 1, None, 3)
+    lref, gref = O.sigmoid_loss_and_grad(pairs64.numpy(), z0, float("inf"), p.cartesian_dist_sig_parameters)
+    np.testing.assert_allclose(lc.item(), 2.0 * lref.item(), rtol=1e-5)
+    assert _relnorm(gz.cpu().numpy(), 2.0 * gref.numpy()) < 5e-5
 
 
 @pytest.mark.gpu
