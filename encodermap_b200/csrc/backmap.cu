@@ -1683,7 +1683,7 @@ __global__ void __launch_bounds__(128) d2c_chain_bwd_kernel(const float* __restr
 
 int d2c_chain_bwd_device(const float* chain, int64_t cstride, const float* xyz, const float* grad_xyz, int64_t b, int64_t n, int one_way,
                          float* grad_chain, cudaStream_t st) {
-  EMK_REQUIRE(chain && xyz && grad_xyz && grad_chain, EMK_E_NULL, "emk_dihedrals_to_cartesian_chain_bwd: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (chain && xyz && grad_xyz && grad_chain), EMK_E_NULL, "emk_dihedrals_to_cartesian_chain_bwd: NULL pointer argument");
   EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_dihedrals_to_cartesian_chain_bwd: need 4 <= n_atoms < 2^20");
   EMK_REQUIRE(b >= 0 && (cstride == 0 || cstride == 3 * n), EMK_E_ARG, "emk_dihedrals_to_cartesian_chain_bwd: chain_batch_stride must be 0 or 3*n_atoms");
   if (b == 0) return EMK_OK;
@@ -1805,7 +1805,7 @@ static int backmap_fwd6_launch(const float* lengths, const float* angles, const 
 
 int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angles, const float* dihedrals, int64_t b,
                        int64_t n, float* xyz, cudaStream_t st) {
-  EMK_REQUIRE(lengths && angles && dihedrals && xyz, EMK_E_NULL, "emk_backmap: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (lengths && angles && dihedrals && xyz), EMK_E_NULL, "emk_backmap: NULL pointer argument");
   EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_backmap: need 4 <= n_atoms < 2^20, got %lld", (long long)n);
   EMK_REQUIRE(b >= 0 && (lstride == 0 || lstride == n - 1), EMK_E_ARG, "emk_backmap: lengths_batch_stride must be 0 or n_atoms-1");
   if (b == 0) return EMK_OK;
@@ -1845,7 +1845,7 @@ int backmap_fwd_device(const float* lengths, int64_t lstride, const float* angle
 }
 
 int chain_in_plane_device(const float* lengths, int64_t lstride, const float* angles, int64_t b, int64_t n, float* xyz, cudaStream_t st) {
-  EMK_REQUIRE(lengths && angles && xyz, EMK_E_NULL, "emk_chain_in_plane: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (lengths && angles && xyz), EMK_E_NULL, "emk_chain_in_plane: NULL pointer argument");
   EMK_REQUIRE(n >= 3 && n < (1 << 20), EMK_E_SHAPE, "emk_chain_in_plane: need 3 <= n_atoms < 2^20, got %lld", (long long)n);
   EMK_REQUIRE(b >= 0 && (lstride == 0 || lstride == n - 1), EMK_E_ARG, "emk_chain_in_plane: lengths_batch_stride must be 0 or n_atoms-1");
   if (b == 0) return EMK_OK;
@@ -1865,7 +1865,7 @@ int chain_in_plane_device(const float* lengths, int64_t lstride, const float* an
 
 int d2c_general_device(const float* dihedrals, const float* chain, int64_t cstride, int64_t b, int64_t n, int one_way,
                        float* xyz, cudaStream_t st) {
-  EMK_REQUIRE(dihedrals && chain && xyz, EMK_E_NULL, "emk_dihedrals_to_cartesian: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (dihedrals && chain && xyz), EMK_E_NULL, "emk_dihedrals_to_cartesian: NULL pointer argument");
   EMK_REQUIRE(n >= 4 && n < (1 << 20), EMK_E_SHAPE, "emk_dihedrals_to_cartesian: need 4 <= n_atoms < 2^20, got %lld", (long long)n);
   EMK_REQUIRE(b >= 0 && (cstride == 0 || cstride == 3 * n), EMK_E_ARG, "emk_dihedrals_to_cartesian: chain_batch_stride must be 0 or 3*n_atoms");
   if (b == 0) return EMK_OK;

@@ -109,14 +109,16 @@ __global__ void __launch_bounds__(CL_THREADS) cart_pair_loss_kernel(const CartLo
             const float dx = xo0 - co[c][0], dy = xo1 - co[c][1], dz = xo2 - co[c][2];
             const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
             const float rinv = s2 >= EMK_TINY ? rsqrt_fast(s2) : 0.f;
-            const float dout = s2 * rinv;                       // pairwise_dist: 0 at zero distance (distances.py:244-253)
+            // __fmul_rn: a product the compiler may not contract into `fma(s2, rinv, -din)` below -- identical structures must
+            // give a difference of exactly 0 as they do in the reference, not the rounding error of one of the two products
+            const float dout = __fmul_rn(s2, rinv);             // pairwise_dist: 0 at zero distance (distances.py:244-253)
             float din;
             if (!TXYZ) {
               din = __ldg(trow + j);
             } else {
               const float ex = xi0 - ci[c][0], ey = xi1 - ci[c][1], ez = xi2 - ci[c][2];
               const float t2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-              din = t2 >= EMK_TINY ? t2 * rsqrt_fast(t2) : 0.f;
+              din = t2 >= EMK_TINY ? __fmul_rn(t2, rsqrt_fast(t2)) : 0.f;
             }
             const float diff = dout - din;                      // the reference forms y_true - y_pred = -(diff): same |.| and square
             if (loss_sweep) {
@@ -247,7 +249,7 @@ static int launch_cart(const CartLossParams& p, cudaStream_t st) {
 }
 
 int cart_pair_loss_device(const CartLossParams& p, cudaStream_t st) {
-  EMK_REQUIRE(p.xyz && p.target && p.loss_sum, EMK_E_NULL, "emk_cartesian_pair_loss: NULL pointer argument");
+  EMK_REQUIRE(p.loss_sum && (p.b == 0 || (p.xyz && p.target)), EMK_E_NULL, "emk_cartesian_pair_loss: NULL pointer argument");
   EMK_REQUIRE(p.b >= 0 && p.n_atoms >= 1 && p.ns >= 0 && p.step >= 1 && p.first >= 0 &&
                   (p.ns == 0 || p.first + (int64_t)(p.ns - 1) * p.step < p.n_atoms),
               EMK_E_SHAPE, "emk_cartesian_pair_loss: atom selection (first %d, count %d, step %d) outside %d atoms", p.first, p.ns, p.step,

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) pairwise_periodic_bwd_kernel(const float*
 }
 int pairwise_periodic_bwd_device(const float* x, int64_t n, int64_t d, double P, const float* dist, const float* go, float* gx,
                                  cudaStream_t st) {
-  EMK_REQUIRE(x && dist && go && gx, EMK_E_NULL, "emk_pairwise_dist_periodic_bwd: NULL pointer argument");
+  EMK_REQUIRE(n == 0 || (x && dist && go && gx), EMK_E_NULL, "emk_pairwise_dist_periodic_bwd: NULL pointer argument");
   EMK_REQUIRE(n >= 0 && d >= 0 && P > 0, EMK_E_ARG, "emk_pairwise_dist_periodic_bwd: bad arguments");
   if (n * d == 0) return EMK_OK;
   EMK_REQUIRE((n + PDB_ROWS - 1) / PDB_ROWS <= 65535, EMK_E_UNSUPPORTED, "emk_pairwise_dist_periodic_bwd: more than %d rows", 65535 * PDB_ROWS);
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(PWB2_THREADS) pairwise_flat3_bwd2_kernel(const
 
 // ---- host launchers -------------------------------------------------------------------------------------------
 int periodic_distance_device(const float* a, const float* b, int64_t count, double P, float* out, cudaStream_t st) {
-  EMK_REQUIRE(a && b && out, EMK_E_NULL, "emk_periodic_distance: NULL pointer argument");
+  EMK_REQUIRE(count == 0 || (a && b && out), EMK_E_NULL, "emk_periodic_distance: NULL pointer argument");
   EMK_REQUIRE(count >= 0, EMK_E_SHAPE, "emk_periodic_distance: negative count");
   if (count == 0) return EMK_OK;
   periodic_distance_kernel<<<grid_for(count), 256, 0, st>>>(a, b, count, std::isinf(P) ? INFINITY : (float)P, out);
@@ -806,20 +806,20 @@ int periodic_distance_device(const float* a, const float* b, int64_t count, doub
 }
 int periodic_distance_bwd_device(const float* a, const float* b, int64_t count, double P, const float* go, float* ga, float* gb,
                                  cudaStream_t st) {
-  EMK_REQUIRE(a && b && go && (ga || gb), EMK_E_NULL, "emk_periodic_distance_bwd: NULL pointer argument");
+  EMK_REQUIRE(count == 0 || (a && b && go && (ga || gb)), EMK_E_NULL, "emk_periodic_distance_bwd: NULL pointer argument");
   if (count == 0) return EMK_OK;
   periodic_distance_bwd_kernel<<<grid_for(count), 256, 0, st>>>(a, b, count, std::isinf(P) ? INFINITY : (float)P, go, ga, gb);
   return launch_status("periodic_distance_bwd_kernel");
 }
 int sigmoid_device(const float* r, int64_t count, float sig, float a, float b, float* out, cudaStream_t st) {
-  EMK_REQUIRE(r && out, EMK_E_NULL, "emk_sigmoid: NULL pointer argument");
+  EMK_REQUIRE(count == 0 || (r && out), EMK_E_NULL, "emk_sigmoid: NULL pointer argument");
   EMK_REQUIRE(sig > 0 && a > 0 && b > 0, EMK_E_ARG, "emk_sigmoid: parameters must be > 0");
   if (count == 0) return EMK_OK;
   sigmoid_kernel<<<grid_for(count), 256, 0, st>>>(r, count, make_sig_spec(sig, a, b), out);
   return launch_status("sigmoid_kernel");
 }
 int sigmoid_bwd_device(const float* r, int64_t count, float sig, float a, float b, const float* go, float* gr, cudaStream_t st) {
-  EMK_REQUIRE(r && go && gr, EMK_E_NULL, "emk_sigmoid_bwd: NULL pointer argument");
+  EMK_REQUIRE(count == 0 || (r && go && gr), EMK_E_NULL, "emk_sigmoid_bwd: NULL pointer argument");
   EMK_REQUIRE(sig > 0 && a > 0 && b > 0, EMK_E_ARG, "emk_sigmoid_bwd: parameters must be > 0");
   if (count == 0) return EMK_OK;
   sigmoid_bwd_kernel<<<grid_for(count), 256, 0, st>>>(r, count, make_sig_spec(sig, a, b), go, gr);
@@ -831,7 +831,7 @@ static inline void periodic_scale(double P, float* scale, int* rescale) {
   *scale = (float)(2.0 * M_PI / P);
 }
 int periodic_input_device(const float* x, int64_t rows, int64_t d, double P, float* out, cudaStream_t st) {
-  EMK_REQUIRE(x && out, EMK_E_NULL, "emk_periodic_input: NULL pointer argument");
+  EMK_REQUIRE(rows * d == 0 || (x && out), EMK_E_NULL, "emk_periodic_input: NULL pointer argument");
   EMK_REQUIRE(rows >= 0 && d >= 0 && P > 0, EMK_E_ARG, "emk_periodic_input: bad arguments");
   if (rows * d == 0) return EMK_OK;
   float sc; int rs;
@@ -845,7 +845,7 @@ int periodic_input_device(const float* x, int64_t rows, int64_t d, double P, flo
   return launch_status("periodic_input_kernel");
 }
 int periodic_input_bwd_device(const float* x, int64_t rows, int64_t d, double P, const float* go, float* gx, cudaStream_t st) {
-  EMK_REQUIRE(x && go && gx, EMK_E_NULL, "emk_periodic_input_bwd: NULL pointer argument");
+  EMK_REQUIRE(rows * d == 0 || (x && go && gx), EMK_E_NULL, "emk_periodic_input_bwd: NULL pointer argument");
   EMK_REQUIRE(rows >= 0 && d >= 0 && P > 0, EMK_E_ARG, "emk_periodic_input_bwd: bad arguments");
   if (rows * d == 0) return EMK_OK;
   float sc; int rs;
@@ -859,7 +859,7 @@ int periodic_input_bwd_device(const float* x, int64_t rows, int64_t d, double P,
   return launch_status("periodic_input_bwd_kernel");
 }
 int rotation_matrix_device(const float* axis, const float* angle, int64_t b, float* out, cudaStream_t st) {
-  EMK_REQUIRE(axis && angle && out, EMK_E_NULL, "emk_rotation_matrix: NULL pointer argument");
+  EMK_REQUIRE(b <= 0 || (axis && angle && out), EMK_E_NULL, "emk_rotation_matrix: NULL pointer argument");
   if (b <= 0) return b == 0 ? EMK_OK : fail(EMK_E_SHAPE, "emk_rotation_matrix: negative batch");
   rotation_matrix_kernel<<<grid_for(b), 256, 0, st>>>(axis, angle, b, out);
   return launch_status("rotation_matrix_kernel");

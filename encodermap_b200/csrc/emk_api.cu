@@ -421,7 +421,7 @@ int emk_sigmoid_cost_host(const float* high_host, int64_t n, int64_t d, const fl
 int emk_cartesian_distance_cost(const float* xyz, int64_t b, int64_t n_atoms, int64_t first, int64_t count, int64_t step, const float* low,
                                 int64_t l, const float sig[6], int64_t tile_begin, int64_t tile_end, double* loss, float* grad_low,
                                 uint32_t flags, void* stream) {
-  EMK_REQUIRE(xyz && low && sig && loss, EMK_E_NULL, "emk_cartesian_distance_cost: NULL pointer argument");
+  EMK_REQUIRE(sig && loss && (b == 0 || (xyz && low)), EMK_E_NULL, "emk_cartesian_distance_cost: NULL pointer argument");
   EMK_REQUIRE(b >= 0 && n_atoms >= 1 && count >= 2 && step >= 1 && first >= 0 && first + (count - 1) * step < n_atoms, EMK_E_SHAPE,
               "emk_cartesian_distance_cost: atom selection (first %lld, count %lld, step %lld) needs >= 2 of %lld atoms", (long long)first,
               (long long)count, (long long)step, (long long)n_atoms);
@@ -495,7 +495,7 @@ int emk_dl_pairwise_dist_periodic_bwd(const DLManagedTensor* x, double periodici
 
 int emk_pairwise_dist(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride, int squared,
                       int flat, float* out, void* stream) {
-  EMK_REQUIRE(x && out, EMK_E_NULL, "emk_pairwise_dist: NULL pointer argument");
+  EMK_REQUIRE((x && out) || b == 0 || n < 2, EMK_E_NULL, "emk_pairwise_dist: NULL pointer argument");
   EMK_REQUIRE(b >= 0 && n >= 0 && d >= 1, EMK_E_SHAPE, "emk_pairwise_dist: bad shape b=%lld n=%lld d=%lld", (long long)b, (long long)n, (long long)d);
   // one big contiguous rank-2 problem with a wide feature axis goes through the TMA pair-tile kernel
   if (b == 1 && !flat && row_stride == d && d >= 16 && n >= 256)
@@ -504,7 +504,7 @@ int emk_pairwise_dist(const float* x, int64_t b, int64_t n, int64_t d, int64_t b
 }
 int emk_pairwise_dist_bwd(const float* x, int64_t b, int64_t n, int64_t d, int64_t batch_stride, int64_t row_stride, int squared,
                           int flat, const float* grad_out, float* grad_x, void* stream) {
-  EMK_REQUIRE(x && grad_out && grad_x, EMK_E_NULL, "emk_pairwise_dist_bwd: NULL pointer argument");
+  EMK_REQUIRE((x && grad_out && grad_x) || b == 0 || n == 0 || (x && grad_x && n < 2), EMK_E_NULL, "emk_pairwise_dist_bwd: NULL pointer argument");
   EMK_REQUIRE(b >= 0 && n >= 0 && d >= 1, EMK_E_SHAPE, "emk_pairwise_dist_bwd: bad shape");
   return pairwise_small_bwd_device(x, b, n, d, batch_stride, row_stride, squared, flat, grad_out, grad_x, as_stream(stream));
 }
@@ -720,7 +720,7 @@ int emk_backmap(const float* lengths, int64_t lengths_batch_stride, const float*
 
 int emk_backmap_bwd(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* xyz, const float* grad_xyz,
                     int64_t b, int64_t n_atoms, float* grad_angles, float* grad_dihedrals, float* grad_lengths, void* stream) {
-  EMK_REQUIRE(lengths && angles && xyz && grad_xyz, EMK_E_NULL, "emk_backmap_bwd: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (lengths && angles && xyz && grad_xyz), EMK_E_NULL, "emk_backmap_bwd: NULL pointer argument");
   EMK_REQUIRE(n_atoms >= 4 && n_atoms < (1 << 20), EMK_E_SHAPE, "emk_backmap_bwd: need 4 <= n_atoms < 2^20");
   EMK_REQUIRE(lengths_batch_stride == 0 || lengths_batch_stride == n_atoms - 1, EMK_E_ARG, "emk_backmap_bwd: lengths_batch_stride must be 0 or n_atoms-1");
   BwdParams p{lengths, lengths_batch_stride, angles, xyz, grad_xyz, b, (int)n_atoms, (int)(n_atoms / 2), (int)(n_atoms / 2 - 1), 0,
@@ -809,7 +809,7 @@ int emk_chain_in_plane(const float* lengths, int64_t lengths_batch_stride, const
 }
 int emk_chain_in_plane_bwd(const float* lengths, int64_t lengths_batch_stride, const float* angles, const float* grad_xyz, int64_t b,
                            int64_t n_atoms, float* grad_angles, float* grad_lengths, void* stream) {
-  EMK_REQUIRE(lengths && angles && grad_xyz, EMK_E_NULL, "emk_chain_in_plane_bwd: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (lengths && angles && grad_xyz), EMK_E_NULL, "emk_chain_in_plane_bwd: NULL pointer argument");
   EMK_REQUIRE(n_atoms >= 3 && n_atoms < (1 << 20), EMK_E_SHAPE, "emk_chain_in_plane_bwd: need 3 <= n_atoms < 2^20");
   EMK_REQUIRE(lengths_batch_stride == 0 || lengths_batch_stride == n_atoms - 1, EMK_E_ARG, "emk_chain_in_plane_bwd: lengths_batch_stride must be 0 or n_atoms-1");
   BwdParams p{lengths, lengths_batch_stride, angles, nullptr, grad_xyz, b, (int)n_atoms, 0, 0, 1, grad_angles, nullptr, grad_lengths};
@@ -848,7 +848,7 @@ int emk_dihedrals_to_cartesian(const float* dihedrals, const float* chain, int64
 }
 int emk_dihedrals_to_cartesian_bwd(const float* xyz, const float* grad_xyz, int64_t b, int64_t n_atoms, int one_way,
                                    float* grad_dihedrals, void* stream) {
-  EMK_REQUIRE(xyz && grad_xyz && grad_dihedrals, EMK_E_NULL, "emk_dihedrals_to_cartesian_bwd: NULL pointer argument");
+  EMK_REQUIRE(b == 0 || (xyz && grad_xyz && grad_dihedrals), EMK_E_NULL, "emk_dihedrals_to_cartesian_bwd: NULL pointer argument");
   EMK_REQUIRE(n_atoms >= 4 && n_atoms < (1 << 20), EMK_E_SHAPE, "emk_dihedrals_to_cartesian_bwd: need 4 <= n_atoms < 2^20");
   BwdParams p{nullptr, 0, nullptr, xyz, grad_xyz, b, (int)n_atoms, 0, one_way ? 0 : (int)(n_atoms / 2 - 1), 0, nullptr, grad_dihedrals, nullptr};
   return backmap_bwd_device(p, as_stream(stream));

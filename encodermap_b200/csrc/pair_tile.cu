@@ -799,8 +799,8 @@ int64_t pair_tile_count(int64_t n) {
 int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* low, int64_t l, double periodicity,
                         const float sig[6], int64_t tile_begin, int64_t tile_end, double* loss, float* grad_low,
                         uint32_t flags, cudaStream_t st) {
-  EMK_REQUIRE(high && low && sig && loss, EMK_E_NULL, "emk_sigmoid_cost: NULL pointer argument");
-  EMK_REQUIRE((flags & EMK_COST_NO_GRAD) || grad_low, EMK_E_NULL, "emk_sigmoid_cost: grad_low is NULL without EMK_COST_NO_GRAD");
+  EMK_REQUIRE(sig && loss && (n == 0 || (high && low)), EMK_E_NULL, "emk_sigmoid_cost: NULL pointer argument");
+  EMK_REQUIRE((flags & EMK_COST_NO_GRAD) || grad_low || n == 0, EMK_E_NULL, "emk_sigmoid_cost: grad_low is NULL without EMK_COST_NO_GRAD");
   EMK_REQUIRE(n >= 0 && d >= 1, EMK_E_SHAPE, "emk_sigmoid_cost: bad shape n=%lld d=%lld", (long long)n, (long long)d);
   EMK_REQUIRE(l >= 1 && l < (1 << 20), EMK_E_SHAPE, "emk_sigmoid_cost: latent width %lld outside [1,2^20)", (long long)l);
   EMK_REQUIRE(n < (int64_t)1 << 30, EMK_E_UNSUPPORTED, "emk_sigmoid_cost: n=%lld too large", (long long)n);
@@ -863,7 +863,7 @@ int sigmoid_cost_device(const float* high, int64_t n, int64_t d, const float* lo
 // (n,n) distance matrix through the same main loop
 int dist_matrix_device(const float* x, int64_t n, int64_t d, double periodicity, bool periodic_form, int squared, float* out,
                        cudaStream_t st) {
-  EMK_REQUIRE(x && out, EMK_E_NULL, "distance matrix: NULL pointer argument");
+  EMK_REQUIRE(n == 0 || (x && out), EMK_E_NULL, "distance matrix: NULL pointer argument");
   EMK_REQUIRE(n >= 0 && d >= 1, EMK_E_SHAPE, "distance matrix: bad shape n=%lld d=%lld", (long long)n, (long long)d);
   EMK_REQUIRE(n < (int64_t)1 << 30, EMK_E_UNSUPPORTED, "distance matrix: n=%lld too large", (long long)n);
   if (n == 0) return EMK_OK;

@@ -1349,3 +1349,38 @@ def test_set_dihedrals_golden_and_oracle(em, golden):
     with pytest.raises(_lib.EmkError):
         set_dihedrals(torch.from_numpy(start), all_quads[:1], all_quads[:1, 1:3], fars[:1], cu(targets[:, :1]))
     assert set_dihedrals(cu(start), np.zeros((0, 4), int), np.zeros((0, 2), int), [], cu(np.zeros((2, 0)))).shape == (2, n_atoms, 3)
+
+
+def test_empty_and_single_frame_batches(em):
+    """Zero-size and one-frame batches go through every round-2 entry point without a launch error (the reference's ops accept
+    them: empty tensors in, empty tensors out)."""
+    from encodermap_b200 import ADCParameters, _ops
+    from encodermap_b200.loss_functions.loss_functions import cartesian_distance_loss_from_coordinates, fused_cartesian_loss
+    from encodermap_b200.misc import backmapping as B
+    from encodermap_b200.misc import distances as D
+
+    p = ADCParameters(cartesian_pwd_start=1, cartesian_pwd_stop=None, cartesian_pwd_step=3)
+    for b in (0, 1):
+        xyz = cu(np.random.default_rng(b).normal(size=(b, 30, 3)))
+        assert D.pairwise_dist(xyz, flat=True).shape == (b, 435)
+        xg = xyz.clone().requires_grad_(True)
+        D.pairwise_dist(xg, flat=True).sum().backward()
+        assert xg.grad.shape == xyz.shape
+        out = xyz.clone().requires_grad_(True)
+        loss = fused_cartesian_loss(None, None, p)(xyz, out)
+        if b:
+            loss.backward()
+            assert float(loss.detach()) == 0.0 and not out.grad.any()   # identical structures: exactly zero, as in the reference
+        z = cu(np.zeros((b, 2))).requires_grad_(True)
+        c = cartesian_distance_loss_from_coordinates(None, p)(xyz, z)
+        if b:
+            c.backward()
+            assert np.isfinite(float(c.detach()))
+        assert B.backbone_with_amide_atoms(xyz, np.arange(30)[::3], np.arange(30)[2::3]).shape == (b, 49, 3)
+        got = B.set_dihedrals(cu(np.random.default_rng(3).normal(size=(6, 3))), [[0, 1, 2, 3]], [[1, 2]], [np.array([2, 3, 4, 5])],
+                              cu(np.full((b, 1), 0.7)))
+        assert got.shape == (b, 6, 3)
+        if b:
+            assert abs(O.dihedral_np(got[0].cpu().double().numpy(), (0, 1, 2, 3)) - 0.7) < 1e-5
+        l_, g_ = _ops.sigmoid_cost_raw(cu(np.zeros((b, 3))), cu(np.zeros((b, 2))), float("inf"), DEFAULT_SIG)
+        assert g_.shape == (b, 2) and (b == 0 or float(l_) == 0.0)
