@@ -659,7 +659,8 @@ __global__ void pairwise_small_bwd_kernel(const float* __restrict__ x, int64_t b
 // is one contiguous run per chunk, addressed from ONE per-lane pointer with the chunk as an immediate offset.  No index
 // table, no per-element decode, no barrier: ~12 instructions per two chunk visits.
 constexpr int PWW_THREADS = 128;
-constexpr int PWW_MAX_N = 128;
+constexpr int PWW_MAX_N = 128;       // backward (gradient staged in shared memory)
+constexpr int PWW_FWD_MAX_N = 320;   // forward (C <= 10 column chunks in registers)
 
 __device__ __forceinline__ float sqrt_fast(float x) {   // one MUFU.SQRT (2 ulp), exact 0 at 0; no denormal fix-up
   float r;
@@ -670,7 +671,7 @@ __device__ __forceinline__ float sqrt_fast(float x) {   // one MUFU.SQRT (2 ulp)
 template <int C, bool SQUARED>
 __global__ void __launch_bounds__(PWW_THREADS) pairwise_flat3_warp_kernel(const float* __restrict__ x, int64_t b, int n, int64_t bstride,
                                                                           int64_t rstride, float* __restrict__ out, int64_t out_pitch) {
-  __shared__ float4 sx4[PWW_THREADS / 32][PWW_MAX_N];
+  __shared__ float4 sx4[PWW_THREADS / 32][C * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = n * (n - 1) / 2;
   float4* sx = sx4[warp];
@@ -886,7 +887,7 @@ int column_mean_device(const float* x, int64_t rows, int64_t cols, float* out, c
 // flat upper triangle of (b, n <= 128, 3) points, one warp per frame, `out_pitch` floats per output row (>= n (n-1) / 2)
 int pairwise_flat3_warp_device(const float* x, int64_t b, int64_t n, int64_t bstride, int64_t rstride, int squared, float* out,
                                int64_t out_pitch, cudaStream_t st) {
-  EMK_REQUIRE(n >= 2 && n <= PWW_MAX_N && out_pitch >= n * (n - 1) / 2, EMK_E_ARG, "pairwise (warp per frame): bad geometry");
+  EMK_REQUIRE(n >= 2 && n <= PWW_FWD_MAX_N && out_pitch >= n * (n - 1) / 2, EMK_E_ARG, "pairwise (warp per frame): bad geometry");
   if (b == 0) return EMK_OK;
   const unsigned grid = (unsigned)std::min<int64_t>((b + PWW_THREADS / 32 - 1) / (PWW_THREADS / 32), (int64_t)sm_count() * 16);
 #define EMK_PWW(CC)                                                                                                                 \
@@ -897,17 +898,20 @@ int pairwise_flat3_warp_device(const float* x, int64_t b, int64_t n, int64_t bst
   if (n <= 32) EMK_PWW(1);
   else if (n <= 64) EMK_PWW(2);
   else if (n <= 96) EMK_PWW(3);
-  else EMK_PWW(4);
+  else if (n <= 128) EMK_PWW(4);
+  else if (n <= 192) EMK_PWW(6);
+  else if (n <= 256) EMK_PWW(8);
+  else EMK_PWW(10);
 #undef EMK_PWW
   return launch_status("pairwise_flat3_warp_kernel");
 }
-int pairwise_warp_max_atoms() { return PWW_MAX_N; }
+int pairwise_warp_max_atoms() { return PWW_FWD_MAX_N; }
 
 int pairwise_small_device(const float* x, int64_t b, int64_t n, int64_t d, int64_t bstride, int64_t rstride, int squared,
                           int flat, float* out, cudaStream_t st) {
   const int64_t per = flat ? n * (n - 1) / 2 : n * n;
   if (b * per == 0) return EMK_OK;
-  if (flat && d == 3 && n >= 2 && n <= PWW_MAX_N) return pairwise_flat3_warp_device(x, b, n, bstride, rstride, squared, out, per, st);
+  if (flat && d == 3 && n >= 2 && n <= PWW_FWD_MAX_N) return pairwise_flat3_warp_device(x, b, n, bstride, rstride, squared, out, per, st);
   if (flat && d == 3 && n >= 2 && n <= 8192) {
     if (n <= PWT_MAX_N) {
       const int64_t per3 = n * (n - 1) / 2;

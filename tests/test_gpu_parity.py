@@ -1247,11 +1247,11 @@ def test_generation_generic_selection_and_errors(em, golden):
 # cartesian_distance_loss straight from the coordinates, reference models/models.py:837-839 + :2419-2422
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("b,n,sel", [(300, 30, (1, None, 3)), (1024, 300, (1, None, 3)), (130, 45, (None, None, None)),
-                                      (64, 402, (None, None, 3)), (200, 9, (2, 8, 2))])
+                                      (64, 402, (None, None, 3)), (40, 1000, (None, None, 3)), (200, 9, (2, 8, 2))])
 def test_cartesian_distance_loss_from_coordinates(em, b, n, sel):
     """Value and d/d(latent) against the float64 oracle of the reference composition, and against the two-step GPU path
     (PairwiseDistances + cartesian_distance_loss).  1024 x 300 with every third atom is BASELINE configs[2] (4 950 pair
-    dims: row pitch padded to 4 952); 402 atoms / step 3 = 134 atoms selects the unpitched fallback (> 128 atoms)."""
+    dims: row pitch padded to 4 952); 1000 atoms / step 3 = 334 atoms selects the unpitched fallback (> 320 atoms)."""
     from encodermap_b200 import ADCParameters, _ops
     from encodermap_b200.loss_functions import cartesian_distance_loss
     from encodermap_b200.loss_functions.loss_functions import cartesian_distance_loss_from_coordinates
