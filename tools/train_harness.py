@@ -207,6 +207,9 @@ def run_all(dev, steps=20):
         "train_cfg2_adc_100res_batch1024_fused_cartesian":
             (lambda: ADCStep(n, ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True), fused_cartesian=True),
              lambda it: (ang, dih, cart, dist)),
+        # the reference's default atom selection (cartesian_pwd_* = None: all 300 backbone atoms, 44 850 pair dims), fused branch
+        "train_cfg2_adc_100res_batch1024_all_atoms_fused_cartesian":
+            (lambda: ADCStep(n, ADCParameters(use_backbone_angles=True), fused_cartesian=True), lambda it: (ang, dih, cart, dist)),
     }
     for name, (make, batch_fn) in cases.items():
         res = {}
