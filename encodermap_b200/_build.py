@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 BUILD = PKG / "_build"
 LIB = PKG / "libemk.so"
-SOURCES = ["emk_api.cu", "pair_tile.cu", "backmap.cu", "elementwise.cu", "comm.cu", "cart_loss.cu", "generate.cu"]
+SOURCES = ["emk_api.cu", "pair_tile.cu", "backmap.cu", "elementwise.cu", "comm.cu", "cart_loss.cu", "generate.cu", "sidechain.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr",

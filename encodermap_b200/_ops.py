@@ -5,6 +5,7 @@ the hot path is produced by a kernel in libemk.so, reached through ctypes with D
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import threading
 from typing import Optional, Sequence, Tuple
@@ -406,6 +407,143 @@ def set_dihedrals_raw(start: torch.Tensor, quads, bonds, far_sides, targets: tor
     with torch.cuda.device(start.device):
         check(_lib.lib().emk_set_dihedrals(start.data_ptr(), start.shape[0], start.shape[1], p32(q), p32(bd), p32(off), p32(far), d,
                                            targets.data_ptr(), frames, out.data_ptr(), stream_of(start)))
+    return out
+
+
+class SidechainPlan:
+    """Host + device step table of BackMapLayerWithSidechains for one topology (``emk_sidechain_plan_create``).  ``counts[r]`` =
+    number of side-chain dihedrals of residue r + 1 (``feature_description[-1]``, reference models/layers.py:234-500).  The plan
+    is bound to the CUDA device that is current when it is built; without a device it can still be inspected."""
+
+    def __init__(self, counts, device: Optional[torch.device] = None):
+        import numpy as np
+        import weakref
+
+        self.counts = np.ascontiguousarray(np.asarray(counts, dtype=np.int32).reshape(-1))
+        handle = C.c_void_p()
+        L = _lib.lib()
+        if device is not None and torch.device(device).type == "cuda":
+            ctx = torch.cuda.device(device)
+        else:
+            import contextlib
+
+            ctx = contextlib.nullcontext()
+        with ctx:
+            rc = L.emk_sidechain_plan_create(len(self.counts), self.counts.ctypes.data_as(_lib.c_i32p), C.byref(handle))
+        if rc == -7:      # EMK_E_UNSUPPORTED: the descriptions the reference's constructor cannot build either
+            raise ValueError(L.emk_last_error().decode(errors="replace"))
+        check(rc)
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, L.emk_sidechain_plan_destroy, handle)
+        info = (C.c_int64 * 10)()
+        check(L.emk_sidechain_plan_info(handle, info))
+        self.n_atoms, self.n_side, self.n_ops, self.n_residues = (int(v) for v in info[:4])
+        self.columns = tuple(int(v) for v in info[4:10])
+        self.device = torch.device(device) if device is not None else None
+
+    def ops(self):
+        """(n_steps, 12) int32: kind, a, b, c, d, column, lo0, hi0, lo1, hi1, 0, 0 (see include/emk.h)."""
+        import numpy as np
+
+        out = np.zeros((self.n_ops, 12), dtype=np.int32)
+        check(_lib.lib().emk_sidechain_plan_ops(self.handle, out.ctypes.data_as(_lib.c_i32p)))
+        return out
+
+
+def _six_inputs(plan: SidechainPlan, inputs):
+    if len(inputs) != 6:
+        raise EmkError(-4, f"BackMapLayerWithSidechains takes six inputs, got {len(inputs)}")
+    ts = [f32c(require_cuda(t, name)) for t, name in zip(inputs, ("central_distances", "central_angles", "central_dihedrals",
+                                                                   "side_distances", "side_angles", "side_dihedrals"))]
+    frames = ts[0].shape[0]
+    for t, cols in zip(ts, plan.columns):
+        if t.dim() != 2 or t.shape[0] != frames or t.shape[1] != cols:
+            raise EmkError(-4, f"BackMapLayerWithSidechains: input shapes {[tuple(t.shape) for t in ts]} do not match the topology "
+                               f"(columns {plan.columns})")
+    return ts
+
+
+def _dl_array(dls):
+    arr = (C.c_void_p * len(dls))()
+    for k, d in enumerate(dls):
+        arr[k] = d.ptr
+    return arr
+
+
+def sidechain_backmap_raw(plan: SidechainPlan, inputs) -> torch.Tensor:
+    ts = _six_inputs(plan, inputs)
+    out = _empty_like_shape(ts[0], (ts[0].shape[0], plan.n_atoms, 3))
+    dls = [DL(t) for t in ts]
+    with torch.cuda.device(ts[0].device):
+        check(_lib.lib().emk_dl_sidechain_backmap(plan.handle, _dl_array(dls), DL(out), stream_of(ts[0])))
+    return out
+
+
+def sidechain_backmap_bwd_raw(plan: SidechainPlan, inputs, grad_xyz: torch.Tensor, needs=(True,) * 6):
+    ts = _six_inputs(plan, inputs)
+    g = f32c(grad_xyz)
+    grads = [torch.empty_like(t) if need else None for t, need in zip(ts, needs)]
+    dls, gdls = [DL(t) for t in ts], [DL(t) for t in grads]
+    with torch.cuda.device(ts[0].device):
+        check(_lib.lib().emk_dl_sidechain_backmap_bwd(plan.handle, _dl_array(dls), DL(g), _dl_array(gdls), stream_of(ts[0])))
+    return grads
+
+
+class SidechainBackmap(torch.autograd.Function):
+    """BackMapLayerWithSidechains.call with its exact VJP (reference models/layers.py:533-843)."""
+
+    @staticmethod
+    def forward(ctx, plan, *inputs):
+        ctx.plan = plan
+        ctx.save_for_backward(*inputs)
+        return sidechain_backmap_raw(plan, inputs)
+
+    @staticmethod
+    def backward(ctx, grad_xyz):
+        grads = sidechain_backmap_bwd_raw(ctx.plan, ctx.saved_tensors, grad_xyz, ctx.needs_input_grad[1:])
+        return (None, *grads)
+
+
+def gather_atoms_raw(xyz: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    require_cuda(xyz, "xyz")
+    xyz = f32c(xyz)
+    out = _empty_like_shape(xyz, (xyz.shape[0], index.shape[0], 3))
+    with torch.cuda.device(xyz.device):
+        check(_lib.lib().emk_dl_gather_atoms(DL(xyz), DL(index), DL(out), stream_of(xyz)))
+    return out
+
+
+class GatherAtoms(torch.autograd.Function):
+    """tf.gather(params=inputs, indices=..., axis=1) of PairwiseDistances (reference models/layers.py:1260-1265)."""
+
+    @staticmethod
+    def forward(ctx, xyz, index):
+        ctx.save_for_backward(index)
+        ctx.n_atoms = xyz.shape[1]
+        return gather_atoms_raw(xyz, index)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (index,) = ctx.saved_tensors
+        g = f32c(grad_out)
+        gx = _empty_like_shape(g, (g.shape[0], ctx.n_atoms, 3))
+        with torch.cuda.device(g.device):
+            check(_lib.lib().emk_dl_gather_atoms_bwd(DL(g), DL(index), DL(gx), stream_of(g)))
+        return gx, None
+
+
+def sidechain_pairwise_indices(counts, start=None, stop=None, step=None):
+    """Atom selection of PairwiseDistances with reconstruct_sidechains (reference models/layers.py:1188-1208), int64 numpy."""
+    import numpy as np
+
+    c = np.ascontiguousarray(np.asarray(counts, dtype=np.int32).reshape(-1))
+    args = [_lib.NONE_INDEX if v is None else int(v) for v in (start, stop, step)]
+    L = _lib.lib()
+    n = int(L.emk_sidechain_pairwise_indices(len(c), c.ctypes.data_as(_lib.c_i32p), *args, None))
+    if n < 0:
+        raise EmkError(-2, "sidechain_pairwise_indices: bad arguments")
+    out = np.zeros(n, dtype=np.int64)
+    L.emk_sidechain_pairwise_indices(len(c), c.ctypes.data_as(_lib.c_i32p), *args, out.ctypes.data_as(_lib.c_i64p))
     return out
 
 

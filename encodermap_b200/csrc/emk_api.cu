@@ -108,6 +108,18 @@ int64_t merged_atom_count(int64_t, const int64_t*, int64_t, const int64_t*, int6
 int set_dihedrals_device(const float*, int64_t, int64_t, const int32_t*, const int32_t*, const int32_t*, const int32_t*, int64_t, const float*,
                          int64_t, float*, cudaStream_t);
 int column_mean_device(const float*, int64_t, int64_t, float*, cudaStream_t);
+struct SidechainPlan;
+int sidechain_plan_create(int64_t, const int32_t*, SidechainPlan**);
+void sidechain_plan_destroy(SidechainPlan*);
+int sidechain_plan_info(const SidechainPlan*, int64_t*);
+int sidechain_plan_ops(const SidechainPlan*, int32_t*);
+const int* sidechain_plan_cols(const SidechainPlan*);
+int sidechain_plan_atoms(const SidechainPlan*);
+int sidechain_backmap_device(const SidechainPlan*, const float* const*, int64_t, float*, cudaStream_t);
+int sidechain_backmap_bwd_device(const SidechainPlan*, const float* const*, int64_t, const float*, float* const*, cudaStream_t);
+int64_t sidechain_pairwise_indices(int64_t, const int32_t*, int64_t, int64_t, int64_t, int64_t*);
+int gather_atoms_device(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, cudaStream_t);
+int gather_atoms_bwd_device(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, cudaStream_t);
 int pairwise_small_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float*, cudaStream_t);
 int pairwise_small_bwd_device(const float*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float*, float*, cudaStream_t);
 int backmap_fwd_device(const float*, int64_t, const float*, const float*, int64_t, int64_t, float*, cudaStream_t);
@@ -927,6 +939,120 @@ int emk_set_dihedrals(const float* start, int64_t start_frames, int64_t n_atoms,
                       float* out, void* stream) {
   return set_dihedrals_device(start, start_frames, n_atoms, quads, bonds, far_offsets, far_atoms, n_dihedrals, targets, frames, out,
                               as_stream(stream));
+}
+
+// ---- back-mapping with side chains ---------------------------------------------------------------------------------
+static inline const emk::SidechainPlan* as_plan(const emk_sidechain_plan* p) { return reinterpret_cast<const emk::SidechainPlan*>(p); }
+
+int emk_sidechain_plan_create(int64_t n_residues, const int32_t* n_side_dihedrals, emk_sidechain_plan** plan) {
+  emk::SidechainPlan* pl = nullptr;
+  int rc = sidechain_plan_create(n_residues, n_side_dihedrals, &pl);
+  if (plan) *plan = reinterpret_cast<emk_sidechain_plan*>(pl);
+  else if (pl) sidechain_plan_destroy(pl);
+  return rc;
+}
+void emk_sidechain_plan_destroy(emk_sidechain_plan* plan) { sidechain_plan_destroy(reinterpret_cast<emk::SidechainPlan*>(plan)); }
+int emk_sidechain_plan_info(const emk_sidechain_plan* plan, int64_t* info) { return sidechain_plan_info(as_plan(plan), info); }
+int emk_sidechain_plan_ops(const emk_sidechain_plan* plan, int32_t* ops) { return sidechain_plan_ops(as_plan(plan), ops); }
+
+int emk_sidechain_backmap(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
+                          const float* central_dihedrals, const float* side_distances, const float* side_angles,
+                          const float* side_dihedrals, int64_t frames, float* xyz, void* stream) {
+  const float* in[6] = {central_distances, central_angles, central_dihedrals, side_distances, side_angles, side_dihedrals};
+  return sidechain_backmap_device(as_plan(plan), in, frames, xyz, as_stream(stream));
+}
+int emk_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
+                              const float* central_dihedrals, const float* side_distances, const float* side_angles,
+                              const float* side_dihedrals, int64_t frames, const float* grad_xyz, float* grad_central_distances,
+                              float* grad_central_angles, float* grad_central_dihedrals, float* grad_side_distances,
+                              float* grad_side_angles, float* grad_side_dihedrals, void* stream) {
+  const float* in[6] = {central_distances, central_angles, central_dihedrals, side_distances, side_angles, side_dihedrals};
+  float* gin[6] = {grad_central_distances, grad_central_angles, grad_central_dihedrals, grad_side_distances, grad_side_angles, grad_side_dihedrals};
+  return sidechain_backmap_bwd_device(as_plan(plan), in, frames, grad_xyz, gin, as_stream(stream));
+}
+
+static int sidechain_views(const char* who, const emk_sidechain_plan* plan, const DLManagedTensor* const* t, bool optional, const float** ptr,
+                           int64_t* frames) {
+  EMK_REQUIRE(plan, EMK_E_NULL, "%s: NULL plan", who);
+  static const char* names[6] = {"central_distances", "central_angles", "central_dihedrals", "side_distances", "side_angles", "side_dihedrals"};
+  const int* cols = sidechain_plan_cols(as_plan(plan));
+  for (int k = 0; k < 6; k++) {
+    ptr[k] = nullptr;
+    if (optional && !t[k]) continue;
+    View v;
+    int rc = view_of(t[k], names[k], kDLFloat, 32, 2, 2, &v);
+    if (rc) return rc;
+    EMK_REQUIRE(v.shape[1] == cols[k], EMK_E_SHAPE, "%s: %s has %lld columns, the plan needs %d", who, names[k], (long long)v.shape[1], cols[k]);
+    if (*frames < 0) *frames = v.shape[0];
+    EMK_REQUIRE(v.shape[0] == *frames, EMK_E_SHAPE, "%s: %s has %lld frames, expected %lld", who, names[k], (long long)v.shape[0], (long long)*frames);
+    ptr[k] = F(v);
+  }
+  return EMK_OK;
+}
+
+int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, DLManagedTensor* xyz, void* stream) {
+  EMK_REQUIRE(inputs, EMK_E_NULL, "emk_dl_sidechain_backmap: NULL inputs");
+  const float* in[6];
+  int64_t frames = -1;
+  int rc = sidechain_views("emk_dl_sidechain_backmap", plan, inputs, false, in, &frames);
+  if (rc) return rc;
+  VIEW(ov, xyz, "xyz", 3, 3);
+  EMK_REQUIRE(ov.shape[0] == frames && ov.shape[1] == sidechain_plan_atoms(as_plan(plan)) && ov.shape[2] == 3, EMK_E_SHAPE,
+              "emk_dl_sidechain_backmap: xyz must be (%lld, %d, 3)", (long long)frames, sidechain_plan_atoms(as_plan(plan)));
+  return sidechain_backmap_device(as_plan(plan), in, frames, F(ov), as_stream(stream));
+}
+int emk_dl_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, const DLManagedTensor* grad_xyz,
+                                 DLManagedTensor* const* grad_inputs, void* stream) {
+  EMK_REQUIRE(inputs && grad_inputs, EMK_E_NULL, "emk_dl_sidechain_backmap_bwd: NULL inputs");
+  const float* in[6];
+  const float* gin_c[6];
+  int64_t frames = -1;
+  int rc = sidechain_views("emk_dl_sidechain_backmap_bwd", plan, inputs, false, in, &frames);
+  if (rc) return rc;
+  rc = sidechain_views("emk_dl_sidechain_backmap_bwd (gradients)", plan, grad_inputs, true, gin_c, &frames);
+  if (rc) return rc;
+  VIEW(gv, grad_xyz, "grad_xyz", 3, 3);
+  EMK_REQUIRE(gv.shape[0] == frames && gv.shape[1] == sidechain_plan_atoms(as_plan(plan)) && gv.shape[2] == 3, EMK_E_SHAPE,
+              "emk_dl_sidechain_backmap_bwd: grad_xyz must be (%lld, %d, 3)", (long long)frames, sidechain_plan_atoms(as_plan(plan)));
+  float* gin[6];
+  for (int k = 0; k < 6; k++) gin[k] = const_cast<float*>(gin_c[k]);
+  return sidechain_backmap_bwd_device(as_plan(plan), in, frames, F(gv), gin, as_stream(stream));
+}
+
+int64_t emk_sidechain_pairwise_indices(int64_t n_residues, const int32_t* n_side_dihedrals, int64_t start, int64_t stop, int64_t step,
+                                       int64_t* indices) {
+  if (n_residues < 1 || !n_side_dihedrals) return -1;
+  int64_t first, cnt, st;
+  if (resolve_slice(3 * n_residues, start, stop, step, &first, &cnt, &st)) return -1;
+  return sidechain_pairwise_indices(n_residues, n_side_dihedrals, first, cnt, st, indices);
+}
+
+int emk_gather_atoms(const float* xyz, int64_t b, int64_t n_atoms, const int32_t* index_dev, int64_t m, float* out, void* stream) {
+  return gather_atoms_device(xyz, b, n_atoms, index_dev, m, out, as_stream(stream));
+}
+int emk_gather_atoms_bwd(const float* grad_out, int64_t b, int64_t n_atoms, const int32_t* index_dev, int64_t m, float* grad_xyz, void* stream) {
+  return gather_atoms_bwd_device(grad_out, b, n_atoms, index_dev, m, grad_xyz, as_stream(stream));
+}
+static int index_view(const DLManagedTensor* t, View* v) { return view_of(t, "index", kDLInt, 32, 1, 1, v); }
+int emk_dl_gather_atoms(const DLManagedTensor* xyz, const DLManagedTensor* index, DLManagedTensor* out, void* stream) {
+  VIEW(xv, xyz, "xyz", 3, 3);
+  View iv;
+  int rc = index_view(index, &iv);
+  if (rc) return rc;
+  VIEW(ov, out, "out", 3, 3);
+  EMK_REQUIRE(xv.shape[2] == 3 && ov.shape[0] == xv.shape[0] && ov.shape[1] == iv.shape[0] && ov.shape[2] == 3, EMK_E_SHAPE,
+              "emk_dl_gather_atoms: need xyz (b, n, 3), index (m), out (b, m, 3)");
+  return gather_atoms_device(F(xv), xv.shape[0], xv.shape[1], static_cast<const int32_t*>(iv.data), iv.shape[0], F(ov), as_stream(stream));
+}
+int emk_dl_gather_atoms_bwd(const DLManagedTensor* grad_out, const DLManagedTensor* index, DLManagedTensor* grad_xyz, void* stream) {
+  VIEW(gv, grad_out, "grad_out", 3, 3);
+  View iv;
+  int rc = index_view(index, &iv);
+  if (rc) return rc;
+  VIEW(xv, grad_xyz, "grad_xyz", 3, 3);
+  EMK_REQUIRE(xv.shape[2] == 3 && gv.shape[0] == xv.shape[0] && gv.shape[1] == iv.shape[0] && gv.shape[2] == 3, EMK_E_SHAPE,
+              "emk_dl_gather_atoms_bwd: need grad_out (b, m, 3), index (m), grad_xyz (b, n, 3)");
+  return gather_atoms_bwd_device(F(gv), xv.shape[0], xv.shape[1], static_cast<const int32_t*>(iv.data), iv.shape[0], F(xv), as_stream(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,613 @@
+// Back-mapping WITH side chains: BackMapLayerWithSidechains, forward and exact backward, plus the atom gather
+// PairwiseDistances uses on its output.
+//
+// Reference: encodermap/models/layers.py:218-843 (numpy twin encodermap/misc/backmapping.py:424-1002).  The layer lays all atoms
+// out in the z = 0 plane -- the 3 n backbone atoms on the x axis at the running sum of the bond lengths, every side chain
+// straight up in y from its CA -- and then sets every bond angle and every dihedral ONE AFTER THE OTHER: measure the current
+// value on the atoms as they stand, rotate the atoms "behind" the pivot / bond by the difference.  Which atoms are behind comes
+// from boolean masks (n_ops x n_atoms) built in the constructor.  In TensorFlow every one of those ~6 n + 2 S steps is a dozen
+// kernels that gather, rotate and re-stack the whole (batch, n_atoms, 4) tensor.
+//
+// Here: the masks of this construction are at most two index ranges per step (a suffix of the backbone and a suffix of the
+// side-chain atoms, or a suffix of one side chain), so the plan is 12 ints per step, built once on the host
+// (emk_sidechain_plan_create) and kept on the device.  One CTA owns a frame: coordinates live in shared memory as float64 for
+// the whole sequence (a bond angle is measured on a still straight triplet at every step but the first of a side chain, where
+// acos turns the rounding of the cosine into sqrt(2 eps): 3.5e-4 rad in float32, 1.5e-8 in float64), warp 0 measures and
+// builds the rotation, all warps apply it to the moving ranges.  The backward kernel re-runs the forward keeping the rotation
+// angles, then walks the steps in reverse: every rotation is undone in place (the pivot and the axis atoms do not move, so the
+// inverse is known from the state after the step), which restores the coordinates each measurement saw without storing them,
+// while the gradient is pulled back through the rotation, its angle, its axis, its pivot and the measured value.
+#include <algorithm>
+#include <vector>
+
+#include "emk_common.cuh"
+
+namespace emk {
+
+constexpr int kOpInts = 12;   // kind, a, b, c, d, column, lo0, hi0, lo1, hi1, 0, 0   (three int4 loads)
+enum OpKind { kCentralAngle = 0, kSideAngle = 1, kCentralDihedral = 2, kSideDihedral = 3 };
+// a measured bond angle with 1 - cos^2 below this is a constant for the backward pass (acos is not differentiable at a straight
+// triplet; TensorFlow gives 0, a huge number or NaN there depending on how the float32 cosine rounded)
+constexpr double kStraightEps = 1e-12;
+
+struct SidechainPlan {
+  int n_res = 0, n_bb = 0, n_side = 0, n_atoms = 0, n_ops = 0;
+  int cols[6] = {0, 0, 0, 0, 0, 0};   // central distances / angles / dihedrals, side distances / angles / dihedrals
+  std::vector<int> ops;               // n_ops x kOpInts
+  std::vector<int> side;              // n_side x 4: CA atom, first atom of its chain, one past its last atom, 0
+  int device = -1;
+  int* d_mem = nullptr;               // ops, then side
+};
+
+// ---- host: the index construction of the layer, as ranges --------------------------------------------------------------------
+// layers.py:249-474.  Mask row r of the backbone bonds keeps backbone atoms <= r and the first T[r] side-chain atoms; T is built
+// exactly as the reference builds its "right side" rows (:254-359): one row of zeros, three rows per residue holding the number
+// of side-chain atoms placed so far (a residue without side chain repeats the previous residue's rows; the first and the last
+// residue contribute nothing when they have none), one row of everything.  That only adds up to the 3 n - 1 bonds when exactly
+// one of the two end residues has no side chain: any other description fails in the reference (np.hstack) and is refused here.
+static int build_plan(int64_t n_res, const int32_t* counts, SidechainPlan* pl) {
+  EMK_REQUIRE(n_res >= 1 && n_res < (1 << 20) && counts, EMK_E_ARG, "emk_sidechain_plan_create: need the side-chain dihedral count of >= 1 residues");
+  int64_t n_side = 0, n_sdih = 0;
+  for (int64_t r = 0; r < n_res; r++) {
+    EMK_REQUIRE(counts[r] >= 0 && counts[r] < 64, EMK_E_ARG, "emk_sidechain_plan_create: residue %lld has %d side-chain dihedrals", (long long)(r + 1), counts[r]);
+    if (counts[r] > 0) n_side += counts[r] + 1;
+    n_sdih += counts[r];
+  }
+  EMK_REQUIRE(n_side > 0, EMK_E_UNSUPPORTED, "emk_sidechain_plan_create: no residue has a side chain (the reference layer cannot be built either: layers.py:477)");
+  const int n_bb = (int)(3 * n_res);
+  std::vector<int> kept;   // T
+  kept.push_back(0);
+  int filled = 0, last = -1;
+  for (int64_t r = 0; r < n_res; r++) {
+    if (counts[r] == 0) {
+      if (r == 0 || r == n_res - 1) continue;
+      EMK_REQUIRE(last >= 0, EMK_E_UNSUPPORTED,
+                  "emk_sidechain_plan_create: residue %lld has no side chain and no residue before it has one (NameError in the reference, layers.py:287)",
+                  (long long)(r + 1));
+    } else {
+      filled += counts[r] + 1;
+      last = filled;
+    }
+    for (int k = 0; k < 3; k++) kept.push_back(last);
+  }
+  kept.push_back((int)n_side);
+  EMK_REQUIRE((int)kept.size() == n_bb - 1, EMK_E_UNSUPPORTED,
+              "emk_sidechain_plan_create: exactly one of the first / last residue must be without side chain (the reference's index "
+              "construction yields %d rows for %d backbone bonds, layers.py:370-372)", (int)kept.size(), n_bb - 1);
+  pl->n_res = (int)n_res; pl->n_bb = n_bb; pl->n_side = (int)n_side; pl->n_atoms = n_bb + (int)n_side;
+  pl->cols[0] = n_bb - 1; pl->cols[1] = n_bb - 2; pl->cols[2] = n_bb - 3; pl->cols[3] = (int)n_side; pl->cols[4] = (int)n_side; pl->cols[5] = (int)n_sdih;
+  auto& ops = pl->ops;
+  auto push = [&](int kind, int a, int b, int c, int d, int col, int lo0, int hi0, int lo1, int hi1) {
+    const int rec[kOpInts] = {kind, a, b, c, d, col, lo0, hi0, lo1, hi1, 0, 0};
+    ops.insert(ops.end(), rec, rec + kOpInts);
+  };
+  const int n_atoms = pl->n_atoms;
+  // backbone bond angles: mask row i + 1, about +z through atom i + 1 (:654-717)
+  for (int i = 0; i + 2 < n_bb; i++) push(kCentralAngle, i, i + 1, i + 2, -1, i, i + 2, n_bb, n_bb + kept[i + 1], n_atoms);
+  // side-chain bond angles, about -z (:720-783); the chain of a residue is N, CA, then its own atoms
+  pl->side.assign((size_t)n_side * 4, 0);
+  {
+    int first = n_bb, j = 0;
+    for (int64_t r = 0; r < n_res; r++) {
+      const int c = counts[r];
+      if (c == 0) continue;
+      const int end = first + c + 1;
+      auto chain = [&](int q) { return q == 0 ? (int)(3 * r) : q == 1 ? (int)(3 * r + 1) : first + q - 2; };
+      for (int q = 0; q <= c; q++, j++) {
+        push(kSideAngle, chain(q), chain(q + 1), chain(q + 2), -1, j, first + q, end, 0, 0);
+        pl->side[4 * (size_t)j] = (int)(3 * r + 1); pl->side[4 * (size_t)j + 1] = first; pl->side[4 * (size_t)j + 2] = end;
+      }
+      first = end;
+    }
+  }
+  // backbone dihedrals: mask row i + 1, about the bond (i + 1, i + 2) (:786-841)
+  for (int i = 0; i + 3 < n_bb; i++) push(kCentralDihedral, i, i + 1, i + 2, i + 3, i, i + 2, n_bb, n_bb + kept[i + 1], n_atoms);
+  // side-chain dihedrals: the rows of the side-chain mask without the last one of every residue (:423-428)
+  {
+    int first = n_bb, col = 0;
+    for (int64_t r = 0; r < n_res; r++) {
+      const int c = counts[r];
+      if (c == 0) continue;
+      const int end = first + c + 1;
+      auto chain = [&](int q) { return q == 0 ? (int)(3 * r) : q == 1 ? (int)(3 * r + 1) : first + q - 2; };
+      for (int q = 0; q < c; q++, col++) push(kSideDihedral, chain(q), chain(q + 1), chain(q + 2), chain(q + 3), col, first + q, end, 0, 0);
+      first = end;
+    }
+  }
+  pl->n_ops = (int)(ops.size() / kOpInts);
+  return EMK_OK;
+}
+
+// ---- device --------------------------------------------------------------------------------------------------------------------
+struct ScParams {
+  const int4* ops;
+  const int4* side;
+  const float* in[6];
+  int cols[6];
+  int64_t frames;
+  int n_bb, n_side, n_atoms, n_ops;
+  float* out;
+  const float* gout;
+  float* gin[6];
+};
+
+// slots of the published transform
+enum { TR_R = 0, TR_P = 9, TR_U = 12, TR_S = 15, TR_C = 16, TR_TH = 17, TR_N = 18 };
+
+__device__ __forceinline__ void cross3d(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3d(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ __forceinline__ int input_of(int kind) { return kind == kCentralAngle ? 1 : kind == kSideAngle ? 4 : kind == kCentralDihedral ? 2 : 5; }
+
+__device__ __forceinline__ double measured_angle(const double* xf, int a, int b, int c, double* t_raw) {
+  double ba[3], bc[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ba[k] = xf[3 * a + k] - xf[3 * b + k]; bc[k] = xf[3 * c + k] - xf[3 * b + k]; }
+  const double t = dot3d(ba, bc) / (sqrt(dot3d(ba, ba)) * sqrt(dot3d(bc, bc)));      // layers.py:674-681
+  *t_raw = t;
+  return acos(fmin(fmax(t, -1.0), 1.0));
+}
+__device__ __forceinline__ double measured_dihedral(const double* xf, int a, int b, int c, int d) {
+  double b1[3], b2[3], b3[3], c1[3], c2[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { b1[k] = xf[3 * b + k] - xf[3 * a + k]; b2[k] = xf[3 * c + k] - xf[3 * b + k]; b3[k] = xf[3 * d + k] - xf[3 * c + k]; }
+  cross3d(b2, b3, c1);
+  cross3d(b1, b2, c2);
+  return atan2(dot3d(b1, c1) * sqrt(dot3d(b2, b2)), dot3d(c1, c2));                  // layers.py:800-808
+}
+
+// rotation by (s, c) about the unit axis u into tr[TR_R..]
+__device__ __forceinline__ void publish_rotation(double* tr, const double* u, double s, double c) {
+  const double oc = 1.0 - c;
+  tr[0] = c + u[0] * u[0] * oc;        tr[1] = u[0] * u[1] * oc - u[2] * s; tr[2] = u[0] * u[2] * oc + u[1] * s;
+  tr[3] = u[1] * u[0] * oc + u[2] * s; tr[4] = c + u[1] * u[1] * oc;        tr[5] = u[1] * u[2] * oc - u[0] * s;
+  tr[6] = u[2] * u[0] * oc - u[1] * s; tr[7] = u[2] * u[1] * oc + u[0] * s; tr[8] = c + u[2] * u[2] * oc;
+  tr[TR_U] = u[0]; tr[TR_U + 1] = u[1]; tr[TR_U + 2] = u[2]; tr[TR_S] = s; tr[TR_C] = c;
+}
+
+// initial planar layout (layers.py:555-648)
+__device__ __forceinline__ void sc_layout(const ScParams& p, int64_t f, double* xf) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const float* cd = p.in[0] + f * p.cols[0];
+  const float* sd = p.in[3] + f * p.cols[3];
+  for (int k = tid; k < p.n_bb; k += nth) {
+    xf[3 * k] = k == 0 ? 0.0 : (double)__ldg(cd + k - 1);
+    xf[3 * k + 1] = 0.0; xf[3 * k + 2] = 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int k = 1; k < p.n_bb; k++) { run += xf[3 * k]; xf[3 * k] = run; }
+  }
+  __syncthreads();
+  for (int m = tid; m < p.n_side; m += nth) {
+    const int4 s = __ldg(p.side + m);
+    double y = 0.0;
+    for (int q = s.y; q <= p.n_bb + m; q++) y += (double)__ldg(sd + q - p.n_bb);
+    const int at = p.n_bb + m;
+    xf[3 * at] = xf[3 * s.x]; xf[3 * at + 1] = y; xf[3 * at + 2] = 0.0;
+  }
+  __syncthreads();
+}
+
+// one forward step; every thread calls it.  th_keep: where warp 0 leaves the rotation angle (or nullptr)
+__device__ __forceinline__ void sc_step(const ScParams& p, int64_t f, int k, double* xf, double* tr, double* th_keep) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int4 o0 = __ldg(p.ops + 3 * k), o1 = __ldg(p.ops + 3 * k + 1), o2 = __ldg(p.ops + 3 * k + 2);
+  if (tid < 32) {
+    const int kind = o0.x, a = o0.y, b = o0.z, c = o0.w, d = o1.x;
+    const int src = input_of(kind);
+    const double target = (double)__ldg(p.in[src] + f * p.cols[src] + o1.y);
+    double theta, u[3];
+    if (kind <= kSideAngle) {
+      double t_raw;
+      theta = fabs(target - measured_angle(xf, a, b, c, &t_raw));                      // :682-683
+      u[0] = 0.0; u[1] = 0.0; u[2] = kind == kCentralAngle ? 1.0 : -1.0;               // self.up / self.down
+    } else {
+      theta = target - measured_dihedral(xf, a, b, c, d);                              // :809
+#pragma unroll
+      for (int q = 0; q < 3; q++) u[q] = xf[3 * c + q] - xf[3 * b + q];
+      const double inv = 1.0 / sqrt(dot3d(u, u));
+      u[0] *= inv; u[1] *= inv; u[2] *= inv;
+    }
+    double s, cs;
+    sincos(theta, &s, &cs);
+    if (tid == 0) {
+      publish_rotation(tr, u, s, cs);
+      tr[TR_P] = xf[3 * b]; tr[TR_P + 1] = xf[3 * b + 1]; tr[TR_P + 2] = xf[3 * b + 2];
+      if (th_keep) *th_keep = theta;
+    }
+  }
+  __syncthreads();
+  const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
+  const double px = tr[TR_P], py = tr[TR_P + 1], pz = tr[TR_P + 2];
+  const int n0 = o1.w - o1.z, total = n0 + (o2.y - o2.x);
+  for (int e = tid; e < total; e += nth) {
+    const int at = e < n0 ? o1.z + e : o2.x + (e - n0);
+    const double x = xf[3 * at] - px, y = xf[3 * at + 1] - py, z = xf[3 * at + 2] - pz;
+    xf[3 * at] = px + r0 * x + r1 * y + r2 * z;
+    xf[3 * at + 1] = py + r3 * x + r4 * y + r5 * z;
+    xf[3 * at + 2] = pz + r6 * x + r7 * y + r8 * z;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) sidechain_fwd_kernel(const ScParams p) {
+  extern __shared__ double sc_smem[];
+  double* xf = sc_smem;
+  double* tr = sc_smem + 3 * (size_t)p.n_atoms;
+  for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    __syncthreads();
+    sc_layout(p, f, xf);
+    for (int k = 0; k < p.n_ops; k++) sc_step(p, f, k, xf, tr, nullptr);
+    float* dst = p.out + f * (int64_t)(3 * p.n_atoms);
+    for (int e = threadIdx.x; e < 3 * p.n_atoms; e += blockDim.x) dst[e] = (float)xf[e];
+  }
+}
+
+// ---- backward --------------------------------------------------------------------------------------------------------------------
+// For the step X' = where(static, X, p + R(theta, u)(X - p)) with theta = target - m(X) (dihedrals) or |target - m(X)| (bond
+// angles), u = e_z / -e_z or the normalised bond X_c - X_b, p = X_b, and incoming gradient G' = dL/dX':
+//   moving atoms:  G_j = R^T G'_j;   g_p += G'_j - R^T G'_j;   g_theta += G'_j . (u x (X'_j - p));
+//                  g_u += sin(theta) (v_j x G'_j) + (1 - cos(theta)) ((u . v_j) G'_j + (u . G'_j) v_j),  v_j = X_j - p
+//   then G_b += g_p;  through the normalisation g_d = (g_u - u (u . g_u)) / |d| to atoms c (+) and b (-);
+//   dL/dtarget = +-g_theta and -+g_theta dm/dX to the three / four measured atoms.
+constexpr int kRed = 7;
+
+__global__ void __launch_bounds__(128) sidechain_bwd_kernel(const ScParams p) {
+  extern __shared__ double sc_smem[];
+  double* xf = sc_smem;
+  double* gf = xf + 3 * (size_t)p.n_atoms;
+  double* th = gf + 3 * (size_t)p.n_atoms;
+  double* tr = th + p.n_ops;
+  double* red = tr + TR_N;                 // (blockDim / 32) x kRed
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nth >> 5;
+  for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    __syncthreads();
+    sc_layout(p, f, xf);
+    for (int k = 0; k < p.n_ops; k++) sc_step(p, f, k, xf, tr, th + k);
+    const float* gsrc = p.gout + f * (int64_t)(3 * p.n_atoms);
+    for (int e = tid; e < 3 * p.n_atoms; e += nth) gf[e] = (double)__ldg(gsrc + e);
+    __syncthreads();
+    for (int k = p.n_ops - 1; k >= 0; k--) {
+      const int4 o0 = __ldg(p.ops + 3 * k), o1 = __ldg(p.ops + 3 * k + 1), o2 = __ldg(p.ops + 3 * k + 2);
+      const int kind = o0.x, a = o0.y, b = o0.z, c = o0.w, d = o1.x;
+      const bool dihedral = kind >= kCentralDihedral;
+      if (tid == 0) {
+        // the rotation of this step, from the state AFTER it: pivot and axis atoms are fixed points of the rotation
+        double u[3];
+        if (!dihedral) {
+          u[0] = 0.0; u[1] = 0.0; u[2] = kind == kCentralAngle ? 1.0 : -1.0;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 3; q++) u[q] = xf[3 * c + q] - xf[3 * b + q];
+          const double inv = 1.0 / sqrt(dot3d(u, u));
+          u[0] *= inv; u[1] *= inv; u[2] *= inv;
+        }
+        double s, cs;
+        sincos(th[k], &s, &cs);
+        publish_rotation(tr, u, s, cs);
+        tr[TR_P] = xf[3 * b]; tr[TR_P + 1] = xf[3 * b + 1]; tr[TR_P + 2] = xf[3 * b + 2];
+      }
+      __syncthreads();
+      double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      {
+        const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
+        const double pv[3] = {tr[TR_P], tr[TR_P + 1], tr[TR_P + 2]};
+        const double u[3] = {tr[TR_U], tr[TR_U + 1], tr[TR_U + 2]};
+        const double s = tr[TR_S], oc = 1.0 - tr[TR_C];
+        const int n0 = o1.w - o1.z, total = n0 + (o2.y - o2.x);
+        for (int e = tid; e < total; e += nth) {
+          const int at = e < n0 ? o1.z + e : o2.x + (e - n0);
+          const double w[3] = {xf[3 * at] - pv[0], xf[3 * at + 1] - pv[1], xf[3 * at + 2] - pv[2]};
+          const double v[3] = {r0 * w[0] + r3 * w[1] + r6 * w[2], r1 * w[0] + r4 * w[1] + r7 * w[2], r2 * w[0] + r5 * w[1] + r8 * w[2]};
+          xf[3 * at] = pv[0] + v[0]; xf[3 * at + 1] = pv[1] + v[1]; xf[3 * at + 2] = pv[2] + v[2];      // the state before the step
+          const double g[3] = {gf[3 * at], gf[3 * at + 1], gf[3 * at + 2]};
+          const double rg[3] = {r0 * g[0] + r3 * g[1] + r6 * g[2], r1 * g[0] + r4 * g[1] + r7 * g[2], r2 * g[0] + r5 * g[1] + r8 * g[2]};
+          double uxw[3];
+          cross3d(u, w, uxw);
+          acc[0] += dot3d(g, uxw);
+          acc[1] += g[0] - rg[0]; acc[2] += g[1] - rg[1]; acc[3] += g[2] - rg[2];
+          if (dihedral) {
+            double vxg[3];
+            cross3d(v, g, vxg);
+            const double uv = dot3d(u, v), ug = dot3d(u, g);
+#pragma unroll
+            for (int q = 0; q < 3; q++) acc[4 + q] += s * vxg[q] + oc * (uv * g[q] + ug * v[q]);
+          }
+          gf[3 * at] = rg[0]; gf[3 * at + 1] = rg[1]; gf[3 * at + 2] = rg[2];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kRed; q++) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kRed; q++) red[warp * kRed + q] = acc[q];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double sum[kRed];
+#pragma unroll
+        for (int q = 0; q < kRed; q++) {
+          double v = 0.0;
+          for (int w = 0; w < n_warps; w++) v += red[w * kRed + q];
+          sum[q] = v;
+        }
+        const int src = input_of(kind);
+        const double target = (double)__ldg(p.in[src] + f * p.cols[src] + o1.y);
+        gf[3 * b] += sum[1]; gf[3 * b + 1] += sum[2]; gf[3 * b + 2] += sum[3];
+        const double g_theta = sum[0];
+        double g_target;
+        if (!dihedral) {
+          double ba[3], bc[3];
+#pragma unroll
+          for (int q = 0; q < 3; q++) { ba[q] = xf[3 * a + q] - xf[3 * b + q]; bc[q] = xf[3 * c + q] - xf[3 * b + q]; }
+          const double na2 = dot3d(ba, ba), nc2 = dot3d(bc, bc), nn = sqrt(na2) * sqrt(nc2);
+          const double t = dot3d(ba, bc) / nn;
+          const double tc = fmin(fmax(t, -1.0), 1.0);
+          const double diff = target - acos(tc);
+          const double sgn = diff > 0.0 ? 1.0 : diff < 0.0 ? -1.0 : 0.0;                     // d|x|/dx
+          g_target = sgn * g_theta;
+          const double one_m = 1.0 - tc * tc;
+          if (t >= -1.0 && t <= 1.0 && one_m >= kStraightEps) {
+            const double gt = g_target / sqrt(one_m);          // dL/dt = (-sgn g_theta) (-1 / sqrt(1 - t^2))
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              const double da = gt * (bc[q] / nn - t * ba[q] / na2), dc = gt * (ba[q] / nn - t * bc[q] / nc2);
+              gf[3 * a + q] += da; gf[3 * c + q] += dc; gf[3 * b + q] -= da + dc;
+            }
+          }
+        } else {
+          g_target = g_theta;
+          // the axis: u = dvec / |dvec|
+          double dv[3], gu[3] = {sum[4], sum[5], sum[6]};
+#pragma unroll
+          for (int q = 0; q < 3; q++) dv[q] = xf[3 * c + q] - xf[3 * b + q];
+          const double len = sqrt(dot3d(dv, dv));
+          const double u[3] = {dv[0] / len, dv[1] / len, dv[2] / len};
+          const double ugu = dot3d(u, gu);
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            const double gd = (gu[q] - u[q] * ugu) / len;
+            gf[3 * c + q] += gd; gf[3 * b + q] -= gd;
+          }
+          // the measured dihedral m = atan2(p1, p2): dL/dm = -g_theta, pulled back by hand through layers.py:800-808
+          double b1[3], b2[3], b3[3], c1[3], c2[3];
+#pragma unroll
+          for (int q = 0; q < 3; q++) { b1[q] = xf[3 * b + q] - xf[3 * a + q]; b2[q] = dv[q]; b3[q] = xf[3 * d + q] - xf[3 * c + q]; }
+          cross3d(b2, b3, c1);
+          cross3d(b1, b2, c2);
+          const double qd = dot3d(b1, c1), p1 = qd * len, p2 = dot3d(c1, c2);
+          const double den = p1 * p1 + p2 * p2;
+          if (den > 0.0) {
+            const double gm = -g_theta;
+            const double gp1 = gm * p2 / den, gp2 = -gm * p1 / den;
+            const double gq = gp1 * len, glen = gp1 * qd;
+            double gb1[3], gb2[3], gb3[3], gc1[3], gc2[3], tmp[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              gb1[q] = gq * c1[q];
+              gc1[q] = gq * b1[q] + gp2 * c2[q];
+              gc2[q] = gp2 * c1[q];
+              gb2[q] = glen * b2[q] / len;
+            }
+            cross3d(b3, gc1, tmp);   // c1 = b2 x b3:  g_b2 += b3 x g_c1,  g_b3 = g_c1 x b2
+#pragma unroll
+            for (int q = 0; q < 3; q++) gb2[q] += tmp[q];
+            cross3d(gc1, b2, gb3);
+            cross3d(b2, gc2, tmp);   // c2 = b1 x b2:  g_b1 += b2 x g_c2,  g_b2 += g_c2 x b1
+#pragma unroll
+            for (int q = 0; q < 3; q++) gb1[q] += tmp[q];
+            cross3d(gc2, b1, tmp);
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              gb2[q] += tmp[q];
+              gf[3 * a + q] -= gb1[q];
+              gf[3 * b + q] += gb1[q] - gb2[q];
+              gf[3 * c + q] += gb2[q] - gb3[q];
+              gf[3 * d + q] += gb3[q];
+            }
+          }
+        }
+        float* gdst = p.gin[src];
+        if (gdst) gdst[f * p.cols[src] + o1.y] = (float)g_target;
+      }
+      __syncthreads();
+    }
+    // the planar layout: x of backbone atom k = sum of the bonds before it, x of a side-chain atom = x of its CA, y = running sum
+    // of its own chain's bonds (layers.py:593-628)
+    float* g_sd = p.gin[3];
+    for (int m = tid; m < p.n_side; m += nth) {
+      const int4 s = __ldg(p.side + m);
+      if (g_sd) {
+        double y = 0.0;
+        for (int q = p.n_bb + m; q < s.z; q++) y += gf[3 * q + 1];
+        g_sd[f * p.cols[3] + m] = (float)y;
+      }
+    }
+    __syncthreads();
+    float* g_cd = p.gin[0];
+    if (tid == 0 && g_cd) {
+      for (int m = 0; m < p.n_side; m++) gf[3 * __ldg(p.side + m).x] += gf[3 * (p.n_bb + m)];
+      double run = 0.0;
+      for (int k = p.n_bb - 1; k >= 1; k--) {
+        run += gf[3 * k];
+        g_cd[f * p.cols[0] + k - 1] = (float)run;
+      }
+    }
+  }
+}
+
+// ---- gather / scatter of atoms (PairwiseDistances with reconstruct_sidechains, layers.py:1260-1265) ---------------------------
+__global__ void gather_atoms_kernel(const float* __restrict__ x, int64_t b, int n, const int* __restrict__ index, int m, float* __restrict__ out) {
+  const int64_t total = b * (int64_t)m * 3;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fr = e / (3 * m);
+    const int r = (int)(e - fr * 3 * m);
+    const int at = __ldg(index + r / 3);
+    out[e] = (at >= 0 && at < n) ? __ldg(x + (fr * n + at) * 3 + r % 3) : __int_as_float(0x7fc00000);
+  }
+}
+__global__ void scatter_atoms_kernel(const float* __restrict__ g, int64_t b, int n, const int* __restrict__ index, int m, float* __restrict__ gx) {
+  const int64_t total = b * (int64_t)m * 3;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fr = e / (3 * m);
+    const int r = (int)(e - fr * 3 * m);
+    const int at = __ldg(index + r / 3);
+    if (at >= 0 && at < n) atomicAdd(gx + (fr * n + at) * 3 + r % 3, __ldg(g + e));
+  }
+}
+
+int gather_atoms_device(const float* x, int64_t b, int64_t n, const int32_t* index_dev, int64_t m, float* out, cudaStream_t st) {
+  EMK_REQUIRE(b >= 0 && n >= 1 && m >= 0 && n < (1 << 28) && m < (1 << 28), EMK_E_SHAPE, "emk_gather_atoms: bad shape");
+  if (b == 0 || m == 0) return EMK_OK;
+  EMK_REQUIRE(x && index_dev && out, EMK_E_NULL, "emk_gather_atoms: NULL pointer argument");
+  const int64_t total = b * m * 3;
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  gather_atoms_kernel<<<grid, 256, 0, st>>>(x, b, (int)n, index_dev, (int)m, out);
+  return launch_status("gather_atoms_kernel");
+}
+int gather_atoms_bwd_device(const float* grad_out, int64_t b, int64_t n, const int32_t* index_dev, int64_t m, float* grad_x, cudaStream_t st) {
+  EMK_REQUIRE(b >= 0 && n >= 1 && m >= 0 && n < (1 << 28) && m < (1 << 28), EMK_E_SHAPE, "emk_gather_atoms_bwd: bad shape");
+  if (b == 0) return EMK_OK;
+  EMK_REQUIRE(grad_x && (m == 0 || (grad_out && index_dev)), EMK_E_NULL, "emk_gather_atoms_bwd: NULL pointer argument");
+  EMK_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)(b * n * 3) * sizeof(float), st));
+  if (m == 0) return EMK_OK;
+  const int64_t total = b * m * 3;
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+  scatter_atoms_kernel<<<grid, 256, 0, st>>>(grad_out, b, (int)n, index_dev, (int)m, grad_x);
+  return launch_status("scatter_atoms_kernel");
+}
+
+// ---- host entry points ------------------------------------------------------------------------------------------------------------
+int sidechain_plan_create(int64_t n_res, const int32_t* counts, SidechainPlan** out) {
+  EMK_REQUIRE(out, EMK_E_NULL, "emk_sidechain_plan_create: NULL plan pointer");
+  *out = nullptr;
+  SidechainPlan* pl = new SidechainPlan();
+  int rc = build_plan(n_res, counts, pl);
+  if (rc) { delete pl; return rc; }
+  // the device copy is optional: without a GPU the plan can still be inspected (emk_sidechain_plan_info / _ops)
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0) {
+    const size_t n_ints = pl->ops.size() + pl->side.size();
+    int* mem = nullptr;
+    cudaError_t e = cudaMalloc(&mem, n_ints * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(mem, pl->ops.data(), pl->ops.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(mem + pl->ops.size(), pl->side.data(), pl->side.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      if (mem) cudaFree(mem);
+      cudaGetLastError();
+      mem = nullptr;
+      dev = -1;
+    }
+    pl->d_mem = mem;
+    pl->device = dev;
+  } else {
+    cudaGetLastError();
+  }
+  *out = pl;
+  return EMK_OK;
+}
+void sidechain_plan_destroy(SidechainPlan* pl) {
+  if (!pl) return;
+  if (pl->d_mem) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != pl->device) cudaSetDevice(pl->device);
+    cudaFree(pl->d_mem);
+    if (cur >= 0 && cur != pl->device) cudaSetDevice(cur);
+  }
+  delete pl;
+}
+int sidechain_plan_info(const SidechainPlan* pl, int64_t* info) {
+  EMK_REQUIRE(pl && info, EMK_E_NULL, "emk_sidechain_plan_info: NULL pointer argument");
+  info[0] = pl->n_atoms; info[1] = pl->n_side; info[2] = pl->n_ops; info[3] = pl->n_res;
+  for (int k = 0; k < 6; k++) info[4 + k] = pl->cols[k];
+  return EMK_OK;
+}
+int sidechain_plan_ops(const SidechainPlan* pl, int32_t* ops) {
+  EMK_REQUIRE(pl && ops, EMK_E_NULL, "emk_sidechain_plan_ops: NULL pointer argument");
+  std::copy(pl->ops.begin(), pl->ops.end(), ops);
+  return EMK_OK;
+}
+const int* sidechain_plan_cols(const SidechainPlan* pl) { return pl->cols; }
+int sidechain_plan_atoms(const SidechainPlan* pl) { return pl->n_atoms; }
+
+static int fill_params(const char* who, const SidechainPlan* pl, const float* const* in, int64_t frames, ScParams* p) {
+  EMK_REQUIRE(pl, EMK_E_NULL, "%s: NULL plan", who);
+  EMK_REQUIRE(frames >= 0, EMK_E_SHAPE, "%s: negative frame count", who);
+  int dev = -1;
+  EMK_CUDA(cudaGetDevice(&dev));
+  EMK_REQUIRE(pl->d_mem && pl->device == dev, EMK_E_DEVICE, "%s: the plan was created on device %d, the current device is %d", who, pl->device, dev);
+  for (int k = 0; k < 6; k++) {
+    EMK_REQUIRE(frames == 0 || pl->cols[k] == 0 || in[k], EMK_E_NULL, "%s: NULL input %d", who, k);
+    p->in[k] = in[k];
+    p->cols[k] = pl->cols[k];
+  }
+  p->ops = reinterpret_cast<const int4*>(pl->d_mem);
+  p->side = reinterpret_cast<const int4*>(pl->d_mem + pl->ops.size());
+  p->frames = frames; p->n_bb = pl->n_bb; p->n_side = pl->n_side; p->n_atoms = pl->n_atoms; p->n_ops = pl->n_ops;
+  return EMK_OK;
+}
+
+static unsigned frames_grid(int64_t frames, size_t smem) {
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, (227 * 1024) / (smem + 1024)));
+  return (unsigned)std::min<int64_t>(frames, (int64_t)sm_count() * per_sm);
+}
+
+int sidechain_backmap_device(const SidechainPlan* pl, const float* const* in, int64_t frames, float* out, cudaStream_t st) {
+  ScParams p{};
+  int rc = fill_params("emk_sidechain_backmap", pl, in, frames, &p);
+  if (rc) return rc;
+  if (frames == 0) return EMK_OK;
+  EMK_REQUIRE(out, EMK_E_NULL, "emk_sidechain_backmap: NULL output");
+  const size_t smem = (3 * (size_t)pl->n_atoms + TR_N) * sizeof(double);
+  EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap: %d atoms need %zu bytes of shared memory per frame (limit 227 KB)", pl->n_atoms, smem);
+  p.out = out;
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(sidechain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  sidechain_fwd_kernel<<<frames_grid(frames, smem), 128, smem, st>>>(p);
+  return launch_status("sidechain_fwd_kernel");
+}
+
+int sidechain_backmap_bwd_device(const SidechainPlan* pl, const float* const* in, int64_t frames, const float* grad_out, float* const* grad_in,
+                                 cudaStream_t st) {
+  ScParams p{};
+  int rc = fill_params("emk_sidechain_backmap_bwd", pl, in, frames, &p);
+  if (rc) return rc;
+  if (frames == 0) return EMK_OK;
+  EMK_REQUIRE(grad_out, EMK_E_NULL, "emk_sidechain_backmap_bwd: NULL grad_out");
+  const size_t smem = (6 * (size_t)pl->n_atoms + pl->n_ops + TR_N + 4 * kRed) * sizeof(double);
+  EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap_bwd: %d atoms / %d steps need %zu bytes of shared memory per frame (limit 227 KB)",
+              pl->n_atoms, pl->n_ops, smem);
+  p.gout = grad_out;
+  for (int k = 0; k < 6; k++) p.gin[k] = grad_in[k];
+  static bool cfg[kMaxDevices] = {false};
+  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(sidechain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  sidechain_bwd_kernel<<<frames_grid(frames, smem), 128, smem, st>>>(p);
+  return launch_status("sidechain_bwd_kernel");
+}
+
+// PairwiseDistances.__init__ with reconstruct_sidechains (layers.py:1188-1208): the sliced backbone plus one index per residue with
+// a side chain; the running index starts at 3 n + 1 and advances by the residue's number of side-chain DIHEDRALS (as the reference
+// does).  out may be NULL to ask for the count.
+int64_t sidechain_pairwise_indices(int64_t n_res, const int32_t* counts, int64_t first, int64_t count, int64_t step, int64_t* out) {
+  int64_t k = 0;
+  for (int64_t i = 0; i < count; i++, k++)
+    if (out) out[k] = first + i * step;
+  int64_t atom = 3 * n_res + 1;
+  for (int64_t r = 0; r < n_res; r++) {
+    if (counts[r] == 0) continue;
+    atom += counts[r];
+    if (out) out[k] = atom;
+    k++;
+  }
+  return k;
+}
+
+}  // namespace emk

@@ -265,6 +265,61 @@ EMK_API int emk_set_dihedrals(const float* start, int64_t start_frames, int64_t 
                               const int32_t* far_offsets, const int32_t* far_atoms, int64_t n_dihedrals, const float* targets,
                               int64_t frames, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Back-mapping WITH side chains: BackMapLayerWithSidechains, forward and exact backward
+ *   encodermap/models/layers.py:218-843 (constructor :234-500, call :533-843; numpy twin _full_backmapping_np,
+ *   encodermap/misc/backmapping.py:424-1002).  Atom order of the output: the 3 n backbone atoms (N, CA, C per residue), then per
+ *   residue with a side chain its (dihedrals + 1) side-chain atoms.  All atoms start in the z = 0 plane (backbone on the x axis,
+ *   side chains straight up from their CA); then every bond angle (backbone about +z, side chains about -z, by |target -
+ *   measured|) and every dihedral (by target - measured, about its central bond) is set one after the other on the atoms behind
+ *   the pivot, in the reference's order: backbone angles, side-chain angles, backbone dihedrals, side-chain dihedrals.
+ *
+ *   emk_sidechain_plan_create   HOST: n_side_dihedrals[r] = feature_description[-1][r + 1].  Builds the 12-int step table
+ *                               (the reference's boolean masks, as index ranges) and uploads it to the CURRENT device (the plan
+ *                               is bound to it; without a device the plan can still be inspected).  Refuses, with
+ *                               EMK_E_UNSUPPORTED, the descriptions the reference's constructor cannot build either: no side
+ *                               chain at all, not exactly one of the first / last residue without side chain, a residue without
+ *                               side chain before the first one with.
+ *   emk_sidechain_plan_info     info[10] = n_atoms, n_side_atoms, n_steps, n_residues, then the column counts of the six inputs
+ *   emk_sidechain_plan_ops      ops (n_steps, 12) int32: kind (0 backbone angle, 1 side angle, 2 backbone dihedral, 3 side
+ *                               dihedral), atoms a b c d (d = -1 for angles), input column, moving ranges [lo0, hi0) [lo1, hi1)
+ *   emk_sidechain_backmap       inputs (frames, columns) float32 device, xyz (frames, n_atoms, 3).  One CTA per frame,
+ *                               coordinates in shared memory as float64 for the whole sequence; capturable.
+ *   emk_sidechain_backmap_bwd   exact VJP (any gradient pointer may be NULL): re-runs the forward, then undoes the rotations in
+ *                               reverse order.  A bond angle measured on a straight triplet (1 - cos^2 < 1e-12) is a constant
+ *                               (acos is not differentiable there; the reference's float32 autodiff gives 0, a huge number or
+ *                               NaN depending on rounding).  At most ~3 500 atoms (shared memory).
+ *   emk_sidechain_pairwise_indices  HOST: the atoms PairwiseDistances selects when side chains are reconstructed
+ *                               (layers.py:1188-1208): backbone[start:stop:step] (INT64_MIN = None) plus one index per residue
+ *                               with a side chain; returns the count (indices may be NULL), -1 on bad arguments
+ *   emk_gather_atoms(_bwd)      out[b, k] = xyz[b, index[k]] (tf.gather, layers.py:1260-1265) and its VJP (scatter-add into a
+ *                               zeroed grad_xyz); index is a DEVICE int32 array, an index outside [0, n_atoms) yields NaN
+ * ---------------------------------------------------------------------------------------- */
+typedef struct emk_sidechain_plan emk_sidechain_plan;
+EMK_API int emk_sidechain_plan_create(int64_t n_residues, const int32_t* n_side_dihedrals, emk_sidechain_plan** plan);
+EMK_API void emk_sidechain_plan_destroy(emk_sidechain_plan* plan);
+EMK_API int emk_sidechain_plan_info(const emk_sidechain_plan* plan, int64_t* info);
+EMK_API int emk_sidechain_plan_ops(const emk_sidechain_plan* plan, int32_t* ops);
+EMK_API int emk_sidechain_backmap(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
+                                  const float* central_dihedrals, const float* side_distances, const float* side_angles,
+                                  const float* side_dihedrals, int64_t frames, float* xyz, void* stream);
+EMK_API int emk_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
+                                      const float* central_dihedrals, const float* side_distances, const float* side_angles,
+                                      const float* side_dihedrals, int64_t frames, const float* grad_xyz,
+                                      float* grad_central_distances, float* grad_central_angles, float* grad_central_dihedrals,
+                                      float* grad_side_distances, float* grad_side_angles, float* grad_side_dihedrals, void* stream);
+/* inputs / grad_inputs: arrays of six tensors in the order above (grad_inputs entries may be NULL) */
+EMK_API int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, DLManagedTensor* xyz, void* stream);
+EMK_API int emk_dl_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, const DLManagedTensor* grad_xyz,
+                                         DLManagedTensor* const* grad_inputs, void* stream);
+EMK_API int64_t emk_sidechain_pairwise_indices(int64_t n_residues, const int32_t* n_side_dihedrals, int64_t start, int64_t stop,
+                                               int64_t step, int64_t* indices);
+EMK_API int emk_gather_atoms(const float* xyz, int64_t b, int64_t n_atoms, const int32_t* index_dev, int64_t m, float* out, void* stream);
+EMK_API int emk_gather_atoms_bwd(const float* grad_out, int64_t b, int64_t n_atoms, const int32_t* index_dev, int64_t m, float* grad_xyz,
+                                 void* stream);
+EMK_API int emk_dl_gather_atoms(const DLManagedTensor* xyz, const DLManagedTensor* index, DLManagedTensor* out, void* stream);
+EMK_API int emk_dl_gather_atoms_bwd(const DLManagedTensor* grad_out, const DLManagedTensor* index, DLManagedTensor* grad_xyz, void* stream);
+
 /* mean over rows: (rows,cols) -> (cols)   the `tf.reduce_mean(distances, 0)` of BackMapLayer.call, layers.py:970 */
 EMK_API int emk_column_mean(const float* x, int64_t rows, int64_t cols, float* out, void* stream);
 EMK_API int emk_dl_column_mean(const DLManagedTensor* x, DLManagedTensor* out, void* stream);

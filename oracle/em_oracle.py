@@ -370,6 +370,182 @@ def back_map_layer(distances, angles, dihedrals, left_split: Optional[int] = Non
 # ----------------------------------------------------------------------------------------
 
 
+# ----------------------------------------------------------------------------------------
+# encodermap/models/layers.py: BackMapLayerWithSidechains
+# ----------------------------------------------------------------------------------------
+
+
+def sidechain_topology(counts: Sequence[int]) -> dict:
+    """Index tables of BackMapLayerWithSidechains for ``counts[r]`` side-chain dihedrals in residue r + 1.
+    Reference: encodermap/models/layers.py:234-474 (numpy twin misc/backmapping.py:571-798).  Atom order: the 3 n backbone
+    atoms, then per residue with a side chain its ``count + 1`` atoms.  ``True`` in a mask row = the atom stays where it is.
+
+    The reference's construction only closes (its hstack of 3 n - 1 rows) when exactly one of the first / last residue has no
+    side chain, and an interior residue without one re-uses the rows of the previous residue: restated as is.
+    """
+    counts = [int(c) for c in counts]
+    n_res = len(counts)
+    n_bb = 3 * n_res
+    n_side = sum(c + 1 for c in counts if c > 0)
+    if n_side == 0:
+        raise ValueError("no side chain at all: the reference layer cannot be built (side_angle_indices undefined, layers.py:477)")
+    central_left = np.tri(n_bb - 1, n_bb, 0).astype(bool)                                      # :249-253
+    right_rows = [np.zeros((1, n_side), bool)]                                                  # :254-256
+    filled = 0                  # side-chain atoms placed so far ("count", :257)
+    next_atom = n_bb            # index of the next side chain's first atom ("count2 - 1", :258)
+    side_triplets, side_quads, side_rows_of_dihedrals = [], [], []
+    last_rows = None
+    for r, c in enumerate(counts):                                                              # :280-349
+        if c == 0:
+            if r == 0 or r == n_res - 1:
+                continue
+            if last_rows is None:
+                raise ValueError("a residue without side chain before the first side chain: NameError in the reference (:287)")
+            right_rows.append(last_rows)
+            continue
+        n_, ca_ = 3 * r, 3 * r + 1
+        chain = [n_, ca_] + list(range(next_atom, next_atom + c + 1))    # N, CA, CB, CG, ...
+        side_rows_of_dihedrals += list(range(filled, filled + c))                              # :289-291
+        for q in range(c + 1):
+            side_triplets.append(chain[q:q + 3])                                                # :298-300, 312-314, 322-328
+            if q < c:
+                side_quads.append(chain[q:q + 4])                                               # :302-309, 316-319, 329-337
+        filled += c + 1
+        next_atom += c + 1
+        last_rows = np.zeros((3, n_side), bool)                                                 # :340-345
+        last_rows[:, :filled] = True
+        right_rows.append(last_rows)
+    right_rows.append(np.ones((1, n_side), bool))                                               # :357-359
+    right = np.vstack(right_rows)
+    if right.shape[0] != n_bb - 1:
+        raise ValueError(f"the reference's index construction needs exactly one of the first / last residue without a side "
+                         f"chain ({right.shape[0]} rows for {n_bb - 1} backbone bonds, layers.py:370-372)")
+    central_mask = np.hstack([central_left, right])                                             # :370-372
+    blocks = []
+    for c in counts:                                                                            # :373-391
+        if c > 0:
+            blocks.append((np.tri(c + 1, c + 2, 0) + 1)[:, 1:])
+    side_right = np.zeros((n_side, n_side))
+    o = 0
+    for b in blocks:
+        side_right[o:o + b.shape[0], o:o + b.shape[1]] = b
+        o += b.shape[0]
+    side_mask = np.hstack([np.ones((n_side, n_bb), bool), (side_right % 2) == 0])
+    bb = np.arange(n_bb)
+    central_triplets = np.stack([bb[:-2], bb[1:-1], bb[2:]], 1)                                 # :261-267
+    central_quads = np.stack([bb[:-3], bb[1:-2], bb[2:-1], bb[3:]], 1)                          # :269-277
+    return {
+        "n_atoms": n_bb + n_side, "n_side": n_side, "n_res": n_res,
+        "central_mask": central_mask,
+        "central_angle_mask": central_mask[1:],                                                 # :410
+        "side_angle_mask": side_mask,                                                           # :415
+        "dihedral_mask": np.vstack([central_mask[1:-1], side_mask[np.array(side_rows_of_dihedrals, dtype=int)]]),   # :423-428
+        "central_angle_triplets": central_triplets,
+        "side_angle_triplets": np.array(side_triplets).reshape(-1, 3),
+        "dihedral_quadruplets": np.vstack([central_quads, np.array(side_quads).reshape(-1, 4)]),
+        "counts": np.array(counts),
+    }
+
+
+def _rotation_about(angle, direction, point):
+    """Batch of 3x3 rotations by ``angle`` about ``direction`` (normalised here) and the translation that makes them rotations
+    about ``point``.  Reference: _rotation_matrices, encodermap/models/layers.py:859-899."""
+    u = direction / torch.sqrt((direction ** 2).sum(1, keepdim=True))
+    ca, sa = torch.cos(angle), torch.sin(angle)
+    eye = torch.eye(3, dtype=angle.dtype).expand(angle.shape[0], 3, 3)
+    rot = eye * ca[:, None, None] + u[:, :, None] * u[:, None, :] * (1.0 - ca)[:, None, None]
+    us = u * sa[:, None]
+    zero = torch.zeros_like(sa)
+    skew = torch.stack([torch.stack([zero, -us[:, 2], us[:, 1]], 1), torch.stack([us[:, 2], zero, -us[:, 0]], 1),
+                        torch.stack([-us[:, 1], us[:, 0], zero], 1)], 1)
+    rot = rot + skew
+    shift = point - torch.einsum("bij,bj->bi", rot, point)
+    return rot, shift
+
+
+#: a measured bond angle whose cosine is this close to +-1 is treated as a constant in the backward pass: acos is not
+#: differentiable there (TensorFlow yields 0, a huge number or NaN depending on how the float32 cosine happened to round)
+STRAIGHT_EPS = 1e-12
+
+
+def backmap_with_sidechains(counts: Sequence[int], inputs, topology: Optional[dict] = None):
+    """BackMapLayerWithSidechains.call: (central_distances, central_angles, central_dihedrals, side_distances, side_angles,
+    side_dihedrals) -> (batch, n_atoms, 3).  Reference: encodermap/models/layers.py:533-843; differentiable (torch autograd
+    over this restatement is the gradient oracle).  All atoms start in the z = 0 plane: the backbone on the x axis at the
+    running sum of its bond lengths, every side chain straight up in y from its CA (:593-648); then every bond angle
+    (backbone: about +z, :654-717; side chains: about -z, :720-783) and every dihedral (:786-841) is set one after the other by
+    rotating the atoms whose mask entry is False about the pivot / bond, by |target - measured| for the bond angles and
+    target - measured for the dihedrals."""
+    topo = topology or sidechain_topology(counts)
+    cd, ca_, cdih, sd, sa_, sdih = [_t(x) for x in inputs]
+    dt = cd.dtype
+    nb = cd.shape[0]
+    counts = [int(c) for c in topo["counts"]]
+    n_bb = 3 * len(counts)
+    zero = torch.zeros(nb, 1, dtype=dt)
+    xs_c = torch.cat([zero, torch.cumsum(cd, 1)], 1)                                            # :593-606
+    xs_s, ys_s = [], []
+    j = 0
+    for r, c in enumerate(counts):                                                              # :607-628
+        if c > 0:
+            for n in range(c + 1):
+                xs_s.append(xs_c[:, 3 * r + 1])
+                ys_s.append(sd[:, j - n:j + 1].sum(1))
+                j += 1
+    xs = torch.cat([xs_c, torch.stack(xs_s, 1)], 1)
+    ys = torch.cat([torch.zeros(nb, n_bb, dtype=dt), torch.stack(ys_s, 1)], 1)
+    xyz = torch.stack([xs, ys, torch.zeros_like(xs)], 2)                                        # :635-648
+
+    def apply(xyz, rot, shift, mask_row):
+        moved = torch.einsum("bij,bnj->bni", rot, xyz) + shift[:, None, :]
+        keep = torch.from_numpy(np.ascontiguousarray(mask_row))[None, :, None]
+        return torch.where(keep, xyz, moved)
+
+    def set_angles(xyz, targets, masks, triplets, z):
+        axis = torch.tensor([[0.0, 0.0, z]], dtype=dt).expand(nb, 3)
+        for i in range(masks.shape[0]):
+            a, b, c = (xyz[:, int(k)] for k in triplets[i])
+            ba, bc = a - b, c - b
+            t = (ba * bc).sum(1) / (torch.sqrt((ba ** 2).sum(1)) * torch.sqrt((bc ** 2).sum(1)))
+            t = torch.clamp(t, -1.0, 1.0)
+            t = torch.where(1.0 - t.detach() ** 2 < STRAIGHT_EPS, t.detach(), t)
+            angle = torch.abs(targets[:, i] - torch.acos(t))
+            rot, shift = _rotation_about(angle, axis, b)
+            xyz = apply(xyz, rot, shift, masks[i])
+        return xyz
+
+    xyz = set_angles(xyz, ca_, topo["central_angle_mask"], topo["central_angle_triplets"], 1.0)
+    xyz = set_angles(xyz, sa_, topo["side_angle_mask"], topo["side_angle_triplets"], -1.0)
+    dih = torch.cat([cdih, sdih], 1)                                                            # :546-552
+    for i in range(topo["dihedral_mask"].shape[0]):
+        a, b, c, d = (xyz[:, int(k)] for k in topo["dihedral_quadruplets"][i])
+        b1, b2, b3 = b - a, c - b, d - c
+        c1 = torch.linalg.cross(b2, b3)
+        c2 = torch.linalg.cross(b1, b2)
+        p1 = (b1 * c1).sum(1) * torch.sqrt((b2 * b2).sum(1))
+        p2 = (c1 * c2).sum(1)
+        angle = dih[:, i] - torch.atan2(p1, p2)
+        rot, shift = _rotation_about(angle, c - b, b)
+        xyz = apply(xyz, rot, shift, topo["dihedral_mask"][i])
+    return xyz
+
+
+def sidechain_pairwise_indices(counts: Sequence[int], start=None, stop=None, step=None) -> np.ndarray:
+    """Atoms PairwiseDistances selects when side chains are reconstructed: the sliced backbone plus one atom index per residue
+    with a side chain.  Reference: encodermap/models/layers.py:1188-1208 (the running index advances by the residue's number of
+    side-chain DIHEDRALS, one less than its atoms: restated as is)."""
+    n_res = len(counts)
+    first = np.arange(3 * n_res)[start:stop:step]
+    atom = 3 * n_res + 1
+    extra = []
+    for c in counts:
+        if c == 0:
+            continue
+        atom += int(c)
+        extra.append(atom)
+    return np.concatenate([first, np.array(extra, dtype=first.dtype)])
+
+
 # ---- generation side: guessed amide H / carbonyl O and the merge (SURVEY.md 8f-3) --------------------------------------
 def guess_sp2_atom(cartesians, indices, angle_to_previous: float, bond_length: float):
     """Reference: encodermap/misc/backmapping.py:1920-1941.  ``cartesians[:, i + 1]`` past the last atom raises in

@@ -384,3 +384,50 @@ def test_near_and_far_sides_against_networkx_on_random_trees():
             comp_v = next(c for c in comps if v in c)
             assert set(nr.tolist()) == comp_u and set(fr.tolist()) == comp_v
             assert np.all(np.diff(nr) > 0) and np.all(np.diff(fr) > 0)      # sorted, unique
+
+
+def test_sidechain_plan_equals_the_reference_masks(L, golden):
+    """emk_sidechain_plan_create against the boolean masks / index tables the reference's constructor builds
+    (models/layers.py:234-474, run by tools/gen_golden.py): bit-exact, as ranges."""
+    from encodermap_b200 import _ops
+
+    g = golden["sidechains"]
+    for tag in ("metlysgly", "first_empty", "twelve", "ub_like"):
+        counts = g[f"{tag}_counts"]
+        plan = _ops.SidechainPlan(counts)
+        ops = plan.ops()
+        masks = np.ones((plan.n_ops, plan.n_atoms), dtype=bool)
+        for k, o in enumerate(ops):
+            assert 0 <= o[6] <= o[7] <= plan.n_atoms and 0 <= o[8] <= o[9] <= plan.n_atoms
+            masks[k, o[6]:o[7]] = False
+            masks[k, o[8]:o[9]] = False
+        want = np.vstack([g[f"{tag}_central_angle_mask"], g[f"{tag}_side_angle_mask"], g[f"{tag}_dihedral_mask"]])
+        assert np.array_equal(masks, want), tag
+        n_ang = len(g[f"{tag}_central_angle_mask"]) + len(g[f"{tag}_side_angle_mask"])
+        assert np.array_equal(ops[:n_ang, 1:4], np.vstack([g[f"{tag}_central_angle_triplets"], g[f"{tag}_side_angle_triplets"]]))
+        assert (ops[:n_ang, 4] == -1).all()
+        assert np.array_equal(ops[n_ang:, 1:5], g[f"{tag}_dihedral_quadruplets"])
+        n_ca, n_sa, n_cd = len(g[f"{tag}_central_angle_mask"]), len(g[f"{tag}_side_angle_mask"]), 3 * len(counts) - 3
+        assert np.array_equal(ops[:, 0], np.concatenate([np.zeros(n_ca), np.ones(n_sa), np.full(n_cd, 2), np.full(plan.n_ops - n_ang - n_cd, 3)]))
+        for kind in range(4):    # every input column is used exactly once, in order
+            cols = ops[ops[:, 0] == kind, 5]
+            assert np.array_equal(cols, np.arange(len(cols)))
+        assert plan.columns == tuple(g[f"{tag}_in_{k}"].shape[1] for k in ("cd", "ca", "cdih", "sd", "sa", "sdih"))
+        assert plan.n_atoms == g[f"{tag}_out"].shape[1]
+        for sel, (a, b, c) in {"ca": (1, None, 3), "all": (None, None, None)}.items():
+            assert np.array_equal(_ops.sidechain_pairwise_indices(counts, a, b, c), g[f"{tag}_pwd_indices_{sel}"])
+
+
+def test_sidechain_plan_refuses_what_the_reference_cannot_build(L):
+    from encodermap_b200 import _ops
+    from encodermap_b200.models.layers import BackMapLayerWithSidechains
+
+    for bad in ([3, 4, 2], [0, 2, 0], [0, 0, 3, 1], [0, 0, 0]):
+        with pytest.raises(ValueError):
+            _ops.SidechainPlan(bad)
+    with pytest.raises(AssertionError):
+        BackMapLayerWithSidechains({-1: {1: 2, 3: 0}})
+    layer = BackMapLayerWithSidechains({-1: {1: 3, 2: 4, 3: 0}})
+    assert layer.n_atoms == 18 and layer.n_sidechains == 9
+    again = BackMapLayerWithSidechains.from_config({"feature_description": {"-1": {"1": 3, "2": 4, "3": 0}}})
+    assert again.counts == layer.counts and again.get_config()["feature_description"] == {-1: {1: 3, 2: 4, 3: 0}}

@@ -1384,3 +1384,160 @@ def test_empty_and_single_frame_batches(em):
             assert abs(O.dihedral_np(got[0].cpu().double().numpy(), (0, 1, 2, 3)) - 0.7) < 1e-5
         l_, g_ = _ops.sigmoid_cost_raw(cu(np.zeros((b, 3))), cu(np.zeros((b, 2))), float("inf"), DEFAULT_SIG)
         assert g_.shape == (b, 2) and (b == 0 or float(l_) == 0.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# back-mapping with side chains: BackMapLayerWithSidechains + the gathered PairwiseDistances
+# (reference models/layers.py:218-843, 1188-1265)
+# ---------------------------------------------------------------------------------------------------
+SIDECHAIN_KEYS = ("cd", "ca", "cdih", "sd", "sa", "sdih")
+
+
+def _sidechain_inputs(rng, counts, frames):
+    n_res = len(counts)
+    n_side = sum(c + 1 for c in counts if c > 0)
+    return [rng.uniform(0.13, 0.16, size=(frames, 3 * n_res - 1)).astype(np.float32),
+            rng.uniform(1.85, 2.25, size=(frames, 3 * n_res - 2)).astype(np.float32),
+            rng.uniform(-pi, pi, size=(frames, 3 * n_res - 3)).astype(np.float32),
+            rng.uniform(0.13, 0.19, size=(frames, n_side)).astype(np.float32),
+            rng.uniform(1.80, 2.20, size=(frames, n_side)).astype(np.float32),
+            rng.uniform(-pi, pi, size=(frames, sum(counts))).astype(np.float32)]
+
+
+@pytest.mark.parametrize("tag", ["metlysgly", "first_empty", "twelve", "ub_like"])
+def test_sidechain_backmap_golden(em, golden, tag):
+    """Against the coordinates the reference's own layer body produced (float64 evaluation, tools/gen_golden.py)."""
+    from encodermap_b200.models.layers import BackMapLayerWithSidechains
+
+    g = golden["sidechains"]
+    counts = g[f"{tag}_counts"]
+    layer = BackMapLayerWithSidechains({-1: {k + 1: int(v) for k, v in enumerate(counts)}})
+    got = layer(tuple(cu(g[f"{tag}_in_{k}"]) for k in SIDECHAIN_KEYS)).cpu().numpy()
+    assert got.shape == g[f"{tag}_out"].shape
+    assert np.abs(got - g[f"{tag}_out"]).max() < 5e-6      # float32 output of coordinates up to 6 nm; the bar is 1e-4 nm
+
+
+def test_sidechain_backmap_forward_and_gradient_vs_oracle(em):
+    """A 60-residue chain, 300 frames (more frames than resident CTAs would be 1 776; the grid-stride loop is covered by the
+    large-batch test below): coordinates to 1e-4 nm, all six input gradients to 1e-5 norm-wise against float64 autograd over the
+    oracle's restatement."""
+    from encodermap_b200 import _ops
+
+    rng = np.random.default_rng(41)
+    counts = [int(v) for v in rng.integers(0, 5, size=60)]
+    counts[0], counts[-1] = 3, 0
+    plan = _ops.SidechainPlan(counts, torch.device("cuda"))
+    frames = 6
+    inputs = _sidechain_inputs(rng, counts, frames)
+    ts = [cu(v).requires_grad_(True) for v in inputs]
+    out = _ops.SidechainBackmap.apply(plan, *ts)
+    w = rng.normal(size=tuple(out.shape))
+    (out * cu(w)).sum().backward()
+    oi = [torch.tensor(v.astype(np.float64), requires_grad=True) for v in inputs]
+    want = O.backmap_with_sidechains(counts, oi)
+    (want * torch.from_numpy(w)).sum().backward()
+    assert np.abs(out.detach().cpu().numpy() - want.detach().numpy()).max() < COORD_ATOL
+    assert np.abs(out.detach().cpu().numpy() - want.detach().numpy()).max() < 1e-5
+    for t, o, name in zip(ts, oi, SIDECHAIN_KEYS):
+        assert relnorm(t.grad.cpu().numpy(), o.grad.numpy()) < GRAD_RTOL, name
+
+
+def test_sidechain_backmap_partial_gradients_and_raw_abi(em):
+    """Only some inputs need gradients (the model feeds the distances as data): NULL gradient pointers are skipped; the raw-pointer
+    entry points give the same numbers as the DLPack ones."""
+    import ctypes
+
+    from encodermap_b200 import _lib, _ops
+
+    rng = np.random.default_rng(42)
+    counts = [2, 0, 4, 1, 3, 0]
+    plan = _ops.SidechainPlan(counts, torch.device("cuda"))
+    inputs = [cu(v) for v in _sidechain_inputs(rng, counts, 5)]
+    full = _ops.sidechain_backmap_bwd_raw(plan, inputs, cu(rng.normal(size=(5, plan.n_atoms, 3))))
+    ts = [t.clone().requires_grad_(k in (1, 2, 5)) for k, t in enumerate(inputs)]
+    out = _ops.SidechainBackmap.apply(plan, *ts)
+    g_out = cu(rng.normal(size=tuple(out.shape)))
+    out.backward(g_out)
+    want = _ops.sidechain_backmap_bwd_raw(plan, inputs, g_out)
+    for k, t in enumerate(ts):
+        assert (t.grad is None) == (k not in (1, 2, 5))
+        if t.grad is not None:
+            assert torch.equal(t.grad, want[k])
+    assert all(torch.isfinite(f).all() for f in full)
+    L = _lib.lib()
+    xyz = torch.empty(5, plan.n_atoms, 3, device="cuda")
+    _lib.check(L.emk_sidechain_backmap(plan.handle, *[t.data_ptr() for t in inputs], 5, xyz.data_ptr(), _lib.stream_of(xyz)))
+    assert torch.equal(xyz, out.detach())
+    grads = [torch.empty_like(t) for t in inputs]
+    _lib.check(L.emk_sidechain_backmap_bwd(plan.handle, *[t.data_ptr() for t in inputs], 5, g_out.data_ptr(),
+                                           *[g.data_ptr() for g in grads], _lib.stream_of(xyz)))
+    for a, b in zip(grads, want):
+        assert torch.equal(a, b)
+    # wrong column count, wrong device pointer class
+    with pytest.raises(_lib.EmkError):
+        _ops.sidechain_backmap_raw(plan, [inputs[0][:, :-1]] + inputs[1:])
+    with pytest.raises(_lib.EmkError):
+        _ops.sidechain_backmap_raw(plan, [inputs[0].cpu()] + inputs[1:])
+    assert _ops.sidechain_backmap_raw(plan, [t[:0] for t in inputs]).shape == (0, plan.n_atoms, 3)
+
+
+def test_sidechain_backmap_large_batch_properties(em):
+    """4 000 frames of a ubiquitin-sized description (448 atoms, 823 steps): more frames than CTAs in the grid.  What the
+    reference's own test asserts (tests/test_autoencoder.py:1018-1075): the bond lengths of the result are the inputs (their
+    rtol 1e-3), backbone angles and dihedrals come out as asked."""
+    from encodermap_b200 import _ops
+
+    g = np.load(str(__import__("pathlib").Path(__file__).parent / "golden" / "sidechains.npz"))
+    counts = g["ub_like_counts"]
+    plan = _ops.SidechainPlan(counts, torch.device("cuda"))
+    rng = np.random.default_rng(43)
+    frames = 4000
+    inputs = _sidechain_inputs(rng, [int(c) for c in counts], frames)
+    out = _ops.sidechain_backmap_raw(plan, [cu(v) for v in inputs]).cpu().numpy().astype(np.float64)
+    assert np.isfinite(out).all()
+    n_bb = 3 * len(counts)
+    d = np.linalg.norm(out[:, 1:n_bb] - out[:, :n_bb - 1], axis=-1)
+    assert np.abs(d / inputs[0] - 1).max() < 1e-4
+    sb = g["ub_like_np_side_distance_indices"]
+    assert np.abs(np.linalg.norm(out[:, sb[:, 1]] - out[:, sb[:, 0]], axis=-1) / inputs[3] - 1).max() < 1e-4
+    ba, bc = out[:, :n_bb - 2] - out[:, 1:n_bb - 1], out[:, 2:n_bb] - out[:, 1:n_bb - 1]
+    ang = np.arccos(np.clip((ba * bc).sum(-1) / np.linalg.norm(ba, axis=-1) / np.linalg.norm(bc, axis=-1), -1, 1))
+    assert np.abs(ang - inputs[1]).max() < 1e-4
+    sub = [0, 1777, frames - 1]
+    quads = g["ub_like_np_central_dihedrals_indices"]
+    dih = np.array([[O.dihedral_np(out[f], q) for q in quads] for f in sub])
+    assert np.abs((dih - inputs[2][sub] + pi) % (2 * pi) - pi).max() < 1e-4
+    want = O.backmap_with_sidechains(counts, [v[sub].astype(np.float64) for v in inputs]).numpy()
+    assert np.abs(out[sub] - want).max() < 2e-5
+
+
+def test_pairwise_distances_with_reconstructed_sidechains(em, golden):
+    """PairwiseDistances(reconstruct_sidechains=True): gathered atoms (reference models/layers.py:1188-1208, 1260-1265), forward and
+    gradient through gather + pairwise distances."""
+    from encodermap_b200 import ADCParameters
+    from encodermap_b200.models.layers import PairwiseDistances
+
+    g = golden["sidechains"]
+    counts = g["twelve_counts"]
+    p = ADCParameters(cartesian_pwd_start=1, cartesian_pwd_stop=None, cartesian_pwd_step=3)
+    p.reconstruct_sidechains = True
+    p.sidechain_info = {-1: {k + 1: int(v) for k, v in enumerate(counts)}}
+    layer = PairwiseDistances(p, "output")
+    assert np.array_equal(layer.indices, g["twelve_pwd_indices_ca"])
+    xyz = g["twelve_out"]
+    x = cu(xyz).requires_grad_(True)
+    got = layer(x)
+    xo = torch.tensor(xyz, requires_grad=True)
+    want = O.pairwise_dist(xo[:, torch.as_tensor(layer.indices)], flat=True)
+    assert got.shape == want.shape
+    assert np.abs(got.detach().cpu().numpy() - want.detach().numpy()).max() < 2e-6
+    w = np.random.default_rng(5).normal(size=tuple(want.shape))
+    (got * cu(w)).sum().backward()
+    (want * torch.from_numpy(w)).sum().backward()
+    assert relnorm(x.grad.cpu().numpy(), xo.grad.numpy()) < GRAD_RTOL
+    # an index past the last atom: tf.gather would return zeros on a GPU; refused here
+    p2 = ADCParameters(cartesian_pwd_start=None, cartesian_pwd_stop=None, cartesian_pwd_step=None)
+    p2.reconstruct_sidechains = True
+    p2.sidechain_info = {-1: {1: 3, 2: 0}}
+    with pytest.raises(IndexError):
+        PairwiseDistances(p2, "output")(cu(np.zeros((2, 10, 3))))

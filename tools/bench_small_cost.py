@@ -14,7 +14,7 @@ from _timing import eager_time, graph_time  # noqa: E402
 dev = torch.device("cuda:0")
 SIG = (4.5, 12, 6, 1, 2, 6)
 for n, d, per in ((256, 3, float("inf")), (256, 1024, 2 * math.pi), (512, 1024, 2 * math.pi), (1024, 1024, 2 * math.pi),
-                  (1024, 4950, float("inf")), (2048, 1024, 2 * math.pi), (3072, 1024, 2 * math.pi), (4096, 1024, 2 * math.pi), (8192, 1024, 2 * math.pi)):
+                  (1024, 4950, float("inf")), (1024, 44850, float("inf")), (2048, 1024, 2 * math.pi), (3072, 1024, 2 * math.pi), (4096, 1024, 2 * math.pi), (8192, 1024, 2 * math.pi)):
     g = torch.Generator(device=dev).manual_seed(1)
     x = (torch.rand(n, d, device=dev, generator=g) * 2 - 1) * math.pi
     z = torch.randn(n, 2, device=dev, generator=g)

@@ -552,9 +552,237 @@ def main():
     g["sd_near_sizes"] = np.array([len(n_) for n_ in near_sides])
     g["sd_start"], g["sd_targets"], g["sd_out"] = start, targets, new_xyz[..., :3]
     np.savez_compressed(OUT / "generation.npz", **g)
+    sidechain_section()
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size} bytes")
 
+
+
+# ----------------------------------------------------------------------------------------
+# side-chain back-mapping: BackMapLayerWithSidechains and its numpy twin
+# ----------------------------------------------------------------------------------------
+
+
+class _TensorArray:
+    """tf.TensorArray as the layer uses it: write returns the array, read / stack."""
+
+    def __init__(self, dtype=None, size=0, clear_after_read=False):
+        self.items = {}
+
+    def write(self, i, value):
+        self.items[int(i)] = np.asarray(value, dtype=np.float64 if np.asarray(value).dtype.kind == "f" else None)
+        return self
+
+    def read(self, i):
+        return _w(self.items[int(i)])
+
+    def stack(self):
+        return _w(np.stack([self.items[k] for k in sorted(self.items)], axis=0))
+
+
+def _set_shape(self, shape):
+    assert tuple(self.shape) == tuple(int(v) for v in shape), (self.shape, shape)
+
+
+T.set_shape = _set_shape
+
+
+class _KerasBackend:
+    @staticmethod
+    def batch_dot(a, b):
+        a, b = np.asarray(a), np.asarray(b)
+        if a.ndim == 2 and b.ndim == 2:
+            return _w(np.sum(a * b, axis=1, keepdims=True))
+        if a.ndim == 3 and b.ndim == 2:
+            return _w(np.einsum("bij,bj->bi", a, b))
+        return _w(np.einsum("bij,bjk->bik", a, b))
+
+
+class _TFShimSide(_TFShim):
+    """The further tf symbols BackMapLayerWithSidechains (models/layers.py:218-908) touches."""
+
+    bool = np.bool_
+    int32 = np.int32
+    TensorArray = _TensorArray
+    keras = type("K", (), {"backend": _KerasBackend()})()
+
+    class linalg(_Linalg):
+        @staticmethod
+        def diag(x, k=0):
+            x = np.asarray(x)
+            out = np.zeros(x.shape + (x.shape[-1],), x.dtype)
+            idx = np.arange(x.shape[-1])
+            out[..., idx, idx] = x
+            return _w(out)
+
+    def constant(self, x, shape=None, dtype=None):
+        a = np.asarray(x)
+        if dtype is np.bool_ or dtype is np.int32:
+            return _w(a.astype(dtype))
+        return _w(a.astype(self.dtype))
+
+    def zeros(self, shape, dtype=None):
+        return _w(np.zeros(tuple(int(v) for v in shape), self.dtype))
+
+    def pad(self, x, paddings, constant_values=0):
+        return _w(np.pad(np.asarray(x), paddings, mode="constant", constant_values=constant_values))
+
+    def repeat(self, x, repeats, axis=None):
+        return _w(np.repeat(np.asarray(x), int(repeats), axis=axis))
+
+    def gather(self, params, indices, axis=None, batch_dims=0):
+        assert batch_dims == 0
+        return _w(np.take(np.asarray(params), np.asarray(indices), axis=axis))
+
+    def where(self, c, a=None, b=None):
+        if a is None:
+            return _w(np.argwhere(np.asarray(c)))
+        return _w(np.where(c, a, b))
+
+    def clip_by_value(self, x, clip_value_min, clip_value_max):
+        return _w(np.clip(x, clip_value_min, clip_value_max))
+
+    def squeeze(self, x):
+        return _w(np.squeeze(x))
+
+    def acos(self, x):
+        return _w(np.arccos(x))
+
+    def atan2(self, y, x):
+        return _w(np.arctan2(y, x))
+
+    def einsum(self, eq, *xs):
+        return _w(np.einsum(eq, *[np.asarray(x) for x in xs]))
+
+    def transpose(self, x, perm=None):
+        return _w(np.transpose(np.asarray(x), perm))
+
+
+def _class_methods(path, cls_name, wanted, ns, drop_super=True):
+    tree = ast.parse(path.read_text())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name)
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in wanted:
+            fn.name = f"{cls_name}_{fn.name.strip('_')}"
+            fn.decorator_list, fn.returns = [], None
+            for a in fn.args.args:
+                a.annotation = None
+            if drop_super:   # `super().__init__()` needs the class cell; the Keras base initialiser does nothing the path needs
+                fn.body = [st for st in fn.body if "super()" not in ast.unparse(st)]
+            mod = ast.Module(body=[fn], type_ignores=[])
+            ast.fix_missing_locations(mod)
+            exec(compile(mod, str(path), "exec"), ns)
+
+
+SIDECHAIN_CASES = {
+    "metlysgly": [3, 4, 0],                                  # the docstring example of _full_backmapping_np
+    "first_empty": [0, 2, 1, 4],                             # residue 1 without side chain (the other admissible end)
+    "twelve": [2, 0, 4, 1, 0, 0, 3, 2, 1, 4, 2, 0],          # interior glycines after a side chain
+    "ub_like": [3, 2, 2, 4, 1, 2, 1, 1, 2, 0, 4, 1, 2, 2, 2, 2, 1, 2, 1, 1, 2, 1, 2, 2, 1, 2, 4, 0, 4, 2, 3, 2, 4, 2, 0, 2, 1,
+                1, 2, 3, 3, 4, 2, 2, 2, 0, 0, 4, 3, 2, 2, 2, 0, 4, 1, 2, 1, 2, 4, 2, 2, 3, 4, 2, 1, 1, 2, 4, 2, 1, 2, 4, 2, 4, 0, 0],
+}
+
+
+def sidechain_section():
+    import itertools
+    import types
+
+    from scipy.linalg import block_diag
+
+    g = {}
+    rng = np.random.default_rng(20261019)
+    tf = _TFShimSide(np.float64)
+    ns = {"tf": tf, "np": np, "itertools": itertools, "block_diag": block_diag, "Any": None}
+    _extract(REF / "encodermap/models/layers.py", ["_batch_fro", "_rotation_matrices", "_unit_vector"], ns)
+    _class_methods(REF / "encodermap/models/layers.py", "BackMapLayerWithSidechains", ("__init__", "call"), ns)
+    _class_methods(REF / "encodermap/models/layers.py", "PairwiseDistances", ("__init__",), ns)
+
+    # the numpy twin imports matplotlib, transformations and encodermap.misc.rotate inside its body: stand-ins for the three.
+    # transformations.rotation_matrix (C. Gohlke, not installed) = the reference's own restatement _rotmat_jit
+    # (misc/backmapping.py:356-381) with its float32 literals promoted, as in the generation section above.
+    gen = {"np": np, "Optional": None, "Union": None}
+    _extract(REF / "encodermap/misc/rotate.py", ["_displacement", "_dihedral"], gen)
+    src = (REF / "encodermap/misc/backmapping.py").read_text()
+    node = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "_rotmat_jit")
+    node.decorator_list = []
+    exec(compile(ast.unparse(node).replace("'float32'", "'float64'").replace("np.float32", "np.float64"), "_rotmat_jit[float64]", "exec"), gen)
+
+    class _Ax:
+        def plot(self, *a, **k):
+            pass
+
+    class _Fig:
+        def savefig(self, *a, **k):
+            pass
+
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.subplots = lambda **k: (_Fig(), (_Ax(), _Ax(), _Ax()))
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    tr = types.ModuleType("transformations")
+    tr.rotation_matrix = lambda angle, direction, point: gen["_rotmat_jit"](
+        float(angle), np.array(direction, dtype=np.float64), np.asarray(point, dtype=np.float64))
+    em = types.ModuleType("encodermap")
+    em_misc = types.ModuleType("encodermap.misc")
+    em_rot = types.ModuleType("encodermap.misc.rotate")
+    em_rot._dihedral = gen["_dihedral"]
+    fakes = {"matplotlib": mpl, "matplotlib.pyplot": plt, "transformations": tr, "encodermap": em, "encodermap.misc": em_misc,
+             "encodermap.misc.rotate": em_rot}
+    saved = {k: sys.modules.get(k) for k in fakes}
+    sys.modules.update(fakes)
+    nsn = {"np": np, "Sequence": None, "Union": None, "Literal": None, "BytesIO": None, "overload": lambda f: f}
+    _extract(REF / "encodermap/misc/backmapping.py", ["_full_backmapping_np"], nsn, take_last=("_full_backmapping_np",))
+
+    try:
+        for tag, counts in SIDECHAIN_CASES.items():
+            fd = {-1: {k + 1: int(v) for k, v in enumerate(counts)}}
+            n_res = len(counts)
+            n_side = sum(v + 1 for v in counts if v > 0)
+            batch = 2 if tag == "ub_like" else 3
+            f32 = lambda a: a.astype(np.float32).astype(np.float64)
+            inputs = [
+                f32(rng.uniform(0.13, 0.16, size=(batch, 3 * n_res - 1))),
+                f32(rng.uniform(1.85, 2.25, size=(batch, 3 * n_res - 2))),
+                f32(rng.uniform(-math.pi, math.pi, size=(batch, 3 * n_res - 3))),
+                f32(rng.uniform(0.13, 0.19, size=(batch, n_side))),
+                f32(rng.uniform(1.80, 2.20, size=(batch, n_side))),
+                f32(rng.uniform(-math.pi, math.pi, size=(batch, sum(counts)))),
+            ]
+            layer = _Self()
+            ns["BackMapLayerWithSidechains_init"](layer, fd)
+            g[f"{tag}_counts"] = np.array(counts, dtype=np.int32)
+            for k, v in zip(("cd", "ca", "cdih", "sd", "sa", "sdih"), inputs):
+                g[f"{tag}_in_{k}"] = v
+            g[f"{tag}_central_mask"] = np.asarray(layer.central_distance_indices)
+            g[f"{tag}_central_angle_mask"] = np.asarray(layer.central_angle_indices)
+            g[f"{tag}_side_angle_mask"] = np.asarray(layer.side_angle_indices)
+            g[f"{tag}_dihedral_mask"] = np.asarray(layer.dihedral_indices)
+            g[f"{tag}_central_angle_triplets"] = np.asarray(layer.central_angle_index_triplets)
+            g[f"{tag}_side_angle_triplets"] = np.asarray(layer.sidechain_angle_index_triplets)
+            g[f"{tag}_dihedral_quadruplets"] = np.asarray(layer.dihedral_index_quadruplets)
+            out_layer = np.asarray(ns["BackMapLayerWithSidechains_call"](layer, tuple(tf.convert_to_tensor(v) for v in inputs)))
+            out_np, _, idx = nsn["_full_backmapping_np"](fd, *inputs, return_indices=True)
+            # the TensorFlow layer and the numpy twin are the same algorithm; they differ by ~1e-8 nm even in float64 because
+            # every bond angle is measured on a still straight triplet, where acos turns a 1e-16 rounding difference of the
+            # cosine into sqrt(2e-16) = 1.4e-8 rad (in float32, as the layer runs in the reference: 3.5e-4 rad)
+            assert np.abs(out_layer - out_np).max() < 1e-6, np.abs(out_layer - out_np).max()
+            g[f"{tag}_out"] = out_layer
+            g[f"{tag}_out_np"] = np.asarray(out_np)
+            for k, v in idx.items():
+                g[f"{tag}_np_{k}"] = np.asarray(v)
+            # the atom selection of PairwiseDistances when side chains are reconstructed (models/layers.py:1188-1208)
+            for sel_tag, (a, b, c) in {"ca": (1, None, 3), "all": (None, None, None)}.items():
+                pl = _Self(p=_Self(reconstruct_sidechains=True, sidechain_info=fd, cartesian_pwd_start=a, cartesian_pwd_stop=b,
+                                   cartesian_pwd_step=c))
+                ns["PairwiseDistances_init"](pl, pl.p, "x")
+                g[f"{tag}_pwd_indices_{sel_tag}"] = np.asarray(pl.indices)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    np.savez_compressed(OUT / "sidechains.npz", **g)
 
 if __name__ == "__main__":
     if not REF.exists():
