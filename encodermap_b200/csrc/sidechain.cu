@@ -12,9 +12,10 @@
 // side-chain atoms, or a suffix of one side chain), so the plan is 12 ints per step, built once on the host
 // (emk_sidechain_plan_create) and kept on the device.  One CTA owns a frame: coordinates live in shared memory as float64 for
 // the whole sequence (a bond angle is measured on a still straight triplet at every step but the first of a side chain, where
-// acos turns the rounding of the cosine into sqrt(2 eps): 3.5e-4 rad in float32, 1.5e-8 in float64), warp 0 measures and
-// builds the rotation, all warps apply it to the moving ranges.  The backward kernel re-runs the forward keeping the rotation
-// angles, then walks the steps in reverse: every rotation is undone in place (the pivot and the axis atoms do not move, so the
+// the reference's acos turns the rounding of the cosine into sqrt(2 eps): 3.5e-4 rad in float32, 1.5e-8 in float64), warp 0
+// measures and builds the rotation -- from sines and cosines only, no inverse trigonometric function -- and all warps apply it
+// to the moving ranges.  The backward kernel re-runs the forward keeping sin / cos of every rotation angle, then walks the steps
+// in reverse: every rotation is undone in place (the pivot and the axis atoms do not move, so the
 // inverse is known from the state after the step), which restores the coordinates each measurement saw without storing them,
 // while the gradient is pulled back through the rotation, its angle, its axis, its pivot and the measured value.
 #include <algorithm>
@@ -35,6 +36,8 @@ struct SidechainPlan {
   int cols[6] = {0, 0, 0, 0, 0, 0};   // central distances / angles / dihedrals, side distances / angles / dihedrals
   std::vector<int> ops;               // n_ops x kOpInts
   std::vector<int> side;              // n_side x 4: CA atom, first atom of its chain, one past its last atom, 0
+  std::vector<int> res;               // residues with a side chain x 4: N atom, first side-chain atom, dihedral count, first dihedral column
+  int n_ca = 0, n_cd = 0;             // backbone bond-angle / dihedral steps
   int device = -1;
   int* d_mem = nullptr;               // ops, then side
 };
@@ -110,10 +113,13 @@ static int build_plan(int64_t n_res, const int32_t* counts, SidechainPlan* pl) {
       if (c == 0) continue;
       const int end = first + c + 1;
       auto chain = [&](int q) { return q == 0 ? (int)(3 * r) : q == 1 ? (int)(3 * r + 1) : first + q - 2; };
+      const int rec[4] = {(int)(3 * r), first, c, col};
+      pl->res.insert(pl->res.end(), rec, rec + 4);
       for (int q = 0; q < c; q++, col++) push(kSideDihedral, chain(q), chain(q + 1), chain(q + 2), chain(q + 3), col, first + q, end, 0, 0);
       first = end;
     }
   }
+  pl->n_ca = n_bb - 2; pl->n_cd = n_bb - 3;
   pl->n_ops = (int)(ops.size() / kOpInts);
   return EMK_OK;
 }
@@ -122,6 +128,8 @@ static int build_plan(int64_t n_res, const int32_t* counts, SidechainPlan* pl) {
 struct ScParams {
   const int4* ops;
   const int4* side;
+  const int4* res;
+  int n_res_side, n_ca, n_cd;
   const float* in[6];
   int cols[6];
   int64_t frames;
@@ -132,7 +140,7 @@ struct ScParams {
 };
 
 // slots of the published transform
-enum { TR_R = 0, TR_P = 9, TR_U = 12, TR_S = 15, TR_C = 16, TR_TH = 17, TR_N = 18 };
+enum { TR_R = 0, TR_P = 9, TR_U = 12, TR_S = 15, TR_C = 16, TR_N = 18 };
 
 __device__ __forceinline__ void cross3d(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
@@ -141,21 +149,48 @@ __device__ __forceinline__ double dot3d(const double* a, const double* b) { retu
 
 __device__ __forceinline__ int input_of(int kind) { return kind == kCentralAngle ? 1 : kind == kSideAngle ? 4 : kind == kCentralDihedral ? 2 : 5; }
 
-__device__ __forceinline__ double measured_angle(const double* xf, int a, int b, int c, double* t_raw) {
-  double ba[3], bc[3];
+// No inverse trigonometric function is evaluated anywhere: a step needs sin and cos of (target - measured), and
+//   cos(t - m) = cos t cos m + sin t sin m,   sin(t - m) = sin t cos m - cos t sin m
+// with sin / cos of the TARGETS tabulated per frame by all threads before the sequence starts (they do not depend on the
+// coordinates) and sin / cos of the MEASURED value read off the vectors: for a bond angle cos m = ba.bc / (|ba||bc|),
+// sin m = |ba x bc| / (|ba||bc|) >= 0; for a dihedral (cos m, sin m) = (p2, p1) / hypot(p1, p2)  (layers.py:674-683, 800-809).
+// The cross product also gives sin m of a (nearly) straight triplet without the cancellation of acos(-1 + eps).
+struct Measured {
+  double s, c;      // sin, cos of (target - measured)
+  double u[3];      // unit rotation axis
+  double sm;        // bond angles: sin of the measured angle
+};
+
+__device__ __forceinline__ Measured sc_measure(const double* xf, int kind, int a, int b, int c, int d, double sin_t, double cos_t) {
+  Measured m;
+  if (kind <= kSideAngle) {
+    double ba[3], bc[3], cr[3];
 #pragma unroll
-  for (int k = 0; k < 3; k++) { ba[k] = xf[3 * a + k] - xf[3 * b + k]; bc[k] = xf[3 * c + k] - xf[3 * b + k]; }
-  const double t = dot3d(ba, bc) / (sqrt(dot3d(ba, ba)) * sqrt(dot3d(bc, bc)));      // layers.py:674-681
-  *t_raw = t;
-  return acos(fmin(fmax(t, -1.0), 1.0));
-}
-__device__ __forceinline__ double measured_dihedral(const double* xf, int a, int b, int c, int d) {
-  double b1[3], b2[3], b3[3], c1[3], c2[3];
+    for (int k = 0; k < 3; k++) { ba[k] = xf[3 * a + k] - xf[3 * b + k]; bc[k] = xf[3 * c + k] - xf[3 * b + k]; }
+    const double inv = rsqrt(dot3d(ba, ba) * dot3d(bc, bc));
+    const double cm = fmin(fmax(dot3d(ba, bc) * inv, -1.0), 1.0);
+    cross3d(ba, bc, cr);
+    m.sm = fmin(sqrt(dot3d(cr, cr)) * inv, 1.0);
+    m.c = cos_t * cm + sin_t * m.sm;
+    m.s = sin_t * cm - cos_t * m.sm;
+    m.u[0] = 0.0; m.u[1] = 0.0; m.u[2] = kind == kCentralAngle ? 1.0 : -1.0;               // self.up / self.down
+  } else {
+    double b1[3], b2[3], b3[3], c1[3], c2[3];
 #pragma unroll
-  for (int k = 0; k < 3; k++) { b1[k] = xf[3 * b + k] - xf[3 * a + k]; b2[k] = xf[3 * c + k] - xf[3 * b + k]; b3[k] = xf[3 * d + k] - xf[3 * c + k]; }
-  cross3d(b2, b3, c1);
-  cross3d(b1, b2, c2);
-  return atan2(dot3d(b1, c1) * sqrt(dot3d(b2, b2)), dot3d(c1, c2));                  // layers.py:800-808
+    for (int k = 0; k < 3; k++) { b1[k] = xf[3 * b + k] - xf[3 * a + k]; b2[k] = xf[3 * c + k] - xf[3 * b + k]; b3[k] = xf[3 * d + k] - xf[3 * c + k]; }
+    const double l2 = dot3d(b2, b2), il = rsqrt(l2);
+    cross3d(b2, b3, c1);
+    cross3d(b1, b2, c2);
+    const double p1 = dot3d(b1, c1) * (l2 * il), p2 = dot3d(c1, c2);
+    const double h2 = p1 * p1 + p2 * p2;
+    double cm = 1.0, sm = 0.0;                                                             // atan2(0, 0) = 0
+    if (h2 > 0.0) { const double ih = rsqrt(h2); cm = p2 * ih; sm = p1 * ih; }
+    m.sm = sm;
+    m.c = cos_t * cm + sin_t * sm;
+    m.s = sin_t * cm - cos_t * sm;
+    m.u[0] = b2[0] * il; m.u[1] = b2[1] * il; m.u[2] = b2[2] * il;
+  }
+  return m;
 }
 
 // rotation by (s, c) about the unit axis u into tr[TR_R..]
@@ -167,14 +202,22 @@ __device__ __forceinline__ void publish_rotation(double* tr, const double* u, do
   tr[TR_U] = u[0]; tr[TR_U + 1] = u[1]; tr[TR_U + 2] = u[2]; tr[TR_S] = s; tr[TR_C] = c;
 }
 
-// initial planar layout (layers.py:555-648)
-__device__ __forceinline__ void sc_layout(const ScParams& p, int64_t f, double* xf) {
+// initial planar layout (layers.py:555-648) and the per-frame table of sin / cos of the targets; flags[k]: 0 the target of a
+// bond angle lies in [0, pi] (the sign of target - measured is the sign of its sine), 1 above, 2 below
+__device__ __forceinline__ void sc_layout(const ScParams& p, int64_t f, double* xf, double* tg, unsigned char* flags) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const float* cd = p.in[0] + f * p.cols[0];
   const float* sd = p.in[3] + f * p.cols[3];
   for (int k = tid; k < p.n_bb; k += nth) {
     xf[3 * k] = k == 0 ? 0.0 : (double)__ldg(cd + k - 1);
     xf[3 * k + 1] = 0.0; xf[3 * k + 2] = 0.0;
+  }
+  for (int k = tid; k < p.n_ops; k += nth) {
+    const int4 o0 = __ldg(p.ops + 3 * k), o1 = __ldg(p.ops + 3 * k + 1);
+    const int src = input_of(o0.x);
+    const double t = (double)__ldg(p.in[src] + f * p.cols[src] + o1.y);
+    sincos(t, tg + 2 * k, tg + 2 * k + 1);
+    if (flags) flags[k] = t > 3.141592653589793 ? 1 : t < 0.0 ? 2 : 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -192,56 +235,97 @@ __device__ __forceinline__ void sc_layout(const ScParams& p, int64_t f, double* 
   __syncthreads();
 }
 
-// one forward step; every thread calls it.  th_keep: where warp 0 leaves the rotation angle (or nullptr)
-__device__ __forceinline__ void sc_step(const ScParams& p, int64_t f, int k, double* xf, double* tr, double* th_keep) {
+// x -> p + R (x - p) for one atom
+__device__ __forceinline__ void sc_rotate_atom(double* xf, const double* tr, int at) {
+  const double x = xf[3 * at] - tr[TR_P], y = xf[3 * at + 1] - tr[TR_P + 1], z = xf[3 * at + 2] - tr[TR_P + 2];
+  xf[3 * at] = tr[TR_P] + tr[0] * x + tr[1] * y + tr[2] * z;
+  xf[3 * at + 1] = tr[TR_P + 1] + tr[3] * x + tr[4] * y + tr[5] * z;
+  xf[3 * at + 2] = tr[TR_P + 2] + tr[6] * x + tr[7] * y + tr[8] * z;
+}
+
+// The steps of the BACKBONE are strictly sequential (each measures atoms the previous one moved).  The steps of a SIDE CHAIN only
+// measure N, CA and the chain's own atoms and only move the chain's own atoms, and no backbone step runs between them: the side
+// chains of different residues are independent, so each gets one thread that walks its chain alone -- no barrier, no hand-over.
+// Sequential depth per frame: 6 n - 5 + (longest side chain) instead of 6 n - 5 + 2 (side-chain atoms).
+
+// backbone steps [k0, k1) by the whole CTA.  KEEP: leave (sin(target - measured), cos) of every step in tg for the backward pass
+template <bool KEEP>
+__device__ __forceinline__ void sc_backbone_steps(const ScParams& p, int k0, int k1, double* xf, double* tg, double* tr) {
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int4 o0 = __ldg(p.ops + 3 * k), o1 = __ldg(p.ops + 3 * k + 1), o2 = __ldg(p.ops + 3 * k + 2);
-  if (tid < 32) {
-    const int kind = o0.x, a = o0.y, b = o0.z, c = o0.w, d = o1.x;
-    const int src = input_of(kind);
-    const double target = (double)__ldg(p.in[src] + f * p.cols[src] + o1.y);
-    double theta, u[3];
-    if (kind <= kSideAngle) {
-      double t_raw;
-      theta = fabs(target - measured_angle(xf, a, b, c, &t_raw));                      // :682-683
-      u[0] = 0.0; u[1] = 0.0; u[2] = kind == kCentralAngle ? 1.0 : -1.0;               // self.up / self.down
-    } else {
-      theta = target - measured_dihedral(xf, a, b, c, d);                              // :809
-#pragma unroll
-      for (int q = 0; q < 3; q++) u[q] = xf[3 * c + q] - xf[3 * b + q];
-      const double inv = 1.0 / sqrt(dot3d(u, u));
-      u[0] *= inv; u[1] *= inv; u[2] *= inv;
+  int4 o0 = __ldg(p.ops + 3 * k0), o1 = __ldg(p.ops + 3 * k0 + 1), o2 = __ldg(p.ops + 3 * k0 + 2);
+  for (int k = k0; k < k1; k++) {
+    int4 n0 = o0, n1 = o1, n2 = o2;
+    if (k + 1 < k1) { n0 = __ldg(p.ops + 3 * k + 3); n1 = __ldg(p.ops + 3 * k + 4); n2 = __ldg(p.ops + 3 * k + 5); }
+    if (tid < 32) {
+      // every lane of warp 0 computes the same numbers (no divergence, no shuffles); lane 0 publishes them
+      const Measured m = sc_measure(xf, o0.x, o0.y, o0.z, o0.w, o1.x, tg[2 * k], tg[2 * k + 1]);
+      if (tid == 0) {
+        publish_rotation(tr, m.u, o0.x <= kSideAngle ? fabs(m.s) : m.s, m.c);            // bond angles rotate by |target - measured|
+        tr[TR_P] = xf[3 * o0.z]; tr[TR_P + 1] = xf[3 * o0.z + 1]; tr[TR_P + 2] = xf[3 * o0.z + 2];
+        if (KEEP) { tg[2 * k] = m.s; tg[2 * k + 1] = m.c; }
+      }
     }
-    double s, cs;
-    sincos(theta, &s, &cs);
-    if (tid == 0) {
-      publish_rotation(tr, u, s, cs);
+    __syncthreads();
+    const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
+    const double px = tr[TR_P], py = tr[TR_P + 1], pz = tr[TR_P + 2];
+    const int c0 = o1.w - o1.z, total = c0 + (o2.y - o2.x);
+    for (int e = tid; e < total; e += nth) {
+      const int at = e < c0 ? o1.z + e : o2.x + (e - c0);
+      const double x = xf[3 * at] - px, y = xf[3 * at + 1] - py, z = xf[3 * at + 2] - pz;
+      xf[3 * at] = px + r0 * x + r1 * y + r2 * z;
+      xf[3 * at + 1] = py + r3 * x + r4 * y + r5 * z;
+      xf[3 * at + 2] = pz + r6 * x + r7 * y + r8 * z;
+    }
+    __syncthreads();
+    o0 = n0; o1 = n1; o2 = n2;
+  }
+}
+
+// atom q of the chain N, CA, CB, CG, ... of a residue
+__device__ __forceinline__ int sc_chain(const int4& r, int q) { return q < 2 ? r.x + q : r.y + q - 2; }
+
+// side-chain steps of one kind (bond angles: DIH = false, k_base = first side-angle step; dihedrals: DIH = true), one thread per
+// residue with a side chain
+template <bool DIH, bool KEEP>
+__device__ __forceinline__ void sc_side_steps(const ScParams& p, int k_base, double* xf, double* tg) {
+  for (int ri = threadIdx.x; ri < p.n_res_side; ri += blockDim.x) {
+    const int4 r = __ldg(p.res + ri);                       // N atom, first side-chain atom, dihedral count, first dihedral column
+    const int end = r.y + r.z + 1;
+    const int k0 = k_base + (DIH ? r.w : r.y - p.n_bb);
+    const int steps = DIH ? r.z : r.z + 1;
+    for (int q = 0; q < steps; q++) {
+      const int k = k0 + q;
+      const int b = sc_chain(r, q + 1);
+      const Measured m = sc_measure(xf, DIH ? kSideDihedral : kSideAngle, sc_chain(r, q), b, sc_chain(r, q + 2), DIH ? sc_chain(r, q + 3) : -1,
+                                    tg[2 * k], tg[2 * k + 1]);
+      double tr[TR_N];
+      publish_rotation(tr, m.u, DIH ? m.s : fabs(m.s), m.c);
       tr[TR_P] = xf[3 * b]; tr[TR_P + 1] = xf[3 * b + 1]; tr[TR_P + 2] = xf[3 * b + 2];
-      if (th_keep) *th_keep = theta;
+      if (KEEP) { tg[2 * k] = m.s; tg[2 * k + 1] = m.c; }
+      for (int at = r.y + q; at < end; at++) sc_rotate_atom(xf, tr, at);
     }
   }
   __syncthreads();
-  const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
-  const double px = tr[TR_P], py = tr[TR_P + 1], pz = tr[TR_P + 2];
-  const int n0 = o1.w - o1.z, total = n0 + (o2.y - o2.x);
-  for (int e = tid; e < total; e += nth) {
-    const int at = e < n0 ? o1.z + e : o2.x + (e - n0);
-    const double x = xf[3 * at] - px, y = xf[3 * at + 1] - py, z = xf[3 * at + 2] - pz;
-    xf[3 * at] = px + r0 * x + r1 * y + r2 * z;
-    xf[3 * at + 1] = py + r3 * x + r4 * y + r5 * z;
-    xf[3 * at + 2] = pz + r6 * x + r7 * y + r8 * z;
-  }
-  __syncthreads();
+}
+
+template <bool KEEP>
+__device__ __forceinline__ void sc_forward(const ScParams& p, double* xf, double* tg, double* tr) {
+  sc_backbone_steps<KEEP>(p, 0, p.n_ca, xf, tg, tr);                                   // layers.py:654-717
+  sc_side_steps<false, KEEP>(p, p.n_ca, xf, tg);                                       // :720-783
+  const int k_cd = p.n_ca + p.n_side;
+  sc_backbone_steps<KEEP>(p, k_cd, k_cd + p.n_cd, xf, tg, tr);                         // :786-841, backbone rows
+  sc_side_steps<true, KEEP>(p, k_cd + p.n_cd, xf, tg);                                 // :786-841, side-chain rows
 }
 
 __global__ void __launch_bounds__(128) sidechain_fwd_kernel(const ScParams p) {
   extern __shared__ double sc_smem[];
   double* xf = sc_smem;
-  double* tr = sc_smem + 3 * (size_t)p.n_atoms;
+  double* tg = xf + 3 * (size_t)p.n_atoms;
+  double* tr = tg + 2 * (size_t)p.n_ops;
   for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
     __syncthreads();
-    sc_layout(p, f, xf);
-    for (int k = 0; k < p.n_ops; k++) sc_step(p, f, k, xf, tr, nullptr);
+    sc_layout(p, f, xf, tg, nullptr);
+    sc_forward<false>(p, xf, tg, tr);
     float* dst = p.out + f * (int64_t)(3 * p.n_atoms);
     for (int e = threadIdx.x; e < 3 * p.n_atoms; e += blockDim.x) dst[e] = (float)xf[e];
   }
@@ -256,72 +340,146 @@ __global__ void __launch_bounds__(128) sidechain_fwd_kernel(const ScParams p) {
 //   dL/dtarget = +-g_theta and -+g_theta dm/dX to the three / four measured atoms.
 constexpr int kRed = 7;
 
-__global__ void __launch_bounds__(128) sidechain_bwd_kernel(const ScParams p) {
-  extern __shared__ double sc_smem[];
-  double* xf = sc_smem;
-  double* gf = xf + 3 * (size_t)p.n_atoms;
-  double* th = gf + 3 * (size_t)p.n_atoms;
-  double* tr = th + p.n_ops;
-  double* red = tr + TR_N;                 // (blockDim / 32) x kRed
-  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nth >> 5;
-  for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
-    __syncthreads();
-    sc_layout(p, f, xf);
-    for (int k = 0; k < p.n_ops; k++) sc_step(p, f, k, xf, tr, th + k);
-    const float* gsrc = p.gout + f * (int64_t)(3 * p.n_atoms);
-    for (int e = tid; e < 3 * p.n_atoms; e += nth) gf[e] = (double)__ldg(gsrc + e);
-    __syncthreads();
-    for (int k = p.n_ops - 1; k >= 0; k--) {
-      const int4 o0 = __ldg(p.ops + 3 * k), o1 = __ldg(p.ops + 3 * k + 1), o2 = __ldg(p.ops + 3 * k + 2);
-      const int kind = o0.x, a = o0.y, b = o0.z, c = o0.w, d = o1.x;
-      const bool dihedral = kind >= kCentralDihedral;
-      if (tid == 0) {
-        // the rotation of this step, from the state AFTER it: pivot and axis atoms are fixed points of the rotation
-        double u[3];
-        if (!dihedral) {
-          u[0] = 0.0; u[1] = 0.0; u[2] = kind == kCentralAngle ? 1.0 : -1.0;
-        } else {
+// the rotation of step k seen from the state AFTER it (pivot and axis atoms are fixed points of the rotation)
+__device__ __forceinline__ void sc_publish_inverse(const double* xf, const double* tg, double* tr, int k, int kind, int b, int c) {
+  double u[3];
+  if (kind <= kSideAngle) {
+    u[0] = 0.0; u[1] = 0.0; u[2] = kind == kCentralAngle ? 1.0 : -1.0;
+  } else {
 #pragma unroll
-          for (int q = 0; q < 3; q++) u[q] = xf[3 * c + q] - xf[3 * b + q];
-          const double inv = 1.0 / sqrt(dot3d(u, u));
-          u[0] *= inv; u[1] *= inv; u[2] *= inv;
-        }
-        double s, cs;
-        sincos(th[k], &s, &cs);
-        publish_rotation(tr, u, s, cs);
-        tr[TR_P] = xf[3 * b]; tr[TR_P + 1] = xf[3 * b + 1]; tr[TR_P + 2] = xf[3 * b + 2];
+    for (int q = 0; q < 3; q++) u[q] = xf[3 * c + q] - xf[3 * b + q];
+    const double inv = rsqrt(dot3d(u, u));
+    u[0] *= inv; u[1] *= inv; u[2] *= inv;
+  }
+  publish_rotation(tr, u, kind <= kSideAngle ? fabs(tg[2 * k]) : tg[2 * k], tg[2 * k + 1]);
+  tr[TR_P] = xf[3 * b]; tr[TR_P + 1] = xf[3 * b + 1]; tr[TR_P + 2] = xf[3 * b + 2];
+}
+
+// one moving atom of a step, backward: restores its position before the step, pulls its gradient back, adds its share of
+// (g_theta, g_p, g_u) to acc
+__device__ __forceinline__ void sc_atom_bwd(double* xf, double* gf, const double* tr, int at, bool dihedral, double* acc) {
+  const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
+  const double pv[3] = {tr[TR_P], tr[TR_P + 1], tr[TR_P + 2]};
+  const double u[3] = {tr[TR_U], tr[TR_U + 1], tr[TR_U + 2]};
+  const double w[3] = {xf[3 * at] - pv[0], xf[3 * at + 1] - pv[1], xf[3 * at + 2] - pv[2]};
+  const double v[3] = {r0 * w[0] + r3 * w[1] + r6 * w[2], r1 * w[0] + r4 * w[1] + r7 * w[2], r2 * w[0] + r5 * w[1] + r8 * w[2]};
+  xf[3 * at] = pv[0] + v[0]; xf[3 * at + 1] = pv[1] + v[1]; xf[3 * at + 2] = pv[2] + v[2];
+  const double g[3] = {gf[3 * at], gf[3 * at + 1], gf[3 * at + 2]};
+  const double rg[3] = {r0 * g[0] + r3 * g[1] + r6 * g[2], r1 * g[0] + r4 * g[1] + r7 * g[2], r2 * g[0] + r5 * g[1] + r8 * g[2]};
+  double uxw[3];
+  cross3d(u, w, uxw);
+  acc[0] += dot3d(g, uxw);
+  acc[1] += g[0] - rg[0]; acc[2] += g[1] - rg[1]; acc[3] += g[2] - rg[2];
+  if (dihedral) {
+    double vxg[3];
+    cross3d(v, g, vxg);
+    const double uv = dot3d(u, v), ug = dot3d(u, g), s = tr[TR_S], oc = 1.0 - tr[TR_C];
+#pragma unroll
+    for (int q = 0; q < 3; q++) acc[4 + q] += s * vxg[q] + oc * (uv * g[q] + ug * v[q]);
+  }
+  gf[3 * at] = rg[0]; gf[3 * at + 1] = rg[1]; gf[3 * at + 2] = rg[2];
+}
+
+// what the sums of a step do to the pivot, the axis atoms and the measured atoms (xf holds the state BEFORE the step); returns
+// dL/dtarget.  sd = sin(target - measured) kept by the forward pass, flag: see sc_layout
+__device__ __forceinline__ double sc_finish_step(const double* xf, double* gf, int kind, int a, int b, int c, int d, const double* sum, double sd,
+                                                 int flag) {
+  gf[3 * b] += sum[1]; gf[3 * b + 1] += sum[2]; gf[3 * b + 2] += sum[3];
+  const double g_theta = sum[0];
+  if (kind <= kSideAngle) {
+    double ba[3], bc[3], cr[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { ba[q] = xf[3 * a + q] - xf[3 * b + q]; bc[q] = xf[3 * c + q] - xf[3 * b + q]; }
+    const double na2 = dot3d(ba, ba), nc2 = dot3d(bc, bc), inv = rsqrt(na2 * nc2);
+    const double t = dot3d(ba, bc) * inv;
+    cross3d(ba, bc, cr);
+    const double sm2 = dot3d(cr, cr) * inv * inv;                                   // sin^2 of the measured angle
+    const double sgn = flag == 1 ? 1.0 : flag == 2 ? -1.0 : sd > 0.0 ? 1.0 : sd < 0.0 ? -1.0 : 0.0;     // d|x|/dx
+    const double g_target = sgn * g_theta;
+    if (t >= -1.0 && t <= 1.0 && sm2 >= kStraightEps) {
+      const double gt = g_target * rsqrt(sm2);           // dL/dcos = (-sgn g_theta) (-1 / sin(measured))
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const double da = gt * (bc[q] * inv - t * ba[q] / na2), dc = gt * (ba[q] * inv - t * bc[q] / nc2);
+        gf[3 * a + q] += da; gf[3 * c + q] += dc; gf[3 * b + q] -= da + dc;
       }
-      __syncthreads();
+    }
+    return g_target;
+  }
+  // the axis: u = dvec / |dvec|
+  double dv[3];
+  const double gu[3] = {sum[4], sum[5], sum[6]};
+#pragma unroll
+  for (int q = 0; q < 3; q++) dv[q] = xf[3 * c + q] - xf[3 * b + q];
+  const double l2 = dot3d(dv, dv), il = rsqrt(l2), len = l2 * il;
+  const double u[3] = {dv[0] * il, dv[1] * il, dv[2] * il};
+  const double ugu = dot3d(u, gu);
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const double gd = (gu[q] - u[q] * ugu) * il;
+    gf[3 * c + q] += gd; gf[3 * b + q] -= gd;
+  }
+  // the measured dihedral m = atan2(p1, p2): dL/dm = -g_theta, pulled back by hand through layers.py:800-808
+  double b1[3], b3[3], c1[3], c2[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) { b1[q] = xf[3 * b + q] - xf[3 * a + q]; b3[q] = xf[3 * d + q] - xf[3 * c + q]; }
+  cross3d(dv, b3, c1);
+  cross3d(b1, dv, c2);
+  const double qd = dot3d(b1, c1), p1 = qd * len, p2 = dot3d(c1, c2);
+  const double den = p1 * p1 + p2 * p2;
+  if (den > 0.0) {
+    const double gm = -g_theta / den;
+    const double gp1 = gm * p2, gp2 = -gm * p1;
+    const double gq = gp1 * len, glen = gp1 * qd * il;
+    double gb1[3], gb2[3], gb3[3], gc1[3], gc2[3], tmp[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      gb1[q] = gq * c1[q];
+      gc1[q] = gq * b1[q] + gp2 * c2[q];
+      gc2[q] = gp2 * c1[q];
+      gb2[q] = glen * dv[q];
+    }
+    cross3d(b3, gc1, tmp);   // c1 = b2 x b3:  g_b2 += b3 x g_c1,  g_b3 = g_c1 x b2
+#pragma unroll
+    for (int q = 0; q < 3; q++) gb2[q] += tmp[q];
+    cross3d(gc1, dv, gb3);
+    cross3d(dv, gc2, tmp);   // c2 = b1 x b2:  g_b1 += b2 x g_c2,  g_b2 += g_c2 x b1
+#pragma unroll
+    for (int q = 0; q < 3; q++) gb1[q] += tmp[q];
+    cross3d(gc2, b1, tmp);
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      gb2[q] += tmp[q];
+      gf[3 * a + q] -= gb1[q];
+      gf[3 * b + q] += gb1[q] - gb2[q];
+      gf[3 * c + q] += gb2[q] - gb3[q];
+      gf[3 * d + q] += gb3[q];
+    }
+  }
+  return g_theta;
+}
+
+// backbone steps [k0, k1) in reverse, by the whole CTA
+__device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t f, int k0, int k1, double* xf, double* gf, const double* tg,
+                                                      const unsigned char* flags, double* tr, double* red) {
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  if (k1 <= k0) return;
+  int4 o0 = __ldg(p.ops + 3 * (k1 - 1)), o1 = __ldg(p.ops + 3 * (k1 - 1) + 1), o2 = __ldg(p.ops + 3 * (k1 - 1) + 2);
+  if (tid == 0) sc_publish_inverse(xf, tg, tr, k1 - 1, o0.x, o0.z, o0.w);
+  __syncthreads();
+  for (int k = k1 - 1; k >= k0; k--) {
+    int4 n0 = o0, n1 = o1, n2 = o2;
+    if (k > k0) { n0 = __ldg(p.ops + 3 * k - 3); n1 = __ldg(p.ops + 3 * k - 2); n2 = __ldg(p.ops + 3 * k - 1); }
+    const int kind = o0.x;
+    const bool dihedral = kind >= kCentralDihedral;
+    const int c0 = o1.w - o1.z, total = c0 + (o2.y - o2.x);
+    const int busy_warps = min(nth >> 5, (total + 31) >> 5);       // warps past this have no moving atom of this step
+    if (warp < busy_warps) {
       double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      {
-        const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
-        const double pv[3] = {tr[TR_P], tr[TR_P + 1], tr[TR_P + 2]};
-        const double u[3] = {tr[TR_U], tr[TR_U + 1], tr[TR_U + 2]};
-        const double s = tr[TR_S], oc = 1.0 - tr[TR_C];
-        const int n0 = o1.w - o1.z, total = n0 + (o2.y - o2.x);
-        for (int e = tid; e < total; e += nth) {
-          const int at = e < n0 ? o1.z + e : o2.x + (e - n0);
-          const double w[3] = {xf[3 * at] - pv[0], xf[3 * at + 1] - pv[1], xf[3 * at + 2] - pv[2]};
-          const double v[3] = {r0 * w[0] + r3 * w[1] + r6 * w[2], r1 * w[0] + r4 * w[1] + r7 * w[2], r2 * w[0] + r5 * w[1] + r8 * w[2]};
-          xf[3 * at] = pv[0] + v[0]; xf[3 * at + 1] = pv[1] + v[1]; xf[3 * at + 2] = pv[2] + v[2];      // the state before the step
-          const double g[3] = {gf[3 * at], gf[3 * at + 1], gf[3 * at + 2]};
-          const double rg[3] = {r0 * g[0] + r3 * g[1] + r6 * g[2], r1 * g[0] + r4 * g[1] + r7 * g[2], r2 * g[0] + r5 * g[1] + r8 * g[2]};
-          double uxw[3];
-          cross3d(u, w, uxw);
-          acc[0] += dot3d(g, uxw);
-          acc[1] += g[0] - rg[0]; acc[2] += g[1] - rg[1]; acc[3] += g[2] - rg[2];
-          if (dihedral) {
-            double vxg[3];
-            cross3d(v, g, vxg);
-            const double uv = dot3d(u, v), ug = dot3d(u, g);
-#pragma unroll
-            for (int q = 0; q < 3; q++) acc[4 + q] += s * vxg[q] + oc * (uv * g[q] + ug * v[q]);
-          }
-          gf[3 * at] = rg[0]; gf[3 * at + 1] = rg[1]; gf[3 * at + 2] = rg[2];
-        }
-      }
+      for (int e = tid; e < total; e += nth) sc_atom_bwd(xf, gf, tr, e < c0 ? o1.z + e : o2.x + (e - c0), dihedral, acc);
 #pragma unroll
       for (int q = 0; q < kRed; q++) {
+        if (q >= 4 && !dihedral) break;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
       }
@@ -329,96 +487,74 @@ __global__ void __launch_bounds__(128) sidechain_bwd_kernel(const ScParams p) {
 #pragma unroll
         for (int q = 0; q < kRed; q++) red[warp * kRed + q] = acc[q];
       }
-      __syncthreads();
-      if (tid == 0) {
-        double sum[kRed];
-#pragma unroll
-        for (int q = 0; q < kRed; q++) {
-          double v = 0.0;
-          for (int w = 0; w < n_warps; w++) v += red[w * kRed + q];
-          sum[q] = v;
-        }
-        const int src = input_of(kind);
-        const double target = (double)__ldg(p.in[src] + f * p.cols[src] + o1.y);
-        gf[3 * b] += sum[1]; gf[3 * b + 1] += sum[2]; gf[3 * b + 2] += sum[3];
-        const double g_theta = sum[0];
-        double g_target;
-        if (!dihedral) {
-          double ba[3], bc[3];
-#pragma unroll
-          for (int q = 0; q < 3; q++) { ba[q] = xf[3 * a + q] - xf[3 * b + q]; bc[q] = xf[3 * c + q] - xf[3 * b + q]; }
-          const double na2 = dot3d(ba, ba), nc2 = dot3d(bc, bc), nn = sqrt(na2) * sqrt(nc2);
-          const double t = dot3d(ba, bc) / nn;
-          const double tc = fmin(fmax(t, -1.0), 1.0);
-          const double diff = target - acos(tc);
-          const double sgn = diff > 0.0 ? 1.0 : diff < 0.0 ? -1.0 : 0.0;                     // d|x|/dx
-          g_target = sgn * g_theta;
-          const double one_m = 1.0 - tc * tc;
-          if (t >= -1.0 && t <= 1.0 && one_m >= kStraightEps) {
-            const double gt = g_target / sqrt(one_m);          // dL/dt = (-sgn g_theta) (-1 / sqrt(1 - t^2))
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-              const double da = gt * (bc[q] / nn - t * ba[q] / na2), dc = gt * (ba[q] / nn - t * bc[q] / nc2);
-              gf[3 * a + q] += da; gf[3 * c + q] += dc; gf[3 * b + q] -= da + dc;
-            }
-          }
-        } else {
-          g_target = g_theta;
-          // the axis: u = dvec / |dvec|
-          double dv[3], gu[3] = {sum[4], sum[5], sum[6]};
-#pragma unroll
-          for (int q = 0; q < 3; q++) dv[q] = xf[3 * c + q] - xf[3 * b + q];
-          const double len = sqrt(dot3d(dv, dv));
-          const double u[3] = {dv[0] / len, dv[1] / len, dv[2] / len};
-          const double ugu = dot3d(u, gu);
-#pragma unroll
-          for (int q = 0; q < 3; q++) {
-            const double gd = (gu[q] - u[q] * ugu) / len;
-            gf[3 * c + q] += gd; gf[3 * b + q] -= gd;
-          }
-          // the measured dihedral m = atan2(p1, p2): dL/dm = -g_theta, pulled back by hand through layers.py:800-808
-          double b1[3], b2[3], b3[3], c1[3], c2[3];
-#pragma unroll
-          for (int q = 0; q < 3; q++) { b1[q] = xf[3 * b + q] - xf[3 * a + q]; b2[q] = dv[q]; b3[q] = xf[3 * d + q] - xf[3 * c + q]; }
-          cross3d(b2, b3, c1);
-          cross3d(b1, b2, c2);
-          const double qd = dot3d(b1, c1), p1 = qd * len, p2 = dot3d(c1, c2);
-          const double den = p1 * p1 + p2 * p2;
-          if (den > 0.0) {
-            const double gm = -g_theta;
-            const double gp1 = gm * p2 / den, gp2 = -gm * p1 / den;
-            const double gq = gp1 * len, glen = gp1 * qd;
-            double gb1[3], gb2[3], gb3[3], gc1[3], gc2[3], tmp[3];
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-              gb1[q] = gq * c1[q];
-              gc1[q] = gq * b1[q] + gp2 * c2[q];
-              gc2[q] = gp2 * c1[q];
-              gb2[q] = glen * b2[q] / len;
-            }
-            cross3d(b3, gc1, tmp);   // c1 = b2 x b3:  g_b2 += b3 x g_c1,  g_b3 = g_c1 x b2
-#pragma unroll
-            for (int q = 0; q < 3; q++) gb2[q] += tmp[q];
-            cross3d(gc1, b2, gb3);
-            cross3d(b2, gc2, tmp);   // c2 = b1 x b2:  g_b1 += b2 x g_c2,  g_b2 += g_c2 x b1
-#pragma unroll
-            for (int q = 0; q < 3; q++) gb1[q] += tmp[q];
-            cross3d(gc2, b1, tmp);
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-              gb2[q] += tmp[q];
-              gf[3 * a + q] -= gb1[q];
-              gf[3 * b + q] += gb1[q] - gb2[q];
-              gf[3 * c + q] += gb2[q] - gb3[q];
-              gf[3 * d + q] += gb3[q];
-            }
-          }
-        }
-        float* gdst = p.gin[src];
-        if (gdst) gdst[f * p.cols[src] + o1.y] = (float)g_target;
-      }
-      __syncthreads();
     }
+    __syncthreads();
+    if (tid == 0) {
+      double sum[kRed];
+#pragma unroll
+      for (int q = 0; q < kRed; q++) {
+        double v = 0.0;
+        for (int w = 0; w < busy_warps; w++) v += red[w * kRed + q];
+        sum[q] = v;
+      }
+      const double g_target = sc_finish_step(xf, gf, kind, o0.y, o0.z, o0.w, o1.x, sum, tg[2 * k], flags[k]);
+      const int src = input_of(kind);
+      float* gdst = p.gin[src];
+      if (gdst) gdst[f * p.cols[src] + o1.y] = (float)g_target;
+      if (k > k0) sc_publish_inverse(xf, tg, tr, k - 1, n0.x, n0.z, n0.w);
+    }
+    __syncthreads();
+    o0 = n0; o1 = n1; o2 = n2;
+  }
+}
+
+// side-chain steps of one kind in reverse, one thread per residue with a side chain
+template <bool DIH>
+__device__ __forceinline__ void sc_side_steps_bwd(const ScParams& p, int64_t f, int k_base, double* xf, double* gf, const double* tg,
+                                                  const unsigned char* flags) {
+  const int kind = DIH ? kSideDihedral : kSideAngle;
+  const int src = input_of(kind);
+  float* gdst = p.gin[src];
+  for (int ri = threadIdx.x; ri < p.n_res_side; ri += blockDim.x) {
+    const int4 r = __ldg(p.res + ri);
+    const int end = r.y + r.z + 1;
+    const int k0 = k_base + (DIH ? r.w : r.y - p.n_bb);
+    const int steps = DIH ? r.z : r.z + 1;
+    for (int q = steps - 1; q >= 0; q--) {
+      const int k = k0 + q;
+      const int a = sc_chain(r, q), b = sc_chain(r, q + 1), c = sc_chain(r, q + 2), d = DIH ? sc_chain(r, q + 3) : -1;
+      double tr[TR_N];
+      sc_publish_inverse(xf, tg, tr, k, kind, b, c);
+      double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int at = r.y + q; at < end; at++) sc_atom_bwd(xf, gf, tr, at, DIH, acc);
+      const double g_target = sc_finish_step(xf, gf, kind, a, b, c, d, acc, tg[2 * k], flags[k]);
+      if (gdst) gdst[f * p.cols[src] + k - k_base] = (float)g_target;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) sidechain_bwd_kernel(const ScParams p) {
+  extern __shared__ double sc_smem[];
+  double* xf = sc_smem;
+  double* gf = xf + 3 * (size_t)p.n_atoms;
+  double* tg = gf + 3 * (size_t)p.n_atoms;
+  double* tr = tg + 2 * (size_t)p.n_ops;
+  double* red = tr + TR_N;                 // (blockDim / 32) x kRed
+  unsigned char* flags = reinterpret_cast<unsigned char*>(red + 4 * kRed);
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int k_cd = p.n_ca + p.n_side;
+  for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    __syncthreads();
+    sc_layout(p, f, xf, tg, flags);
+    sc_forward<true>(p, xf, tg, tr);
+    const float* gsrc = p.gout + f * (int64_t)(3 * p.n_atoms);
+    for (int e = tid; e < 3 * p.n_atoms; e += nth) gf[e] = (double)__ldg(gsrc + e);
+    __syncthreads();
+    sc_side_steps_bwd<true>(p, f, k_cd + p.n_cd, xf, gf, tg, flags);
+    sc_backbone_steps_bwd(p, f, k_cd, k_cd + p.n_cd, xf, gf, tg, flags, tr, red);
+    sc_side_steps_bwd<false>(p, f, p.n_ca, xf, gf, tg, flags);
+    sc_backbone_steps_bwd(p, f, 0, p.n_ca, xf, gf, tg, flags, tr, red);
     // the planar layout: x of backbone atom k = sum of the bonds before it, x of a side-chain atom = x of its CA, y = running sum
     // of its own chain's bonds (layers.py:593-628)
     float* g_sd = p.gin[3];
@@ -494,11 +630,13 @@ int sidechain_plan_create(int64_t n_res, const int32_t* counts, SidechainPlan** 
   // the device copy is optional: without a GPU the plan can still be inspected (emk_sidechain_plan_info / _ops)
   int dev = -1;
   if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0) {
-    const size_t n_ints = pl->ops.size() + pl->side.size();
+    const size_t n_ints = pl->ops.size() + pl->side.size() + pl->res.size();
     int* mem = nullptr;
     cudaError_t e = cudaMalloc(&mem, n_ints * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(mem, pl->ops.data(), pl->ops.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(mem + pl->ops.size(), pl->side.data(), pl->side.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(mem + pl->ops.size() + pl->side.size(), pl->res.data(), pl->res.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       if (mem) cudaFree(mem);
       cudaGetLastError();
@@ -551,6 +689,8 @@ static int fill_params(const char* who, const SidechainPlan* pl, const float* co
   }
   p->ops = reinterpret_cast<const int4*>(pl->d_mem);
   p->side = reinterpret_cast<const int4*>(pl->d_mem + pl->ops.size());
+  p->res = reinterpret_cast<const int4*>(pl->d_mem + pl->ops.size() + pl->side.size());
+  p->n_res_side = (int)(pl->res.size() / 4); p->n_ca = pl->n_ca; p->n_cd = pl->n_cd;
   p->frames = frames; p->n_bb = pl->n_bb; p->n_side = pl->n_side; p->n_atoms = pl->n_atoms; p->n_ops = pl->n_ops;
   return EMK_OK;
 }
@@ -566,7 +706,7 @@ int sidechain_backmap_device(const SidechainPlan* pl, const float* const* in, in
   if (rc) return rc;
   if (frames == 0) return EMK_OK;
   EMK_REQUIRE(out, EMK_E_NULL, "emk_sidechain_backmap: NULL output");
-  const size_t smem = (3 * (size_t)pl->n_atoms + TR_N) * sizeof(double);
+  const size_t smem = (3 * (size_t)pl->n_atoms + 2 * (size_t)pl->n_ops + TR_N) * sizeof(double);
   EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap: %d atoms need %zu bytes of shared memory per frame (limit 227 KB)", pl->n_atoms, smem);
   p.out = out;
   static bool cfg[kMaxDevices] = {false};
@@ -582,7 +722,7 @@ int sidechain_backmap_bwd_device(const SidechainPlan* pl, const float* const* in
   if (rc) return rc;
   if (frames == 0) return EMK_OK;
   EMK_REQUIRE(grad_out, EMK_E_NULL, "emk_sidechain_backmap_bwd: NULL grad_out");
-  const size_t smem = (6 * (size_t)pl->n_atoms + pl->n_ops + TR_N + 4 * kRed) * sizeof(double);
+  const size_t smem = (6 * (size_t)pl->n_atoms + 2 * (size_t)pl->n_ops + TR_N + 4 * kRed) * sizeof(double) + (((size_t)pl->n_ops + 15) & ~(size_t)15);
   EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap_bwd: %d atoms / %d steps need %zu bytes of shared memory per frame (limit 227 KB)",
               pl->n_atoms, pl->n_ops, smem);
   p.gout = grad_out;
