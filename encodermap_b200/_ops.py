@@ -513,6 +513,15 @@ def gather_atoms_raw(xyz: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gather_atoms_bwd_raw(grad_out: torch.Tensor, index: torch.Tensor, n_atoms: int) -> torch.Tensor:
+    require_cuda(grad_out, "grad_out")
+    g = f32c(grad_out)
+    gx = _empty_like_shape(g, (g.shape[0], n_atoms, 3))
+    with torch.cuda.device(g.device):
+        check(_lib.lib().emk_dl_gather_atoms_bwd(DL(g), DL(index), DL(gx), stream_of(g)))
+    return gx
+
+
 class GatherAtoms(torch.autograd.Function):
     """tf.gather(params=inputs, indices=..., axis=1) of PairwiseDistances (reference models/layers.py:1260-1265)."""
 
@@ -525,11 +534,7 @@ class GatherAtoms(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (index,) = ctx.saved_tensors
-        g = f32c(grad_out)
-        gx = _empty_like_shape(g, (g.shape[0], ctx.n_atoms, 3))
-        with torch.cuda.device(g.device):
-            check(_lib.lib().emk_dl_gather_atoms_bwd(DL(g), DL(index), DL(gx), stream_of(g)))
-        return gx, None
+        return gather_atoms_bwd_raw(grad_out, index, ctx.n_atoms), None
 
 
 def sidechain_pairwise_indices(counts, start=None, stop=None, step=None):

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(128) sidechain_fwd_kernel(const ScParams p) {
 //   then G_b += g_p;  through the normalisation g_d = (g_u - u (u . g_u)) / |d| to atoms c (+) and b (-);
 //   dL/dtarget = +-g_theta and -+g_theta dm/dX to the three / four measured atoms.
 constexpr int kRed = 7;
+constexpr int kScThreads = 128;     // threads per frame (>= 64: thread 32 prepares the next rotation of the backward pass)
 
 // the rotation of step k seen from the state AFTER it (pivot and axis atoms are fixed points of the rotation)
 __device__ __forceinline__ void sc_publish_inverse(const double* xf, const double* tg, double* tr, int k, int kind, int b, int c) {
@@ -501,7 +502,9 @@ __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t
       const int src = input_of(kind);
       float* gdst = p.gin[src];
       if (gdst) gdst[f * p.cols[src] + o1.y] = (float)g_target;
-      if (k > k0) sc_publish_inverse(xf, tg, tr, k - 1, n0.x, n0.z, n0.w);
+    } else if (tid == 32 && k > k0) {
+      // meanwhile another warp prepares the rotation of the next (earlier) step: it only needs the restored coordinates
+      sc_publish_inverse(xf, tg, tr, k - 1, n0.x, n0.z, n0.w);
     }
     __syncthreads();
     o0 = n0; o1 = n1; o2 = n2;
@@ -534,14 +537,14 @@ __device__ __forceinline__ void sc_side_steps_bwd(const ScParams& p, int64_t f, 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) sidechain_bwd_kernel(const ScParams p) {
+__global__ void __launch_bounds__(kScThreads) sidechain_bwd_kernel(const ScParams p) {
   extern __shared__ double sc_smem[];
   double* xf = sc_smem;
   double* gf = xf + 3 * (size_t)p.n_atoms;
   double* tg = gf + 3 * (size_t)p.n_atoms;
   double* tr = tg + 2 * (size_t)p.n_ops;
   double* red = tr + TR_N;                 // (blockDim / 32) x kRed
-  unsigned char* flags = reinterpret_cast<unsigned char*>(red + 4 * kRed);
+  unsigned char* flags = reinterpret_cast<unsigned char*>(red + (kScThreads / 32) * kRed);
   const int tid = threadIdx.x, nth = blockDim.x;
   const int k_cd = p.n_ca + p.n_side;
   for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
@@ -722,14 +725,14 @@ int sidechain_backmap_bwd_device(const SidechainPlan* pl, const float* const* in
   if (rc) return rc;
   if (frames == 0) return EMK_OK;
   EMK_REQUIRE(grad_out, EMK_E_NULL, "emk_sidechain_backmap_bwd: NULL grad_out");
-  const size_t smem = (6 * (size_t)pl->n_atoms + 2 * (size_t)pl->n_ops + TR_N + 4 * kRed) * sizeof(double) + (((size_t)pl->n_ops + 15) & ~(size_t)15);
+  const size_t smem = (6 * (size_t)pl->n_atoms + 2 * (size_t)pl->n_ops + TR_N + (kScThreads / 32) * kRed) * sizeof(double) + (((size_t)pl->n_ops + 15) & ~(size_t)15);
   EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap_bwd: %d atoms / %d steps need %zu bytes of shared memory per frame (limit 227 KB)",
               pl->n_atoms, pl->n_ops, smem);
   p.gout = grad_out;
   for (int k = 0; k < 6; k++) p.gin[k] = grad_in[k];
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(sidechain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  sidechain_bwd_kernel<<<frames_grid(frames, smem), 128, smem, st>>>(p);
+  sidechain_bwd_kernel<<<frames_grid(frames, smem), kScThreads, smem, st>>>(p);
   return launch_status("sidechain_bwd_kernel");
 }
 

@@ -344,6 +344,82 @@ def back_map(distances, angles, dihedrals):
     return op(_f32(distances), _f32(angles), _f32(dihedrals))
 
 
+_SIDECHAIN_PLANS = {}
+
+
+def _sidechain_plan(counts, device):
+    key = (tuple(int(c) for c in counts), str(device))
+    plan = _SIDECHAIN_PLANS.get(key)
+    if plan is None:
+        plan = _ops.SidechainPlan(key[0], device)
+        _SIDECHAIN_PLANS[key] = plan
+    return plan
+
+
+def back_map_with_sidechains(feature_description, inputs):
+    """``BackMapLayerWithSidechains.call`` (models/layers.py:533-843) as one differentiable op: the six inputs (central
+    distances / angles / dihedrals, side distances / angles / dihedrals) -> (batch, n_atoms, 3); one forward and one backward
+    kernel instead of a dozen TensorFlow kernels per bond angle and dihedral."""
+    _require_tf()
+    info = feature_description[-1]
+    counts = [int(info[k]) for k in sorted(info.keys())]
+    n_atoms = 3 * len(counts) + sum(c + 1 for c in counts if c > 0)
+
+    @tf.custom_gradient
+    def op(*ins):
+        def run(*ts):
+            return (_ops.sidechain_backmap_raw(_sidechain_plan(counts, ts[0].device), ts),)
+
+        (xyz,) = _eager(run, list(ins), 1)
+        xyz = tf.reshape(xyz, [tf.shape(ins[0])[0], n_atoms, 3])
+
+        def backward(g):
+            def run_b(*ts):
+                return tuple(_ops.sidechain_backmap_bwd_raw(_sidechain_plan(counts, ts[0].device), ts[:6], ts[6]))
+
+            grads = _eager(run_b, list(ins) + [g], 6)
+            return tuple(tf.reshape(gr, tf.shape(t)) for gr, t in zip(grads, ins))
+
+        return xyz, backward
+
+    return op(*[_f32(t) for t in inputs])
+
+
+def gathered_pairwise_distances(inputs, indices):
+    """``PairwiseDistances.call`` with reconstructed side chains (models/layers.py:1260-1265): tf.gather of the selected atoms +
+    flat pairwise distances, both in libemk."""
+    _require_tf()
+    idx_host = [int(i) for i in indices]
+    n_sel = len(idx_host)
+    inputs = _f32(inputs)
+    n_atoms = int(inputs.shape[1])
+    if n_sel and (min(idx_host) < 0 or max(idx_host) >= n_atoms):
+        raise IndexError(f"PairwiseDistances: atom index {max(idx_host)} outside the {n_atoms} atoms of the input")
+
+    @tf.custom_gradient
+    def op(x):
+        def run(t):
+            index = torch.as_tensor(idx_host, dtype=torch.int32, device=t.device)
+            return (_ops.pairwise_dist_raw(_ops.gather_atoms_raw(t, index), False, True, None, None, None),)
+
+        (out,) = _eager(run, [x], 1)
+        out = tf.reshape(out, [tf.shape(x)[0], n_sel * (n_sel - 1) // 2])
+
+        def backward(g):
+            def run_b(t, g_):
+                index = torch.as_tensor(idx_host, dtype=torch.int32, device=t.device)
+                sel = _ops.gather_atoms_raw(t, index)
+                g_sel = _ops.pairwise_dist_bwd_raw(sel, g_, False, True, None, None, None)
+                return (_ops.gather_atoms_bwd_raw(g_sel, index, t.shape[1]),)
+
+            (gx,) = _eager(run_b, [x, g], 1)
+            return tf.reshape(gx, tf.shape(x))
+
+        return out, backward
+
+    return op(inputs)
+
+
 # ---- encodermap/encodermap_tf1/backmapping.py, encodermap/misc/backmapping.py ---------------------------------------------
 def chain_in_plane(lengths, angles):
     """``encodermap.encodermap_tf1.backmapping.chain_in_plane`` (:97-119); ``lengths`` (1,n-1) or (b,n-1)."""
@@ -486,8 +562,7 @@ def _layer_calls():
 
     def pairwise_distances_call(self, inputs):
         if getattr(self.p, "reconstruct_sidechains", False):
-            # side-chain gather (layers.py:1260-1265) is outside the hot path: the reference's own TF gather feeds the kernel
-            return pairwise_dist(tf.gather(params=inputs, indices=self.indices, axis=1, batch_dims=0), flat=True)
+            return gathered_pairwise_distances(inputs, self.indices)      # the gather of layers.py:1260-1265 and the distances
         return pairwise_distances(inputs, self.p.cartesian_pwd_start, self.p.cartesian_pwd_stop, self.p.cartesian_pwd_step)
 
     def back_map_call(self, inputs):
@@ -497,7 +572,11 @@ def _layer_calls():
             raise ValueError(f"BackMapLayer(left_split={self.left_split}, right_split={self.right_split}) does not match {n} atoms")
         return back_map(distances, angles, dihedrals)
 
-    return {"PeriodicInput": periodic_input_call, "PairwiseDistances": pairwise_distances_call, "BackMapLayer": back_map_call}
+    def back_map_with_sidechains_call(self, inputs):
+        return back_map_with_sidechains(self.feature_description, inputs)
+
+    return {"PeriodicInput": periodic_input_call, "PairwiseDistances": pairwise_distances_call, "BackMapLayer": back_map_call,
+            "BackMapLayerWithSidechains": back_map_with_sidechains_call}
 
 
 def install(enable_layers: bool = True, require_gpu_env: bool = True) -> dict:

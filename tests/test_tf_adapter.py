@@ -73,6 +73,7 @@ def test_restated_callers_match_reference_bodies(tf_env):
     dist = rng.uniform(0.13, 0.15, (b, n_atoms - 1))
     w0 = rng.normal(size=(2 * n_atoms - 5, 2)) * 0.3
     pair = np.abs(rng.normal(size=(b, 15)))
+    side_xyz = np.random.default_rng(4).normal(size=(2, 17, 3))
     results = {}
     for mode in ("reference", "restated"):
         mods = ref_callers_tf.build(tf, mode)
@@ -104,6 +105,12 @@ def test_restated_callers_match_reference_bodies(tf_env):
         out["backmap"] = xyz.numpy()
         out["pairwise"] = layers.PairwiseDistances(p, "pd")(xyz).numpy()
         out["periodic_input"] = layers.PeriodicInput(ref_callers_tf._P(periodicity=360.0), "pi")(tf.convert_to_tensor(dih * 50)).numpy()
+        # PairwiseDistances with reconstructed side chains: the atom selection of its constructor and the gather of its call
+        ps = ref_callers_tf._P(cartesian_pwd_start=1, cartesian_pwd_step=3, reconstruct_sidechains=True,
+                               sidechain_info={-1: {1: 2, 2: 0, 3: 1, 4: 0}})
+        pds = layers.PairwiseDistances(ps, "pds")
+        out["side_indices"] = np.asarray(pds.indices)
+        out["side_pairwise"] = pds(tf.convert_to_tensor(side_xyz)).numpy()
         results[mode] = out
         ref_callers_tf.remove()
     for key, ref in results["reference"].items():
@@ -265,6 +272,42 @@ def test_tf_adapter_adc_branch_on_gpu(tf_gpu):
     lref, gref = O.sigmoid_loss_and_grad(pairs64.numpy(), z0, float("inf"), p.cartesian_dist_sig_parameters)
     np.testing.assert_allclose(lc.item(), 2.0 * lref.item(), rtol=1e-5)
     assert _relnorm(gz.cpu().numpy(), 2.0 * gref.numpy()) < 5e-5
+
+
+@pytest.mark.gpu
+def test_tf_adapter_sidechain_branch_on_gpu(tf_gpu):
+    """The Cartesian branch with reconstructed side chains through the reference's layer classes (calls rebound by install()):
+    BackMapLayerWithSidechains -> PairwiseDistances (gathered atoms) -> mean |difference|; gradients w.r.t. variables added to
+    the angle and dihedral inputs.  The reference's own BackMapLayerWithSidechains.call is a placeholder that raises here."""
+    tf, adapter, mods = tf_gpu
+    layers = mods["encodermap.models.layers"]
+    rng = np.random.default_rng(11)
+    counts = [2, 0, 4, 1, 3, 0]
+    fd = {-1: {k + 1: c for k, c in enumerate(counts)}}
+    n_res, n_side, b = len(counts), sum(c + 1 for c in counts if c > 0), 7
+    vals = [rng.uniform(0.13, 0.16, (b, 3 * n_res - 1)), rng.uniform(1.85, 2.25, (b, 3 * n_res - 2)), rng.uniform(-pi, pi, (b, 3 * n_res - 3)),
+            rng.uniform(0.13, 0.19, (b, n_side)), rng.uniform(1.8, 2.2, (b, n_side)), rng.uniform(-pi, pi, (b, sum(counts)))]
+    vals = [v.astype(np.float32) for v in vals]
+    p = ref_callers_tf._P(cartesian_pwd_start=1, cartesian_pwd_step=3, reconstruct_sidechains=True, sidechain_info=fd)
+    offs0 = [np.zeros((1, v.shape[1]), np.float32) for v in vals]
+    offs = [tf.Variable(o) for o in offs0]
+    pd_layer = layers.PairwiseDistances(p, "pairwise")
+    n_sel = len(pd_layer.indices)
+    target = np.abs(rng.normal(size=(b, n_sel * (n_sel - 1) // 2))).astype(np.float32)
+    with tf.GradientTape() as tape:
+        xyz = layers.BackMapLayerWithSidechains(fd)(tuple(tf.convert_to_tensor(v) + o for v, o in zip(vals, offs)))
+        pw = pd_layer(xyz)
+        loss = tf.reduce_mean(tf.abs(pw - tf.convert_to_tensor(target)))
+    grads = tape.gradient(loss, offs)
+    o64 = [torch.zeros(1, v.shape[1], dtype=torch.float64, requires_grad=True) for v in vals]
+    xyz64 = O.backmap_with_sidechains(counts, [torch.from_numpy(v).double() + o for v, o in zip(vals, o64)])
+    pw64 = O.pairwise_dist(xyz64[:, torch.as_tensor(O.sidechain_pairwise_indices(counts, 1, None, 3))], flat=True)
+    l64 = (pw64 - torch.from_numpy(target).double()).abs().mean()
+    l64.backward()
+    assert np.abs(xyz.detach().cpu().numpy() - xyz64.detach().numpy()).max() < 1e-4      # nm
+    np.testing.assert_allclose(loss.item(), l64.item(), rtol=1e-5)
+    for g, o in zip(grads, o64):
+        assert _relnorm(g.cpu().numpy(), o.grad.numpy()) < 5e-5
 
 
 @pytest.mark.gpu

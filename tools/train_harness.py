@@ -130,6 +130,50 @@ class ADCStep(nn.Module):
         return dihedral_loss + angle_loss + cartesian_loss + cart_dist + center + reg
 
 
+class ADCSidechainStep(nn.Module):
+    """The ADC model with reconstructed side chains (reference models/models.py:704-760, 935-944): encoder over the periodic
+    embeddings of backbone angles, backbone dihedrals and side-chain dihedrals; decoder back to those plus the side-chain angles;
+    BackMapLayerWithSidechains on (input backbone distances, decoded angles, decoded dihedrals, input side distances, decoded
+    side angles, decoded side dihedrals); PairwiseDistances on the gathered atoms of input and output; the ADC losses."""
+
+    def __init__(self, counts, p: ADCParameters):
+        super().__init__()
+        from encodermap_b200.models.layers import BackMapLayerWithSidechains
+
+        self.p = p
+        fd = {-1: {k + 1: int(c) for k, c in enumerate(counts)}}
+        p.reconstruct_sidechains, p.sidechain_info = True, fd
+        self.backmap = BackMapLayerWithSidechains(fd)
+        n_res = len(counts)
+        self.sizes = [3 * n_res - 2, 3 * n_res - 3, self.backmap.n_sidechains, sum(counts)]   # ca, cdih, sa, sdih
+        d_in = 2 * (self.sizes[0] + self.sizes[1] + self.sizes[3])
+        self.pi = PeriodicInput(p, "inputs")
+        self.encoder_model = mlp([d_in, *p.n_neurons])
+        self.decoder_model = mlp([p.n_neurons[-1], *p.n_neurons[-2::-1], 2 * sum(self.sizes)])
+        self.pairwise = PairwiseDistances(p, "pairwise")
+        self.cart_dist_loss = cartesian_distance_loss(self, p)
+
+    def encoder(self, inputs, training=False):
+        ca, cdih, sdih = inputs
+        return self.encoder_model(torch.cat([self.pi(ca), self.pi(cdih), self.pi(sdih)], dim=1))
+
+    def loss(self, ca, cdih, sa, sdih, cartesians, cd, sd):
+        z = self.encoder((ca, cdih, sdih))
+        y = self.decoder_model(z)
+        sin, cos = torch.split(y, [sum(self.sizes)] * 2, dim=1)
+        o_ca, o_cdih, o_sa, o_sdih = torch.split(torch.atan2(sin, cos), self.sizes, dim=1)
+        back = self.backmap((cd, o_ca, o_cdih, sd, o_sa, o_sdih))
+        inp_pair = self.pairwise(cartesians)
+        out_pair = self.pairwise(back)
+        per = self.p.periodicity
+        dihedral_loss = periodic_distance(cdih, o_cdih, per).mean() + periodic_distance(sdih, o_sdih, per).mean()
+        angle_loss = periodic_distance(ca, o_ca, per).mean() + periodic_distance(sa, o_sa, per).mean()
+        cartesian_loss = (inp_pair - out_pair).abs().mean()
+        reg = sum((m.weight ** 2).sum() for m in self.modules() if isinstance(m, nn.Linear)) * self.p.l2_reg_constant
+        center = (z ** 2).mean() * self.p.center_cost_scale
+        return dihedral_loss + angle_loss + cartesian_loss + self.cart_dist_loss(inp_pair, z) + center + reg
+
+
 def time_steps(model, batch_fn, steps=20, warmup=5, graph=False, grad_sync=None):
     """steps/s of a full training step (forward, backward, [data-parallel gradient averaging], clip, Adam).  graph=True
     captures the whole step in one CUDA graph (encodermap_b200.graph.graphed_train_step) and replays it."""
@@ -211,6 +255,27 @@ def run_all(dev, steps=20):
         "train_cfg2_adc_100res_batch1024_all_atoms_fused_cartesian":
             (lambda: ADCStep(n, ADCParameters(use_backbone_angles=True), fused_cartesian=True), lambda it: (ang, dih, cart, dist)),
     }
+    # the same model with reconstructed side chains on a ubiquitin-sized topology (76 residues, 448 atoms), at the
+    # reference's default batch size and at 1024
+    import numpy as np
+
+    rs = np.random.default_rng(5)
+    counts = [int(c) for c in rs.integers(0, 5, size=76)]
+    counts[0], counts[-1] = 3, 0
+    n_side, n_sdih = sum(c + 1 for c in counts if c > 0), sum(counts)
+    for bs in (256, 1024):
+        s_in = [1.9 + 0.3 * torch.rand(bs, 226, device=dev, generator=g), (torch.rand(bs, 225, device=dev, generator=g) * 2 - 1) * math.pi,
+                1.85 + 0.3 * torch.rand(bs, n_side, device=dev, generator=g), (torch.rand(bs, n_sdih, device=dev, generator=g) * 2 - 1) * math.pi]
+        s_cd = 0.13 + 0.02 * torch.rand(bs, 227, device=dev, generator=g)
+        s_sd = 0.14 + 0.03 * torch.rand(bs, n_side, device=dev, generator=g)
+        with torch.no_grad():
+            from encodermap_b200.models.layers import BackMapLayerWithSidechains
+
+            s_cart = BackMapLayerWithSidechains({-1: {k + 1: c for k, c in enumerate(counts)}})((s_cd, s_in[0], s_in[1], s_sd, s_in[2], s_in[3]))
+        batch = (s_in[0], s_in[1], s_in[2], s_in[3], s_cart, s_cd, s_sd)
+        cases[f"train_adc_sidechains_76res_batch{bs}"] = (
+            lambda: ADCSidechainStep(counts, ADCParameters(cartesian_pwd_start=1, cartesian_pwd_step=3, use_backbone_angles=True, use_sidechains=True)),
+            (lambda bt: (lambda it: bt))(batch))
     for name, (make, batch_fn) in cases.items():
         res = {}
         for mode in ("eager", "cuda_graph"):
