@@ -92,10 +92,11 @@ SIGNATURES = {
     "emk_sidechain_plan_destroy": ([vp], None),
     "emk_sidechain_plan_info": ([vp, c_i64p], C.c_int),
     "emk_sidechain_plan_ops": ([vp, c_i32p], C.c_int),
-    "emk_sidechain_backmap": ([vp, vp, vp, vp, vp, vp, vp, i64, vp, vp], C.c_int),
-    "emk_sidechain_backmap_bwd": ([vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
-    "emk_dl_sidechain_backmap": ([vp, C.POINTER(vp), vp, vp], C.c_int),
-    "emk_dl_sidechain_backmap_bwd": ([vp, C.POINTER(vp), vp, C.POINTER(vp), vp], C.c_int),
+    "emk_sidechain_backmap": ([vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp], C.c_int),
+    "emk_sidechain_backmap_bwd": ([vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+    "emk_dl_sidechain_backmap": ([vp, C.POINTER(vp), vp, vp, vp], C.c_int),
+    "emk_dl_sidechain_backmap_bwd": ([vp, C.POINTER(vp), vp, vp, C.POINTER(vp), vp], C.c_int),
+    "emk_sidechain_saved_size": ([vp], i64),
     "emk_sidechain_pairwise_indices": ([i64, c_i32p, i64, i64, i64, c_i64p], i64),
     "emk_gather_atoms": ([vp, i64, i64, vp, i64, vp, vp], C.c_int),
     "emk_gather_atoms_bwd": ([vp, i64, i64, vp, i64, vp, vp], C.c_int),

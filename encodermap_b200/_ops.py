@@ -439,6 +439,7 @@ class SidechainPlan:
         check(L.emk_sidechain_plan_info(handle, info))
         self.n_atoms, self.n_side, self.n_ops, self.n_residues = (int(v) for v in info[:4])
         self.columns = tuple(int(v) for v in info[4:10])
+        self.saved_size = int(L.emk_sidechain_saved_size(handle))
         self.device = torch.device(device) if device is not None else None
 
     def ops(self):
@@ -470,22 +471,25 @@ def _dl_array(dls):
     return arr
 
 
-def sidechain_backmap_raw(plan: SidechainPlan, inputs) -> torch.Tensor:
+def sidechain_backmap_raw(plan: SidechainPlan, inputs, save_state: bool = False):
+    """-> xyz, or (xyz, saved_state) with save_state=True: the float64 block the backward pass takes over instead of repeating the
+    forward pass (sin / cos of every rotation, the coordinates before rounding)."""
     ts = _six_inputs(plan, inputs)
     out = _empty_like_shape(ts[0], (ts[0].shape[0], plan.n_atoms, 3))
+    saved = _empty_like_shape(ts[0], (ts[0].shape[0], plan.saved_size), torch.float64) if save_state else None
     dls = [DL(t) for t in ts]
     with torch.cuda.device(ts[0].device):
-        check(_lib.lib().emk_dl_sidechain_backmap(plan.handle, _dl_array(dls), DL(out), stream_of(ts[0])))
-    return out
+        check(_lib.lib().emk_dl_sidechain_backmap(plan.handle, _dl_array(dls), DL(out), DL(saved), stream_of(ts[0])))
+    return (out, saved) if save_state else out
 
 
-def sidechain_backmap_bwd_raw(plan: SidechainPlan, inputs, grad_xyz: torch.Tensor, needs=(True,) * 6):
+def sidechain_backmap_bwd_raw(plan: SidechainPlan, inputs, grad_xyz: torch.Tensor, needs=(True,) * 6, saved: Optional[torch.Tensor] = None):
     ts = _six_inputs(plan, inputs)
     g = f32c(grad_xyz)
     grads = [torch.empty_like(t) if need else None for t, need in zip(ts, needs)]
     dls, gdls = [DL(t) for t in ts], [DL(t) for t in grads]
     with torch.cuda.device(ts[0].device):
-        check(_lib.lib().emk_dl_sidechain_backmap_bwd(plan.handle, _dl_array(dls), DL(g), _dl_array(gdls), stream_of(ts[0])))
+        check(_lib.lib().emk_dl_sidechain_backmap_bwd(plan.handle, _dl_array(dls), DL(g), DL(saved), _dl_array(gdls), stream_of(ts[0])))
     return grads
 
 
@@ -495,12 +499,18 @@ class SidechainBackmap(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, *inputs):
         ctx.plan = plan
-        ctx.save_for_backward(*inputs)
-        return sidechain_backmap_raw(plan, inputs)
+        if any(ctx.needs_input_grad[1:]):
+            out, saved = sidechain_backmap_raw(plan, inputs, save_state=True)
+            ctx.save_for_backward(*inputs, saved)
+        else:
+            out = sidechain_backmap_raw(plan, inputs)
+            ctx.save_for_backward(*inputs)
+        return out
 
     @staticmethod
     def backward(ctx, grad_xyz):
-        grads = sidechain_backmap_bwd_raw(ctx.plan, ctx.saved_tensors, grad_xyz, ctx.needs_input_grad[1:])
+        saved = ctx.saved_tensors[6] if len(ctx.saved_tensors) > 6 else None
+        grads = sidechain_backmap_bwd_raw(ctx.plan, ctx.saved_tensors[:6], grad_xyz, ctx.needs_input_grad[1:], saved)
         return (None, *grads)
 
 

@@ -115,8 +115,9 @@ int sidechain_plan_info(const SidechainPlan*, int64_t*);
 int sidechain_plan_ops(const SidechainPlan*, int32_t*);
 const int* sidechain_plan_cols(const SidechainPlan*);
 int sidechain_plan_atoms(const SidechainPlan*);
-int sidechain_backmap_device(const SidechainPlan*, const float* const*, int64_t, float*, cudaStream_t);
-int sidechain_backmap_bwd_device(const SidechainPlan*, const float* const*, int64_t, const float*, float* const*, cudaStream_t);
+int sidechain_backmap_device(const SidechainPlan*, const float* const*, int64_t, float*, double*, cudaStream_t);
+int sidechain_backmap_bwd_device(const SidechainPlan*, const float* const*, int64_t, const float*, const double*, float* const*, cudaStream_t);
+int64_t sidechain_saved_doubles(const SidechainPlan*);
 int64_t sidechain_pairwise_indices(int64_t, const int32_t*, int64_t, int64_t, int64_t, int64_t*);
 int gather_atoms_device(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, cudaStream_t);
 int gather_atoms_bwd_device(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, cudaStream_t);
@@ -957,18 +958,19 @@ int emk_sidechain_plan_ops(const emk_sidechain_plan* plan, int32_t* ops) { retur
 
 int emk_sidechain_backmap(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
                           const float* central_dihedrals, const float* side_distances, const float* side_angles,
-                          const float* side_dihedrals, int64_t frames, float* xyz, void* stream) {
+                          const float* side_dihedrals, int64_t frames, float* xyz, double* saved_state, void* stream) {
   const float* in[6] = {central_distances, central_angles, central_dihedrals, side_distances, side_angles, side_dihedrals};
-  return sidechain_backmap_device(as_plan(plan), in, frames, xyz, as_stream(stream));
+  return sidechain_backmap_device(as_plan(plan), in, frames, xyz, saved_state, as_stream(stream));
 }
 int emk_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
                               const float* central_dihedrals, const float* side_distances, const float* side_angles,
-                              const float* side_dihedrals, int64_t frames, const float* grad_xyz, float* grad_central_distances,
+                              const float* side_dihedrals, int64_t frames, const float* grad_xyz, const double* saved_state,
+                              float* grad_central_distances,
                               float* grad_central_angles, float* grad_central_dihedrals, float* grad_side_distances,
                               float* grad_side_angles, float* grad_side_dihedrals, void* stream) {
   const float* in[6] = {central_distances, central_angles, central_dihedrals, side_distances, side_angles, side_dihedrals};
   float* gin[6] = {grad_central_distances, grad_central_angles, grad_central_dihedrals, grad_side_distances, grad_side_angles, grad_side_dihedrals};
-  return sidechain_backmap_bwd_device(as_plan(plan), in, frames, grad_xyz, gin, as_stream(stream));
+  return sidechain_backmap_bwd_device(as_plan(plan), in, frames, grad_xyz, saved_state, gin, as_stream(stream));
 }
 
 static int sidechain_views(const char* who, const emk_sidechain_plan* plan, const DLManagedTensor* const* t, bool optional, const float** ptr,
@@ -990,7 +992,22 @@ static int sidechain_views(const char* who, const emk_sidechain_plan* plan, cons
   return EMK_OK;
 }
 
-int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, DLManagedTensor* xyz, void* stream) {
+static int saved_view(const char* who, const emk_sidechain_plan* plan, const DLManagedTensor* t, int64_t frames, double** ptr) {
+  *ptr = nullptr;
+  if (!t) return EMK_OK;
+  View v;
+  int rc = view_of(t, "saved_state", kDLFloat, 64, 2, 2, &v);
+  if (rc) return rc;
+  EMK_REQUIRE(v.shape[0] == frames && v.shape[1] == sidechain_saved_doubles(as_plan(plan)), EMK_E_SHAPE,
+              "%s: saved_state must be (%lld, %lld) float64 (emk_sidechain_saved_size)", who, (long long)frames,
+              (long long)sidechain_saved_doubles(as_plan(plan)));
+  *ptr = static_cast<double*>(v.data);
+  return EMK_OK;
+}
+int64_t emk_sidechain_saved_size(const emk_sidechain_plan* plan) { return sidechain_saved_doubles(as_plan(plan)); }
+
+int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, DLManagedTensor* xyz,
+                             DLManagedTensor* saved_state, void* stream) {
   EMK_REQUIRE(inputs, EMK_E_NULL, "emk_dl_sidechain_backmap: NULL inputs");
   const float* in[6];
   int64_t frames = -1;
@@ -999,10 +1016,13 @@ int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTens
   VIEW(ov, xyz, "xyz", 3, 3);
   EMK_REQUIRE(ov.shape[0] == frames && ov.shape[1] == sidechain_plan_atoms(as_plan(plan)) && ov.shape[2] == 3, EMK_E_SHAPE,
               "emk_dl_sidechain_backmap: xyz must be (%lld, %d, 3)", (long long)frames, sidechain_plan_atoms(as_plan(plan)));
-  return sidechain_backmap_device(as_plan(plan), in, frames, F(ov), as_stream(stream));
+  double* sv;
+  rc = saved_view("emk_dl_sidechain_backmap", plan, saved_state, frames, &sv);
+  if (rc) return rc;
+  return sidechain_backmap_device(as_plan(plan), in, frames, F(ov), sv, as_stream(stream));
 }
 int emk_dl_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, const DLManagedTensor* grad_xyz,
-                                 DLManagedTensor* const* grad_inputs, void* stream) {
+                                 const DLManagedTensor* saved_state, DLManagedTensor* const* grad_inputs, void* stream) {
   EMK_REQUIRE(inputs && grad_inputs, EMK_E_NULL, "emk_dl_sidechain_backmap_bwd: NULL inputs");
   const float* in[6];
   const float* gin_c[6];
@@ -1016,7 +1036,10 @@ int emk_dl_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const DLManaged
               "emk_dl_sidechain_backmap_bwd: grad_xyz must be (%lld, %d, 3)", (long long)frames, sidechain_plan_atoms(as_plan(plan)));
   float* gin[6];
   for (int k = 0; k < 6; k++) gin[k] = const_cast<float*>(gin_c[k]);
-  return sidechain_backmap_bwd_device(as_plan(plan), in, frames, F(gv), gin, as_stream(stream));
+  double* sv;
+  rc = saved_view("emk_dl_sidechain_backmap_bwd", plan, saved_state, frames, &sv);
+  if (rc) return rc;
+  return sidechain_backmap_bwd_device(as_plan(plan), in, frames, F(gv), sv, gin, as_stream(stream));
 }
 
 int64_t emk_sidechain_pairwise_indices(int64_t n_residues, const int32_t* n_side_dihedrals, int64_t start, int64_t stop, int64_t step,

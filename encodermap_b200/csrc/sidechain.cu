@@ -137,6 +137,9 @@ struct ScParams {
   float* out;
   const float* gout;
   float* gin[6];
+  double* save;           // forward: per frame (sin, cos) of every rotation, the angle flags and the float64 coordinates, or nullptr
+  const double* saved;    // backward: the same block, or nullptr (the forward pass is then repeated inside the kernel)
+  int64_t save_stride;    // doubles per frame
 };
 
 // slots of the published transform
@@ -317,17 +320,30 @@ __device__ __forceinline__ void sc_forward(const ScParams& p, double* xf, double
   sc_side_steps<true, KEEP>(p, k_cd + p.n_cd, xf, tg);                                 // :786-841, side-chain rows
 }
 
+// doubles per frame of the state the backward pass can take over from the forward pass
+__host__ __device__ inline int64_t sc_saved_doubles(int n_atoms, int n_ops) { return 2 * (int64_t)n_ops + (n_ops + 7) / 8 + 3 * (int64_t)n_atoms; }
+
+template <bool SAVE>
 __global__ void __launch_bounds__(128) sidechain_fwd_kernel(const ScParams p) {
   extern __shared__ double sc_smem[];
   double* xf = sc_smem;
   double* tg = xf + 3 * (size_t)p.n_atoms;
   double* tr = tg + 2 * (size_t)p.n_ops;
+  unsigned char* flags = SAVE ? reinterpret_cast<unsigned char*>(tr + TR_N) : nullptr;
   for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
     __syncthreads();
-    sc_layout(p, f, xf, tg, nullptr);
-    sc_forward<false>(p, xf, tg, tr);
+    sc_layout(p, f, xf, tg, flags);
+    sc_forward<SAVE>(p, xf, tg, tr);
     float* dst = p.out + f * (int64_t)(3 * p.n_atoms);
     for (int e = threadIdx.x; e < 3 * p.n_atoms; e += blockDim.x) dst[e] = (float)xf[e];
+    if (SAVE) {
+      double* sv = p.save + f * p.save_stride;
+      for (int e = threadIdx.x; e < 2 * p.n_ops; e += blockDim.x) sv[e] = tg[e];
+      unsigned char* sf = reinterpret_cast<unsigned char*>(sv + 2 * (size_t)p.n_ops);
+      for (int e = threadIdx.x; e < p.n_ops; e += blockDim.x) sf[e] = flags[e];
+      double* sx = sv + 2 * (size_t)p.n_ops + (p.n_ops + 7) / 8;
+      for (int e = threadIdx.x; e < 3 * p.n_atoms; e += blockDim.x) sx[e] = xf[e];
+    }
   }
 }
 
@@ -549,8 +565,17 @@ __global__ void __launch_bounds__(kScThreads) sidechain_bwd_kernel(const ScParam
   const int k_cd = p.n_ca + p.n_side;
   for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
     __syncthreads();
-    sc_layout(p, f, xf, tg, flags);
-    sc_forward<true>(p, xf, tg, tr);
+    if (p.saved) {
+      const double* sv = p.saved + f * p.save_stride;
+      for (int e = tid; e < 2 * p.n_ops; e += nth) tg[e] = sv[e];
+      const unsigned char* sf = reinterpret_cast<const unsigned char*>(sv + 2 * (size_t)p.n_ops);
+      for (int e = tid; e < p.n_ops; e += nth) flags[e] = sf[e];
+      const double* sx = sv + 2 * (size_t)p.n_ops + (p.n_ops + 7) / 8;
+      for (int e = tid; e < 3 * p.n_atoms; e += nth) xf[e] = sx[e];
+    } else {
+      sc_layout(p, f, xf, tg, flags);
+      sc_forward<true>(p, xf, tg, tr);
+    }
     const float* gsrc = p.gout + f * (int64_t)(3 * p.n_atoms);
     for (int e = tid; e < 3 * p.n_atoms; e += nth) gf[e] = (double)__ldg(gsrc + e);
     __syncthreads();
@@ -703,23 +728,31 @@ static unsigned frames_grid(int64_t frames, size_t smem) {
   return (unsigned)std::min<int64_t>(frames, (int64_t)sm_count() * per_sm);
 }
 
-int sidechain_backmap_device(const SidechainPlan* pl, const float* const* in, int64_t frames, float* out, cudaStream_t st) {
+int64_t sidechain_saved_doubles(const SidechainPlan* pl) { return pl ? sc_saved_doubles(pl->n_atoms, pl->n_ops) : -1; }
+
+int sidechain_backmap_device(const SidechainPlan* pl, const float* const* in, int64_t frames, float* out, double* save, cudaStream_t st) {
   ScParams p{};
   int rc = fill_params("emk_sidechain_backmap", pl, in, frames, &p);
   if (rc) return rc;
   if (frames == 0) return EMK_OK;
   EMK_REQUIRE(out, EMK_E_NULL, "emk_sidechain_backmap: NULL output");
-  const size_t smem = (3 * (size_t)pl->n_atoms + 2 * (size_t)pl->n_ops + TR_N) * sizeof(double);
+  const size_t smem = (3 * (size_t)pl->n_atoms + 2 * (size_t)pl->n_ops + TR_N) * sizeof(double) + (save ? (((size_t)pl->n_ops + 15) & ~(size_t)15) : 0);
   EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap: %d atoms need %zu bytes of shared memory per frame (limit 227 KB)", pl->n_atoms, smem);
   p.out = out;
+  p.save = save;
+  p.save_stride = sc_saved_doubles(pl->n_atoms, pl->n_ops);
   static bool cfg[kMaxDevices] = {false};
-  if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(sidechain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  sidechain_fwd_kernel<<<frames_grid(frames, smem), 128, smem, st>>>(p);
+  if (first_use_on_device(cfg)) {
+    EMK_CUDA(cudaFuncSetAttribute(sidechain_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    EMK_CUDA(cudaFuncSetAttribute(sidechain_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  if (save) sidechain_fwd_kernel<true><<<frames_grid(frames, smem), 128, smem, st>>>(p);
+  else sidechain_fwd_kernel<false><<<frames_grid(frames, smem), 128, smem, st>>>(p);
   return launch_status("sidechain_fwd_kernel");
 }
 
-int sidechain_backmap_bwd_device(const SidechainPlan* pl, const float* const* in, int64_t frames, const float* grad_out, float* const* grad_in,
-                                 cudaStream_t st) {
+int sidechain_backmap_bwd_device(const SidechainPlan* pl, const float* const* in, int64_t frames, const float* grad_out, const double* saved,
+                                 float* const* grad_in, cudaStream_t st) {
   ScParams p{};
   int rc = fill_params("emk_sidechain_backmap_bwd", pl, in, frames, &p);
   if (rc) return rc;
@@ -729,6 +762,8 @@ int sidechain_backmap_bwd_device(const SidechainPlan* pl, const float* const* in
   EMK_REQUIRE(smem <= 227 * 1024, EMK_E_UNSUPPORTED, "emk_sidechain_backmap_bwd: %d atoms / %d steps need %zu bytes of shared memory per frame (limit 227 KB)",
               pl->n_atoms, pl->n_ops, smem);
   p.gout = grad_out;
+  p.saved = saved;
+  p.save_stride = sc_saved_doubles(pl->n_atoms, pl->n_ops);
   for (int k = 0; k < 6; k++) p.gin[k] = grad_in[k];
   static bool cfg[kMaxDevices] = {false};
   if (first_use_on_device(cfg)) EMK_CUDA(cudaFuncSetAttribute(sidechain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

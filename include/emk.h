@@ -285,8 +285,10 @@ EMK_API int emk_set_dihedrals(const float* start, int64_t start_frames, int64_t 
  *                               dihedral), atoms a b c d (d = -1 for angles), input column, moving ranges [lo0, hi0) [lo1, hi1)
  *   emk_sidechain_backmap       inputs (frames, columns) float32 device, xyz (frames, n_atoms, 3).  One CTA per frame,
  *                               coordinates in shared memory as float64 for the whole sequence; capturable.
- *   emk_sidechain_backmap_bwd   exact VJP (any gradient pointer may be NULL): re-runs the forward, then undoes the rotations in
- *                               reverse order.  A bond angle measured on a straight triplet (1 - cos^2 < 1e-12) is a constant
+ *                               saved_state (optional, (frames, emk_sidechain_saved_size(plan)) float64): sin / cos of every
+ *                               rotation and the float64 coordinates, for the backward pass
+ *   emk_sidechain_backmap_bwd   exact VJP (any gradient pointer may be NULL): takes the forward state over from saved_state, or
+ *                               re-runs the forward when that is NULL, then undoes the rotations in reverse order.  A bond angle measured on a straight triplet (1 - cos^2 < 1e-12) is a constant
  *                               (acos is not differentiable there; the reference's float32 autodiff gives 0, a huge number or
  *                               NaN depending on rounding).  At most ~3 500 atoms (shared memory).
  *   emk_sidechain_pairwise_indices  HOST: the atoms PairwiseDistances selects when side chains are reconstructed
@@ -302,16 +304,18 @@ EMK_API int emk_sidechain_plan_info(const emk_sidechain_plan* plan, int64_t* inf
 EMK_API int emk_sidechain_plan_ops(const emk_sidechain_plan* plan, int32_t* ops);
 EMK_API int emk_sidechain_backmap(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
                                   const float* central_dihedrals, const float* side_distances, const float* side_angles,
-                                  const float* side_dihedrals, int64_t frames, float* xyz, void* stream);
+                                  const float* side_dihedrals, int64_t frames, float* xyz, double* saved_state, void* stream);
 EMK_API int emk_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const float* central_distances, const float* central_angles,
                                       const float* central_dihedrals, const float* side_distances, const float* side_angles,
-                                      const float* side_dihedrals, int64_t frames, const float* grad_xyz,
+                                      const float* side_dihedrals, int64_t frames, const float* grad_xyz, const double* saved_state,
                                       float* grad_central_distances, float* grad_central_angles, float* grad_central_dihedrals,
                                       float* grad_side_distances, float* grad_side_angles, float* grad_side_dihedrals, void* stream);
 /* inputs / grad_inputs: arrays of six tensors in the order above (grad_inputs entries may be NULL) */
-EMK_API int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, DLManagedTensor* xyz, void* stream);
+EMK_API int emk_dl_sidechain_backmap(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, DLManagedTensor* xyz,
+                                     DLManagedTensor* saved_state, void* stream);
 EMK_API int emk_dl_sidechain_backmap_bwd(const emk_sidechain_plan* plan, const DLManagedTensor* const* inputs, const DLManagedTensor* grad_xyz,
-                                         DLManagedTensor* const* grad_inputs, void* stream);
+                                         const DLManagedTensor* saved_state, DLManagedTensor* const* grad_inputs, void* stream);
+EMK_API int64_t emk_sidechain_saved_size(const emk_sidechain_plan* plan);
 EMK_API int64_t emk_sidechain_pairwise_indices(int64_t n_residues, const int32_t* n_side_dihedrals, int64_t start, int64_t stop,
                                                int64_t step, int64_t* indices);
 EMK_API int emk_gather_atoms(const float* xyz, int64_t b, int64_t n_atoms, const int32_t* index_dev, int64_t m, float* out, void* stream);

@@ -1466,13 +1466,20 @@ def test_sidechain_backmap_partial_gradients_and_raw_abi(em):
     assert all(torch.isfinite(f).all() for f in full)
     L = _lib.lib()
     xyz = torch.empty(5, plan.n_atoms, 3, device="cuda")
-    _lib.check(L.emk_sidechain_backmap(plan.handle, *[t.data_ptr() for t in inputs], 5, xyz.data_ptr(), _lib.stream_of(xyz)))
+    _lib.check(L.emk_sidechain_backmap(plan.handle, *[t.data_ptr() for t in inputs], 5, xyz.data_ptr(), None, _lib.stream_of(xyz)))
     assert torch.equal(xyz, out.detach())
     grads = [torch.empty_like(t) for t in inputs]
-    _lib.check(L.emk_sidechain_backmap_bwd(plan.handle, *[t.data_ptr() for t in inputs], 5, g_out.data_ptr(),
+    _lib.check(L.emk_sidechain_backmap_bwd(plan.handle, *[t.data_ptr() for t in inputs], 5, g_out.data_ptr(), None,
                                            *[g.data_ptr() for g in grads], _lib.stream_of(xyz)))
     for a, b in zip(grads, want):
         assert torch.equal(a, b)
+    # the backward pass taking the forward state over (what autograd does) = the backward pass repeating the forward
+    xyz2, saved = _ops.sidechain_backmap_raw(plan, inputs, save_state=True)
+    assert torch.equal(xyz2, xyz) and saved.shape == (5, plan.saved_size) and saved.dtype == torch.float64
+    for a, b in zip(_ops.sidechain_backmap_bwd_raw(plan, inputs, g_out, saved=saved), want):
+        assert torch.equal(a, b)
+    with pytest.raises(_lib.EmkError):
+        _ops.sidechain_backmap_bwd_raw(plan, inputs, g_out, saved=saved[:, :-1].contiguous())
     # wrong column count, wrong device pointer class
     with pytest.raises(_lib.EmkError):
         _ops.sidechain_backmap_raw(plan, [inputs[0][:, :-1]] + inputs[1:])

@@ -41,8 +41,11 @@ for name, counts in topologies.items():
         gout = torch.randn(frames, plan.n_atoms, 3, device=dev)
         fwd = graph_time(lambda: _ops.sidechain_backmap_raw(plan, inputs), reps=3, replays=3)
         bwd = graph_time(lambda: _ops.sidechain_backmap_bwd_raw(plan, inputs, gout), reps=3, replays=3)
-        print(f"  {frames:6d} frames: forward {fwd:8.3f} ms ({frames / fwd * 1e3:10.0f} frames/s)   backward (incl. its own forward) "
-              f"{bwd:8.3f} ms ({frames / bwd * 1e3:10.0f} frames/s)")
+        _, saved = _ops.sidechain_backmap_raw(plan, inputs, save_state=True)
+        fwd_s = graph_time(lambda: _ops.sidechain_backmap_raw(plan, inputs, save_state=True), reps=3, replays=3)
+        bwd_s = graph_time(lambda: _ops.sidechain_backmap_bwd_raw(plan, inputs, gout, saved=saved), reps=3, replays=3)
+        print(f"  {frames:6d} frames: forward {fwd:8.3f} ms ({frames / fwd * 1e3:10.0f} frames/s)   backward incl. its own forward "
+              f"{bwd:8.3f} ms   |  training: forward keeping its state {fwd_s:8.3f} ms + backward {bwd_s:8.3f} ms")
     cpu_frames = 64
     ci = [torch.tensor(v.astype(np.float64), requires_grad=True) for v in make_inputs(counts, cpu_frames)]
     t0 = time.perf_counter()
