@@ -372,27 +372,39 @@ __device__ __forceinline__ void sc_publish_inverse(const double* xf, const doubl
   tr[TR_P] = xf[3 * b]; tr[TR_P + 1] = xf[3 * b + 1]; tr[TR_P + 2] = xf[3 * b + 2];
 }
 
+// the published transform of a step, in registers
+struct Rot {
+  double r[9], p[3], u[3], s, oc;
+};
+__device__ __forceinline__ Rot sc_load_rot(const double* tr) {
+  Rot t;
+#pragma unroll
+  for (int q = 0; q < 9; q++) t.r[q] = tr[q];
+#pragma unroll
+  for (int q = 0; q < 3; q++) { t.p[q] = tr[TR_P + q]; t.u[q] = tr[TR_U + q]; }
+  t.s = tr[TR_S]; t.oc = 1.0 - tr[TR_C];
+  return t;
+}
+
 // one moving atom of a step, backward: restores its position before the step, pulls its gradient back, adds its share of
 // (g_theta, g_p, g_u) to acc
-__device__ __forceinline__ void sc_atom_bwd(double* xf, double* gf, const double* tr, int at, bool dihedral, double* acc) {
-  const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
-  const double pv[3] = {tr[TR_P], tr[TR_P + 1], tr[TR_P + 2]};
-  const double u[3] = {tr[TR_U], tr[TR_U + 1], tr[TR_U + 2]};
-  const double w[3] = {xf[3 * at] - pv[0], xf[3 * at + 1] - pv[1], xf[3 * at + 2] - pv[2]};
-  const double v[3] = {r0 * w[0] + r3 * w[1] + r6 * w[2], r1 * w[0] + r4 * w[1] + r7 * w[2], r2 * w[0] + r5 * w[1] + r8 * w[2]};
-  xf[3 * at] = pv[0] + v[0]; xf[3 * at + 1] = pv[1] + v[1]; xf[3 * at + 2] = pv[2] + v[2];
+__device__ __forceinline__ void sc_atom_bwd(double* xf, double* gf, const Rot& t, int at, bool dihedral, double* acc) {
+  const double* r = t.r;
+  const double w[3] = {xf[3 * at] - t.p[0], xf[3 * at + 1] - t.p[1], xf[3 * at + 2] - t.p[2]};
+  const double v[3] = {r[0] * w[0] + r[3] * w[1] + r[6] * w[2], r[1] * w[0] + r[4] * w[1] + r[7] * w[2], r[2] * w[0] + r[5] * w[1] + r[8] * w[2]};
+  xf[3 * at] = t.p[0] + v[0]; xf[3 * at + 1] = t.p[1] + v[1]; xf[3 * at + 2] = t.p[2] + v[2];
   const double g[3] = {gf[3 * at], gf[3 * at + 1], gf[3 * at + 2]};
-  const double rg[3] = {r0 * g[0] + r3 * g[1] + r6 * g[2], r1 * g[0] + r4 * g[1] + r7 * g[2], r2 * g[0] + r5 * g[1] + r8 * g[2]};
+  const double rg[3] = {r[0] * g[0] + r[3] * g[1] + r[6] * g[2], r[1] * g[0] + r[4] * g[1] + r[7] * g[2], r[2] * g[0] + r[5] * g[1] + r[8] * g[2]};
   double uxw[3];
-  cross3d(u, w, uxw);
+  cross3d(t.u, w, uxw);
   acc[0] += dot3d(g, uxw);
   acc[1] += g[0] - rg[0]; acc[2] += g[1] - rg[1]; acc[3] += g[2] - rg[2];
   if (dihedral) {
     double vxg[3];
     cross3d(v, g, vxg);
-    const double uv = dot3d(u, v), ug = dot3d(u, g), s = tr[TR_S], oc = 1.0 - tr[TR_C];
+    const double uv = dot3d(t.u, v), ug = dot3d(t.u, g);
 #pragma unroll
-    for (int q = 0; q < 3; q++) acc[4 + q] += s * vxg[q] + oc * (uv * g[q] + ug * v[q]);
+    for (int q = 0; q < 3; q++) acc[4 + q] += t.s * vxg[q] + t.oc * (uv * g[q] + ug * v[q]);
   }
   gf[3 * at] = rg[0]; gf[3 * at + 1] = rg[1]; gf[3 * at + 2] = rg[2];
 }
@@ -401,79 +413,75 @@ __device__ __forceinline__ void sc_atom_bwd(double* xf, double* gf, const double
 // dL/dtarget.  sd = sin(target - measured) kept by the forward pass, flag: see sc_layout
 __device__ __forceinline__ double sc_finish_step(const double* xf, double* gf, int kind, int a, int b, int c, int d, const double* sum, double sd,
                                                  int flag) {
-  gf[3 * b] += sum[1]; gf[3 * b + 1] += sum[2]; gf[3 * b + 2] += sum[3];
+  // contributions are collected per atom in registers and added to shared memory once at the end (a, b, c, d are four different
+  // atoms): read-modify-write chains through shared memory on the same address would serialise
+  double ga[3] = {0.0, 0.0, 0.0}, gb[3] = {sum[1], sum[2], sum[3]}, gc[3] = {0.0, 0.0, 0.0}, gd[3] = {0.0, 0.0, 0.0};
   const double g_theta = sum[0];
+  double g_target;
+  double xa[3], xb[3], xc[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) { xa[q] = xf[3 * a + q]; xb[q] = xf[3 * b + q]; xc[q] = xf[3 * c + q]; }
   if (kind <= kSideAngle) {
     double ba[3], bc[3], cr[3];
 #pragma unroll
-    for (int q = 0; q < 3; q++) { ba[q] = xf[3 * a + q] - xf[3 * b + q]; bc[q] = xf[3 * c + q] - xf[3 * b + q]; }
+    for (int q = 0; q < 3; q++) { ba[q] = xa[q] - xb[q]; bc[q] = xc[q] - xb[q]; }
     const double na2 = dot3d(ba, ba), nc2 = dot3d(bc, bc), inv = rsqrt(na2 * nc2);
     const double t = dot3d(ba, bc) * inv;
     cross3d(ba, bc, cr);
     const double sm2 = dot3d(cr, cr) * inv * inv;                                   // sin^2 of the measured angle
     const double sgn = flag == 1 ? 1.0 : flag == 2 ? -1.0 : sd > 0.0 ? 1.0 : sd < 0.0 ? -1.0 : 0.0;     // d|x|/dx
-    const double g_target = sgn * g_theta;
+    g_target = sgn * g_theta;
     if (t >= -1.0 && t <= 1.0 && sm2 >= kStraightEps) {
       const double gt = g_target * rsqrt(sm2);           // dL/dcos = (-sgn g_theta) (-1 / sin(measured))
+      const double ta = t / na2, tc = t / nc2;
 #pragma unroll
       for (int q = 0; q < 3; q++) {
-        const double da = gt * (bc[q] * inv - t * ba[q] / na2), dc = gt * (ba[q] * inv - t * bc[q] / nc2);
-        gf[3 * a + q] += da; gf[3 * c + q] += dc; gf[3 * b + q] -= da + dc;
+        ga[q] = gt * (bc[q] * inv - ta * ba[q]);
+        gc[q] = gt * (ba[q] * inv - tc * bc[q]);
+        gb[q] -= ga[q] + gc[q];
       }
     }
-    return g_target;
-  }
-  // the axis: u = dvec / |dvec|
-  double dv[3];
-  const double gu[3] = {sum[4], sum[5], sum[6]};
+  } else {
+    g_target = g_theta;
+    // the axis: u = dvec / |dvec|
+    double dv[3], xd[3];
+    const double gu[3] = {sum[4], sum[5], sum[6]};
 #pragma unroll
-  for (int q = 0; q < 3; q++) dv[q] = xf[3 * c + q] - xf[3 * b + q];
-  const double l2 = dot3d(dv, dv), il = rsqrt(l2), len = l2 * il;
-  const double u[3] = {dv[0] * il, dv[1] * il, dv[2] * il};
-  const double ugu = dot3d(u, gu);
-#pragma unroll
-  for (int q = 0; q < 3; q++) {
-    const double gd = (gu[q] - u[q] * ugu) * il;
-    gf[3 * c + q] += gd; gf[3 * b + q] -= gd;
-  }
-  // the measured dihedral m = atan2(p1, p2): dL/dm = -g_theta, pulled back by hand through layers.py:800-808
-  double b1[3], b3[3], c1[3], c2[3];
-#pragma unroll
-  for (int q = 0; q < 3; q++) { b1[q] = xf[3 * b + q] - xf[3 * a + q]; b3[q] = xf[3 * d + q] - xf[3 * c + q]; }
-  cross3d(dv, b3, c1);
-  cross3d(b1, dv, c2);
-  const double qd = dot3d(b1, c1), p1 = qd * len, p2 = dot3d(c1, c2);
-  const double den = p1 * p1 + p2 * p2;
-  if (den > 0.0) {
-    const double gm = -g_theta / den;
-    const double gp1 = gm * p2, gp2 = -gm * p1;
-    const double gq = gp1 * len, glen = gp1 * qd * il;
-    double gb1[3], gb2[3], gb3[3], gc1[3], gc2[3], tmp[3];
+    for (int q = 0; q < 3; q++) { dv[q] = xc[q] - xb[q]; xd[q] = xf[3 * d + q]; }
+    const double l2 = dot3d(dv, dv), il = rsqrt(l2), len = l2 * il;
+    const double ugu = dot3d(dv, gu) * il * il;          // (u . g_u) / |d|
 #pragma unroll
     for (int q = 0; q < 3; q++) {
-      gb1[q] = gq * c1[q];
-      gc1[q] = gq * b1[q] + gp2 * c2[q];
-      gc2[q] = gp2 * c1[q];
-      gb2[q] = glen * dv[q];
+      const double gdir = gu[q] * il - dv[q] * ugu * il;      // (g_u - u (u . g_u)) / |d|
+      gc[q] = gdir; gb[q] -= gdir;
     }
-    cross3d(b3, gc1, tmp);   // c1 = b2 x b3:  g_b2 += b3 x g_c1,  g_b3 = g_c1 x b2
+    // the measured dihedral m = atan2(p1, p2) of layers.py:800-808, dL/dm = -g_theta.  With A = b1 x b2, B = b2 x b3:
+    //   dm/da = -|b2| A / A^2,   dm/dd = |b2| B / B^2,
+    //   dm/db = -(1 + b1.b2 / b2^2) dm/da + (b3.b2 / b2^2) dm/dd,   dm/dc = (b1.b2 / b2^2) dm/da - (1 + b3.b2 / b2^2) dm/dd
+    double b1[3], b3[3], A[3], B[3];
 #pragma unroll
-    for (int q = 0; q < 3; q++) gb2[q] += tmp[q];
-    cross3d(gc1, dv, gb3);
-    cross3d(dv, gc2, tmp);   // c2 = b1 x b2:  g_b1 += b2 x g_c2,  g_b2 += g_c2 x b1
+    for (int q = 0; q < 3; q++) { b1[q] = xb[q] - xa[q]; b3[q] = xd[q] - xc[q]; }
+    cross3d(b1, dv, A);
+    cross3d(dv, b3, B);
+    const double a2 = dot3d(A, A), b2n = dot3d(B, B);
+    if (a2 > 0.0 && b2n > 0.0) {
+      const double ka = g_theta * len / a2, kd = -g_theta * len / b2n;      // -g_theta dm/da = ka A,  -g_theta dm/dd = kd B
+      const double fa = dot3d(b1, dv) * il * il, fb = dot3d(b3, dv) * il * il;
 #pragma unroll
-    for (int q = 0; q < 3; q++) gb1[q] += tmp[q];
-    cross3d(gc2, b1, tmp);
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      gb2[q] += tmp[q];
-      gf[3 * a + q] -= gb1[q];
-      gf[3 * b + q] += gb1[q] - gb2[q];
-      gf[3 * c + q] += gb2[q] - gb3[q];
-      gf[3 * d + q] += gb3[q];
+      for (int q = 0; q < 3; q++) {
+        const double pa = ka * A[q], pd = kd * B[q];
+        ga[q] = pa;
+        gd[q] = pd;
+        gb[q] += fb * pd - (1.0 + fa) * pa;
+        gc[q] += fa * pa - (1.0 + fb) * pd;
+      }
     }
+#pragma unroll
+    for (int q = 0; q < 3; q++) gf[3 * d + q] += gd[q];
   }
-  return g_theta;
+#pragma unroll
+  for (int q = 0; q < 3; q++) { gf[3 * a + q] += ga[q]; gf[3 * b + q] += gb[q]; gf[3 * c + q] += gc[q]; }
+  return g_target;
 }
 
 // backbone steps [k0, k1) in reverse, by the whole CTA
@@ -493,7 +501,8 @@ __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t
     const int busy_warps = min(nth >> 5, (total + 31) >> 5);       // warps past this have no moving atom of this step
     if (warp < busy_warps) {
       double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int e = tid; e < total; e += nth) sc_atom_bwd(xf, gf, tr, e < c0 ? o1.z + e : o2.x + (e - c0), dihedral, acc);
+      const Rot rot = sc_load_rot(tr);
+      for (int e = tid; e < total; e += nth) sc_atom_bwd(xf, gf, rot, e < c0 ? o1.z + e : o2.x + (e - c0), dihedral, acc);
 #pragma unroll
       for (int q = 0; q < kRed; q++) {
         if (q >= 4 && !dihedral) break;
@@ -545,7 +554,8 @@ __device__ __forceinline__ void sc_side_steps_bwd(const ScParams& p, int64_t f, 
       double tr[TR_N];
       sc_publish_inverse(xf, tg, tr, k, kind, b, c);
       double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int at = r.y + q; at < end; at++) sc_atom_bwd(xf, gf, tr, at, DIH, acc);
+      const Rot rot = sc_load_rot(tr);
+      for (int at = r.y + q; at < end; at++) sc_atom_bwd(xf, gf, rot, at, DIH, acc);
       const double g_target = sc_finish_step(xf, gf, kind, a, b, c, d, acc, tg[2 * k], flags[k]);
       if (gdst) gdst[f * p.cols[src] + k - k_base] = (float)g_target;
     }
