@@ -23,6 +23,9 @@ ncu --set full --clock-control none --import-source on -k regex:"pairwise_flat3"
     python tools/profile_pairwise.py > gpurun_out/r02_pairwise.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"small_cost_kernel|Geom<64" -c 4 -o gpurun_out/r02_small_cost \
     python tools/bench_small_cost.py > gpurun_out/r02_small_cost.log 2>&1
+# (6) back-mapping with side chains at the training batch (256 frames x 448 atoms)
+ncu --set full --clock-control none --import-source on -k regex:sidechain -s 4 -c 2 -o gpurun_out/r02_sidechain \
+    python tools/experiments/profile_sidechain.py > gpurun_out/r02_sidechain.log 2>&1
 # summarise on the box and drop the captures (gpurun_out/ is limited to 64 MiB)
 python tools/profile_summarise.py r02 gpurun_out/summary > gpurun_out/r02_summarise.log 2>&1
 rm -f gpurun_out/*.ncu-rep

@@ -2,7 +2,7 @@
     compute-sanitizer --tool memcheck python tools/sanitize_round2.py
 narrow-input cost, warp-per-frame PairwiseDistances forward / backward (1..4 chunks), fused Cartesian loss (one and four warps
 per frame, every variant, both target kinds), cartesian_distance_loss from coordinates, generation-side atoms, lane-per-frame
-back-mapping (float64 chain and the float32 first pass with fall-back)."""
+back-mapping (float64 chain and the float32 first pass with fall-back), back-mapping with side chains and the atom gather."""
 import math
 import sys
 from pathlib import Path
@@ -54,5 +54,22 @@ for ext in (0, 16):
         dih = ((torch.rand(b, n - 3, device=dev, generator=g) * 2 - 1) * math.pi).contiguous()
         dih[0] = math.pi   # an extended chain: the float32 pass falls back
         _ops.backmap_raw(lengths, ang, dih)
+# back-mapping with side chains: forward (with and without kept state), backward (both), gathered pairwise distances,
+# set_dihedrals; a frame count above the grid so the frame loop of a CTA runs more than once is covered by the GPU tests
+for counts, frames in (([3, 4, 0], 3), ([0, 2, 1, 4], 2), ([2, 0, 4, 1, 0, 0, 3, 2, 1, 4, 2, 0], 40)):
+    plan = _ops.SidechainPlan(counts, dev)
+    n_res, n_side = len(counts), sum(c + 1 for c in counts if c > 0)
+    ins = [0.13 + 0.03 * torch.rand(frames, 3 * n_res - 1, device=dev, generator=g), 1.9 + 0.3 * torch.rand(frames, 3 * n_res - 2, device=dev, generator=g),
+           (torch.rand(frames, 3 * n_res - 3, device=dev, generator=g) * 2 - 1) * math.pi, 0.13 + 0.05 * torch.rand(frames, n_side, device=dev, generator=g),
+           1.8 + 0.4 * torch.rand(frames, n_side, device=dev, generator=g), (torch.rand(frames, sum(counts), device=dev, generator=g) * 2 - 1) * math.pi]
+    xyz, saved = _ops.sidechain_backmap_raw(plan, ins, save_state=True)
+    _ops.sidechain_backmap_raw(plan, ins)
+    go = torch.randn_like(xyz)
+    _ops.sidechain_backmap_bwd_raw(plan, ins, go, saved=saved)
+    _ops.sidechain_backmap_bwd_raw(plan, ins, go, needs=(False, True, True, False, True, True))
+    index = torch.as_tensor(_ops.sidechain_pairwise_indices(counts, 1, None, 3), dtype=torch.int32, device=dev)
+    if int(index.max()) < plan.n_atoms:
+        sel = _ops.gather_atoms_raw(xyz, index)
+        _ops.gather_atoms_bwd_raw(torch.randn_like(sel), index, plan.n_atoms)
 torch.cuda.synchronize()
 print("sanitize workload done")
