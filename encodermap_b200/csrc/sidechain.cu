@@ -259,14 +259,12 @@ __device__ __forceinline__ void sc_backbone_steps(const ScParams& p, int k0, int
   for (int k = k0; k < k1; k++) {
     int4 n0 = o0, n1 = o1, n2 = o2;
     if (k + 1 < k1) { n0 = __ldg(p.ops + 3 * k + 3); n1 = __ldg(p.ops + 3 * k + 4); n2 = __ldg(p.ops + 3 * k + 5); }
-    if (tid < 32) {
-      // every lane of warp 0 computes the same numbers (no divergence, no shuffles); lane 0 publishes them
+    if (tid == 0) {
+      // one thread measures and publishes the rotation (a serial chain of ~300 float64 instructions: nothing to share out)
       const Measured m = sc_measure(xf, o0.x, o0.y, o0.z, o0.w, o1.x, tg[2 * k], tg[2 * k + 1]);
-      if (tid == 0) {
-        publish_rotation(tr, m.u, o0.x <= kSideAngle ? fabs(m.s) : m.s, m.c);            // bond angles rotate by |target - measured|
-        tr[TR_P] = xf[3 * o0.z]; tr[TR_P + 1] = xf[3 * o0.z + 1]; tr[TR_P + 2] = xf[3 * o0.z + 2];
-        if (KEEP) { tg[2 * k] = m.s; tg[2 * k + 1] = m.c; }
-      }
+      publish_rotation(tr, m.u, o0.x <= kSideAngle ? fabs(m.s) : m.s, m.c);              // bond angles rotate by |target - measured|
+      tr[TR_P] = xf[3 * o0.z]; tr[TR_P + 1] = xf[3 * o0.z + 1]; tr[TR_P + 2] = xf[3 * o0.z + 2];
+      if (KEEP) { tg[2 * k] = m.s; tg[2 * k + 1] = m.c; }
     }
     __syncthreads();
     const double r0 = tr[0], r1 = tr[1], r2 = tr[2], r3 = tr[3], r4 = tr[4], r5 = tr[5], r6 = tr[6], r7 = tr[7], r8 = tr[8];
