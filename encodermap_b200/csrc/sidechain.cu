@@ -474,11 +474,23 @@ __device__ __forceinline__ double sc_finish_step(const double* xf, double* gf, i
         gc[q] += fa * pa - (1.0 + fb) * pd;
       }
     }
+  }
+  // all loads first, then all stores (a, b, c, d are different atoms; written as += the compiler must assume they may alias and
+  // serialises twelve load - add - store round trips)
+  const bool four = kind > kSideAngle;
+  double oa[3], ob[3], oc[3], od[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int q = 0; q < 3; q++) gf[3 * d + q] += gd[q];
+  for (int q = 0; q < 3; q++) { oa[q] = gf[3 * a + q]; ob[q] = gf[3 * b + q]; oc[q] = gf[3 * c + q]; }
+  if (four) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) od[q] = gf[3 * d + q];
   }
 #pragma unroll
-  for (int q = 0; q < 3; q++) { gf[3 * a + q] += ga[q]; gf[3 * b + q] += gb[q]; gf[3 * c + q] += gc[q]; }
+  for (int q = 0; q < 3; q++) { gf[3 * a + q] = oa[q] + ga[q]; gf[3 * b + q] = ob[q] + gb[q]; gf[3 * c + q] = oc[q] + gc[q]; }
+  if (four) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) gf[3 * d + q] = od[q] + gd[q];
+  }
   return g_target;
 }
 
@@ -496,16 +508,20 @@ __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t
     const int kind = o0.x;
     const bool dihedral = kind >= kCentralDihedral;
     const int c0 = o1.w - o1.z, total = c0 + (o2.y - o2.x);
-    const int busy_warps = min(nth >> 5, (total + 31) >> 5);       // warps past this have no moving atom of this step
-    if (warp < busy_warps) {
+    {
+      // every warp leaves its partial sums (zeros when none of its lanes has a moving atom of this step): thread 0 then adds a
+      // FIXED number of slots with independent loads -- a loop over "the warps that had work" is a chain of dependent
+      // LDS + DADD round trips (measured: 1 600 of the 3 800 cycles of a step, profiles/r02_sidechain_backmap.txt)
       double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      const Rot rot = sc_load_rot(tr);
-      for (int e = tid; e < total; e += nth) sc_atom_bwd(xf, gf, rot, e < c0 ? o1.z + e : o2.x + (e - c0), dihedral, acc);
+      if (warp * 32 < total) {
+        const Rot rot = sc_load_rot(tr);
+        for (int e = tid; e < total; e += nth) sc_atom_bwd(xf, gf, rot, e < c0 ? o1.z + e : o2.x + (e - c0), dihedral, acc);
 #pragma unroll
-      for (int q = 0; q < kRed; q++) {
-        if (q >= 4 && !dihedral) break;
+        for (int q = 0; q < kRed; q++) {
+          if (q >= 4 && !dihedral) break;
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
+          for (int m = 16; m >= 1; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
+        }
       }
       if (lane == 0) {
 #pragma unroll
@@ -514,11 +530,15 @@ __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t
     }
     __syncthreads();
     if (tid == 0) {
+      double part[(kScThreads / 32) * kRed];
+#pragma unroll
+      for (int q = 0; q < (kScThreads / 32) * kRed; q++) part[q] = red[q];
       double sum[kRed];
 #pragma unroll
       for (int q = 0; q < kRed; q++) {
-        double v = 0.0;
-        for (int w = 0; w < busy_warps; w++) v += red[w * kRed + q];
+        double v = part[q];
+#pragma unroll
+        for (int w = 1; w < kScThreads / 32; w++) v += part[w * kRed + q];
         sum[q] = v;
       }
       const double g_target = sc_finish_step(xf, gf, kind, o0.y, o0.z, o0.w, o1.x, sum, tg[2 * k], flags[k]);
