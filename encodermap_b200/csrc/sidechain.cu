@@ -223,9 +223,20 @@ __device__ __forceinline__ void sc_layout(const ScParams& p, int64_t f, double* 
     if (flags) flags[k] = t > 3.141592653589793 ? 1 : t < 0.0 ? 2 : 0;
   }
   __syncthreads();
-  if (tid == 0) {
-    double run = 0.0;
-    for (int k = 1; k < p.n_bb; k++) { run += xf[3 * k]; xf[3 * k] = run; }
+  if (tid < 32) {       // running sum of the bond lengths: warp scan over 32 atoms at a time
+    double carry = 0.0;
+    for (int base = 0; base < p.n_bb; base += 32) {
+      const int k = base + tid;
+      double v = k < p.n_bb ? xf[3 * k] : 0.0;
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, v, m);
+        if (tid >= m) v += up;
+      }
+      v += carry;
+      if (k < p.n_bb) xf[3 * k] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
   }
   __syncthreads();
   for (int m = tid; m < p.n_side; m += nth) {
@@ -322,7 +333,7 @@ __device__ __forceinline__ void sc_forward(const ScParams& p, double* xf, double
 __host__ __device__ inline int64_t sc_saved_doubles(int n_atoms, int n_ops) { return 2 * (int64_t)n_ops + (n_ops + 7) / 8 + 3 * (int64_t)n_atoms; }
 
 template <bool SAVE>
-__global__ void __launch_bounds__(128) sidechain_fwd_kernel(const ScParams p) {
+__global__ void __launch_bounds__(128, 7) sidechain_fwd_kernel(const ScParams p) {
   extern __shared__ double sc_smem[];
   double* xf = sc_smem;
   double* tg = xf + 3 * (size_t)p.n_atoms;
@@ -624,12 +635,29 @@ __global__ void __launch_bounds__(kScThreads) sidechain_bwd_kernel(const ScParam
     }
     __syncthreads();
     float* g_cd = p.gin[0];
-    if (tid == 0 && g_cd) {
-      for (int m = 0; m < p.n_side; m++) gf[3 * __ldg(p.side + m).x] += gf[3 * (p.n_bb + m)];
-      double run = 0.0;
-      for (int k = p.n_bb - 1; k >= 1; k--) {
-        run += gf[3 * k];
-        g_cd[f * p.cols[0] + k - 1] = (float)run;
+    if (g_cd) {
+      // every side-chain atom starts at the x of its CA: one thread per residue folds its chain into the CA
+      for (int ri = tid; ri < p.n_res_side; ri += nth) {
+        const int4 r = __ldg(p.res + ri);
+        double v = 0.0;
+        for (int q = r.y; q <= r.y + r.z; q++) v += gf[3 * q];
+        gf[3 * (r.x + 1)] += v;
+      }
+      __syncthreads();
+      if (tid < 32) {     // d x_k / d bond_i = 1 for k > i: suffix sums, warp scan over 32 atoms at a time from the far end
+        double carry = 0.0;
+        for (int base = p.n_bb - 1; base >= 1; base -= 32) {
+          const int k = base - tid;
+          double v = k >= 1 ? gf[3 * k] : 0.0;
+#pragma unroll
+          for (int m = 1; m < 32; m <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, v, m);
+            if (tid >= m) v += up;
+          }
+          v += carry;
+          if (k >= 1) g_cd[f * p.cols[0] + k - 1] = (float)v;
+          carry = __shfl_sync(0xffffffffu, v, 31);
+        }
       }
     }
   }
