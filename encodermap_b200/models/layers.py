@@ -65,6 +65,16 @@ class BackMapLayerWithSidechains(torch.nn.Module):
     def get_config(self) -> dict:
         return {"feature_description": self.feature_description}
 
+    # the plans hold library handles and device memory: they are rebuilt on demand, never copied or pickled
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_plans"] = {}
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._plans = {}
+
     @classmethod
     def from_config(cls, config: dict) -> "BackMapLayerWithSidechains":
         fd = {int(k): {int(kk): vv for kk, vv in v.items()} for k, v in config.pop("feature_description").items()}

@@ -25,6 +25,7 @@ autograd graph is kept alive between TF's forward and backward passes.
 from __future__ import annotations
 
 import os
+import threading
 from math import pi
 
 import torch
@@ -345,14 +346,16 @@ def back_map(distances, angles, dihedrals):
 
 
 _SIDECHAIN_PLANS = {}
+_SIDECHAIN_LOCK = threading.Lock()      # py_function bodies may run on TensorFlow's executor threads
 
 
 def _sidechain_plan(counts, device):
     key = (tuple(int(c) for c in counts), str(device))
-    plan = _SIDECHAIN_PLANS.get(key)
-    if plan is None:
-        plan = _ops.SidechainPlan(key[0], device)
-        _SIDECHAIN_PLANS[key] = plan
+    with _SIDECHAIN_LOCK:
+        plan = _SIDECHAIN_PLANS.get(key)
+        if plan is None:
+            plan = _ops.SidechainPlan(key[0], device)
+            _SIDECHAIN_PLANS[key] = plan
     return plan
 
 

@@ -429,5 +429,10 @@ def test_sidechain_plan_refuses_what_the_reference_cannot_build(L):
         BackMapLayerWithSidechains({-1: {1: 2, 3: 0}})
     layer = BackMapLayerWithSidechains({-1: {1: 3, 2: 4, 3: 0}})
     assert layer.n_atoms == 18 and layer.n_sidechains == 9
+    import copy
+    import pickle
+
+    for clone in (copy.deepcopy(layer), pickle.loads(pickle.dumps(layer))):     # library handles are rebuilt, not copied
+        assert clone.counts == layer.counts and clone._plans == {} and clone._plan_for(None).n_atoms == 18
     again = BackMapLayerWithSidechains.from_config({"feature_description": {"-1": {"1": 3, "2": 4, "3": 0}}})
     assert again.counts == layer.counts and again.get_config()["feature_description"] == {-1: {1: 3, 2: 4, 3: 0}}
