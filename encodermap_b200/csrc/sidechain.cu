@@ -418,6 +418,20 @@ __device__ __forceinline__ void sc_atom_bwd(double* xf, double* gf, const Rot& t
   gf[3 * at] = rg[0]; gf[3 * at + 1] = rg[1]; gf[3 * at + 2] = rg[2];
 }
 
+// the same for a bond-angle step of the backbone, whose axis is +-e_z: the rotation is planar (x, y mix; z, and the z component
+// of the gradient, pass through), and (u x w) = u_z (-w_y, w_x, 0)
+__device__ __forceinline__ void sc_atom_bwd_planar(double* xf, double* gf, const Rot& t, int at, double* acc) {
+  const double c = t.r[0], sn = t.r[3];                 // R = [[c, -sn, 0], [sn, c, 0], [0, 0, 1]]
+  const double wx = xf[3 * at] - t.p[0], wy = xf[3 * at + 1] - t.p[1];
+  xf[3 * at] = t.p[0] + (c * wx + sn * wy);
+  xf[3 * at + 1] = t.p[1] + (c * wy - sn * wx);
+  const double gx = gf[3 * at], gy = gf[3 * at + 1];
+  const double rgx = c * gx + sn * gy, rgy = c * gy - sn * gx;
+  acc[0] += t.u[2] * (gy * wx - gx * wy);
+  acc[1] += gx - rgx; acc[2] += gy - rgy;
+  gf[3 * at] = rgx; gf[3 * at + 1] = rgy;
+}
+
 // what the sums of a step do to the pivot, the axis atoms and the measured atoms (xf holds the state BEFORE the step); returns
 // dL/dtarget.  sd = sin(target - measured) kept by the forward pass, flag: see sc_layout
 __device__ __forceinline__ double sc_finish_step(const double* xf, double* gf, int kind, int a, int b, int c, int d, const double* sum, double sd,
@@ -505,19 +519,22 @@ __device__ __forceinline__ double sc_finish_step(const double* xf, double* gf, i
   return g_target;
 }
 
-// backbone steps [k0, k1) in reverse, by the whole CTA
+// backbone steps [k0, k1) in reverse, by the whole CTA; all bond angles (DIH = false) or all dihedrals
+template <bool DIH>
 __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t f, int k0, int k1, double* xf, double* gf, const double* tg,
                                                       const unsigned char* flags, double* tr, double* red) {
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (k1 <= k0) return;
+  constexpr int kind = DIH ? kCentralDihedral : kCentralAngle;
+  constexpr bool dihedral = DIH;
+  constexpr int src = DIH ? 2 : 1;                               // input_of(kind): where dL/dtarget of these steps goes
+  float* const gdst = p.gin[src] ? p.gin[src] + f * p.cols[src] : nullptr;
   int4 o0 = __ldg(p.ops + 3 * (k1 - 1)), o1 = __ldg(p.ops + 3 * (k1 - 1) + 1), o2 = __ldg(p.ops + 3 * (k1 - 1) + 2);
-  if (tid == 0) sc_publish_inverse(xf, tg, tr, k1 - 1, o0.x, o0.z, o0.w);
+  if (tid == 0) sc_publish_inverse(xf, tg, tr, k1 - 1, kind, o0.z, o0.w);
   __syncthreads();
   for (int k = k1 - 1; k >= k0; k--) {
     int4 n0 = o0, n1 = o1, n2 = o2;
     if (k > k0) { n0 = __ldg(p.ops + 3 * k - 3); n1 = __ldg(p.ops + 3 * k - 2); n2 = __ldg(p.ops + 3 * k - 1); }
-    const int kind = o0.x;
-    const bool dihedral = kind >= kCentralDihedral;
     const int c0 = o1.w - o1.z, total = c0 + (o2.y - o2.x);
     {
       // every warp leaves its partial sums (zeros when none of its lanes has a moving atom of this step): thread 0 then adds a
@@ -526,10 +543,14 @@ __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t
       double acc[kRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (warp * 32 < total) {
         const Rot rot = sc_load_rot(tr);
-        for (int e = tid; e < total; e += nth) sc_atom_bwd(xf, gf, rot, e < c0 ? o1.z + e : o2.x + (e - c0), dihedral, acc);
+        for (int e = tid; e < total; e += nth) {
+          const int at = e < c0 ? o1.z + e : o2.x + (e - c0);
+          if (DIH) sc_atom_bwd(xf, gf, rot, at, true, acc);
+          else sc_atom_bwd_planar(xf, gf, rot, at, acc);
+        }
 #pragma unroll
         for (int q = 0; q < kRed; q++) {
-          if (q >= 4 && !dihedral) break;
+          if (q >= 3 && !dihedral) break;
 #pragma unroll
           for (int m = 16; m >= 1; m >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], m);
         }
@@ -553,12 +574,10 @@ __device__ __forceinline__ void sc_backbone_steps_bwd(const ScParams& p, int64_t
         sum[q] = v;
       }
       const double g_target = sc_finish_step(xf, gf, kind, o0.y, o0.z, o0.w, o1.x, sum, tg[2 * k], flags[k]);
-      const int src = input_of(kind);
-      float* gdst = p.gin[src];
-      if (gdst) gdst[f * p.cols[src] + o1.y] = (float)g_target;
+      if (gdst) gdst[o1.y] = (float)g_target;
     } else if (tid == 32 && k > k0) {
       // meanwhile another warp prepares the rotation of the next (earlier) step: it only needs the restored coordinates
-      sc_publish_inverse(xf, tg, tr, k - 1, n0.x, n0.z, n0.w);
+      sc_publish_inverse(xf, tg, tr, k - 1, kind, n0.z, n0.w);
     }
     __syncthreads();
     o0 = n0; o1 = n1; o2 = n2;
@@ -619,9 +638,9 @@ __global__ void __launch_bounds__(kScThreads) sidechain_bwd_kernel(const ScParam
     for (int e = tid; e < 3 * p.n_atoms; e += nth) gf[e] = (double)__ldg(gsrc + e);
     __syncthreads();
     sc_side_steps_bwd<true>(p, f, k_cd + p.n_cd, xf, gf, tg, flags);
-    sc_backbone_steps_bwd(p, f, k_cd, k_cd + p.n_cd, xf, gf, tg, flags, tr, red);
+    sc_backbone_steps_bwd<true>(p, f, k_cd, k_cd + p.n_cd, xf, gf, tg, flags, tr, red);
     sc_side_steps_bwd<false>(p, f, p.n_ca, xf, gf, tg, flags);
-    sc_backbone_steps_bwd(p, f, 0, p.n_ca, xf, gf, tg, flags, tr, red);
+    sc_backbone_steps_bwd<false>(p, f, 0, p.n_ca, xf, gf, tg, flags, tr, red);
     // the planar layout: x of backbone atom k = sum of the bonds before it, x of a side-chain atom = x of its CA, y = running sum
     // of its own chain's bonds (layers.py:593-628)
     float* g_sd = p.gin[3];

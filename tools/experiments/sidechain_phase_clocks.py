@@ -27,5 +27,5 @@ L.emk_debug_sc_prof(out, 0)
 v = list(out)
 n = v[4]
 print("backbone steps timed:", n)
-print("thread 0 per step: apply+reduce %.0f, wait at barrier 1 %.0f, finish %.0f, wait at barrier 2 %.0f cycles" % (v[0] / n, v[1] / n, v[2] / n, v[3] / n))
-print("thread 32 per step: publish %.0f cycles;  thread 64: apply+reduce %.0f, wait 1 %.0f" % (v[5] / n, v[6] / n, v[7] / n))
+print("thread 0 per step: apply + reduce %.0f, barrier 1 %.0f, sums %.0f, finish %.0f, store + rest %.0f, barrier 2 %.0f" % tuple(v[q] / n for q in (0, 1, 2, 3, 5, 6)))
+print("thread 32: next inverse rotation %.0f" % (v[7] / n))
