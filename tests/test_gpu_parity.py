@@ -1418,9 +1418,8 @@ def test_sidechain_backmap_golden(em, golden, tag):
 
 
 def test_sidechain_backmap_forward_and_gradient_vs_oracle(em):
-    """A 60-residue chain, 300 frames (more frames than resident CTAs would be 1 776; the grid-stride loop is covered by the
-    large-batch test below): coordinates to 1e-4 nm, all six input gradients to 1e-5 norm-wise against float64 autograd over the
-    oracle's restatement."""
+    """A 60-residue chain with random side chains, six frames (the frame loop of a CTA is covered by the large-batch test below):
+    coordinates to 1e-5 nm, all six input gradients to 1e-5 norm-wise against float64 autograd over the oracle's restatement."""
     from encodermap_b200 import _ops
 
     rng = np.random.default_rng(41)
