@@ -436,3 +436,36 @@ def test_sidechain_plan_refuses_what_the_reference_cannot_build(L):
         assert clone.counts == layer.counts and clone._plans == {} and clone._plan_for(None).n_atoms == 18
     again = BackMapLayerWithSidechains.from_config({"feature_description": {"-1": {"1": 3, "2": 4, "3": 0}}})
     assert again.counts == layer.counts and again.get_config()["feature_description"] == {-1: {1: 3, 2: 4, 3: 0}}
+
+
+def test_sidechain_plan_equals_the_oracle_topology_on_random_descriptions(L):
+    """300 random admissible residue descriptions (either end bare, interior residues with 0..6 side-chain dihedrals): the step
+    table of the library, expanded to masks, equals the oracle's restatement of the reference constructor (itself pinned to the
+    reference's own constructor on four descriptions, tests/test_oracle_golden.py) bit for bit."""
+    from oracle import em_oracle as O
+
+    from encodermap_b200 import _ops
+
+    rng = np.random.default_rng(77)
+    for trial in range(300):
+        n_res = int(rng.integers(2, 40))
+        counts = [int(v) for v in rng.integers(0, 7, size=n_res)]
+        if trial % 2:
+            counts[0], counts[-1] = 0, max(1, counts[-1])
+            if n_res > 2:
+                counts[1] = max(1, counts[1])        # the reference needs a side chain before the first interior bare residue
+        else:
+            counts[0], counts[-1] = max(1, counts[0]), 0
+        topo = O.sidechain_topology(counts)
+        plan = _ops.SidechainPlan(counts)
+        ops = plan.ops()
+        masks = np.ones((plan.n_ops, plan.n_atoms), dtype=bool)
+        for k, o in enumerate(ops):
+            masks[k, o[6]:o[7]] = False
+            masks[k, o[8]:o[9]] = False
+        want = np.vstack([topo["central_angle_mask"], topo["side_angle_mask"], topo["dihedral_mask"]])
+        assert np.array_equal(masks, want), counts
+        n_ang = len(topo["central_angle_mask"]) + len(topo["side_angle_mask"])
+        assert np.array_equal(ops[:n_ang, 1:4], np.vstack([topo["central_angle_triplets"], topo["side_angle_triplets"]])), counts
+        assert np.array_equal(ops[n_ang:, 1:5], topo["dihedral_quadruplets"]), counts
+        assert np.array_equal(_ops.sidechain_pairwise_indices(counts, 1, None, 3), O.sidechain_pairwise_indices(counts, 1, None, 3))
