@@ -1441,6 +1441,29 @@ def test_sidechain_backmap_forward_and_gradient_vs_oracle(em):
         assert relnorm(t.grad.cpu().numpy(), o.grad.numpy()) < GRAD_RTOL, name
 
 
+@pytest.mark.parametrize("counts", [[0, 2, 1, 4, 0, 3], [0, 5, 0, 0, 2, 1, 1], [1, 0, 0, 6, 0]])
+def test_sidechain_backmap_gradient_generic_geometry(em, counts):
+    """Descriptions whose first residue is bare detach every side chain from its CA in the reference's construction (mask rows
+    shifted by one residue, see the oracle test): the side-chain bond angles are then measured on generic, not straight or
+    right-angled, triplets -- the branch of the gradient that goes through acos and |target - measured| with both signs."""
+    from encodermap_b200 import _ops
+
+    rng = np.random.default_rng(sum(counts))
+    plan = _ops.SidechainPlan(counts, torch.device("cuda"))
+    inputs = _sidechain_inputs(rng, counts, 9)
+    inputs[4] = rng.uniform(0.3, 2.9, size=inputs[4].shape).astype(np.float32)      # side angles on both sides of the measured ones
+    ts = [cu(v).requires_grad_(True) for v in inputs]
+    out = _ops.SidechainBackmap.apply(plan, *ts)
+    w = rng.normal(size=tuple(out.shape))
+    (out * cu(w)).sum().backward()
+    oi = [torch.tensor(v.astype(np.float64), requires_grad=True) for v in inputs]
+    want = O.backmap_with_sidechains(counts, oi)
+    (want * torch.from_numpy(w)).sum().backward()
+    assert np.abs(out.detach().cpu().numpy() - want.detach().numpy()).max() < 1e-5
+    for t, o, name in zip(ts, oi, SIDECHAIN_KEYS):
+        assert relnorm(t.grad.cpu().numpy(), o.grad.numpy()) < GRAD_RTOL, name
+
+
 def test_sidechain_backmap_partial_gradients_and_raw_abi(em):
     """Only some inputs need gradients (the model feeds the distances as data): NULL gradient pointers are skipped; the raw-pointer
     entry points give the same numbers as the DLPack ones."""
