@@ -240,3 +240,12 @@ def test_sidechain_oracle_gradient_is_finite_and_matches_differences(golden):
         minus[which][0, col] -= h
         fd = (f(plus) - f(minus)) / (2 * h)
         assert abs(fd - float(inputs[which].grad[0, col])) < 2e-4 * max(1.0, abs(fd)), (which, col)
+
+
+def test_sidechain_reference_float32_error_band(golden):
+    """The reference's layer body evaluated in float32 (as it runs in TensorFlow) against its float64 evaluation: 4e-4 nm at 18
+    atoms, 8e-3 nm at 448 -- every bond angle is measured on a straight triplet, where acos(-1 + 6e-8) = pi - 3.5e-4.  The
+    kernels are held to the float64 evaluation (2e-6 nm in tests/test_gpu_parity.py); this is the band the reference itself is in."""
+    g = golden["sidechains"]
+    band = {tag: np.abs(g[f"{tag}_out_f32"].astype(np.float64) - g[f"{tag}_out"]).max() for tag in SIDECHAIN_TAGS}
+    assert 1e-4 < band["metlysgly"] < 2e-3 and 2e-3 < band["ub_like"] < 5e-2, band

@@ -566,11 +566,13 @@ def main():
 class _TensorArray:
     """tf.TensorArray as the layer uses it: write returns the array, read / stack."""
 
+    work_dtype = np.float64       # the evaluation dtype of the shim that owns this class (TensorFlow: the array's dtype argument)
+
     def __init__(self, dtype=None, size=0, clear_after_read=False):
         self.items = {}
 
     def write(self, i, value):
-        self.items[int(i)] = np.asarray(value, dtype=np.float64 if np.asarray(value).dtype.kind == "f" else None)
+        self.items[int(i)] = np.asarray(value, dtype=self.work_dtype if np.asarray(value).dtype.kind == "f" else None)
         return self
 
     def read(self, i):
@@ -614,6 +616,10 @@ class _TFShimSide(_TFShim):
             idx = np.arange(x.shape[-1])
             out[..., idx, idx] = x
             return _w(out)
+
+    def __init__(self, dtype):
+        super().__init__(dtype)
+        self.TensorArray = type("TensorArray", (_TensorArray,), {"work_dtype": self.dtype.type})
 
     def constant(self, x, shape=None, dtype=None):
         a = np.asarray(x)
@@ -696,6 +702,10 @@ def sidechain_section():
     _extract(REF / "encodermap/models/layers.py", ["_batch_fro", "_rotation_matrices", "_unit_vector"], ns)
     _class_methods(REF / "encodermap/models/layers.py", "BackMapLayerWithSidechains", ("__init__", "call"), ns)
     _class_methods(REF / "encodermap/models/layers.py", "PairwiseDistances", ("__init__",), ns)
+    tf32 = _TFShimSide(np.float32)
+    ns32 = {"tf": tf32, "np": np, "itertools": itertools, "block_diag": block_diag, "Any": None}
+    _extract(REF / "encodermap/models/layers.py", ["_batch_fro", "_rotation_matrices", "_unit_vector"], ns32)
+    _class_methods(REF / "encodermap/models/layers.py", "BackMapLayerWithSidechains", ("__init__", "call"), ns32)
 
     # the numpy twin imports matplotlib, transformations and encodermap.misc.rotate inside its body: stand-ins for the three.
     # transformations.rotation_matrix (C. Gohlke, not installed) = the reference's own restatement _rotmat_jit
@@ -767,6 +777,13 @@ def sidechain_section():
             # cosine into sqrt(2e-16) = 1.4e-8 rad (in float32, as the layer runs in the reference: 3.5e-4 rad)
             assert np.abs(out_layer - out_np).max() < 1e-6, np.abs(out_layer - out_np).max()
             g[f"{tag}_out"] = out_layer
+            # the same layer body evaluated in float32, as the reference runs it: how far its own output is from the float64
+            # evaluation (every bond angle measured on a straight triplet costs acos(-1 + 6e-8) = pi - 3.5e-4)
+            layer32 = _Self()
+            ns32["BackMapLayerWithSidechains_init"](layer32, fd)
+            out32 = np.asarray(ns32["BackMapLayerWithSidechains_call"](layer32, tuple(tf32.convert_to_tensor(v.astype(np.float32)) for v in inputs)))
+            assert out32.dtype == np.float32, out32.dtype
+            g[f"{tag}_out_f32"] = out32
             g[f"{tag}_out_np"] = np.asarray(out_np)
             for k, v in idx.items():
                 g[f"{tag}_np_{k}"] = np.asarray(v)
